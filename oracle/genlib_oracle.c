@@ -1,0 +1,504 @@
+/*
+ * genlib_oracle.c -- TEST INFRASTRUCTURE ONLY.
+ *
+ * A plain-C, CPU restatement of the one GenLib.jl path this repository
+ * accelerates: gen.genealogy -> gen.pro -> gen.phi(ped, probands).  It is the
+ * checker for the CUDA path (tests/, __graft_entry__.smoke(), bench.py's
+ * cpu_baseline / --impl reference leg).  Nothing under genlib.jl_b200/ may
+ * include, link or call it; the product path has no CPU fallback.
+ *
+ * It follows the reference's ALGORITHM (cut vertices, pair-by-pair recursion
+ * with founder_index, Float64 accumulator, Float32 store), not the engine's
+ * level-synchronous formulation, so that agreement between the two is evidence
+ * and not a tautology.  Reference lines (relative to /root/reference):
+ *
+ *   src/create.jl:161-189   CSV parse                     -> parse_csv()
+ *   src/create.jl:196-209   _max_depth!                   -> max_depth()
+ *   src/create.jl:217-227   _ordered_pedigree (stable)    -> build_ped()
+ *   src/create.jl:234-254   _finalize_pedigree (rank)     -> build_ped()
+ *   src/identify.jl:35-39   pro                           -> oracle_pro()
+ *   src/compute.jl:66-95    phi(ind, ind) Karigl          -> pair_phi()
+ *   src/compute.jl:105-158  phi(ind, ind, Psi)            -> cut_phi()
+ *   src/compute.jl:193-207  _previous_generation          -> previous_generation()
+ *   src/compute.jl:236-251  cut vertices                  -> build_cuts()
+ *   src/compute.jl:271-302  step loop, threaded pair loop -> oracle_phi_ranks()
+ *   src/compute.jl:454-459  phiMean                       -> oracle_phi_mean()
+ *
+ * Parity pinning: geneaJi is pinned by the reference's own known-answer test
+ * (test/runtests.jl:47-53, checked in tests/test_oracle.py).  genea140 has no
+ * kinship value in the reference's tests; it is pinned by the survey's
+ * independent NumPy emulation checksum and by an
+ * exact-rational Karigl recursion on sampled pairs -- i.e. "pinned by
+ * cross-restatement", not by the reference itself (Julia is not installable
+ * here).
+ *
+ * Arithmetic contract: every '+' is one IEEE binary64
+ * round-to-nearest addition in the order written, x/2 is exact, the store into
+ * the step matrix is binary64 -> binary32 round-to-nearest-even with gradual
+ * underflow.  Compile WITHOUT -ffast-math.
+ */
+#define _GNU_SOURCE
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include <pthread.h>
+#include <sched.h>
+#include <unistd.h>
+
+#define ORACLE_OK 0
+#define ORACLE_EKEY 1   /* unknown ID: the reference raises KeyError (create.jl:70) */
+#define ORACLE_EIO 2
+#define ORACLE_EORDER 3 /* parent does not precede child */
+#define ORACLE_ENOMEM 4
+
+typedef struct oracle_ped {
+    int n;
+    int64_t *id;      /* by rank (0-based position = rank-1 of create.jl:244) */
+    int32_t *father;  /* 0-based rank of the father, -1 = nothing */
+    int32_t *mother;
+    int32_t *sex;
+    int32_t *nchild;  /* length of .children (create.jl:246-251) */
+    /* ID -> rank hash (open addressing) */
+    int64_t *hkey;
+    int32_t *hval;
+    uint64_t hmask;
+} oracle_ped;
+
+static double now_s(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+/* ---------------------------------------------------------------- hashing */
+static uint64_t mix64(uint64_t x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33;
+    x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33; return x;
+}
+static int hash_build(int n, const int64_t *keys, int64_t **hk, int32_t **hv, uint64_t *mask) {
+    uint64_t cap = 16; while (cap < (uint64_t)n * 2 + 2) cap <<= 1;
+    int64_t *k = malloc(cap * sizeof *k); int32_t *v = malloc(cap * sizeof *v);
+    if (!k || !v) { free(k); free(v); return ORACLE_ENOMEM; }
+    for (uint64_t i = 0; i < cap; i++) v[i] = -1;
+    for (int i = 0; i < n; i++) {
+        uint64_t h = mix64((uint64_t)keys[i]) & (cap - 1);
+        while (v[h] >= 0 && k[h] != keys[i]) h = (h + 1) & (cap - 1);
+        k[h] = keys[i]; v[h] = i;     /* later duplicates overwrite, like Dict setindex! */
+    }
+    *hk = k; *hv = v; *mask = cap - 1; return ORACLE_OK;
+}
+static int hash_get(const int64_t *hk, const int32_t *hv, uint64_t mask, int64_t key) {
+    uint64_t h = mix64((uint64_t)key) & mask;
+    while (hv[h] >= 0) { if (hk[h] == key) return hv[h]; h = (h + 1) & mask; }
+    return -1;
+}
+
+/* ------------------------------------------------ create.jl: the pedigree */
+
+/* create.jl:196-209 -- memoised recursive depth; founders have depth 1. */
+static int max_depth(int i, const int32_t *f, const int32_t *m, int32_t *depth) {
+    if (depth[i] == -1) {
+        int fd = 0, md = 0;
+        if (f[i] >= 0) fd += max_depth(f[i], f, m, depth);
+        if (m[i] >= 0) md += max_depth(m[i], f, m, depth);
+        depth[i] = (fd > md ? fd : md) + 1;
+    }
+    return depth[i];
+}
+
+void oracle_free(oracle_ped *p) {
+    if (!p) return;
+    free(p->id); free(p->father); free(p->mother); free(p->sex); free(p->nchild);
+    free(p->hkey); free(p->hval); free(p);
+}
+
+/* create.jl:131-146 + 217-254: file-order records -> rank-ordered pedigree.
+ * ind/father/mother are IDs, 0 = unknown parent (create.jl:240-241). */
+static oracle_ped *build_ped(int n, const int64_t *ind, const int64_t *fid, const int64_t *mid,
+                             const int32_t *sex, int do_sort, int *status) {
+    *status = ORACLE_OK;
+    int64_t *hk = NULL; int32_t *hv = NULL; uint64_t mask = 0;
+    if (hash_build(n, ind, &hk, &hv, &mask)) { *status = ORACLE_ENOMEM; return NULL; }
+    int32_t *f = malloc((size_t)(n + 1) * sizeof *f), *m = malloc((size_t)(n + 1) * sizeof *m);
+    int32_t *depth = malloc((size_t)(n + 1) * sizeof *depth), *order = malloc((size_t)(n + 1) * sizeof *order);
+    int32_t *pos = malloc((size_t)(n + 1) * sizeof *pos);
+    oracle_ped *p = calloc(1, sizeof *p);
+    for (int i = 0; i < n; i++) {           /* file index of each parent */
+        f[i] = fid[i] == 0 ? -1 : hash_get(hk, hv, mask, fid[i]);
+        m[i] = mid[i] == 0 ? -1 : hash_get(hk, hv, mask, mid[i]);
+        if ((fid[i] != 0 && f[i] < 0) || (mid[i] != 0 && m[i] < 0)) { *status = ORACLE_EKEY; goto fail; }
+        depth[i] = -1;
+    }
+    if (do_sort) {
+        int maxd = 0;
+        for (int i = 0; i < n; i++) { int d = max_depth(i, f, m, depth); if (d > maxd) maxd = d; }
+        /* sortperm(depths) is stable: counting sort keeps file order inside a depth */
+        int32_t *cnt = calloc((size_t)maxd + 2, sizeof *cnt);
+        for (int i = 0; i < n; i++) cnt[depth[i] + 1]++;
+        for (int d = 1; d <= maxd + 1; d++) cnt[d] += cnt[d - 1];
+        for (int i = 0; i < n; i++) order[cnt[depth[i]]++] = i;
+        free(cnt);
+    } else {
+        for (int i = 0; i < n; i++) order[i] = i;
+    }
+    for (int r = 0; r < n; r++) pos[order[r]] = r;
+    p->n = n;
+    p->id = malloc((size_t)(n + 1) * sizeof *p->id);
+    p->father = malloc((size_t)(n + 1) * sizeof *p->father);
+    p->mother = malloc((size_t)(n + 1) * sizeof *p->mother);
+    p->sex = malloc((size_t)(n + 1) * sizeof *p->sex);
+    p->nchild = calloc((size_t)n + 1, sizeof *p->nchild);
+    for (int r = 0; r < n; r++) {           /* create.jl:237-252 */
+        int i = order[r];
+        p->id[r] = ind[i];
+        p->father[r] = f[i] < 0 ? -1 : pos[f[i]];
+        p->mother[r] = m[i] < 0 ? -1 : pos[m[i]];
+        p->sex[r] = sex ? sex[i] : 0;
+        /* pedigree[individual.father] must already exist (KeyError otherwise) */
+        if (p->father[r] >= r || p->mother[r] >= r) { *status = ORACLE_EORDER; goto fail; }
+        if (p->father[r] >= 0) p->nchild[p->father[r]]++;
+        if (p->mother[r] >= 0) p->nchild[p->mother[r]]++;
+    }
+    free(hk); free(hv); hk = NULL; hv = NULL;
+    if (hash_build(n, p->id, &p->hkey, &p->hval, &p->hmask)) { *status = ORACLE_ENOMEM; goto fail; }
+    free(f); free(m); free(depth); free(order); free(pos);
+    return p;
+fail:
+    free(hk); free(hv); free(f); free(m); free(depth); free(order); free(pos);
+    oracle_free(p);
+    return NULL;
+}
+
+oracle_ped *oracle_genealogy_arrays(int n, const int64_t *ind, const int64_t *father,
+                                    const int64_t *mother, const int32_t *sex, int do_sort,
+                                    int *status) {
+    return build_ped(n, ind, father, mother, sex, do_sort, status);
+}
+
+/* create.jl:161-189: skip the first line, then whitespace-separated
+ * "ind father mother sex" per line. */
+oracle_ped *oracle_genealogy_csv(const char *path, int do_sort, int *status) {
+    FILE *fp = fopen(path, "r");
+    if (!fp) { *status = ORACLE_EIO; return NULL; }
+    size_t cap = 1 << 16, n = 0;
+    int64_t *ind = malloc(cap * sizeof *ind), *fa = malloc(cap * sizeof *fa), *mo = malloc(cap * sizeof *mo);
+    int32_t *sx = malloc(cap * sizeof *sx);
+    char *line = NULL; size_t lcap = 0; int first = 1;
+    while (getline(&line, &lcap, fp) > 0) {
+        if (first) { first = 0; continue; }
+        long long a, b, c, d;
+        if (sscanf(line, "%lld %lld %lld %lld", &a, &b, &c, &d) != 4) continue;
+        if (n == cap) {
+            cap *= 2;
+            ind = realloc(ind, cap * sizeof *ind); fa = realloc(fa, cap * sizeof *fa);
+            mo = realloc(mo, cap * sizeof *mo); sx = realloc(sx, cap * sizeof *sx);
+        }
+        ind[n] = a; fa[n] = b; mo[n] = c; sx[n] = (int32_t)d; n++;
+    }
+    free(line); fclose(fp);
+    oracle_ped *p = build_ped((int)n, ind, fa, mo, sx, do_sort, status);
+    free(ind); free(fa); free(mo); free(sx);
+    return p;
+}
+
+int oracle_ped_n(const oracle_ped *p) { return p->n; }
+
+/* Flat view in rank order (what the C ABI of the product takes). */
+void oracle_ped_arrays(const oracle_ped *p, int64_t *ids, int32_t *father, int32_t *mother, int32_t *sex) {
+    for (int r = 0; r < p->n; r++) {
+        if (ids) ids[r] = p->id[r];
+        if (father) father[r] = p->father[r];
+        if (mother) mother[r] = p->mother[r];
+        if (sex) sex[r] = p->sex[r];
+    }
+}
+
+int oracle_rank_of(const oracle_ped *p, int64_t id) { return hash_get(p->hkey, p->hval, p->hmask, id); }
+
+static int cmp_i64(const void *a, const void *b) {
+    int64_t x = *(const int64_t *)a, y = *(const int64_t *)b; return (x > y) - (x < y);
+}
+
+/* identify.jl:35-39 -- IDs without children, sorted ascending.  Returns count. */
+int oracle_pro(const oracle_ped *p, int64_t *out) {
+    int k = 0;
+    for (int r = 0; r < p->n; r++) if (p->nchild[r] == 0) { if (out) out[k] = p->id[r]; k++; }
+    if (out) qsort(out, (size_t)k, sizeof *out, cmp_i64);
+    return k;
+}
+
+/* compute.jl:66-95 -- plain Karigl recursion (exponential; small inputs only). */
+static double pair_phi(const oracle_ped *p, int i, int j) {
+    double value = 0.;
+    if (i > j) {
+        if (p->father[i] >= 0) value += pair_phi(p, p->father[i], j) / 2;
+        if (p->mother[i] >= 0) value += pair_phi(p, p->mother[i], j) / 2;
+    } else if (j > i) {
+        if (p->father[j] >= 0) value += pair_phi(p, p->father[j], i) / 2;
+        if (p->mother[j] >= 0) value += pair_phi(p, p->mother[j], i) / 2;
+    } else {
+        value += 0.5;
+        if (p->father[i] >= 0 && p->mother[i] >= 0) value += pair_phi(p, p->father[i], p->mother[i]) / 2;
+    }
+    return value;
+}
+int oracle_phi_pair(const oracle_ped *p, int64_t id1, int64_t id2, double *out) {
+    int a = oracle_rank_of(p, id1), b = oracle_rank_of(p, id2);
+    if (a < 0 || b < 0) return ORACLE_EKEY;
+    *out = pair_phi(p, a, b);
+    return ORACLE_OK;
+}
+
+/* ------------------------------------------- compute.jl: the square matrix */
+
+typedef struct { int32_t *v; int n, cap; } ivec;
+static void iv_push(ivec *a, int32_t x) {
+    if (a->n == a->cap) { a->cap = a->cap ? a->cap * 2 : 64; a->v = realloc(a->v, (size_t)a->cap * sizeof *a->v); }
+    a->v[a->n++] = x;
+}
+
+/* compute.jl:193-207 -- father then mother per member, unique! keeps the first
+ * occurrence.  `stamp`/`tick` implement unique!. */
+static ivec previous_generation(const int32_t *father, const int32_t *mother, const ivec *next,
+                                int32_t *stamp, int32_t tick) {
+    ivec prev = {0};
+    for (int t = 0; t < next->n; t++) {
+        int x = next->v[t];
+        int f = father[x], m = mother[x];
+        if (f >= 0 && stamp[f] != tick) { stamp[f] = tick; iv_push(&prev, f); }
+        if (m >= 0 && stamp[m] != tick) { stamp[m] = tick; iv_push(&prev, m); }
+    }
+    return prev;
+}
+
+typedef struct {
+    int S;        /* number of levels (length(cut_vertices)) */
+    ivec *cut;    /* cut[k], k = 0..S-1, members are 0-based ranks */
+} cuts_t;
+
+static void cuts_free(cuts_t *c) { for (int k = 0; k < c->S; k++) free(c->cut[k].v); free(c->cut); }
+
+/* compute.jl:236-251.  top_down[k] = union(levels[k], top_down[k-1]) and
+ * bottom_up[k] = union(levels[k], bottom_up[k+1]) are realised with
+ * first/last level marks: x is in top_down[k] iff first[x] <= k, in
+ * bottom_up[k] iff last[x] >= k.  The ORDER of cut[k] is that of
+ * intersect(top_down[k], bottom_up[k]) = top_down[k] filtered, i.e. levels[k]
+ * (deduplicated) followed by the surviving members of top_down[k-1] in their
+ * previous order. */
+static cuts_t build_cuts(int n, const int32_t *father, const int32_t *mother, const ivec *probands) {
+    int32_t *stamp = malloc((size_t)(n + 1) * sizeof *stamp);
+    for (int i = 0; i < n; i++) stamp[i] = -1;
+    /* raw levels, bottom first, then reversed (pushfirst!) */
+    int cap = 16, S = 0; ivec *rev = malloc((size_t)cap * sizeof *rev);
+    ivec cur = {0};
+    for (int t = 0; t < probands->n; t++) iv_push(&cur, probands->v[t]);
+    rev[S++] = cur;
+    for (;;) {
+        ivec prev = previous_generation(father, mother, &rev[S - 1], stamp, S);
+        if (prev.n == 0) { free(prev.v); break; }
+        if (S == cap) { cap *= 2; rev = realloc(rev, (size_t)cap * sizeof *rev); }
+        rev[S++] = prev;
+    }
+    ivec *levels = malloc((size_t)S * sizeof *levels);
+    for (int k = 0; k < S; k++) levels[k] = rev[S - 1 - k];
+    free(rev);
+    int32_t *first = malloc((size_t)(n + 1) * sizeof *first), *last = malloc((size_t)(n + 1) * sizeof *last);
+    for (int i = 0; i < n; i++) { first[i] = -1; last[i] = -1; }
+    for (int k = 0; k < S; k++)
+        for (int t = 0; t < levels[k].n; t++) {
+            int x = levels[k].v[t];
+            if (first[x] < 0) first[x] = k;
+            last[x] = k;
+        }
+    cuts_t c; c.S = S; c.cut = calloc((size_t)S, sizeof *c.cut);
+    ivec top = {0};
+    for (int i = 0; i < n; i++) stamp[i] = -1;
+    for (int k = 0; k < S; k++) {
+        /* top_down[k] = union(levels[k], top_down[k-1]) */
+        ivec nt = {0};
+        for (int t = 0; t < levels[k].n; t++) {
+            int x = levels[k].v[t];
+            if (stamp[x] != k) { stamp[x] = k; iv_push(&nt, x); }
+        }
+        for (int t = 0; t < top.n; t++) {
+            int x = top.v[t];
+            /* members whose last level is behind us can never re-enter a cut:
+             * dropping them here keeps later orders unchanged */
+            if (stamp[x] != k && last[x] >= k) { stamp[x] = k; iv_push(&nt, x); }
+        }
+        free(top.v); top = nt;
+        for (int t = 0; t < top.n; t++) if (last[top.v[t]] >= k) iv_push(&c.cut[k], top.v[t]);
+    }
+    free(top.v);
+    for (int k = 0; k < S; k++) free(levels[k].v);
+    free(levels); free(first); free(last); free(stamp);
+    return c;
+}
+
+typedef struct {
+    const int32_t *father, *mother;
+    const int32_t *founder_index;   /* 0 = not indexed, else 1-based position (never reset) */
+    const float *Psi;
+    int ldpsi;
+} phi_ctx;
+
+/* compute.jl:105-158, branch for branch.  `i`, `j` are 0-based ranks, so the
+ * reference's `rank` comparisons are index comparisons. */
+static double cut_phi(const phi_ctx *c, int i, int j) {
+    double value = 0.;
+    int fi = c->founder_index[i], fj = c->founder_index[j];
+    if (fi != 0 && fj != 0) {
+        value += c->Psi[(size_t)(fi - 1) * c->ldpsi + (fj - 1)];
+    } else if (fi != 0) {
+        if (c->father[j] >= 0) value += cut_phi(c, i, c->father[j]) / 2;
+        if (c->mother[j] >= 0) value += cut_phi(c, i, c->mother[j]) / 2;
+    } else if (fj != 0) {
+        if (c->father[i] >= 0) value += cut_phi(c, j, c->father[i]) / 2;
+        if (c->mother[i] >= 0) value += cut_phi(c, j, c->mother[i]) / 2;
+    } else {
+        if (i > j) {
+            if (c->father[i] >= 0) value += cut_phi(c, c->father[i], j) / 2;
+            if (c->mother[i] >= 0) value += cut_phi(c, c->mother[i], j) / 2;
+        } else if (j > i) {
+            if (c->father[j] >= 0) value += cut_phi(c, c->father[j], i) / 2;
+            if (c->mother[j] >= 0) value += cut_phi(c, c->mother[j], i) / 2;
+        } else {
+            value += 0.5;
+            if (c->father[i] >= 0 && c->mother[i] >= 0)
+                value += cut_phi(c, c->father[i], c->mother[i]) / 2;
+        }
+    }
+    return value;
+}
+
+/* compute.jl:293-299 -- Threads.@threads over i (and j): rows are handed out
+ * dynamically to `nthreads` POSIX threads; writes are disjoint (i <= j guard). */
+typedef struct {
+    const phi_ctx *ctx; const int32_t *mem; int nn; float *phi; int next_row; pthread_mutex_t mu;
+} pair_job;
+static void *pair_worker(void *arg) {
+    pair_job *job = arg;
+    const int chunk = 8;
+    for (;;) {
+        pthread_mutex_lock(&job->mu);
+        int i0 = job->next_row; job->next_row += chunk;
+        pthread_mutex_unlock(&job->mu);
+        if (i0 >= job->nn) break;
+        int i1 = i0 + chunk < job->nn ? i0 + chunk : job->nn;
+        for (int i = i0; i < i1; i++)
+            for (int j = i; j < job->nn; j++) {
+                float v = (float)cut_phi(job->ctx, job->mem[i], job->mem[j]);
+                job->phi[(size_t)i * job->nn + j] = v;
+                job->phi[(size_t)j * job->nn + i] = v;
+            }
+    }
+    return NULL;
+}
+static void pair_loop(const phi_ctx *ctx, const int32_t *mem, int nn, float *phi, int nthreads) {
+    pair_job job = { ctx, mem, nn, phi, 0, PTHREAD_MUTEX_INITIALIZER };
+    if (nthreads > 256) nthreads = 256;
+    if (nthreads <= 1 || nn < 64) { pair_worker(&job); return; }
+    pthread_t th[256];
+    int started = 0;
+    for (int t = 0; t < nthreads - 1; t++) if (pthread_create(&th[started], NULL, pair_worker, &job) == 0) started++;
+    pair_worker(&job);
+    for (int t = 0; t < started; t++) pthread_join(th[t], NULL);
+}
+
+int oracle_num_threads(void);
+
+/*
+ * compute.jl:233-304 on flat rank-indexed arrays.
+ *   out        n_unique^2 floats (row-major; the matrix is symmetric), may be NULL
+ *   n_unique   number of distinct probands (duplicates collapse, compute.jl:251)
+ *   max_steps  <0: all steps; otherwise stop after that many steps (bounded CPU
+ *              baseline); `out` is then not written
+ *   step_info  optional, 6 doubles per step: founders, probands, both (the
+ *              verbose line, compute.jl:257-260), pair evaluations, new members,
+ *              seconds
+ * Returns the number of steps S-1 (>= 0) or a negative error.
+ */
+int oracle_phi_ranks(int n, const int32_t *father, const int32_t *mother, int n_pro,
+                     const int32_t *pro_rank, float *out, int *n_unique, int nthreads,
+                     int max_steps, double *step_info, int step_info_cap) {
+    ivec pro = {0};
+    for (int t = 0; t < n_pro; t++) {
+        if (pro_rank[t] < 0 || pro_rank[t] >= n) { free(pro.v); return -ORACLE_EKEY; }
+        iv_push(&pro, pro_rank[t]);
+    }
+    cuts_t c = build_cuts(n, father, mother, &pro);
+    free(pro.v);
+    int S = c.S;
+    int nu = c.cut[S - 1].n;
+    if (n_unique) *n_unique = nu;
+    int32_t *founder_index = calloc((size_t)n + 1, sizeof *founder_index);
+    int32_t *stamp = malloc((size_t)(n + 1) * sizeof *stamp);
+    for (int i = 0; i < n; i++) stamp[i] = -1;
+    /* compute.jl:271-274 */
+    int n0 = c.cut[0].n;
+    float *Psi = calloc((size_t)n0 * n0 + 1, sizeof *Psi);
+    for (int i = 0; i < n0; i++) Psi[(size_t)i * n0 + i] = 0.5f;
+    int nPsi = n0;
+    if (nthreads <= 0) nthreads = oracle_num_threads();
+    int steps_done = 0;
+    for (int k = 0; k + 1 < S; k++) {                     /* compute.jl:276 */
+        if (max_steps >= 0 && k >= max_steps) break;
+        const ivec *prev = &c.cut[k], *next = &c.cut[k + 1];
+        double t0 = now_s();
+        for (int t = 0; t < prev->n; t++) { founder_index[prev->v[t]] = t + 1; stamp[prev->v[t]] = k; }
+        int both = 0, nn = next->n;
+        for (int t = 0; t < nn; t++) if (stamp[next->v[t]] == k) both++;
+        float *phi = malloc(((size_t)nn * nn + 1) * sizeof *phi);   /* compute.jl:291 */
+        phi_ctx ctx = { father, mother, founder_index, Psi, nPsi };
+        const int32_t *mem = next->v;
+        /* compute.jl:293-299: all pairs i <= j, both triangles stored */
+        pair_loop(&ctx, mem, nn, phi, nthreads);
+        free(Psi); Psi = phi; nPsi = nn;                  /* compute.jl:301 */
+        double t1 = now_s();
+        if (step_info && k < step_info_cap) {
+            double *s = step_info + 6 * (size_t)k;
+            s[0] = prev->n; s[1] = nn; s[2] = both;
+            s[3] = (double)nn * (nn + 1) / 2; s[4] = nn - both; s[5] = t1 - t0;
+        }
+        steps_done++;
+    }
+    if (out && steps_done == S - 1) memcpy(out, Psi, (size_t)nu * nu * sizeof *out);
+    free(Psi); free(founder_index); free(stamp);
+    cuts_free(&c);
+    return S - 1;
+}
+
+/* gen.phi(ped, probandIDs): IDs -> ranks (KeyError on unknown ID, create.jl:70
+ * reached from compute.jl:196), then the core above. */
+int oracle_phi(const oracle_ped *p, int n_pro, const int64_t *proband_ids, float *out,
+               int *n_unique, int nthreads, int max_steps, double *step_info, int step_info_cap) {
+    int32_t *r = malloc((size_t)(n_pro + 1) * sizeof *r);
+    for (int t = 0; t < n_pro; t++) {
+        r[t] = oracle_rank_of(p, proband_ids[t]);
+        if (r[t] < 0) { free(r); return -ORACLE_EKEY; }
+    }
+    int rc = oracle_phi_ranks(p->n, p->father, p->mother, n_pro, r, out, n_unique, nthreads,
+                              max_steps, step_info, step_info_cap);
+    free(r);
+    return rc;
+}
+
+/* compute.jl:454-459 -- Float32 sums in Julia's order are pairwise; we return
+ * the Float64 value of (sum - trace) / (n^2 - n) and let the caller compare
+ * with a tolerance-free check only where the sums are exact (geneaJi). */
+double oracle_phi_mean(const float *phi, int n) {
+    double total = 0., diag = 0.;
+    for (size_t i = 0; i < (size_t)n * n; i++) total += phi[i];
+    for (int i = 0; i < n; i++) diag += phi[(size_t)i * n + i];
+    return (total - diag) / ((double)n * n - n);
+}
+
+/* Threads the baseline uses by default: the cores this process may run on. */
+int oracle_num_threads(void) {
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof set, &set) == 0) { int c = CPU_COUNT(&set); if (c > 0) return c; }
+    long c = sysconf(_SC_NPROCESSORS_ONLN);
+    return c > 0 ? (int)c : 1;
+}
