@@ -1,0 +1,483 @@
+// engine.cu -- device runtime + C ABI of libgenlib_cuda.so (include/genlib_cuda.h).
+//
+// The ABI stands where the reference's Julia method stands:
+//   phi(pedigree, probandIDs; verbose, compute)            src/compute.jl:233-304
+// There is no CPU fallback: without a usable CUDA device every compute entry
+// point returns GENLIB_ECUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/genlib_cuda.h"
+#include "kernels.cuh"
+#include "plan.hpp"
+
+using namespace genlib;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(e_ == cudaErrorMemoryAllocation ? GENLIB_ENOMEM : GENLIB_ECUDA,       \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));                  \
+    } while (0)
+
+double now_ms() {
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool active = false;
+    int enter(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) return fail(GENLIB_ECUDA, "no usable CUDA device (cudaGetDevice failed)");
+        if (dev >= 0 && dev != prev) {
+            if (cudaSetDevice(dev) != cudaSuccess) return fail(GENLIB_ECUDA, "cudaSetDevice failed");
+            active = true;
+        }
+        return GENLIB_OK;
+    }
+    ~DeviceGuard() { if (active) cudaSetDevice(prev); }
+};
+
+template <typename T> struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t count) { n = count; return cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)); }
+    cudaError_t upload(const std::vector<T> &h, cudaStream_t s) {
+        cudaError_t e = alloc(h.size());
+        if (e != cudaSuccess || h.empty()) return e;
+        return cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+    }
+};
+
+}  // namespace
+
+struct genlib_plan {
+    Plan p;
+    double ms_plan = 0;
+};
+
+struct genlib_engine {
+    const genlib_plan *plan = nullptr;
+    int numerics = 0, device = 0;
+    size_t esize = 4;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    void *A = nullptr;
+    double *Rt = nullptr;
+    DevBuf<int32_t> mem_ind, mem_slot, mem_fam, fam_pf, fam_pm, fam_start, mt_min, mt_max, pro_slot;
+    DevBuf<uint8_t> flags;
+    DevBuf<double> acc;
+    std::vector<genlib_layer_info> info;
+    std::vector<cudaEvent_t> events;
+    genlib_stats stats{};
+    bool ran = false;
+    ~genlib_engine() {
+        for (auto e : events) cudaEventDestroy(e);
+        if (A) cudaFree(A);
+        if (Rt) cudaFree(Rt);
+        if (stream) cudaStreamDestroy(stream);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+    }
+};
+
+namespace {
+
+size_t engine_bytes(const Plan &P, int numerics) {
+    const size_t es = numerics == GENLIB_NUMERICS_FP64 ? 8 : 4;
+    size_t b = (size_t)P.capacity * (size_t)P.capacity * es;
+    b += P.rt_elems_max * sizeof(double);
+    b += (P.mem_ind.size() * 3 + P.fam_pf.size() * 2 + P.fam_start.size() + P.mtile_minrank.size() * 2 +
+          P.pro_slot.size()) * sizeof(int32_t);
+    b += P.flags.size();
+    return b;
+}
+
+LayerArgs layer_args(const genlib_engine &E, int t) {
+    const Plan &P = E.plan->p;
+    const Layer &L = P.layers[t];
+    LayerArgs a;
+    a.n_new = L.n_new; a.n_fam = L.n_fam; a.rt_lo = L.rt_lo; a.rt_rows = L.rt_rows; a.nf_pad = L.nf_pad;
+    a.any_carried = L.carried > 0;
+    a.mem_ind = E.mem_ind.p + L.mem_off; a.mem_slot = E.mem_slot.p + L.mem_off; a.mem_fam = E.mem_fam.p + L.mem_off;
+    a.fam_pf = E.fam_pf.p + L.fam_off; a.fam_pm = E.fam_pm.p + L.fam_off;
+    a.fam_start = E.fam_start.p + L.fam_off + t;
+    a.flags = E.flags.p + L.flag_off;
+    a.mt_minrank = E.mt_min.p + L.mtile_off; a.mt_maxrank = E.mt_max.p + L.mtile_off;
+    return a;
+}
+
+template <typename T>
+int launch_layers(genlib_engine &E, bool timed) {
+    const Plan &P = E.plan->p;
+    T *A = static_cast<T *>(E.A);
+    const int64_t ld = P.capacity;
+    const size_t cross_smem = (size_t)kFTile * kSRStride * sizeof(double);
+    const size_t intra_smem = sizeof(IntraSmem<T>);
+    CU(cudaFuncSetAttribute(cross_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cross_smem));
+    CU(cudaFuncSetAttribute(intra_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)intra_smem));
+    int launches = 0;
+    size_t ev = 0;
+    for (int t = 0; t < (int)P.layers.size(); t++) {
+        const Layer &L = P.layers[t];
+        if (L.n_new == 0) continue;
+        LayerArgs a = layer_args(E, t);
+        if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
+        if (L.live_before > 0) {
+            dim3 grid((unsigned)(L.rt_rows / kPTile), (unsigned)((L.n_fam + kFTile - 1) / kFTile));
+            cross_kernel<T><<<grid, kThreads, cross_smem, E.stream>>>(A, ld, E.Rt, a);
+            launches++;
+        }
+        if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
+        {
+            const long long nt = L.n_mtiles;
+            const long long pairs = nt * (nt + 1) / 2;
+            if (pairs > 0x7fffffffLL) return fail(GENLIB_EINVAL, "layer too wide for one intra launch");
+            intra_kernel<T><<<(unsigned)pairs, kThreads, intra_smem, E.stream>>>(A, ld, E.Rt, a);
+            launches++;
+        }
+        if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
+    }
+    CU(cudaGetLastError());
+    E.stats.kernel_launches = launches;
+    return GENLIB_OK;
+}
+
+template <typename T, typename O>
+int fetch_rows(genlib_engine &E, O *out) {
+    const Plan &P = E.plan->p;
+    const int32_t n = P.n_unique;
+    if (n == 0) return GENLIB_OK;
+    // stream row blocks through two staging buffers so the gather of block b+1
+    // overlaps the D2H copy of block b
+    const size_t row_bytes = (size_t)n * sizeof(O);
+    int32_t rows_per = (int32_t)std::max<size_t>(1, std::min<size_t>((size_t)n, ((size_t)64 << 20) / row_bytes));
+    rows_per = std::min(rows_per, 65535);
+    O *stage[2] = {nullptr, nullptr};
+    cudaEvent_t done[2], copied[2];
+    for (int b = 0; b < 2; b++) {
+        CU(cudaMalloc(&stage[b], (size_t)rows_per * row_bytes));
+        CU(cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
+    }
+    int rc = GENLIB_OK;
+    int blk = 0;
+    for (int32_t r0 = 0; r0 < n; r0 += rows_per, blk++) {
+        const int b = blk & 1;
+        const int32_t nr = std::min(rows_per, n - r0);
+        if (blk >= 2 && cudaStreamWaitEvent(E.stream, copied[b], 0) != cudaSuccess) { rc = GENLIB_ECUDA; break; }
+        dim3 grid((unsigned)std::min<int32_t>((n + 255) / 256, 64), (unsigned)nr);
+        gather_kernel<T, O><<<grid, 256, 0, E.stream>>>(static_cast<const T *>(E.A), P.capacity, E.pro_slot.p, n, r0, nr, stage[b]);
+        cudaEventRecord(done[b], E.stream);
+        cudaStreamWaitEvent(E.copy_stream, done[b], 0);
+        if (cudaMemcpyAsync(out + (size_t)r0 * n, stage[b], (size_t)nr * row_bytes, cudaMemcpyDeviceToHost, E.copy_stream) != cudaSuccess) { rc = GENLIB_ECUDA; break; }
+        cudaEventRecord(copied[b], E.copy_stream);
+    }
+    cudaError_t e1 = cudaStreamSynchronize(E.stream), e2 = cudaStreamSynchronize(E.copy_stream);
+    for (int b = 0; b < 2; b++) { cudaFree(stage[b]); cudaEventDestroy(done[b]); cudaEventDestroy(copied[b]); }
+    if (rc != GENLIB_OK || e1 != cudaSuccess || e2 != cudaSuccess)
+        return fail(GENLIB_ECUDA, std::string("proband fetch failed: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    E.stats.d2h_bytes += (int64_t)n * (int64_t)row_bytes;
+    return GENLIB_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------ ABI
+extern "C" {
+
+int genlib_version(void) { return GENLIB_ABI_VERSION; }
+const char *genlib_last_error(void) { return g_err.c_str(); }
+
+int genlib_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { g_err = "cudaGetDeviceCount failed (no driver / no device)"; return -GENLIB_ECUDA; }
+    return n;
+}
+
+int genlib_plan_create(int32_t n, const int32_t *father, const int32_t *mother, int32_t n_pro,
+                       const int32_t *proband, int32_t world, genlib_plan **out) {
+    if (!out) return fail(GENLIB_EINVAL, "genlib_plan_create: out is null");
+    *out = nullptr;
+    std::unique_ptr<genlib_plan> pl(new (std::nothrow) genlib_plan);
+    if (!pl) return fail(GENLIB_ENOMEM, "out of host memory");
+    const double t0 = now_ms();
+    std::string err;
+    int rc;
+    try {
+        rc = build_plan(n, father, mother, n_pro, proband, world, pl->p, err);
+    } catch (const std::bad_alloc &) {
+        return fail(GENLIB_ENOMEM, "out of host memory while planning");
+    }
+    if (rc != GENLIB_OK) return fail(rc, err);
+    pl->ms_plan = now_ms() - t0;
+    *out = pl.release();
+    return GENLIB_OK;
+}
+
+void genlib_plan_destroy(genlib_plan *plan) { delete plan; }
+int32_t genlib_plan_n_unique(const genlib_plan *plan) { return plan ? plan->p.n_unique : -1; }
+int32_t genlib_plan_n_layers(const genlib_plan *plan) { return plan ? (int32_t)plan->p.layers.size() : -1; }
+int64_t genlib_plan_capacity(const genlib_plan *plan) { return plan ? plan->p.capacity : -1; }
+int64_t genlib_plan_row_updates(const genlib_plan *plan) { return plan ? plan->p.row_updates : -1; }
+
+static void fill_info(const Layer &L, genlib_layer_info *o) {
+    std::memset(o, 0, sizeof *o);
+    o->n_new = L.n_new; o->n_fam = L.n_fam; o->live_before = L.live_before; o->carried = L.carried;
+    o->ref_founders = L.ref_founders; o->ref_probands = L.ref_probands; o->ref_both = L.ref_both;
+    o->alg_elems = L.alg_elems;
+}
+
+int genlib_plan_layer_info(const genlib_plan *plan, int32_t layer, genlib_layer_info *out) {
+    if (!plan || !out || layer < 0 || layer >= (int32_t)plan->p.layers.size()) return fail(GENLIB_EINVAL, "bad layer");
+    fill_info(plan->p.layers[layer], out);
+    return GENLIB_OK;
+}
+
+int64_t genlib_plan_device_bytes(const genlib_plan *plan, int numerics, int32_t rank) {
+    (void)rank;
+    return plan ? (int64_t)engine_bytes(plan->p, numerics) : -1;
+}
+
+int genlib_plan_layer_arrays(const genlib_plan *plan, int32_t layer, int32_t *member_ind,
+                             int32_t *member_slot, int32_t *member_fam, int32_t *fam_father_slot,
+                             int32_t *fam_mother_slot, int32_t *member_owner) {
+    if (!plan || layer < 0 || layer >= (int32_t)plan->p.layers.size()) return fail(GENLIB_EINVAL, "bad layer");
+    const Plan &P = plan->p;
+    const Layer &L = P.layers[layer];
+    for (int32_t q = 0; q < L.n_new; q++) {
+        if (member_ind) member_ind[q] = P.mem_ind[L.mem_off + q];
+        if (member_slot) member_slot[q] = P.mem_slot[L.mem_off + q];
+        if (member_fam) member_fam[q] = P.mem_fam[L.mem_off + q];
+        if (member_owner) member_owner[q] = 0;
+    }
+    for (int32_t f = 0; f < L.n_fam; f++) {
+        if (fam_father_slot) fam_father_slot[f] = P.fam_pf[L.fam_off + f];
+        if (fam_mother_slot) fam_mother_slot[f] = P.fam_pm[L.fam_off + f];
+    }
+    return GENLIB_OK;
+}
+
+int genlib_plan_layer_flags(const genlib_plan *plan, int32_t layer, uint8_t *live_flags) {
+    if (!plan || !live_flags || layer < 0 || layer >= (int32_t)plan->p.layers.size()) return fail(GENLIB_EINVAL, "bad layer");
+    const Plan &P = plan->p;
+    const Layer &L = P.layers[layer];
+    std::memset(live_flags, 0, (size_t)P.capacity);
+    for (int32_t r = 0; r < L.rt_rows; r++) live_flags[L.rt_lo + r] = P.flags[L.flag_off + r];
+    return GENLIB_OK;
+}
+
+int genlib_plan_proband_slots(const genlib_plan *plan, int32_t *slots) {
+    if (!plan || !slots) return fail(GENLIB_EINVAL, "null argument");
+    std::copy(plan->p.pro_slot.begin(), plan->p.pro_slot.end(), slots);
+    return GENLIB_OK;
+}
+
+int genlib_engine_create(const genlib_plan *plan, int numerics, int device, genlib_engine **out) {
+    if (!plan || !out) return fail(GENLIB_EINVAL, "genlib_engine_create: null argument");
+    *out = nullptr;
+    if (numerics != GENLIB_NUMERICS_REFERENCE && numerics != GENLIB_NUMERICS_FP64) return fail(GENLIB_EINVAL, "unknown numerics mode");
+    if (plan->p.world != 1) return fail(GENLIB_EINVAL, "plan was built for several ranks; use the distributed engine");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(GENLIB_ECUDA, "no CUDA device: libgenlib_cuda has no CPU fallback");
+    DeviceGuard guard;
+    if (int rc = guard.enter(device)) return rc;
+    std::unique_ptr<genlib_engine> E(new (std::nothrow) genlib_engine);
+    if (!E) return fail(GENLIB_ENOMEM, "out of host memory");
+    const Plan &P = plan->p;
+    E->plan = plan; E->numerics = numerics;
+    E->esize = numerics == GENLIB_NUMERICS_FP64 ? 8 : 4;
+    CU(cudaGetDevice(&E->device));
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    const size_t need = engine_bytes(P, numerics);
+    if (need + ((size_t)256 << 20) > free_b) {
+        char msg[256];
+        std::snprintf(msg, sizeof msg, "frontier needs %.2f GB on the device, %.2f GB free (capacity %lld slots): shard over more GPUs",
+                      need / 1e9, free_b / 1e9, (long long)P.capacity);
+        return fail(GENLIB_ENOMEM, msg);
+    }
+    const double t0 = now_ms();
+    CU(cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&E->copy_stream, cudaStreamNonBlocking));
+    CU(cudaMalloc(&E->A, std::max<size_t>((size_t)P.capacity * (size_t)P.capacity * E->esize, 16)));
+    CU(cudaMalloc(&E->Rt, std::max<size_t>(P.rt_elems_max * sizeof(double), 16)));
+    CU(E->mem_ind.upload(P.mem_ind, E->stream));
+    CU(E->mem_slot.upload(P.mem_slot, E->stream));
+    CU(E->mem_fam.upload(P.mem_fam, E->stream));
+    CU(E->fam_pf.upload(P.fam_pf, E->stream));
+    CU(E->fam_pm.upload(P.fam_pm, E->stream));
+    CU(E->fam_start.upload(P.fam_start, E->stream));
+    CU(E->mt_min.upload(P.mtile_minrank, E->stream));
+    CU(E->mt_max.upload(P.mtile_maxrank, E->stream));
+    CU(E->pro_slot.upload(P.pro_slot, E->stream));
+    CU(E->flags.upload(P.flags, E->stream));
+    CU(E->acc.alloc(2));
+    CU(cudaStreamSynchronize(E->stream));
+    E->info.resize(P.layers.size());
+    for (size_t t = 0; t < P.layers.size(); t++) fill_info(P.layers[t], &E->info[t]);
+    E->events.resize(P.layers.size() * 3 + 2);
+    for (auto &e : E->events) CU(cudaEventCreate(&e));
+    genlib_stats &s = E->stats;
+    s.n_unique = P.n_unique; s.n_layers = (int32_t)P.layers.size(); s.row_updates = P.row_updates;
+    s.capacity = P.capacity; s.device_bytes = (int64_t)need; s.alg_bytes = P.alg_elems * (double)E->esize;
+    s.ms_plan = plan->ms_plan; s.ms_upload = now_ms() - t0;
+    s.h2d_bytes = (int64_t)((P.mem_ind.size() * 3 + P.fam_pf.size() * 2 + P.fam_start.size() +
+                             P.mtile_minrank.size() * 2 + P.pro_slot.size()) * sizeof(int32_t) + P.flags.size());
+    *out = E.release();
+    return GENLIB_OK;
+}
+
+void genlib_engine_destroy(genlib_engine *eng) {
+    if (!eng) return;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(eng->device);
+    delete eng;
+    if (prev >= 0) cudaSetDevice(prev);
+}
+
+int genlib_engine_run(genlib_engine *eng, int time_layers) {
+    if (!eng) return fail(GENLIB_EINVAL, "null engine");
+    DeviceGuard guard;
+    if (int rc = guard.enter(eng->device)) return rc;
+    genlib_engine &E = *eng;
+    const size_t nev = E.events.size();
+    CU(cudaEventRecord(E.events[nev - 2], E.stream));
+    int rc = E.numerics == GENLIB_NUMERICS_FP64 ? launch_layers<double>(E, time_layers != 0)
+                                                : launch_layers<float>(E, time_layers != 0);
+    if (rc != GENLIB_OK) return rc;
+    CU(cudaEventRecord(E.events[nev - 1], E.stream));
+    CU(cudaStreamSynchronize(E.stream));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, E.events[nev - 2], E.events[nev - 1]));
+    E.stats.ms_kernels = ms;
+    if (time_layers) {
+        size_t ev = 0;
+        for (size_t t = 0; t < E.info.size(); t++) {
+            if (E.info[t].n_new == 0) continue;
+            float a = 0, b = 0;
+            CU(cudaEventElapsedTime(&a, E.events[ev], E.events[ev + 1]));
+            CU(cudaEventElapsedTime(&b, E.events[ev + 1], E.events[ev + 2]));
+            ev += 3;
+            E.info[t].ms_cross = a; E.info[t].ms_intra = b;
+        }
+    }
+    E.ran = true;
+    return GENLIB_OK;
+}
+
+int genlib_engine_layer_info(const genlib_engine *eng, int32_t layer, genlib_layer_info *out) {
+    if (!eng || !out || layer < 0 || layer >= (int32_t)eng->info.size()) return fail(GENLIB_EINVAL, "bad layer");
+    *out = eng->info[layer];
+    return GENLIB_OK;
+}
+
+int genlib_engine_stats(const genlib_engine *eng, genlib_stats *out) {
+    if (!eng || !out) return fail(GENLIB_EINVAL, "null argument");
+    *out = eng->stats;
+    return GENLIB_OK;
+}
+
+int genlib_engine_fetch(genlib_engine *eng, void *out, int out_dtype) {
+    if (!eng || (!out && eng->plan->p.n_unique > 0)) return fail(GENLIB_EINVAL, "null argument");
+    if (!eng->ran) return fail(GENLIB_EINVAL, "genlib_engine_fetch before genlib_engine_run");
+    if (out_dtype != GENLIB_F32 && out_dtype != GENLIB_F64) return fail(GENLIB_EINVAL, "unknown out_dtype");
+    DeviceGuard guard;
+    if (int rc = guard.enter(eng->device)) return rc;
+    const double t0 = now_ms();
+    int rc;
+    if (eng->numerics == GENLIB_NUMERICS_FP64)
+        rc = out_dtype == GENLIB_F64 ? fetch_rows<double, double>(*eng, (double *)out) : fetch_rows<double, float>(*eng, (float *)out);
+    else
+        rc = out_dtype == GENLIB_F64 ? fetch_rows<float, double>(*eng, (double *)out) : fetch_rows<float, float>(*eng, (float *)out);
+    eng->stats.ms_fetch = now_ms() - t0;
+    return rc;
+}
+
+int genlib_engine_phi_mean(genlib_engine *eng, double *out) {
+    if (!eng || !out) return fail(GENLIB_EINVAL, "null argument");
+    if (!eng->ran) return fail(GENLIB_EINVAL, "genlib_engine_phi_mean before genlib_engine_run");
+    DeviceGuard guard;
+    if (int rc = guard.enter(eng->device)) return rc;
+    const Plan &P = eng->plan->p;
+    const int32_t n = P.n_unique;
+    if (n < 2) { *out = 0.0; return GENLIB_OK; }
+    CU(cudaMemsetAsync(eng->acc.p, 0, 2 * sizeof(double), eng->stream));
+    const unsigned grid = (unsigned)std::min<int32_t>(n, 148 * 8);
+    if (eng->numerics == GENLIB_NUMERICS_FP64)
+        mean_kernel<double><<<grid, kThreads, 0, eng->stream>>>((const double *)eng->A, P.capacity, eng->pro_slot.p, n, eng->acc.p);
+    else
+        mean_kernel<float><<<grid, kThreads, 0, eng->stream>>>((const float *)eng->A, P.capacity, eng->pro_slot.p, n, eng->acc.p);
+    double h[2] = {0, 0};
+    CU(cudaMemcpyAsync(h, eng->acc.p, sizeof h, cudaMemcpyDeviceToHost, eng->stream));
+    CU(cudaStreamSynchronize(eng->stream));
+    *out = (h[0] - h[1]) / ((double)n * n - n);
+    return GENLIB_OK;
+}
+
+int genlib_engine_read_block(genlib_engine *eng, int32_t n_slots, const int32_t *slots, double *out) {
+    if (!eng || !slots || !out || n_slots < 0) return fail(GENLIB_EINVAL, "null argument");
+    DeviceGuard guard;
+    if (int rc = guard.enter(eng->device)) return rc;
+    if (n_slots == 0) return GENLIB_OK;
+    const Plan &P = eng->plan->p;
+    for (int32_t i = 0; i < n_slots; i++)
+        if (slots[i] < 0 || slots[i] >= P.capacity) return fail(GENLIB_EINVAL, "slot out of range");
+    int32_t *dslots = nullptr;
+    double *dout = nullptr;
+    CU(cudaMalloc(&dslots, (size_t)n_slots * sizeof(int32_t)));
+    CU(cudaMalloc(&dout, (size_t)n_slots * n_slots * sizeof(double)));
+    CU(cudaMemcpyAsync(dslots, slots, (size_t)n_slots * sizeof(int32_t), cudaMemcpyHostToDevice, eng->stream));
+    for (int32_t r0 = 0; r0 < n_slots; r0 += 65535) {
+        const int32_t nr = std::min(65535, n_slots - r0);
+        dim3 grid((unsigned)std::min<int32_t>((n_slots + 255) / 256, 64), (unsigned)nr);
+        if (eng->numerics == GENLIB_NUMERICS_FP64)
+            gather_kernel<double, double><<<grid, 256, 0, eng->stream>>>((const double *)eng->A, P.capacity, dslots, n_slots, r0, nr, dout + (size_t)r0 * n_slots);
+        else
+            gather_kernel<float, double><<<grid, 256, 0, eng->stream>>>((const float *)eng->A, P.capacity, dslots, n_slots, r0, nr, dout + (size_t)r0 * n_slots);
+    }
+    CU(cudaMemcpyAsync(out, dout, (size_t)n_slots * n_slots * sizeof(double), cudaMemcpyDeviceToHost, eng->stream));
+    CU(cudaStreamSynchronize(eng->stream));
+    cudaFree(dslots); cudaFree(dout);
+    return GENLIB_OK;
+}
+
+int genlib_phi(int32_t n, const int32_t *father, const int32_t *mother, int32_t n_pro,
+               const int32_t *proband, void *out, int out_dtype, int numerics, int device,
+               genlib_stats *stats) {
+    genlib_plan *plan = nullptr;
+    int rc = genlib_plan_create(n, father, mother, n_pro, proband, 1, &plan);
+    if (rc != GENLIB_OK) return rc;
+    std::unique_ptr<genlib_plan> pguard(plan);
+    if (plan->p.n_unique == 0) {
+        if (stats) { std::memset(stats, 0, sizeof *stats); stats->ms_plan = plan->ms_plan; }
+        return GENLIB_OK;                       // 0 x 0 matrix, like the reference
+    }
+    if (!out) return fail(GENLIB_EINVAL, "genlib_phi: out is null");
+    genlib_engine *eng = nullptr;
+    rc = genlib_engine_create(plan, numerics, device, &eng);
+    if (rc != GENLIB_OK) return rc;
+    rc = genlib_engine_run(eng, 0);
+    if (rc == GENLIB_OK) rc = genlib_engine_fetch(eng, out, out_dtype);
+    if (rc == GENLIB_OK && stats) *stats = eng->stats;
+    genlib_engine_destroy(eng);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,247 @@
+// plan.cpp -- see plan.hpp.  Pure host C++17.
+#include "plan.hpp"
+
+#include <algorithm>
+#include <climits>
+
+#include "../../include/genlib_cuda.h"
+
+namespace genlib {
+
+namespace {
+
+inline int32_t round_up(int64_t x, int64_t m) { return (int32_t)(((x + m - 1) / m) * m); }
+
+// (father, mother) -> family id of the current layer.  Open addressing with a
+// generation stamp so the table is never cleared.
+struct FamilyTable {
+    std::vector<uint64_t> key;
+    std::vector<int32_t> val, stamp;
+    uint64_t mask = 0;
+    void reserve(size_t n) {
+        size_t cap = 64;
+        while (cap < 2 * n + 2) cap <<= 1;
+        if (cap > key.size()) { key.assign(cap, 0); val.assign(cap, 0); stamp.assign(cap, -1); }
+        mask = key.size() - 1;
+    }
+    static uint64_t mix(uint64_t x) {
+        x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33;
+        x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33; return x;
+    }
+    // returns the slot index of `k` (existing or fresh); *found tells which
+    size_t find(uint64_t k, int32_t tick, bool *found) {
+        size_t h = mix(k) & mask;
+        while (stamp[h] == tick && key[h] != k) h = (h + 1) & mask;
+        *found = stamp[h] == tick;
+        if (!*found) { stamp[h] = tick; key[h] = k; }
+        return h;
+    }
+};
+
+}  // namespace
+
+int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t n_pro,
+               const int32_t *proband, int32_t world, Plan &P, std::string &err) {
+    P = Plan();
+    if (n < 0 || n_pro < 0 || world < 1 || (n > 0 && (!father || !mother)) || (n_pro > 0 && !proband)) {
+        err = "genlib_plan_create: null pointer or negative size";
+        return GENLIB_EINVAL;
+    }
+    P.n = n; P.world = world;
+    for (int32_t i = 0; i < n; i++) {
+        int32_t f = father[i], m = mother[i];
+        if (f < -1 || f >= n || m < -1 || m >= n) {
+            err = "KeyError: parent index out of range at rank " + std::to_string(i);
+            return GENLIB_EKEY;
+        }
+        if (f >= i || m >= i) {
+            err = "parent does not precede child at rank " + std::to_string(i);
+            return GENLIB_EORDER;
+        }
+    }
+    // probands: first occurrence wins (intersect/union keep first-argument order, compute.jl:247,251)
+    std::vector<uint8_t> is_pro((size_t)n + 1, 0);
+    for (int32_t t = 0; t < n_pro; t++) {
+        int32_t x = proband[t];
+        if (x < 0 || x >= n) {
+            err = "KeyError: proband index " + std::to_string(x) + " not in pedigree";
+            return GENLIB_EKEY;
+        }
+        if (!is_pro[x]) { is_pro[x] = 1; P.pro_ind.push_back(x); }
+    }
+    P.n_unique = (int32_t)P.pro_ind.size();
+    if (P.n_unique == 0) return GENLIB_OK;
+
+    // height above the probands = longest downward path to one (compute.jl:236-241
+    // builds the same levels by repeated _previous_generation)
+    std::vector<int32_t> h((size_t)n, -1);
+    for (int32_t x : P.pro_ind) h[x] = 0;
+    int32_t hmax = 0;
+    for (int32_t x = n - 1; x >= 0; x--) {
+        if (h[x] < 0) continue;
+        hmax = std::max(hmax, h[x]);
+        int32_t f = father[x], m = mother[x];
+        if (f >= 0) h[f] = std::max(h[f], h[x] + 1);
+        if (m >= 0) h[m] = std::max(h[m], h[x] + 1);
+    }
+    const int32_t S = hmax + 1;
+    // layer = first raw level; last_read = layer of the last child born (engine eviction);
+    // ref_last = last raw level (the reference keeps the individual in its cuts until then)
+    std::vector<int32_t> layer((size_t)n, -1), last_read((size_t)n, -1), ref_last((size_t)n, -1);
+    std::vector<int32_t> count((size_t)S + 1, 0);
+    for (int32_t x = 0; x < n; x++)
+        if (h[x] >= 0) { layer[x] = S - 1 - h[x]; count[layer[x]]++; if (is_pro[x]) ref_last[x] = S - 1; }
+    for (int32_t x = n - 1; x >= 0; x--) {
+        if (h[x] < 0) continue;
+        for (int32_t p : {father[x], mother[x]}) {
+            if (p < 0) continue;
+            last_read[p] = std::max(last_read[p], layer[x]);
+            ref_last[p] = std::max(ref_last[p], ref_last[x] - 1);
+        }
+    }
+    // members of each layer in rank order
+    std::vector<size_t> lstart((size_t)S + 1, 0);
+    for (int32_t t = 0; t < S; t++) lstart[t + 1] = lstart[t] + count[t];
+    std::vector<int32_t> by_layer(lstart[S]);
+    {
+        std::vector<size_t> pos(lstart.begin(), lstart.end() - 1);
+        for (int32_t x = 0; x < n; x++) if (h[x] >= 0) by_layer[pos[layer[x]]++] = x;
+    }
+    // the reference's cut sizes (verbose lines, compute.jl:254-261)
+    std::vector<int64_t> d_cut((size_t)S + 2, 0), d_both((size_t)S + 2, 0);
+    for (int32_t x = 0; x < n; x++) {
+        if (h[x] < 0) continue;
+        d_cut[layer[x]]++; d_cut[ref_last[x] + 1]--;             // in cut[k] for layer <= k <= ref_last
+        if (ref_last[x] > layer[x]) { d_both[layer[x]]++; d_both[ref_last[x]]--; }  // in cut[k] and cut[k+1]
+    }
+    std::vector<int32_t> cut_size((size_t)S, 0), both_size((size_t)S, 0);
+    {
+        int64_t a = 0, b = 0;
+        for (int32_t k = 0; k < S; k++) { a += d_cut[k]; b += d_both[k]; cut_size[k] = (int32_t)a; both_size[k] = (int32_t)b; }
+    }
+
+    P.layers.resize(S);
+    P.mem_ind.reserve(lstart[S]); P.mem_slot.reserve(lstart[S]); P.mem_fam.reserve(lstart[S]);
+    std::vector<int32_t> slot_of((size_t)n, -1);
+    std::vector<int32_t> live, next_live;        // individuals live before the current step
+    std::vector<int32_t> freelist;               // ascending free slots below next_fresh
+    int32_t next_fresh = 0;
+    FamilyTable table;
+    std::vector<int32_t> fam_of, fam_count, fam_first, order;
+    std::vector<int32_t> freed;
+
+    for (int32_t t = 0; t < S; t++) {
+        Layer &L = P.layers[t];
+        const int32_t *X = by_layer.data() + lstart[t];
+        const int32_t nn = count[t];
+        L.n_new = nn;
+        L.live_before = (int32_t)live.size();
+        L.ref_founders = t > 0 ? cut_size[t - 1] : 0;
+        L.ref_probands = cut_size[t];
+        L.ref_both = t > 0 ? both_size[t - 1] : 0;
+        L.mem_off = P.mem_ind.size();
+        L.fam_off = P.fam_pf.size();
+        L.flag_off = P.flags.size();
+        L.mtile_off = P.mtile_minrank.size();
+
+        // ---- live range and flags (state BEFORE the step) ----
+        freed.clear();
+        next_live.clear();
+        if (!live.empty()) {
+            int32_t lo = INT_MAX, hi = -1;
+            for (int32_t x : live) { lo = std::min(lo, slot_of[x]); hi = std::max(hi, slot_of[x]); }
+            L.rt_lo = (lo / kPTile) * kPTile;
+            L.rt_rows = round_up(hi + 1, kPTile) - L.rt_lo;
+            P.flags.resize(L.flag_off + (size_t)L.rt_rows, 0);
+            uint8_t *fl = P.flags.data() + L.flag_off;
+            for (int32_t x : live) {
+                // read for the last time in step last_read[x]; probands stay to the end
+                bool stays = is_pro[x] || last_read[x] > t;
+                fl[slot_of[x] - L.rt_lo] = (uint8_t)(kFlagLive | (stays ? kFlagCarried : 0));
+                if (stays) { next_live.push_back(x); L.carried++; }
+                else freed.push_back(slot_of[x]);
+            }
+        }
+
+        // ---- families: same (father, mother) => same cross row (compute.jl:111-126 gives
+        //      full siblings identical kinship to everybody else) ----
+        table.reserve((size_t)nn);
+        fam_of.assign((size_t)nn, 0);
+        fam_count.clear(); fam_first.clear();
+        for (int32_t q = 0; q < nn; q++) {
+            int32_t x = X[q];
+            uint64_t key = ((uint64_t)(uint32_t)(father[x] + 1) << 32) | (uint32_t)(mother[x] + 1);
+            bool found;
+            size_t hsl = table.find(key, t, &found);
+            if (found && fam_count[table.val[hsl]] < kMaxFamily) {
+                fam_of[q] = table.val[hsl];
+            } else {
+                fam_of[q] = (int32_t)fam_count.size();
+                table.val[hsl] = fam_of[q];
+                fam_count.push_back(0);
+                fam_first.push_back(q);
+            }
+            fam_count[fam_of[q]]++;
+        }
+        const int32_t nf = (int32_t)fam_count.size();
+        L.n_fam = nf;
+        L.nf_pad = round_up(std::max(nf, 1), 32);
+        // family-major order (families by first member's rank, members by rank)
+        size_t fs0 = P.fam_start.size();
+        P.fam_start.resize(fs0 + (size_t)nf + 1);
+        int32_t *fstart = P.fam_start.data() + fs0;
+        fstart[0] = 0;
+        for (int32_t f = 0; f < nf; f++) fstart[f + 1] = fstart[f] + fam_count[f];
+        order.assign((size_t)nn, 0);
+        {
+            std::vector<int32_t> pos(fstart, fstart + nf);
+            for (int32_t q = 0; q < nn; q++) order[pos[fam_of[q]]++] = q;
+        }
+        // ---- slots: lowest free first, then fresh ones ----
+        size_t take = std::min((size_t)nn, freelist.size());
+        for (int32_t q = 0; q < nn; q++) {
+            int32_t x = X[order[q]];
+            int32_t s = (size_t)q < take ? freelist[q] : next_fresh++;
+            slot_of[x] = s;
+            P.mem_ind.push_back(x);
+            P.mem_slot.push_back(s);
+            P.mem_fam.push_back(fam_of[order[q]]);
+        }
+        freelist.erase(freelist.begin(), freelist.begin() + (ptrdiff_t)take);
+        for (int32_t f = 0; f < nf; f++) {
+            int32_t x = X[fam_first[f]];
+            P.fam_pf.push_back(father[x] >= 0 ? slot_of[father[x]] : -1);
+            P.fam_pm.push_back(mother[x] >= 0 ? slot_of[mother[x]] : -1);
+        }
+        // per member tile rank range (lets the intra kernel skip one orientation)
+        L.n_mtiles = (nn + kMTile - 1) / kMTile;
+        for (int32_t mt = 0; mt < L.n_mtiles; mt++) {
+            int32_t lo = INT_MAX, hi = -1;
+            for (int32_t q = mt * kMTile; q < std::min(nn, (mt + 1) * kMTile); q++) {
+                int32_t x = P.mem_ind[L.mem_off + q];
+                lo = std::min(lo, x); hi = std::max(hi, x);
+            }
+            P.mtile_minrank.push_back(lo); P.mtile_maxrank.push_back(hi);
+        }
+        L.alg_elems = 4.0 * nn * (double)L.live_before + 3.0 * (double)nn * nn;
+        P.alg_elems += L.alg_elems;
+        P.row_updates += nn;
+        P.rt_elems_max = std::max(P.rt_elems_max, (size_t)L.rt_rows * (size_t)L.nf_pad);
+
+        // ---- after the step: evicted slots become reusable from the next layer on ----
+        if (!freed.empty()) {
+            std::sort(freed.begin(), freed.end());
+            std::vector<int32_t> merged(freelist.size() + freed.size());
+            std::merge(freelist.begin(), freelist.end(), freed.begin(), freed.end(), merged.begin());
+            freelist.swap(merged);
+        }
+        for (int32_t q = 0; q < nn; q++) next_live.push_back(X[q]);
+        live.swap(next_live);
+    }
+    P.capacity = round_up(std::max(next_fresh, 1), kPTile);
+    P.pro_slot.resize(P.pro_ind.size());
+    for (size_t u = 0; u < P.pro_ind.size(); u++) P.pro_slot[u] = slot_of[P.pro_ind[u]];
+    return GENLIB_OK;
+}
+
+}  // namespace genlib

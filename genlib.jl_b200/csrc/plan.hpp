@@ -1,0 +1,62 @@
+// plan.hpp -- host-side schedule of the level-synchronous kinship sweep.
+//
+// Replaces, on flat arrays, what gen.phi does serially before and inside its
+// step loop (reference, relative to /root/reference):
+//   src/compute.jl:193-207,236-241  raw levels by upward BFS from the probands
+//   src/compute.jl:243-251          cut vertices (who is live in which step)
+//   src/compute.jl:165-186          _index_pedigree
+//   src/compute.jl:287-289          founder_index (here: a slot in the frontier matrix)
+// plus the Kirkpatrick-2019 eviction rule the reference states in sparse_phi
+// (src/compute.jl:400-430): a row is dropped once its last child is born.
+//
+// No CUDA in this file: the plan is testable without a GPU.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace genlib {
+
+constexpr int kPTile = 128;      // frontier columns per cross-kernel tile (and slot-range alignment)
+constexpr int kFTile = 32;       // families per cross-kernel tile
+constexpr int kMTile = 64;       // members per intra-kernel tile
+constexpr int kMaxFamily = 32;   // sibships larger than this are split (bounds per-tile work)
+
+constexpr uint8_t kFlagLive = 1;     // slot holds an individual that is live before the step
+constexpr uint8_t kFlagCarried = 2;  // ... and stays live after it
+
+struct Layer {
+    int32_t n_new = 0, n_fam = 0;
+    int32_t live_before = 0, carried = 0;
+    int32_t ref_founders = 0, ref_probands = 0, ref_both = 0;
+    int32_t rt_lo = 0, rt_rows = 0;   // live slots lie in [rt_lo, rt_lo + rt_rows), both multiples of kPTile
+    int32_t nf_pad = 0;               // row stride of the transposed cross block (families, multiple of 32)
+    int32_t n_mtiles = 0;
+    size_t mem_off = 0;               // into mem_* arrays
+    size_t fam_off = 0;               // into fam_pf / fam_pm; fam_start uses fam_off + layer index
+    size_t flag_off = 0;              // into flags
+    size_t mtile_off = 0;             // into mtile_minrank / mtile_maxrank
+    double alg_elems = 0;             // 4 n L + 3 n^2
+};
+
+struct Plan {
+    int32_t n = 0, n_unique = 0, world = 1;
+    int64_t capacity = 0;             // W, multiple of kPTile; also the leading dimension
+    int64_t row_updates = 0;
+    double alg_elems = 0;
+    size_t rt_elems_max = 0;          // max over layers of rt_rows * nf_pad
+    std::vector<Layer> layers;
+    std::vector<int32_t> pro_ind, pro_slot;
+    // concatenated per-layer arrays
+    std::vector<int32_t> mem_ind, mem_slot, mem_fam;   // family-major order inside a layer
+    std::vector<int32_t> fam_pf, fam_pm, fam_start;    // parents as slots (-1 = none)
+    std::vector<uint8_t> flags;
+    std::vector<int32_t> mtile_minrank, mtile_maxrank;
+};
+
+// Returns 0 or a GENLIB_E* status; `err` receives a message.
+int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t n_pro,
+               const int32_t *proband, int32_t world, Plan &plan, std::string &err);
+
+}  // namespace genlib

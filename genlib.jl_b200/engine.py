@@ -1,0 +1,185 @@
+"""Plan / Engine handles over the C ABI and the `gen.phi` front end.
+
+`phi` keeps the reference's signature and behaviour (src/compute.jl:233-304):
+    phi(pedigree, probandIDs = pro(pedigree); verbose = false, compute = true)
+returns a symmetric Float32 matrix in probandIDs order (duplicates collapsed),
+`None` when compute is false, raises KeyError for an unknown ID.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import LayerInfo, Stats, check, lib, ptr
+from .pedigree import Pedigree, pro
+
+
+class Plan:
+    """Host schedule (levels, Kirkpatrick frontier, slots). Needs no GPU."""
+
+    def __init__(self, father, mother, proband_ranks, world: int = 1):
+        self.father = np.ascontiguousarray(father, np.int32)
+        self.mother = np.ascontiguousarray(mother, np.int32)
+        self.probands = np.ascontiguousarray(proband_ranks, np.int32)
+        if len(self.father) != len(self.mother):
+            raise ValueError("father and mother must have the same length")
+        h = C.c_void_p()
+        check(lib().genlib_plan_create(len(self.father), ptr(self.father), ptr(self.mother),
+                                       len(self.probands), ptr(self.probands), world, C.byref(h)))
+        self._h = h
+        self.world = world
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            lib().genlib_plan_destroy(h)
+
+    n_unique = property(lambda s: lib().genlib_plan_n_unique(s._h))
+    n_layers = property(lambda s: lib().genlib_plan_n_layers(s._h))
+    capacity = property(lambda s: lib().genlib_plan_capacity(s._h))
+    row_updates = property(lambda s: lib().genlib_plan_row_updates(s._h))
+
+    def device_bytes(self, numerics="reference", rank: int = 0) -> int:
+        return lib().genlib_plan_device_bytes(self._h, _lib.NUMERICS[numerics], rank)
+
+    def layer_info(self, layer: int) -> dict:
+        info = LayerInfo()
+        check(lib().genlib_plan_layer_info(self._h, layer, C.byref(info)))
+        return info.as_dict()
+
+    def layers(self):
+        return [self.layer_info(t) for t in range(self.n_layers)]
+
+    def layer_arrays(self, layer: int) -> dict:
+        info = self.layer_info(layer)
+        n, nf = info["n_new"], info["n_fam"]
+        out = {k: np.zeros(n, np.int32) for k in ("member_ind", "member_slot", "member_fam", "member_owner")}
+        out.update({k: np.zeros(nf, np.int32) for k in ("fam_father_slot", "fam_mother_slot")})
+        check(lib().genlib_plan_layer_arrays(self._h, layer, ptr(out["member_ind"]), ptr(out["member_slot"]),
+                                             ptr(out["member_fam"]), ptr(out["fam_father_slot"]),
+                                             ptr(out["fam_mother_slot"]), ptr(out["member_owner"])))
+        flags = np.zeros(max(self.capacity, 1), np.uint8)
+        check(lib().genlib_plan_layer_flags(self._h, layer, ptr(flags)))
+        out["live_flags"] = flags
+        return out
+
+    def proband_slots(self) -> np.ndarray:
+        s = np.zeros(self.n_unique, np.int32)
+        if self.n_unique:
+            check(lib().genlib_plan_proband_slots(self._h, ptr(s)))
+        return s
+
+    def verbose_lines(self, running: bool = False):
+        """The reference's per-step lines (src/compute.jl:257-260 and :281-284)."""
+        infos = self.layers()[1:]
+        S1 = len(infos)
+        for k, i in enumerate(infos, 1):
+            counts = (f"{i['ref_founders']} founders, {i['ref_probands']} probands, {i['ref_both']} both")
+            yield (f"Running step {k} of {S1} ({counts})." if running else f"Step {k} of {S1}: {counts}.")
+
+
+class Engine:
+    """Device state of one rank: frontier matrix, scratch, uploaded schedule."""
+
+    def __init__(self, plan: Plan, numerics="reference", device: int = -1):
+        self.plan = plan
+        self.numerics = _lib.NUMERICS[numerics]
+        h = C.c_void_p()
+        check(lib().genlib_engine_create(plan._h, self.numerics, device, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            lib().genlib_engine_destroy(h)
+
+    __del__ = close
+
+    def run(self, time_layers: bool = False) -> float:
+        """All generation steps on the device; returns CUDA-event milliseconds."""
+        check(lib().genlib_engine_run(self._h, int(time_layers)))
+        return self.stats()["ms_kernels"]
+
+    def stats(self) -> dict:
+        s = Stats()
+        check(lib().genlib_engine_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def layer_info(self, layer: int) -> dict:
+        info = LayerInfo()
+        check(lib().genlib_engine_layer_info(self._h, layer, C.byref(info)))
+        return info.as_dict()
+
+    def fetch(self, out: Optional[np.ndarray] = None, dtype=np.float32) -> np.ndarray:
+        n = self.plan.n_unique
+        if out is None:
+            out = np.empty((n, n), dtype)
+        if out.shape != (n, n) or not out.flags.c_contiguous or out.dtype not in _lib.DTYPES:
+            raise ValueError("out must be a C-contiguous (n_unique, n_unique) float32/float64 array")
+        check(lib().genlib_engine_fetch(self._h, ptr(out), _lib.DTYPES[out.dtype]))
+        return out
+
+    def phi_mean(self) -> float:
+        v = C.c_double(0)
+        check(lib().genlib_engine_phi_mean(self._h, C.byref(v)))
+        return v.value
+
+    def read_block(self, slots) -> np.ndarray:
+        slots = np.ascontiguousarray(slots, np.int32)
+        out = np.zeros((len(slots), len(slots)), np.float64)
+        check(lib().genlib_engine_read_block(self._h, len(slots), ptr(slots), ptr(out)))
+        return out
+
+
+def phi(pedigree: Pedigree, probandIDs=None, *, verbose: bool = False, compute: bool = True,
+        numerics="reference", dtype=np.float32, device: int = -1, out: Optional[np.ndarray] = None,
+        return_stats: bool = False):
+    """gen.phi(pedigree, probandIDs; verbose, compute) on the B200 engine."""
+    IDs = pro(pedigree) if probandIDs is None else np.asarray(probandIDs, np.int64)
+    ranks = pedigree.rank_of(IDs)                       # KeyError, like pedigree[ID]
+    plan = Plan(pedigree.father, pedigree.mother, ranks)
+    if verbose or not compute:
+        for line in plan.verbose_lines():
+            print(line)
+    if not compute:
+        return None
+    n = plan.n_unique
+    if n == 0:
+        res = np.zeros((0, 0), dtype)
+        return (res, {}) if return_stats else res
+    if verbose:
+        for line in plan.verbose_lines(running=True):
+            print(line)
+    eng = Engine(plan, numerics=numerics, device=device)
+    try:
+        eng.run()
+        res = eng.fetch(out=out, dtype=dtype)
+        stats = eng.stats()
+    finally:
+        eng.close()
+    return (res, stats) if return_stats else res
+
+
+def phi_arrays(father, mother, proband_ranks, *, numerics="reference", dtype=np.float32,
+               device: int = -1, out: Optional[np.ndarray] = None):
+    """One-shot C-ABI call `genlib_phi` on flat arrays (what the Julia shim ccalls)."""
+    father = np.ascontiguousarray(father, np.int32)
+    mother = np.ascontiguousarray(mother, np.int32)
+    pr = np.ascontiguousarray(proband_ranks, np.int32)
+    n_unique = len(np.unique(pr)) if ((pr >= 0) & (pr < len(father))).all() else len(pr)
+    if out is None:
+        out = np.empty((n_unique, n_unique), dtype)
+    st = Stats()
+    check(lib().genlib_phi(len(father), ptr(father), ptr(mother), len(pr), ptr(pr), ptr(out),
+                           _lib.DTYPES[np.dtype(out.dtype)], _lib.NUMERICS[numerics], device, C.byref(st)))
+    return out, st.as_dict()
+
+
+def phiMean(phi_matrix) -> np.float32:
+    """gen.phiMean(::Matrix{Float32}) (src/compute.jl:454-459), host side."""
+    m = np.asarray(phi_matrix, np.float32)
+    total = m.sum(dtype=np.float32) - np.trace(m, dtype=np.float32)
+    return np.float32(total / np.float32(m.size - m.shape[0]))

@@ -1,0 +1,146 @@
+/*
+ * genlib_cuda.h -- C ABI of libgenlib_cuda.so, the B200 kinship engine that sits
+ * behind GenLib.jl's `gen.phi(ped)` / `gen.phi(ped, probandIDs)`.
+ *
+ * The reference has no FFI boundary: the path is the Julia method
+ *     phi(pedigree::Pedigree, probandIDs::Vector{Int} = pro(pedigree);
+ *         verbose::Bool = false, compute::Bool = true)      src/compute.jl:233-304
+ * so these entry points are what a `ccall` shim (genlib.jl_b200/julia/GenLibCUDA.jl,
+ * INTEGRATION.md) binds in its place.  Everything is plain pointers and sizes;
+ * the caller owns every buffer; no call throws, exits or keeps a pointer after
+ * it returns (handles excepted).
+ *
+ * Pedigree encoding (what `values(pedigree)` yields, src/create.jl:234-254):
+ *   individuals are numbered by 0-based rank (Individual.rank - 1); father[i] /
+ *   mother[i] are the rank of the parent or -1 for `nothing`; every parent
+ *   precedes its children.  Probands are ranks, in the order the output matrix
+ *   must have (src/compute.jl:303); duplicates collapse onto their first
+ *   occurrence (the `intersect` at src/compute.jl:251).
+ */
+#ifndef GENLIB_CUDA_H
+#define GENLIB_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GENLIB_ABI_VERSION 1
+
+/* status codes (0 = ok) */
+#define GENLIB_OK 0
+#define GENLIB_EINVAL 1    /* malformed arguments (null pointer, bad dtype ...)          */
+#define GENLIB_EKEY 2      /* proband or parent index out of range: Julia's KeyError,   */
+                           /* src/create.jl:70 reached from src/compute.jl:196          */
+#define GENLIB_EORDER 3    /* a parent does not precede its child (create.jl:240)       */
+#define GENLIB_ECUDA 4     /* CUDA runtime / driver error, no usable device             */
+#define GENLIB_ENOMEM 5    /* working set does not fit the device(s)                    */
+#define GENLIB_ECOMM 6     /* NCCL / peer-memory set-up failed                          */
+
+/* numerics: how the frontier is stored between generation steps */
+#define GENLIB_NUMERICS_REFERENCE 0 /* Float32 storage, Float64 arithmetic, one RN32 per   */
+                                    /* cut-vertex step: bit-identical to src/compute.jl:   */
+                                    /* 105-158,291-301                                      */
+#define GENLIB_NUMERICS_FP64 1      /* Float64 storage, no intermediate rounding           */
+
+/* output element type */
+#define GENLIB_F32 0 /* Matrix{Float32}: what gen.phi returns (src/compute.jl:271,291)      */
+#define GENLIB_F64 1
+
+typedef struct genlib_plan genlib_plan;     /* host-side schedule; needs no GPU */
+typedef struct genlib_engine genlib_engine; /* device-side state of one rank    */
+
+/* One generation step (= one cut-vertex step of src/compute.jl:276-302). */
+typedef struct genlib_layer_info {
+    int32_t n_new;        /* individuals born in this layer (row-updates)               */
+    int32_t n_fam;        /* distinct (father, mother) couples among them               */
+    int32_t live_before;  /* L: individuals whose rows are live when the step starts    */
+    int32_t carried;      /* of those, how many stay live after the step                */
+    int32_t ref_founders; /* |cut[k]|   -- "founders" of the verbose line, compute.jl:258 */
+    int32_t ref_probands; /* |cut[k+1]| -- "probands", compute.jl:259                     */
+    int32_t ref_both;     /* |cut[k] n cut[k+1]|, compute.jl:260                          */
+    int32_t reserved;
+    double alg_elems;     /* 4*n*L + 3*n^2; bytes = elems * sizeof(storage) */
+    double ms_cross;      /* device time of the cross-block kernel (when timed)          */
+    double ms_intra;      /* device time of the intra-layer kernel (when timed)          */
+} genlib_layer_info;
+
+typedef struct genlib_stats {
+    int32_t n_unique;      /* side of the output matrix                                  */
+    int32_t n_layers;      /* generation layers including the top one                    */
+    int64_t row_updates;   /* individuals born = sum of n_new                            */
+    int64_t capacity;      /* W: slots (rows/columns) of the frontier matrix             */
+    int64_t device_bytes;  /* device memory the engine allocated on this rank            */
+    double alg_bytes;      /* sum over layers of s*(4nL+3n^2)                             */
+    double ms_plan;        /* host planning                                              */
+    double ms_upload;      /* plan H2D                                                   */
+    double ms_kernels;     /* all layers, CUDA events on the engine's stream             */
+    double ms_fetch;       /* proband gather + D2H                                       */
+    int64_t h2d_bytes;
+    int64_t d2h_bytes;
+    int32_t kernel_launches;
+    int32_t reserved;
+} genlib_stats;
+
+int genlib_version(void);
+/* Thread-local, human-readable description of the last failure on this thread. */
+const char *genlib_last_error(void);
+/* Number of visible CUDA devices, or a negative status. */
+int genlib_device_count(void);
+
+/* ---- planning (host only): levels, Kirkpatrick frontier, slots -------------
+ * Replaces src/compute.jl:236-251 (cut vertices), :165-186 (_index_pedigree)
+ * and :287-289 (founder_index).  `world` > 1 prepares the row-sharded schedule
+ * for that many ranks. */
+int genlib_plan_create(int32_t n, const int32_t *father, const int32_t *mother, int32_t n_pro,
+                       const int32_t *proband, int32_t world, genlib_plan **out);
+void genlib_plan_destroy(genlib_plan *plan);
+int32_t genlib_plan_n_unique(const genlib_plan *plan);
+int32_t genlib_plan_n_layers(const genlib_plan *plan);
+int64_t genlib_plan_capacity(const genlib_plan *plan);
+int64_t genlib_plan_row_updates(const genlib_plan *plan);
+int genlib_plan_layer_info(const genlib_plan *plan, int32_t layer, genlib_layer_info *out);
+/* Device bytes rank `rank` needs for the given numerics. */
+int64_t genlib_plan_device_bytes(const genlib_plan *plan, int numerics, int32_t rank);
+/* Schedule export (tests replay it on the CPU to check the planner).  Arrays
+ * may be NULL; sizes come from genlib_plan_layer_info.  member_*: n_new
+ * entries in family-major order; fam_*: n_fam entries; slots are columns of
+ * the frontier matrix; parents are given as slots (-1 = none). */
+int genlib_plan_layer_arrays(const genlib_plan *plan, int32_t layer, int32_t *member_ind,
+                             int32_t *member_slot, int32_t *member_fam, int32_t *fam_father_slot,
+                             int32_t *fam_mother_slot, int32_t *member_owner);
+/* live_flags: capacity bytes; bit0 = live before the step, bit1 = still live after it. */
+int genlib_plan_layer_flags(const genlib_plan *plan, int32_t layer, uint8_t *live_flags);
+int genlib_plan_proband_slots(const genlib_plan *plan, int32_t *slots);
+
+/* ---- one-shot: the `gen.phi(ped, probandIDs)` call -------------------------
+ * out: n_unique^2 elements of out_dtype (row-major == column-major: symmetric),
+ * host memory (pinned or pageable).  n_unique <= n_pro; query it with
+ * genlib_plan_n_unique or read stats->n_unique.  device < 0 = current device. */
+int genlib_phi(int32_t n, const int32_t *father, const int32_t *mother, int32_t n_pro,
+               const int32_t *proband, void *out, int out_dtype, int numerics, int device,
+               genlib_stats *stats);
+
+/* ---- handle API: keep the schedule on the device, run, fetch ---------------
+ * (what the benchmark and a multi-call Julia session use) */
+int genlib_engine_create(const genlib_plan *plan, int numerics, int device, genlib_engine **out);
+void genlib_engine_destroy(genlib_engine *eng);
+/* Run every layer on the engine's stream and wait.  time_layers != 0 brackets
+ * every kernel with CUDA events (per-layer ms in genlib_engine_layer_info). */
+int genlib_engine_run(genlib_engine *eng, int time_layers);
+int genlib_engine_layer_info(const genlib_engine *eng, int32_t layer, genlib_layer_info *out);
+int genlib_engine_stats(const genlib_engine *eng, genlib_stats *out);
+/* Gather proband rows/columns and stream them to host memory. */
+int genlib_engine_fetch(genlib_engine *eng, void *out, int out_dtype);
+/* Mean off-diagonal kinship of the proband matrix, reduced on the device
+ * (consumer of the path: phiMean, src/compute.jl:454-459). */
+int genlib_engine_phi_mean(genlib_engine *eng, double *out);
+/* Debug/test: copy the frontier entry block [slots x slots] (as double). */
+int genlib_engine_read_block(genlib_engine *eng, int32_t n_slots, const int32_t *slots, double *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GENLIB_CUDA_H */

@@ -1,0 +1,52 @@
+"""The C ABI: the library loads, exports every symbol include/genlib_cuda.h declares,
+and fails loudly (no CPU fallback) when no CUDA device is present."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "genlib_cuda.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(genlib_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_library_agree(gen):
+    from genlib_jl_b200 import _lib
+    names = declared_symbols()
+    assert len(names) >= 20
+    assert sorted(_lib.SYMBOLS) == names, "ctypes table and header drifted apart"
+    L = C.CDLL(gen.LIB_PATH)
+    for n in names:
+        assert hasattr(L, n), f"{n} not exported"
+    assert gen.lib().genlib_version() == 1
+
+
+def test_layer_info_struct_layout(gen):
+    from genlib_jl_b200 import _lib
+    assert C.sizeof(_lib.LayerInfo) == 56 and C.sizeof(_lib.Stats) == 96
+
+
+def test_no_cpu_fallback(gen):
+    if gen.lib().genlib_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    ped = gen.genealogy(gen.geneaJi)
+    with pytest.raises(gen.GenlibError) as e:
+        gen.phi(ped)
+    assert e.value.status == 4            # GENLIB_ECUDA
+    with pytest.raises(gen.GenlibError):
+        gen.phi_arrays(ped.father, ped.mother, ped.rank_of([1, 2, 29]))
+
+
+def test_product_does_not_touch_the_oracle():
+    pkg = os.path.join(ROOT, "genlib.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".jl", "Makefile")):
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle" not in src.lower(), f"{f} mentions the oracle"

@@ -1,0 +1,153 @@
+"""Host-side mirror of the reference interface: genealogy / pro / phi front end, planner."""
+import io
+from contextlib import redirect_stdout
+
+import numpy as np
+import pytest
+
+from plan_replay import replay
+from util import random_pedigree
+
+
+def test_pedigree_matches_reference_show(gen):
+    ped = gen.genealogy(gen.genea140)
+    assert repr(ped) == ("A pedigree with:\n41523 individuals;\n68248 parent-child relations;\n20773 men;"
+                         "\n20750 women;\n140 subjects;\n18 generations.")        # runtests.jl:18-20
+    assert repr(ped[33724]) == "ind: 33724\nfather: 10086\nmother: 10087\nsex: 1"  # runtests.jl:24-25
+    assert [c.ID for c in ped[33724].children] == [10033, 113470]                 # runtests.jl:26
+    assert ped[33724].children[1].father.ID == 33724                              # runtests.jl:27
+    assert len(ped) == 41523 and ped.depth() == 18
+
+
+def test_custom_pedigree(gen):                                                    # runtests.jl:5-13
+    df = {"ind": [1, 2, 3, 4, 5, 6, 7, 8, 9, 10], "father": [0, 0, 0, 1, 1, 0, 3, 3, 6, 6],
+          "mother": [0, 0, 0, 2, 2, 0, 4, 4, 5, 5], "sex": [1, 2, 1, 2, 2, 1, 2, 1, 1, 2]}
+    ped = gen.genealogy(df)
+    assert ped[9].mother.sex == 2
+
+
+def test_geneaji_selectors(gen):
+    ped = gen.genealogy(gen.geneaJi)
+    assert gen.pro(ped).tolist() == [1, 2, 29]                                    # runtests.jl:41
+    assert gen.founder(ped).tolist() == [17, 19, 20, 23, 25, 26]                  # runtests.jl:42
+    with pytest.raises(KeyError):
+        ped[1000]
+    assert 17 in ped and 1000 not in ped
+
+
+def test_rank_order_equals_oracle(gen, ob):
+    for path in (gen.geneaJi, gen.genea140):
+        ped, o = gen.genealogy(path), ob.OraclePedigree.from_csv(path)
+        assert np.array_equal(ped.ids, o.ids) and np.array_equal(ped.father, o.father)
+        assert np.array_equal(ped.mother, o.mother) and np.array_equal(gen.pro(ped), o.pro())
+    rng = np.random.default_rng(0)
+    rec = random_pedigree(rng, 300, 20)
+    ped = gen.genealogy(rec)
+    o = ob.OraclePedigree.from_arrays(rec["ind"], rec["father"], rec["mother"], rec["sex"])
+    assert np.array_equal(ped.ids, o.ids) and np.array_equal(ped.father, o.father)
+
+
+def test_unsorted_file_needs_sort(gen):
+    rec = {"ind": [1, 2, 3], "father": [2, 0, 0], "mother": [3, 0, 0], "sex": [1, 1, 2]}
+    assert gen.genealogy(rec).ids.tolist() == [2, 3, 1]
+    with pytest.raises(KeyError):
+        gen.genealogy(rec, sort=False)                                            # create.jl:240
+
+
+def test_verbose_lines_match_reference_cuts(gen, ob, genea140_oracle):
+    """`Step i of S: a founders, b probands, c both.` (compute.jl:257-260) from the planner
+    equal the oracle's cut sizes (which restate compute.jl:236-251)."""
+    for path in (gen.geneaJi, gen.genea140):
+        ped = gen.genealogy(path)
+        plan = gen.Plan(ped.father, ped.mother, ped.rank_of(gen.pro(ped)))
+        steps = genea140_oracle[2] if path == gen.genea140 else \
+            ob.OraclePedigree.from_csv(path).phi(with_steps=True)[1]
+        lines = list(plan.verbose_lines())
+        assert len(lines) == len(steps)
+        for k, (line, s) in enumerate(zip(lines, steps), 1):
+            assert line == (f"Step {k} of {len(steps)}: {int(s[0])} founders, {int(s[1])} probands, "
+                            f"{int(s[2])} both.")
+    buf = io.StringIO()
+    ped = gen.genealogy(gen.geneaJi)
+    with redirect_stdout(buf):
+        assert gen.phi(ped, compute=False) is None                               # compute.jl:264-266
+    assert buf.getvalue().splitlines()[0] == "Step 1 of 7: 2 founders, 4 probands, 2 both."
+
+
+def test_plan_errors(gen):
+    with pytest.raises(KeyError):
+        gen.Plan([-1, -1, 0], [-1, -1, 1], [5])
+    with pytest.raises(gen.GenlibError):
+        gen.Plan([1, -1], [-1, -1], [0])                    # parent after child
+    ped = gen.genealogy(gen.geneaJi)
+    with pytest.raises(KeyError):
+        gen.phi(ped, [1, 12345], compute=False)
+    assert gen.phi(ped, [], compute=True).shape == (0, 0)   # empty list needs no device
+
+
+def test_plan_invariants(gen):
+    s = gen.synth.generate(4000, 10, 200, alpha=0.05, demes=2, migration=0.1, overlap=3, seed=5)
+    ped = gen.genealogy(s.as_columns())
+    plan = gen.Plan(ped.father, ped.mother, ped.rank_of(s.probands))
+    seen = set()
+    live = {}
+    for t in range(plan.n_layers):
+        info, arr = plan.layer_info(t), plan.layer_arrays(t)
+        flags = arr["live_flags"]
+        assert set(np.nonzero(flags & 1)[0]) == set(live.values())
+        assert info["n_fam"] <= info["n_new"] and np.all(np.diff(arr["member_fam"]) >= 0)
+        for ind, slot in zip(arr["member_ind"], arr["member_slot"]):
+            assert ind not in seen and slot not in live.values()
+            seen.add(int(ind))
+        carried = set(np.nonzero(flags & 2)[0])
+        live = {i: sl for i, sl in live.items() if sl in carried}
+        live.update({int(i): int(sl) for i, sl in zip(arr["member_ind"], arr["member_slot"])})
+        # parents of the layer are live before it
+        for f in np.concatenate([arr["fam_father_slot"], arr["fam_mother_slot"]]):
+            assert f == -1 or flags[f] & 1
+    assert plan.row_updates == len(seen)
+    assert set(plan.proband_slots()) <= set(live.values())
+
+
+@pytest.mark.parametrize("numerics", ["reference", "fp64"])
+def test_replayed_schedule_equals_oracle_geneaji(gen, ob, numerics):
+    ped = gen.genealogy(gen.geneaJi)
+    plan = gen.Plan(ped.father, ped.mother, ped.rank_of(gen.pro(ped)))
+    want = ob.OraclePedigree.from_csv(gen.geneaJi).phi()
+    assert np.array_equal(replay(plan, numerics).astype(np.float32), want)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_replayed_schedule_equals_oracle_random(gen, ob, seed):
+    rng = np.random.default_rng(100 + seed)
+    n = int(rng.integers(40, 400))
+    rec = random_pedigree(rng, n, int(rng.integers(2, 12)), p_single=0.15, p_none=0.03,
+                          window=int(rng.choice([0, 0, 30, 80])))
+    ped = gen.genealogy(rec)
+    o = ob.OraclePedigree.from_arrays(rec["ind"], rec["father"], rec["mother"], rec["sex"])
+    pro = rng.permutation(ped.ids)[: int(rng.integers(1, 40))]
+    pro = np.concatenate([pro, pro[:2]])                     # duplicates
+    plan = gen.Plan(ped.father, ped.mother, ped.rank_of(pro))
+    assert np.array_equal(replay(plan), o.phi(pro))
+
+
+def test_replayed_schedule_deep_pedigree_rounding(gen, ob):
+    """40 generations x 16: Float32 stores are lossy and Float64 sums inexact, so the
+    reference's rounding schedule and rank grouping both matter."""
+    s = gen.synth.generate(16 * 40, 40, 16, alpha=0.2, overlap=1, seed=11)
+    ped = gen.genealogy(s.as_columns())
+    o = ob.OraclePedigree.from_arrays(s.ind, s.father, s.mother, s.sex)
+    plan = gen.Plan(ped.father, ped.mother, ped.rank_of(s.probands))
+    want = o.phi(s.probands)
+    got = replay(plan)
+    assert np.array_equal(got, want)
+    assert not np.array_equal(replay(plan, "fp64").astype(np.float32), want)   # the modes do differ
+
+
+def test_synth_is_deterministic(gen):
+    a = gen.synth.generate(5000, 10, 100, alpha=0.02, demes=3, migration=0.05, overlap=2, seed=9)
+    b = gen.synth.generate(5000, 10, 100, alpha=0.02, demes=3, migration=0.05, overlap=2, seed=9)
+    assert np.array_equal(a.father, b.father) and np.array_equal(a.probands, b.probands)
+    assert (a.father[a.generation > 0] > 0).all() and (a.father < a.ind).all()
+    c = gen.synth.generate(5000, 10, 100, alpha=0.02, demes=3, migration=0.05, overlap=2, seed=10)
+    assert not np.array_equal(a.father, c.father)
