@@ -51,6 +51,8 @@ SYMBOLS = {
     "genlib_version": (C.c_int, []),
     "genlib_last_error": (C.c_char_p, []),
     "genlib_device_count": (C.c_int, []),
+    "genlib_pinned_alloc": (C.c_int, [C.c_size_t, C.POINTER(_P)]),
+    "genlib_pinned_free": (C.c_int, [_P]),
     "genlib_plan_create": (C.c_int, [C.c_int32, _P, _P, C.c_int32, _P, C.c_int32, C.POINTER(_P)]),
     "genlib_plan_destroy": (None, [_P]),
     "genlib_plan_n_unique": (C.c_int32, [_P]),
@@ -71,6 +73,7 @@ SYMBOLS = {
     "genlib_engine_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "genlib_engine_fetch": (C.c_int, [_P, _P, C.c_int]),
     "genlib_engine_phi_mean": (C.c_int, [_P, C.POINTER(C.c_double)]),
+    "genlib_engine_set_layer_limit": (C.c_int, [_P, C.c_int32]),
     "genlib_engine_read_block": (C.c_int, [_P, C.c_int32, _P, _P]),
 }
 

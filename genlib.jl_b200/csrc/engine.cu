@@ -86,6 +86,7 @@ struct genlib_engine {
     std::vector<cudaEvent_t> events;
     genlib_stats stats{};
     bool ran = false;
+    int32_t layer_limit = -1;
     ~genlib_engine() {
         for (auto e : events) cudaEventDestroy(e);
         if (A) cudaFree(A);
@@ -135,6 +136,7 @@ int launch_layers(genlib_engine &E, bool timed) {
     for (int t = 0; t < (int)P.layers.size(); t++) {
         const Layer &L = P.layers[t];
         if (L.n_new == 0) continue;
+        if (E.layer_limit >= 0 && t >= E.layer_limit) break;
         LayerArgs a = layer_args(E, t);
         if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
         if (L.live_before > 0) {
@@ -207,6 +209,18 @@ int genlib_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { g_err = "cudaGetDeviceCount failed (no driver / no device)"; return -GENLIB_ECUDA; }
     return n;
+}
+
+int genlib_pinned_alloc(size_t bytes, void **out) {
+    if (!out) return fail(GENLIB_EINVAL, "null argument");
+    *out = nullptr;
+    CU(cudaHostAlloc(out, std::max<size_t>(bytes, 16), cudaHostAllocDefault));
+    return GENLIB_OK;
+}
+
+int genlib_pinned_free(void *ptr) {
+    if (ptr) CU(cudaFreeHost(ptr));
+    return GENLIB_OK;
 }
 
 int genlib_plan_create(int32_t n, const int32_t *father, const int32_t *mother, int32_t n_pro,
@@ -371,6 +385,7 @@ int genlib_engine_run(genlib_engine *eng, int time_layers) {
         size_t ev = 0;
         for (size_t t = 0; t < E.info.size(); t++) {
             if (E.info[t].n_new == 0) continue;
+            if (E.layer_limit >= 0 && (int32_t)t >= E.layer_limit) break;
             float a = 0, b = 0;
             CU(cudaEventElapsedTime(&a, E.events[ev], E.events[ev + 1]));
             CU(cudaEventElapsedTime(&b, E.events[ev + 1], E.events[ev + 2]));
@@ -428,6 +443,12 @@ int genlib_engine_phi_mean(genlib_engine *eng, double *out) {
     CU(cudaMemcpyAsync(h, eng->acc.p, sizeof h, cudaMemcpyDeviceToHost, eng->stream));
     CU(cudaStreamSynchronize(eng->stream));
     *out = (h[0] - h[1]) / ((double)n * n - n);
+    return GENLIB_OK;
+}
+
+int genlib_engine_set_layer_limit(genlib_engine *eng, int32_t n_layers) {
+    if (!eng) return fail(GENLIB_EINVAL, "null engine");
+    eng->layer_limit = n_layers;
     return GENLIB_OK;
 }
 

@@ -98,8 +98,9 @@ class Engine:
 
     __del__ = close
 
-    def run(self, time_layers: bool = False) -> float:
+    def run(self, time_layers: bool = False, layer_limit: int = -1) -> float:
         """All generation steps on the device; returns CUDA-event milliseconds."""
+        check(lib().genlib_engine_set_layer_limit(self._h, layer_limit))
         check(lib().genlib_engine_run(self._h, int(time_layers)))
         return self.stats()["ms_kernels"]
 
@@ -132,6 +133,27 @@ class Engine:
         out = np.zeros((len(slots), len(slots)), np.float64)
         check(lib().genlib_engine_read_block(self._h, len(slots), ptr(slots), ptr(out)))
         return out
+
+
+class PinnedMatrix:
+    """A page-locked (n, n) host matrix for `out=` (genlib_pinned_alloc)."""
+
+    def __init__(self, n: int, dtype=np.float32):
+        self.dtype = np.dtype(dtype)
+        nbytes = max(1, n * n * self.dtype.itemsize)
+        p = C.c_void_p()
+        check(lib().genlib_pinned_alloc(nbytes, C.byref(p)))
+        self._p = p
+        buf = (C.c_char * nbytes).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=n * n).reshape(n, n)
+
+    def free(self):
+        p, self._p = getattr(self, "_p", None), None
+        if p:
+            self.array = None
+            lib().genlib_pinned_free(p)
+
+    __del__ = free
 
 
 def phi(pedigree: Pedigree, probandIDs=None, *, verbose: bool = False, compute: bool = True,

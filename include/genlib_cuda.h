@@ -90,6 +90,11 @@ const char *genlib_last_error(void);
 /* Number of visible CUDA devices, or a negative status. */
 int genlib_device_count(void);
 
+/* Page-locked host memory for `out` buffers (D2H at full PCIe speed).  Optional:
+ * every entry point also accepts pageable memory. */
+int genlib_pinned_alloc(size_t bytes, void **out);
+int genlib_pinned_free(void *ptr);
+
 /* ---- planning (host only): levels, Kirkpatrick frontier, slots -------------
  * Replaces src/compute.jl:236-251 (cut vertices), :165-186 (_index_pedigree)
  * and :287-289 (founder_index).  `world` > 1 prepares the row-sharded schedule
@@ -137,6 +142,8 @@ int genlib_engine_fetch(genlib_engine *eng, void *out, int out_dtype);
 /* Mean off-diagonal kinship of the proband matrix, reduced on the device
  * (consumer of the path: phiMean, src/compute.jl:454-459). */
 int genlib_engine_phi_mean(genlib_engine *eng, double *out);
+/* Debug/test: stop genlib_engine_run after `n_layers` layers (< 0: no limit). */
+int genlib_engine_set_layer_limit(genlib_engine *eng, int32_t n_layers);
 /* Debug/test: copy the frontier entry block [slots x slots] (as double). */
 int genlib_engine_read_block(genlib_engine *eng, int32_t n_slots, const int32_t *slots, double *out);
 

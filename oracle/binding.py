@@ -44,6 +44,7 @@ def lib():
         L.oracle_phi_ranks.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                        C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_int,
                                        C.c_void_p, C.c_int]
+        L.oracle_set_time_budget.argtypes = [C.c_double]
         L.oracle_phi_mean.restype = C.c_double
         L.oracle_phi_mean.argtypes = [C.c_void_p, C.c_int]
         _LIB = L
@@ -124,8 +125,7 @@ class OraclePedigree:
             u = nu.value
             res = out.reshape(-1)[: u * u].reshape(u, u).copy()
         if with_steps:
-            nsteps = rc if max_steps < 0 else min(rc, max_steps)
-            return res, steps[:nsteps].copy()
+            return res, steps[:rc].copy()
         return res
 
 
@@ -142,12 +142,31 @@ def phi_ranks(father, mother, pro_ranks, nthreads: int = 0, max_steps: int = -1)
                                 C.byref(nu), nthreads, max_steps, _p(steps), cap)
     if rc < 0:
         raise KeyError(f"oracle_phi_ranks status {rc}")
-    nsteps = rc if max_steps < 0 else min(rc, max_steps)
     res = None
     if out is not None:
         u = nu.value
         res = out.reshape(-1)[: u * u].reshape(u, u).copy()
-    return res, steps[:nsteps].copy()
+    return res, steps[:rc].copy()
+
+
+def bounded_steps(father, mother, pro_ranks, seconds: float, nthreads: int = 0):
+    """Run the reference algorithm step by step until `seconds` have elapsed (the step in
+    flight finishes); returns the per-step info of the steps that ran.  CPU baseline only."""
+    father = np.ascontiguousarray(father, np.int32)
+    mother = np.ascontiguousarray(mother, np.int32)
+    pro = np.ascontiguousarray(pro_ranks, np.int32)
+    cap = 4096
+    steps = np.zeros((cap, 6), np.float64)
+    nu = C.c_int(0)
+    lib().oracle_set_time_budget(float(seconds))
+    try:
+        rc = lib().oracle_phi_ranks(len(father), _p(father), _p(mother), len(pro), _p(pro), None,
+                                    C.byref(nu), nthreads, -1, _p(steps), cap)
+    finally:
+        lib().oracle_set_time_budget(0.0)
+    if rc < 0:
+        raise KeyError(f"oracle_phi_ranks status {rc}")
+    return steps[:rc].copy()
 
 
 def phi_mean(phi: np.ndarray) -> float:

@@ -409,6 +409,10 @@ static void pair_loop(const phi_ctx *ctx, const int32_t *mem, int nn, float *phi
 
 int oracle_num_threads(void);
 
+/* Bounded CPU baseline: stop after the step that crosses this many seconds (<= 0: off). */
+static double g_time_budget = 0.0;
+void oracle_set_time_budget(double seconds) { g_time_budget = seconds; }
+
 /*
  * compute.jl:233-304 on flat rank-indexed arrays.
  *   out        n_unique^2 floats (row-major; the matrix is symmetric), may be NULL
@@ -443,8 +447,10 @@ int oracle_phi_ranks(int n, const int32_t *father, const int32_t *mother, int n_
     int nPsi = n0;
     if (nthreads <= 0) nthreads = oracle_num_threads();
     int steps_done = 0;
+    const double t_begin = now_s();
     for (int k = 0; k + 1 < S; k++) {                     /* compute.jl:276 */
         if (max_steps >= 0 && k >= max_steps) break;
+        if (g_time_budget > 0 && now_s() - t_begin > g_time_budget) break;
         const ivec *prev = &c.cut[k], *next = &c.cut[k + 1];
         double t0 = now_s();
         for (int t = 0; t < prev->n; t++) { founder_index[prev->v[t]] = t + 1; stamp[prev->v[t]] = k; }
@@ -467,7 +473,7 @@ int oracle_phi_ranks(int n, const int32_t *father, const int32_t *mother, int n_
     if (out && steps_done == S - 1) memcpy(out, Psi, (size_t)nu * nu * sizeof *out);
     free(Psi); free(founder_index); free(stamp);
     cuts_free(&c);
-    return S - 1;
+    return (max_steps >= 0 || g_time_budget > 0) ? steps_done : S - 1;
 }
 
 /* gen.phi(ped, probandIDs): IDs -> ranks (KeyError on unknown ID, create.jl:70

@@ -12,7 +12,7 @@ from __future__ import annotations
 import numpy as np
 
 
-def replay(plan, numerics: str = "reference", check_poison: bool = True) -> np.ndarray:
+def replay(plan, numerics: str = "reference", check_poison: bool = True, on_layer=None) -> np.ndarray:
     T = np.float32 if numerics == "reference" else np.float64
     W = int(plan.capacity)
     A = np.full((W, W), np.nan, T)
@@ -60,6 +60,8 @@ def replay(plan, numerics: str = "reference", check_poison: bool = True) -> np.n
             dv[both] = 0.5 + 0.5 * A[pf[both], pm[both]].astype(np.float64)
         blk[np.arange(n), np.arange(n)] = dv[fam]
         A[np.ix_(slot, slot)] = blk.astype(T)
+        if on_layer is not None:
+            on_layer(t, A, np.union1d(carried, slot))      # frontier after the layer, live slots
     ps = plan.proband_slots()
     out = A[np.ix_(ps, ps)]
     if check_poison:

@@ -1,0 +1,208 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle: bit-exact, every case.
+
+Everything here runs on a B200 (`-m gpu`).  /root/reference is not read.
+"""
+import hashlib
+
+import numpy as np
+import pytest
+
+from plan_replay import replay
+from util import exact_kinship, random_pedigree
+
+pytestmark = pytest.mark.gpu
+
+GENEAJI_PHI = np.array([[0.591796875, 0.37109375, 0.072265625],
+                        [0.37109375, 0.591796875, 0.072265625],
+                        [0.072265625, 0.072265625, 0.53515625]], np.float32)   # runtests.jl:51-52
+
+
+def assert_bit_equal(got, want):
+    assert got.dtype == want.dtype and got.shape == want.shape
+    if not np.array_equal(got.view(np.uint32 if got.dtype == np.float32 else np.uint64),
+                          want.view(np.uint32 if want.dtype == np.float32 else np.uint64)):
+        bad = np.argwhere(got != want)
+        i, j = bad[0]
+        raise AssertionError(f"{len(bad)} of {got.size} entries differ; first at ({i},{j}): "
+                             f"{got[i, j]!r} vs {want[i, j]!r}")
+
+
+def test_native_library_is_loaded(gen):
+    assert gen.lib().genlib_device_count() >= 1
+    maps = open("/proc/self/maps").read()
+    assert "libgenlib_cuda.so" in maps
+
+
+def test_geneaji_golden(gen):
+    ped = gen.genealogy(gen.geneaJi)
+    phi = gen.phi(ped)
+    assert_bit_equal(phi, GENEAJI_PHI)                         # runtests.jl:50-52
+    assert gen.phiMean(phi) == np.float32(0.171875)            # runtests.jl:53
+    out, stats = gen.phi_arrays(ped.father, ped.mother, ped.rank_of([1, 2, 29]))   # one-shot C ABI
+    assert_bit_equal(out, GENEAJI_PHI)
+    assert stats["n_unique"] == 3 and stats["kernel_launches"] > 0
+    assert_bit_equal(gen.phi(ped, numerics="fp64", dtype=np.float64), GENEAJI_PHI.astype(np.float64))
+
+
+def test_geneaji_every_layer_equals_replay(gen):
+    """Frontier after each layer == NumPy replay of the same schedule (localises a kernel bug)."""
+    ped = gen.genealogy(gen.geneaJi)
+    plan = gen.Plan(ped.father, ped.mother, ped.rank_of(gen.pro(ped)))
+    states = {}
+    replay(plan, on_layer=lambda t, A, live: states.__setitem__(t, (A[np.ix_(live, live)].copy(), live)))
+    eng = gen.Engine(plan)
+    for t in range(plan.n_layers):
+        eng.run(layer_limit=t + 1)
+        want, live = states[t]
+        got = eng.read_block(live).astype(np.float32)
+        assert_bit_equal(got, want)
+    eng.close()
+
+
+def test_genea140_equals_oracle(gen, genea140_oracle):
+    _, want, _ = genea140_oracle
+    ped = gen.genealogy(gen.genea140)
+    got, stats = gen.phi(ped, return_stats=True)
+    assert_bit_equal(got, want)
+    assert hashlib.sha256(got.tobytes()).hexdigest() == \
+        "fe0313bf6871185b7c7f4ac42edaa5f50ef781d567722f27bc373b1bd013ddea"
+    assert stats["row_updates"] == 41523 and stats["n_layers"] == 18
+    # Float64 storage rounds once at the end; on genea140 that is the same matrix
+    assert_bit_equal(gen.phi(ped, numerics="fp64"), want)
+
+
+def test_genea140_subsets_and_order(gen, ob):
+    ped = gen.genealogy(gen.genea140)
+    o = ob.OraclePedigree.from_csv(gen.genea140)
+    pro = gen.pro(ped)
+    rng = np.random.default_rng(1)
+    sel = rng.permutation(pro)[:17]
+    sel = np.concatenate([sel, sel[:3], [10086, 33724]])          # duplicates, a founder, an ancestor
+    assert_bit_equal(gen.phi(ped, sel), o.phi(sel))
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_pedigrees(gen, ob, seed):
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(30, 1500))
+    rec = random_pedigree(rng, n, int(rng.integers(2, 40)), p_single=0.15, p_none=0.03,
+                          window=int(rng.choice([0, 0, 40, 200])))
+    ped = gen.genealogy(rec)
+    o = ob.OraclePedigree.from_arrays(rec["ind"], rec["father"], rec["mother"], rec["sex"])
+    k = int(rng.integers(1, min(n, 300)))
+    pro = rng.permutation(ped.ids)[:k]
+    assert_bit_equal(gen.phi(ped, pro), o.phi(pro))
+    if seed % 3 == 0:
+        assert_bit_equal(gen.phi(ped), o.phi())                    # default probands = gen.pro
+
+
+@pytest.mark.parametrize("name,scale", [("C3", 0.02), ("C4", 0.004), ("C5", 0.02)])
+def test_named_configs_scaled(gen, ob, name, scale):
+    s = gen.synth.config(name, scale)
+    ped = gen.genealogy(s.as_columns())
+    o = ob.OraclePedigree.from_arrays(s.ind, s.father, s.mother, s.sex)
+    got, stats = gen.phi(ped, s.probands, return_stats=True)
+    assert_bit_equal(got, o.phi(s.probands))
+    assert stats["n_unique"] == len(s.probands)
+
+
+def test_deep_pedigree_rounding_schedule(gen, ob):
+    """Float32 stores are lossy and Float64 sums inexact here: only the
+    reference's rounding points and rank grouping reproduce the matrix."""
+    s = gen.synth.generate(16 * 60, 60, 16, alpha=0.2, overlap=1, seed=11)
+    ped = gen.genealogy(s.as_columns())
+    o = ob.OraclePedigree.from_arrays(s.ind, s.father, s.mother, s.sex)
+    want = o.phi(s.probands)
+    assert_bit_equal(gen.phi(ped, s.probands), want)
+    assert not np.array_equal(gen.phi(ped, s.probands, numerics="fp64"), want)
+    # 300 generations: values reach Float32 subnormals (gradual underflow must be kept)
+    s = gen.synth.generate(12 * 300, 300, 12, alpha=0.0, overlap=1, seed=3)
+    ped = gen.genealogy(s.as_columns())
+    o = ob.OraclePedigree.from_arrays(s.ind, s.father, s.mother, s.sex)
+    assert_bit_equal(gen.phi(ped, s.probands), o.phi(s.probands))
+
+
+def test_fp64_mode_is_exact_on_shallow_pedigrees(gen):
+    rng = np.random.default_rng(5)
+    rec = random_pedigree(rng, 400, 30, p_single=0.1, window=60)
+    ped = gen.genealogy(rec)
+    pro = rng.permutation(ped.ids)[:40]
+    got = gen.phi(ped, pro, numerics="fp64", dtype=np.float64)
+    ex = exact_kinship(ped.father, ped.mother)
+    rk = ped.rank_of(pro)
+    for a in range(0, 40, 3):
+        for b in range(40):
+            v = ex(int(rk[a]), int(rk[b]))
+            if v.denominator.bit_length() <= 50:
+                assert got[a, b] == float(v)
+
+
+def test_edge_cases(gen, ob):
+    ped = gen.genealogy(gen.geneaJi)
+    assert gen.phi(ped, []).shape == (0, 0)
+    assert gen.phi(ped, [17]).tolist() == [[0.5]]
+    assert_bit_equal(gen.phi(ped, [1, 2, 1, 29, 2]), GENEAJI_PHI)
+    assert_bit_equal(gen.phi(ped, [29, 1]), GENEAJI_PHI[np.ix_([2, 0], [2, 0])])
+    o = ob.OraclePedigree.from_csv(gen.geneaJi)
+    for sel in ([1, 4, 17], [17, 19, 20, 23, 25, 26], list(range(1, 30)), [9, 11]):
+        assert_bit_equal(gen.phi(ped, sel), o.phi(np.array(sel)))
+    with pytest.raises(KeyError):
+        gen.phi(ped, [1, 999])
+    # a 1000-child sibship (split into couples of <= 32 members) and 3000 unrelated founders
+    n = 3002 + 1000
+    father = np.full(n, -1, np.int32); mother = np.full(n, -1, np.int32)
+    father[3002:] = 0; mother[3002:] = 1
+    pro = np.arange(2, n, dtype=np.int32)
+    got, _ = gen.phi_arrays(father, mother, pro)
+    want, _ = ob.phi_ranks(father, mother, pro)
+    assert_bit_equal(got, want)
+
+
+def test_out_dtype_and_mean(gen):
+    ped = gen.genealogy(gen.genea140)
+    plan = gen.Plan(ped.father, ped.mother, ped.rank_of(gen.pro(ped)))
+    eng = gen.Engine(plan)
+    eng.run(time_layers=True)
+    f32 = eng.fetch()
+    f64 = eng.fetch(dtype=np.float64)
+    assert_bit_equal(f64, f32.astype(np.float64))
+    mean = eng.phi_mean()
+    want = (f64.sum() - np.trace(f64)) / (140 * 139)
+    assert abs(mean - want) < 1e-15
+    assert abs(mean - 0.0011437357710109676) < 1e-15
+    infos = [eng.layer_info(t) for t in range(plan.n_layers)]
+    assert all(i["ms_intra"] > 0 for i in infos)
+    eng.close()
+
+
+def test_full_size_properties(gen):
+    """C3 at 1/4 scale (10k individuals per generation): too big for the oracle in a test,
+    checked through size-independent properties."""
+    s = gen.synth.config("C3", 0.25)
+    ped = gen.genealogy(s.as_columns())
+    a, stats = gen.phi(ped, s.probands, return_stats=True)
+    b = gen.phi(ped, s.probands)
+    assert_bit_equal(a, b)                                         # deterministic
+    assert np.array_equal(a, a.T)                                  # symmetric
+    d = np.diag(a)
+    assert (d >= 0.5).all() and (d < 1).all() and (a >= 0).all() and (a <= d[:, None] + 1e-7).all()
+    # full siblings among the probands have identical kinship with everybody else
+    rk = ped.rank_of(s.probands)
+    key = ped.father[rk].astype(np.int64) * (len(ped) + 1) + ped.mother[rk]
+    order = np.argsort(key, kind="stable")
+    same = np.nonzero(key[order][1:] == key[order][:-1])[0]
+    assert len(same) > 10
+    for q in same[:200]:
+        i, j = order[q], order[q + 1]
+        mask = np.ones(len(rk), bool); mask[[i, j]] = False
+        assert np.array_equal(a[i, mask], a[j, mask])
+    # the diagonal is 1/2 (1 + kinship of the parents): check through a second run that
+    # asks for the parents themselves (fp64 storage so both runs are exact to ~2^-40)
+    sub = s.probands[:50]
+    parents = np.unique(np.concatenate([s.father[sub - 1], s.mother[sub - 1]]))
+    pp = gen.phi(ped, parents, numerics="fp64", dtype=np.float64)
+    dd = gen.phi(ped, sub, numerics="fp64", dtype=np.float64)
+    pos = {int(x): k for k, x in enumerate(parents)}
+    for k, x in enumerate(sub):
+        f, m = pos[int(s.father[x - 1])], pos[int(s.mother[x - 1])]
+        assert abs(dd[k, k] - 0.5 * (1 + pp[f, m])) < 1e-12
