@@ -1,0 +1,93 @@
+# GenLibCUDA.jl -- the `ccall` shim a GenLib.jl maintainer would add so that
+# `gen.phi(ped)` / `gen.phi(ped, probandIDs)` run on libgenlib_cuda.so (B200).
+#
+# NOT EXECUTED in this repository's CI: Julia is not installed in the build image
+# (SURVEY.md F6).  The same C ABI is exercised through Python ctypes by tests/.
+#
+# It keeps the reference's signature and return type (src/compute.jl:233-304):
+#     phi(pedigree::Pedigree, probandIDs::Vector{Int} = pro(pedigree);
+#         verbose::Bool = false, compute::Bool = true) -> Matrix{Float32}
+# There is no CPU fallback: if the library or a CUDA device is missing, it throws.
+module GenLibCUDA
+
+import GenLib
+using Libdl
+
+const libgenlib = Ref{String}(get(ENV, "GENLIB_CUDA_LIB", "libgenlib_cuda.so"))
+
+struct LayerInfo            # genlib_layer_info, include/genlib_cuda.h
+    n_new::Int32; n_fam::Int32; live_before::Int32; carried::Int32
+    ref_founders::Int32; ref_probands::Int32; ref_both::Int32; reserved::Int32
+    alg_elems::Float64; ms_cross::Float64; ms_intra::Float64
+end
+
+struct Stats                # genlib_stats
+    n_unique::Int32; n_layers::Int32; row_updates::Int64; capacity::Int64; device_bytes::Int64
+    alg_bytes::Float64; ms_plan::Float64; ms_upload::Float64; ms_kernels::Float64; ms_fetch::Float64
+    h2d_bytes::Int64; d2h_bytes::Int64; kernel_launches::Int32; reserved::Int32
+end
+
+function check(status::Cint)
+    status == 0 && return
+    msg = unsafe_string(ccall((:genlib_last_error, libgenlib[]), Cstring, ()))
+    status == 2 && throw(KeyError(msg))            # same exception as pedigree[ID] (src/create.jl:70)
+    status == 5 && throw(OutOfMemoryError())
+    error("libgenlib_cuda status $status: $msg")
+end
+
+"""Flatten a `Pedigree` into 0-based parent ranks (iteration order is rank order,
+src/create.jl:234-254)."""
+function flatten(pedigree::GenLib.Pedigree)
+    n = length(pedigree)
+    father = Vector{Int32}(undef, n)
+    mother = Vector{Int32}(undef, n)
+    for individual in values(pedigree)
+        r = individual.rank
+        father[r] = isnothing(individual.father) ? Int32(-1) : Int32(individual.father.rank - 1)
+        mother[r] = isnothing(individual.mother) ? Int32(-1) : Int32(individual.mother.rank - 1)
+    end
+    father, mother
+end
+
+function phi(pedigree::GenLib.Pedigree, probandIDs::Vector{Int} = GenLib.pro(pedigree);
+             verbose::Bool = false, compute::Bool = true, numerics::Symbol = :reference,
+             device::Integer = -1)
+    father, mother = flatten(pedigree)
+    probands = Int32[pedigree[ID].rank - 1 for ID in probandIDs]      # KeyError on unknown ID
+    plan = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:genlib_plan_create, libgenlib[]), Cint,
+                (Int32, Ptr{Int32}, Ptr{Int32}, Int32, Ptr{Int32}, Int32, Ptr{Ptr{Cvoid}}),
+                length(father), father, mother, length(probands), probands, 1, plan))
+    try
+        layers = ccall((:genlib_plan_n_layers, libgenlib[]), Int32, (Ptr{Cvoid},), plan[])
+        if verbose || !compute                                         # src/compute.jl:253-262
+            for k in 1:layers-1
+                info = Ref{LayerInfo}()
+                check(ccall((:genlib_plan_layer_info, libgenlib[]), Cint,
+                            (Ptr{Cvoid}, Int32, Ref{LayerInfo}), plan[], k, info))
+                println("Step $k of $(layers-1): $(info[].ref_founders) founders, " *
+                        "$(info[].ref_probands) probands, $(info[].ref_both) both.")
+            end
+        end
+        compute || return nothing                                      # src/compute.jl:264-266
+        n = ccall((:genlib_plan_n_unique, libgenlib[]), Int32, (Ptr{Cvoid},), plan[])
+        ϕ = Matrix{Float32}(undef, n, n)                               # symmetric: layout-free
+        n == 0 && return ϕ
+        engine = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:genlib_engine_create, libgenlib[]), Cint,
+                    (Ptr{Cvoid}, Cint, Cint, Ptr{Ptr{Cvoid}}),
+                    plan[], numerics === :fp64 ? 1 : 0, device, engine))
+        try
+            check(ccall((:genlib_engine_run, libgenlib[]), Cint, (Ptr{Cvoid}, Cint), engine[], 0))
+            GC.@preserve ϕ check(ccall((:genlib_engine_fetch, libgenlib[]), Cint,
+                                       (Ptr{Cvoid}, Ptr{Cvoid}, Cint), engine[], ϕ, 0))
+        finally
+            ccall((:genlib_engine_destroy, libgenlib[]), Cvoid, (Ptr{Cvoid},), engine[])
+        end
+        return ϕ
+    finally
+        ccall((:genlib_plan_destroy, libgenlib[]), Cvoid, (Ptr{Cvoid},), plan[])
+    end
+end
+
+end # module
