@@ -53,7 +53,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)],
+                                          "-lms", "50", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -152,7 +152,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C3", choices=["C3", "C4", "C5", "genea140"])
@@ -183,20 +183,27 @@ def main():
     for _ in range(max(args.warmup, 3)):
         eng.run()
     K = args.steps
-    cross_ms, intra_ms, step_ms = [], [], []
+    cross_ms, couple_ms, expand_ms, step_ms = [], [], [], []
     with ClockSampler(local) as clocks:
+        time.sleep(0.6)                      # let nvidia-smi start sampling
+        n0 = len(clocks.rows)
+        while len(clocks.rows) == n0 and clocks.proc and time.time() < t0 + 60:
+            eng.run()                        # keep the GPU under load until the first sample lands
+        clocks.rows.clear()
         t0 = time.time()
         for _ in range(K):
             step_ms.append(eng.run(time_layers=True))
             infos = [eng.layer_info(t) for t in range(plan.n_layers)]
             cross_ms.append([i["ms_cross"] for i in infos])
-            intra_ms.append([i["ms_intra"] for i in infos])
+            couple_ms.append([i["ms_couple"] for i in infos])
+            expand_ms.append([i["ms_expand"] for i in infos])
         wall_ms = (time.time() - t0) * 1e3
     stats = eng.stats()
     total_ms = float(np.sum(step_ms))
     value = rows * K / (total_ms * 1e-3)
     infos = plan.layers()
-    cross_ms, intra_ms = np.array(cross_ms), np.array(intra_ms)
+    cross_ms, couple_ms, expand_ms = np.array(cross_ms), np.array(couple_ms), np.array(expand_ms)
+    intra_ms = couple_ms + expand_ms
     # dominant kernel: cross_kernel.  Algorithmic bytes per launch = s * 4 n L.
     cross_bytes = np.array([esize * 4.0 * i["n_new"] * i["live_before"] for i in infos])
     intra_bytes = np.array([esize * 3.0 * i["n_new"] ** 2 for i in infos])
@@ -212,14 +219,16 @@ def main():
                 "avg_launch_ms": float(cross_ms[:, launched].mean()) if launched.any() else 0.0,
                 "alg_bytes_per_launch": float(cross_bytes[launched].mean()) if launched.any() else 0.0,
                 "share_of_step": c_t / (total_ms * 1e-3),
-                "intra_kernel": {"achieved": intra_bytes.sum() * K / i_t / 1e9 if i_t > 0 else 0.0,
-                                 "share_of_step": i_t / (total_ms * 1e-3)},
+                "intra_kernels": {"achieved": intra_bytes.sum() * K / i_t / 1e9 if i_t > 0 else 0.0,
+                                  "share_of_step": i_t / (total_ms * 1e-3),
+                                  "couple_share": float(couple_ms.sum() / total_ms),
+                                  "expand_share": float(expand_ms.sum() / total_ms)},
                 "whole_step": {"achieved": whole, "frac": whole / peak,
                                "frac_of_8TBs_nominal": whole / 8000.0}}
     if args.layers_json:
         with open(args.layers_json, "w") as fh:
-            json.dump([{**i, "ms_cross": float(cross_ms[:, t].mean()), "ms_intra": float(intra_ms[:, t].mean())}
-                       for t, i in enumerate(infos)], fh, indent=1)
+            json.dump([{**i, "ms_cross": float(cross_ms[:, t].mean()), "ms_couple": float(couple_ms[:, t].mean()),
+                        "ms_expand": float(expand_ms[:, t].mean())} for t, i in enumerate(infos)], fh, indent=1)
     eng.close()
 
     # ---- end to end: the public call with host buffers, pinned output ----
@@ -231,7 +240,7 @@ def main():
         _, st = gen.phi_arrays(ped.father, ped.mother, ranks, numerics=args.numerics, device=local,
                                out=pinned.array)
         dt = time.time() - t0
-        if it > 0:
+        if it > 0 or args.e2e_steps == 0:
             e2e_t.append(dt)
         h2d = st["h2d_bytes"] + ped.father.nbytes + ped.mother.nbytes + ranks.nbytes
         d2h = st["d2h_bytes"]

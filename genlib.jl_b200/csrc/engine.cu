@@ -79,7 +79,9 @@ struct genlib_engine {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     void *A = nullptr;
     double *Rt = nullptr;
-    DevBuf<int32_t> mem_ind, mem_slot, mem_fam, fam_pf, fam_pm, fam_start, mt_min, mt_max, pro_slot;
+    void *V = nullptr, *Dg = nullptr;      // couple matrix and couple diagonal of the current layer
+    DevBuf<int32_t> mem_ind, mem_slot, mem_fam, fam_pf, fam_pm, fam_start, fam_ncol, mt_min, mt_max, mt_fam0,
+        mt_nfam, pro_slot;
     DevBuf<uint8_t> flags;
     DevBuf<double> acc;
     std::vector<genlib_layer_info> info;
@@ -91,6 +93,8 @@ struct genlib_engine {
         for (auto e : events) cudaEventDestroy(e);
         if (A) cudaFree(A);
         if (Rt) cudaFree(Rt);
+        if (V) cudaFree(V);
+        if (Dg) cudaFree(Dg);
         if (stream) cudaStreamDestroy(stream);
         if (copy_stream) cudaStreamDestroy(copy_stream);
     }
@@ -98,12 +102,17 @@ struct genlib_engine {
 
 namespace {
 
+size_t plan_index_bytes(const Plan &P) {
+    return (P.mem_ind.size() * 3 + P.fam_pf.size() * 3 + P.fam_start.size() + P.mtile_minrank.size() * 4 +
+            P.pro_slot.size()) * sizeof(int32_t);
+}
+
 size_t engine_bytes(const Plan &P, int numerics) {
     const size_t es = numerics == GENLIB_NUMERICS_FP64 ? 8 : 4;
     size_t b = (size_t)P.capacity * (size_t)P.capacity * es;
     b += P.rt_elems_max * sizeof(double);
-    b += (P.mem_ind.size() * 3 + P.fam_pf.size() * 2 + P.fam_start.size() + P.mtile_minrank.size() * 2 +
-          P.pro_slot.size()) * sizeof(int32_t);
+    b += (P.v_elems_max + P.fam_pf.size()) * es;
+    b += plan_index_bytes(P);
     b += P.flags.size();
     return b;
 }
@@ -118,7 +127,10 @@ LayerArgs layer_args(const genlib_engine &E, int t) {
     a.fam_pf = E.fam_pf.p + L.fam_off; a.fam_pm = E.fam_pm.p + L.fam_off;
     a.fam_start = E.fam_start.p + L.fam_off + t;
     a.flags = E.flags.p + L.flag_off;
+    a.fam_ncol = E.fam_ncol.p + L.fam_off;
     a.mt_minrank = E.mt_min.p + L.mtile_off; a.mt_maxrank = E.mt_max.p + L.mtile_off;
+    a.mt_fam0 = E.mt_fam0.p + L.mtile_off; a.mt_nfam = E.mt_nfam.p + L.mtile_off;
+    a.n_mtiles = L.n_mtiles;
     return a;
 }
 
@@ -128,9 +140,10 @@ int launch_layers(genlib_engine &E, bool timed) {
     T *A = static_cast<T *>(E.A);
     const int64_t ld = P.capacity;
     const size_t cross_smem = (size_t)kFTile * kSRStride * sizeof(double);
-    const size_t intra_smem = sizeof(IntraSmem<T>);
+    const size_t expand_smem = sizeof(ExpandSmem<T>);
     CU(cudaFuncSetAttribute(cross_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cross_smem));
-    CU(cudaFuncSetAttribute(intra_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)intra_smem));
+    CU(cudaFuncSetAttribute(expand_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem));
+    T *V = static_cast<T *>(E.V), *Dg = static_cast<T *>(E.Dg);
     int launches = 0;
     size_t ev = 0;
     for (int t = 0; t < (int)P.layers.size(); t++) {
@@ -146,10 +159,15 @@ int launch_layers(genlib_engine &E, bool timed) {
         }
         if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
         {
-            const long long nt = L.n_mtiles;
-            const long long pairs = nt * (nt + 1) / 2;
-            if (pairs > 0x7fffffffLL) return fail(GENLIB_EINVAL, "layer too wide for one intra launch");
-            intra_kernel<T><<<(unsigned)pairs, kThreads, intra_smem, E.stream>>>(A, ld, E.Rt, a);
+            dim3 grid((unsigned)((L.nf_pad + kCChunk - 1) / kCChunk), (unsigned)((L.n_fam + kThreads / 32 - 1) / (kThreads / 32)));
+            couple_kernel<T><<<grid, kThreads, 0, E.stream>>>(A, ld, E.Rt, V, Dg, a);
+            launches++;
+        }
+        if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
+        {
+            if (L.n_mtiles > 65535) return fail(GENLIB_EINVAL, "layer too wide for one expand launch");
+            dim3 grid((unsigned)((L.n_mtiles + kJChunk - 1) / kJChunk), (unsigned)L.n_mtiles);
+            expand_kernel<T><<<grid, kThreads, expand_smem, E.stream>>>(A, ld, V, Dg, a);
             launches++;
         }
         if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
@@ -331,28 +349,32 @@ int genlib_engine_create(const genlib_plan *plan, int numerics, int device, genl
     CU(cudaStreamCreateWithFlags(&E->copy_stream, cudaStreamNonBlocking));
     CU(cudaMalloc(&E->A, std::max<size_t>((size_t)P.capacity * (size_t)P.capacity * E->esize, 16)));
     CU(cudaMalloc(&E->Rt, std::max<size_t>(P.rt_elems_max * sizeof(double), 16)));
+    CU(cudaMalloc(&E->V, std::max<size_t>(P.v_elems_max * E->esize, 16)));
+    CU(cudaMalloc(&E->Dg, std::max<size_t>(P.fam_pf.size() * E->esize, 16)));
     CU(E->mem_ind.upload(P.mem_ind, E->stream));
     CU(E->mem_slot.upload(P.mem_slot, E->stream));
     CU(E->mem_fam.upload(P.mem_fam, E->stream));
     CU(E->fam_pf.upload(P.fam_pf, E->stream));
     CU(E->fam_pm.upload(P.fam_pm, E->stream));
     CU(E->fam_start.upload(P.fam_start, E->stream));
+    CU(E->fam_ncol.upload(P.fam_ncol, E->stream));
     CU(E->mt_min.upload(P.mtile_minrank, E->stream));
     CU(E->mt_max.upload(P.mtile_maxrank, E->stream));
+    CU(E->mt_fam0.upload(P.mtile_fam0, E->stream));
+    CU(E->mt_nfam.upload(P.mtile_nfam, E->stream));
     CU(E->pro_slot.upload(P.pro_slot, E->stream));
     CU(E->flags.upload(P.flags, E->stream));
     CU(E->acc.alloc(2));
     CU(cudaStreamSynchronize(E->stream));
     E->info.resize(P.layers.size());
     for (size_t t = 0; t < P.layers.size(); t++) fill_info(P.layers[t], &E->info[t]);
-    E->events.resize(P.layers.size() * 3 + 2);
+    E->events.resize(P.layers.size() * 4 + 2);
     for (auto &e : E->events) CU(cudaEventCreate(&e));
     genlib_stats &s = E->stats;
     s.n_unique = P.n_unique; s.n_layers = (int32_t)P.layers.size(); s.row_updates = P.row_updates;
     s.capacity = P.capacity; s.device_bytes = (int64_t)need; s.alg_bytes = P.alg_elems * (double)E->esize;
     s.ms_plan = plan->ms_plan; s.ms_upload = now_ms() - t0;
-    s.h2d_bytes = (int64_t)((P.mem_ind.size() * 3 + P.fam_pf.size() * 2 + P.fam_start.size() +
-                             P.mtile_minrank.size() * 2 + P.pro_slot.size()) * sizeof(int32_t) + P.flags.size());
+    s.h2d_bytes = (int64_t)(plan_index_bytes(P) + P.flags.size());
     *out = E.release();
     return GENLIB_OK;
 }
@@ -386,11 +408,12 @@ int genlib_engine_run(genlib_engine *eng, int time_layers) {
         for (size_t t = 0; t < E.info.size(); t++) {
             if (E.info[t].n_new == 0) continue;
             if (E.layer_limit >= 0 && (int32_t)t >= E.layer_limit) break;
-            float a = 0, b = 0;
+            float a = 0, b = 0, c = 0;
             CU(cudaEventElapsedTime(&a, E.events[ev], E.events[ev + 1]));
             CU(cudaEventElapsedTime(&b, E.events[ev + 1], E.events[ev + 2]));
-            ev += 3;
-            E.info[t].ms_cross = a; E.info[t].ms_intra = b;
+            CU(cudaEventElapsedTime(&c, E.events[ev + 2], E.events[ev + 3]));
+            ev += 4;
+            E.info[t].ms_cross = a; E.info[t].ms_couple = b; E.info[t].ms_expand = c;
         }
     }
     E.ran = true;

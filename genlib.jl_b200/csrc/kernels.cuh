@@ -9,14 +9,15 @@
 //                 for every couple F of the layer and every live column p; written
 //                   - rounded, as the rows/columns (new member x carried individual), and
 //                   - unrounded fp64, transposed, into the scratch block Rt[p, F].
-//   intra_kernel  V[F, G] = 1/2 Rt[f_F, G] + 1/2 Rt[m_F, G]         (compute.jl:130-147)
+//   couple_kernel V[F, G] = 1/2 Rt[f_F, G] + 1/2 Rt[m_F, G]         (compute.jl:130-147)
 //                 = the kinship of a member of F with a member of G when the F member has
-//                 the larger rank (it is "climbed first"); expanded to members, with the
-//                 diagonal 1/2 + 1/2 Psi[f, m] (compute.jl:148-155).
+//                 the larger rank (it is "climbed first"); plus the diagonal value
+//                 1/2 + 1/2 Psi[f, m] of the couple's members (compute.jl:148-155).
+//   expand_kernel couples -> members: entry (i, j) = V[F_i, G_j] or V[G_j, F_i] by rank.
 //
 // Arithmetic is binary64 in the reference's grouping; storage type T is float
 // (GENLIB_NUMERICS_REFERENCE: one RN32 per step, like compute.jl:296) or double.
-// Both kernels are HBM-bound streaming kernels: 128-bit loads of contiguous row
+// All three are HBM-bound streaming kernels: 128-bit loads of contiguous row
 // segments, shared-memory tile transposes, coalesced stores; no tensor cores.
 #pragma once
 #include <cuda_runtime.h>
@@ -31,7 +32,9 @@ struct LayerArgs {
     const int32_t *mem_ind, *mem_slot, *mem_fam;
     const int32_t *fam_pf, *fam_pm, *fam_start;
     const uint8_t *flags;
-    const int32_t *mt_minrank, *mt_maxrank;
+    const int32_t *fam_ncol;
+    const int32_t *mt_minrank, *mt_maxrank, *mt_fam0, *mt_nfam;
+    int32_t n_mtiles;
 };
 
 constexpr int kThreads = 256;
@@ -107,7 +110,7 @@ cross_kernel(T *__restrict__ A, int64_t ld, double *__restrict__ Rt, LayerArgs L
         if (carried_here) {
             // rows of the new members against this tile's columns (rounded once, compute.jl:296).
             // Columns that are not carried receive values nobody reads; new x new is
-            // rewritten by intra_kernel afterwards.
+            // rewritten by expand_kernel afterwards.
             const int F = F0 + warp * 4 + q;
             if (F < L.n_fam) {
                 const int m1 = L.fam_start[F + 1];
@@ -138,99 +141,146 @@ cross_kernel(T *__restrict__ A, int64_t ld, double *__restrict__ Rt, LayerArgs L
 }
 
 // =====================================================================================
-// intra_kernel: one CTA per pair (I >= J) of member tiles (kMTile members each).
+// couple_kernel: V[F, G] = 1/2 Rt[f_F, G] + 1/2 Rt[m_F, G], one warp per couple row F,
+// columns restricted to the prefix [0, fam_ncol[F]) that can be selected at all.
+// Also the diagonal value of the couple's members, Dg[F] = 1/2 + 1/2 Psi[f_F, m_F]
+// (compute.jl:148-155).  grid (column chunks, row groups of 8).
 // =====================================================================================
-template <typename T>
-struct IntraSmem {
-    T Vab[kMTile * kVStride];   // [family of I][family of J]: the I member is climbed first
-    T Vba[kMTile * kVStride];   // [family of J][family of I]: the J member is climbed first
-    T diag[kMTile];
-    int32_t fam[2][kMTile], rank[2][kMTile], slot[2][kMTile];
-};
+constexpr int kCChunk = 1024;
+
+template <typename T> struct Pair;
+template <> struct Pair<float> { using type = float2; };
+template <> struct Pair<double> { using type = double2; };
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
-intra_kernel(T *__restrict__ A, int64_t ld, const double *__restrict__ Rt, LayerArgs L) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    IntraSmem<T> &S = *reinterpret_cast<IntraSmem<T> *>(smem_raw);
+couple_kernel(const T *__restrict__ A, int64_t ld, const double *__restrict__ Rt, T *__restrict__ V,
+              T *__restrict__ Dg, LayerArgs L) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // linear index over the lower triangle -> (I, J), I >= J
-    const long long t = blockIdx.x;
-    int I = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-    while ((long long)I * (I + 1) / 2 > t) I--;
-    while ((long long)(I + 1) * (I + 2) / 2 <= t) I++;
-    const int J = (int)(t - (long long)I * (I + 1) / 2);
-    const int mI0 = I * kMTile, mJ0 = J * kMTile;
-    const int cI = min(kMTile, L.n_new - mI0), cJ = min(kMTile, L.n_new - mJ0);
-
-    if (threadIdx.x < 2 * kMTile) {
-        const int side = threadIdx.x / kMTile, q = threadIdx.x % kMTile;
-        const int c = side ? cJ : cI, m = (side ? mJ0 : mI0) + min(q, c - 1);
-        S.fam[side][q] = L.mem_fam[m];
-        S.rank[side][q] = L.mem_ind[m];
-        S.slot[side][q] = L.mem_slot[m];
-    }
-    __syncthreads();
-    const int fI0 = S.fam[0][0], nfI = S.fam[0][cI - 1] - fI0 + 1;
-    const int fJ0 = S.fam[1][0], nfJ = S.fam[1][cJ - 1] - fJ0 + 1;
-    const bool same = (I == J);
-    // rank ranges decide which orientation can occur at all
-    const bool need_ab = same || L.mt_maxrank[I] > L.mt_minrank[J];
-    const bool need_ba = !same && L.mt_maxrank[J] > L.mt_minrank[I];
-
-    if (need_ab) {
-        for (int f = warp; f < nfI; f += kThreads / 32) {
-            const int pf = L.fam_pf[fI0 + f], pm = L.fam_pm[fI0 + f];
-            const double *rf = Rt + (size_t)max(pf - L.rt_lo, 0) * L.nf_pad + fJ0;
-            const double *rm = Rt + (size_t)max(pm - L.rt_lo, 0) * L.nf_pad + fJ0;
-            for (int g = lane; g < nfJ; g += 32) {
-                const double a = pf >= 0 ? __ldg(rf + g) : 0.0;
-                const double b = pm >= 0 ? __ldg(rm + g) : 0.0;
-                S.Vab[f * kVStride + g] = (T)half_sum(a, b);
-            }
-        }
-    }
-    if (need_ba) {
-        for (int g = warp; g < nfJ; g += kThreads / 32) {
-            const int pf = L.fam_pf[fJ0 + g], pm = L.fam_pm[fJ0 + g];
-            const double *rf = Rt + (size_t)max(pf - L.rt_lo, 0) * L.nf_pad + fI0;
-            const double *rm = Rt + (size_t)max(pm - L.rt_lo, 0) * L.nf_pad + fI0;
-            for (int f = lane; f < nfI; f += 32) {
-                const double a = pf >= 0 ? __ldg(rf + f) : 0.0;
-                const double b = pm >= 0 ? __ldg(rm + f) : 0.0;
-                S.Vba[g * kVStride + f] = (T)half_sum(a, b);
-            }
-        }
-    }
-    if (same && threadIdx.x < nfI) {
-        // compute.jl:148-155: 1/2 + 1/2 Psi[father, mother] when both parents are known
-        const int pf = L.fam_pf[fI0 + threadIdx.x], pm = L.fam_pm[fI0 + threadIdx.x];
+    const int F = blockIdx.y * (kThreads / 32) + warp;
+    if (F >= L.n_fam) return;
+    const int pf = L.fam_pf[F], pm = L.fam_pm[F];
+    if (blockIdx.x == 0 && lane == 0) {
         double v = 0.5;
         if (pf >= 0 && pm >= 0) v = fma(0.5, (double)A[(int64_t)pf * ld + pm], 0.5);
-        S.diag[threadIdx.x] = (T)v;
+        Dg[F] = (T)v;
     }
-    __syncthreads();
+    const int ncol = L.fam_ncol[F];
+    const int c0 = blockIdx.x * kCChunk;
+    if (c0 >= ncol) return;
+    const int cend = min(c0 + kCChunk, (ncol + 1) & ~1);
+    const double2 *rf = reinterpret_cast<const double2 *>(Rt + (size_t)max(pf - L.rt_lo, 0) * L.nf_pad);
+    const double2 *rm = reinterpret_cast<const double2 *>(Rt + (size_t)max(pm - L.rt_lo, 0) * L.nf_pad);
+    typename Pair<T>::type *out = reinterpret_cast<typename Pair<T>::type *>(V + (size_t)F * L.nf_pad);
+    const double2 zero = make_double2(0.0, 0.0);
+#pragma unroll 4
+    for (int c = c0 + 2 * lane; c < cend; c += 64) {
+        const double2 a = pf >= 0 ? __ldg(rf + (c >> 1)) : zero;
+        const double2 b = pm >= 0 ? __ldg(rm + (c >> 1)) : zero;
+        typename Pair<T>::type v;
+        v.x = (T)half_sum(a.x, b.x);
+        v.y = (T)half_sum(a.y, b.y);
+        out[c >> 1] = v;
+    }
+}
 
-    // ---- expand couples to members: rows of I ----
-    for (int il = warp; il < cI; il += kThreads / 32) {
-        const int f = S.fam[0][il] - fI0, ri = S.rank[0][il];
-        T *row = A + (int64_t)S.slot[0][il] * ld;
-        for (int jl = lane; jl < cJ; jl += 32) {
-            const int g = S.fam[1][jl] - fJ0, rj = S.rank[1][jl];
-            T v;
-            if (same) v = (ri == rj) ? S.diag[f] : (ri > rj ? S.Vab[f * kVStride + g] : S.Vab[g * kVStride + f]);
-            else v = ri > rj ? S.Vab[f * kVStride + g] : S.Vba[g * kVStride + f];
-            row[S.slot[1][jl]] = v;
-        }
+// =====================================================================================
+// expand_kernel: couples -> members.  CTA = one tile of kMTile member ROWS against
+// kJChunk consecutive tiles of kMTile member COLUMNS; every CTA writes only its own rows
+// (long contiguous segments), so the symmetric partner block is written by the CTA that
+// owns those rows -- no transposed stores.
+//   entry (i, j), i in couple F, j in couple G:  rank_i > rank_j ? V[F, G] : V[G, F]
+//   (compute.jl:130-147: the higher rank is climbed first);  i == j: Dg[F].
+// Thread t owns columns 4(t%16)..+3 of the column tile and rows t/16 + 16k.
+// =====================================================================================
+constexpr int kJChunk = 8;
+
+template <typename T>
+struct ExpandSmem {
+    T Vab[kMTile * kVStride];   // [couple of the row tile][couple of the column tile]
+    T Vba[kMTile * kVStride];   // [couple of the column tile][couple of the row tile]
+    int32_t famI[kMTile], rankI[kMTile], slotI[kMTile];
+    int32_t famJ[kMTile], rankJ[kMTile], slotJ[kMTile];
+};
+
+__device__ __forceinline__ void store_vec4(float *p, const float (&v)[4]) {
+    *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void store_vec4(double *p, const double (&v)[4]) {
+    reinterpret_cast<double2 *>(p)[0] = make_double2(v[0], v[1]);
+    reinterpret_cast<double2 *>(p)[1] = make_double2(v[2], v[3]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+expand_kernel(T *__restrict__ A, int64_t ld, const T *__restrict__ V, const T *__restrict__ Dg, LayerArgs L) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ExpandSmem<T> &S = *reinterpret_cast<ExpandSmem<T> *>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int I = blockIdx.y;
+    const int mI0 = I * kMTile;
+    const int cI = min(kMTile, L.n_new - mI0);
+    const int fI0 = L.mt_fam0[I], nfI = L.mt_nfam[I];
+    const int minI = L.mt_minrank[I], maxI = L.mt_maxrank[I];
+    if (threadIdx.x < kMTile) {
+        const int m = mI0 + min((int)threadIdx.x, cI - 1);
+        S.famI[threadIdx.x] = L.mem_fam[m] - fI0;
+        S.rankI[threadIdx.x] = L.mem_ind[m];
+        S.slotI[threadIdx.x] = L.mem_slot[m];
     }
-    // ---- and the symmetric block: rows of J ----
-    if (!same) {
-        for (int jl = warp; jl < cJ; jl += kThreads / 32) {
-            const int g = S.fam[1][jl] - fJ0, rj = S.rank[1][jl];
-            T *row = A + (int64_t)S.slot[1][jl] * ld;
-            for (int il = lane; il < cI; il += 32) {
-                const int f = S.fam[0][il] - fI0, ri = S.rank[0][il];
-                row[S.slot[0][il]] = ri > rj ? S.Vab[f * kVStride + g] : S.Vba[g * kVStride + f];
+    const int cg = threadIdx.x & 15, rg = threadIdx.x >> 4;
+    const int Jend = min(L.n_mtiles, (int)(blockIdx.x + 1) * kJChunk);
+    for (int J = blockIdx.x * kJChunk; J < Jend; J++) {
+        const int mJ0 = J * kMTile;
+        const int cJ = min(kMTile, L.n_new - mJ0);
+        const int fJ0 = L.mt_fam0[J], nfJ = L.mt_nfam[J];
+        const bool need_ab = maxI > L.mt_minrank[J];      // some row member outranks a column member
+        const bool need_ba = L.mt_maxrank[J] > minI;
+        __syncthreads();                                   // previous tile fully expanded
+        if (threadIdx.x >= kMTile && threadIdx.x < 2 * kMTile) {
+            const int q = threadIdx.x - kMTile;
+            const int m = mJ0 + min(q, cJ - 1);
+            S.famJ[q] = L.mem_fam[m] - fJ0;
+            S.rankJ[q] = L.mem_ind[m];
+            S.slotJ[q] = L.mem_slot[m];
+        }
+        if (need_ab) {
+            for (int f = warp; f < nfI; f += kThreads / 32) {
+                const T *src = V + (size_t)(fI0 + f) * L.nf_pad + fJ0;
+                for (int g = lane; g < nfJ; g += 32) S.Vab[f * kVStride + g] = __ldg(src + g);
+            }
+        }
+        if (need_ba) {
+            for (int g = warp; g < nfJ; g += kThreads / 32) {
+                const T *src = V + (size_t)(fJ0 + g) * L.nf_pad + fI0;
+                for (int f = lane; f < nfI; f += 32) S.Vba[g * kVStride + f] = __ldg(src + f);
+            }
+        }
+        __syncthreads();
+        const int j0 = 4 * cg;
+        if (j0 >= cJ) continue;
+        int gj[4], rj[4], sj[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { gj[k] = S.famJ[j0 + k]; rj[k] = S.rankJ[j0 + k]; sj[k] = S.slotJ[j0 + k]; }
+        const bool vec = (j0 + 3 < cJ) && ((sj[0] & 3) == 0) && sj[1] == sj[0] + 1 && sj[2] == sj[0] + 2 &&
+                         sj[3] == sj[0] + 3;
+#pragma unroll
+        for (int r = 0; r < kMTile / 16; r++) {
+            const int il = rg + 16 * r;
+            if (il >= cI) break;
+            const int f = S.famI[il], ri = S.rankI[il];
+            T *row = A + (int64_t)S.slotI[il] * ld;
+            T v[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (ri > rj[k]) v[k] = S.Vab[f * kVStride + gj[k]];
+                else if (ri < rj[k]) v[k] = S.Vba[gj[k] * kVStride + f];
+                else v[k] = Dg[fI0 + f];
+            }
+            if (vec) store_vec4(row + sj[0], v);
+            else {
+#pragma unroll
+                for (int k = 0; k < 4; k++) if (j0 + k < cJ) row[sj[k]] = v[k];
             }
         }
     }

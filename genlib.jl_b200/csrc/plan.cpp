@@ -213,6 +213,19 @@ int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t 
             P.fam_pf.push_back(father[x] >= 0 ? slot_of[father[x]] : -1);
             P.fam_pm.push_back(mother[x] >= 0 ? slot_of[mother[x]] : -1);
         }
+        // V[F, G] ("a member of F is climbed first", compute.jl:130-138) is read only when some
+        // member of F outranks some member of G.  Couples are ordered by their first (lowest
+        // rank) member, so those G form a prefix [0, fam_ncol[F]).
+        {
+            const int32_t *mi = P.mem_ind.data() + L.mem_off;
+            // minrank(G) increases with G; maxrank(F) does not, so search per row
+            std::vector<int32_t> minr((size_t)nf);
+            for (int32_t f = 0; f < nf; f++) minr[f] = mi[fstart[f]];
+            for (int32_t f = 0; f < nf; f++) {
+                const int32_t maxr = mi[fstart[f + 1] - 1];
+                P.fam_ncol.push_back((int32_t)(std::lower_bound(minr.begin(), minr.end(), maxr) - minr.begin()));
+            }
+        }
         // per member tile rank range (lets the intra kernel skip one orientation)
         L.n_mtiles = (nn + kMTile - 1) / kMTile;
         for (int32_t mt = 0; mt < L.n_mtiles; mt++) {
@@ -222,11 +235,15 @@ int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t 
                 lo = std::min(lo, x); hi = std::max(hi, x);
             }
             P.mtile_minrank.push_back(lo); P.mtile_maxrank.push_back(hi);
+            const int32_t q0 = mt * kMTile, q1 = std::min(nn, (mt + 1) * kMTile) - 1;
+            const int32_t f0 = P.mem_fam[L.mem_off + q0], f1 = P.mem_fam[L.mem_off + q1];
+            P.mtile_fam0.push_back(f0); P.mtile_nfam.push_back(f1 - f0 + 1);
         }
         L.alg_elems = 4.0 * nn * (double)L.live_before + 3.0 * (double)nn * nn;
         P.alg_elems += L.alg_elems;
         P.row_updates += nn;
         P.rt_elems_max = std::max(P.rt_elems_max, (size_t)L.rt_rows * (size_t)L.nf_pad);
+        P.v_elems_max = std::max(P.v_elems_max, (size_t)nf * (size_t)L.nf_pad);
 
         // ---- after the step: evicted slots become reusable from the next layer on ----
         if (!freed.empty()) {

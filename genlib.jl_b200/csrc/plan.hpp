@@ -36,7 +36,7 @@ struct Layer {
     size_t mem_off = 0;               // into mem_* arrays
     size_t fam_off = 0;               // into fam_pf / fam_pm; fam_start uses fam_off + layer index
     size_t flag_off = 0;              // into flags
-    size_t mtile_off = 0;             // into mtile_minrank / mtile_maxrank
+    size_t mtile_off = 0;             // into mtile_* arrays
     double alg_elems = 0;             // 4 n L + 3 n^2
 };
 
@@ -52,7 +52,10 @@ struct Plan {
     std::vector<int32_t> mem_ind, mem_slot, mem_fam;   // family-major order inside a layer
     std::vector<int32_t> fam_pf, fam_pm, fam_start;    // parents as slots (-1 = none)
     std::vector<uint8_t> flags;
-    std::vector<int32_t> mtile_minrank, mtile_maxrank;
+    std::vector<int32_t> fam_ncol;                     // couple row F needs V[F, 0 .. fam_ncol[F])
+    std::vector<int32_t> mtile_minrank, mtile_maxrank; // rank range of a member tile
+    std::vector<int32_t> mtile_fam0, mtile_nfam;       // family range of a member tile
+    size_t v_elems_max = 0;           // max over layers of n_fam * nf_pad
 };
 
 // Returns 0 or a GENLIB_E* status; `err` receives a message.

@@ -63,8 +63,9 @@ typedef struct genlib_layer_info {
     int32_t ref_both;     /* |cut[k] n cut[k+1]|, compute.jl:260                          */
     int32_t reserved;
     double alg_elems;     /* 4*n*L + 3*n^2; bytes = elems * sizeof(storage) */
-    double ms_cross;      /* device time of the cross-block kernel (when timed)          */
-    double ms_intra;      /* device time of the intra-layer kernel (when timed)          */
+    double ms_cross;      /* device time of cross_kernel (when timed)                    */
+    double ms_couple;     /* ... of couple_kernel                                        */
+    double ms_expand;     /* ... of expand_kernel                                        */
 } genlib_layer_info;
 
 typedef struct genlib_stats {

@@ -171,7 +171,7 @@ def test_out_dtype_and_mean(gen):
     assert abs(mean - want) < 1e-15
     assert abs(mean - 0.0011437357710109676) < 1e-15
     infos = [eng.layer_info(t) for t in range(plan.n_layers)]
-    assert all(i["ms_intra"] > 0 for i in infos)
+    assert all(i["ms_expand"] > 0 for i in infos)
     eng.close()
 
 
