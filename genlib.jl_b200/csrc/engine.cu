@@ -143,6 +143,8 @@ int launch_layers(genlib_engine &E, bool timed) {
     const size_t expand_smem = sizeof(ExpandSmem<T>);
     CU(cudaFuncSetAttribute(cross_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cross_smem));
     CU(cudaFuncSetAttribute(expand_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem));
+    CU(cudaFuncSetAttribute(cross_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CU(cudaFuncSetAttribute(expand_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     T *V = static_cast<T *>(E.V), *Dg = static_cast<T *>(E.Dg);
     int launches = 0;
     size_t ev = 0;

@@ -69,7 +69,7 @@ __device__ __forceinline__ double half_sum(double x, double y) { return fma(0.5,
 // owns columns 4l..4l+3 of the tile (one 128-bit load per parent row).
 // =====================================================================================
 template <typename T>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 cross_kernel(T *__restrict__ A, int64_t ld, double *__restrict__ Rt, LayerArgs L) {
     extern __shared__ double sR[];                       // [kFTile][kSRStride]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -195,12 +195,27 @@ couple_kernel(const T *__restrict__ A, int64_t ld, const double *__restrict__ Rt
 // =====================================================================================
 constexpr int kJChunk = 8;
 
+// cp.async (LDGSTS): global -> shared without register staging, so the next column tile
+// streams in while the current one is expanded.
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void *smem, const void *gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(s), "l"(gmem), "n"(BYTES));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
 template <typename T>
-struct ExpandSmem {
+struct ExpandStage {
     T Vab[kMTile * kVStride];   // [couple of the row tile][couple of the column tile]
     T Vba[kMTile * kVStride];   // [couple of the column tile][couple of the row tile]
-    int32_t famI[kMTile], rankI[kMTile], slotI[kMTile];
     int32_t famJ[kMTile], rankJ[kMTile], slotJ[kMTile];
+};
+template <typename T>
+struct ExpandSmem {
+    ExpandStage<T> st[2];
+    int4 metaI[kMTile];         // {couple - fI0, rank, slot, 0} of the row tile
 };
 
 __device__ __forceinline__ void store_vec4(float *p, const float (&v)[4]) {
@@ -212,77 +227,103 @@ __device__ __forceinline__ void store_vec4(double *p, const double (&v)[4]) {
 }
 
 template <typename T>
+__device__ __forceinline__ void expand_prefetch(ExpandStage<T> &B, const T *__restrict__ V, const LayerArgs &L,
+                                                int J, int fI0, int nfI, int minI, int maxI) {
+    const int mJ0 = J * kMTile;
+    const int cJ = min(kMTile, L.n_new - mJ0);
+    const int fJ0 = L.mt_fam0[J], nfJ = L.mt_nfam[J];
+    const int col = threadIdx.x & (kMTile - 1), row0 = threadIdx.x >> 6;      // 4 row phases
+    if (maxI > L.mt_minrank[J] && col < nfJ) {            // some row member outranks a column member
+        const T *src = V + (size_t)fI0 * L.nf_pad + fJ0 + col;
+#pragma unroll 4
+        for (int f = row0; f < nfI; f += kThreads / kMTile)
+            cp_async<sizeof(T)>(&B.Vab[f * kVStride + col], src + (size_t)f * L.nf_pad);
+    }
+    if (L.mt_maxrank[J] > minI && col < nfI) {
+        const T *src = V + (size_t)fJ0 * L.nf_pad + fI0 + col;
+#pragma unroll 4
+        for (int g = row0; g < nfJ; g += kThreads / kMTile)
+            cp_async<sizeof(T)>(&B.Vba[g * kVStride + col], src + (size_t)g * L.nf_pad);
+    }
+    if (threadIdx.x < kMTile) {
+        const int m = mJ0 + min((int)threadIdx.x, cJ - 1);
+        cp_async<4>(&B.famJ[threadIdx.x], L.mem_fam + m);
+        cp_async<4>(&B.rankJ[threadIdx.x], L.mem_ind + m);
+        cp_async<4>(&B.slotJ[threadIdx.x], L.mem_slot + m);
+    }
+}
+
+template <typename T>
 __global__ void __launch_bounds__(kThreads)
 expand_kernel(T *__restrict__ A, int64_t ld, const T *__restrict__ V, const T *__restrict__ Dg, LayerArgs L) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ExpandSmem<T> &S = *reinterpret_cast<ExpandSmem<T> *>(smem_raw);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int I = blockIdx.y;
     const int mI0 = I * kMTile;
     const int cI = min(kMTile, L.n_new - mI0);
     const int fI0 = L.mt_fam0[I], nfI = L.mt_nfam[I];
     const int minI = L.mt_minrank[I], maxI = L.mt_maxrank[I];
+    const int Jbeg = blockIdx.x * kJChunk, Jend = min(L.n_mtiles, Jbeg + kJChunk);
+    expand_prefetch(S.st[0], V, L, Jbeg, fI0, nfI, minI, maxI);
+    cp_async_commit();
     if (threadIdx.x < kMTile) {
         const int m = mI0 + min((int)threadIdx.x, cI - 1);
-        S.famI[threadIdx.x] = L.mem_fam[m] - fI0;
-        S.rankI[threadIdx.x] = L.mem_ind[m];
-        S.slotI[threadIdx.x] = L.mem_slot[m];
+        S.metaI[threadIdx.x] = make_int4(L.mem_fam[m] - fI0, L.mem_ind[m], L.mem_slot[m], 0);
     }
     const int cg = threadIdx.x & 15, rg = threadIdx.x >> 4;
-    const int Jend = min(L.n_mtiles, (int)(blockIdx.x + 1) * kJChunk);
-    for (int J = blockIdx.x * kJChunk; J < Jend; J++) {
-        const int mJ0 = J * kMTile;
-        const int cJ = min(kMTile, L.n_new - mJ0);
-        const int fJ0 = L.mt_fam0[J], nfJ = L.mt_nfam[J];
-        const bool need_ab = maxI > L.mt_minrank[J];      // some row member outranks a column member
-        const bool need_ba = L.mt_maxrank[J] > minI;
-        __syncthreads();                                   // previous tile fully expanded
-        if (threadIdx.x >= kMTile && threadIdx.x < 2 * kMTile) {
-            const int q = threadIdx.x - kMTile;
-            const int m = mJ0 + min(q, cJ - 1);
-            S.famJ[q] = L.mem_fam[m] - fJ0;
-            S.rankJ[q] = L.mem_ind[m];
-            S.slotJ[q] = L.mem_slot[m];
+    const int j0 = 4 * cg;
+    int buf = 0;
+    for (int J = Jbeg; J < Jend; J++, buf ^= 1) {
+        if (J + 1 < Jend) {
+            expand_prefetch(S.st[buf ^ 1], V, L, J + 1, fI0, nfI, minI, maxI);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
         }
-        if (need_ab) {
-            for (int f = warp; f < nfI; f += kThreads / 32) {
-                const T *src = V + (size_t)(fI0 + f) * L.nf_pad + fJ0;
-                for (int g = lane; g < nfJ; g += 32) S.Vab[f * kVStride + g] = __ldg(src + g);
-            }
-        }
-        if (need_ba) {
-            for (int g = warp; g < nfJ; g += kThreads / 32) {
-                const T *src = V + (size_t)(fJ0 + g) * L.nf_pad + fI0;
-                for (int f = lane; f < nfI; f += 32) S.Vba[g * kVStride + f] = __ldg(src + f);
-            }
-        }
-        __syncthreads();
-        const int j0 = 4 * cg;
-        if (j0 >= cJ) continue;
-        int gj[4], rj[4], sj[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) { gj[k] = S.famJ[j0 + k]; rj[k] = S.rankJ[j0 + k]; sj[k] = S.slotJ[j0 + k]; }
-        const bool vec = (j0 + 3 < cJ) && ((sj[0] & 3) == 0) && sj[1] == sj[0] + 1 && sj[2] == sj[0] + 2 &&
-                         sj[3] == sj[0] + 3;
-#pragma unroll
-        for (int r = 0; r < kMTile / 16; r++) {
-            const int il = rg + 16 * r;
-            if (il >= cI) break;
-            const int f = S.famI[il], ri = S.rankI[il];
-            T *row = A + (int64_t)S.slotI[il] * ld;
-            T v[4];
+        __syncthreads();                                   // tile J (and metaI) visible to everybody
+        const ExpandStage<T> &B = S.st[buf];
+        const int cJ = min(kMTile, L.n_new - J * kMTile);
+        if (j0 < cJ) {
+            const int fJ0 = L.mt_fam0[J];
+            int ab[4], ba[4], rj[4], sj[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                if (ri > rj[k]) v[k] = S.Vab[f * kVStride + gj[k]];
-                else if (ri < rj[k]) v[k] = S.Vba[gj[k] * kVStride + f];
-                else v[k] = Dg[fI0 + f];
+                const int g = B.famJ[j0 + k] - fJ0;
+                ab[k] = g; ba[k] = g * kVStride;
+                rj[k] = B.rankJ[j0 + k]; sj[k] = B.slotJ[j0 + k];
             }
-            if (vec) store_vec4(row + sj[0], v);
-            else {
+            const bool vec = (j0 + 3 < cJ) && ((sj[0] & 3) == 0) && sj[1] == sj[0] + 1 && sj[2] == sj[0] + 2 &&
+                             sj[3] == sj[0] + 3;
+            const int dj = (I == J) ? j0 : -8;             // tile-local column of the diagonal, if any
 #pragma unroll
-                for (int k = 0; k < 4; k++) if (j0 + k < cJ) row[sj[k]] = v[k];
+            for (int r = 0; r < kMTile / 16; r++) {
+                const int il = rg + 16 * r;
+                if (il < cI) {
+                    const int4 mi = S.metaI[il];           // couple, rank, slot
+                    const T *va = B.Vab + mi.x * kVStride;
+                    const T *vb = B.Vba + mi.x;
+                    T v[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const T a = va[ab[k]], b = vb[ba[k]];
+                        v[k] = mi.y > rj[k] ? a : b;       // the higher rank is climbed first
+                    }
+                    if ((unsigned)(il - dj) < 4u) {        // own diagonal entry (compute.jl:148-155)
+                        const T d = Dg[fI0 + mi.x];
+#pragma unroll
+                        for (int k = 0; k < 4; k++) if (il - dj == k) v[k] = d;
+                    }
+                    T *row = A + (int64_t)mi.z * ld;
+                    if (vec) store_vec4(row + sj[0], v);
+                    else {
+#pragma unroll
+                        for (int k = 0; k < 4; k++) if (j0 + k < cJ) row[sj[k]] = v[k];
+                    }
+                }
             }
         }
+        __syncthreads();                                   // done with st[buf] before it is refilled
     }
 }
 
