@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -79,8 +80,8 @@ struct genlib_engine {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     void *A = nullptr;
     double *Rt = nullptr;
-    void *V = nullptr, *Dg = nullptr;      // couple matrix and couple diagonal of the current layer
-    DevBuf<int32_t> mem_ind, mem_slot, mem_fam, fam_pf, fam_pm, fam_start, fam_ncol, mt_min, mt_max, mt_fam0,
+    void *V = nullptr, *Vt = nullptr, *Dg = nullptr;   // couple matrix, its transpose, couple diagonal (current layer)
+    DevBuf<int32_t> mem_ind, mem_slot, mem_fam, fam_pf, fam_pm, fam_start, fam_minrank, fam_maxrank, mt_min, mt_max, mt_fam0,
         mt_nfam, pro_slot;
     DevBuf<uint8_t> flags;
     DevBuf<double> acc;
@@ -94,6 +95,7 @@ struct genlib_engine {
         if (A) cudaFree(A);
         if (Rt) cudaFree(Rt);
         if (V) cudaFree(V);
+        if (Vt) cudaFree(Vt);
         if (Dg) cudaFree(Dg);
         if (stream) cudaStreamDestroy(stream);
         if (copy_stream) cudaStreamDestroy(copy_stream);
@@ -103,7 +105,7 @@ struct genlib_engine {
 namespace {
 
 size_t plan_index_bytes(const Plan &P) {
-    return (P.mem_ind.size() * 3 + P.fam_pf.size() * 3 + P.fam_start.size() + P.mtile_minrank.size() * 4 +
+    return (P.mem_ind.size() * 3 + P.fam_pf.size() * 4 + P.fam_start.size() + P.mtile_minrank.size() * 4 +
             P.pro_slot.size()) * sizeof(int32_t);
 }
 
@@ -111,7 +113,7 @@ size_t engine_bytes(const Plan &P, int numerics) {
     const size_t es = numerics == GENLIB_NUMERICS_FP64 ? 8 : 4;
     size_t b = (size_t)P.capacity * (size_t)P.capacity * es;
     b += P.rt_elems_max * sizeof(double);
-    b += (P.v_elems_max + P.fam_pf.size()) * es;
+    b += (2 * P.v_elems_max + P.fam_pf.size()) * es;
     b += plan_index_bytes(P);
     b += P.flags.size();
     return b;
@@ -127,7 +129,7 @@ LayerArgs layer_args(const genlib_engine &E, int t) {
     a.fam_pf = E.fam_pf.p + L.fam_off; a.fam_pm = E.fam_pm.p + L.fam_off;
     a.fam_start = E.fam_start.p + L.fam_off + t;
     a.flags = E.flags.p + L.flag_off;
-    a.fam_ncol = E.fam_ncol.p + L.fam_off;
+    a.fam_minrank = E.fam_minrank.p + L.fam_off; a.fam_maxrank = E.fam_maxrank.p + L.fam_off;
     a.mt_minrank = E.mt_min.p + L.mtile_off; a.mt_maxrank = E.mt_max.p + L.mtile_off;
     a.mt_fam0 = E.mt_fam0.p + L.mtile_off; a.mt_nfam = E.mt_nfam.p + L.mtile_off;
     a.n_mtiles = L.n_mtiles;
@@ -140,12 +142,17 @@ int launch_layers(genlib_engine &E, bool timed) {
     T *A = static_cast<T *>(E.A);
     const int64_t ld = P.capacity;
     const size_t cross_smem = (size_t)kFTile * kSRStride * sizeof(double);
-    const size_t expand_smem = sizeof(ExpandSmem<T>);
+    static const int stages = [] { const char *s = std::getenv("GENLIB_EXPAND_STAGES"); return s && s[0] == '1' ? 1 : 2; }();
+    const size_t expand_smem = stages == 1 ? sizeof(ExpandSmem<T, 1>) : sizeof(ExpandSmem<T, 2>);
+    auto expand_fn = stages == 1 ? expand_kernel<T, 1> : expand_kernel<T, 2>;
     CU(cudaFuncSetAttribute(cross_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cross_smem));
-    CU(cudaFuncSetAttribute(expand_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem));
+    CU(cudaFuncSetAttribute(expand_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem));
     CU(cudaFuncSetAttribute(cross_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    CU(cudaFuncSetAttribute(expand_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    T *V = static_cast<T *>(E.V), *Dg = static_cast<T *>(E.Dg);
+    CU(cudaFuncSetAttribute(expand_fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    T *V = static_cast<T *>(E.V), *Vt = static_cast<T *>(E.Vt), *Dg = static_cast<T *>(E.Dg);
+    const size_t couple_smem = sizeof(T) * kFTile * kCStride;
+    CU(cudaFuncSetAttribute(couple_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)couple_smem));
+    CU(cudaFuncSetAttribute(couple_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     int launches = 0;
     size_t ev = 0;
     for (int t = 0; t < (int)P.layers.size(); t++) {
@@ -161,15 +168,15 @@ int launch_layers(genlib_engine &E, bool timed) {
         }
         if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
         {
-            dim3 grid((unsigned)((L.nf_pad + kCChunk - 1) / kCChunk), (unsigned)((L.n_fam + kThreads / 32 - 1) / (kThreads / 32)));
-            couple_kernel<T><<<grid, kThreads, 0, E.stream>>>(A, ld, E.Rt, V, Dg, a);
+            dim3 grid((unsigned)((L.nf_pad + kCTile - 1) / kCTile), (unsigned)((L.n_fam + kFTile - 1) / kFTile));
+            couple_kernel<T><<<grid, kThreads, couple_smem, E.stream>>>(A, ld, E.Rt, V, Vt, Dg, a);
             launches++;
         }
         if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
         {
             if (L.n_mtiles > 65535) return fail(GENLIB_EINVAL, "layer too wide for one expand launch");
             dim3 grid((unsigned)((L.n_mtiles + kJChunk - 1) / kJChunk), (unsigned)L.n_mtiles);
-            expand_kernel<T><<<grid, kThreads, expand_smem, E.stream>>>(A, ld, V, Dg, a);
+            expand_fn<<<grid, kExpandThreads, expand_smem, E.stream>>>(A, ld, V, Vt, Dg, a);
             launches++;
         }
         if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
@@ -352,6 +359,7 @@ int genlib_engine_create(const genlib_plan *plan, int numerics, int device, genl
     CU(cudaMalloc(&E->A, std::max<size_t>((size_t)P.capacity * (size_t)P.capacity * E->esize, 16)));
     CU(cudaMalloc(&E->Rt, std::max<size_t>(P.rt_elems_max * sizeof(double), 16)));
     CU(cudaMalloc(&E->V, std::max<size_t>(P.v_elems_max * E->esize, 16)));
+    CU(cudaMalloc(&E->Vt, std::max<size_t>(P.v_elems_max * E->esize, 16)));
     CU(cudaMalloc(&E->Dg, std::max<size_t>(P.fam_pf.size() * E->esize, 16)));
     CU(E->mem_ind.upload(P.mem_ind, E->stream));
     CU(E->mem_slot.upload(P.mem_slot, E->stream));
@@ -359,7 +367,8 @@ int genlib_engine_create(const genlib_plan *plan, int numerics, int device, genl
     CU(E->fam_pf.upload(P.fam_pf, E->stream));
     CU(E->fam_pm.upload(P.fam_pm, E->stream));
     CU(E->fam_start.upload(P.fam_start, E->stream));
-    CU(E->fam_ncol.upload(P.fam_ncol, E->stream));
+    CU(E->fam_minrank.upload(P.fam_minrank, E->stream));
+    CU(E->fam_maxrank.upload(P.fam_maxrank, E->stream));
     CU(E->mt_min.upload(P.mtile_minrank, E->stream));
     CU(E->mt_max.upload(P.mtile_maxrank, E->stream));
     CU(E->mt_fam0.upload(P.mtile_fam0, E->stream));

@@ -32,7 +32,7 @@ struct LayerArgs {
     const int32_t *mem_ind, *mem_slot, *mem_fam;
     const int32_t *fam_pf, *fam_pm, *fam_start;
     const uint8_t *flags;
-    const int32_t *fam_ncol;
+    const int32_t *fam_minrank, *fam_maxrank;
     const int32_t *mt_minrank, *mt_maxrank, *mt_fam0, *mt_nfam;
     int32_t n_mtiles;
 };
@@ -59,6 +59,13 @@ __device__ __forceinline__ void store4(float *p, const double (&d)[4]) {
 __device__ __forceinline__ void store4(double *p, const double (&d)[4]) {
     reinterpret_cast<double2 *>(p)[0] = make_double2(d[0], d[1]);
     reinterpret_cast<double2 *>(p)[1] = make_double2(d[2], d[3]);
+}
+__device__ __forceinline__ void store_vec4(float *p, const float (&v)[4]) {
+    *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void store_vec4(double *p, const double (&v)[4]) {
+    reinterpret_cast<double2 *>(p)[0] = make_double2(v[0], v[1]);
+    reinterpret_cast<double2 *>(p)[1] = make_double2(v[2], v[3]);
 }
 // 1/2 x + 1/2 y with ONE binary64 rounding (1/2 y is exact), = Julia's `0 + x/2 + y/2`
 __device__ __forceinline__ double half_sum(double x, double y) { return fma(0.5, x, 0.5 * y); }
@@ -141,66 +148,85 @@ cross_kernel(T *__restrict__ A, int64_t ld, double *__restrict__ Rt, LayerArgs L
 }
 
 // =====================================================================================
-// couple_kernel: V[F, G] = 1/2 Rt[f_F, G] + 1/2 Rt[m_F, G], one warp per couple row F,
-// columns restricted to the prefix [0, fam_ncol[F]) that can be selected at all.
-// Also the diagonal value of the couple's members, Dg[F] = 1/2 + 1/2 Psi[f_F, m_F]
-// (compute.jl:148-155).  grid (column chunks, row groups of 8).
+// couple_kernel: V[F, G] = 1/2 Rt[f_F, G] + 1/2 Rt[m_F, G]  and its transpose Vt[G, F].
+// Same shape as cross_kernel: tile = kFTile couple rows x kCTile couple columns, warp w owns
+// rows 4w..4w+3, lane l owns columns 4l..4l+3 (two 128-bit loads per parent row); the tile
+// goes out row-major (V) and, through shared memory, transposed (Vt), so that expand_kernel
+// finds both orientations of a couple pair at the SAME offset of two row-major matrices.
+// Rows whose members cannot outrank any member of the tile's columns are skipped.
+// Also Dg[F] = 1/2 + 1/2 Psi[f_F, m_F], the diagonal of the couple's members (compute.jl:148-155).
 // =====================================================================================
-constexpr int kCChunk = 1024;
-
-template <typename T> struct Pair;
-template <> struct Pair<float> { using type = float2; };
-template <> struct Pair<double> { using type = double2; };
+constexpr int kCTile = 128;
+constexpr int kCStride = kCTile + 1;
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 couple_kernel(const T *__restrict__ A, int64_t ld, const double *__restrict__ Rt, T *__restrict__ V,
-              T *__restrict__ Dg, LayerArgs L) {
+              T *__restrict__ Vt, T *__restrict__ Dg, LayerArgs L) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *sV = reinterpret_cast<T *>(smem_raw);                  // [kFTile][kCStride]
+    __shared__ int s_skip[kFTile];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int F = blockIdx.y * (kThreads / 32) + warp;
-    if (F >= L.n_fam) return;
-    const int pf = L.fam_pf[F], pm = L.fam_pm[F];
-    if (blockIdx.x == 0 && lane == 0) {
-        double v = 0.5;
-        if (pf >= 0 && pm >= 0) v = fma(0.5, (double)A[(int64_t)pf * ld + pm], 0.5);
-        Dg[F] = (T)v;
+    const int F0 = blockIdx.y * kFTile, G0 = blockIdx.x * kCTile;
+    const int minG = L.fam_minrank[min(G0, L.n_fam - 1)];     // minrank increases with the couple index
+    const int g = G0 + 4 * lane;
+    const bool col_ok = g < L.nf_pad;                         // nf_pad is a multiple of 4
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int fl = warp * 4 + q, F = F0 + fl;
+        bool skip = true;
+        if (F < L.n_fam && G0 < L.n_fam) {
+            const int pf = L.fam_pf[F], pm = L.fam_pm[F];
+            if (blockIdx.x == 0 && lane == 0) {
+                double d = 0.5;
+                if (pf >= 0 && pm >= 0) d = fma(0.5, (double)A[(int64_t)pf * ld + pm], 0.5);
+                Dg[F] = (T)d;
+            }
+            skip = L.fam_maxrank[F] <= minG;                  // nobody in F outranks anybody in the tile
+            if (!skip && col_ok) {
+                double a[4] = {0.0, 0.0, 0.0, 0.0}, b[4] = {0.0, 0.0, 0.0, 0.0};
+                if (pf >= 0) load4(Rt + (size_t)(pf - L.rt_lo) * L.nf_pad + g, a);
+                if (pm >= 0) load4(Rt + (size_t)(pm - L.rt_lo) * L.nf_pad + g, b);
+                T v[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    v[k] = (T)half_sum(a[k], b[k]);
+                    sV[fl * kCStride + 4 * lane + k] = v[k];
+                }
+                store_vec4(V + (size_t)F * L.nf_pad + g, v);
+            }
+        }
+        if (lane == 0) s_skip[fl] = skip;
     }
-    const int ncol = L.fam_ncol[F];
-    const int c0 = blockIdx.x * kCChunk;
-    if (c0 >= ncol) return;
-    const int cend = min(c0 + kCChunk, (ncol + 1) & ~1);
-    const double2 *rf = reinterpret_cast<const double2 *>(Rt + (size_t)max(pf - L.rt_lo, 0) * L.nf_pad);
-    const double2 *rm = reinterpret_cast<const double2 *>(Rt + (size_t)max(pm - L.rt_lo, 0) * L.nf_pad);
-    typename Pair<T>::type *out = reinterpret_cast<typename Pair<T>::type *>(V + (size_t)F * L.nf_pad);
-    const double2 zero = make_double2(0.0, 0.0);
-#pragma unroll 4
-    for (int c = c0 + 2 * lane; c < cend; c += 64) {
-        const double2 a = pf >= 0 ? __ldg(rf + (c >> 1)) : zero;
-        const double2 b = pm >= 0 ? __ldg(rm + (c >> 1)) : zero;
-        typename Pair<T>::type v;
-        v.x = (T)half_sum(a.x, b.x);
-        v.y = (T)half_sum(a.y, b.y);
-        out[c >> 1] = v;
-    }
+    __syncthreads();
+    // transposed: Vt[G, F0 .. F0+32), one couple column per warp iteration, lane = couple row
+    const bool row_ok = (F0 + lane < L.n_fam) && !s_skip[lane];
+    const int gl_end = min(kCTile, L.n_fam - G0);
+    for (int gl = warp; gl < gl_end; gl += kThreads / 32)
+        if (row_ok) Vt[(size_t)(G0 + gl) * L.nf_pad + F0 + lane] = sV[lane * kCStride + gl];
 }
 
 // =====================================================================================
 // expand_kernel: couples -> members.  CTA = one tile of kMTile member ROWS against
 // kJChunk consecutive tiles of kMTile member COLUMNS; every CTA writes only its own rows
-// (long contiguous segments), so the symmetric partner block is written by the CTA that
-// owns those rows -- no transposed stores.
-//   entry (i, j), i in couple F, j in couple G:  rank_i > rank_j ? V[F, G] : V[G, F]
+// (contiguous segments); the symmetric partner block is written by the CTA that owns those
+// rows -- no transposed stores.
+//   entry (i, j), i in couple F, j in couple G:  rank_i > rank_j ? V[F, G] : V[G, F] = Vt[F, G]
 //   (compute.jl:130-147: the higher rank is climbed first);  i == j: Dg[F].
-// Thread t owns columns 4(t%16)..+3 of the column tile and rows t/16 + 16k.
+// The two couple tiles V[F.., G..] and Vt[F.., G..] stream in with 16-byte cp.async, double
+// buffered, while the previous column tile is expanded.  Thread t owns columns 4(t%16)..+3
+// of the column tile and rows t/16 + 8k (8 rows per thread).
 // =====================================================================================
-constexpr int kJChunk = 8;
+constexpr int kJChunk = 16;
+constexpr int kExpandThreads = 128;
 
-// cp.async (LDGSTS): global -> shared without register staging, so the next column tile
-// streams in while the current one is expanded.
 template <int BYTES>
 __device__ __forceinline__ void cp_async(void *smem, const void *gmem) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(s), "l"(gmem), "n"(BYTES));
+    if constexpr (BYTES == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(s), "l"(gmem), "n"(BYTES));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
@@ -208,42 +234,36 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 template <typename T>
 struct ExpandStage {
-    T Vab[kMTile * kVStride];   // [couple of the row tile][couple of the column tile]
-    T Vba[kMTile * kVStride];   // [couple of the column tile][couple of the row tile]
+    static constexpr int kVec = 16 / sizeof(T);            // elements per 16-byte chunk
+    static constexpr int kStride = kMTile + kVec;           // row stride (multiple of kVec)
+    T Vab[kMTile * kStride];    // V [couple of the row tile][couple of the column tile]
+    T Vba[kMTile * kStride];    // Vt, same indexing
     int32_t famJ[kMTile], rankJ[kMTile], slotJ[kMTile];
 };
-template <typename T>
+template <typename T, int kStages>
 struct ExpandSmem {
-    ExpandStage<T> st[2];
+    ExpandStage<T> st[kStages];
     int4 metaI[kMTile];         // {couple - fI0, rank, slot, 0} of the row tile
 };
 
-__device__ __forceinline__ void store_vec4(float *p, const float (&v)[4]) {
-    *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
-}
-__device__ __forceinline__ void store_vec4(double *p, const double (&v)[4]) {
-    reinterpret_cast<double2 *>(p)[0] = make_double2(v[0], v[1]);
-    reinterpret_cast<double2 *>(p)[1] = make_double2(v[2], v[3]);
-}
-
 template <typename T>
-__device__ __forceinline__ void expand_prefetch(ExpandStage<T> &B, const T *__restrict__ V, const LayerArgs &L,
-                                                int J, int fI0, int nfI, int minI, int maxI) {
+__device__ __forceinline__ void expand_prefetch(ExpandStage<T> &B, const T *__restrict__ V,
+                                                const T *__restrict__ Vt, const LayerArgs &L, int J, int fI0,
+                                                int nfI, int minI, int maxI) {
+    constexpr int kVec = ExpandStage<T>::kVec, kStride = ExpandStage<T>::kStride;
     const int mJ0 = J * kMTile;
     const int cJ = min(kMTile, L.n_new - mJ0);
     const int fJ0 = L.mt_fam0[J], nfJ = L.mt_nfam[J];
-    const int col = threadIdx.x & (kMTile - 1), row0 = threadIdx.x >> 6;      // 4 row phases
-    if (maxI > L.mt_minrank[J] && col < nfJ) {            // some row member outranks a column member
-        const T *src = V + (size_t)fI0 * L.nf_pad + fJ0 + col;
-#pragma unroll 4
-        for (int f = row0; f < nfI; f += kThreads / kMTile)
-            cp_async<sizeof(T)>(&B.Vab[f * kVStride + col], src + (size_t)f * L.nf_pad);
-    }
-    if (L.mt_maxrank[J] > minI && col < nfI) {
-        const T *src = V + (size_t)fJ0 * L.nf_pad + fI0 + col;
-#pragma unroll 4
-        for (int g = row0; g < nfJ; g += kThreads / kMTile)
-            cp_async<sizeof(T)>(&B.Vba[g * kVStride + col], src + (size_t)g * L.nf_pad);
+    const int c0 = fJ0 & ~(kVec - 1);                       // 16-byte aligned column start
+    const int nchunk = (fJ0 + nfJ - c0 + kVec - 1) / kVec;  // <= kStride / kVec
+    const bool need_ab = maxI > L.mt_minrank[J];            // some row member outranks a column member
+    const bool need_ba = L.mt_maxrank[J] > minI;
+    const int total = nfI * nchunk;
+    for (int idx = threadIdx.x; idx < total; idx += kExpandThreads) {
+        const int f = idx / nchunk, c = idx - f * nchunk;
+        const size_t goff = (size_t)(fI0 + f) * L.nf_pad + c0 + c * kVec;
+        if (need_ab) cp_async<16>(&B.Vab[f * kStride + c * kVec], V + goff);
+        if (need_ba) cp_async<16>(&B.Vba[f * kStride + c * kVec], Vt + goff);
     }
     if (threadIdx.x < kMTile) {
         const int m = mJ0 + min((int)threadIdx.x, cJ - 1);
@@ -253,29 +273,32 @@ __device__ __forceinline__ void expand_prefetch(ExpandStage<T> &B, const T *__re
     }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kThreads)
-expand_kernel(T *__restrict__ A, int64_t ld, const T *__restrict__ V, const T *__restrict__ Dg, LayerArgs L) {
+template <typename T, int kStages>
+__global__ void __launch_bounds__(kExpandThreads)
+expand_kernel(T *__restrict__ A, int64_t ld, const T *__restrict__ V, const T *__restrict__ Vt,
+              const T *__restrict__ Dg, LayerArgs L) {
+    constexpr int kVec = ExpandStage<T>::kVec, kStride = ExpandStage<T>::kStride;
+    constexpr int kRows = kMTile / (kExpandThreads / 16);   // rows per thread
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    ExpandSmem<T> &S = *reinterpret_cast<ExpandSmem<T> *>(smem_raw);
+    ExpandSmem<T, kStages> &S = *reinterpret_cast<ExpandSmem<T, kStages> *>(smem_raw);
     const int I = blockIdx.y;
     const int mI0 = I * kMTile;
     const int cI = min(kMTile, L.n_new - mI0);
     const int fI0 = L.mt_fam0[I], nfI = L.mt_nfam[I];
     const int minI = L.mt_minrank[I], maxI = L.mt_maxrank[I];
     const int Jbeg = blockIdx.x * kJChunk, Jend = min(L.n_mtiles, Jbeg + kJChunk);
-    expand_prefetch(S.st[0], V, L, Jbeg, fI0, nfI, minI, maxI);
+    expand_prefetch(S.st[0], V, Vt, L, Jbeg, fI0, nfI, minI, maxI);
     cp_async_commit();
     if (threadIdx.x < kMTile) {
         const int m = mI0 + min((int)threadIdx.x, cI - 1);
-        S.metaI[threadIdx.x] = make_int4(L.mem_fam[m] - fI0, L.mem_ind[m], L.mem_slot[m], 0);
+        S.metaI[threadIdx.x] = make_int4((L.mem_fam[m] - fI0) * kStride, L.mem_ind[m], L.mem_slot[m], L.mem_fam[m]);
     }
     const int cg = threadIdx.x & 15, rg = threadIdx.x >> 4;
     const int j0 = 4 * cg;
     int buf = 0;
-    for (int J = Jbeg; J < Jend; J++, buf ^= 1) {
-        if (J + 1 < Jend) {
-            expand_prefetch(S.st[buf ^ 1], V, L, J + 1, fI0, nfI, minI, maxI);
+    for (int J = Jbeg; J < Jend; J++, buf = (buf + 1) % kStages) {
+        if (kStages > 1 && J + 1 < Jend) {
+            expand_prefetch(S.st[(buf + 1) % kStages], V, Vt, L, J + 1, fI0, nfI, minI, maxI);
             cp_async_commit();
             cp_async_wait<1>();
         } else {
@@ -285,32 +308,30 @@ expand_kernel(T *__restrict__ A, int64_t ld, const T *__restrict__ V, const T *_
         const ExpandStage<T> &B = S.st[buf];
         const int cJ = min(kMTile, L.n_new - J * kMTile);
         if (j0 < cJ) {
-            const int fJ0 = L.mt_fam0[J];
-            int ab[4], ba[4], rj[4], sj[4];
+            const int c0 = L.mt_fam0[J] & ~(kVec - 1);
+            int go[4], rj[4], sj[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const int g = B.famJ[j0 + k] - fJ0;
-                ab[k] = g; ba[k] = g * kVStride;
+                go[k] = B.famJ[j0 + k] - c0;               // column inside the staged tile
                 rj[k] = B.rankJ[j0 + k]; sj[k] = B.slotJ[j0 + k];
             }
             const bool vec = (j0 + 3 < cJ) && ((sj[0] & 3) == 0) && sj[1] == sj[0] + 1 && sj[2] == sj[0] + 2 &&
                              sj[3] == sj[0] + 3;
-            const int dj = (I == J) ? j0 : -8;             // tile-local column of the diagonal, if any
+            const int dj = (I == J) ? j0 : -8;             // tile-local column of a diagonal entry, if any
 #pragma unroll
-            for (int r = 0; r < kMTile / 16; r++) {
-                const int il = rg + 16 * r;
+            for (int r = 0; r < kRows; r++) {
+                const int il = rg + (kExpandThreads / 16) * r;
                 if (il < cI) {
-                    const int4 mi = S.metaI[il];           // couple, rank, slot
-                    const T *va = B.Vab + mi.x * kVStride;
-                    const T *vb = B.Vba + mi.x;
+                    const int4 mi = S.metaI[il];           // couple row offset, rank, slot, couple
                     T v[4];
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
-                        const T a = va[ab[k]], b = vb[ba[k]];
+                        const int o = mi.x + go[k];
+                        const T a = B.Vab[o], b = B.Vba[o];
                         v[k] = mi.y > rj[k] ? a : b;       // the higher rank is climbed first
                     }
                     if ((unsigned)(il - dj) < 4u) {        // own diagonal entry (compute.jl:148-155)
-                        const T d = Dg[fI0 + mi.x];
+                        const T d = Dg[mi.w];
 #pragma unroll
                         for (int k = 0; k < 4; k++) if (il - dj == k) v[k] = d;
                     }
@@ -324,6 +345,10 @@ expand_kernel(T *__restrict__ A, int64_t ld, const T *__restrict__ V, const T *_
             }
         }
         __syncthreads();                                   // done with st[buf] before it is refilled
+        if (kStages == 1 && J + 1 < Jend) {
+            expand_prefetch(S.st[0], V, Vt, L, J + 1, fI0, nfI, minI, maxI);
+            cp_async_commit();
+        }
     }
 }
 

@@ -214,16 +214,12 @@ int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t 
             P.fam_pm.push_back(mother[x] >= 0 ? slot_of[mother[x]] : -1);
         }
         // V[F, G] ("a member of F is climbed first", compute.jl:130-138) is read only when some
-        // member of F outranks some member of G.  Couples are ordered by their first (lowest
-        // rank) member, so those G form a prefix [0, fam_ncol[F]).
+        // member of F outranks some member of G; the kernels skip the rest by these ranges.
         {
             const int32_t *mi = P.mem_ind.data() + L.mem_off;
-            // minrank(G) increases with G; maxrank(F) does not, so search per row
-            std::vector<int32_t> minr((size_t)nf);
-            for (int32_t f = 0; f < nf; f++) minr[f] = mi[fstart[f]];
             for (int32_t f = 0; f < nf; f++) {
-                const int32_t maxr = mi[fstart[f + 1] - 1];
-                P.fam_ncol.push_back((int32_t)(std::lower_bound(minr.begin(), minr.end(), maxr) - minr.begin()));
+                P.fam_minrank.push_back(mi[fstart[f]]);           // increasing with f
+                P.fam_maxrank.push_back(mi[fstart[f + 1] - 1]);
             }
         }
         // per member tile rank range (lets the intra kernel skip one orientation)

@@ -52,7 +52,7 @@ struct Plan {
     std::vector<int32_t> mem_ind, mem_slot, mem_fam;   // family-major order inside a layer
     std::vector<int32_t> fam_pf, fam_pm, fam_start;    // parents as slots (-1 = none)
     std::vector<uint8_t> flags;
-    std::vector<int32_t> fam_ncol;                     // couple row F needs V[F, 0 .. fam_ncol[F])
+    std::vector<int32_t> fam_minrank, fam_maxrank;     // rank range of a couple's members
     std::vector<int32_t> mtile_minrank, mtile_maxrank; // rank range of a member tile
     std::vector<int32_t> mtile_fam0, mtile_nfam;       // family range of a member tile
     size_t v_elems_max = 0;           // max over layers of n_fam * nf_pad
