@@ -35,6 +35,7 @@ struct LayerArgs {
     const int32_t *fam_minrank, *fam_maxrank;
     const int32_t *mt_minrank, *mt_maxrank, *mt_fam0, *mt_nfam;
     int32_t n_mtiles;
+    int32_t vrows, vstride;     // staged couple tile of expand_kernel: rows, row stride (elements)
 };
 
 constexpr int kThreads = 256;
@@ -224,52 +225,60 @@ template <int BYTES>
 __device__ __forceinline__ void cp_async(void *smem, const void *gmem) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     if constexpr (BYTES == 16)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
     else
-        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(s), "l"(gmem), "n"(BYTES));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(s), "l"(gmem), "n"(BYTES) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// Shared-memory layout of one expand CTA (runtime strides, sized per layer by the host):
+//   metaI[kMTile] int4 {byte offset of the couple row, rank, row pointer lo, hi}
+//   famI[kMTile]  couple index of each row member (for Dg)
+//   kStages x { Vab[vrows][vstride], Vba[vrows][vstride], famJ, rankJ, slotJ [kMTile] }
+// vrows = most couples in any member tile of the layer, vstride = vrows rounded up to a
+// 16-byte multiple plus one chunk (the column start is aligned down to 16 bytes).
+template <typename T>
+__host__ __device__ inline size_t expand_stage_bytes(int vrows, int vstride) {
+    return 2 * (size_t)vrows * vstride * sizeof(T) + 3 * kMTile * sizeof(int32_t);
+}
+template <typename T>
+__host__ __device__ inline size_t expand_smem_bytes(int vrows, int vstride, int stages) {
+    return kMTile * (sizeof(int4) + sizeof(int32_t)) + stages * expand_stage_bytes<T>(vrows, vstride);
+}
 
 template <typename T>
-struct ExpandStage {
-    static constexpr int kVec = 16 / sizeof(T);            // elements per 16-byte chunk
-    static constexpr int kStride = kMTile + kVec;           // row stride (multiple of kVec)
-    T Vab[kMTile * kStride];    // V [couple of the row tile][couple of the column tile]
-    T Vba[kMTile * kStride];    // Vt, same indexing
-    int32_t famJ[kMTile], rankJ[kMTile], slotJ[kMTile];
-};
-template <typename T, int kStages>
-struct ExpandSmem {
-    ExpandStage<T> st[kStages];
-    int4 metaI[kMTile];         // {couple - fI0, rank, slot, 0} of the row tile
-};
-
-template <typename T>
-__device__ __forceinline__ void expand_prefetch(ExpandStage<T> &B, const T *__restrict__ V,
+__device__ __forceinline__ void expand_prefetch(unsigned char *stage, const T *__restrict__ V,
                                                 const T *__restrict__ Vt, const LayerArgs &L, int J, int fI0,
                                                 int nfI, int minI, int maxI) {
-    constexpr int kVec = ExpandStage<T>::kVec, kStride = ExpandStage<T>::kStride;
+    constexpr int kVec = 16 / sizeof(T);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    T *Vab = reinterpret_cast<T *>(stage);
+    T *Vba = Vab + (size_t)L.vrows * L.vstride;
+    int32_t *metaJ = reinterpret_cast<int32_t *>(Vba + (size_t)L.vrows * L.vstride);
     const int mJ0 = J * kMTile;
     const int cJ = min(kMTile, L.n_new - mJ0);
     const int fJ0 = L.mt_fam0[J], nfJ = L.mt_nfam[J];
     const int c0 = fJ0 & ~(kVec - 1);                       // 16-byte aligned column start
-    const int nchunk = (fJ0 + nfJ - c0 + kVec - 1) / kVec;  // <= kStride / kVec
+    const int nchunk = (fJ0 + nfJ - c0 + kVec - 1) / kVec;  // <= vstride / kVec
     const bool need_ab = maxI > L.mt_minrank[J];            // some row member outranks a column member
     const bool need_ba = L.mt_maxrank[J] > minI;
-    const int total = nfI * nchunk;
-    for (int idx = threadIdx.x; idx < total; idx += kExpandThreads) {
-        const int f = idx / nchunk, c = idx - f * nchunk;
-        const size_t goff = (size_t)(fI0 + f) * L.nf_pad + c0 + c * kVec;
-        if (need_ab) cp_async<16>(&B.Vab[f * kStride + c * kVec], V + goff);
-        if (need_ba) cp_async<16>(&B.Vba[f * kStride + c * kVec], Vt + goff);
+    // warp w streams couple rows w, w+4, ...; lane = 16-byte chunk of the row (two passes for
+    // the 8-byte type, whose rows have up to 33 chunks)
+    for (int c = lane; c < nchunk; c += 32) {
+        const size_t goff = (size_t)fI0 * L.nf_pad + c0 + c * kVec;
+        const int soff = c * kVec;
+        for (int f = warp; f < nfI; f += kExpandThreads / 32) {
+            if (need_ab) cp_async<16>(Vab + f * L.vstride + soff, V + goff + (size_t)f * L.nf_pad);
+            if (need_ba) cp_async<16>(Vba + f * L.vstride + soff, Vt + goff + (size_t)f * L.nf_pad);
+        }
     }
     if (threadIdx.x < kMTile) {
         const int m = mJ0 + min((int)threadIdx.x, cJ - 1);
-        cp_async<4>(&B.famJ[threadIdx.x], L.mem_fam + m);
-        cp_async<4>(&B.rankJ[threadIdx.x], L.mem_ind + m);
-        cp_async<4>(&B.slotJ[threadIdx.x], L.mem_slot + m);
+        cp_async<4>(metaJ + threadIdx.x, L.mem_fam + m);
+        cp_async<4>(metaJ + kMTile + threadIdx.x, L.mem_ind + m);
+        cp_async<4>(metaJ + 2 * kMTile + threadIdx.x, L.mem_slot + m);
     }
 }
 
@@ -277,43 +286,54 @@ template <typename T, int kStages>
 __global__ void __launch_bounds__(kExpandThreads)
 expand_kernel(T *__restrict__ A, int64_t ld, const T *__restrict__ V, const T *__restrict__ Vt,
               const T *__restrict__ Dg, LayerArgs L) {
-    constexpr int kVec = ExpandStage<T>::kVec, kStride = ExpandStage<T>::kStride;
+    constexpr int kVec = 16 / sizeof(T);
     constexpr int kRows = kMTile / (kExpandThreads / 16);   // rows per thread
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    ExpandSmem<T, kStages> &S = *reinterpret_cast<ExpandSmem<T, kStages> *>(smem_raw);
+    int4 *metaI = reinterpret_cast<int4 *>(smem_raw);
+    int32_t *famI = reinterpret_cast<int32_t *>(metaI + kMTile);
+    unsigned char *stages = reinterpret_cast<unsigned char *>(famI + kMTile);
+    const size_t stage_bytes = expand_stage_bytes<T>(L.vrows, L.vstride);
+    const int vba_off = L.vrows * L.vstride * (int)sizeof(T);   // Vba relative to Vab, bytes
     const int I = blockIdx.y;
     const int mI0 = I * kMTile;
     const int cI = min(kMTile, L.n_new - mI0);
     const int fI0 = L.mt_fam0[I], nfI = L.mt_nfam[I];
     const int minI = L.mt_minrank[I], maxI = L.mt_maxrank[I];
     const int Jbeg = blockIdx.x * kJChunk, Jend = min(L.n_mtiles, Jbeg + kJChunk);
-    expand_prefetch(S.st[0], V, Vt, L, Jbeg, fI0, nfI, minI, maxI);
+    expand_prefetch<T>(stages, V, Vt, L, Jbeg, fI0, nfI, minI, maxI);
     cp_async_commit();
     if (threadIdx.x < kMTile) {
         const int m = mI0 + min((int)threadIdx.x, cI - 1);
-        S.metaI[threadIdx.x] = make_int4((L.mem_fam[m] - fI0) * kStride, L.mem_ind[m], L.mem_slot[m], L.mem_fam[m]);
+        const int fam = L.mem_fam[m];
+        const unsigned long long p = (unsigned long long)(A + (int64_t)L.mem_slot[m] * ld);
+        metaI[threadIdx.x] = make_int4((fam - fI0) * L.vstride * (int)sizeof(T), L.mem_ind[m], (int)(unsigned)p,
+                                       (int)(unsigned)(p >> 32));
+        famI[threadIdx.x] = fam;
     }
     const int cg = threadIdx.x & 15, rg = threadIdx.x >> 4;
     const int j0 = 4 * cg;
     int buf = 0;
     for (int J = Jbeg; J < Jend; J++, buf = (buf + 1) % kStages) {
         if (kStages > 1 && J + 1 < Jend) {
-            expand_prefetch(S.st[(buf + 1) % kStages], V, Vt, L, J + 1, fI0, nfI, minI, maxI);
+            expand_prefetch<T>(stages + ((buf + 1) % kStages) * stage_bytes, V, Vt, L, J + 1, fI0, nfI, minI, maxI);
             cp_async_commit();
             cp_async_wait<1>();
         } else {
             cp_async_wait<0>();
         }
         __syncthreads();                                   // tile J (and metaI) visible to everybody
-        const ExpandStage<T> &B = S.st[buf];
+        const unsigned char *stage = stages + buf * stage_bytes;
+        const int32_t *metaJ = reinterpret_cast<const int32_t *>(stage + 2 * (size_t)vba_off);
         const int cJ = min(kMTile, L.n_new - J * kMTile);
         if (j0 < cJ) {
             const int c0 = L.mt_fam0[J] & ~(kVec - 1);
-            int go[4], rj[4], sj[4];
+            const unsigned sbase = (unsigned)__cvta_generic_to_shared(stage);
+            unsigned go[4];
+            int rj[4], sj[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                go[k] = B.famJ[j0 + k] - c0;               // column inside the staged tile
-                rj[k] = B.rankJ[j0 + k]; sj[k] = B.slotJ[j0 + k];
+                go[k] = sbase + (unsigned)(metaJ[j0 + k] - c0) * (unsigned)sizeof(T);   // column, shared address
+                rj[k] = metaJ[kMTile + j0 + k]; sj[k] = metaJ[2 * kMTile + j0 + k];
             }
             const bool vec = (j0 + 3 < cJ) && ((sj[0] & 3) == 0) && sj[1] == sj[0] + 1 && sj[2] == sj[0] + 2 &&
                              sj[3] == sj[0] + 3;
@@ -322,20 +342,22 @@ expand_kernel(T *__restrict__ A, int64_t ld, const T *__restrict__ V, const T *_
             for (int r = 0; r < kRows; r++) {
                 const int il = rg + (kExpandThreads / 16) * r;
                 if (il < cI) {
-                    const int4 mi = S.metaI[il];           // couple row offset, rank, slot, couple
+                    const int4 mi = metaI[il];             // couple row byte offset, rank, row pointer
                     T v[4];
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
-                        const int o = mi.x + go[k];
-                        const T a = B.Vab[o], b = B.Vba[o];
-                        v[k] = mi.y > rj[k] ? a : b;       // the higher rank is climbed first
+                        // the higher rank is climbed first: V[F, G] if the row member outranks
+                        // the column member, V[G, F] = Vt[F, G] otherwise
+                        const unsigned addr = go[k] + (unsigned)mi.x + (mi.y > rj[k] ? 0u : (unsigned)vba_off);
+                        if constexpr (sizeof(T) == 4) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[k]) : "r"(addr));
+                        else asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v[k]) : "r"(addr));
                     }
                     if ((unsigned)(il - dj) < 4u) {        // own diagonal entry (compute.jl:148-155)
-                        const T d = Dg[mi.w];
+                        const T d = Dg[famI[il]];
 #pragma unroll
                         for (int k = 0; k < 4; k++) if (il - dj == k) v[k] = d;
                     }
-                    T *row = A + (int64_t)mi.z * ld;
+                    T *row = reinterpret_cast<T *>(((unsigned long long)(unsigned)mi.w << 32) | (unsigned)mi.z);
                     if (vec) store_vec4(row + sj[0], v);
                     else {
 #pragma unroll
@@ -344,9 +366,9 @@ expand_kernel(T *__restrict__ A, int64_t ld, const T *__restrict__ V, const T *_
                 }
             }
         }
-        __syncthreads();                                   // done with st[buf] before it is refilled
+        __syncthreads();                                   // done with this stage before it is refilled
         if (kStages == 1 && J + 1 < Jend) {
-            expand_prefetch(S.st[0], V, Vt, L, J + 1, fI0, nfI, minI, maxI);
+            expand_prefetch<T>(stages, V, Vt, L, J + 1, fI0, nfI, minI, maxI);
             cp_async_commit();
         }
     }

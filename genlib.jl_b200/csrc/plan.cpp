@@ -234,6 +234,7 @@ int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t 
             const int32_t q0 = mt * kMTile, q1 = std::min(nn, (mt + 1) * kMTile) - 1;
             const int32_t f0 = P.mem_fam[L.mem_off + q0], f1 = P.mem_fam[L.mem_off + q1];
             P.mtile_fam0.push_back(f0); P.mtile_nfam.push_back(f1 - f0 + 1);
+            L.max_tile_fam = std::max(L.max_tile_fam, f1 - f0 + 1);
         }
         L.alg_elems = 4.0 * nn * (double)L.live_before + 3.0 * (double)nn * nn;
         P.alg_elems += L.alg_elems;

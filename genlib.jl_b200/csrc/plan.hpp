@@ -33,6 +33,7 @@ struct Layer {
     int32_t rt_lo = 0, rt_rows = 0;   // live slots lie in [rt_lo, rt_lo + rt_rows), both multiples of kPTile
     int32_t nf_pad = 0;               // row stride of the transposed cross block (families, multiple of 32)
     int32_t n_mtiles = 0;
+    int32_t max_tile_fam = 0;         // most couples in one member tile
     size_t mem_off = 0;               // into mem_* arrays
     size_t fam_off = 0;               // into fam_pf / fam_pm; fam_start uses fam_off + layer index
     size_t flag_off = 0;              // into flags
