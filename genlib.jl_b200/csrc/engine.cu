@@ -134,8 +134,8 @@ LayerArgs layer_args(const genlib_engine &E, int t) {
     a.mt_fam0 = E.mt_fam0.p + L.mtile_off; a.mt_nfam = E.mt_nfam.p + L.mtile_off;
     a.n_mtiles = L.n_mtiles;
     const int vec = 16 / (int)E.esize;
-    a.vrows = std::max(L.max_tile_fam, 1);
-    a.vstride = (a.vrows + vec - 1) / vec * vec + vec;
+    a.vrows = kERows;
+    a.vstride = (std::max(L.max_tile_fam, 1) + vec - 1) / vec * vec + vec;
     return a;
 }
 
@@ -145,13 +145,11 @@ int launch_layers(genlib_engine &E, bool timed) {
     T *A = static_cast<T *>(E.A);
     const int64_t ld = P.capacity;
     const size_t cross_smem = (size_t)kFTile * kSRStride * sizeof(double);
-    static const int stages = [] { const char *s = std::getenv("GENLIB_EXPAND_STAGES"); return s && s[0] == '1' ? 1 : 2; }();
-    const size_t expand_smem_max = expand_smem_bytes<T>(kMTile, kMTile + 16 / (int)sizeof(T), stages);
-    auto expand_fn = stages == 1 ? expand_kernel<T, 1> : expand_kernel<T, 2>;
-    CU(cudaFuncSetAttribute(cross_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cross_smem));
-    CU(cudaFuncSetAttribute(expand_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem_max));
+    const int vec = 16 / (int)sizeof(T);
+    const size_t expand_smem_max = (size_t)kEWarps * 2 * expand_stage_bytes<T>(kMTile + vec);
+    CU(cudaFuncSetAttribute(expand_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem_max));
     CU(cudaFuncSetAttribute(cross_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    CU(cudaFuncSetAttribute(expand_fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CU(cudaFuncSetAttribute(expand_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     T *V = static_cast<T *>(E.V), *Vt = static_cast<T *>(E.Vt), *Dg = static_cast<T *>(E.Dg);
     const size_t couple_smem = sizeof(T) * kFTile * kCStride;
     CU(cudaFuncSetAttribute(couple_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)couple_smem));
@@ -177,10 +175,10 @@ int launch_layers(genlib_engine &E, bool timed) {
         }
         if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
         {
-            if (L.n_mtiles > 65535) return fail(GENLIB_EINVAL, "layer too wide for one expand launch");
-            dim3 grid((unsigned)((L.n_mtiles + kJChunk - 1) / kJChunk), (unsigned)L.n_mtiles);
-            const size_t smem = expand_smem_bytes<T>(a.vrows, a.vstride, stages);
-            expand_fn<<<grid, kExpandThreads, smem, E.stream>>>(A, ld, V, Vt, Dg, a);
+            const int rows_per_cta = kEWarps * kERows;
+            dim3 grid((unsigned)((L.n_new + rows_per_cta - 1) / rows_per_cta), (unsigned)((L.n_mtiles + kEChunk - 1) / kEChunk));
+            const size_t smem = (size_t)kEWarps * 2 * expand_stage_bytes<T>(a.vstride);
+            expand_kernel<T><<<grid, kExpandThreads, smem, E.stream>>>(A, ld, V, Vt, Dg, a);
             launches++;
         }
         if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));

@@ -208,18 +208,20 @@ couple_kernel(const T *__restrict__ A, int64_t ld, const double *__restrict__ Rt
 }
 
 // =====================================================================================
-// expand_kernel: couples -> members.  CTA = one tile of kMTile member ROWS against
-// kJChunk consecutive tiles of kMTile member COLUMNS; every CTA writes only its own rows
-// (contiguous segments); the symmetric partner block is written by the CTA that owns those
-// rows -- no transposed stores.
+// expand_kernel: couples -> members.  Every WARP owns kERows consecutive member rows and sweeps
+// the member columns in steps of kMTile (= 4 per lane), writing only its own rows (one
+// contiguous 512-byte segment per row and step); the symmetric partner block is written by
+// the warp that owns those rows -- no transposed stores, no block-wide barriers.
 //   entry (i, j), i in couple F, j in couple G:  rank_i > rank_j ? V[F, G] : V[G, F] = Vt[F, G]
 //   (compute.jl:130-147: the higher rank is climbed first);  i == j: Dg[F].
-// The two couple tiles V[F.., G..] and Vt[F.., G..] stream in with 16-byte cp.async, double
-// buffered, while the previous column tile is expanded.  Thread t owns columns 4(t%16)..+3
-// of the column tile and rows t/16 + 8k (8 rows per thread).
+// The <= kERows couple rows of V and Vt that a warp needs for the next column step, and that
+// step's column metadata, stream into warp-private shared memory with cp.async while the
+// current step is expanded (double buffered).
 // =====================================================================================
-constexpr int kJChunk = 16;
-constexpr int kExpandThreads = 128;
+constexpr int kERows = 8;          // member rows per warp
+constexpr int kEWarps = 4;         // warps per CTA
+constexpr int kEChunk = 16;        // column steps per CTA
+constexpr int kExpandThreads = kEWarps * 32;
 
 template <int BYTES>
 __device__ __forceinline__ void cp_async(void *smem, const void *gmem) {
@@ -233,144 +235,135 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-// Shared-memory layout of one expand CTA (runtime strides, sized per layer by the host):
-//   metaI[kMTile] int4 {byte offset of the couple row, rank, row pointer lo, hi}
-//   famI[kMTile]  couple index of each row member (for Dg)
-//   kStages x { Vab[vrows][vstride], Vba[vrows][vstride], famJ, rankJ, slotJ [kMTile] }
-// vrows = most couples in any member tile of the layer, vstride = vrows rounded up to a
-// 16-byte multiple plus one chunk (the column start is aligned down to 16 bytes).
+// per warp and stage: Vab[kERows][vstride], Vba[kERows][vstride], famJ/rankJ/slotJ[kMTile]
 template <typename T>
-__host__ __device__ inline size_t expand_stage_bytes(int vrows, int vstride) {
-    return 2 * (size_t)vrows * vstride * sizeof(T) + 3 * kMTile * sizeof(int32_t);
-}
-template <typename T>
-__host__ __device__ inline size_t expand_smem_bytes(int vrows, int vstride, int stages) {
-    return kMTile * (sizeof(int4) + sizeof(int32_t)) + stages * expand_stage_bytes<T>(vrows, vstride);
+__host__ __device__ inline size_t expand_stage_bytes(int vstride) {
+    return 2 * (size_t)kERows * vstride * sizeof(T) + 3 * kMTile * sizeof(int32_t);
 }
 
 template <typename T>
-__device__ __forceinline__ void expand_prefetch(unsigned char *stage, const T *__restrict__ V,
-                                                const T *__restrict__ Vt, const LayerArgs &L, int J, int fI0,
-                                                int nfI, int minI, int maxI) {
-    constexpr int kVec = 16 / sizeof(T);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    T *Vab = reinterpret_cast<T *>(stage);
-    T *Vba = Vab + (size_t)L.vrows * L.vstride;
-    int32_t *metaJ = reinterpret_cast<int32_t *>(Vba + (size_t)L.vrows * L.vstride);
-    const int mJ0 = J * kMTile;
-    const int cJ = min(kMTile, L.n_new - mJ0);
-    const int fJ0 = L.mt_fam0[J], nfJ = L.mt_nfam[J];
-    const int c0 = fJ0 & ~(kVec - 1);                       // 16-byte aligned column start
-    const int nchunk = (fJ0 + nfJ - c0 + kVec - 1) / kVec;  // <= vstride / kVec
-    const bool need_ab = maxI > L.mt_minrank[J];            // some row member outranks a column member
-    const bool need_ba = L.mt_maxrank[J] > minI;
-    // warp w streams couple rows w, w+4, ...; lane = 16-byte chunk of the row (two passes for
-    // the 8-byte type, whose rows have up to 33 chunks)
-    for (int c = lane; c < nchunk; c += 32) {
-        const size_t goff = (size_t)fI0 * L.nf_pad + c0 + c * kVec;
-        const int soff = c * kVec;
-        for (int f = warp; f < nfI; f += kExpandThreads / 32) {
-            if (need_ab) cp_async<16>(Vab + f * L.vstride + soff, V + goff + (size_t)f * L.nf_pad);
-            if (need_ba) cp_async<16>(Vba + f * L.vstride + soff, Vt + goff + (size_t)f * L.nf_pad);
-        }
-    }
-    if (threadIdx.x < kMTile) {
-        const int m = mJ0 + min((int)threadIdx.x, cJ - 1);
-        cp_async<4>(metaJ + threadIdx.x, L.mem_fam + m);
-        cp_async<4>(metaJ + kMTile + threadIdx.x, L.mem_ind + m);
-        cp_async<4>(metaJ + 2 * kMTile + threadIdx.x, L.mem_slot + m);
-    }
-}
-
-template <typename T, int kStages>
 __global__ void __launch_bounds__(kExpandThreads)
 expand_kernel(T *__restrict__ A, int64_t ld, const T *__restrict__ V, const T *__restrict__ Vt,
               const T *__restrict__ Dg, LayerArgs L) {
     constexpr int kVec = 16 / sizeof(T);
-    constexpr int kRows = kMTile / (kExpandThreads / 16);   // rows per thread
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    int4 *metaI = reinterpret_cast<int4 *>(smem_raw);
-    int32_t *famI = reinterpret_cast<int32_t *>(metaI + kMTile);
-    unsigned char *stages = reinterpret_cast<unsigned char *>(famI + kMTile);
-    const size_t stage_bytes = expand_stage_bytes<T>(L.vrows, L.vstride);
-    const int vba_off = L.vrows * L.vstride * (int)sizeof(T);   // Vba relative to Vab, bytes
-    const int I = blockIdx.y;
-    const int mI0 = I * kMTile;
-    const int cI = min(kMTile, L.n_new - mI0);
-    const int fI0 = L.mt_fam0[I], nfI = L.mt_nfam[I];
-    const int minI = L.mt_minrank[I], maxI = L.mt_maxrank[I];
-    const int Jbeg = blockIdx.x * kJChunk, Jend = min(L.n_mtiles, Jbeg + kJChunk);
-    expand_prefetch<T>(stages, V, Vt, L, Jbeg, fI0, nfI, minI, maxI);
-    cp_async_commit();
-    if (threadIdx.x < kMTile) {
-        const int m = mI0 + min((int)threadIdx.x, cI - 1);
-        const int fam = L.mem_fam[m];
-        const unsigned long long p = (unsigned long long)(A + (int64_t)L.mem_slot[m] * ld);
-        metaI[threadIdx.x] = make_int4((fam - fI0) * L.vstride * (int)sizeof(T), L.mem_ind[m], (int)(unsigned)p,
-                                       (int)(unsigned)(p >> 32));
-        famI[threadIdx.x] = fam;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row0 = (blockIdx.x * kEWarps + warp) * kERows;
+    if (row0 >= L.n_new) return;                            // no block-wide barrier below
+    const int nr = min(kERows, L.n_new - row0);
+    const size_t stage_bytes = expand_stage_bytes<T>(L.vstride);
+    unsigned char *mine = smem_raw + (size_t)warp * 2 * stage_bytes;
+    const int vba_off = kERows * L.vstride * (int)sizeof(T);
+
+    // ---- the warp's rows: couple, rank, row pointer (registers) ----
+    const int mrow = row0 + min(lane, nr - 1);
+    const int myfam = L.mem_fam[mrow], myrank = L.mem_ind[mrow], myslot = L.mem_slot[mrow];
+    const int f0 = __shfl_sync(0xffffffffu, myfam, 0);
+    const int nfr = __shfl_sync(0xffffffffu, myfam, nr - 1) - f0 + 1;      // <= kERows couples
+    int minI = myrank, maxI = myrank;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {                       // lanes >= nr repeat the last row
+        minI = min(minI, __shfl_xor_sync(0xffffffffu, minI, o));
+        maxI = max(maxI, __shfl_xor_sync(0xffffffffu, maxI, o));
     }
-    const int cg = threadIdx.x & 15, rg = threadIdx.x >> 4;
-    const int j0 = 4 * cg;
-    int buf = 0;
-    for (int J = Jbeg; J < Jend; J++, buf = (buf + 1) % kStages) {
-        if (kStages > 1 && J + 1 < Jend) {
-            expand_prefetch<T>(stages + ((buf + 1) % kStages) * stage_bytes, V, Vt, L, J + 1, fI0, nfI, minI, maxI);
-            cp_async_commit();
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
+    minI = __shfl_sync(0xffffffffu, minI, 0); maxI = __shfl_sync(0xffffffffu, maxI, 0);
+    unsigned roff[kERows];
+    int rrank[kERows], rfam[kERows];
+    T *rptr[kERows];
+#pragma unroll
+    for (int r = 0; r < kERows; r++) {
+        rfam[r] = __shfl_sync(0xffffffffu, myfam, r);
+        roff[r] = (unsigned)((rfam[r] - f0) * L.vstride) * (unsigned)sizeof(T);
+        rrank[r] = __shfl_sync(0xffffffffu, myrank, r);
+        rptr[r] = A + (int64_t)__shfl_sync(0xffffffffu, myslot, r) * ld;
+    }
+    // ---- the column steps of this CTA: tile metadata once, in registers (lane = step) ----
+    const int Jbeg = blockIdx.y * kEChunk, Jend = min(L.n_mtiles, Jbeg + kEChunk);
+    const int Jl = min(Jbeg + lane, L.n_mtiles - 1);
+    const int t_fam0 = L.mt_fam0[Jl], t_nfam = L.mt_nfam[Jl];
+    const int t_min = L.mt_minrank[Jl], t_max = L.mt_maxrank[Jl];
+
+    auto prefetch = [&](int J, int buf) {
+        unsigned char *stage = mine + (size_t)buf * stage_bytes;
+        T *Vab = reinterpret_cast<T *>(stage);
+        T *Vba = reinterpret_cast<T *>(stage + vba_off);
+        int32_t *metaJ = reinterpret_cast<int32_t *>(stage + 2 * (size_t)vba_off);
+        const int fJ0 = __shfl_sync(0xffffffffu, t_fam0, J - Jbeg), nfJ = __shfl_sync(0xffffffffu, t_nfam, J - Jbeg);
+        const bool need_ab = maxI > __shfl_sync(0xffffffffu, t_min, J - Jbeg);   // a row outranks a column
+        const bool need_ba = __shfl_sync(0xffffffffu, t_max, J - Jbeg) > minI;
+        const int c0 = fJ0 & ~(kVec - 1);                   // 16-byte aligned column start
+        const int nchunk = (fJ0 + nfJ - c0 + kVec - 1) / kVec;
+        for (int c = lane; c < nchunk; c += 32) {
+            const size_t goff = (size_t)f0 * L.nf_pad + c0 + c * kVec;
+            for (int f = 0; f < nfr; f++) {
+                if (need_ab) cp_async<16>(Vab + f * L.vstride + c * kVec, V + goff + (size_t)f * L.nf_pad);
+                if (need_ba) cp_async<16>(Vba + f * L.vstride + c * kVec, Vt + goff + (size_t)f * L.nf_pad);
+            }
         }
-        __syncthreads();                                   // tile J (and metaI) visible to everybody
-        const unsigned char *stage = stages + buf * stage_bytes;
-        const int32_t *metaJ = reinterpret_cast<const int32_t *>(stage + 2 * (size_t)vba_off);
-        const int cJ = min(kMTile, L.n_new - J * kMTile);
-        if (j0 < cJ) {
-            const int c0 = L.mt_fam0[J] & ~(kVec - 1);
-            const unsigned sbase = (unsigned)__cvta_generic_to_shared(stage);
-            unsigned go[4];
-            int rj[4], sj[4];
+        // column metadata: 4 members per lane (clamped at the end of the layer)
+        const int mJ0 = J * kMTile;
+        if (mJ0 + 4 * lane + 3 < L.n_new) {
+            cp_async<16>(metaJ + 4 * lane, L.mem_fam + mJ0 + 4 * lane);
+            cp_async<16>(metaJ + kMTile + 4 * lane, L.mem_ind + mJ0 + 4 * lane);
+            cp_async<16>(metaJ + 2 * kMTile + 4 * lane, L.mem_slot + mJ0 + 4 * lane);
+        } else {
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                go[k] = sbase + (unsigned)(metaJ[j0 + k] - c0) * (unsigned)sizeof(T);   // column, shared address
-                rj[k] = metaJ[kMTile + j0 + k]; sj[k] = metaJ[2 * kMTile + j0 + k];
+                const int m = min(mJ0 + 4 * lane + k, L.n_new - 1);
+                cp_async<4>(metaJ + 4 * lane + k, L.mem_fam + m);
+                cp_async<4>(metaJ + kMTile + 4 * lane + k, L.mem_ind + m);
+                cp_async<4>(metaJ + 2 * kMTile + 4 * lane + k, L.mem_slot + m);
             }
-            const bool vec = (j0 + 3 < cJ) && ((sj[0] & 3) == 0) && sj[1] == sj[0] + 1 && sj[2] == sj[0] + 2 &&
+        }
+        cp_async_commit();
+    };
+
+    prefetch(Jbeg, 0);
+    int buf = 0;
+    for (int J = Jbeg; J < Jend; J++, buf ^= 1) {
+        if (J + 1 < Jend) { prefetch(J + 1, buf ^ 1); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncwarp();                                      // other lanes' copies are visible
+        const unsigned char *stage = mine + (size_t)buf * stage_bytes;
+        const int4 *metaJ = reinterpret_cast<const int4 *>(stage + 2 * (size_t)vba_off);
+        const int mJ0 = J * kMTile, j0 = mJ0 + 4 * lane;
+        const int c0 = __shfl_sync(0xffffffffu, t_fam0, J - Jbeg) & ~(kVec - 1);
+        if (j0 < L.n_new) {
+            const int4 gj = metaJ[lane], rj4 = metaJ[kMTile / 4 + lane], sj4 = metaJ[2 * kMTile / 4 + lane];
+            const unsigned sbase = (unsigned)__cvta_generic_to_shared(stage);
+            const unsigned go[4] = {sbase + (unsigned)(gj.x - c0) * (unsigned)sizeof(T), sbase + (unsigned)(gj.y - c0) * (unsigned)sizeof(T),
+                                    sbase + (unsigned)(gj.z - c0) * (unsigned)sizeof(T), sbase + (unsigned)(gj.w - c0) * (unsigned)sizeof(T)};
+            const int rj[4] = {rj4.x, rj4.y, rj4.z, rj4.w}, sj[4] = {sj4.x, sj4.y, sj4.z, sj4.w};
+            const int ncol = min(4, L.n_new - j0);
+            const bool vec = ncol == 4 && ((sj[0] & 3) == 0) && sj[1] == sj[0] + 1 && sj[2] == sj[0] + 2 &&
                              sj[3] == sj[0] + 3;
-            const int dj = (I == J) ? j0 : -8;             // tile-local column of a diagonal entry, if any
 #pragma unroll
-            for (int r = 0; r < kRows; r++) {
-                const int il = rg + (kExpandThreads / 16) * r;
-                if (il < cI) {
-                    const int4 mi = metaI[il];             // couple row byte offset, rank, row pointer
+            for (int r = 0; r < kERows; r++) {
+                if (r < nr) {
                     T v[4];
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
-                        // the higher rank is climbed first: V[F, G] if the row member outranks
-                        // the column member, V[G, F] = Vt[F, G] otherwise
-                        const unsigned addr = go[k] + (unsigned)mi.x + (mi.y > rj[k] ? 0u : (unsigned)vba_off);
+                        // the higher rank is climbed first: V[F, G] if the row member outranks the
+                        // column member, V[G, F] = Vt[F, G] otherwise
+                        const unsigned addr = go[k] + roff[r] + (rrank[r] > rj[k] ? 0u : (unsigned)vba_off);
                         if constexpr (sizeof(T) == 4) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[k]) : "r"(addr));
                         else asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v[k]) : "r"(addr));
                     }
-                    if ((unsigned)(il - dj) < 4u) {        // own diagonal entry (compute.jl:148-155)
-                        const T d = Dg[famI[il]];
+                    const int dk = row0 + r - j0;          // own diagonal entry (compute.jl:148-155)
+                    if ((unsigned)dk < 4u) {
+                        const T d = Dg[rfam[r]];
 #pragma unroll
-                        for (int k = 0; k < 4; k++) if (il - dj == k) v[k] = d;
+                        for (int k = 0; k < 4; k++) if (dk == k) v[k] = d;
                     }
-                    T *row = reinterpret_cast<T *>(((unsigned long long)(unsigned)mi.w << 32) | (unsigned)mi.z);
-                    if (vec) store_vec4(row + sj[0], v);
+                    if (vec) store_vec4(rptr[r] + sj[0], v);
                     else {
 #pragma unroll
-                        for (int k = 0; k < 4; k++) if (j0 + k < cJ) row[sj[k]] = v[k];
+                        for (int k = 0; k < 4; k++) if (k < ncol) rptr[r][sj[k]] = v[k];
                     }
                 }
             }
         }
-        __syncthreads();                                   // done with this stage before it is refilled
-        if (kStages == 1 && J + 1 < Jend) {
-            expand_prefetch<T>(stages, V, Vt, L, J + 1, fI0, nfI, minI, maxI);
-            cp_async_commit();
-        }
+        __syncwarp();                                      // stage free before it is refilled
     }
 }
 

@@ -139,6 +139,8 @@ int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t 
         L.ref_founders = t > 0 ? cut_size[t - 1] : 0;
         L.ref_probands = cut_size[t];
         L.ref_both = t > 0 ? both_size[t - 1] : 0;
+        // member arrays of a layer start 16-byte aligned (the expand kernel copies them in 16-byte chunks)
+        while (P.mem_ind.size() % 4) { P.mem_ind.push_back(0); P.mem_slot.push_back(0); P.mem_fam.push_back(0); }
         L.mem_off = P.mem_ind.size();
         L.fam_off = P.fam_pf.size();
         L.flag_off = P.flags.size();

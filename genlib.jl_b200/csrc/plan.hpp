@@ -20,7 +20,7 @@ namespace genlib {
 
 constexpr int kPTile = 128;      // frontier columns per cross-kernel tile (and slot-range alignment)
 constexpr int kFTile = 32;       // families per cross-kernel tile
-constexpr int kMTile = 64;       // members per intra-kernel tile
+constexpr int kMTile = 128;      // member columns per expand step (4 per lane)
 constexpr int kMaxFamily = 32;   // sibships larger than this are split (bounds per-tile work)
 
 constexpr uint8_t kFlagLive = 1;     // slot holds an individual that is live before the step
