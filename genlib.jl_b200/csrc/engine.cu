@@ -146,7 +146,7 @@ int launch_layers(genlib_engine &E, bool timed) {
     const int64_t ld = P.capacity;
     const size_t cross_smem = (size_t)kFTile * kSRStride * sizeof(double);
     const int vec = 16 / (int)sizeof(T);
-    const size_t expand_smem_max = (size_t)kEWarps * 2 * expand_stage_bytes<T>(kMTile + vec);
+    const size_t expand_smem_max = (size_t)kEWarps * expand_warp_bytes<T>(kMTile + vec);
     CU(cudaFuncSetAttribute(expand_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem_max));
     CU(cudaFuncSetAttribute(cross_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CU(cudaFuncSetAttribute(expand_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -177,7 +177,7 @@ int launch_layers(genlib_engine &E, bool timed) {
         {
             const int rows_per_cta = kEWarps * kERows;
             dim3 grid((unsigned)((L.n_new + rows_per_cta - 1) / rows_per_cta), (unsigned)((L.n_mtiles + kEChunk - 1) / kEChunk));
-            const size_t smem = (size_t)kEWarps * 2 * expand_stage_bytes<T>(a.vstride);
+            const size_t smem = (size_t)kEWarps * expand_warp_bytes<T>(a.vstride);
             expand_kernel<T><<<grid, kExpandThreads, smem, E.stream>>>(A, ld, V, Vt, Dg, a);
             launches++;
         }

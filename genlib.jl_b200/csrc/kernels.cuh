@@ -214,31 +214,50 @@ couple_kernel(const T *__restrict__ A, int64_t ld, const double *__restrict__ Rt
 // the warp that owns those rows -- no transposed stores, no block-wide barriers.
 //   entry (i, j), i in couple F, j in couple G:  rank_i > rank_j ? V[F, G] : V[G, F] = Vt[F, G]
 //   (compute.jl:130-147: the higher rank is climbed first);  i == j: Dg[F].
-// The <= kERows couple rows of V and Vt that a warp needs for the next column step, and that
-// step's column metadata, stream into warp-private shared memory with cp.async while the
-// current step is expanded (double buffered).
+// The <= kERows couple rows of V and Vt a warp needs for the next column step, and that
+// step's column metadata, are contiguous in global memory: each is ONE TMA bulk copy
+// (cp.async.bulk, SASS UBLKCP) into warp-private shared memory, completing on a per-warp
+// mbarrier, double buffered against the expansion of the current step.
 // =====================================================================================
 constexpr int kERows = 8;          // member rows per warp
 constexpr int kEWarps = 4;         // warps per CTA
 constexpr int kEChunk = 16;        // column steps per CTA
 constexpr int kExpandThreads = kEWarps * 32;
 
-template <int BYTES>
-__device__ __forceinline__ void cp_async(void *smem, const void *gmem) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    if constexpr (BYTES == 16)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
-    else
-        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(s), "l"(gmem), "n"(BYTES) : "memory");
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+// global -> shared bulk copy (16-byte aligned, size a multiple of 16), completes on `bar`
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 
-// per warp and stage: Vab[kERows][vstride], Vba[kERows][vstride], famJ/rankJ/slotJ[kMTile]
+// per warp: 2 mbarriers (16 B), then per stage Vab[kERows][vstride], Vba[kERows][vstride], famJ/rankJ/slotJ[kMTile]
 template <typename T>
 __host__ __device__ inline size_t expand_stage_bytes(int vstride) {
     return 2 * (size_t)kERows * vstride * sizeof(T) + 3 * kMTile * sizeof(int32_t);
+}
+template <typename T>
+__host__ __device__ inline size_t expand_warp_bytes(int vstride) { return 16 + 2 * expand_stage_bytes<T>(vstride); }
+
+template <typename T>
+__device__ __forceinline__ T lds(unsigned addr) {
+    T v;
+    if constexpr (sizeof(T) == 4) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    else asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
 }
 
 template <typename T>
@@ -251,9 +270,13 @@ expand_kernel(T *__restrict__ A, int64_t ld, const T *__restrict__ V, const T *_
     const int row0 = (blockIdx.x * kEWarps + warp) * kERows;
     if (row0 >= L.n_new) return;                            // no block-wide barrier below
     const int nr = min(kERows, L.n_new - row0);
-    const size_t stage_bytes = expand_stage_bytes<T>(L.vstride);
-    unsigned char *mine = smem_raw + (size_t)warp * 2 * stage_bytes;
-    const int vba_off = kERows * L.vstride * (int)sizeof(T);
+    const unsigned stage_bytes = (unsigned)expand_stage_bytes<T>(L.vstride);
+    const unsigned mine = smem_u32(smem_raw + (size_t)warp * expand_warp_bytes<T>(L.vstride));
+    const unsigned stage0 = mine + 16;
+    const unsigned vba_off = (unsigned)(kERows * L.vstride) * (unsigned)sizeof(T);
+    if (lane == 0) { mbar_init(mine, 1); mbar_init(mine + 8, 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
 
     // ---- the warp's rows: couple, rank, row pointer (registers) ----
     const int mrow = row0 + min(lane, nr - 1);
@@ -268,12 +291,11 @@ expand_kernel(T *__restrict__ A, int64_t ld, const T *__restrict__ V, const T *_
     }
     minI = __shfl_sync(0xffffffffu, minI, 0); maxI = __shfl_sync(0xffffffffu, maxI, 0);
     unsigned roff[kERows];
-    int rrank[kERows], rfam[kERows];
+    int rrank[kERows];
     T *rptr[kERows];
 #pragma unroll
     for (int r = 0; r < kERows; r++) {
-        rfam[r] = __shfl_sync(0xffffffffu, myfam, r);
-        roff[r] = (unsigned)((rfam[r] - f0) * L.vstride) * (unsigned)sizeof(T);
+        roff[r] = (unsigned)((__shfl_sync(0xffffffffu, myfam, r) - f0) * L.vstride) * (unsigned)sizeof(T);
         rrank[r] = __shfl_sync(0xffffffffu, myrank, r);
         rptr[r] = A + (int64_t)__shfl_sync(0xffffffffu, myslot, r) * ld;
     }
@@ -284,76 +306,73 @@ expand_kernel(T *__restrict__ A, int64_t ld, const T *__restrict__ V, const T *_
     const int t_min = L.mt_minrank[Jl], t_max = L.mt_maxrank[Jl];
 
     auto prefetch = [&](int J, int buf) {
-        unsigned char *stage = mine + (size_t)buf * stage_bytes;
-        T *Vab = reinterpret_cast<T *>(stage);
-        T *Vba = reinterpret_cast<T *>(stage + vba_off);
-        int32_t *metaJ = reinterpret_cast<int32_t *>(stage + 2 * (size_t)vba_off);
+        const unsigned stage = stage0 + (unsigned)buf * stage_bytes, bar = mine + 8u * (unsigned)buf;
         const int fJ0 = __shfl_sync(0xffffffffu, t_fam0, J - Jbeg), nfJ = __shfl_sync(0xffffffffu, t_nfam, J - Jbeg);
         const bool need_ab = maxI > __shfl_sync(0xffffffffu, t_min, J - Jbeg);   // a row outranks a column
         const bool need_ba = __shfl_sync(0xffffffffu, t_max, J - Jbeg) > minI;
         const int c0 = fJ0 & ~(kVec - 1);                   // 16-byte aligned column start
-        const int nchunk = (fJ0 + nfJ - c0 + kVec - 1) / kVec;
-        for (int c = lane; c < nchunk; c += 32) {
-            const size_t goff = (size_t)f0 * L.nf_pad + c0 + c * kVec;
-            for (int f = 0; f < nfr; f++) {
-                if (need_ab) cp_async<16>(Vab + f * L.vstride + c * kVec, V + goff + (size_t)f * L.nf_pad);
-                if (need_ba) cp_async<16>(Vba + f * L.vstride + c * kVec, Vt + goff + (size_t)f * L.nf_pad);
-            }
-        }
-        // column metadata: 4 members per lane (clamped at the end of the layer)
+        const unsigned rowbytes = (unsigned)((fJ0 + nfJ - c0 + kVec - 1) / kVec) * 16u;
         const int mJ0 = J * kMTile;
-        if (mJ0 + 4 * lane + 3 < L.n_new) {
-            cp_async<16>(metaJ + 4 * lane, L.mem_fam + mJ0 + 4 * lane);
-            cp_async<16>(metaJ + kMTile + 4 * lane, L.mem_ind + mJ0 + 4 * lane);
-            cp_async<16>(metaJ + 2 * kMTile + 4 * lane, L.mem_slot + mJ0 + 4 * lane);
-        } else {
+        const bool full = mJ0 + kMTile <= L.n_new;
+        if (lane == 0)
+            mbar_expect_tx(bar, rowbytes * (unsigned)nfr * ((need_ab ? 1u : 0u) + (need_ba ? 1u : 0u)) +
+                                    (full ? 3u * kMTile * 4u : 0u));
+        __syncwarp();
+        const size_t goff = (size_t)(f0 + (lane & 7)) * L.nf_pad + c0;
+        const unsigned soff = (unsigned)((lane & 7) * L.vstride) * (unsigned)sizeof(T);
+        if (lane < 8) { if (need_ab && lane < nfr) bulk_g2s(stage + soff, V + goff, rowbytes, bar); }
+        else if (lane < 16) { if (need_ba && (lane & 7) < nfr) bulk_g2s(stage + vba_off + soff, Vt + goff, rowbytes, bar); }
+        else if (lane < 19 && full) {
+            const int32_t *src = (lane == 16 ? L.mem_fam : lane == 17 ? L.mem_ind : L.mem_slot) + mJ0;
+            bulk_g2s(stage + 2 * vba_off + (unsigned)(lane - 16) * kMTile * 4u, src, kMTile * 4u, bar);
+        }
+        if (!full) {                                        // ragged last tile of the layer: plain copies
+            int32_t *metaJ = reinterpret_cast<int32_t *>(smem_raw + (stage + 2 * vba_off - smem_u32(smem_raw)));
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const int m = min(mJ0 + 4 * lane + k, L.n_new - 1);
-                cp_async<4>(metaJ + 4 * lane + k, L.mem_fam + m);
-                cp_async<4>(metaJ + kMTile + 4 * lane + k, L.mem_ind + m);
-                cp_async<4>(metaJ + 2 * kMTile + 4 * lane + k, L.mem_slot + m);
+                metaJ[4 * lane + k] = L.mem_fam[m];
+                metaJ[kMTile + 4 * lane + k] = L.mem_ind[m];
+                metaJ[2 * kMTile + 4 * lane + k] = L.mem_slot[m];
             }
         }
-        cp_async_commit();
     };
 
     prefetch(Jbeg, 0);
+    unsigned parity0 = 0, parity1 = 0;
     int buf = 0;
     for (int J = Jbeg; J < Jend; J++, buf ^= 1) {
-        if (J + 1 < Jend) { prefetch(J + 1, buf ^ 1); cp_async_wait<1>(); }
-        else cp_async_wait<0>();
-        __syncwarp();                                      // other lanes' copies are visible
-        const unsigned char *stage = mine + (size_t)buf * stage_bytes;
-        const int4 *metaJ = reinterpret_cast<const int4 *>(stage + 2 * (size_t)vba_off);
+        if (J + 1 < Jend) prefetch(J + 1, buf ^ 1);
+        mbar_wait(mine + 8u * (unsigned)buf, buf ? parity1 : parity0);
+        if (buf) parity1 ^= 1; else parity0 ^= 1;
+        __syncwarp();
+        const unsigned stage = stage0 + (unsigned)buf * stage_bytes;
+        const unsigned metaJ = stage + 2 * vba_off;
         const int mJ0 = J * kMTile, j0 = mJ0 + 4 * lane;
         const int c0 = __shfl_sync(0xffffffffu, t_fam0, J - Jbeg) & ~(kVec - 1);
         if (j0 < L.n_new) {
-            const int4 gj = metaJ[lane], rj4 = metaJ[kMTile / 4 + lane], sj4 = metaJ[2 * kMTile / 4 + lane];
-            const unsigned sbase = (unsigned)__cvta_generic_to_shared(stage);
-            const unsigned go[4] = {sbase + (unsigned)(gj.x - c0) * (unsigned)sizeof(T), sbase + (unsigned)(gj.y - c0) * (unsigned)sizeof(T),
-                                    sbase + (unsigned)(gj.z - c0) * (unsigned)sizeof(T), sbase + (unsigned)(gj.w - c0) * (unsigned)sizeof(T)};
+            int4 gj, rj4, sj4;
+            asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(gj.x), "=r"(gj.y), "=r"(gj.z), "=r"(gj.w) : "r"(metaJ + 16u * lane));
+            asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(rj4.x), "=r"(rj4.y), "=r"(rj4.z), "=r"(rj4.w) : "r"(metaJ + kMTile * 4u + 16u * lane));
+            asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(sj4.x), "=r"(sj4.y), "=r"(sj4.z), "=r"(sj4.w) : "r"(metaJ + 2u * kMTile * 4u + 16u * lane));
+            const unsigned go[4] = {stage + (unsigned)(gj.x - c0) * (unsigned)sizeof(T), stage + (unsigned)(gj.y - c0) * (unsigned)sizeof(T),
+                                    stage + (unsigned)(gj.z - c0) * (unsigned)sizeof(T), stage + (unsigned)(gj.w - c0) * (unsigned)sizeof(T)};
             const int rj[4] = {rj4.x, rj4.y, rj4.z, rj4.w}, sj[4] = {sj4.x, sj4.y, sj4.z, sj4.w};
             const int ncol = min(4, L.n_new - j0);
             const bool vec = ncol == 4 && ((sj[0] & 3) == 0) && sj[1] == sj[0] + 1 && sj[2] == sj[0] + 2 &&
                              sj[3] == sj[0] + 3;
+            const int dk0 = row0 - j0;                     // the diagonal crosses this lane's columns?
 #pragma unroll
             for (int r = 0; r < kERows; r++) {
                 if (r < nr) {
                     T v[4];
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        // the higher rank is climbed first: V[F, G] if the row member outranks the
-                        // column member, V[G, F] = Vt[F, G] otherwise
-                        const unsigned addr = go[k] + roff[r] + (rrank[r] > rj[k] ? 0u : (unsigned)vba_off);
-                        if constexpr (sizeof(T) == 4) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[k]) : "r"(addr));
-                        else asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v[k]) : "r"(addr));
-                    }
-                    const int dk = row0 + r - j0;          // own diagonal entry (compute.jl:148-155)
-                    if ((unsigned)dk < 4u) {
-                        const T d = Dg[rfam[r]];
+                    for (int k = 0; k < 4; k++)            // the higher rank is climbed first: V[F, G] if the row
+                        v[k] = lds<T>(go[k] + roff[r] + (rrank[r] > rj[k] ? 0u : vba_off));   // outranks the column, else Vt[F, G]
+                    if ((unsigned)(dk0 + r) < 4u) {        // own diagonal entry (compute.jl:148-155)
+                        const T d = Dg[f0 + roff[r] / ((unsigned)L.vstride * (unsigned)sizeof(T))];
 #pragma unroll
-                        for (int k = 0; k < 4; k++) if (dk == k) v[k] = d;
+                        for (int k = 0; k < 4; k++) if (dk0 + r == k) v[k] = d;
                     }
                     if (vec) store_vec4(rptr[r] + sj[0], v);
                     else {
