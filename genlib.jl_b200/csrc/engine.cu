@@ -146,10 +146,11 @@ int launch_layers(genlib_engine &E, bool timed) {
     const int64_t ld = P.capacity;
     const size_t cross_smem = (size_t)kFTile * kSRStride * sizeof(double);
     const int vec = 16 / (int)sizeof(T);
-    const size_t expand_smem_max = (size_t)kEWarps * expand_warp_bytes<T>(kMTile + vec);
-    CU(cudaFuncSetAttribute(expand_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem_max));
+    const size_t expand_smem_max = (size_t)kEWarps * 2 * expand_stage_bytes<T>(kMTile + vec);
+    auto expand_fn = expand_kernel<T>;
+    CU(cudaFuncSetAttribute(expand_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem_max));
     CU(cudaFuncSetAttribute(cross_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    CU(cudaFuncSetAttribute(expand_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CU(cudaFuncSetAttribute(expand_fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     T *V = static_cast<T *>(E.V), *Vt = static_cast<T *>(E.Vt), *Dg = static_cast<T *>(E.Dg);
     const size_t couple_smem = sizeof(T) * kFTile * kCStride;
     CU(cudaFuncSetAttribute(couple_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)couple_smem));
@@ -176,9 +177,10 @@ int launch_layers(genlib_engine &E, bool timed) {
         if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
         {
             const int rows_per_cta = kEWarps * kERows;
-            dim3 grid((unsigned)((L.n_new + rows_per_cta - 1) / rows_per_cta), (unsigned)((L.n_mtiles + kEChunk - 1) / kEChunk));
-            const size_t smem = (size_t)kEWarps * expand_warp_bytes<T>(a.vstride);
-            expand_kernel<T><<<grid, kExpandThreads, smem, E.stream>>>(A, ld, V, Vt, Dg, a);
+            dim3 grid((unsigned)((L.n_mtiles + kEChunk - 1) / kEChunk), (unsigned)((L.n_new + rows_per_cta - 1) / rows_per_cta));
+            if (grid.y > 65535) return fail(GENLIB_EINVAL, "layer too wide for one expand launch");
+            const size_t smem = (size_t)kEWarps * 2 * expand_stage_bytes<T>(a.vstride);
+            expand_fn<<<grid, kExpandThreads, smem, E.stream>>>(A, ld, V, Vt, Dg, a);
             launches++;
         }
         if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));

@@ -214,43 +214,32 @@ couple_kernel(const T *__restrict__ A, int64_t ld, const double *__restrict__ Rt
 // the warp that owns those rows -- no transposed stores, no block-wide barriers.
 //   entry (i, j), i in couple F, j in couple G:  rank_i > rank_j ? V[F, G] : V[G, F] = Vt[F, G]
 //   (compute.jl:130-147: the higher rank is climbed first);  i == j: Dg[F].
-// The <= kERows couple rows of V and Vt a warp needs for the next column step, and that
-// step's column metadata, are contiguous in global memory: each is ONE TMA bulk copy
-// (cp.async.bulk, SASS UBLKCP) into warp-private shared memory, completing on a per-warp
-// mbarrier, double buffered against the expansion of the current step.
+// The <= kERows couple rows of V and Vt that a warp needs for the next column step, and that
+// step's column metadata, stream into warp-private shared memory with cp.async while the
+// current step is expanded (double buffered).
 // =====================================================================================
 constexpr int kERows = 8;          // member rows per warp
 constexpr int kEWarps = 4;         // warps per CTA
 constexpr int kEChunk = 16;        // column steps per CTA
 constexpr int kExpandThreads = kEWarps * 32;
 
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void *smem, const void *gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    if constexpr (BYTES == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(s), "l"(gmem), "n"(BYTES) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-    unsigned ok;
-    do {
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    } while (!ok);
-}
-// global -> shared bulk copy (16-byte aligned, size a multiple of 16), completes on `bar`
-__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-// per warp: 2 mbarriers (16 B), then per stage Vab[kERows][vstride], Vba[kERows][vstride], famJ/rankJ/slotJ[kMTile]
+// per warp and stage: Vab[kERows][vstride], Vba[kERows][vstride], famJ/rankJ/slotJ[kMTile]
 template <typename T>
 __host__ __device__ inline size_t expand_stage_bytes(int vstride) {
     return 2 * (size_t)kERows * vstride * sizeof(T) + 3 * kMTile * sizeof(int32_t);
 }
-template <typename T>
-__host__ __device__ inline size_t expand_warp_bytes(int vstride) { return 16 + 2 * expand_stage_bytes<T>(vstride); }
 
 template <typename T>
 __device__ __forceinline__ T lds(unsigned addr) {
@@ -258,6 +247,42 @@ __device__ __forceinline__ T lds(unsigned addr) {
     if constexpr (sizeof(T) == 4) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
     else asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
     return v;
+}
+__device__ __forceinline__ int4 lds_int4(unsigned addr) {
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void cp_async16_s(unsigned smem, const void *gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem), "l"(gmem) : "memory");
+}
+
+// One column step of one warp.  FAST: all kERows rows exist, the column tile is complete and the
+// lane's four column slots are consecutive and 16-byte aligned (one 128-bit store per row).
+template <typename T, bool FAST, bool DIAG>
+__device__ __forceinline__ void expand_step(const unsigned (&go)[4], const int (&rj)[4], const int (&sj)[4],
+                                            const unsigned (&roff)[kERows], const int (&rrank)[kERows],
+                                            T *const (&rptr)[kERows], unsigned vba_off, int nr, int ncol, int dk0,
+                                            const T *__restrict__ Dg, const int (&rfam)[kERows]) {
+#pragma unroll
+    for (int r = 0; r < kERows; r++) {
+        if (FAST || r < nr) {
+            T v[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++)                    // the higher rank is climbed first: V[F, G] if the row
+                v[k] = lds<T>(go[k] + roff[r] + (rrank[r] > rj[k] ? 0u : vba_off));   // outranks the column, else Vt[F, G]
+            if (DIAG && (unsigned)(dk0 + r) < 4u) {        // own diagonal entry (compute.jl:148-155)
+                const T d = Dg[rfam[r]];
+#pragma unroll
+                for (int k = 0; k < 4; k++) if (dk0 + r == k) v[k] = d;
+            }
+            if (FAST) store_vec4(rptr[r] + sj[0], v);
+            else {
+#pragma unroll
+                for (int k = 0; k < 4; k++) if (k < ncol) rptr[r][sj[k]] = v[k];
+            }
+        }
+    }
 }
 
 template <typename T>
@@ -267,16 +292,16 @@ expand_kernel(T *__restrict__ A, int64_t ld, const T *__restrict__ V, const T *_
     constexpr int kVec = 16 / sizeof(T);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row0 = (blockIdx.x * kEWarps + warp) * kERows;
+    // blockIdx.x = column chunk (fastest): CTAs that run together stream the SAME couple rows of
+    // V / Vt and the same output rows at adjacent columns
+    const int row0 = (blockIdx.y * kEWarps + warp) * kERows;
     if (row0 >= L.n_new) return;                            // no block-wide barrier below
     const int nr = min(kERows, L.n_new - row0);
     const unsigned stage_bytes = (unsigned)expand_stage_bytes<T>(L.vstride);
-    const unsigned mine = smem_u32(smem_raw + (size_t)warp * expand_warp_bytes<T>(L.vstride));
-    const unsigned stage0 = mine + 16;
-    const unsigned vba_off = (unsigned)(kERows * L.vstride) * (unsigned)sizeof(T);
-    if (lane == 0) { mbar_init(mine, 1); mbar_init(mine + 8, 1); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    __syncwarp();
+    const unsigned mine = (unsigned)__cvta_generic_to_shared(smem_raw) + (unsigned)warp * 2u * stage_bytes;
+    const unsigned row_bytes = (unsigned)L.vstride * (unsigned)sizeof(T);
+    const unsigned vba_off = kERows * row_bytes;
+    const unsigned meta_off = 2 * vba_off;
 
     // ---- the warp's rows: couple, rank, row pointer (registers) ----
     const int mrow = row0 + min(lane, nr - 1);
@@ -291,70 +316,79 @@ expand_kernel(T *__restrict__ A, int64_t ld, const T *__restrict__ V, const T *_
     }
     minI = __shfl_sync(0xffffffffu, minI, 0); maxI = __shfl_sync(0xffffffffu, maxI, 0);
     unsigned roff[kERows];
-    int rrank[kERows];
+    int rrank[kERows], rfam[kERows];
     T *rptr[kERows];
 #pragma unroll
     for (int r = 0; r < kERows; r++) {
-        roff[r] = (unsigned)((__shfl_sync(0xffffffffu, myfam, r) - f0) * L.vstride) * (unsigned)sizeof(T);
+        rfam[r] = __shfl_sync(0xffffffffu, myfam, r);
+        roff[r] = (unsigned)(rfam[r] - f0) * row_bytes;
         rrank[r] = __shfl_sync(0xffffffffu, myrank, r);
-        rptr[r] = A + (int64_t)__shfl_sync(0xffffffffu, myslot, r) * ld;
+        unsigned long long p = (unsigned long long)(A + (int64_t)__shfl_sync(0xffffffffu, myslot, r) * ld);
+        asm volatile("" : "+l"(p));                        // keep the pointer; do not recompute it per store
+        rptr[r] = reinterpret_cast<T *>(p);
     }
-    // ---- the column steps of this CTA: tile metadata once, in registers (lane = step) ----
-    const int Jbeg = blockIdx.y * kEChunk, Jend = min(L.n_mtiles, Jbeg + kEChunk);
-    const int Jl = min(Jbeg + lane, L.n_mtiles - 1);
-    const int t_fam0 = L.mt_fam0[Jl], t_nfam = L.mt_nfam[Jl];
-    const int t_min = L.mt_minrank[Jl], t_max = L.mt_maxrank[Jl];
+    // ---- the column steps of this CTA, one per lane: aligned first couple column, 16-byte chunks
+    //      per couple row, which orientations can be selected at all ----
+    const int Jbeg = blockIdx.x * kEChunk, Jend = min(L.n_mtiles, Jbeg + kEChunk);
+    int t_c0, t_info;
+    {
+        const int Jl = min(Jbeg + lane, L.n_mtiles - 1);
+        const int fJ0 = L.mt_fam0[Jl], nfJ = L.mt_nfam[Jl];
+        t_c0 = fJ0 & ~(kVec - 1);
+        const int nchunk = (fJ0 + nfJ - t_c0 + kVec - 1) / kVec;
+        t_info = nchunk | (maxI > L.mt_minrank[Jl] ? 0x100 : 0)      // some row outranks some column
+                        | (L.mt_maxrank[Jl] > minI ? 0x200 : 0);
+    }
+    const T *vsrc = V + (size_t)f0 * L.nf_pad + lane * kVec;
+    const T *vtsrc = Vt + (size_t)f0 * L.nf_pad + lane * kVec;
+    const int32_t *msrc = L.mem_fam + 4 * lane;
+    const long long mstride1 = L.mem_ind - L.mem_fam, mstride2 = L.mem_slot - L.mem_fam;
 
     auto prefetch = [&](int J, int buf) {
-        const unsigned stage = stage0 + (unsigned)buf * stage_bytes, bar = mine + 8u * (unsigned)buf;
-        const int fJ0 = __shfl_sync(0xffffffffu, t_fam0, J - Jbeg), nfJ = __shfl_sync(0xffffffffu, t_nfam, J - Jbeg);
-        const bool need_ab = maxI > __shfl_sync(0xffffffffu, t_min, J - Jbeg);   // a row outranks a column
-        const bool need_ba = __shfl_sync(0xffffffffu, t_max, J - Jbeg) > minI;
-        const int c0 = fJ0 & ~(kVec - 1);                   // 16-byte aligned column start
-        const unsigned rowbytes = (unsigned)((fJ0 + nfJ - c0 + kVec - 1) / kVec) * 16u;
-        const int mJ0 = J * kMTile;
-        const bool full = mJ0 + kMTile <= L.n_new;
-        if (lane == 0)
-            mbar_expect_tx(bar, rowbytes * (unsigned)nfr * ((need_ab ? 1u : 0u) + (need_ba ? 1u : 0u)) +
-                                    (full ? 3u * kMTile * 4u : 0u));
-        __syncwarp();
-        const size_t goff = (size_t)(f0 + (lane & 7)) * L.nf_pad + c0;
-        const unsigned soff = (unsigned)((lane & 7) * L.vstride) * (unsigned)sizeof(T);
-        if (lane < 8) { if (need_ab && lane < nfr) bulk_g2s(stage + soff, V + goff, rowbytes, bar); }
-        else if (lane < 16) { if (need_ba && (lane & 7) < nfr) bulk_g2s(stage + vba_off + soff, Vt + goff, rowbytes, bar); }
-        else if (lane < 19 && full) {
-            const int32_t *src = (lane == 16 ? L.mem_fam : lane == 17 ? L.mem_ind : L.mem_slot) + mJ0;
-            bulk_g2s(stage + 2 * vba_off + (unsigned)(lane - 16) * kMTile * 4u, src, kMTile * 4u, bar);
+        const unsigned stage = mine + (unsigned)buf * stage_bytes;
+        const int c0 = __shfl_sync(0xffffffffu, t_c0, J - Jbeg), info = __shfl_sync(0xffffffffu, t_info, J - Jbeg);
+        const int nchunk = info & 0xff;
+        for (int c = lane; c < nchunk; c += 32) {           // one pass (two for the 8-byte type)
+            unsigned dst = stage + (unsigned)c * 16u;
+            const T *a = vsrc + c0 + (c - lane) * kVec, *b = vtsrc + c0 + (c - lane) * kVec;
+            for (int f = 0; f < nfr; f++, dst += row_bytes, a += L.nf_pad, b += L.nf_pad) {
+                if (info & 0x100) cp_async16_s(dst, a);
+                if (info & 0x200) cp_async16_s(dst + vba_off, b);
+            }
         }
-        if (!full) {                                        // ragged last tile of the layer: plain copies
-            int32_t *metaJ = reinterpret_cast<int32_t *>(smem_raw + (stage + 2 * vba_off - smem_u32(smem_raw)));
+        // column metadata: 4 members per lane (clamped at the ragged end of the layer)
+        const int mJ0 = J * kMTile;
+        const unsigned mdst = stage + meta_off + 16u * (unsigned)lane;
+        if (mJ0 + 4 * lane + 3 < L.n_new) {
+            cp_async16_s(mdst, msrc + mJ0);
+            cp_async16_s(mdst + kMTile * 4u, msrc + mJ0 + mstride1);
+            cp_async16_s(mdst + 2u * kMTile * 4u, msrc + mJ0 + mstride2);
+        } else {
+            int32_t *metaJ = reinterpret_cast<int32_t *>(smem_raw + (stage + meta_off - (unsigned)__cvta_generic_to_shared(smem_raw)));
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const int m = min(mJ0 + 4 * lane + k, L.n_new - 1);
-                metaJ[4 * lane + k] = L.mem_fam[m];
-                metaJ[kMTile + 4 * lane + k] = L.mem_ind[m];
-                metaJ[2 * kMTile + 4 * lane + k] = L.mem_slot[m];
+                cp_async<4>(metaJ + 4 * lane + k, L.mem_fam + m);
+                cp_async<4>(metaJ + kMTile + 4 * lane + k, L.mem_ind + m);
+                cp_async<4>(metaJ + 2 * kMTile + 4 * lane + k, L.mem_slot + m);
             }
         }
+        cp_async_commit();
     };
 
     prefetch(Jbeg, 0);
-    unsigned parity0 = 0, parity1 = 0;
     int buf = 0;
     for (int J = Jbeg; J < Jend; J++, buf ^= 1) {
-        if (J + 1 < Jend) prefetch(J + 1, buf ^ 1);
-        mbar_wait(mine + 8u * (unsigned)buf, buf ? parity1 : parity0);
-        if (buf) parity1 ^= 1; else parity0 ^= 1;
-        __syncwarp();
-        const unsigned stage = stage0 + (unsigned)buf * stage_bytes;
-        const unsigned metaJ = stage + 2 * vba_off;
+        if (J + 1 < Jend) { prefetch(J + 1, buf ^ 1); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncwarp();                                      // other lanes' copies are visible
+        const unsigned stage = mine + (unsigned)buf * stage_bytes;
         const int mJ0 = J * kMTile, j0 = mJ0 + 4 * lane;
-        const int c0 = __shfl_sync(0xffffffffu, t_fam0, J - Jbeg) & ~(kVec - 1);
+        const int c0 = __shfl_sync(0xffffffffu, t_c0, J - Jbeg);
         if (j0 < L.n_new) {
-            int4 gj, rj4, sj4;
-            asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(gj.x), "=r"(gj.y), "=r"(gj.z), "=r"(gj.w) : "r"(metaJ + 16u * lane));
-            asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(rj4.x), "=r"(rj4.y), "=r"(rj4.z), "=r"(rj4.w) : "r"(metaJ + kMTile * 4u + 16u * lane));
-            asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(sj4.x), "=r"(sj4.y), "=r"(sj4.z), "=r"(sj4.w) : "r"(metaJ + 2u * kMTile * 4u + 16u * lane));
+            const int4 gj = lds_int4(stage + meta_off + 16u * lane);
+            const int4 rj4 = lds_int4(stage + meta_off + kMTile * 4u + 16u * lane);
+            const int4 sj4 = lds_int4(stage + meta_off + 2u * kMTile * 4u + 16u * lane);
             const unsigned go[4] = {stage + (unsigned)(gj.x - c0) * (unsigned)sizeof(T), stage + (unsigned)(gj.y - c0) * (unsigned)sizeof(T),
                                     stage + (unsigned)(gj.z - c0) * (unsigned)sizeof(T), stage + (unsigned)(gj.w - c0) * (unsigned)sizeof(T)};
             const int rj[4] = {rj4.x, rj4.y, rj4.z, rj4.w}, sj[4] = {sj4.x, sj4.y, sj4.z, sj4.w};
@@ -362,24 +396,12 @@ expand_kernel(T *__restrict__ A, int64_t ld, const T *__restrict__ V, const T *_
             const bool vec = ncol == 4 && ((sj[0] & 3) == 0) && sj[1] == sj[0] + 1 && sj[2] == sj[0] + 2 &&
                              sj[3] == sj[0] + 3;
             const int dk0 = row0 - j0;                     // the diagonal crosses this lane's columns?
-#pragma unroll
-            for (int r = 0; r < kERows; r++) {
-                if (r < nr) {
-                    T v[4];
-#pragma unroll
-                    for (int k = 0; k < 4; k++)            // the higher rank is climbed first: V[F, G] if the row
-                        v[k] = lds<T>(go[k] + roff[r] + (rrank[r] > rj[k] ? 0u : vba_off));   // outranks the column, else Vt[F, G]
-                    if ((unsigned)(dk0 + r) < 4u) {        // own diagonal entry (compute.jl:148-155)
-                        const T d = Dg[f0 + roff[r] / ((unsigned)L.vstride * (unsigned)sizeof(T))];
-#pragma unroll
-                        for (int k = 0; k < 4; k++) if (dk0 + r == k) v[k] = d;
-                    }
-                    if (vec) store_vec4(rptr[r] + sj[0], v);
-                    else {
-#pragma unroll
-                        for (int k = 0; k < 4; k++) if (k < ncol) rptr[r][sj[k]] = v[k];
-                    }
-                }
+            const bool diag_tile = (row0 / kMTile) == J;   // warp-uniform (kERows divides kMTile)
+            if (nr == kERows && vec) {
+                if (diag_tile) expand_step<T, true, true>(go, rj, sj, roff, rrank, rptr, vba_off, nr, ncol, dk0, Dg, rfam);
+                else expand_step<T, true, false>(go, rj, sj, roff, rrank, rptr, vba_off, nr, ncol, dk0, Dg, rfam);
+            } else {
+                expand_step<T, false, true>(go, rj, sj, roff, rrank, rptr, vba_off, nr, ncol, dk0, Dg, rfam);
             }
         }
         __syncwarp();                                      // stage free before it is refilled
