@@ -51,6 +51,7 @@ SYMBOLS = {
     "genlib_version": (C.c_int, []),
     "genlib_last_error": (C.c_char_p, []),
     "genlib_device_count": (C.c_int, []),
+    "genlib_release_cache": (C.c_int, []),
     "genlib_pinned_alloc": (C.c_int, [C.c_size_t, C.POINTER(_P)]),
     "genlib_pinned_free": (C.c_int, [_P]),
     "genlib_plan_create": (C.c_int, [C.c_int32, _P, _P, C.c_int32, _P, C.c_int32, C.POINTER(_P)]),

@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -54,17 +55,63 @@ struct DeviceGuard {
     ~DeviceGuard() { if (active) cudaSetDevice(prev); }
 };
 
+// ---- device arena: ONE allocation per engine, cached across calls -------------------------
+// cudaMalloc / cudaFree of tens of GB cost hundreds of milliseconds; a repeated gen.phi call
+// (and the one-shot genlib_phi) reuses the previous arena when it is large enough.
+struct Arena {
+    void *base = nullptr;
+    size_t size = 0;
+    int device = -1;
+};
+
+class ArenaCache {
+    std::mutex mu_;
+    std::vector<Arena> free_;
+public:
+    cudaError_t acquire(int device, size_t bytes, Arena &out) {
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            int best = -1;
+            for (int i = 0; i < (int)free_.size(); i++)
+                if (free_[i].device == device && free_[i].size >= bytes && (best < 0 || free_[i].size < free_[best].size)) best = i;
+            if (best >= 0) { out = free_[best]; free_.erase(free_.begin() + best); return cudaSuccess; }
+        }
+        release_device(device);                      // too small: give the memory back first
+        out = Arena{nullptr, bytes, device};
+        return cudaMalloc(&out.base, bytes);
+    }
+    void release(Arena a) {
+        if (!a.base) return;
+        std::lock_guard<std::mutex> g(mu_);
+        free_.push_back(a);
+    }
+    void release_device(int device) {
+        std::lock_guard<std::mutex> g(mu_);
+        for (size_t i = 0; i < free_.size();) {
+            if (device < 0 || free_[i].device == device) {
+                int prev = -1; cudaGetDevice(&prev);
+                cudaSetDevice(free_[i].device); cudaFree(free_[i].base);
+                if (prev >= 0) cudaSetDevice(prev);
+                free_.erase(free_.begin() + (long)i);
+            } else i++;
+        }
+    }
+};
+ArenaCache g_arenas;
+
+// non-owning typed view into the arena
 template <typename T> struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
-    ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t count) { n = count; return cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)); }
+    static size_t padded(size_t count) { return (std::max<size_t>(count, 1) * sizeof(T) + 255) / 256 * 256; }
+    void place(unsigned char *&cursor, size_t count) { p = reinterpret_cast<T *>(cursor); n = count; cursor += padded(count); }
     cudaError_t upload(const std::vector<T> &h, cudaStream_t s) {
-        cudaError_t e = alloc(h.size());
-        if (e != cudaSuccess || h.empty()) return e;
+        if (h.empty()) return cudaSuccess;
         return cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s);
     }
 };
+
+constexpr size_t kFetchStageBytes = (size_t)64 << 20;
 
 }  // namespace
 
@@ -78,9 +125,11 @@ struct genlib_engine {
     int numerics = 0, device = 0;
     size_t esize = 4;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
+    Arena arena;
     void *A = nullptr;
     double *Rt = nullptr;
     void *V = nullptr, *Vt = nullptr, *Dg = nullptr;   // couple matrix, its transpose, couple diagonal (current layer)
+    unsigned char *fetch_stage[2] = {nullptr, nullptr};
     DevBuf<int32_t> mem_ind, mem_slot, mem_fam, fam_pf, fam_pm, fam_start, fam_minrank, fam_maxrank, mt_min, mt_max, mt_fam0,
         mt_nfam, pro_slot;
     DevBuf<uint8_t> flags;
@@ -92,11 +141,9 @@ struct genlib_engine {
     int32_t layer_limit = -1;
     ~genlib_engine() {
         for (auto e : events) cudaEventDestroy(e);
-        if (A) cudaFree(A);
-        if (Rt) cudaFree(Rt);
-        if (V) cudaFree(V);
-        if (Vt) cudaFree(Vt);
-        if (Dg) cudaFree(Dg);
+        if (stream) cudaStreamSynchronize(stream);
+        if (copy_stream) cudaStreamSynchronize(copy_stream);
+        g_arenas.release(arena);
         if (stream) cudaStreamDestroy(stream);
         if (copy_stream) cudaStreamDestroy(copy_stream);
     }
@@ -109,13 +156,17 @@ size_t plan_index_bytes(const Plan &P) {
             P.pro_slot.size()) * sizeof(int32_t);
 }
 
+size_t pad256(size_t b) { return (std::max<size_t>(b, 1) + 255) / 256 * 256; }
+
 size_t engine_bytes(const Plan &P, int numerics) {
     const size_t es = numerics == GENLIB_NUMERICS_FP64 ? 8 : 4;
-    size_t b = (size_t)P.capacity * (size_t)P.capacity * es;
-    b += P.rt_elems_max * sizeof(double);
-    b += (2 * P.v_elems_max + P.fam_pf.size()) * es;
-    b += plan_index_bytes(P);
-    b += P.flags.size();
+    size_t b = pad256((size_t)P.capacity * (size_t)P.capacity * es);     // A
+    b += pad256(P.rt_elems_max * sizeof(double));                        // Rt
+    b += 2 * pad256(P.v_elems_max * es) + pad256(P.fam_pf.size() * es);  // V, Vt, Dg
+    b += 2 * pad256(kFetchStageBytes);                                   // proband staging
+    b += 3 * DevBuf<int32_t>::padded(P.mem_ind.size()) + 4 * DevBuf<int32_t>::padded(P.fam_pf.size()) +
+         DevBuf<int32_t>::padded(P.fam_start.size()) + 4 * DevBuf<int32_t>::padded(P.mtile_minrank.size()) +
+         DevBuf<int32_t>::padded(P.pro_slot.size()) + DevBuf<uint8_t>::padded(P.flags.size()) + DevBuf<double>::padded(2);
     return b;
 }
 
@@ -198,12 +249,13 @@ int fetch_rows(genlib_engine &E, O *out) {
     // stream row blocks through two staging buffers so the gather of block b+1
     // overlaps the D2H copy of block b
     const size_t row_bytes = (size_t)n * sizeof(O);
-    int32_t rows_per = (int32_t)std::max<size_t>(1, std::min<size_t>((size_t)n, ((size_t)64 << 20) / row_bytes));
+    int32_t rows_per = (int32_t)std::max<size_t>(1, std::min<size_t>((size_t)n, kFetchStageBytes / row_bytes));
+    if ((size_t)rows_per * row_bytes > kFetchStageBytes) return fail(GENLIB_EINVAL, "proband row does not fit the staging buffer");
     rows_per = std::min(rows_per, 65535);
     O *stage[2] = {nullptr, nullptr};
     cudaEvent_t done[2], copied[2];
     for (int b = 0; b < 2; b++) {
-        CU(cudaMalloc(&stage[b], (size_t)rows_per * row_bytes));
+        stage[b] = reinterpret_cast<O *>(E.fetch_stage[b]);
         CU(cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
     }
@@ -221,7 +273,7 @@ int fetch_rows(genlib_engine &E, O *out) {
         cudaEventRecord(copied[b], E.copy_stream);
     }
     cudaError_t e1 = cudaStreamSynchronize(E.stream), e2 = cudaStreamSynchronize(E.copy_stream);
-    for (int b = 0; b < 2; b++) { cudaFree(stage[b]); cudaEventDestroy(done[b]); cudaEventDestroy(copied[b]); }
+    for (int b = 0; b < 2; b++) { cudaEventDestroy(done[b]); cudaEventDestroy(copied[b]); }
     if (rc != GENLIB_OK || e1 != cudaSuccess || e2 != cudaSuccess)
         return fail(GENLIB_ECUDA, std::string("proband fetch failed: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
     E.stats.d2h_bytes += (int64_t)n * (int64_t)row_bytes;
@@ -240,6 +292,11 @@ int genlib_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { g_err = "cudaGetDeviceCount failed (no driver / no device)"; return -GENLIB_ECUDA; }
     return n;
+}
+
+int genlib_release_cache(void) {
+    g_arenas.release_device(-1);
+    return GENLIB_OK;
 }
 
 int genlib_pinned_alloc(size_t bytes, void **out) {
@@ -348,23 +405,40 @@ int genlib_engine_create(const genlib_plan *plan, int numerics, int device, genl
     E->plan = plan; E->numerics = numerics;
     E->esize = numerics == GENLIB_NUMERICS_FP64 ? 8 : 4;
     CU(cudaGetDevice(&E->device));
-    size_t free_b = 0, total_b = 0;
-    CU(cudaMemGetInfo(&free_b, &total_b));
     const size_t need = engine_bytes(P, numerics);
-    if (need + ((size_t)256 << 20) > free_b) {
-        char msg[256];
-        std::snprintf(msg, sizeof msg, "frontier needs %.2f GB on the device, %.2f GB free (capacity %lld slots): shard over more GPUs",
-                      need / 1e9, free_b / 1e9, (long long)P.capacity);
-        return fail(GENLIB_ENOMEM, msg);
-    }
     const double t0 = now_ms();
     CU(cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&E->copy_stream, cudaStreamNonBlocking));
-    CU(cudaMalloc(&E->A, std::max<size_t>((size_t)P.capacity * (size_t)P.capacity * E->esize, 16)));
-    CU(cudaMalloc(&E->Rt, std::max<size_t>(P.rt_elems_max * sizeof(double), 16)));
-    CU(cudaMalloc(&E->V, std::max<size_t>(P.v_elems_max * E->esize, 16)));
-    CU(cudaMalloc(&E->Vt, std::max<size_t>(P.v_elems_max * E->esize, 16)));
-    CU(cudaMalloc(&E->Dg, std::max<size_t>(P.fam_pf.size() * E->esize, 16)));
+    {
+        cudaError_t ce = g_arenas.acquire(E->device, need, E->arena);
+        if (ce != cudaSuccess) {
+            E->arena = Arena();
+            cudaGetLastError();
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            char msg[256];
+            std::snprintf(msg, sizeof msg, "frontier needs %.2f GB on the device, %.2f GB free (capacity %lld slots): shard over more GPUs",
+                          need / 1e9, free_b / 1e9, (long long)P.capacity);
+            return fail(GENLIB_ENOMEM, msg);
+        }
+        unsigned char *cur = static_cast<unsigned char *>(E->arena.base);
+        auto take = [&](size_t bytes) { unsigned char *p = cur; cur += pad256(bytes); return p; };
+        E->A = take((size_t)P.capacity * (size_t)P.capacity * E->esize);
+        E->Rt = reinterpret_cast<double *>(take(P.rt_elems_max * sizeof(double)));
+        E->V = take(P.v_elems_max * E->esize);
+        E->Vt = take(P.v_elems_max * E->esize);
+        E->Dg = take(P.fam_pf.size() * E->esize);
+        E->fetch_stage[0] = take(kFetchStageBytes);
+        E->fetch_stage[1] = take(kFetchStageBytes);
+        E->mem_ind.place(cur, P.mem_ind.size()); E->mem_slot.place(cur, P.mem_slot.size()); E->mem_fam.place(cur, P.mem_fam.size());
+        E->fam_pf.place(cur, P.fam_pf.size()); E->fam_pm.place(cur, P.fam_pm.size());
+        E->fam_minrank.place(cur, P.fam_minrank.size()); E->fam_maxrank.place(cur, P.fam_maxrank.size());
+        E->fam_start.place(cur, P.fam_start.size());
+        E->mt_min.place(cur, P.mtile_minrank.size()); E->mt_max.place(cur, P.mtile_maxrank.size());
+        E->mt_fam0.place(cur, P.mtile_fam0.size()); E->mt_nfam.place(cur, P.mtile_nfam.size());
+        E->pro_slot.place(cur, P.pro_slot.size()); E->flags.place(cur, P.flags.size()); E->acc.place(cur, 2);
+        if ((size_t)(cur - static_cast<unsigned char *>(E->arena.base)) > need) return fail(GENLIB_EINVAL, "internal: arena layout overflow");
+    }
     CU(E->mem_ind.upload(P.mem_ind, E->stream));
     CU(E->mem_slot.upload(P.mem_slot, E->stream));
     CU(E->mem_fam.upload(P.mem_fam, E->stream));
@@ -379,7 +453,6 @@ int genlib_engine_create(const genlib_plan *plan, int numerics, int device, genl
     CU(E->mt_nfam.upload(P.mtile_nfam, E->stream));
     CU(E->pro_slot.upload(P.pro_slot, E->stream));
     CU(E->flags.upload(P.flags, E->stream));
-    CU(E->acc.alloc(2));
     CU(cudaStreamSynchronize(E->stream));
     E->info.resize(P.layers.size());
     for (size_t t = 0; t < P.layers.size(); t++) fill_info(P.layers[t], &E->info[t]);

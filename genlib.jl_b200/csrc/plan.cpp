@@ -73,46 +73,50 @@ int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t 
     if (P.n_unique == 0) return GENLIB_OK;
 
     // height above the probands = longest downward path to one (compute.jl:236-241
-    // builds the same levels by repeated _previous_generation)
+    // builds the same levels by repeated _previous_generation).  Children have larger ranks,
+    // so one reverse sweep finalises h[x] before x is visited.
     std::vector<int32_t> h((size_t)n, -1);
     for (int32_t x : P.pro_ind) h[x] = 0;
     int32_t hmax = 0;
+    std::vector<int32_t> hist;
     for (int32_t x = n - 1; x >= 0; x--) {
-        if (h[x] < 0) continue;
-        hmax = std::max(hmax, h[x]);
-        int32_t f = father[x], m = mother[x];
-        if (f >= 0) h[f] = std::max(h[f], h[x] + 1);
-        if (m >= 0) h[m] = std::max(h[m], h[x] + 1);
+        const int32_t hx = h[x];
+        if (hx < 0) continue;
+        if (hx >= (int32_t)hist.size()) hist.resize((size_t)hx + 64, 0);
+        hist[hx]++;
+        hmax = std::max(hmax, hx);
+        const int32_t f = father[x], m = mother[x];
+        if (f >= 0 && h[f] <= hx) h[f] = hx + 1;
+        if (m >= 0 && h[m] <= hx) h[m] = hx + 1;
     }
     const int32_t S = hmax + 1;
-    // layer = first raw level; last_read = layer of the last child born (engine eviction);
+    // layer = first raw level = S-1-h; last_read = layer of the last child born (engine eviction);
     // ref_last = last raw level (the reference keeps the individual in its cuts until then)
-    std::vector<int32_t> layer((size_t)n, -1), last_read((size_t)n, -1), ref_last((size_t)n, -1);
+    std::vector<int32_t> last_read((size_t)n, -1), ref_last((size_t)n, -1);
     std::vector<int32_t> count((size_t)S + 1, 0);
-    for (int32_t x = 0; x < n; x++)
-        if (h[x] >= 0) { layer[x] = S - 1 - h[x]; count[layer[x]]++; if (is_pro[x]) ref_last[x] = S - 1; }
+    for (int32_t k = 0; k < S; k++) count[S - 1 - k] = hist[k];
+    for (int32_t x : P.pro_ind) ref_last[x] = S - 1;
     for (int32_t x = n - 1; x >= 0; x--) {
         if (h[x] < 0) continue;
-        for (int32_t p : {father[x], mother[x]}) {
-            if (p < 0) continue;
-            last_read[p] = std::max(last_read[p], layer[x]);
-            ref_last[p] = std::max(ref_last[p], ref_last[x] - 1);
-        }
+        const int32_t lx = S - 1 - h[x], rx = ref_last[x] - 1;
+        const int32_t f = father[x], m = mother[x];
+        if (f >= 0) { if (last_read[f] < lx) last_read[f] = lx; if (ref_last[f] < rx) ref_last[f] = rx; }
+        if (m >= 0) { if (last_read[m] < lx) last_read[m] = lx; if (ref_last[m] < rx) ref_last[m] = rx; }
     }
-    // members of each layer in rank order
+    // members of each layer in rank order + the reference's cut sizes (verbose lines, compute.jl:254-261)
     std::vector<size_t> lstart((size_t)S + 1, 0);
     for (int32_t t = 0; t < S; t++) lstart[t + 1] = lstart[t] + count[t];
     std::vector<int32_t> by_layer(lstart[S]);
+    std::vector<int64_t> d_cut((size_t)S + 2, 0), d_both((size_t)S + 2, 0);
     {
         std::vector<size_t> pos(lstart.begin(), lstart.end() - 1);
-        for (int32_t x = 0; x < n; x++) if (h[x] >= 0) by_layer[pos[layer[x]]++] = x;
-    }
-    // the reference's cut sizes (verbose lines, compute.jl:254-261)
-    std::vector<int64_t> d_cut((size_t)S + 2, 0), d_both((size_t)S + 2, 0);
-    for (int32_t x = 0; x < n; x++) {
-        if (h[x] < 0) continue;
-        d_cut[layer[x]]++; d_cut[ref_last[x] + 1]--;             // in cut[k] for layer <= k <= ref_last
-        if (ref_last[x] > layer[x]) { d_both[layer[x]]++; d_both[ref_last[x]]--; }  // in cut[k] and cut[k+1]
+        for (int32_t x = 0; x < n; x++) {
+            if (h[x] < 0) continue;
+            const int32_t lx = S - 1 - h[x];
+            by_layer[pos[lx]++] = x;
+            d_cut[lx]++; d_cut[ref_last[x] + 1]--;                 // in cut[k] for layer <= k <= ref_last
+            if (ref_last[x] > lx) { d_both[lx]++; d_both[ref_last[x]]--; }   // in cut[k] and cut[k+1]
+        }
     }
     std::vector<int32_t> cut_size((size_t)S, 0), both_size((size_t)S, 0);
     {
@@ -161,8 +165,9 @@ int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t 
                 bool stays = is_pro[x] || last_read[x] > t;
                 fl[slot_of[x] - L.rt_lo] = (uint8_t)(kFlagLive | (stays ? kFlagCarried : 0));
                 if (stays) { next_live.push_back(x); L.carried++; }
-                else freed.push_back(slot_of[x]);
             }
+            for (int32_t r = 0; r < L.rt_rows; r++)        // evicted slots, already in ascending order
+                if (fl[r] == kFlagLive) freed.push_back(L.rt_lo + r);
         }
 
         // ---- families: same (father, mother) => same cross row (compute.jl:111-126 gives
@@ -201,13 +206,15 @@ int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t 
         }
         // ---- slots: lowest free first, then fresh ones ----
         size_t take = std::min((size_t)nn, freelist.size());
-        for (int32_t q = 0; q < nn; q++) {
-            int32_t x = X[order[q]];
-            int32_t s = (size_t)q < take ? freelist[q] : next_fresh++;
-            slot_of[x] = s;
-            P.mem_ind.push_back(x);
-            P.mem_slot.push_back(s);
-            P.mem_fam.push_back(fam_of[order[q]]);
+        P.mem_ind.resize(L.mem_off + (size_t)nn); P.mem_slot.resize(L.mem_off + (size_t)nn); P.mem_fam.resize(L.mem_off + (size_t)nn);
+        {
+            int32_t *mi = P.mem_ind.data() + L.mem_off, *ms = P.mem_slot.data() + L.mem_off, *mf = P.mem_fam.data() + L.mem_off;
+            for (int32_t q = 0; q < nn; q++) {
+                const int32_t oq = order[q], x = X[oq];
+                const int32_t s = (size_t)q < take ? freelist[q] : next_fresh++;
+                slot_of[x] = s;
+                mi[q] = x; ms[q] = s; mf[q] = fam_of[oq];
+            }
         }
         freelist.erase(freelist.begin(), freelist.begin() + (ptrdiff_t)take);
         for (int32_t f = 0; f < nf; f++) {
@@ -246,7 +253,6 @@ int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t 
 
         // ---- after the step: evicted slots become reusable from the next layer on ----
         if (!freed.empty()) {
-            std::sort(freed.begin(), freed.end());
             std::vector<int32_t> merged(freelist.size() + freed.size());
             std::merge(freelist.begin(), freelist.end(), freed.begin(), freed.end(), merged.begin());
             freelist.swap(merged);

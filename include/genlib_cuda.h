@@ -91,6 +91,10 @@ const char *genlib_last_error(void);
 /* Number of visible CUDA devices, or a negative status. */
 int genlib_device_count(void);
 
+/* The library keeps the device arena of the last engine per device for reuse (cudaMalloc of
+ * tens of GB costs hundreds of ms).  This frees every cached arena. */
+int genlib_release_cache(void);
+
 /* Page-locked host memory for `out` buffers (D2H at full PCIe speed).  Optional:
  * every entry point also accepts pageable memory. */
 int genlib_pinned_alloc(size_t bytes, void **out);
