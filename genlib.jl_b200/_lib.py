@@ -63,6 +63,11 @@ SYMBOLS = {
     "genlib_plan_layer_info": (C.c_int, [_P, C.c_int32, C.POINTER(LayerInfo)]),
     "genlib_plan_device_bytes": (C.c_int64, [_P, C.c_int, C.c_int32]),
     "genlib_plan_layer_arrays": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P]),
+    "genlib_plan_layer_shard": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P, _P]),
+    "genlib_plan_layer_live_rows": (C.c_int, [_P, C.c_int32, _P, _P]),
+    "genlib_plan_rank_rows": (C.c_int64, [_P, C.c_int32]),
+    "genlib_plan_world": (C.c_int32, [_P]),
+    "genlib_plan_proband_rows": (C.c_int, [_P, _P, _P]),
     "genlib_plan_layer_flags": (C.c_int, [_P, C.c_int32, _P]),
     "genlib_plan_proband_slots": (C.c_int, [_P, _P]),
     "genlib_phi": (C.c_int, [C.c_int32, _P, _P, C.c_int32, _P, _P, C.c_int, C.c_int, C.c_int,
@@ -73,6 +78,10 @@ SYMBOLS = {
     "genlib_engine_layer_info": (C.c_int, [_P, C.c_int32, C.POINTER(LayerInfo)]),
     "genlib_engine_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "genlib_engine_fetch": (C.c_int, [_P, _P, C.c_int]),
+    "genlib_engine_own_probands": (C.c_int32, [_P, _P]),
+    "genlib_engine_create_dist": (C.c_int, [_P, C.c_int, C.c_int, C.c_int32, C.POINTER(_P)]),
+    "genlib_engine_ipc_export": (C.c_int, [_P, _P]),
+    "genlib_engine_ipc_attach": (C.c_int, [_P, _P, C.c_size_t]),
     "genlib_engine_phi_mean": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "genlib_engine_set_layer_limit": (C.c_int, [_P, C.c_int32]),
     "genlib_engine_read_block": (C.c_int, [_P, C.c_int32, _P, _P]),

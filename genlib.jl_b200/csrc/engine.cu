@@ -123,17 +123,26 @@ struct genlib_plan {
 struct genlib_engine {
     const genlib_plan *plan = nullptr;
     int numerics = 0, device = 0;
+    int rank = 0, world = 1;
+    bool attached = false;                 // peers' arenas mapped (always true for one rank)
     size_t esize = 4;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     Arena arena;
-    void *A = nullptr;
-    double *Rt = nullptr;
-    void *V = nullptr, *Vt = nullptr, *Dg = nullptr;   // couple matrix, its transpose, couple diagonal (current layer)
+    void *A = nullptr;                     // this rank's frontier rows: rows_cap x capacity
+    double *Rt = nullptr;                  // transposed cross block: live slots x own couples (fp64)
+    void *Vrow = nullptr, *Vt = nullptr, *Dg = nullptr;   // V[own F, G], V[G, own F], couple diagonal
+    unsigned *bar_flags = nullptr;
     unsigned char *fetch_stage[2] = {nullptr, nullptr};
-    DevBuf<int32_t> mem_ind, mem_slot, mem_fam, fam_pf, fam_pm, fam_start, fam_minrank, fam_maxrank, mt_min, mt_max, mt_fam0,
-        mt_nfam, pro_slot;
+    PeerTable peers{};
+    BarrierTable bars{};
+    void *peer_base[kMaxWorld] = {};       // cudaIpcOpenMemHandle mappings (to close)
+    unsigned epoch = 0;
+    DevBuf<int32_t> mem_ind, mem_slot, mem_fam, mem_lrow, fam_pf, fam_pm, fam_pf_lrow, fam_pm_lrow, fam_start,
+        fam_minrank, fam_maxrank, mt_min, mt_max, mt_fam0, mt_nfam, pro_slot, own_pro_row, live_lrow;
+    DevBuf<int8_t> fam_pf_owner, fam_pm_owner, live_owner;
     DevBuf<uint8_t> flags;
     DevBuf<double> acc;
+    std::vector<int32_t> own_pro;          // proband indices (output rows) this rank owns, ascending
     std::vector<genlib_layer_info> info;
     std::vector<cudaEvent_t> events;
     genlib_stats stats{};
@@ -143,6 +152,7 @@ struct genlib_engine {
         for (auto e : events) cudaEventDestroy(e);
         if (stream) cudaStreamSynchronize(stream);
         if (copy_stream) cudaStreamSynchronize(copy_stream);
+        for (int g = 0; g < kMaxWorld; g++) if (peer_base[g]) cudaIpcCloseMemHandle(peer_base[g]);
         g_arenas.release(arena);
         if (stream) cudaStreamDestroy(stream);
         if (copy_stream) cudaStreamDestroy(copy_stream);
@@ -151,22 +161,39 @@ struct genlib_engine {
 
 namespace {
 
-size_t plan_index_bytes(const Plan &P) {
-    return (P.mem_ind.size() * 3 + P.fam_pf.size() * 4 + P.fam_start.size() + P.mtile_minrank.size() * 4 +
-            P.pro_slot.size()) * sizeof(int32_t);
+void fill_info(const Layer &L, genlib_layer_info *o) {
+    std::memset(o, 0, sizeof *o);
+    o->n_new = L.n_new; o->n_fam = L.n_fam; o->live_before = L.live_before; o->carried = L.carried;
+    o->ref_founders = L.ref_founders; o->ref_probands = L.ref_probands; o->ref_both = L.ref_both;
+    o->alg_elems = L.alg_elems;
 }
 
 size_t pad256(size_t b) { return (std::max<size_t>(b, 1) + 255) / 256 * 256; }
 
-size_t engine_bytes(const Plan &P, int numerics) {
+size_t plan_index_bytes(const Plan &P) {
+    return (P.mem_ind.size() * 4 + P.fam_pf.size() * 6 + P.fam_start.size() + P.mtile_minrank.size() * 4 +
+            P.pro_slot.size() * 2 + P.live_lrow.size()) * sizeof(int32_t) + P.fam_pf.size() * 2 + P.live_owner.size() + P.flags.size();
+}
+
+// Arena layout of rank g.  The first three regions are what peers address (barrier flags,
+// frontier rows, row block of V), so their offsets must be computable by every rank.
+constexpr size_t kFlagBytes = 256;
+size_t a_bytes(const Plan &P, size_t es, int g) { return pad256((size_t)P.rows_cap[g] * (size_t)P.capacity * es); }
+size_t v_bytes(const Plan &P, size_t es, int g) { return pad256(P.rank_v_elems[g] * es); }
+size_t off_A() { return kFlagBytes; }
+size_t off_Vrow(const Plan &P, size_t es, int g) { return kFlagBytes + a_bytes(P, es, g); }
+
+size_t engine_bytes(const Plan &P, int numerics, int g) {
     const size_t es = numerics == GENLIB_NUMERICS_FP64 ? 8 : 4;
-    size_t b = pad256((size_t)P.capacity * (size_t)P.capacity * es);     // A
-    b += pad256(P.rt_elems_max * sizeof(double));                        // Rt
-    b += 2 * pad256(P.v_elems_max * es) + pad256(P.fam_pf.size() * es);  // V, Vt, Dg
-    b += 2 * pad256(kFetchStageBytes);                                   // proband staging
-    b += 3 * DevBuf<int32_t>::padded(P.mem_ind.size()) + 4 * DevBuf<int32_t>::padded(P.fam_pf.size()) +
+    size_t b = kFlagBytes + a_bytes(P, es, g) + 2 * v_bytes(P, es, g);          // flags, A, Vrow, Vt
+    b += pad256(P.rank_rt_elems[g] * sizeof(double));                          // Rt
+    b += pad256(P.fam_pf.size() * es);                                         // Dg
+    b += 2 * pad256(kFetchStageBytes);                                         // proband staging
+    b += 4 * DevBuf<int32_t>::padded(P.mem_ind.size()) + 6 * DevBuf<int32_t>::padded(P.fam_pf.size()) +
          DevBuf<int32_t>::padded(P.fam_start.size()) + 4 * DevBuf<int32_t>::padded(P.mtile_minrank.size()) +
-         DevBuf<int32_t>::padded(P.pro_slot.size()) + DevBuf<uint8_t>::padded(P.flags.size()) + DevBuf<double>::padded(2);
+         2 * DevBuf<int32_t>::padded(P.pro_slot.size()) + DevBuf<int32_t>::padded(P.live_lrow.size()) +
+         2 * DevBuf<int8_t>::padded(P.fam_pf.size()) + DevBuf<int8_t>::padded(P.live_owner.size()) +
+         DevBuf<uint8_t>::padded(P.flags.size()) + DevBuf<double>::padded(2);
     return b;
 }
 
@@ -174,12 +201,23 @@ LayerArgs layer_args(const genlib_engine &E, int t) {
     const Plan &P = E.plan->p;
     const Layer &L = P.layers[t];
     LayerArgs a;
+    std::memset(&a, 0, sizeof a);
     a.n_new = L.n_new; a.n_fam = L.n_fam; a.rt_lo = L.rt_lo; a.rt_rows = L.rt_rows; a.nf_pad = L.nf_pad;
     a.any_carried = L.carried > 0;
+    a.rank = E.rank; a.world = E.world;
+    const int32_t *fb = P.fam_base.data() + L.base_off, *mb = P.mem_base.data() + L.base_off;
+    for (int g = 0; g <= E.world; g++) a.fam_base[g] = fb[g];
+    a.own_f0 = fb[E.rank]; a.own_nf = fb[E.rank + 1] - fb[E.rank];
+    a.own_m0 = mb[E.rank]; a.own_nm = mb[E.rank + 1] - mb[E.rank];
+    a.nfo_pad = pad32(a.own_nf);
     a.mem_ind = E.mem_ind.p + L.mem_off; a.mem_slot = E.mem_slot.p + L.mem_off; a.mem_fam = E.mem_fam.p + L.mem_off;
+    a.mem_lrow = E.mem_lrow.p + L.mem_off;
     a.fam_pf = E.fam_pf.p + L.fam_off; a.fam_pm = E.fam_pm.p + L.fam_off;
+    a.fam_pf_owner = E.fam_pf_owner.p + L.fam_off; a.fam_pm_owner = E.fam_pm_owner.p + L.fam_off;
+    a.fam_pf_lrow = E.fam_pf_lrow.p + L.fam_off; a.fam_pm_lrow = E.fam_pm_lrow.p + L.fam_off;
     a.fam_start = E.fam_start.p + L.fam_off + t;
     a.flags = E.flags.p + L.flag_off;
+    a.live_owner = E.live_owner.p + L.flag_off; a.live_lrow = E.live_lrow.p + L.flag_off;
     a.fam_minrank = E.fam_minrank.p + L.fam_off; a.fam_maxrank = E.fam_maxrank.p + L.fam_off;
     a.mt_minrank = E.mt_min.p + L.mtile_off; a.mt_maxrank = E.mt_max.p + L.mtile_off;
     a.mt_fam0 = E.mt_fam0.p + L.mtile_off; a.mt_nfam = E.mt_nfam.p + L.mtile_off;
@@ -190,6 +228,13 @@ LayerArgs layer_args(const genlib_engine &E, int t) {
     return a;
 }
 
+int launch_barrier(genlib_engine &E) {
+    if (E.world == 1) return GENLIB_OK;
+    E.epoch++;
+    barrier_kernel<<<1, 32, 0, E.stream>>>(E.bars, E.rank, E.world, E.epoch, (long long)20e9);
+    return GENLIB_OK;
+}
+
 template <typename T>
 int launch_layers(genlib_engine &E, bool timed) {
     const Plan &P = E.plan->p;
@@ -197,12 +242,15 @@ int launch_layers(genlib_engine &E, bool timed) {
     const int64_t ld = P.capacity;
     const size_t cross_smem = (size_t)kFTile * kSRStride * sizeof(double);
     const int vec = 16 / (int)sizeof(T);
-    const size_t expand_smem_max = (size_t)kEWarps * 2 * expand_stage_bytes<T>(kMTile + vec);
+    int max_tile_fam = 1;
+    for (const Layer &L : P.layers) max_tile_fam = std::max(max_tile_fam, L.max_tile_fam);
+    const size_t expand_smem_max = (size_t)kEWarps * 2 * expand_stage_bytes<T>((max_tile_fam + vec - 1) / vec * vec + vec);
+    if (expand_smem_max > 227 * 1024) return fail(GENLIB_EINVAL, "couple tile too wide for the expand kernel");
     auto expand_fn = expand_kernel<T>;
     CU(cudaFuncSetAttribute(expand_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem_max));
     CU(cudaFuncSetAttribute(cross_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CU(cudaFuncSetAttribute(expand_fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    T *V = static_cast<T *>(E.V), *Vt = static_cast<T *>(E.Vt), *Dg = static_cast<T *>(E.Dg);
+    T *V = static_cast<T *>(E.Vrow), *Vt = static_cast<T *>(E.Vt), *Dg = static_cast<T *>(E.Dg);
     const size_t couple_smem = sizeof(T) * kFTile * kCStride;
     CU(cudaFuncSetAttribute(couple_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)couple_smem));
     CU(cudaFuncSetAttribute(couple_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -214,26 +262,28 @@ int launch_layers(genlib_engine &E, bool timed) {
         if (E.layer_limit >= 0 && t >= E.layer_limit) break;
         LayerArgs a = layer_args(E, t);
         if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
-        if (L.live_before > 0) {
-            dim3 grid((unsigned)(L.rt_rows / kPTile), (unsigned)((L.n_fam + kFTile - 1) / kFTile));
-            cross_kernel<T><<<grid, kThreads, cross_smem, E.stream>>>(A, ld, E.Rt, a);
+        if (L.live_before > 0 && a.own_nf > 0) {
+            dim3 grid((unsigned)(L.rt_rows / kPTile), (unsigned)((a.own_nf + kFTile - 1) / kFTile));
+            cross_kernel<T><<<grid, kThreads, cross_smem, E.stream>>>(A, ld, E.Rt, E.peers, a);
             launches++;
         }
         if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
-        {
-            dim3 grid((unsigned)((L.nf_pad + kCTile - 1) / kCTile), (unsigned)((L.n_fam + kFTile - 1) / kFTile));
-            couple_kernel<T><<<grid, kThreads, couple_smem, E.stream>>>(A, ld, E.Rt, V, Vt, Dg, a);
+        if (a.own_nf > 0) {
+            dim3 grid((unsigned)((a.nfo_pad + kCTile - 1) / kCTile), (unsigned)((L.n_fam + kFTile - 1) / kFTile));
+            couple_kernel<T><<<grid, kThreads, couple_smem, E.stream>>>(ld, E.Rt, Vt, Dg, E.peers, a);
             launches++;
         }
+        launch_barrier(E);                 // every rank's row block of V is complete (peer stores landed)
         if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
-        {
+        if (a.own_nm > 0) {
             const int rows_per_cta = kEWarps * kERows;
-            dim3 grid((unsigned)((L.n_mtiles + kEChunk - 1) / kEChunk), (unsigned)((L.n_new + rows_per_cta - 1) / rows_per_cta));
+            dim3 grid((unsigned)((L.n_mtiles + kEChunk - 1) / kEChunk), (unsigned)((a.own_nm + rows_per_cta - 1) / rows_per_cta));
             if (grid.y > 65535) return fail(GENLIB_EINVAL, "layer too wide for one expand launch");
             const size_t smem = (size_t)kEWarps * 2 * expand_stage_bytes<T>(a.vstride);
             expand_fn<<<grid, kExpandThreads, smem, E.stream>>>(A, ld, V, Vt, Dg, a);
             launches++;
         }
+        launch_barrier(E);                 // all new rows exist everywhere before the next layer reads them
         if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
     }
     CU(cudaGetLastError());
@@ -241,15 +291,16 @@ int launch_layers(genlib_engine &E, bool timed) {
     return GENLIB_OK;
 }
 
+// Rows of this rank's probands (own_pro order), all proband columns, streamed to host memory.
 template <typename T, typename O>
 int fetch_rows(genlib_engine &E, O *out) {
     const Plan &P = E.plan->p;
-    const int32_t n = P.n_unique;
-    if (n == 0) return GENLIB_OK;
+    const int32_t n = P.n_unique, nown = (int32_t)E.own_pro.size();
+    if (n == 0 || nown == 0) return GENLIB_OK;
     // stream row blocks through two staging buffers so the gather of block b+1
     // overlaps the D2H copy of block b
     const size_t row_bytes = (size_t)n * sizeof(O);
-    int32_t rows_per = (int32_t)std::max<size_t>(1, std::min<size_t>((size_t)n, kFetchStageBytes / row_bytes));
+    int32_t rows_per = (int32_t)std::max<size_t>(1, std::min<size_t>((size_t)nown, kFetchStageBytes / row_bytes));
     if ((size_t)rows_per * row_bytes > kFetchStageBytes) return fail(GENLIB_EINVAL, "proband row does not fit the staging buffer");
     rows_per = std::min(rows_per, 65535);
     O *stage[2] = {nullptr, nullptr};
@@ -261,12 +312,13 @@ int fetch_rows(genlib_engine &E, O *out) {
     }
     int rc = GENLIB_OK;
     int blk = 0;
-    for (int32_t r0 = 0; r0 < n; r0 += rows_per, blk++) {
+    for (int32_t r0 = 0; r0 < nown; r0 += rows_per, blk++) {
         const int b = blk & 1;
-        const int32_t nr = std::min(rows_per, n - r0);
+        const int32_t nr = std::min(rows_per, nown - r0);
         if (blk >= 2 && cudaStreamWaitEvent(E.stream, copied[b], 0) != cudaSuccess) { rc = GENLIB_ECUDA; break; }
         dim3 grid((unsigned)std::min<int32_t>((n + 255) / 256, 64), (unsigned)nr);
-        gather_kernel<T, O><<<grid, 256, 0, E.stream>>>(static_cast<const T *>(E.A), P.capacity, E.pro_slot.p, n, r0, nr, stage[b]);
+        gather_kernel<T, O><<<grid, 256, 0, E.stream>>>(static_cast<const T *>(E.A), P.capacity, E.own_pro_row.p, E.pro_slot.p,
+                                                       n, r0, nr, stage[b]);
         cudaEventRecord(done[b], E.stream);
         cudaStreamWaitEvent(E.copy_stream, done[b], 0);
         if (cudaMemcpyAsync(out + (size_t)r0 * n, stage[b], (size_t)nr * row_bytes, cudaMemcpyDeviceToHost, E.copy_stream) != cudaSuccess) { rc = GENLIB_ECUDA; break; }
@@ -276,7 +328,112 @@ int fetch_rows(genlib_engine &E, O *out) {
     for (int b = 0; b < 2; b++) { cudaEventDestroy(done[b]); cudaEventDestroy(copied[b]); }
     if (rc != GENLIB_OK || e1 != cudaSuccess || e2 != cudaSuccess)
         return fail(GENLIB_ECUDA, std::string("proband fetch failed: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
-    E.stats.d2h_bytes += (int64_t)n * (int64_t)row_bytes;
+    E.stats.d2h_bytes += (int64_t)nown * (int64_t)row_bytes;
+    return GENLIB_OK;
+}
+
+int create_engine(const genlib_plan *plan, int numerics, int device, int rank, genlib_engine **out) {
+    if (!plan || !out) return fail(GENLIB_EINVAL, "genlib_engine_create: null argument");
+    *out = nullptr;
+    if (numerics != GENLIB_NUMERICS_REFERENCE && numerics != GENLIB_NUMERICS_FP64) return fail(GENLIB_EINVAL, "unknown numerics mode");
+    const Plan &P = plan->p;
+    if (rank < 0 || rank >= P.world) return fail(GENLIB_EINVAL, "rank outside the plan's world");
+    if (P.world > kMaxWorld) return fail(GENLIB_EINVAL, "the engine supports at most 16 ranks");
+    if (P.n_unique == 0) return fail(GENLIB_EINVAL, "empty proband list: nothing to run");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(GENLIB_ECUDA, "no CUDA device: libgenlib_cuda has no CPU fallback");
+    DeviceGuard guard;
+    if (int rc = guard.enter(device)) return rc;
+    std::unique_ptr<genlib_engine> E(new (std::nothrow) genlib_engine);
+    if (!E) return fail(GENLIB_ENOMEM, "out of host memory");
+    E->plan = plan; E->numerics = numerics; E->rank = rank; E->world = P.world;
+    E->esize = numerics == GENLIB_NUMERICS_FP64 ? 8 : 4;
+    CU(cudaGetDevice(&E->device));
+    const size_t need = engine_bytes(P, numerics, rank);
+    const double t0 = now_ms();
+    CU(cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&E->copy_stream, cudaStreamNonBlocking));
+    {
+        cudaError_t ce = g_arenas.acquire(E->device, need, E->arena);
+        if (ce != cudaSuccess) {
+            E->arena = Arena();
+            cudaGetLastError();
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            char msg[256];
+            std::snprintf(msg, sizeof msg, "rank %d needs %.2f GB on the device, %.2f GB free (capacity %lld slots, %lld rows): shard over more GPUs",
+                          rank, need / 1e9, free_b / 1e9, (long long)P.capacity, (long long)P.rows_cap[rank]);
+            return fail(GENLIB_ENOMEM, msg);
+        }
+        unsigned char *base = static_cast<unsigned char *>(E->arena.base), *cur = base;
+        auto take = [&](size_t bytes) { unsigned char *p = cur; cur += pad256(bytes); return p; };
+        E->bar_flags = reinterpret_cast<unsigned *>(take(kFlagBytes));
+        E->A = take((size_t)P.rows_cap[rank] * (size_t)P.capacity * E->esize);
+        E->Vrow = take(P.rank_v_elems[rank] * E->esize);
+        E->Vt = take(P.rank_v_elems[rank] * E->esize);
+        E->Rt = reinterpret_cast<double *>(take(P.rank_rt_elems[rank] * sizeof(double)));
+        E->Dg = take(P.fam_pf.size() * E->esize);
+        E->fetch_stage[0] = take(kFetchStageBytes);
+        E->fetch_stage[1] = take(kFetchStageBytes);
+        E->mem_ind.place(cur, P.mem_ind.size()); E->mem_slot.place(cur, P.mem_slot.size()); E->mem_fam.place(cur, P.mem_fam.size());
+        E->mem_lrow.place(cur, P.mem_lrow.size());
+        E->fam_pf.place(cur, P.fam_pf.size()); E->fam_pm.place(cur, P.fam_pm.size());
+        E->fam_pf_lrow.place(cur, P.fam_pf_lrow.size()); E->fam_pm_lrow.place(cur, P.fam_pm_lrow.size());
+        E->fam_minrank.place(cur, P.fam_minrank.size()); E->fam_maxrank.place(cur, P.fam_maxrank.size());
+        E->fam_start.place(cur, P.fam_start.size());
+        E->mt_min.place(cur, P.mtile_minrank.size()); E->mt_max.place(cur, P.mtile_maxrank.size());
+        E->mt_fam0.place(cur, P.mtile_fam0.size()); E->mt_nfam.place(cur, P.mtile_nfam.size());
+        E->pro_slot.place(cur, P.pro_slot.size()); E->own_pro_row.place(cur, P.pro_slot.size());
+        E->live_lrow.place(cur, P.live_lrow.size());
+        E->fam_pf_owner.place(cur, P.fam_pf_owner.size()); E->fam_pm_owner.place(cur, P.fam_pm_owner.size());
+        E->live_owner.place(cur, P.live_owner.size());
+        E->flags.place(cur, P.flags.size()); E->acc.place(cur, 2);
+        if ((size_t)(cur - base) > need) return fail(GENLIB_EINVAL, "internal: arena layout overflow");
+        if ((size_t)(static_cast<unsigned char *>(E->A) - base) != off_A() ||
+            (size_t)(static_cast<unsigned char *>(E->Vrow) - base) != off_Vrow(P, E->esize, rank))
+            return fail(GENLIB_EINVAL, "internal: peer-visible arena offsets drifted");
+    }
+    // this rank's probands, in output order
+    std::vector<int32_t> own_rows;
+    for (size_t u = 0; u < P.pro_ind.size(); u++)
+        if (P.pro_owner[u] == rank) { E->own_pro.push_back((int32_t)u); own_rows.push_back(P.pro_lrow[u]); }
+    CU(cudaMemsetAsync(E->bar_flags, 0, kFlagBytes, E->stream));
+    CU(E->mem_ind.upload(P.mem_ind, E->stream));
+    CU(E->mem_slot.upload(P.mem_slot, E->stream));
+    CU(E->mem_fam.upload(P.mem_fam, E->stream));
+    CU(E->mem_lrow.upload(P.mem_lrow, E->stream));
+    CU(E->fam_pf.upload(P.fam_pf, E->stream));
+    CU(E->fam_pm.upload(P.fam_pm, E->stream));
+    CU(E->fam_pf_lrow.upload(P.fam_pf_lrow, E->stream));
+    CU(E->fam_pm_lrow.upload(P.fam_pm_lrow, E->stream));
+    CU(E->fam_pf_owner.upload(P.fam_pf_owner, E->stream));
+    CU(E->fam_pm_owner.upload(P.fam_pm_owner, E->stream));
+    CU(E->fam_start.upload(P.fam_start, E->stream));
+    CU(E->fam_minrank.upload(P.fam_minrank, E->stream));
+    CU(E->fam_maxrank.upload(P.fam_maxrank, E->stream));
+    CU(E->mt_min.upload(P.mtile_minrank, E->stream));
+    CU(E->mt_max.upload(P.mtile_maxrank, E->stream));
+    CU(E->mt_fam0.upload(P.mtile_fam0, E->stream));
+    CU(E->mt_nfam.upload(P.mtile_nfam, E->stream));
+    CU(E->pro_slot.upload(P.pro_slot, E->stream));
+    CU(E->own_pro_row.upload(own_rows, E->stream));
+    CU(E->live_owner.upload(P.live_owner, E->stream));
+    CU(E->live_lrow.upload(P.live_lrow, E->stream));
+    CU(E->flags.upload(P.flags, E->stream));
+    CU(cudaStreamSynchronize(E->stream));
+    E->peers.A[rank] = E->A; E->peers.Vrow[rank] = E->Vrow; E->bars.flags[rank] = E->bar_flags;
+    E->attached = P.world == 1;
+    E->info.resize(P.layers.size());
+    for (size_t t = 0; t < P.layers.size(); t++) fill_info(P.layers[t], &E->info[t]);
+    E->events.resize(P.layers.size() * 4 + 2);
+    for (auto &e : E->events) CU(cudaEventCreate(&e));
+    genlib_stats &s = E->stats;
+    s.n_unique = P.n_unique; s.n_layers = (int32_t)P.layers.size(); s.row_updates = P.row_updates;
+    s.capacity = P.capacity; s.device_bytes = (int64_t)need; s.alg_bytes = P.alg_elems * (double)E->esize;
+    s.ms_plan = plan->ms_plan; s.ms_upload = now_ms() - t0;
+    s.h2d_bytes = (int64_t)plan_index_bytes(P);
+    *out = E.release();
     return GENLIB_OK;
 }
 
@@ -337,13 +494,6 @@ int32_t genlib_plan_n_layers(const genlib_plan *plan) { return plan ? (int32_t)p
 int64_t genlib_plan_capacity(const genlib_plan *plan) { return plan ? plan->p.capacity : -1; }
 int64_t genlib_plan_row_updates(const genlib_plan *plan) { return plan ? plan->p.row_updates : -1; }
 
-static void fill_info(const Layer &L, genlib_layer_info *o) {
-    std::memset(o, 0, sizeof *o);
-    o->n_new = L.n_new; o->n_fam = L.n_fam; o->live_before = L.live_before; o->carried = L.carried;
-    o->ref_founders = L.ref_founders; o->ref_probands = L.ref_probands; o->ref_both = L.ref_both;
-    o->alg_elems = L.alg_elems;
-}
-
 int genlib_plan_layer_info(const genlib_plan *plan, int32_t layer, genlib_layer_info *out) {
     if (!plan || !out || layer < 0 || layer >= (int32_t)plan->p.layers.size()) return fail(GENLIB_EINVAL, "bad layer");
     fill_info(plan->p.layers[layer], out);
@@ -351,8 +501,8 @@ int genlib_plan_layer_info(const genlib_plan *plan, int32_t layer, genlib_layer_
 }
 
 int64_t genlib_plan_device_bytes(const genlib_plan *plan, int numerics, int32_t rank) {
-    (void)rank;
-    return plan ? (int64_t)engine_bytes(plan->p, numerics) : -1;
+    if (!plan || rank < 0 || rank >= plan->p.world || plan->p.n_unique == 0) return plan ? 0 : -1;
+    return (int64_t)engine_bytes(plan->p, numerics, rank);
 }
 
 int genlib_plan_layer_arrays(const genlib_plan *plan, int32_t layer, int32_t *member_ind,
@@ -365,12 +515,62 @@ int genlib_plan_layer_arrays(const genlib_plan *plan, int32_t layer, int32_t *me
         if (member_ind) member_ind[q] = P.mem_ind[L.mem_off + q];
         if (member_slot) member_slot[q] = P.mem_slot[L.mem_off + q];
         if (member_fam) member_fam[q] = P.mem_fam[L.mem_off + q];
-        if (member_owner) member_owner[q] = 0;
+        if (member_owner) {
+            int g = 0;
+            while (g + 1 < P.world && q >= P.mem_base[L.base_off + g + 1]) g++;
+            member_owner[q] = g;
+        }
     }
     for (int32_t f = 0; f < L.n_fam; f++) {
         if (fam_father_slot) fam_father_slot[f] = P.fam_pf[L.fam_off + f];
         if (fam_mother_slot) fam_mother_slot[f] = P.fam_pm[L.fam_off + f];
     }
+    return GENLIB_OK;
+}
+
+int genlib_plan_layer_shard(const genlib_plan *plan, int32_t layer, int32_t *fam_base, int32_t *mem_base,
+                            int32_t *member_lrow, int32_t *fam_father_owner, int32_t *fam_father_lrow,
+                            int32_t *fam_mother_owner, int32_t *fam_mother_lrow) {
+    if (!plan || layer < 0 || layer >= (int32_t)plan->p.layers.size()) return fail(GENLIB_EINVAL, "bad layer");
+    const Plan &P = plan->p;
+    const Layer &L = P.layers[layer];
+    for (int32_t g = 0; g <= P.world; g++) {
+        if (fam_base) fam_base[g] = P.fam_base[L.base_off + g];
+        if (mem_base) mem_base[g] = P.mem_base[L.base_off + g];
+    }
+    for (int32_t q = 0; q < L.n_new; q++) if (member_lrow) member_lrow[q] = P.mem_lrow[L.mem_off + q];
+    for (int32_t f = 0; f < L.n_fam; f++) {
+        if (fam_father_owner) fam_father_owner[f] = P.fam_pf_owner[L.fam_off + f];
+        if (fam_father_lrow) fam_father_lrow[f] = P.fam_pf_lrow[L.fam_off + f];
+        if (fam_mother_owner) fam_mother_owner[f] = P.fam_pm_owner[L.fam_off + f];
+        if (fam_mother_lrow) fam_mother_lrow[f] = P.fam_pm_lrow[L.fam_off + f];
+    }
+    return GENLIB_OK;
+}
+
+int genlib_plan_layer_live_rows(const genlib_plan *plan, int32_t layer, int32_t *live_owner, int32_t *live_lrow) {
+    if (!plan || !live_owner || !live_lrow || layer < 0 || layer >= (int32_t)plan->p.layers.size()) return fail(GENLIB_EINVAL, "bad layer");
+    const Plan &P = plan->p;
+    const Layer &L = P.layers[layer];
+    for (int64_t s = 0; s < P.capacity; s++) { live_owner[s] = -1; live_lrow[s] = -1; }
+    for (int32_t r = 0; r < L.rt_rows; r++)
+        if (P.flags[L.flag_off + r] & kFlagLive) {
+            live_owner[L.rt_lo + r] = P.live_owner[L.flag_off + r];
+            live_lrow[L.rt_lo + r] = P.live_lrow[L.flag_off + r];
+        }
+    return GENLIB_OK;
+}
+
+int64_t genlib_plan_rank_rows(const genlib_plan *plan, int32_t rank) {
+    if (!plan || rank < 0 || rank >= plan->p.world) return -1;
+    return plan->p.rows_cap.empty() ? 0 : plan->p.rows_cap[rank];
+}
+
+int32_t genlib_plan_world(const genlib_plan *plan) { return plan ? plan->p.world : -1; }
+
+int genlib_plan_proband_rows(const genlib_plan *plan, int32_t *owner, int32_t *lrow) {
+    if (!plan || !owner || !lrow) return fail(GENLIB_EINVAL, "null argument");
+    for (size_t u = 0; u < plan->p.pro_ind.size(); u++) { owner[u] = plan->p.pro_owner[u]; lrow[u] = plan->p.pro_lrow[u]; }
     return GENLIB_OK;
 }
 
@@ -390,81 +590,55 @@ int genlib_plan_proband_slots(const genlib_plan *plan, int32_t *slots) {
 }
 
 int genlib_engine_create(const genlib_plan *plan, int numerics, int device, genlib_engine **out) {
-    if (!plan || !out) return fail(GENLIB_EINVAL, "genlib_engine_create: null argument");
-    *out = nullptr;
-    if (numerics != GENLIB_NUMERICS_REFERENCE && numerics != GENLIB_NUMERICS_FP64) return fail(GENLIB_EINVAL, "unknown numerics mode");
-    if (plan->p.world != 1) return fail(GENLIB_EINVAL, "plan was built for several ranks; use the distributed engine");
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
-        return fail(GENLIB_ECUDA, "no CUDA device: libgenlib_cuda has no CPU fallback");
+    if (plan && plan->p.world != 1) return fail(GENLIB_EINVAL, "plan was built for several ranks: use genlib_engine_create_dist");
+    return create_engine(plan, numerics, device, 0, out);
+}
+
+int genlib_engine_create_dist(const genlib_plan *plan, int numerics, int device, int32_t rank, genlib_engine **out) {
+    return create_engine(plan, numerics, device, rank, out);
+}
+
+int genlib_engine_ipc_export(genlib_engine *eng, void *handle64) {
+    if (!eng || !handle64) return fail(GENLIB_EINVAL, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     DeviceGuard guard;
-    if (int rc = guard.enter(device)) return rc;
-    std::unique_ptr<genlib_engine> E(new (std::nothrow) genlib_engine);
-    if (!E) return fail(GENLIB_ENOMEM, "out of host memory");
-    const Plan &P = plan->p;
-    E->plan = plan; E->numerics = numerics;
-    E->esize = numerics == GENLIB_NUMERICS_FP64 ? 8 : 4;
-    CU(cudaGetDevice(&E->device));
-    const size_t need = engine_bytes(P, numerics);
-    const double t0 = now_ms();
-    CU(cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&E->copy_stream, cudaStreamNonBlocking));
-    {
-        cudaError_t ce = g_arenas.acquire(E->device, need, E->arena);
-        if (ce != cudaSuccess) {
-            E->arena = Arena();
-            cudaGetLastError();
-            size_t free_b = 0, total_b = 0;
-            cudaMemGetInfo(&free_b, &total_b);
-            char msg[256];
-            std::snprintf(msg, sizeof msg, "frontier needs %.2f GB on the device, %.2f GB free (capacity %lld slots): shard over more GPUs",
-                          need / 1e9, free_b / 1e9, (long long)P.capacity);
-            return fail(GENLIB_ENOMEM, msg);
-        }
-        unsigned char *cur = static_cast<unsigned char *>(E->arena.base);
-        auto take = [&](size_t bytes) { unsigned char *p = cur; cur += pad256(bytes); return p; };
-        E->A = take((size_t)P.capacity * (size_t)P.capacity * E->esize);
-        E->Rt = reinterpret_cast<double *>(take(P.rt_elems_max * sizeof(double)));
-        E->V = take(P.v_elems_max * E->esize);
-        E->Vt = take(P.v_elems_max * E->esize);
-        E->Dg = take(P.fam_pf.size() * E->esize);
-        E->fetch_stage[0] = take(kFetchStageBytes);
-        E->fetch_stage[1] = take(kFetchStageBytes);
-        E->mem_ind.place(cur, P.mem_ind.size()); E->mem_slot.place(cur, P.mem_slot.size()); E->mem_fam.place(cur, P.mem_fam.size());
-        E->fam_pf.place(cur, P.fam_pf.size()); E->fam_pm.place(cur, P.fam_pm.size());
-        E->fam_minrank.place(cur, P.fam_minrank.size()); E->fam_maxrank.place(cur, P.fam_maxrank.size());
-        E->fam_start.place(cur, P.fam_start.size());
-        E->mt_min.place(cur, P.mtile_minrank.size()); E->mt_max.place(cur, P.mtile_maxrank.size());
-        E->mt_fam0.place(cur, P.mtile_fam0.size()); E->mt_nfam.place(cur, P.mtile_nfam.size());
-        E->pro_slot.place(cur, P.pro_slot.size()); E->flags.place(cur, P.flags.size()); E->acc.place(cur, 2);
-        if ((size_t)(cur - static_cast<unsigned char *>(E->arena.base)) > need) return fail(GENLIB_EINVAL, "internal: arena layout overflow");
-    }
-    CU(E->mem_ind.upload(P.mem_ind, E->stream));
-    CU(E->mem_slot.upload(P.mem_slot, E->stream));
-    CU(E->mem_fam.upload(P.mem_fam, E->stream));
-    CU(E->fam_pf.upload(P.fam_pf, E->stream));
-    CU(E->fam_pm.upload(P.fam_pm, E->stream));
-    CU(E->fam_start.upload(P.fam_start, E->stream));
-    CU(E->fam_minrank.upload(P.fam_minrank, E->stream));
-    CU(E->fam_maxrank.upload(P.fam_maxrank, E->stream));
-    CU(E->mt_min.upload(P.mtile_minrank, E->stream));
-    CU(E->mt_max.upload(P.mtile_maxrank, E->stream));
-    CU(E->mt_fam0.upload(P.mtile_fam0, E->stream));
-    CU(E->mt_nfam.upload(P.mtile_nfam, E->stream));
-    CU(E->pro_slot.upload(P.pro_slot, E->stream));
-    CU(E->flags.upload(P.flags, E->stream));
-    CU(cudaStreamSynchronize(E->stream));
-    E->info.resize(P.layers.size());
-    for (size_t t = 0; t < P.layers.size(); t++) fill_info(P.layers[t], &E->info[t]);
-    E->events.resize(P.layers.size() * 4 + 2);
-    for (auto &e : E->events) CU(cudaEventCreate(&e));
-    genlib_stats &s = E->stats;
-    s.n_unique = P.n_unique; s.n_layers = (int32_t)P.layers.size(); s.row_updates = P.row_updates;
-    s.capacity = P.capacity; s.device_bytes = (int64_t)need; s.alg_bytes = P.alg_elems * (double)E->esize;
-    s.ms_plan = plan->ms_plan; s.ms_upload = now_ms() - t0;
-    s.h2d_bytes = (int64_t)(plan_index_bytes(P) + P.flags.size());
-    *out = E.release();
+    if (int rc = guard.enter(eng->device)) return rc;
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, eng->arena.base));
+    std::memcpy(handle64, &h, sizeof h);
     return GENLIB_OK;
+}
+
+int genlib_engine_ipc_attach(genlib_engine *eng, const void *handles, size_t stride) {
+    if (!eng || !handles || stride < 64) return fail(GENLIB_EINVAL, "null argument");
+    if (eng->attached) return GENLIB_OK;
+    DeviceGuard guard;
+    if (int rc = guard.enter(eng->device)) return rc;
+    const Plan &P = eng->plan->p;
+    for (int g = 0; g < eng->world; g++) {
+        if (g == eng->rank) continue;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, static_cast<const unsigned char *>(handles) + (size_t)g * stride, sizeof h);
+        void *base = nullptr;
+        cudaError_t ce = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+        if (ce != cudaSuccess) {
+            cudaGetLastError();
+            return fail(GENLIB_ECOMM, std::string("cudaIpcOpenMemHandle(rank ") + std::to_string(g) + "): " + cudaGetErrorString(ce));
+        }
+        eng->peer_base[g] = base;
+        unsigned char *b = static_cast<unsigned char *>(base);
+        eng->bars.flags[g] = reinterpret_cast<unsigned *>(b);
+        eng->peers.A[g] = b + off_A();
+        eng->peers.Vrow[g] = b + off_Vrow(P, eng->esize, g);
+    }
+    eng->attached = true;
+    return GENLIB_OK;
+}
+
+int32_t genlib_engine_own_probands(const genlib_engine *eng, int32_t *index) {
+    if (!eng) return -1;
+    if (index) std::copy(eng->own_pro.begin(), eng->own_pro.end(), index);
+    return (int32_t)eng->own_pro.size();
 }
 
 void genlib_engine_destroy(genlib_engine *eng) {
@@ -481,6 +655,7 @@ int genlib_engine_run(genlib_engine *eng, int time_layers) {
     DeviceGuard guard;
     if (int rc = guard.enter(eng->device)) return rc;
     genlib_engine &E = *eng;
+    if (!E.attached) return fail(GENLIB_ECOMM, "genlib_engine_run before genlib_engine_ipc_attach");
     const size_t nev = E.events.size();
     CU(cudaEventRecord(E.events[nev - 2], E.stream));
     int rc = E.numerics == GENLIB_NUMERICS_FP64 ? launch_layers<double>(E, time_layers != 0)
@@ -503,6 +678,11 @@ int genlib_engine_run(genlib_engine *eng, int time_layers) {
             ev += 4;
             E.info[t].ms_cross = a; E.info[t].ms_couple = b; E.info[t].ms_expand = c;
         }
+    }
+    if (E.world > 1) {
+        unsigned errw = 0;
+        CU(cudaMemcpy(&errw, E.bar_flags + kMaxWorld, sizeof errw, cudaMemcpyDeviceToHost));
+        if (errw) return fail(GENLIB_ECOMM, "a rank did not reach the inter-GPU barrier within the time limit");
     }
     E.ran = true;
     return GENLIB_OK;
@@ -539,6 +719,7 @@ int genlib_engine_fetch(genlib_engine *eng, void *out, int out_dtype) {
 int genlib_engine_phi_mean(genlib_engine *eng, double *out) {
     if (!eng || !out) return fail(GENLIB_EINVAL, "null argument");
     if (!eng->ran) return fail(GENLIB_EINVAL, "genlib_engine_phi_mean before genlib_engine_run");
+    if (eng->world != 1) return fail(GENLIB_EINVAL, "genlib_engine_phi_mean: single-rank engines only");
     DeviceGuard guard;
     if (int rc = guard.enter(eng->device)) return rc;
     const Plan &P = eng->plan->p;
@@ -565,6 +746,7 @@ int genlib_engine_set_layer_limit(genlib_engine *eng, int32_t n_layers) {
 
 int genlib_engine_read_block(genlib_engine *eng, int32_t n_slots, const int32_t *slots, double *out) {
     if (!eng || !slots || !out || n_slots < 0) return fail(GENLIB_EINVAL, "null argument");
+    if (eng->world != 1) return fail(GENLIB_EINVAL, "genlib_engine_read_block: single-rank engines only");
     DeviceGuard guard;
     if (int rc = guard.enter(eng->device)) return rc;
     if (n_slots == 0) return GENLIB_OK;
@@ -580,9 +762,9 @@ int genlib_engine_read_block(genlib_engine *eng, int32_t n_slots, const int32_t 
         const int32_t nr = std::min(65535, n_slots - r0);
         dim3 grid((unsigned)std::min<int32_t>((n_slots + 255) / 256, 64), (unsigned)nr);
         if (eng->numerics == GENLIB_NUMERICS_FP64)
-            gather_kernel<double, double><<<grid, 256, 0, eng->stream>>>((const double *)eng->A, P.capacity, dslots, n_slots, r0, nr, dout + (size_t)r0 * n_slots);
+            gather_kernel<double, double><<<grid, 256, 0, eng->stream>>>((const double *)eng->A, P.capacity, dslots, dslots, n_slots, r0, nr, dout + (size_t)r0 * n_slots);
         else
-            gather_kernel<float, double><<<grid, 256, 0, eng->stream>>>((const float *)eng->A, P.capacity, dslots, n_slots, r0, nr, dout + (size_t)r0 * n_slots);
+            gather_kernel<float, double><<<grid, 256, 0, eng->stream>>>((const float *)eng->A, P.capacity, dslots, dslots, n_slots, r0, nr, dout + (size_t)r0 * n_slots);
     }
     CU(cudaMemcpyAsync(out, dout, (size_t)n_slots * n_slots * sizeof(double), cudaMemcpyDeviceToHost, eng->stream));
     CU(cudaStreamSynchronize(eng->stream));

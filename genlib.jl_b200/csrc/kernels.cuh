@@ -27,10 +27,25 @@
 
 namespace genlib {
 
+constexpr int kMaxWorld = 16;
+
+// Where every rank keeps its frontier rows and its couple-matrix rows.  One process per GPU:
+// entries of other ranks are CUDA-IPC mappings of their arenas (NVLink peer memory).
+struct PeerTable {
+    void *A[kMaxWorld];       // rows_cap[g] x ld frontier rows of rank g
+    void *Vrow[kMaxWorld];    // own couples x nf_pad rows of V on rank g
+};
+
 struct LayerArgs {
     int32_t n_new, n_fam, rt_lo, rt_rows, nf_pad, any_carried;
-    const int32_t *mem_ind, *mem_slot, *mem_fam;
+    // row sharding: this rank owns couples [own_f0, own_f0 + own_nf) and members
+    // [own_m0, own_m0 + own_nm); nfo_pad = row stride of its transposed cross block
+    int32_t rank, world, own_f0, own_nf, own_m0, own_nm, nfo_pad;
+    int32_t fam_base[kMaxWorld + 1];
+    const int32_t *mem_ind, *mem_slot, *mem_fam, *mem_lrow;
     const int32_t *fam_pf, *fam_pm, *fam_start;
+    const int8_t *fam_pf_owner, *fam_pm_owner, *live_owner;
+    const int32_t *fam_pf_lrow, *fam_pm_lrow, *live_lrow;
     const uint8_t *flags;
     const int32_t *fam_minrank, *fam_maxrank;
     const int32_t *mt_minrank, *mt_maxrank, *mt_fam0, *mt_nfam;
@@ -78,10 +93,10 @@ __device__ __forceinline__ double half_sum(double x, double y) { return fma(0.5,
 // =====================================================================================
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 4)
-cross_kernel(T *__restrict__ A, int64_t ld, double *__restrict__ Rt, LayerArgs L) {
+cross_kernel(T *__restrict__ A, int64_t ld, double *__restrict__ Rt, PeerTable PT, LayerArgs L) {
     extern __shared__ double sR[];                       // [kFTile][kSRStride]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int F0 = blockIdx.y * kFTile;
+    const int F0 = blockIdx.y * kFTile;                  // local couple index (own couples only)
     const int pt = blockIdx.x;
     const int p0 = L.rt_lo + pt * kPTile;
     const uint8_t *fl = L.flags + (size_t)pt * kPTile;
@@ -90,22 +105,27 @@ cross_kernel(T *__restrict__ A, int64_t ld, double *__restrict__ Rt, LayerArgs L
     if (!live_here) return;                              // hole in a fragmented slot range
     const int carried_here = L.any_carried ? __syncthreads_or(myflag & kFlagCarried) : 0;
 
-    // ---- gather-average of the two parent rows ----
-    int pf[4], pm[4];
+    // ---- gather-average of the two parent rows (wherever they live: local HBM or a peer's,
+    //      read through NVLink) ----
+    const T *rf[4], *rm[4];
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-        const int F = F0 + warp * 4 + q;
-        const bool ok = F < L.n_fam;
-        pf[q] = ok ? L.fam_pf[F] : -1;
-        pm[q] = ok ? L.fam_pm[F] : -1;
+        const int Fl = F0 + warp * 4 + q;
+        rf[q] = nullptr; rm[q] = nullptr;
+        if (Fl < L.own_nf) {
+            const int F = L.own_f0 + Fl;
+            const int of = L.fam_pf_owner[F], om = L.fam_pm_owner[F];
+            if (of >= 0) rf[q] = static_cast<const T *>(PT.A[of]) + (int64_t)L.fam_pf_lrow[F] * ld + p0 + 4 * lane;
+            if (om >= 0) rm[q] = static_cast<const T *>(PT.A[om]) + (int64_t)L.fam_pm_lrow[F] * ld + p0 + 4 * lane;
+        }
     }
     double x[4][4], y[4][4];
 #pragma unroll
     for (int q = 0; q < 4; q++) {
 #pragma unroll
         for (int k = 0; k < 4; k++) { x[q][k] = 0.0; y[q][k] = 0.0; }
-        if (pf[q] >= 0) load4(A + (int64_t)pf[q] * ld + p0 + 4 * lane, x[q]);
-        if (pm[q] >= 0) load4(A + (int64_t)pm[q] * ld + p0 + 4 * lane, y[q]);
+        if (rf[q]) load4(rf[q], x[q]);
+        if (rm[q]) load4(rm[q], y[q]);
     }
 #pragma unroll
     for (int q = 0; q < 4; q++) {
@@ -119,11 +139,12 @@ cross_kernel(T *__restrict__ A, int64_t ld, double *__restrict__ Rt, LayerArgs L
             // rows of the new members against this tile's columns (rounded once, compute.jl:296).
             // Columns that are not carried receive values nobody reads; new x new is
             // rewritten by expand_kernel afterwards.
-            const int F = F0 + warp * 4 + q;
-            if (F < L.n_fam) {
+            const int Fl = F0 + warp * 4 + q;
+            if (Fl < L.own_nf) {
+                const int F = L.own_f0 + Fl;
                 const int m1 = L.fam_start[F + 1];
                 for (int m = L.fam_start[F]; m < m1; m++)
-                    store4(A + (int64_t)L.mem_slot[m] * ld + p0 + 4 * lane, r);
+                    store4(A + (int64_t)L.mem_lrow[m] * ld + p0 + 4 * lane, r);
             }
         }
     }
@@ -132,18 +153,20 @@ cross_kernel(T *__restrict__ A, int64_t ld, double *__restrict__ Rt, LayerArgs L
     // ---- transposed, unrounded: Rt[p, F] for every live column p of the tile ----
     for (int pl = warp; pl < kPTile; pl += kThreads / 32) {
         if (fl[pl] & kFlagLive)
-            Rt[((size_t)pt * kPTile + pl) * L.nf_pad + F0 + lane] = sR[lane * kSRStride + pl];
+            Rt[((size_t)pt * kPTile + pl) * L.nfo_pad + F0 + lane] = sR[lane * kSRStride + pl];
     }
-    // ---- mirror: columns of the new members in the rows of carried individuals ----
+    // ---- mirror: columns of the new members in the rows of carried individuals (a peer
+    //      store when the carried row lives on another GPU) ----
     if (carried_here) {
-        const int m0 = L.fam_start[F0];
-        const int Fe = min(F0 + kFTile, L.n_fam);
+        const int m0 = L.fam_start[L.own_f0 + F0];
+        const int Fe = L.own_f0 + min(F0 + kFTile, L.own_nf);
         const int m1 = L.fam_start[Fe];
         for (int pl = warp; pl < kPTile; pl += kThreads / 32) {
             if (!(fl[pl] & kFlagCarried)) continue;
-            T *row = A + (int64_t)(p0 + pl) * ld;
+            const size_t r = (size_t)pt * kPTile + pl;
+            T *row = static_cast<T *>(PT.A[L.live_owner[r]]) + (int64_t)L.live_lrow[r] * ld;
             for (int m = m0 + lane; m < m1; m += 32)
-                row[L.mem_slot[m]] = (T)sR[(L.mem_fam[m] - F0) * kSRStride + pl];
+                row[L.mem_slot[m]] = (T)sR[(L.mem_fam[m] - L.own_f0 - F0) * kSRStride + pl];
         }
     }
 }
@@ -162,49 +185,56 @@ constexpr int kCStride = kCTile + 1;
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
-couple_kernel(const T *__restrict__ A, int64_t ld, const double *__restrict__ Rt, T *__restrict__ V,
-              T *__restrict__ Vt, T *__restrict__ Dg, LayerArgs L) {
+couple_kernel(int64_t ld, const double *__restrict__ Rt, T *__restrict__ Vt, T *__restrict__ Dg, PeerTable PT,
+              LayerArgs L) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *sV = reinterpret_cast<T *>(smem_raw);                  // [kFTile][kCStride]
     __shared__ int s_skip[kFTile];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // rows: ALL couples F of the layer; columns: this rank's own couples G (local index gl)
     const int F0 = blockIdx.y * kFTile, G0 = blockIdx.x * kCTile;
-    const int minG = L.fam_minrank[min(G0, L.n_fam - 1)];     // minrank increases with the couple index
-    const int g = G0 + 4 * lane;
-    const bool col_ok = g < L.nf_pad;                         // nf_pad is a multiple of 4
+    const int minG = L.fam_minrank[L.own_f0 + min(G0, max(L.own_nf - 1, 0))];   // increases inside the own range
+    const int gl = G0 + 4 * lane;
+    const bool col_ok = gl < L.nfo_pad;                       // nfo_pad is a multiple of 4
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         const int fl = warp * 4 + q, F = F0 + fl;
         bool skip = true;
-        if (F < L.n_fam && G0 < L.n_fam) {
+        if (F < L.n_fam && G0 < L.own_nf) {
             const int pf = L.fam_pf[F], pm = L.fam_pm[F];
-            if (blockIdx.x == 0 && lane == 0) {
-                double d = 0.5;
-                if (pf >= 0 && pm >= 0) d = fma(0.5, (double)A[(int64_t)pf * ld + pm], 0.5);
+            if (blockIdx.x == 0 && lane == 0 && F >= L.own_f0 && F < L.own_f0 + L.own_nf) {
+                double d = 0.5;                               // diagonal of the couple's members
+                if (pf >= 0 && pm >= 0)
+                    d = fma(0.5, (double)(static_cast<const T *>(PT.A[L.fam_pf_owner[F]]) + (int64_t)L.fam_pf_lrow[F] * ld)[pm], 0.5);
                 Dg[F] = (T)d;
             }
             skip = L.fam_maxrank[F] <= minG;                  // nobody in F outranks anybody in the tile
             if (!skip && col_ok) {
                 double a[4] = {0.0, 0.0, 0.0, 0.0}, b[4] = {0.0, 0.0, 0.0, 0.0};
-                if (pf >= 0) load4(Rt + (size_t)(pf - L.rt_lo) * L.nf_pad + g, a);
-                if (pm >= 0) load4(Rt + (size_t)(pm - L.rt_lo) * L.nf_pad + g, b);
+                if (pf >= 0) load4(Rt + (size_t)(pf - L.rt_lo) * L.nfo_pad + gl, a);
+                if (pm >= 0) load4(Rt + (size_t)(pm - L.rt_lo) * L.nfo_pad + gl, b);
                 T v[4];
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     v[k] = (T)half_sum(a[k], b[k]);
                     sV[fl * kCStride + 4 * lane + k] = v[k];
                 }
-                store_vec4(V + (size_t)F * L.nf_pad + g, v);
+                // V[F, own G] goes to the rank that owns couple F (its row block of V): local, or
+                // a 16-byte peer store over NVLink
+                int o = 0;
+                while (o + 1 < L.world && F >= L.fam_base[o + 1]) o++;
+                T *vrow = static_cast<T *>(PT.Vrow[o]) + (size_t)(F - L.fam_base[o]) * L.nf_pad + L.own_f0;
+                store_vec4(vrow + gl, v);
             }
         }
         if (lane == 0) s_skip[fl] = skip;
     }
     __syncthreads();
-    // transposed: Vt[G, F0 .. F0+32), one couple column per warp iteration, lane = couple row
+    // transposed, local: Vt[own G, F0 .. F0+32), one couple column per warp iteration, lane = couple row
     const bool row_ok = (F0 + lane < L.n_fam) && !s_skip[lane];
-    const int gl_end = min(kCTile, L.n_fam - G0);
-    for (int gl = warp; gl < gl_end; gl += kThreads / 32)
-        if (row_ok) Vt[(size_t)(G0 + gl) * L.nf_pad + F0 + lane] = sV[lane * kCStride + gl];
+    const int gl_end = min(kCTile, L.own_nf - G0);
+    for (int g = warp; g < gl_end; g += kThreads / 32)
+        if (row_ok) Vt[(size_t)(G0 + g) * L.nf_pad + F0 + lane] = sV[lane * kCStride + g];
 }
 
 // =====================================================================================
@@ -294,9 +324,9 @@ expand_kernel(T *__restrict__ A, int64_t ld, const T *__restrict__ V, const T *_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // blockIdx.x = column chunk (fastest): CTAs that run together stream the SAME couple rows of
     // V / Vt and the same output rows at adjacent columns
-    const int row0 = (blockIdx.y * kEWarps + warp) * kERows;
-    if (row0 >= L.n_new) return;                            // no block-wide barrier below
-    const int nr = min(kERows, L.n_new - row0);
+    const int row0 = L.own_m0 + (blockIdx.y * kEWarps + warp) * kERows;   // this rank's member rows only
+    if (row0 >= L.own_m0 + L.own_nm) return;                // no block-wide barrier below
+    const int nr = min(kERows, L.own_m0 + L.own_nm - row0);
     const unsigned stage_bytes = (unsigned)expand_stage_bytes<T>(L.vstride);
     const unsigned mine = (unsigned)__cvta_generic_to_shared(smem_raw) + (unsigned)warp * 2u * stage_bytes;
     const unsigned row_bytes = (unsigned)L.vstride * (unsigned)sizeof(T);
@@ -305,7 +335,7 @@ expand_kernel(T *__restrict__ A, int64_t ld, const T *__restrict__ V, const T *_
 
     // ---- the warp's rows: couple, rank, row pointer (registers) ----
     const int mrow = row0 + min(lane, nr - 1);
-    const int myfam = L.mem_fam[mrow], myrank = L.mem_ind[mrow], myslot = L.mem_slot[mrow];
+    const int myfam = L.mem_fam[mrow], myrank = L.mem_ind[mrow], myslot = L.mem_lrow[mrow];   // local row
     const int f0 = __shfl_sync(0xffffffffu, myfam, 0);
     const int nfr = __shfl_sync(0xffffffffu, myfam, nr - 1) - f0 + 1;      // <= kERows couples
     int minI = myrank, maxI = myrank;
@@ -339,8 +369,8 @@ expand_kernel(T *__restrict__ A, int64_t ld, const T *__restrict__ V, const T *_
         t_info = nchunk | (maxI > L.mt_minrank[Jl] ? 0x100 : 0)      // some row outranks some column
                         | (L.mt_maxrank[Jl] > minI ? 0x200 : 0);
     }
-    const T *vsrc = V + (size_t)f0 * L.nf_pad + lane * kVec;
-    const T *vtsrc = Vt + (size_t)f0 * L.nf_pad + lane * kVec;
+    const T *vsrc = V + (size_t)(f0 - L.own_f0) * L.nf_pad + lane * kVec;     // V, Vt hold own couple rows
+    const T *vtsrc = Vt + (size_t)(f0 - L.own_f0) * L.nf_pad + lane * kVec;
     const int32_t *msrc = L.mem_fam + 4 * lane;
     const long long mstride1 = L.mem_ind - L.mem_fam, mstride2 = L.mem_slot - L.mem_fam;
 
@@ -396,7 +426,7 @@ expand_kernel(T *__restrict__ A, int64_t ld, const T *__restrict__ V, const T *_
             const bool vec = ncol == 4 && ((sj[0] & 3) == 0) && sj[1] == sj[0] + 1 && sj[2] == sj[0] + 2 &&
                              sj[3] == sj[0] + 3;
             const int dk0 = row0 - j0;                     // the diagonal crosses this lane's columns?
-            const bool diag_tile = (row0 / kMTile) == J;   // warp-uniform (kERows divides kMTile)
+            const bool diag_tile = (row0 / kMTile) == J || ((row0 + kERows - 1) / kMTile) == J;   // warp-uniform
             if (nr == kERows && vec) {
                 if (diag_tile) expand_step<T, true, true>(go, rj, sj, roff, rrank, rptr, vba_off, nr, ncol, dk0, Dg, rfam);
                 else expand_step<T, true, false>(go, rj, sj, roff, rrank, rptr, vba_off, nr, ncol, dk0, Dg, rfam);
@@ -409,20 +439,22 @@ expand_kernel(T *__restrict__ A, int64_t ld, const T *__restrict__ V, const T *_
 }
 
 // =====================================================================================
-// proband gather (compute.jl:303: the last frontier, rows/columns in probandIDs order)
+// proband gather (compute.jl:303: the last frontier, rows/columns in probandIDs order).
+// rows[] are LOCAL rows of this rank's probands, cols[] the global slots of all probands.
 // =====================================================================================
 template <typename T, typename O>
-__global__ void gather_kernel(const T *__restrict__ A, int64_t ld, const int32_t *__restrict__ slots,
-                              int32_t P, int32_t row0, int32_t nrows, O *__restrict__ out) {
-    const int u = row0 + blockIdx.y;
+__global__ void gather_kernel(const T *__restrict__ A, int64_t ld, const int32_t *__restrict__ rows,
+                              const int32_t *__restrict__ cols, int32_t P, int32_t row0, int32_t nrows,
+                              O *__restrict__ out) {
     if (blockIdx.y >= (unsigned)nrows) return;
-    const T *row = A + (int64_t)slots[u] * ld;
+    const T *row = A + (int64_t)rows[row0 + blockIdx.y] * ld;
     O *dst = out + (size_t)blockIdx.y * P;
     for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < P; v += gridDim.x * blockDim.x)
-        dst[v] = (O)row[slots[v]];
+        dst[v] = (O)row[cols[v]];
 }
 
-// sum and trace of the proband block, binary64 accumulation (phiMean, compute.jl:454-459)
+// sum and trace of the proband block, binary64 accumulation (phiMean, compute.jl:454-459);
+// one rank: rows == cols == the proband slots
 template <typename T>
 __global__ void mean_kernel(const T *__restrict__ A, int64_t ld, const int32_t *__restrict__ slots,
                             int32_t P, double *__restrict__ acc /* [0]=sum, [1]=trace */) {
@@ -444,6 +476,34 @@ __global__ void mean_kernel(const T *__restrict__ A, int64_t ld, const int32_t *
         atomicAdd(acc, s);
         atomicAdd(acc + 1, tr);
     }
+}
+
+// =====================================================================================
+// barrier_kernel: all ranks of one box meet here (one process per GPU, so every rank's
+// kernel is resident on its own device).  Rank r stores `epoch` into slot r of every peer's
+// flag array (release, system scope, through the NVLink mapping) and waits until all slots of
+// its own array have reached `epoch`.  A rank that waits longer than ~10 s records an error
+// instead of hanging.
+// =====================================================================================
+struct BarrierTable {
+    unsigned *flags[kMaxWorld];   // [world] words on each rank; word kMaxWorld = error flag
+};
+
+__global__ void barrier_kernel(BarrierTable B, int rank, int world, unsigned epoch, long long timeout_cycles) {
+    const int peer = threadIdx.x;
+    if (peer >= world) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(B.flags[peer] + rank), "r"(epoch) : "memory");
+    const unsigned *mine = B.flags[rank] + peer;
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+        if ((int)(v - epoch) >= 0) break;
+        if (clock64() - t0 > timeout_cycles) { B.flags[rank][kMaxWorld] = 1u; break; }
+        __nanosleep(200);
+    }
+    __threadfence_system();
 }
 
 }  // namespace genlib

@@ -124,15 +124,41 @@ int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t 
         for (int32_t k = 0; k < S; k++) { a += d_cut[k]; b += d_both[k]; cut_size[k] = (int32_t)a; both_size[k] = (int32_t)b; }
     }
 
+    if (world > 127) { err = "at most 127 ranks"; return GENLIB_EINVAL; }
     P.layers.resize(S);
-    P.mem_ind.reserve(lstart[S]); P.mem_slot.reserve(lstart[S]); P.mem_fam.reserve(lstart[S]);
-    std::vector<int32_t> slot_of((size_t)n, -1);
+    P.mem_ind.reserve(lstart[S] + 4 * (size_t)S); P.mem_slot.reserve(lstart[S] + 4 * (size_t)S);
+    P.mem_fam.reserve(lstart[S] + 4 * (size_t)S); P.mem_lrow.reserve(lstart[S] + 4 * (size_t)S);
+    std::vector<int32_t> slot_of((size_t)n, -1), lrow_of((size_t)n, -1);
+    std::vector<int8_t> owner_of((size_t)n, 0);
     std::vector<int32_t> live, next_live;        // individuals live before the current step
-    std::vector<int32_t> freelist;               // ascending free slots below next_fresh
-    int32_t next_fresh = 0;
+    // lowest-free-first allocators: global column slots, and local rows per rank
+    struct Alloc {
+        std::vector<int32_t> freelist;           // ascending
+        int32_t next_fresh = 0;
+        size_t cursor = 0;
+        int32_t take() { return cursor < freelist.size() ? freelist[cursor++] : next_fresh++; }
+        void end_layer(std::vector<int32_t> &freed_sorted) {
+            freelist.erase(freelist.begin(), freelist.begin() + (ptrdiff_t)cursor);
+            cursor = 0;
+            if (!freed_sorted.empty()) {
+                std::vector<int32_t> merged(freelist.size() + freed_sorted.size());
+                std::merge(freelist.begin(), freelist.end(), freed_sorted.begin(), freed_sorted.end(), merged.begin());
+                freelist.swap(merged);
+                freed_sorted.clear();
+            }
+        }
+    };
+    Alloc slots;
+    std::vector<Alloc> rows((size_t)world);
+    std::vector<std::vector<int32_t>> freed_rows((size_t)world);
+    P.rows_cap.assign((size_t)world, 0);
+    P.rank_rt_elems.assign((size_t)world, 0);
+    P.rank_v_elems.assign((size_t)world, 0);
     FamilyTable table;
-    std::vector<int32_t> fam_of, fam_count, fam_first, order;
+    std::vector<int32_t> fam_of, fam_count, fam_first, order, newid, load((size_t)world);
+    std::vector<int8_t> fam_own;
     std::vector<int32_t> freed;
+    int32_t rr = 0;
 
     for (int32_t t = 0; t < S; t++) {
         Layer &L = P.layers[t];
@@ -144,11 +170,12 @@ int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t 
         L.ref_probands = cut_size[t];
         L.ref_both = t > 0 ? both_size[t - 1] : 0;
         // member arrays of a layer start 16-byte aligned (the expand kernel copies them in 16-byte chunks)
-        while (P.mem_ind.size() % 4) { P.mem_ind.push_back(0); P.mem_slot.push_back(0); P.mem_fam.push_back(0); }
+        while (P.mem_ind.size() % 4) { P.mem_ind.push_back(0); P.mem_slot.push_back(0); P.mem_fam.push_back(0); P.mem_lrow.push_back(0); }
         L.mem_off = P.mem_ind.size();
         L.fam_off = P.fam_pf.size();
         L.flag_off = P.flags.size();
         L.mtile_off = P.mtile_minrank.size();
+        L.base_off = P.fam_base.size();
 
         // ---- live range and flags (state BEFORE the step) ----
         freed.clear();
@@ -159,12 +186,18 @@ int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t 
             L.rt_lo = (lo / kPTile) * kPTile;
             L.rt_rows = round_up(hi + 1, kPTile) - L.rt_lo;
             P.flags.resize(L.flag_off + (size_t)L.rt_rows, 0);
+            P.live_owner.resize(L.flag_off + (size_t)L.rt_rows, 0);
+            P.live_lrow.resize(L.flag_off + (size_t)L.rt_rows, 0);
             uint8_t *fl = P.flags.data() + L.flag_off;
             for (int32_t x : live) {
                 // read for the last time in step last_read[x]; probands stay to the end
-                bool stays = is_pro[x] || last_read[x] > t;
-                fl[slot_of[x] - L.rt_lo] = (uint8_t)(kFlagLive | (stays ? kFlagCarried : 0));
+                const bool stays = is_pro[x] || last_read[x] > t;
+                const int32_t r = slot_of[x] - L.rt_lo;
+                fl[r] = (uint8_t)(kFlagLive | (stays ? kFlagCarried : 0));
+                P.live_owner[L.flag_off + r] = owner_of[x];
+                P.live_lrow[L.flag_off + r] = lrow_of[x];
                 if (stays) { next_live.push_back(x); L.carried++; }
+                else if (world > 1) freed_rows[owner_of[x]].push_back(lrow_of[x]);
             }
             for (int32_t r = 0; r < L.rt_rows; r++)        // evicted slots, already in ascending order
                 if (fl[r] == kFlagLive) freed.push_back(L.rt_lo + r);
@@ -190,48 +223,97 @@ int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t 
             }
             fam_count[fam_of[q]]++;
         }
-        const int32_t nf = (int32_t)fam_count.size();
+        const int32_t nf_real = (int32_t)fam_count.size();
+
+        // ---- row owners: a couple's children live with one of their parents' rows (the other
+        //      parent row is read through NVLink); spill to the least loaded rank past +12.5 %.
+        //      Couples are renumbered rank-major; every rank's range starts at a multiple of 4
+        //      (16-byte aligned couple columns), the gaps are empty dummy couples. ----
+        fam_own.assign((size_t)nf_real, 0);
+        newid.assign((size_t)nf_real, 0);
+        P.fam_base.resize(L.base_off + (size_t)world + 1, 0);
+        P.mem_base.resize(L.base_off + (size_t)world + 1, 0);
+        int32_t *fbase = P.fam_base.data() + L.base_off, *mbase = P.mem_base.data() + L.base_off;
+        int32_t nf = nf_real;
+        if (world > 1) {
+            std::fill(load.begin(), load.end(), 0);
+            std::vector<int32_t> cnt((size_t)world, 0);
+            const int32_t cap = (nn + world - 1) / world + (nn + world - 1) / world / 8 + kMaxFamily;
+            for (int32_t f = 0; f < nf_real; f++) {
+                const int32_t x = X[fam_first[f]];
+                const int32_t fa = father[x], mo = mother[x];
+                int32_t g;
+                if (fa >= 0 && mo >= 0) g = load[owner_of[mo]] < load[owner_of[fa]] ? owner_of[mo] : owner_of[fa];
+                else if (fa >= 0) g = owner_of[fa];
+                else if (mo >= 0) g = owner_of[mo];
+                else g = rr++ % world;
+                if (load[g] + fam_count[f] > cap) g = (int32_t)(std::min_element(load.begin(), load.end()) - load.begin());
+                fam_own[f] = (int8_t)g;
+                load[g] += fam_count[f];
+                cnt[g]++;
+            }
+            for (int32_t g = 0; g < world; g++) fbase[g + 1] = round_up(fbase[g] + cnt[g], 4);
+            nf = fbase[world];
+            std::vector<int32_t> pos(fbase, fbase + world);
+            for (int32_t f = 0; f < nf_real; f++) newid[f] = pos[fam_own[f]]++;     // rank-major, stable
+        } else {
+            fbase[1] = nf;
+            for (int32_t f = 0; f < nf_real; f++) newid[f] = f;
+        }
         L.n_fam = nf;
         L.nf_pad = round_up(std::max(nf, 1), 32);
-        // family-major order (families by first member's rank, members by rank)
+        // couple-major member order (couples rank-major, then by first member's rank; members by rank)
         size_t fs0 = P.fam_start.size();
         P.fam_start.resize(fs0 + (size_t)nf + 1);
         int32_t *fstart = P.fam_start.data() + fs0;
-        fstart[0] = 0;
-        for (int32_t f = 0; f < nf; f++) fstart[f + 1] = fstart[f] + fam_count[f];
+        std::fill(fstart, fstart + nf + 1, 0);
+        for (int32_t f = 0; f < nf_real; f++) fstart[newid[f] + 1] = fam_count[f];
+        for (int32_t f = 0; f < nf; f++) fstart[f + 1] += fstart[f];
+        for (int32_t g = 0; g <= world; g++) mbase[g] = fstart[fbase[g]];
         order.assign((size_t)nn, 0);
         {
             std::vector<int32_t> pos(fstart, fstart + nf);
-            for (int32_t q = 0; q < nn; q++) order[pos[fam_of[q]]++] = q;
+            for (int32_t q = 0; q < nn; q++) order[pos[newid[fam_of[q]]]++] = q;
         }
-        // ---- slots: lowest free first, then fresh ones ----
-        size_t take = std::min((size_t)nn, freelist.size());
-        P.mem_ind.resize(L.mem_off + (size_t)nn); P.mem_slot.resize(L.mem_off + (size_t)nn); P.mem_fam.resize(L.mem_off + (size_t)nn);
+        // ---- column slots (global) and local rows (per owner): lowest free first, then fresh ----
+        P.mem_ind.resize(L.mem_off + (size_t)nn); P.mem_slot.resize(L.mem_off + (size_t)nn);
+        P.mem_fam.resize(L.mem_off + (size_t)nn); P.mem_lrow.resize(L.mem_off + (size_t)nn);
         {
-            int32_t *mi = P.mem_ind.data() + L.mem_off, *ms = P.mem_slot.data() + L.mem_off, *mf = P.mem_fam.data() + L.mem_off;
+            int32_t *mi = P.mem_ind.data() + L.mem_off, *ms = P.mem_slot.data() + L.mem_off;
+            int32_t *mf = P.mem_fam.data() + L.mem_off, *ml = P.mem_lrow.data() + L.mem_off;
             for (int32_t q = 0; q < nn; q++) {
-                const int32_t oq = order[q], x = X[oq];
-                const int32_t s = (size_t)q < take ? freelist[q] : next_fresh++;
-                slot_of[x] = s;
-                mi[q] = x; ms[q] = s; mf[q] = fam_of[oq];
+                const int32_t oq = order[q], x = X[oq], f = fam_of[oq];
+                const int32_t g = fam_own[f];
+                const int32_t s = slots.take(), lr = world > 1 ? rows[g].take() : s;   // one rank: row == slot
+                slot_of[x] = s; lrow_of[x] = lr; owner_of[x] = (int8_t)g;
+                mi[q] = x; ms[q] = s; mf[q] = newid[f]; ml[q] = lr;
             }
         }
-        freelist.erase(freelist.begin(), freelist.begin() + (ptrdiff_t)take);
-        for (int32_t f = 0; f < nf; f++) {
-            int32_t x = X[fam_first[f]];
-            P.fam_pf.push_back(father[x] >= 0 ? slot_of[father[x]] : -1);
-            P.fam_pm.push_back(mother[x] >= 0 ? slot_of[mother[x]] : -1);
+        P.fam_pf.resize(L.fam_off + (size_t)nf, -1); P.fam_pm.resize(L.fam_off + (size_t)nf, -1);
+        P.fam_pf_owner.resize(L.fam_off + (size_t)nf, -1); P.fam_pm_owner.resize(L.fam_off + (size_t)nf, -1);
+        P.fam_pf_lrow.resize(L.fam_off + (size_t)nf, -1); P.fam_pm_lrow.resize(L.fam_off + (size_t)nf, -1);
+        P.fam_minrank.resize(L.fam_off + (size_t)nf); P.fam_maxrank.resize(L.fam_off + (size_t)nf);
+        for (int32_t f = 0; f < nf_real; f++) {
+            const int32_t x = X[fam_first[f]], fa = father[x], mo = mother[x];
+            const size_t k = L.fam_off + (size_t)newid[f];
+            P.fam_pf[k] = fa >= 0 ? slot_of[fa] : -1;
+            P.fam_pm[k] = mo >= 0 ? slot_of[mo] : -1;
+            P.fam_pf_owner[k] = fa >= 0 ? owner_of[fa] : (int8_t)-1;
+            P.fam_pm_owner[k] = mo >= 0 ? owner_of[mo] : (int8_t)-1;
+            P.fam_pf_lrow[k] = fa >= 0 ? lrow_of[fa] : -1;
+            P.fam_pm_lrow[k] = mo >= 0 ? lrow_of[mo] : -1;
         }
         // V[F, G] ("a member of F is climbed first", compute.jl:130-138) is read only when some
         // member of F outranks some member of G; the kernels skip the rest by these ranges.
         {
             const int32_t *mi = P.mem_ind.data() + L.mem_off;
             for (int32_t f = 0; f < nf; f++) {
-                P.fam_minrank.push_back(mi[fstart[f]]);           // increasing with f
-                P.fam_maxrank.push_back(mi[fstart[f + 1] - 1]);
+                const bool empty = fstart[f + 1] == fstart[f];          // dummy couple: outranks nobody
+                P.fam_minrank[L.fam_off + f] = empty ? INT_MAX : mi[fstart[f]];   // increasing inside a rank's range
+                P.fam_maxrank[L.fam_off + f] = empty ? -1 : mi[fstart[f + 1] - 1];
             }
         }
-        // per member tile rank range (lets the intra kernel skip one orientation)
+        // per member tile rank range (lets the expand kernel skip one orientation)
         L.n_mtiles = (nn + kMTile - 1) / kMTile;
         for (int32_t mt = 0; mt < L.n_mtiles; mt++) {
             int32_t lo = INT_MAX, hi = -1;
@@ -250,19 +332,30 @@ int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t 
         P.row_updates += nn;
         P.rt_elems_max = std::max(P.rt_elems_max, (size_t)L.rt_rows * (size_t)L.nf_pad);
         P.v_elems_max = std::max(P.v_elems_max, (size_t)nf * (size_t)L.nf_pad);
+        for (int32_t g = 0; g < world; g++) {
+            const int32_t nfo = fbase[g + 1] - fbase[g];
+            P.rank_rt_elems[g] = std::max(P.rank_rt_elems[g], (size_t)L.rt_rows * (size_t)pad32(nfo));
+            P.rank_v_elems[g] = std::max(P.rank_v_elems[g], (size_t)std::max(nfo, 1) * (size_t)L.nf_pad);
+        }
 
-        // ---- after the step: evicted slots become reusable from the next layer on ----
-        if (!freed.empty()) {
-            std::vector<int32_t> merged(freelist.size() + freed.size());
-            std::merge(freelist.begin(), freelist.end(), freed.begin(), freed.end(), merged.begin());
-            freelist.swap(merged);
+        // ---- after the step: evicted slots / rows become reusable from the next layer on ----
+        slots.end_layer(freed);
+        for (int32_t g = 0; g < world && world > 1; g++) {
+            std::sort(freed_rows[g].begin(), freed_rows[g].end());
+            rows[g].end_layer(freed_rows[g]);
         }
         for (int32_t q = 0; q < nn; q++) next_live.push_back(X[q]);
         live.swap(next_live);
     }
-    P.capacity = round_up(std::max(next_fresh, 1), kPTile);
-    P.pro_slot.resize(P.pro_ind.size());
-    for (size_t u = 0; u < P.pro_ind.size(); u++) P.pro_slot[u] = slot_of[P.pro_ind[u]];
+    P.capacity = round_up(std::max(slots.next_fresh, 1), kPTile);
+    for (int32_t g = 0; g < world; g++) P.rows_cap[g] = world > 1 ? std::max(rows[g].next_fresh, 1) : P.capacity;
+    const size_t np = P.pro_ind.size();
+    P.pro_slot.resize(np); P.pro_owner.resize(np); P.pro_lrow.resize(np);
+    for (size_t u = 0; u < np; u++) {
+        P.pro_slot[u] = slot_of[P.pro_ind[u]];
+        P.pro_owner[u] = owner_of[P.pro_ind[u]];
+        P.pro_lrow[u] = lrow_of[P.pro_ind[u]];
+    }
     return GENLIB_OK;
 }
 

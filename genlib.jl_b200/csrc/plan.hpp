@@ -38,6 +38,7 @@ struct Layer {
     size_t fam_off = 0;               // into fam_pf / fam_pm; fam_start uses fam_off + layer index
     size_t flag_off = 0;              // into flags
     size_t mtile_off = 0;             // into mtile_* arrays
+    size_t base_off = 0;              // into fam_base / mem_base (world + 1 entries each)
     double alg_elems = 0;             // 4 n L + 3 n^2
 };
 
@@ -56,8 +57,24 @@ struct Plan {
     std::vector<int32_t> fam_minrank, fam_maxrank;     // rank range of a couple's members
     std::vector<int32_t> mtile_minrank, mtile_maxrank; // rank range of a member tile
     std::vector<int32_t> mtile_fam0, mtile_nfam;       // family range of a member tile
-    size_t v_elems_max = 0;           // max over layers of n_fam * nf_pad
+    size_t v_elems_max = 0;           // max over layers of n_fam * nf_pad (world == 1)
+    // ---- row sharding (world ranks; world == 1 puts everything on rank 0) ----
+    // Couples are numbered rank-major inside a layer: rank g owns couples
+    // [fam_base[g], fam_base[g+1]) and members [mem_base[g], mem_base[g+1]), and holds the
+    // full-width rows of those members at local row indices mem_lrow.
+    std::vector<int32_t> fam_base, mem_base;           // per layer, world + 1 entries
+    std::vector<int32_t> mem_lrow;                     // parallel to mem_ind
+    std::vector<int8_t> fam_pf_owner, fam_pm_owner;    // parallel to fam_pf (-1 = no such parent)
+    std::vector<int32_t> fam_pf_lrow, fam_pm_lrow;
+    std::vector<int8_t> live_owner;                    // parallel to flags
+    std::vector<int32_t> live_lrow;
+    std::vector<int8_t> pro_owner;
+    std::vector<int32_t> pro_lrow;
+    std::vector<int64_t> rows_cap;                     // per rank: local rows needed
+    std::vector<size_t> rank_rt_elems, rank_v_elems;   // per rank: max rt_rows*nfo_pad, max nf_own*nf_pad
 };
+
+inline int32_t pad32(int32_t x) { return ((x > 0 ? x : 1) + 31) / 32 * 32; }
 
 // Returns 0 or a GENLIB_E* status; `err` receives a message.
 int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t n_pro,

@@ -66,6 +66,33 @@ class Plan:
         out["live_flags"] = flags
         return out
 
+    def layer_shard(self, layer: int) -> dict:
+        """Row sharding of a layer: own couple/member ranges per rank, local rows, parents' homes."""
+        info = self.layer_info(layer)
+        n, nf, w = info["n_new"], info["n_fam"], self.world
+        out = {"fam_base": np.zeros(w + 1, np.int32), "mem_base": np.zeros(w + 1, np.int32),
+               "member_lrow": np.zeros(n, np.int32)}
+        out.update({k: np.zeros(nf, np.int32) for k in ("fam_father_owner", "fam_father_lrow",
+                                                        "fam_mother_owner", "fam_mother_lrow")})
+        check(lib().genlib_plan_layer_shard(self._h, layer, ptr(out["fam_base"]), ptr(out["mem_base"]),
+                                            ptr(out["member_lrow"]), ptr(out["fam_father_owner"]),
+                                            ptr(out["fam_father_lrow"]), ptr(out["fam_mother_owner"]),
+                                            ptr(out["fam_mother_lrow"])))
+        cap = max(self.capacity, 1)
+        out["live_owner"], out["live_lrow"] = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+        check(lib().genlib_plan_layer_live_rows(self._h, layer, ptr(out["live_owner"]), ptr(out["live_lrow"])))
+        return out
+
+    def rank_rows(self, rank: int) -> int:
+        return lib().genlib_plan_rank_rows(self._h, rank)
+
+    def proband_rows(self):
+        n = self.n_unique
+        owner, lrow = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        if n:
+            check(lib().genlib_plan_proband_rows(self._h, ptr(owner), ptr(lrow)))
+        return owner, lrow
+
     def proband_slots(self) -> np.ndarray:
         s = np.zeros(self.n_unique, np.int32)
         if self.n_unique:
@@ -82,14 +109,40 @@ class Plan:
 
 
 class Engine:
-    """Device state of one rank: frontier matrix, scratch, uploaded schedule."""
+    """Device state of one rank: frontier rows, scratch, uploaded schedule.
 
-    def __init__(self, plan: Plan, numerics="reference", device: int = -1):
+    rank=None: the whole problem on one GPU.  With a plan built for world > 1, pass this
+    process's rank; exchange `ipc_handle()` with the peers and `attach()` them before `run()`
+    (see `phi_distributed`)."""
+
+    def __init__(self, plan: Plan, numerics="reference", device: int = -1, rank: Optional[int] = None):
         self.plan = plan
         self.numerics = _lib.NUMERICS[numerics]
+        self.rank = 0 if rank is None else rank
         h = C.c_void_p()
-        check(lib().genlib_engine_create(plan._h, self.numerics, device, C.byref(h)))
+        if rank is None:
+            check(lib().genlib_engine_create(plan._h, self.numerics, device, C.byref(h)))
+        else:
+            check(lib().genlib_engine_create_dist(plan._h, self.numerics, device, rank, C.byref(h)))
         self._h = h
+
+    def ipc_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        check(lib().genlib_engine_ipc_export(self._h, buf))
+        return buf.raw
+
+    def attach(self, handles):
+        """handles: one 64-byte CUDA-IPC handle per rank, rank-major (this rank's own is ignored)."""
+        blob = b"".join(handles)
+        assert len(blob) == 64 * self.plan.world
+        check(lib().genlib_engine_ipc_attach(self._h, blob, 64))
+
+    def own_probands(self) -> np.ndarray:
+        n = lib().genlib_engine_own_probands(self._h, None)
+        idx = np.zeros(n, np.int32)
+        if n:
+            lib().genlib_engine_own_probands(self._h, ptr(idx))
+        return idx
 
     def close(self):
         h, self._h = getattr(self, "_h", None), None
@@ -115,11 +168,13 @@ class Engine:
         return info.as_dict()
 
     def fetch(self, out: Optional[np.ndarray] = None, dtype=np.float32) -> np.ndarray:
+        """Rows of this rank's probands (all of them on one GPU) x all probands."""
         n = self.plan.n_unique
+        rows = n if self.plan.world == 1 else lib().genlib_engine_own_probands(self._h, None)
         if out is None:
-            out = np.empty((n, n), dtype)
-        if out.shape != (n, n) or not out.flags.c_contiguous or out.dtype not in _lib.DTYPES:
-            raise ValueError("out must be a C-contiguous (n_unique, n_unique) float32/float64 array")
+            out = np.empty((rows, n), dtype)
+        if out.shape != (rows, n) or not out.flags.c_contiguous or out.dtype not in _lib.DTYPES:
+            raise ValueError("out must be a C-contiguous (own rows, n_unique) float32/float64 array")
         check(lib().genlib_engine_fetch(self._h, ptr(out), _lib.DTYPES[out.dtype]))
         return out
 
@@ -182,6 +237,50 @@ def phi(pedigree: Pedigree, probandIDs=None, *, verbose: bool = False, compute: 
         stats = eng.stats()
     finally:
         eng.close()
+    return (res, stats) if return_stats else res
+
+
+def phi_distributed(pedigree: Pedigree, probandIDs=None, *, numerics="reference", dtype=np.float32,
+                    device: Optional[int] = None, gather: bool = True, return_stats: bool = False):
+    """gen.phi on all ranks of a `torch.distributed` job (one process per GPU of one box).
+
+    Every rank builds the same plan, owns a share of the frontier rows, reads parent rows and
+    pushes couple-matrix rows through NVLink peer mappings.  Collective: call on every rank.
+    gather=True returns the full matrix on rank 0 (None elsewhere); gather=False returns
+    (own_proband_indices, own_rows) on every rank."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    IDs = pro(pedigree) if probandIDs is None else np.asarray(probandIDs, np.int64)
+    ranks = pedigree.rank_of(IDs)
+    plan = Plan(pedigree.father, pedigree.mother, ranks, world=world)
+    n = plan.n_unique
+    if n == 0:
+        res = np.zeros((0, 0), dtype)
+        return (res, {}) if return_stats else res
+    if device is None:
+        import os
+        device = int(os.environ.get("LOCAL_RANK", rank))
+    eng = Engine(plan, numerics=numerics, device=device, rank=rank)
+    try:
+        handles = [None] * world
+        dist.all_gather_object(handles, eng.ipc_handle())
+        eng.attach(handles)
+        dist.barrier()
+        eng.run()
+        own, rows = eng.own_probands(), eng.fetch(dtype=dtype)
+        stats = eng.stats()
+        dist.barrier()                      # nobody unmaps while a peer may still read
+    finally:
+        eng.close()
+    if not gather:
+        return ((own, rows), stats) if return_stats else (own, rows)
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object((own, rows), parts, dst=0)
+    res = None
+    if rank == 0:
+        res = np.empty((n, n), dtype)
+        for idx, blk in parts:
+            res[idx] = blk
     return (res, stats) if return_stats else res
 
 

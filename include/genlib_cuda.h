@@ -121,6 +121,19 @@ int64_t genlib_plan_device_bytes(const genlib_plan *plan, int numerics, int32_t 
 int genlib_plan_layer_arrays(const genlib_plan *plan, int32_t layer, int32_t *member_ind,
                              int32_t *member_slot, int32_t *member_fam, int32_t *fam_father_slot,
                              int32_t *fam_mother_slot, int32_t *member_owner);
+/* Row sharding of a layer (plans built with world > 1; world == 1 puts everything on rank 0):
+ * fam_base / mem_base have world + 1 entries (rank g owns couples [fam_base[g], fam_base[g+1])
+ * and members [mem_base[g], mem_base[g+1])); member_lrow is the local row of each member on
+ * its owner; the parents of each couple are given as (owner rank, local row), -1 = none. */
+int genlib_plan_layer_shard(const genlib_plan *plan, int32_t layer, int32_t *fam_base, int32_t *mem_base,
+                            int32_t *member_lrow, int32_t *fam_father_owner, int32_t *fam_father_lrow,
+                            int32_t *fam_mother_owner, int32_t *fam_mother_lrow);
+/* Owner rank and local row of whoever is live in each slot before the step (capacity entries). */
+int genlib_plan_layer_live_rows(const genlib_plan *plan, int32_t layer, int32_t *live_owner, int32_t *live_lrow);
+/* Local rows rank `rank` needs. */
+int64_t genlib_plan_rank_rows(const genlib_plan *plan, int32_t rank);
+int32_t genlib_plan_world(const genlib_plan *plan);
+int genlib_plan_proband_rows(const genlib_plan *plan, int32_t *owner, int32_t *lrow);
 /* live_flags: capacity bytes; bit0 = live before the step, bit1 = still live after it. */
 int genlib_plan_layer_flags(const genlib_plan *plan, int32_t layer, uint8_t *live_flags);
 int genlib_plan_proband_slots(const genlib_plan *plan, int32_t *slots);
@@ -142,8 +155,22 @@ void genlib_engine_destroy(genlib_engine *eng);
 int genlib_engine_run(genlib_engine *eng, int time_layers);
 int genlib_engine_layer_info(const genlib_engine *eng, int32_t layer, genlib_layer_info *out);
 int genlib_engine_stats(const genlib_engine *eng, genlib_stats *out);
-/* Gather proband rows/columns and stream them to host memory. */
+/* Gather proband rows/columns and stream them to host memory.  A sharded engine writes only
+ * the rows of the probands it owns, compactly: n_own x n_unique elements, in the order of
+ * genlib_engine_own_probands. */
 int genlib_engine_fetch(genlib_engine *eng, void *out, int out_dtype);
+/* Output rows (proband indices, ascending) held by this rank; returns their number. */
+int32_t genlib_engine_own_probands(const genlib_engine *eng, int32_t *index);
+
+/* ---- several GPUs of one box: one process (rank) per GPU, rows sharded ---------------------
+ * Every rank builds the SAME plan with world = N, creates its engine, exports the CUDA-IPC
+ * handle of its device arena (64 bytes), exchanges handles with its peers by any means and
+ * attaches them (rank-major array, `stride` bytes apart).  run / fetch are then collective:
+ * every rank must call them.  Kernels read parent rows and push couple-matrix rows directly
+ * through the NVLink peer mappings; ranks meet at in-stream barriers twice per layer. */
+int genlib_engine_create_dist(const genlib_plan *plan, int numerics, int device, int32_t rank, genlib_engine **out);
+int genlib_engine_ipc_export(genlib_engine *eng, void *handle64);
+int genlib_engine_ipc_attach(genlib_engine *eng, const void *handles, size_t stride);
 /* Mean off-diagonal kinship of the proband matrix, reduced on the device
  * (consumer of the path: phiMean, src/compute.jl:454-459). */
 int genlib_engine_phi_mean(genlib_engine *eng, double *out);
