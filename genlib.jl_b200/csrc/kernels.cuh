@@ -224,7 +224,7 @@ couple_kernel(int64_t ld, const double *__restrict__ Rt, T *__restrict__ Vt, T *
                 int o = 0;
                 while (o + 1 < L.world && F >= L.fam_base[o + 1]) o++;
                 T *vrow = static_cast<T *>(PT.Vrow[o]) + (size_t)(F - L.fam_base[o]) * L.nf_pad + L.own_f0;
-                store_vec4(vrow + gl, v);
+                if (gl < L.own_nf) store_vec4(vrow + gl, v);   // never into the next rank's couple columns
             }
         }
         if (lane == 0) s_skip[fl] = skip;

@@ -39,6 +39,12 @@ def main():
             print(f"[dist x{world}] {name}: {'ok' if ok else 'MISMATCH'} ({got.shape[0]}x{got.shape[0]})", flush=True)
             if not ok:
                 failures.append(name)
+                if got.shape[0] <= 29:
+                    np.set_printoptions(linewidth=250, precision=4)
+                    print("got\n", got, "\nwant\n", single, flush=True)
+                else:
+                    bad = np.argwhere(got != single)
+                    print("  mismatches", len(bad), "of", got.size, "first", bad[:5].tolist(), "rows affected", len(set(bad[:, 0])), "cols", len(set(bad[:, 1])), flush=True)
 
     ped = gen.genealogy(gen.geneaJi)
     check("geneaJi", ped, None, ob.OraclePedigree.from_csv(gen.geneaJi).phi() if rank == 0 else None)
