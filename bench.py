@@ -141,7 +141,7 @@ def run_reference(args, rank, world):
     ms = (time.time() - t0) * 1e3 / max(1, args.steps)
     v = float(np.mean(vals))
     last["value"] = v
-    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+    emit(({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
                       "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                       "config": {"workload": desc}, "cpu_baseline": last,
@@ -149,7 +149,27 @@ def run_reference(args, rank, world):
                       "gpu_launches": 0}))
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries (NCCL, torchrun banners) print to fd 1; the contract is ONE JSON line on stdout.
+    Everything written to fd 1 from here on goes to stderr; emit() writes the line to the real one."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -169,7 +189,7 @@ def main():
         return run_reference(args, rank, world)
     if world > 1:
         from bench_dist import main_dist          # sharded path (one rank per GPU)
-        return main_dist(args, rank, world, local)
+        return main_dist(args, rank, world, local, sys.modules[__name__])
 
     gen, ped, ranks, desc = build_workload(args)
     if gen.lib().genlib_device_count() < 1:
@@ -261,7 +281,7 @@ def main():
                        "host_wall_ms_per_step": wall_ms / K, "output_checksum": checksum},
             "roofline": roofline, "cpu_baseline": base, "e2e": e2e,
             "gpu_launches": int(stats["kernel_launches"]) * K, "clocks": clocks.summary()}
-    print(json.dumps(line))
+    emit(line)
 
 
 if __name__ == "__main__":

@@ -11,10 +11,11 @@ import time
 import numpy as np
 
 
-def main_dist(args, rank, world, local):
+def main_dist(args, rank, world, local, B):
     import torch
     import torch.distributed as dist
-    from bench import METRIC, UNIT, ClockSampler, build_workload, cpu_baseline, measured_peaks
+    METRIC, UNIT, ClockSampler, build_workload = B.METRIC, B.UNIT, B.ClockSampler, B.build_workload
+    cpu_baseline, emit, measured_peaks = B.cpu_baseline, B.emit, B.measured_peaks
 
     torch.cuda.set_device(local)
     dist.init_process_group("cpu:gloo,cuda:nccl")
@@ -137,6 +138,6 @@ def main_dist(args, rank, world, local):
                            "setup_s": setup_s, "host_wall_ms_per_step": wall_ms / K, "output_checksum": float(csum.item())},
                 "roofline": roofline, "cpu_baseline": base, "e2e": e2e, "gpu_launches": launches * K * world,
                 "clocks": clocks.summary()}
-        print(json.dumps(line))
+        emit(line)
     dist.barrier()
     dist.destroy_process_group()
