@@ -69,114 +69,138 @@ def replay(plan, numerics: str = "reference", check_poison: bool = True, on_laye
     return out
 
 
-def replay_sharded(plan, numerics: str = "reference", exchange=None) -> np.ndarray:
-    """Replay of the ROW-SHARDED schedule: every rank holds only the full-width rows of the
-    individuals it owns (A[g] is rows_cap[g] x W, NaN-poisoned).  Mirrors what the multi-GPU
-    kernels do: parent rows are read wherever they live, the couple matrix is computed in column
-    blocks (own couples) and pushed to the owner of each row couple, every rank expands its own
-    rows.  All ranks are simulated in this process; `exchange`, if given, is called as
-    exchange(layer, rank_from, rank_to, nbytes) for every remote access (traffic accounting).
+class ShardedReplay:
+    """Row-sharded schedule, rank by rank (NumPy, fp64 arithmetic in the kernels' grouping).
+
+    `ranks` = the ranks this object simulates (all of them by default).  A[g] is rank g's
+    rows_cap[g] x W frontier block, NaN where nothing was written.  Phases of one layer, in the
+    order the engine launches them: cross(g) -> apply_cross_writes -> couple(g) -> apply_pushes
+    -> expand(g).  Remote accesses go through self.A / self.push, so a multi-process test only
+    has to exchange those between phases.
     """
-    T = np.float32 if numerics == "reference" else np.float64
-    W, G = int(plan.capacity), plan.world
-    A = [np.full((max(plan.rank_rows(g), 1), W), np.nan, T) for g in range(G)]
-    es = np.dtype(T).itemsize
 
-    def note(layer, src, dst, nbytes):
-        if exchange is not None and src != dst and nbytes:
-            exchange(layer, int(src), int(dst), int(nbytes))
+    def __init__(self, plan, numerics="reference", exchange=None):
+        self.plan, self.T = plan, (np.float32 if numerics == "reference" else np.float64)
+        self.W, self.G = int(plan.capacity), plan.world
+        self.A = [np.full((max(plan.rank_rows(g), 1), self.W), np.nan, self.T) for g in range(self.G)]
+        self.es = np.dtype(self.T).itemsize
+        self.exchange = exchange
 
-    for t in range(plan.n_layers):
-        info, arr, sh = plan.layer_info(t), plan.layer_arrays(t), plan.layer_shard(t)
-        n, nf = info["n_new"], info["n_fam"]
-        if n == 0:
-            continue
-        slot, fam, ind, lrow = arr["member_slot"], arr["member_fam"], arr["member_ind"], sh["member_lrow"]
-        pf, pm = arr["fam_father_slot"], arr["fam_mother_slot"]
-        live = np.nonzero(arr["live_flags"] & 1)[0]
-        carried = np.nonzero(arr["live_flags"] & 2)[0]
+    def note(self, src, dst, nbytes):
+        if self.exchange is not None and src != dst and nbytes:
+            self.exchange(self.t, int(src), int(dst), int(nbytes))
+
+    def begin(self, t):
+        plan = self.plan
+        self.t = t
+        self.info, self.arr, self.sh = plan.layer_info(t), plan.layer_arrays(t), plan.layer_shard(t)
+        a, sh = self.arr, self.sh
+        self.n, self.nf = self.info["n_new"], self.info["n_fam"]
+        self.live = np.nonzero(a["live_flags"] & 1)[0]
+        self.carried = np.nonzero(a["live_flags"] & 2)[0]
+        self.pos_in_live = np.full(self.W, -1)
+        self.pos_in_live[self.live] = np.arange(len(self.live))
         fb, mb = sh["fam_base"], sh["mem_base"]
-        assert fb[0] == 0 and fb[-1] == nf and mb[-1] == n and np.all(np.diff(fam) >= 0)
-        pos_in_live = np.full(W, -1)
-        pos_in_live[live] = np.arange(len(live))
+        assert fb[0] == 0 and fb[-1] == self.nf and mb[-1] == self.n and np.all(np.diff(a["member_fam"]) >= 0)
+        self.owner_of_fam = np.repeat(np.arange(self.G), np.diff(fb))
+        self.Rt, self.writes, self.pushes = {}, [], []
+        self.Vrow = {g: np.full((fb[g + 1] - fb[g], self.nf), np.nan) for g in range(self.G)}
+        self.Vt = {g: np.full((fb[g + 1] - fb[g], self.nf), np.nan) for g in range(self.G)}
+        return self.n > 0
 
-        def row_of(owner, lr, cols, t=t, reader=None):
-            """Row (owner, lr) restricted to `cols` (fp64)."""
-            if reader is not None:
-                note(t, owner, reader, len(cols) * es)
-            return A[owner][lr, cols].astype(np.float64)
+    def row(self, owner, lr, cols, reader):
+        self.note(owner, reader, len(cols) * self.es)
+        return self.A[owner][lr, cols].astype(np.float64)
 
-        # ---- cross: each rank, own couples ----
-        Rt = [None] * G
-        for g in range(G):
-            F0, F1 = fb[g], fb[g + 1]
-            R = np.zeros((F1 - F0, len(live)))
-            for F in range(F0, F1):
-                acc = np.zeros(len(live))
-                for own, lr in ((sh["fam_father_owner"][F], sh["fam_father_lrow"][F]),
-                                (sh["fam_mother_owner"][F], sh["fam_mother_lrow"][F])):
-                    if own >= 0:
-                        acc = acc + 0.5 * row_of(own, lr, live, reader=g) if False else acc
-                # grouping must match: 0.5*father + 0.5*mother with one rounding
-                f_ok, m_ok = sh["fam_father_owner"][F] >= 0, sh["fam_mother_owner"][F] >= 0
-                x = row_of(sh["fam_father_owner"][F], sh["fam_father_lrow"][F], live, reader=g) if f_ok else 0.0
-                y = row_of(sh["fam_mother_owner"][F], sh["fam_mother_lrow"][F], live, reader=g) if m_ok else 0.0
-                R[F - F0] = 0.5 * x + 0.5 * y
-            if len(live):
-                assert not np.isnan(R).any(), f"layer {t} rank {g}: cross block read an unwritten entry"
-            Rt[g] = R                                        # [own couple][live position]
-        # rows/columns new x carried (all cross blocks are complete before anything is written)
-        writes = []
-        for g in range(G):
-            M0, M1 = mb[g], mb[g + 1]
-            if len(carried) and M1 > M0:
-                cpos = pos_in_live[carried]
-                blk = Rt[g][fam[M0:M1] - fb[g]][:, cpos].astype(T)          # (own members, carried)
-                writes.append((g, lrow[M0:M1], carried, blk))
-                for k, c in enumerate(carried):                              # mirror into the carried rows
-                    co, cl = sh["live_owner"][c], sh["live_lrow"][c]
-                    writes.append((co, np.array([cl]), slot[M0:M1], blk[:, k][None, :]))
-                    note(t, g, co, (M1 - M0) * es)
-        for g, rows_, cols_, blk in writes:
-            A[g][np.ix_(rows_, cols_)] = blk
-        # ---- couple: rank g computes V[F, G] for all F and its own G; pushes rows to owner(F) ----
-        Vrow = [np.full((fb[g + 1] - fb[g], nf), np.nan) for g in range(G)]   # V[F own, G]
-        Vt = [np.full((fb[g + 1] - fb[g], nf), np.nan) for g in range(G)]     # V[G, F own] stored [F own][G]
-        owner_of_fam = np.repeat(np.arange(G), np.diff(fb))
-        for g in range(G):
-            G0, G1 = fb[g], fb[g + 1]
-            if G1 == G0:
-                continue
-            Rg = Rt[g]                                       # [own couple G][live pos]
-            zero = np.zeros(G1 - G0)
-            for F in range(nf):
-                a = Rg[:, pos_in_live[pf[F]]] if pf[F] >= 0 else zero
-                b = Rg[:, pos_in_live[pm[F]]] if pm[F] >= 0 else zero
-                v = 0.5 * a + 0.5 * b                        # V[F, G0:G1]
-                o = owner_of_fam[F]
-                Vrow[o][F - fb[o], G0:G1] = v
-                Vt[g][:, F] = v
-                note(t, g, o, (G1 - G0) * es)
-        # ---- expand: every rank its own rows ----
-        for g in range(G):
-            M0, M1 = mb[g], mb[g + 1]
-            if M1 == M0:
-                continue
-            fl = fam[M0:M1] - fb[g]
-            a = Vrow[g][fl][:, fam]                          # V[F_i, G_j]
-            b = Vt[g][fl][:, fam]                            # V[G_j, F_i]
-            hi = ind[M0:M1, None] > ind[None, :]
-            blk = np.where(hi, a, b)
-            for q in range(M0, M1):                          # diagonal: 1/2 + 1/2 Psi[father, mother]
-                F = fam[q]
-                d = 0.5
-                if pf[F] >= 0 and pm[F] >= 0:
-                    d = 0.5 + 0.5 * float(row_of(sh["fam_father_owner"][F], sh["fam_father_lrow"][F], [pm[F]], reader=g)[0])
-                blk[q - M0, q] = d
-            assert not np.isnan(blk).any(), f"layer {t} rank {g}: expand read an unwritten couple entry"
-            A[g][np.ix_(lrow[M0:M1], slot)] = blk.astype(T)
-    ps = plan.proband_slots()
-    po, pl = plan.proband_rows()
-    out = np.stack([A[o][l, ps] for o, l in zip(po, pl)]) if len(ps) else np.zeros((0, 0), T)
+    def cross(self, g):
+        a, sh, live = self.arr, self.sh, self.live
+        F0, F1 = sh["fam_base"][g], sh["fam_base"][g + 1]
+        R = np.zeros((F1 - F0, len(live)))
+        for F in range(F0, F1):
+            fo, mo = sh["fam_father_owner"][F], sh["fam_mother_owner"][F]
+            x = self.row(fo, sh["fam_father_lrow"][F], live, g) if fo >= 0 else 0.0
+            y = self.row(mo, sh["fam_mother_lrow"][F], live, g) if mo >= 0 else 0.0
+            R[F - F0] = 0.5 * x + 0.5 * y                       # one rounding (1/2 y is exact)
+        if len(live):
+            assert not np.isnan(R).any(), f"layer {self.t} rank {g}: cross block read an unwritten entry"
+        self.Rt[g] = R
+        M0, M1 = sh["mem_base"][g], sh["mem_base"][g + 1]
+        if len(self.carried) and M1 > M0:                       # rows/columns new x carried, rounded once
+            blk = R[a["member_fam"][M0:M1] - F0][:, self.pos_in_live[self.carried]].astype(self.T)
+            self.writes.append((g, sh["member_lrow"][M0:M1], self.carried, blk))
+            for k, c in enumerate(self.carried):                # mirror into the carried rows (peer store)
+                co, cl = sh["live_owner"][c], sh["live_lrow"][c]
+                self.writes.append((co, np.array([cl]), a["member_slot"][M0:M1], blk[:, k][None, :]))
+                self.note(g, co, (M1 - M0) * self.es)
+
+    def apply_cross_writes(self, only=None):
+        for g, rows_, cols_, blk in self.writes:
+            if only is None or g in only:
+                self.A[g][np.ix_(rows_, cols_)] = blk
+
+    def couple(self, g):
+        a, sh = self.arr, self.sh
+        G0, G1 = sh["fam_base"][g], sh["fam_base"][g + 1]
+        if G1 == G0:
+            return
+        Rg, pf, pm = self.Rt[g], a["fam_father_slot"], a["fam_mother_slot"]
+        zero = np.zeros(G1 - G0)
+        for F in range(self.nf):
+            x = Rg[:, self.pos_in_live[pf[F]]] if pf[F] >= 0 else zero
+            y = Rg[:, self.pos_in_live[pm[F]]] if pm[F] >= 0 else zero
+            v = 0.5 * x + 0.5 * y                               # V[F, G0:G1]
+            o = self.owner_of_fam[F]
+            self.pushes.append((o, F - sh["fam_base"][o], G0, G1, v))
+            self.Vt[g][:, F] = v
+            self.note(g, o, (G1 - G0) * self.es)
+
+    def apply_pushes(self, only=None):
+        for o, fl, G0, G1, v in self.pushes:
+            if only is None or o in only:
+                self.Vrow[o][fl, G0:G1] = v
+
+    def expand(self, g):
+        a, sh = self.arr, self.sh
+        M0, M1 = sh["mem_base"][g], sh["mem_base"][g + 1]
+        if M1 == M0:
+            return
+        fam, ind, pf, pm = a["member_fam"], a["member_ind"], a["fam_father_slot"], a["fam_mother_slot"]
+        fl = fam[M0:M1] - sh["fam_base"][g]
+        blk = np.where(ind[M0:M1, None] > ind[None, :], self.Vrow[g][fl][:, fam], self.Vt[g][fl][:, fam])
+        for q in range(M0, M1):                                 # diagonal: 1/2 + 1/2 Psi[father, mother]
+            F, d = fam[q], 0.5
+            if pf[F] >= 0 and pm[F] >= 0:
+                d = 0.5 + 0.5 * float(self.row(sh["fam_father_owner"][F], sh["fam_father_lrow"][F], [pm[F]], g)[0])
+            blk[q - M0, q] = d
+        assert not np.isnan(blk).any(), f"layer {self.t} rank {g}: expand read an unwritten couple entry"
+        self.A[g][np.ix_(sh["member_lrow"][M0:M1], a["member_slot"])] = blk.astype(self.T)
+
+    def result_rows(self, g):
+        ps = self.plan.proband_slots()
+        po, pl = self.plan.proband_rows()
+        idx = np.nonzero(po == g)[0]
+        return idx, (np.stack([self.A[g][pl[u], ps] for u in idx]) if len(idx) else np.zeros((0, len(ps)), self.T))
+
+
+def replay_sharded(plan, numerics: str = "reference", exchange=None) -> np.ndarray:
+    """All ranks of the row-sharded schedule simulated in this process; `exchange(layer, src,
+    dst, nbytes)` is called for every remote access (traffic accounting)."""
+    R = ShardedReplay(plan, numerics, exchange)
+    for t in range(plan.n_layers):
+        if not R.begin(t):
+            continue
+        for g in range(R.G):
+            R.cross(g)
+        R.apply_cross_writes()
+        for g in range(R.G):
+            R.couple(g)
+        R.apply_pushes()
+        for g in range(R.G):
+            R.expand(g)
+    n = plan.n_unique
+    out = np.zeros((n, n), R.T)
+    for g in range(R.G):
+        idx, rows = R.result_rows(g)
+        out[idx] = rows
     assert not np.isnan(out).any()
     return out

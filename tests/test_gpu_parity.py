@@ -206,3 +206,20 @@ def test_full_size_properties(gen):
     for k, x in enumerate(sub):
         f, m = pos[int(s.father[x - 1])], pos[int(s.mother[x - 1])]
         assert abs(dd[k, k] - 0.5 * (1 + pp[f, m])) < 1e-12
+
+
+def test_multi_gpu_equals_single_gpu(gen):
+    """Row-sharded engine on every visible GPU (one rank per GPU under torchrun) == one GPU ==
+    oracle, bit for bit (tests/dist_check.py).  Needs >= 2 GPUs; the 1-GPU driver run skips it."""
+    import os
+    import subprocess
+    import sys
+    n = gen.lib().genlib_device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    n = 2 if n < 4 else (4 if n < 8 else 8)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "dist_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=1200)
+    assert res.returncode == 0 and "dist_check: all equal" in res.stdout, (res.stdout + res.stderr)[-3000:]
