@@ -76,9 +76,17 @@ public:
                 if (free_[i].device == device && free_[i].size >= bytes && (best < 0 || free_[i].size < free_[best].size)) best = i;
             if (best >= 0) { out = free_[best]; free_.erase(free_.begin() + best); return cudaSuccess; }
         }
-        release_device(device);                      // too small: give the memory back first
+        // Nothing cached fits.  Cached arenas may still be mapped by peer processes (CUDA IPC), and
+        // freeing exported memory under an open mapping is undefined, so they are only given back
+        // when the device is out of memory.
         out = Arena{nullptr, bytes, device};
-        return cudaMalloc(&out.base, bytes);
+        cudaError_t ce = cudaMalloc(&out.base, bytes);
+        if (ce == cudaErrorMemoryAllocation) {
+            cudaGetLastError();
+            release_device(device);
+            ce = cudaMalloc(&out.base, bytes);
+        }
+        return ce;
     }
     void release(Arena a) {
         if (!a.base) return;
@@ -98,6 +106,37 @@ public:
     }
 };
 ArenaCache g_arenas;
+
+// cudaIpcOpenMemHandle / CloseMemHandle of multi-GB arenas cost tens of milliseconds per peer.
+// Arenas are cached, so the same handles come back call after call: keep the mappings open.
+class PeerMapCache {
+    std::mutex mu_;
+    struct Entry { unsigned char handle[64]; int device; void *base; };
+    std::vector<Entry> open_;
+public:
+    cudaError_t map(int device, const void *handle64, void **base) {
+        std::lock_guard<std::mutex> g(mu_);
+        for (const Entry &en : open_)
+            if (en.device == device && std::memcmp(en.handle, handle64, 64) == 0) { *base = en.base; return cudaSuccess; }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, handle64, sizeof h);
+        cudaError_t ce = cudaIpcOpenMemHandle(base, h, cudaIpcMemLazyEnablePeerAccess);
+        if (ce != cudaSuccess) return ce;
+        Entry en; std::memcpy(en.handle, handle64, 64); en.device = device; en.base = *base;
+        open_.push_back(en);
+        return cudaSuccess;
+    }
+    void close_all() {
+        std::lock_guard<std::mutex> g(mu_);
+        for (const Entry &en : open_) {
+            int prev = -1; cudaGetDevice(&prev);
+            cudaSetDevice(en.device); cudaIpcCloseMemHandle(en.base);
+            if (prev >= 0) cudaSetDevice(prev);
+        }
+        open_.clear();
+    }
+};
+PeerMapCache g_peer_maps;
 
 // non-owning typed view into the arena
 template <typename T> struct DevBuf {
@@ -152,7 +191,6 @@ struct genlib_engine {
         for (auto e : events) cudaEventDestroy(e);
         if (stream) cudaStreamSynchronize(stream);
         if (copy_stream) cudaStreamSynchronize(copy_stream);
-        for (int g = 0; g < kMaxWorld; g++) if (peer_base[g]) cudaIpcCloseMemHandle(peer_base[g]);
         g_arenas.release(arena);
         if (stream) cudaStreamDestroy(stream);
         if (copy_stream) cudaStreamDestroy(copy_stream);
@@ -452,6 +490,7 @@ int genlib_device_count(void) {
 }
 
 int genlib_release_cache(void) {
+    g_peer_maps.close_all();
     g_arenas.release_device(-1);
     return GENLIB_OK;
 }
@@ -617,10 +656,8 @@ int genlib_engine_ipc_attach(genlib_engine *eng, const void *handles, size_t str
     const Plan &P = eng->plan->p;
     for (int g = 0; g < eng->world; g++) {
         if (g == eng->rank) continue;
-        cudaIpcMemHandle_t h;
-        std::memcpy(&h, static_cast<const unsigned char *>(handles) + (size_t)g * stride, sizeof h);
         void *base = nullptr;
-        cudaError_t ce = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+        cudaError_t ce = g_peer_maps.map(eng->device, static_cast<const unsigned char *>(handles) + (size_t)g * stride, &base);
         if (ce != cudaSuccess) {
             cudaGetLastError();
             return fail(GENLIB_ECOMM, std::string("cudaIpcOpenMemHandle(rank ") + std::to_string(g) + "): " + cudaGetErrorString(ce));
