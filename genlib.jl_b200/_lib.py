@@ -63,7 +63,7 @@ SYMBOLS = {
     "genlib_plan_layer_info": (C.c_int, [_P, C.c_int32, C.POINTER(LayerInfo)]),
     "genlib_plan_device_bytes": (C.c_int64, [_P, C.c_int, C.c_int32]),
     "genlib_plan_layer_arrays": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P]),
-    "genlib_plan_layer_shard": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P, _P]),
+    "genlib_plan_layer_shard": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "genlib_plan_layer_live_rows": (C.c_int, [_P, C.c_int32, _P, _P]),
     "genlib_plan_rank_rows": (C.c_int64, [_P, C.c_int32]),
     "genlib_plan_world": (C.c_int32, [_P]),

@@ -178,7 +178,8 @@ struct genlib_engine {
     unsigned epoch = 0;
     DevBuf<int32_t> mem_ind, mem_slot, mem_fam, mem_lrow, fam_pf, fam_pm, fam_pf_lrow, fam_pm_lrow, fam_start,
         fam_minrank, fam_maxrank, mt_min, mt_max, mt_fam0, mt_nfam, pro_slot, own_pro_row, live_lrow;
-    DevBuf<int8_t> fam_pf_owner, fam_pm_owner, live_owner;
+    DevBuf<int8_t> fam_pf_owner, fam_pm_owner, live_owner, mem_gowner;
+    DevBuf<int32_t> mem_glrow;
     DevBuf<uint8_t> flags;
     DevBuf<double> acc;
     std::vector<int32_t> own_pro;          // proband indices (output rows) this rank owns, ascending
@@ -216,7 +217,8 @@ size_t plan_index_bytes(const Plan &P) {
 // Arena layout of rank g.  The first three regions are what peers address (barrier flags,
 // frontier rows, row block of V), so their offsets must be computable by every rank.
 constexpr size_t kFlagBytes = 256;
-size_t a_bytes(const Plan &P, size_t es, int g) { return pad256((size_t)P.rows_cap[g] * (size_t)P.capacity * es); }
+size_t total_rows(const Plan &P, int g) { return (size_t)P.rows_cap[g] + 2 * (size_t)P.guest_cap[g]; }
+size_t a_bytes(const Plan &P, size_t es, int g) { return pad256(total_rows(P, g) * (size_t)P.capacity * es); }
 size_t v_bytes(const Plan &P, size_t es, int g) { return pad256(P.rank_v_elems[g] * es); }
 size_t off_A() { return kFlagBytes; }
 size_t off_Vrow(const Plan &P, size_t es, int g) { return kFlagBytes + a_bytes(P, es, g); }
@@ -231,6 +233,7 @@ size_t engine_bytes(const Plan &P, int numerics, int g) {
          DevBuf<int32_t>::padded(P.fam_start.size()) + 4 * DevBuf<int32_t>::padded(P.mtile_minrank.size()) +
          2 * DevBuf<int32_t>::padded(P.pro_slot.size()) + DevBuf<int32_t>::padded(P.live_lrow.size()) +
          2 * DevBuf<int8_t>::padded(P.fam_pf.size()) + DevBuf<int8_t>::padded(P.live_owner.size()) +
+         DevBuf<int8_t>::padded(P.mem_gowner.size()) + DevBuf<int32_t>::padded(P.mem_glrow.size()) +
          DevBuf<uint8_t>::padded(P.flags.size()) + DevBuf<double>::padded(2);
     return b;
 }
@@ -250,6 +253,7 @@ LayerArgs layer_args(const genlib_engine &E, int t) {
     a.nfo_pad = pad32(a.own_nf);
     a.mem_ind = E.mem_ind.p + L.mem_off; a.mem_slot = E.mem_slot.p + L.mem_off; a.mem_fam = E.mem_fam.p + L.mem_off;
     a.mem_lrow = E.mem_lrow.p + L.mem_off;
+    a.mem_gowner = E.mem_gowner.p + L.mem_off; a.mem_glrow = E.mem_glrow.p + L.mem_off;
     a.fam_pf = E.fam_pf.p + L.fam_off; a.fam_pm = E.fam_pm.p + L.fam_off;
     a.fam_pf_owner = E.fam_pf_owner.p + L.fam_off; a.fam_pm_owner = E.fam_pm_owner.p + L.fam_off;
     a.fam_pf_lrow = E.fam_pf_lrow.p + L.fam_off; a.fam_pm_lrow = E.fam_pm_lrow.p + L.fam_off;
@@ -284,7 +288,7 @@ int launch_layers(genlib_engine &E, bool timed) {
     for (const Layer &L : P.layers) max_tile_fam = std::max(max_tile_fam, L.max_tile_fam);
     const size_t expand_smem_max = (size_t)kEWarps * 2 * expand_stage_bytes<T>((max_tile_fam + vec - 1) / vec * vec + vec);
     if (expand_smem_max > 227 * 1024) return fail(GENLIB_EINVAL, "couple tile too wide for the expand kernel");
-    auto expand_fn = expand_kernel<T>;
+    auto expand_fn = E.world > 1 ? expand_kernel<T, true> : expand_kernel<T, false>;
     CU(cudaFuncSetAttribute(expand_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem_max));
     CU(cudaFuncSetAttribute(cross_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CU(cudaFuncSetAttribute(expand_fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -318,7 +322,7 @@ int launch_layers(genlib_engine &E, bool timed) {
             dim3 grid((unsigned)((L.n_mtiles + kEChunk - 1) / kEChunk), (unsigned)((a.own_nm + rows_per_cta - 1) / rows_per_cta));
             if (grid.y > 65535) return fail(GENLIB_EINVAL, "layer too wide for one expand launch");
             const size_t smem = (size_t)kEWarps * 2 * expand_stage_bytes<T>(a.vstride);
-            expand_fn<<<grid, kExpandThreads, smem, E.stream>>>(A, ld, V, Vt, Dg, a);
+            expand_fn<<<grid, kExpandThreads, smem, E.stream>>>(A, ld, V, Vt, Dg, E.peers, a);
             launches++;
         }
         launch_barrier(E);                 // all new rows exist everywhere before the next layer reads them
@@ -407,7 +411,7 @@ int create_engine(const genlib_plan *plan, int numerics, int device, int rank, g
         unsigned char *base = static_cast<unsigned char *>(E->arena.base), *cur = base;
         auto take = [&](size_t bytes) { unsigned char *p = cur; cur += pad256(bytes); return p; };
         E->bar_flags = reinterpret_cast<unsigned *>(take(kFlagBytes));
-        E->A = take((size_t)P.rows_cap[rank] * (size_t)P.capacity * E->esize);
+        E->A = take(total_rows(P, rank) * (size_t)P.capacity * E->esize);
         E->Vrow = take(P.rank_v_elems[rank] * E->esize);
         E->Vt = take(P.rank_v_elems[rank] * E->esize);
         E->Rt = reinterpret_cast<double *>(take(P.rank_rt_elems[rank] * sizeof(double)));
@@ -426,6 +430,7 @@ int create_engine(const genlib_plan *plan, int numerics, int device, int rank, g
         E->live_lrow.place(cur, P.live_lrow.size());
         E->fam_pf_owner.place(cur, P.fam_pf_owner.size()); E->fam_pm_owner.place(cur, P.fam_pm_owner.size());
         E->live_owner.place(cur, P.live_owner.size());
+        E->mem_gowner.place(cur, P.mem_gowner.size()); E->mem_glrow.place(cur, P.mem_glrow.size());
         E->flags.place(cur, P.flags.size()); E->acc.place(cur, 2);
         if ((size_t)(cur - base) > need) return fail(GENLIB_EINVAL, "internal: arena layout overflow");
         if ((size_t)(static_cast<unsigned char *>(E->A) - base) != off_A() ||
@@ -458,6 +463,8 @@ int create_engine(const genlib_plan *plan, int numerics, int device, int rank, g
     CU(E->own_pro_row.upload(own_rows, E->stream));
     CU(E->live_owner.upload(P.live_owner, E->stream));
     CU(E->live_lrow.upload(P.live_lrow, E->stream));
+    CU(E->mem_gowner.upload(P.mem_gowner, E->stream));
+    CU(E->mem_glrow.upload(P.mem_glrow, E->stream));
     CU(E->flags.upload(P.flags, E->stream));
     CU(cudaStreamSynchronize(E->stream));
     E->peers.A[rank] = E->A; E->peers.Vrow[rank] = E->Vrow; E->bars.flags[rank] = E->bar_flags;
@@ -569,7 +576,8 @@ int genlib_plan_layer_arrays(const genlib_plan *plan, int32_t layer, int32_t *me
 
 int genlib_plan_layer_shard(const genlib_plan *plan, int32_t layer, int32_t *fam_base, int32_t *mem_base,
                             int32_t *member_lrow, int32_t *fam_father_owner, int32_t *fam_father_lrow,
-                            int32_t *fam_mother_owner, int32_t *fam_mother_lrow) {
+                            int32_t *fam_mother_owner, int32_t *fam_mother_lrow, int32_t *member_guest_owner,
+                            int32_t *member_guest_lrow) {
     if (!plan || layer < 0 || layer >= (int32_t)plan->p.layers.size()) return fail(GENLIB_EINVAL, "bad layer");
     const Plan &P = plan->p;
     const Layer &L = P.layers[layer];
@@ -577,7 +585,11 @@ int genlib_plan_layer_shard(const genlib_plan *plan, int32_t layer, int32_t *fam
         if (fam_base) fam_base[g] = P.fam_base[L.base_off + g];
         if (mem_base) mem_base[g] = P.mem_base[L.base_off + g];
     }
-    for (int32_t q = 0; q < L.n_new; q++) if (member_lrow) member_lrow[q] = P.mem_lrow[L.mem_off + q];
+    for (int32_t q = 0; q < L.n_new; q++) {
+        if (member_lrow) member_lrow[q] = P.mem_lrow[L.mem_off + q];
+        if (member_guest_owner) member_guest_owner[q] = P.mem_gowner[L.mem_off + q];
+        if (member_guest_lrow) member_guest_lrow[q] = P.mem_glrow[L.mem_off + q];
+    }
     for (int32_t f = 0; f < L.n_fam; f++) {
         if (fam_father_owner) fam_father_owner[f] = P.fam_pf_owner[L.fam_off + f];
         if (fam_father_lrow) fam_father_lrow[f] = P.fam_pf_lrow[L.fam_off + f];
@@ -602,7 +614,7 @@ int genlib_plan_layer_live_rows(const genlib_plan *plan, int32_t layer, int32_t 
 
 int64_t genlib_plan_rank_rows(const genlib_plan *plan, int32_t rank) {
     if (!plan || rank < 0 || rank >= plan->p.world) return -1;
-    return plan->p.rows_cap.empty() ? 0 : plan->p.rows_cap[rank];
+    return plan->p.rows_cap.empty() ? 0 : (int64_t)total_rows(plan->p, rank);
 }
 
 int32_t genlib_plan_world(const genlib_plan *plan) { return plan ? plan->p.world : -1; }

@@ -44,8 +44,8 @@ struct LayerArgs {
     int32_t fam_base[kMaxWorld + 1];
     const int32_t *mem_ind, *mem_slot, *mem_fam, *mem_lrow;
     const int32_t *fam_pf, *fam_pm, *fam_start;
-    const int8_t *fam_pf_owner, *fam_pm_owner, *live_owner;
-    const int32_t *fam_pf_lrow, *fam_pm_lrow, *live_lrow;
+    const int8_t *fam_pf_owner, *fam_pm_owner, *live_owner, *mem_gowner;
+    const int32_t *fam_pf_lrow, *fam_pm_lrow, *live_lrow, *mem_glrow;
     const uint8_t *flags;
     const int32_t *fam_minrank, *fam_maxrank;
     const int32_t *mt_minrank, *mt_maxrank, *mt_fam0, *mt_nfam;
@@ -143,8 +143,11 @@ cross_kernel(T *__restrict__ A, int64_t ld, double *__restrict__ Rt, PeerTable P
             if (Fl < L.own_nf) {
                 const int F = L.own_f0 + Fl;
                 const int m1 = L.fam_start[F + 1];
-                for (int m = L.fam_start[F]; m < m1; m++)
+                for (int m = L.fam_start[F]; m < m1; m++) {
                     store4(A + (int64_t)L.mem_lrow[m] * ld + p0 + 4 * lane, r);
+                    const int go = L.mem_gowner[m];        // guest copy of the new row (multi-GPU)
+                    if (go >= 0) store4(static_cast<T *>(PT.A[go]) + (int64_t)L.mem_glrow[m] * ld + p0 + 4 * lane, r);
+                }
             }
         }
     }
@@ -289,11 +292,12 @@ __device__ __forceinline__ void cp_async16_s(unsigned smem, const void *gmem) {
 
 // One column step of one warp.  FAST: all kERows rows exist, the column tile is complete and the
 // lane's four column slots are consecutive and 16-byte aligned (one 128-bit store per row).
-template <typename T, bool FAST, bool DIAG>
+template <typename T, bool FAST, bool DIAG, bool GUESTS>
 __device__ __forceinline__ void expand_step(const unsigned (&go)[4], const int (&rj)[4], const int (&sj)[4],
                                             const unsigned (&roff)[kERows], const int (&rrank)[kERows],
-                                            T *const (&rptr)[kERows], unsigned vba_off, int nr, int ncol, int dk0,
-                                            const T *__restrict__ Dg, const int (&rfam)[kERows]) {
+                                            T *const (&rptr)[kERows], T *const (&gptr)[kERows], unsigned vba_off,
+                                            int nr, int ncol, int dk0, const T *__restrict__ Dg,
+                                            const int (&rfam)[kERows]) {
 #pragma unroll
     for (int r = 0; r < kERows; r++) {
         if (FAST || r < nr) {
@@ -311,14 +315,21 @@ __device__ __forceinline__ void expand_step(const unsigned (&go)[4], const int (
 #pragma unroll
                 for (int k = 0; k < 4; k++) if (k < ncol) rptr[r][sj[k]] = v[k];
             }
+            if (GUESTS && gptr[r]) {                       // the same row, into the guest copy on another GPU
+                if (FAST) store_vec4(gptr[r] + sj[0], v);
+                else {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) if (k < ncol) gptr[r][sj[k]] = v[k];
+                }
+            }
         }
     }
 }
 
-template <typename T>
+template <typename T, bool GUESTS>
 __global__ void __launch_bounds__(kExpandThreads)
 expand_kernel(T *__restrict__ A, int64_t ld, const T *__restrict__ V, const T *__restrict__ Vt,
-              const T *__restrict__ Dg, LayerArgs L) {
+              const T *__restrict__ Dg, PeerTable PT, LayerArgs L) {
     constexpr int kVec = 16 / sizeof(T);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -345,11 +356,22 @@ expand_kernel(T *__restrict__ A, int64_t ld, const T *__restrict__ V, const T *_
         maxI = max(maxI, __shfl_xor_sync(0xffffffffu, maxI, o));
     }
     minI = __shfl_sync(0xffffffffu, minI, 0); maxI = __shfl_sync(0xffffffffu, maxI, 0);
+    int mygo = -1, mygl = 0;
+    if (GUESTS) { mygo = L.mem_gowner[mrow]; mygl = L.mem_glrow[mrow]; }
     unsigned roff[kERows];
     int rrank[kERows], rfam[kERows];
-    T *rptr[kERows];
+    T *rptr[kERows], *gptr[kERows];
 #pragma unroll
     for (int r = 0; r < kERows; r++) {
+        gptr[r] = nullptr;
+        if (GUESTS) {
+            const int go = __shfl_sync(0xffffffffu, mygo, r), gl = __shfl_sync(0xffffffffu, mygl, r);
+            if (go >= 0 && r < nr) {
+                unsigned long long q = (unsigned long long)(static_cast<T *>(PT.A[go]) + (int64_t)gl * ld);
+                asm volatile("" : "+l"(q));
+                gptr[r] = reinterpret_cast<T *>(q);
+            }
+        }
         rfam[r] = __shfl_sync(0xffffffffu, myfam, r);
         roff[r] = (unsigned)(rfam[r] - f0) * row_bytes;
         rrank[r] = __shfl_sync(0xffffffffu, myrank, r);
@@ -428,10 +450,10 @@ expand_kernel(T *__restrict__ A, int64_t ld, const T *__restrict__ V, const T *_
             const int dk0 = row0 - j0;                     // the diagonal crosses this lane's columns?
             const bool diag_tile = (row0 / kMTile) == J || ((row0 + kERows - 1) / kMTile) == J;   // warp-uniform
             if (nr == kERows && vec) {
-                if (diag_tile) expand_step<T, true, true>(go, rj, sj, roff, rrank, rptr, vba_off, nr, ncol, dk0, Dg, rfam);
-                else expand_step<T, true, false>(go, rj, sj, roff, rrank, rptr, vba_off, nr, ncol, dk0, Dg, rfam);
+                if (diag_tile) expand_step<T, true, true, GUESTS>(go, rj, sj, roff, rrank, rptr, gptr, vba_off, nr, ncol, dk0, Dg, rfam);
+                else expand_step<T, true, false, GUESTS>(go, rj, sj, roff, rrank, rptr, gptr, vba_off, nr, ncol, dk0, Dg, rfam);
             } else {
-                expand_step<T, false, true>(go, rj, sj, roff, rrank, rptr, vba_off, nr, ncol, dk0, Dg, rfam);
+                expand_step<T, false, true, GUESTS>(go, rj, sj, roff, rrank, rptr, gptr, vba_off, nr, ncol, dk0, Dg, rfam);
             }
         }
         __syncwarp();                                      // stage free before it is refilled

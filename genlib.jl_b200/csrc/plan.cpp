@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <climits>
+#include <cstdlib>
 
 #include "../../include/genlib_cuda.h"
 
@@ -125,11 +126,21 @@ int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t 
     }
 
     if (world > 127) { err = "at most 127 ranks"; return GENLIB_EINVAL; }
+    const bool use_guests = [] { const char *s = std::getenv("GENLIB_NO_GUESTS"); return !(s && s[0] == '1'); }();
     P.layers.resize(S);
     P.mem_ind.reserve(lstart[S] + 4 * (size_t)S); P.mem_slot.reserve(lstart[S] + 4 * (size_t)S);
     P.mem_fam.reserve(lstart[S] + 4 * (size_t)S); P.mem_lrow.reserve(lstart[S] + 4 * (size_t)S);
     std::vector<int32_t> slot_of((size_t)n, -1), lrow_of((size_t)n, -1);
     std::vector<int8_t> owner_of((size_t)n, 0);
+    // guest copies: the row of an individual born in layer t-1 is ALSO written, while it is
+    // computed, into a spare row of the rank that owns a layer-t couple of which it is the
+    // remote parent; that couple's cross kernel then reads locally instead of through NVLink.
+    // Encoded until the end of planning: kGuestMark + parity * kGuestStride + index.
+    constexpr int32_t kGuestMark = 1 << 30, kGuestStride = 1 << 28;
+    std::vector<int32_t> born_layer((size_t)n, -1);
+    std::vector<size_t> mem_pos_of((size_t)n, 0);
+    std::vector<int32_t> guest_count((size_t)world, 0);
+    P.guest_cap.assign((size_t)world, 0);
     std::vector<int32_t> live, next_live;        // individuals live before the current step
     // lowest-free-first allocators: global column slots, and local rows per rank
     struct Alloc {
@@ -170,7 +181,10 @@ int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t 
         L.ref_probands = cut_size[t];
         L.ref_both = t > 0 ? both_size[t - 1] : 0;
         // member arrays of a layer start 16-byte aligned (the expand kernel copies them in 16-byte chunks)
-        while (P.mem_ind.size() % 4) { P.mem_ind.push_back(0); P.mem_slot.push_back(0); P.mem_fam.push_back(0); P.mem_lrow.push_back(0); }
+        while (P.mem_ind.size() % 4) {
+            P.mem_ind.push_back(0); P.mem_slot.push_back(0); P.mem_fam.push_back(0); P.mem_lrow.push_back(0);
+            P.mem_gowner.push_back(-1); P.mem_glrow.push_back(-1);
+        }
         L.mem_off = P.mem_ind.size();
         L.fam_off = P.fam_pf.size();
         L.flag_off = P.flags.size();
@@ -278,6 +292,7 @@ int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t 
         // ---- column slots (global) and local rows (per owner): lowest free first, then fresh ----
         P.mem_ind.resize(L.mem_off + (size_t)nn); P.mem_slot.resize(L.mem_off + (size_t)nn);
         P.mem_fam.resize(L.mem_off + (size_t)nn); P.mem_lrow.resize(L.mem_off + (size_t)nn);
+        P.mem_gowner.resize(L.mem_off + (size_t)nn, -1); P.mem_glrow.resize(L.mem_off + (size_t)nn, -1);
         {
             int32_t *mi = P.mem_ind.data() + L.mem_off, *ms = P.mem_slot.data() + L.mem_off;
             int32_t *mf = P.mem_fam.data() + L.mem_off, *ml = P.mem_lrow.data() + L.mem_off;
@@ -286,6 +301,7 @@ int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t 
                 const int32_t g = fam_own[f];
                 const int32_t s = slots.take(), lr = world > 1 ? rows[g].take() : s;   // one rank: row == slot
                 slot_of[x] = s; lrow_of[x] = lr; owner_of[x] = (int8_t)g;
+                born_layer[x] = t; mem_pos_of[x] = L.mem_off + (size_t)q;
                 mi[q] = x; ms[q] = s; mf[q] = newid[f]; ml[q] = lr;
             }
         }
@@ -293,16 +309,31 @@ int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t 
         P.fam_pf_owner.resize(L.fam_off + (size_t)nf, -1); P.fam_pm_owner.resize(L.fam_off + (size_t)nf, -1);
         P.fam_pf_lrow.resize(L.fam_off + (size_t)nf, -1); P.fam_pm_lrow.resize(L.fam_off + (size_t)nf, -1);
         P.fam_minrank.resize(L.fam_off + (size_t)nf); P.fam_maxrank.resize(L.fam_off + (size_t)nf);
+        std::fill(guest_count.begin(), guest_count.end(), 0);
         for (int32_t f = 0; f < nf_real; f++) {
             const int32_t x = X[fam_first[f]], fa = father[x], mo = mother[x];
             const size_t k = L.fam_off + (size_t)newid[f];
+            const int32_t g = fam_own[f];
             P.fam_pf[k] = fa >= 0 ? slot_of[fa] : -1;
             P.fam_pm[k] = mo >= 0 ? slot_of[mo] : -1;
-            P.fam_pf_owner[k] = fa >= 0 ? owner_of[fa] : (int8_t)-1;
-            P.fam_pm_owner[k] = mo >= 0 ? owner_of[mo] : (int8_t)-1;
-            P.fam_pf_lrow[k] = fa >= 0 ? lrow_of[fa] : -1;
-            P.fam_pm_lrow[k] = mo >= 0 ? lrow_of[mo] : -1;
+            int8_t *po[2] = {&P.fam_pf_owner[k], &P.fam_pm_owner[k]};
+            int32_t *pl[2] = {&P.fam_pf_lrow[k], &P.fam_pm_lrow[k]};
+            const int32_t par[2] = {fa, mo};
+            for (int s = 0; s < 2; s++) {
+                const int32_t p = par[s];
+                if (p < 0) { *po[s] = -1; *pl[s] = -1; continue; }
+                *po[s] = owner_of[p]; *pl[s] = lrow_of[p];
+                if (world > 1 && use_guests && owner_of[p] != g && born_layer[p] == t - 1) {
+                    const size_t mp = mem_pos_of[p];
+                    if (P.mem_gowner[mp] < 0) {                 // first remote consumer gets the copy
+                        P.mem_gowner[mp] = (int8_t)g;
+                        P.mem_glrow[mp] = kGuestMark + (t & 1) * kGuestStride + guest_count[g]++;
+                    }
+                    if (P.mem_gowner[mp] == g) { *po[s] = (int8_t)g; *pl[s] = P.mem_glrow[mp]; }
+                }
+            }
         }
+        for (int32_t g = 0; g < world; g++) P.guest_cap[g] = std::max(P.guest_cap[g], guest_count[g]);
         // V[F, G] ("a member of F is climbed first", compute.jl:130-138) is read only when some
         // member of F outranks some member of G; the kernels skip the rest by these ranges.
         {
@@ -349,6 +380,19 @@ int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t 
     }
     P.capacity = round_up(std::max(slots.next_fresh, 1), kPTile);
     for (int32_t g = 0; g < world; g++) P.rows_cap[g] = world > 1 ? std::max(rows[g].next_fresh, 1) : P.capacity;
+    // resolve the guest rows: they sit behind the home rows of their rank, two banks (layer parity)
+    auto resolve = [&](int32_t owner, int32_t &lr) {
+        if (lr >= kGuestMark) {
+            const int32_t v = lr - kGuestMark, par = v / kGuestStride, idx = v % kGuestStride;
+            lr = (int32_t)P.rows_cap[owner] + par * P.guest_cap[owner] + idx;
+        }
+    };
+    for (size_t k = 0; k < P.fam_pf_lrow.size(); k++) {
+        if (P.fam_pf_owner[k] >= 0) resolve(P.fam_pf_owner[k], P.fam_pf_lrow[k]);
+        if (P.fam_pm_owner[k] >= 0) resolve(P.fam_pm_owner[k], P.fam_pm_lrow[k]);
+    }
+    for (size_t k = 0; k < P.mem_glrow.size(); k++)
+        if (P.mem_gowner[k] >= 0) resolve(P.mem_gowner[k], P.mem_glrow[k]);
     const size_t np = P.pro_ind.size();
     P.pro_slot.resize(np); P.pro_owner.resize(np); P.pro_lrow.resize(np);
     for (size_t u = 0; u < np; u++) {

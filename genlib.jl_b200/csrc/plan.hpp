@@ -70,7 +70,10 @@ struct Plan {
     std::vector<int32_t> live_lrow;
     std::vector<int8_t> pro_owner;
     std::vector<int32_t> pro_lrow;
-    std::vector<int64_t> rows_cap;                     // per rank: local rows needed
+    std::vector<int8_t> mem_gowner;                    // parallel to mem_ind: rank holding a guest copy of the row (-1 none)
+    std::vector<int32_t> mem_glrow;                    //                      and its row there
+    std::vector<int64_t> rows_cap;                     // per rank: home rows
+    std::vector<int32_t> guest_cap;                    // per rank: guest rows per bank (two banks behind the home rows)
     std::vector<size_t> rank_rt_elems, rank_v_elems;   // per rank: max rt_rows*nfo_pad, max nf_own*nf_pad
 };
 

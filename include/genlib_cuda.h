@@ -124,10 +124,13 @@ int genlib_plan_layer_arrays(const genlib_plan *plan, int32_t layer, int32_t *me
 /* Row sharding of a layer (plans built with world > 1; world == 1 puts everything on rank 0):
  * fam_base / mem_base have world + 1 entries (rank g owns couples [fam_base[g], fam_base[g+1])
  * and members [mem_base[g], mem_base[g+1])); member_lrow is the local row of each member on
- * its owner; the parents of each couple are given as (owner rank, local row), -1 = none. */
+ * its owner; the parents of each couple are given as (rank, local row) of the copy to read,
+ * -1 = none; member_guest_* name the rank and row of the guest copy a member's row is also
+ * written to while it is computed (-1 = none). */
 int genlib_plan_layer_shard(const genlib_plan *plan, int32_t layer, int32_t *fam_base, int32_t *mem_base,
                             int32_t *member_lrow, int32_t *fam_father_owner, int32_t *fam_father_lrow,
-                            int32_t *fam_mother_owner, int32_t *fam_mother_lrow);
+                            int32_t *fam_mother_owner, int32_t *fam_mother_lrow, int32_t *member_guest_owner,
+                            int32_t *member_guest_lrow);
 /* Owner rank and local row of whoever is live in each slot before the step (capacity entries). */
 int genlib_plan_layer_live_rows(const genlib_plan *plan, int32_t layer, int32_t *live_owner, int32_t *live_lrow);
 /* Local rows rank `rank` needs. */

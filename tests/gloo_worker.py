@@ -66,6 +66,10 @@ def run(rank: int, world: int, port: int, out_path: str):
             R.apply_pushes(only={rank})
             sync_rows()                        # diagonal reads a parent row that may be remote
             R.expand(rank)
+            gw = [None] * world                # guest copies of new rows, pushed to the rank that needs them
+            dist.all_gather_object(gw, R.guest_writes)
+            R.guest_writes = [x for xs in gw for x in xs]
+            R.apply_guest_writes(only={rank})
             dist.barrier()
         parts = [None] * world
         dist.all_gather_object(parts, R.result_rows(rank))

@@ -128,6 +128,11 @@ class ShardedReplay:
         if len(self.carried) and M1 > M0:                       # rows/columns new x carried, rounded once
             blk = R[a["member_fam"][M0:M1] - F0][:, self.pos_in_live[self.carried]].astype(self.T)
             self.writes.append((g, sh["member_lrow"][M0:M1], self.carried, blk))
+            for k in range(M0, M1):                              # the same row segment into the guest copy
+                go = sh["member_guest_owner"][k]
+                if go >= 0:
+                    self.writes.append((go, np.array([sh["member_guest_lrow"][k]]), self.carried, blk[k - M0][None, :]))
+                    self.note(g, go, len(self.carried) * self.es)
             for k, c in enumerate(self.carried):                # mirror into the carried rows (peer store)
                 co, cl = sh["live_owner"][c], sh["live_lrow"][c]
                 self.writes.append((co, np.array([cl]), a["member_slot"][M0:M1], blk[:, k][None, :]))
@@ -174,6 +179,18 @@ class ShardedReplay:
             blk[q - M0, q] = d
         assert not np.isnan(blk).any(), f"layer {self.t} rank {g}: expand read an unwritten couple entry"
         self.A[g][np.ix_(sh["member_lrow"][M0:M1], a["member_slot"])] = blk.astype(self.T)
+        self.guest_writes = getattr(self, "guest_writes", [])
+        for q in range(M0, M1):                                 # guest copies on other ranks (peer stores)
+            go = sh["member_guest_owner"][q]
+            if go >= 0:
+                self.guest_writes.append((go, int(sh["member_guest_lrow"][q]), a["member_slot"], blk[q - M0].astype(self.T)))
+                self.note(g, go, self.n * self.es)
+
+    def apply_guest_writes(self, only=None):
+        for go, gl, cols, vals in getattr(self, "guest_writes", []):
+            if only is None or go in only:
+                self.A[go][gl, cols] = vals
+        self.guest_writes = []
 
     def result_rows(self, g):
         ps = self.plan.proband_slots()
@@ -197,6 +214,7 @@ def replay_sharded(plan, numerics: str = "reference", exchange=None) -> np.ndarr
         R.apply_pushes()
         for g in range(R.G):
             R.expand(g)
+        R.apply_guest_writes()
     n = plan.n_unique
     out = np.zeros((n, n), R.T)
     for g in range(R.G):

@@ -63,7 +63,11 @@ def test_shard_invariants(gen):
                 assert (int(o), int(r)) not in live_rows
                 live_rows.add((int(o), int(r)))
                 used[o].add(int(r))
-        assert [max(u) + 1 if u else 1 for u in used] == rows
+            # a guest copy lives on another rank, behind that rank's home rows
+            for o, go, gl in zip(arr["member_owner"], sh["member_guest_owner"], sh["member_guest_lrow"]):
+                assert go == -1 or (go != o and 0 <= gl < rows[go])
+        # home rows come first; the two banks of guest rows sit behind them
+        assert all((max(u) + 1 if u else 1) <= r for u, r in zip(used, rows))
         owner, lrow = plan.proband_rows()
         assert len(owner) == plan.n_unique and (owner >= 0).all() and (owner < world).all()
 
