@@ -103,7 +103,7 @@ class ShardedReplay:
         fb, mb = sh["fam_base"], sh["mem_base"]
         assert fb[0] == 0 and fb[-1] == self.nf and mb[-1] == self.n and np.all(np.diff(a["member_fam"]) >= 0)
         self.owner_of_fam = np.repeat(np.arange(self.G), np.diff(fb))
-        self.Rt, self.writes, self.pushes = {}, [], []
+        self.Rt, self.writes, self.pushes, self.guest_writes = {}, [], [], []
         self.Vrow = {g: np.full((fb[g + 1] - fb[g], self.nf), np.nan) for g in range(self.G)}
         self.Vt = {g: np.full((fb[g + 1] - fb[g], self.nf), np.nan) for g in range(self.G)}
         return self.n > 0
@@ -179,7 +179,6 @@ class ShardedReplay:
             blk[q - M0, q] = d
         assert not np.isnan(blk).any(), f"layer {self.t} rank {g}: expand read an unwritten couple entry"
         self.A[g][np.ix_(sh["member_lrow"][M0:M1], a["member_slot"])] = blk.astype(self.T)
-        self.guest_writes = getattr(self, "guest_writes", [])
         for q in range(M0, M1):                                 # guest copies on other ranks (peer stores)
             go = sh["member_guest_owner"][q]
             if go >= 0:
@@ -187,7 +186,7 @@ class ShardedReplay:
                 self.note(g, go, self.n * self.es)
 
     def apply_guest_writes(self, only=None):
-        for go, gl, cols, vals in getattr(self, "guest_writes", []):
+        for go, gl, cols, vals in self.guest_writes:
             if only is None or go in only:
                 self.A[go][gl, cols] = vals
         self.guest_writes = []
