@@ -44,7 +44,7 @@ def main_dist(args, rank, world, local, B):
     for _ in range(W):
         eng.run()
     K = args.steps
-    step_ms, cross_ms, couple_ms, expand_ms = [], [], [], []
+    step_ms, cross_ms, couple_ms, expand_ms, wait_ms = [], [], [], [], []
     with ClockSampler(local) as clocks:
         time.sleep(0.6)
         clocks.rows.clear()
@@ -56,12 +56,14 @@ def main_dist(args, rank, world, local, B):
             cross_ms.append([i["ms_cross"] for i in infos])
             couple_ms.append([i["ms_couple"] for i in infos])
             expand_ms.append([i["ms_expand"] for i in infos])
+            wait_ms.append([i["ms_wait"] for i in infos])
         torch.cuda.synchronize(); dist.barrier()
         wall_ms = (time.time() - t0) * 1e3
     step_ms = reduce_max(step_ms)                          # per step: slowest rank, device time
     cross_ms = reduce_max(np.array(cross_ms).ravel()).reshape(K, -1)
     couple_ms = reduce_max(np.array(couple_ms).ravel()).reshape(K, -1)
     expand_ms = reduce_max(np.array(expand_ms).ravel()).reshape(K, -1)
+    wait_ms = -reduce_max(-np.array(wait_ms).ravel()).reshape(K, -1)      # the rank that waited least
     stats = eng.stats()
     dev_bytes = reduce_max([float(stats["device_bytes"])])[0]
     total_ms = float(step_ms.sum())
@@ -85,13 +87,15 @@ def main_dist(args, rank, world, local, B):
                 "intra_kernels": {"achieved": intra_bytes.sum() * K / i_t / 1e9 if i_t > 0 else 0.0,
                                   "share_of_step": i_t / (total_ms * 1e-3),
                                   "couple_share": float(couple_ms.sum() / total_ms),
-                                  "expand_share": float(expand_ms.sum() / total_ms)},
+                                  "expand_share": float(expand_ms.sum() / total_ms),
+                                  "min_barrier_wait_share": float(wait_ms.sum() / total_ms)},
                 "whole_step": {"achieved": whole, "frac": whole / peak, "frac_of_8TBs_nominal": whole / (8000.0 * world)},
-                "note": "aggregate over ranks; per-kernel times are the slowest rank's (barrier waits included in couple/expand)"}
+                "note": "aggregate over ranks; per-kernel times are the slowest rank's for that kernel"}
     if args.layers_json and rank == 0:
         with open(args.layers_json, "w") as fh:
             json.dump([{**i, "ms_cross": float(cross_ms[:, t].mean()), "ms_couple": float(couple_ms[:, t].mean()),
-                        "ms_expand": float(expand_ms[:, t].mean())} for t, i in enumerate(infos)], fh, indent=1)
+                        "ms_expand": float(expand_ms[:, t].mean()), "ms_wait_min": float(wait_ms[:, t].mean())}
+                       for t, i in enumerate(infos)], fh, indent=1)
     launches = int(reduce_max([float(stats["kernel_launches"])])[0])
     dist.barrier()
     eng.close()

@@ -28,7 +28,7 @@ class LayerInfo(C.Structure):
     _fields_ = [("n_new", C.c_int32), ("n_fam", C.c_int32), ("live_before", C.c_int32),
                 ("carried", C.c_int32), ("ref_founders", C.c_int32), ("ref_probands", C.c_int32),
                 ("ref_both", C.c_int32), ("reserved", C.c_int32), ("alg_elems", C.c_double),
-                ("ms_cross", C.c_double), ("ms_couple", C.c_double), ("ms_expand", C.c_double)]
+                ("ms_cross", C.c_double), ("ms_couple", C.c_double), ("ms_expand", C.c_double), ("ms_wait", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}

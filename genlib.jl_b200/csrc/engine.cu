@@ -315,6 +315,7 @@ int launch_layers(genlib_engine &E, bool timed) {
             couple_kernel<T><<<grid, kThreads, couple_smem, E.stream>>>(ld, E.Rt, Vt, Dg, E.peers, a);
             launches++;
         }
+        if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
         launch_barrier(E);                 // every rank's row block of V is complete (peer stores landed)
         if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
         if (a.own_nm > 0) {
@@ -325,6 +326,7 @@ int launch_layers(genlib_engine &E, bool timed) {
             expand_fn<<<grid, kExpandThreads, smem, E.stream>>>(A, ld, V, Vt, Dg, E.peers, a);
             launches++;
         }
+        if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
         launch_barrier(E);                 // all new rows exist everywhere before the next layer reads them
         if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
     }
@@ -471,7 +473,7 @@ int create_engine(const genlib_plan *plan, int numerics, int device, int rank, g
     E->attached = P.world == 1;
     E->info.resize(P.layers.size());
     for (size_t t = 0; t < P.layers.size(); t++) fill_info(P.layers[t], &E->info[t]);
-    E->events.resize(P.layers.size() * 4 + 2);
+    E->events.resize(P.layers.size() * 6 + 2);
     for (auto &e : E->events) CU(cudaEventCreate(&e));
     genlib_stats &s = E->stats;
     s.n_unique = P.n_unique; s.n_layers = (int32_t)P.layers.size(); s.row_updates = P.row_updates;
@@ -720,12 +722,15 @@ int genlib_engine_run(genlib_engine *eng, int time_layers) {
         for (size_t t = 0; t < E.info.size(); t++) {
             if (E.info[t].n_new == 0) continue;
             if (E.layer_limit >= 0 && (int32_t)t >= E.layer_limit) break;
-            float a = 0, b = 0, c = 0;
+            float a = 0, b = 0, w1 = 0, c = 0, w2 = 0;
             CU(cudaEventElapsedTime(&a, E.events[ev], E.events[ev + 1]));
             CU(cudaEventElapsedTime(&b, E.events[ev + 1], E.events[ev + 2]));
-            CU(cudaEventElapsedTime(&c, E.events[ev + 2], E.events[ev + 3]));
-            ev += 4;
+            CU(cudaEventElapsedTime(&w1, E.events[ev + 2], E.events[ev + 3]));
+            CU(cudaEventElapsedTime(&c, E.events[ev + 3], E.events[ev + 4]));
+            CU(cudaEventElapsedTime(&w2, E.events[ev + 4], E.events[ev + 5]));
+            ev += 6;
             E.info[t].ms_cross = a; E.info[t].ms_couple = b; E.info[t].ms_expand = c;
+            E.info[t].ms_wait = w1 + w2;
         }
     }
     if (E.world > 1) {

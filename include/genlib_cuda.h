@@ -66,6 +66,7 @@ typedef struct genlib_layer_info {
     double ms_cross;      /* device time of cross_kernel (when timed)                    */
     double ms_couple;     /* ... of couple_kernel                                        */
     double ms_expand;     /* ... of expand_kernel                                        */
+    double ms_wait;       /* ... spent in the two inter-GPU barriers (multi-GPU)         */
 } genlib_layer_info;
 
 typedef struct genlib_stats {

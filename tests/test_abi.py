@@ -29,7 +29,7 @@ def test_header_and_library_agree(gen):
 
 def test_layer_info_struct_layout(gen):
     from genlib_jl_b200 import _lib
-    assert C.sizeof(_lib.LayerInfo) == 64 and C.sizeof(_lib.Stats) == 96
+    assert C.sizeof(_lib.LayerInfo) == 72 and C.sizeof(_lib.Stats) == 96
 
 
 def test_no_cpu_fallback(gen):
