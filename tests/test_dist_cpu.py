@@ -38,6 +38,19 @@ def test_sharded_replay_random(gen, ob, seed):
         assert sum(traffic) > 0                         # the shards do talk to each other
 
 
+@pytest.mark.parametrize("guests", ["0", "1"])
+def test_guest_rows_replay(gen, ob, guests, monkeypatch):
+    """GENLIB_GUESTS=1: a new row is also written to the rank that will read it as a remote parent."""
+    monkeypatch.setenv("GENLIB_GUESTS", guests)
+    s = gen.synth.generate(3000, 8, 120, alpha=0.05, demes=2, migration=0.1, overlap=2, seed=4)
+    ped = gen.genealogy(s.as_columns())
+    want = ob.OraclePedigree.from_arrays(s.ind, s.father, s.mother, s.sex).phi(s.probands)
+    plan = gen.Plan(ped.father, ped.mother, ped.rank_of(s.probands), world=4)
+    n_guest = sum(int((plan.layer_shard(t)["member_guest_owner"] >= 0).sum()) for t in range(plan.n_layers))
+    assert (n_guest > 0) == (guests == "1")
+    assert np.array_equal(replay_sharded(plan), want)
+
+
 def test_shard_invariants(gen):
     s = gen.synth.generate(6000, 10, 300, alpha=0.05, demes=2, migration=0.1, overlap=2, seed=3)
     ped = gen.genealogy(s.as_columns())
