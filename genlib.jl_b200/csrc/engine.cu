@@ -177,7 +177,7 @@ struct genlib_engine {
     void *peer_base[kMaxWorld] = {};       // cudaIpcOpenMemHandle mappings (to close)
     unsigned epoch = 0;
     DevBuf<int32_t> mem_ind, mem_slot, mem_fam, mem_lrow, fam_pf, fam_pm, fam_pf_lrow, fam_pm_lrow, fam_start,
-        fam_minrank, fam_maxrank, mt_min, mt_max, mt_fam0, mt_nfam, pro_slot, own_pro_row, live_lrow;
+        fam_minrank, fam_maxrank, mt_min, mt_max, mt_fam0, mt_nfam, mt_m0, mt_cnt, pro_slot, own_pro_row, live_lrow;
     DevBuf<int8_t> fam_pf_owner, fam_pm_owner, live_owner, mem_gowner;
     DevBuf<int32_t> mem_glrow;
     DevBuf<uint8_t> flags;
@@ -210,7 +210,7 @@ void fill_info(const Layer &L, genlib_layer_info *o) {
 size_t pad256(size_t b) { return (std::max<size_t>(b, 1) + 255) / 256 * 256; }
 
 size_t plan_index_bytes(const Plan &P) {
-    return (P.mem_ind.size() * 4 + P.fam_pf.size() * 6 + P.fam_start.size() + P.mtile_minrank.size() * 4 +
+    return (P.mem_ind.size() * 4 + P.fam_pf.size() * 6 + P.fam_start.size() + P.mtile_minrank.size() * 6 +
             P.pro_slot.size() * 2 + P.live_lrow.size()) * sizeof(int32_t) + P.fam_pf.size() * 2 + P.live_owner.size() + P.flags.size();
 }
 
@@ -230,7 +230,7 @@ size_t engine_bytes(const Plan &P, int numerics, int g) {
     b += pad256(P.fam_pf.size() * es);                                         // Dg
     b += 2 * pad256(kFetchStageBytes);                                         // proband staging
     b += 4 * DevBuf<int32_t>::padded(P.mem_ind.size()) + 6 * DevBuf<int32_t>::padded(P.fam_pf.size()) +
-         DevBuf<int32_t>::padded(P.fam_start.size()) + 4 * DevBuf<int32_t>::padded(P.mtile_minrank.size()) +
+         DevBuf<int32_t>::padded(P.fam_start.size()) + 6 * DevBuf<int32_t>::padded(P.mtile_minrank.size()) +
          2 * DevBuf<int32_t>::padded(P.pro_slot.size()) + DevBuf<int32_t>::padded(P.live_lrow.size()) +
          2 * DevBuf<int8_t>::padded(P.fam_pf.size()) + DevBuf<int8_t>::padded(P.live_owner.size()) +
          DevBuf<int8_t>::padded(P.mem_gowner.size()) + DevBuf<int32_t>::padded(P.mem_glrow.size()) +
@@ -263,6 +263,7 @@ LayerArgs layer_args(const genlib_engine &E, int t) {
     a.fam_minrank = E.fam_minrank.p + L.fam_off; a.fam_maxrank = E.fam_maxrank.p + L.fam_off;
     a.mt_minrank = E.mt_min.p + L.mtile_off; a.mt_maxrank = E.mt_max.p + L.mtile_off;
     a.mt_fam0 = E.mt_fam0.p + L.mtile_off; a.mt_nfam = E.mt_nfam.p + L.mtile_off;
+    a.mt_m0 = E.mt_m0.p + L.mtile_off; a.mt_cnt = E.mt_cnt.p + L.mtile_off;
     a.n_mtiles = L.n_mtiles;
     const int vec = 16 / (int)E.esize;
     a.vrows = kERows;
@@ -428,6 +429,7 @@ int create_engine(const genlib_plan *plan, int numerics, int device, int rank, g
         E->fam_start.place(cur, P.fam_start.size());
         E->mt_min.place(cur, P.mtile_minrank.size()); E->mt_max.place(cur, P.mtile_maxrank.size());
         E->mt_fam0.place(cur, P.mtile_fam0.size()); E->mt_nfam.place(cur, P.mtile_nfam.size());
+        E->mt_m0.place(cur, P.mtile_m0.size()); E->mt_cnt.place(cur, P.mtile_cnt.size());
         E->pro_slot.place(cur, P.pro_slot.size()); E->own_pro_row.place(cur, P.pro_slot.size());
         E->live_lrow.place(cur, P.live_lrow.size());
         E->fam_pf_owner.place(cur, P.fam_pf_owner.size()); E->fam_pm_owner.place(cur, P.fam_pm_owner.size());
@@ -461,6 +463,8 @@ int create_engine(const genlib_plan *plan, int numerics, int device, int rank, g
     CU(E->mt_max.upload(P.mtile_maxrank, E->stream));
     CU(E->mt_fam0.upload(P.mtile_fam0, E->stream));
     CU(E->mt_nfam.upload(P.mtile_nfam, E->stream));
+    CU(E->mt_m0.upload(P.mtile_m0, E->stream));
+    CU(E->mt_cnt.upload(P.mtile_cnt, E->stream));
     CU(E->pro_slot.upload(P.pro_slot, E->stream));
     CU(E->own_pro_row.upload(own_rows, E->stream));
     CU(E->live_owner.upload(P.live_owner, E->stream));

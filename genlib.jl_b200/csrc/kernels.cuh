@@ -48,7 +48,7 @@ struct LayerArgs {
     const int32_t *fam_pf_lrow, *fam_pm_lrow, *live_lrow, *mem_glrow;
     const uint8_t *flags;
     const int32_t *fam_minrank, *fam_maxrank;
-    const int32_t *mt_minrank, *mt_maxrank, *mt_fam0, *mt_nfam;
+    const int32_t *mt_minrank, *mt_maxrank, *mt_fam0, *mt_nfam, *mt_m0, *mt_cnt;
     int32_t n_mtiles;
     int32_t vrows, vstride;     // staged couple tile of expand_kernel: rows, row stride (elements)
 };
@@ -104,6 +104,12 @@ cross_kernel(T *__restrict__ A, int64_t ld, double *__restrict__ Rt, PeerTable P
     const int live_here = __syncthreads_or(myflag & kFlagLive);
     if (!live_here) return;                              // hole in a fragmented slot range
     const int carried_here = L.any_carried ? __syncthreads_or(myflag & kFlagCarried) : 0;
+    // per-column flags as bit masks in shared memory (read again after the tile barrier below)
+    __shared__ unsigned s_live[kPTile / 32], s_carr[kPTile / 32];
+    {
+        const unsigned lm = __ballot_sync(0xffffffffu, myflag & kFlagLive), cm = __ballot_sync(0xffffffffu, myflag & kFlagCarried);
+        if (lane == 0 && warp < kPTile / 32) { s_live[warp] = lm; s_carr[warp] = cm; }
+    }
 
     // ---- gather-average of the two parent rows (wherever they live: local HBM or a peer's,
     //      read through NVLink) ----
@@ -155,7 +161,7 @@ cross_kernel(T *__restrict__ A, int64_t ld, double *__restrict__ Rt, PeerTable P
 
     // ---- transposed, unrounded: Rt[p, F] for every live column p of the tile ----
     for (int pl = warp; pl < kPTile; pl += kThreads / 32) {
-        if (fl[pl] & kFlagLive)
+        if ((s_live[pl >> 5] >> (pl & 31)) & 1u)
             Rt[((size_t)pt * kPTile + pl) * L.nfo_pad + F0 + lane] = sR[lane * kSRStride + pl];
     }
     // ---- mirror: columns of the new members in the rows of carried individuals (a peer
@@ -165,7 +171,7 @@ cross_kernel(T *__restrict__ A, int64_t ld, double *__restrict__ Rt, PeerTable P
         const int Fe = L.own_f0 + min(F0 + kFTile, L.own_nf);
         const int m1 = L.fam_start[Fe];
         for (int pl = warp; pl < kPTile; pl += kThreads / 32) {
-            if (!(fl[pl] & kFlagCarried)) continue;
+            if (!((s_carr[pl >> 5] >> (pl & 31)) & 1u)) continue;
             const size_t r = (size_t)pt * kPTile + pl;
             T *row = static_cast<T *>(PT.A[L.live_owner[r]]) + (int64_t)L.live_lrow[r] * ld;
             for (int m = m0 + lane; m < m1; m += 32)
@@ -382,9 +388,10 @@ expand_kernel(T *__restrict__ A, int64_t ld, const T *__restrict__ V, const T *_
     // ---- the column steps of this CTA, one per lane: aligned first couple column, 16-byte chunks
     //      per couple row, which orientations can be selected at all ----
     const int Jbeg = blockIdx.x * kEChunk, Jend = min(L.n_mtiles, Jbeg + kEChunk);
-    int t_c0, t_info;
+    int t_c0, t_info, t_m0, t_cnt;
     {
         const int Jl = min(Jbeg + lane, L.n_mtiles - 1);
+        t_m0 = L.mt_m0[Jl]; t_cnt = L.mt_cnt[Jl];
         const int fJ0 = L.mt_fam0[Jl], nfJ = L.mt_nfam[Jl];
         t_c0 = fJ0 & ~(kVec - 1);
         const int nchunk = (fJ0 + nfJ - t_c0 + kVec - 1) / kVec;
@@ -408,10 +415,10 @@ expand_kernel(T *__restrict__ A, int64_t ld, const T *__restrict__ V, const T *_
                 if (info & 0x200) cp_async16_s(dst + vba_off, b);
             }
         }
-        // column metadata: 4 members per lane (clamped at the ragged end of the layer)
-        const int mJ0 = J * kMTile;
+        // column metadata: 4 members per lane (clamped at the ragged end of the tile)
+        const int mJ0 = __shfl_sync(0xffffffffu, t_m0, J - Jbeg), mJ1 = mJ0 + __shfl_sync(0xffffffffu, t_cnt, J - Jbeg);
         const unsigned mdst = stage + meta_off + 16u * (unsigned)lane;
-        if (mJ0 + 4 * lane + 3 < L.n_new) {
+        if (mJ0 + 4 * lane + 3 < mJ1) {
             cp_async16_s(mdst, msrc + mJ0);
             cp_async16_s(mdst + kMTile * 4u, msrc + mJ0 + mstride1);
             cp_async16_s(mdst + 2u * kMTile * 4u, msrc + mJ0 + mstride2);
@@ -419,7 +426,7 @@ expand_kernel(T *__restrict__ A, int64_t ld, const T *__restrict__ V, const T *_
             int32_t *metaJ = reinterpret_cast<int32_t *>(smem_raw + (stage + meta_off - (unsigned)__cvta_generic_to_shared(smem_raw)));
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const int m = min(mJ0 + 4 * lane + k, L.n_new - 1);
+                const int m = min(mJ0 + 4 * lane + k, mJ1 - 1);
                 cp_async<4>(metaJ + 4 * lane + k, L.mem_fam + m);
                 cp_async<4>(metaJ + kMTile + 4 * lane + k, L.mem_ind + m);
                 cp_async<4>(metaJ + 2 * kMTile + 4 * lane + k, L.mem_slot + m);
@@ -435,20 +442,21 @@ expand_kernel(T *__restrict__ A, int64_t ld, const T *__restrict__ V, const T *_
         else cp_async_wait<0>();
         __syncwarp();                                      // other lanes' copies are visible
         const unsigned stage = mine + (unsigned)buf * stage_bytes;
-        const int mJ0 = J * kMTile, j0 = mJ0 + 4 * lane;
+        const int mJ0 = __shfl_sync(0xffffffffu, t_m0, J - Jbeg), mJ1 = mJ0 + __shfl_sync(0xffffffffu, t_cnt, J - Jbeg);
+        const int j0 = mJ0 + 4 * lane;
         const int c0 = __shfl_sync(0xffffffffu, t_c0, J - Jbeg);
-        if (j0 < L.n_new) {
+        if (j0 < mJ1) {
             const int4 gj = lds_int4(stage + meta_off + 16u * lane);
             const int4 rj4 = lds_int4(stage + meta_off + kMTile * 4u + 16u * lane);
             const int4 sj4 = lds_int4(stage + meta_off + 2u * kMTile * 4u + 16u * lane);
             const unsigned go[4] = {stage + (unsigned)(gj.x - c0) * (unsigned)sizeof(T), stage + (unsigned)(gj.y - c0) * (unsigned)sizeof(T),
                                     stage + (unsigned)(gj.z - c0) * (unsigned)sizeof(T), stage + (unsigned)(gj.w - c0) * (unsigned)sizeof(T)};
             const int rj[4] = {rj4.x, rj4.y, rj4.z, rj4.w}, sj[4] = {sj4.x, sj4.y, sj4.z, sj4.w};
-            const int ncol = min(4, L.n_new - j0);
+            const int ncol = min(4, mJ1 - j0);
             const bool vec = ncol == 4 && ((sj[0] & 3) == 0) && sj[1] == sj[0] + 1 && sj[2] == sj[0] + 2 &&
                              sj[3] == sj[0] + 3;
             const int dk0 = row0 - j0;                     // the diagonal crosses this lane's columns?
-            const bool diag_tile = (row0 / kMTile) == J || ((row0 + kERows - 1) / kMTile) == J;   // warp-uniform
+            const bool diag_tile = row0 < mJ1 && row0 + kERows > mJ0;   // warp-uniform: the rows meet the columns
             if (nr == kERows && vec) {
                 if (diag_tile) expand_step<T, true, true, GUESTS>(go, rj, sj, roff, rrank, rptr, gptr, vba_off, nr, ncol, dk0, Dg, rfam);
                 else expand_step<T, true, false, GUESTS>(go, rj, sj, roff, rrank, rptr, gptr, vba_off, nr, ncol, dk0, Dg, rfam);

@@ -348,19 +348,26 @@ int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t 
                 P.fam_maxrank[L.fam_off + f] = empty ? -1 : mi[fstart[f + 1] - 1];
             }
         }
-        // per member tile rank range (lets the expand kernel skip one orientation)
-        L.n_mtiles = (nn + kMTile - 1) / kMTile;
-        for (int32_t mt = 0; mt < L.n_mtiles; mt++) {
+        // member tiles = the column steps of the expand kernel: at most kMTile members and at most
+        // kMaxTileFam couples (bounds the staged couple tile), starting at multiples of 4; per tile
+        // the rank range (lets the kernel skip one orientation) and the couple range
+        L.n_mtiles = 0;
+        for (int32_t q0 = 0; q0 < nn;) {
+            const int32_t *mf = P.mem_fam.data() + L.mem_off;
+            int32_t q1 = std::min(nn, q0 + kMTile);
+            while (q1 > q0 + 4 && mf[q1 - 1] - mf[q0] >= kMaxTileFam) q1 = std::max(q0 + 4, (q1 - 1) & ~3);
             int32_t lo = INT_MAX, hi = -1;
-            for (int32_t q = mt * kMTile; q < std::min(nn, (mt + 1) * kMTile); q++) {
+            for (int32_t q = q0; q < q1; q++) {
                 int32_t x = P.mem_ind[L.mem_off + q];
                 lo = std::min(lo, x); hi = std::max(hi, x);
             }
             P.mtile_minrank.push_back(lo); P.mtile_maxrank.push_back(hi);
-            const int32_t q0 = mt * kMTile, q1 = std::min(nn, (mt + 1) * kMTile) - 1;
-            const int32_t f0 = P.mem_fam[L.mem_off + q0], f1 = P.mem_fam[L.mem_off + q1];
+            const int32_t f0 = mf[q0], f1 = mf[q1 - 1];
             P.mtile_fam0.push_back(f0); P.mtile_nfam.push_back(f1 - f0 + 1);
+            P.mtile_m0.push_back(q0); P.mtile_cnt.push_back(q1 - q0);
             L.max_tile_fam = std::max(L.max_tile_fam, f1 - f0 + 1);
+            L.n_mtiles++;
+            q0 = q1;
         }
         L.alg_elems = 4.0 * nn * (double)L.live_before + 3.0 * (double)nn * nn;
         P.alg_elems += L.alg_elems;

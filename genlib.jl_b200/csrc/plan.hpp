@@ -22,6 +22,7 @@ constexpr int kPTile = 128;      // frontier columns per cross-kernel tile (and 
 constexpr int kFTile = 32;       // families per cross-kernel tile
 constexpr int kMTile = 128;      // member columns per expand step (4 per lane)
 constexpr int kMaxFamily = 32;   // sibships larger than this are split (bounds per-tile work)
+constexpr int kMaxTileFam = 64;  // couples per member tile (bounds the couple tile staged by the expand kernel)
 
 constexpr uint8_t kFlagLive = 1;     // slot holds an individual that is live before the step
 constexpr uint8_t kFlagCarried = 2;  // ... and stays live after it
@@ -56,7 +57,8 @@ struct Plan {
     std::vector<uint8_t> flags;
     std::vector<int32_t> fam_minrank, fam_maxrank;     // rank range of a couple's members
     std::vector<int32_t> mtile_minrank, mtile_maxrank; // rank range of a member tile
-    std::vector<int32_t> mtile_fam0, mtile_nfam;       // family range of a member tile
+    std::vector<int32_t> mtile_fam0, mtile_nfam;       // couple range of a member tile
+    std::vector<int32_t> mtile_m0, mtile_cnt;          // first member and size of a member tile
     size_t v_elems_max = 0;           // max over layers of n_fam * nf_pad (world == 1)
     // ---- row sharding (world ranks; world == 1 puts everything on rank 0) ----
     // Couples are numbered rank-major inside a layer: rank g owns couples
