@@ -54,6 +54,14 @@ SYMBOLS = {
     "genlib_release_cache": (C.c_int, []),
     "genlib_pinned_alloc": (C.c_int, [C.c_size_t, C.POINTER(_P)]),
     "genlib_pinned_free": (C.c_int, [_P]),
+    "genlib_genealogy_csv": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(_P)]),
+    "genlib_genealogy_arrays": (C.c_int, [C.c_int64, _P, _P, _P, _P, C.c_int, C.POINTER(_P)]),
+    "genlib_pedigree_destroy": (None, [_P]),
+    "genlib_pedigree_n": (C.c_int64, [_P]),
+    "genlib_pedigree_depth": (C.c_int32, [_P]),
+    "genlib_pedigree_arrays": (C.c_int, [_P, _P, _P, _P, _P]),
+    "genlib_pedigree_pro": (C.c_int64, [_P, _P]),
+    "genlib_pedigree_ranks": (C.c_int, [_P, C.c_int64, _P, _P]),
     "genlib_plan_create": (C.c_int, [C.c_int32, _P, _P, C.c_int32, _P, C.c_int32, C.POINTER(_P)]),
     "genlib_plan_destroy": (None, [_P]),
     "genlib_plan_n_unique": (C.c_int32, [_P]),
@@ -112,6 +120,10 @@ def check(status: int):
         msg = lib().genlib_last_error().decode(errors="replace")
         if status == EKEY:
             raise KeyError(msg)          # the reference raises KeyError (src/create.jl:70)
+        if status == EINVAL and ("duplicate" in msg or "malformed" in msg or "same length" in msg):
+            raise ValueError(msg)
+        if status == EINVAL and msg.startswith("cannot open"):
+            raise FileNotFoundError(msg)
         if status == ENOMEM:
             raise MemoryError(msg)
         raise GenlibError(status, msg)

@@ -27,6 +27,9 @@ namespace {
 thread_local std::string g_err;
 
 int fail(int code, const std::string &msg) { g_err = msg; return code; }
+}  // namespace
+int genlib::set_error(int code, const std::string &msg) { return fail(code, msg); }
+namespace {
 
 #define CU(call)                                                                              \
     do {                                                                                      \

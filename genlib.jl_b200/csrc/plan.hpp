@@ -81,6 +81,9 @@ struct Plan {
 
 inline int32_t pad32(int32_t x) { return ((x > 0 ? x : 1) + 31) / 32 * 32; }
 
+// Records `msg` as the calling thread's last error (genlib_last_error) and returns `code`.
+int set_error(int code, const std::string &msg);
+
 // Returns 0 or a GENLIB_E* status; `err` receives a message.
 int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t n_pro,
                const int32_t *proband, int32_t world, Plan &plan, std::string &err);

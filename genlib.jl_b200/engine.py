@@ -301,6 +301,27 @@ def phi_arrays(father, mother, proband_ranks, *, numerics="reference", dtype=np.
     return out, st.as_dict()
 
 
+def f(pedigree: Pedigree, IDs, *, device: int = -1) -> np.ndarray:
+    """gen.f(pedigree, IDs): inbreeding coefficients, Float32 (src/compute.jl:500-511).
+
+    The reference evaluates phi(father, mother) by the exponential pairwise recursion in Float64
+    and rounds once; here the parents of all requested individuals go through ONE sweep of the
+    engine with Float64 storage (exact while kinships fit 53 bits, i.e. up to ~26 generations)
+    and the result is rounded to Float32.  SURVEY.md 8(f) N3."""
+    IDs = np.asarray(IDs, np.int64)
+    ranks = pedigree.rank_of(IDs)
+    fa, mo = pedigree.father[ranks], pedigree.mother[ranks]
+    both = (fa >= 0) & (mo >= 0)
+    out = np.zeros(len(IDs), np.float32)
+    if both.any():
+        parents = np.unique(np.concatenate([fa[both], mo[both]]))
+        k = phi(pedigree, pedigree.ids[parents], numerics="fp64", dtype=np.float64, device=device)
+        pos = {int(r): i for i, r in enumerate(parents)}
+        idx = np.nonzero(both)[0]
+        out[idx] = [np.float32(k[pos[int(fa[i])], pos[int(mo[i])]]) for i in idx]
+    return out
+
+
 def phiMean(phi_matrix) -> np.float32:
     """gen.phiMean(::Matrix{Float32}) (src/compute.jl:454-459), host side."""
     m = np.asarray(phi_matrix, np.float32)

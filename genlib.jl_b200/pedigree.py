@@ -132,7 +132,9 @@ class Pedigree:
                 + np.bincount(self.mother[self.mother >= 0], minlength=n))
 
     def depth(self) -> int:
-        return int(_max_depth(self.father, self.mother).max()) if len(self.ids) else 0
+        if getattr(self, "_depth", None) is None:
+            self._depth = int(_max_depth(self.father, self.mother).max()) if len(self.ids) else 0
+        return self._depth
 
     def __repr__(self):  # src/create.jl:76-111 (counts only)
         n = len(self.ids)
@@ -161,56 +163,40 @@ def _max_depth(father: np.ndarray, mother: np.ndarray) -> np.ndarray:
     raise ValueError("pedigree contains a cycle")
 
 
-def _from_records(ind, fid, mid, sex, sort: bool) -> Pedigree:
-    ind = np.ascontiguousarray(ind, np.int64)
-    fid = np.ascontiguousarray(fid, np.int64)
-    mid = np.ascontiguousarray(mid, np.int64)
-    sex = np.ascontiguousarray(sex, np.int32)
-    n = len(ind)
-    if len(np.unique(ind)) != n:
-        raise ValueError("duplicate individual IDs")
-    order = np.argsort(ind, kind="stable")
-    sid = ind[order]
-
-    def file_index(p):
-        out = np.full(n, -1, np.int64)
-        known = p != 0                                  # 0 = unknown parent (create.jl:240-241)
-        if n == 0 or not known.any():
-            return out
-        pos = np.minimum(np.searchsorted(sid, p[known]), n - 1)
-        if (sid[pos] != p[known]).any():
-            raise KeyError(int(p[known][np.argmax(sid[pos] != p[known])]))
-        out[known] = order[pos]
-        return out
-
-    f, m = file_index(fid), file_index(mid)
-    if sort:
-        depth = _max_depth(f.astype(np.int64), m.astype(np.int64))
-        perm = np.argsort(depth, kind="stable")         # sortperm is stable (create.jl:220)
-    else:
-        perm = np.arange(n)
-    pos = np.empty(n, np.int64)
-    pos[perm] = np.arange(n)
-    fr = np.where(f[perm] >= 0, pos[np.maximum(f[perm], 0)], -1)
-    mr = np.where(m[perm] >= 0, pos[np.maximum(m[perm], 0)], -1)
-    r = np.arange(n)
-    if ((fr >= r) | (mr >= r)).any():                   # pedigree[father] not yet defined (create.jl:240)
-        bad = int(np.argmax((fr >= r) | (mr >= r)))
-        raise KeyError(int(ind[perm][bad]))
-    return Pedigree(ind[perm], fr, mr, sex[perm])
+def _from_handle(h) -> Pedigree:
+    from ._lib import check, lib, ptr
+    try:
+        n = lib().genlib_pedigree_n(h)
+        ids = np.zeros(n, np.int64)
+        father, mother, sex = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32)
+        check(lib().genlib_pedigree_arrays(h, ptr(ids), ptr(father), ptr(mother), ptr(sex)))
+        depth = lib().genlib_pedigree_depth(h)
+    finally:
+        lib().genlib_pedigree_destroy(h)
+    ped = Pedigree(ids, father, mother, sex)
+    ped._depth = int(depth)
+    return ped
 
 
 def genealogy(source, sort: bool = True) -> Pedigree:
-    """gen.genealogy: a path to a 4-column file (create.jl:161-189), a pandas DataFrame
-    with columns ind/father/mother/sex (create.jl:131-146), or a mapping of such arrays."""
+    """gen.genealogy: a path to a 4-column file (create.jl:161-189), a pandas DataFrame with
+    columns ind/father/mother/sex (create.jl:131-146), or a mapping of such arrays.  Parsing,
+    depth ordering and ranking run in the library's C++ loader (`genlib_genealogy_*`)."""
+    import ctypes as C
+    from ._lib import check, lib, ptr
+    h = C.c_void_p()
     if isinstance(source, (str, bytes)) or hasattr(source, "__fspath__"):
-        # first line skipped, whitespace-separated integers
-        data = np.loadtxt(source, dtype=np.int64, skiprows=1, ndmin=2)
-        if data.size == 0:
-            data = data.reshape(0, 4)
-        return _from_records(data[:, 0], data[:, 1], data[:, 2], data[:, 3], sort)
-    cols = {k: np.asarray(source[k]) for k in ("ind", "father", "mother", "sex")}
-    return _from_records(cols["ind"], cols["father"], cols["mother"], cols["sex"], sort)
+        path = source if isinstance(source, bytes) else str(source).encode()
+        check(lib().genlib_genealogy_csv(path, int(sort), C.byref(h)))
+        return _from_handle(h)
+    ind = np.ascontiguousarray(np.asarray(source["ind"]), np.int64)
+    fid = np.ascontiguousarray(np.asarray(source["father"]), np.int64)
+    mid = np.ascontiguousarray(np.asarray(source["mother"]), np.int64)
+    sex = np.ascontiguousarray(np.asarray(source["sex"]), np.int32)
+    if not (len(ind) == len(fid) == len(mid) == len(sex)):
+        raise ValueError("ind, father, mother and sex must have the same length")
+    check(lib().genlib_genealogy_arrays(len(ind), ptr(ind), ptr(fid), ptr(mid), ptr(sex), int(sort), C.byref(h)))
+    return _from_handle(h)
 
 
 def pro(pedigree: Pedigree) -> np.ndarray:

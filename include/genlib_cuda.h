@@ -101,6 +101,26 @@ int genlib_release_cache(void);
 int genlib_pinned_alloc(size_t bytes, void **out);
 int genlib_pinned_free(void *ptr);
 
+/* ---- input side (host only): the `gen.genealogy` ordering on flat arrays --------------------
+ * Replaces genealogy(::String) / genealogy(::DataFrame), src/create.jl:131-189, with the stable
+ * depth ordering of :196-227 and the rank assignment of :234-254 (5 M-row
+ * files must not become the bottleneck).  IDs are arbitrary non-zero integers, 0 = unknown
+ * parent; `sort = 0` keeps the file order and requires parents to come first (KeyError else). */
+typedef struct genlib_pedigree genlib_pedigree;
+int genlib_genealogy_csv(const char *path, int sort, genlib_pedigree **out);
+int genlib_genealogy_arrays(int64_t n, const int64_t *ind, const int64_t *father, const int64_t *mother,
+                            const int32_t *sex /* may be NULL */, int sort, genlib_pedigree **out);
+void genlib_pedigree_destroy(genlib_pedigree *ped);
+int64_t genlib_pedigree_n(const genlib_pedigree *ped);
+/* Number of generations (gen.depth, src/describe.jl:60-66 = largest _max_depth). */
+int32_t genlib_pedigree_depth(const genlib_pedigree *ped);
+/* Rank-ordered view: IDs, 0-based parent ranks (-1 = none), sex.  Any pointer may be NULL. */
+int genlib_pedigree_arrays(const genlib_pedigree *ped, int64_t *ids, int32_t *father, int32_t *mother, int32_t *sex);
+/* gen.pro (src/identify.jl:35-39): IDs without children, ascending; returns the count. */
+int64_t genlib_pedigree_pro(const genlib_pedigree *ped, int64_t *out);
+/* IDs -> 0-based ranks; GENLIB_EKEY (Julia's KeyError) on an unknown ID. */
+int genlib_pedigree_ranks(const genlib_pedigree *ped, int64_t n, const int64_t *ids, int32_t *ranks);
+
 /* ---- planning (host only): levels, Kirkpatrick frontier, slots -------------
  * Replaces src/compute.jl:236-251 (cut vertices), :165-186 (_index_pedigree)
  * and :287-289 (founder_index).  `world` > 1 prepares the row-sharded schedule

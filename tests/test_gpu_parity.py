@@ -223,3 +223,15 @@ def test_multi_gpu_equals_single_gpu(gen):
            "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "dist_check.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=1200)
     assert res.returncode == 0 and "dist_check: all equal" in res.stdout, (res.stdout + res.stderr)[-3000:]
+
+
+def test_inbreeding_f(gen, ob):
+    """gen.f (src/compute.jl:500-511) from one engine sweep; known answers of test/runtests.jl:47-48."""
+    ped = gen.genealogy(gen.geneaJi)
+    assert gen.f(ped, [1]).tolist() == [0.18359375] and gen.f(ped, [17]).tolist() == [0.0]
+    got = gen.f(ped, ped.ids)
+    o = ob.OraclePedigree.from_csv(gen.geneaJi)
+    for ID, v in zip(ped.ids, got):
+        x = ped[int(ID)]
+        want = 0.0 if x.father is None or x.mother is None else o.phi_pair(x.father.ID, x.mother.ID)
+        assert v == np.float32(want)

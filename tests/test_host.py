@@ -151,3 +151,43 @@ def test_synth_is_deterministic(gen):
     assert (a.father[a.generation > 0] > 0).all() and (a.father < a.ind).all()
     c = gen.synth.generate(5000, 10, 100, alpha=0.02, demes=3, migration=0.05, overlap=2, seed=10)
     assert not np.array_equal(a.father, c.father)
+
+
+def test_loader_edge_cases(gen, tmp_path):
+    """C++ loader (`genlib_genealogy_csv/arrays`): file format of create.jl:161-189 and its errors."""
+    p = tmp_path / "ped.asc"
+    p.write_text("ind\tfather\tmother\tsex\r\n3 1 2 1\r\n\n1\t0\t0\t1\n2   0 0   2\n4 3 0 2")       # CRLF, blanks, no final newline
+    ped = gen.genealogy(str(p))
+    assert ped.ids.tolist() == [1, 2, 3, 4] and ped.father.tolist() == [-1, -1, 0, 2] and ped.mother.tolist() == [-1, -1, 1, -1]
+    assert gen.pro(ped).tolist() == [4] and ped[4].father.ID == 3 and ped[4].mother is None
+    with pytest.raises(KeyError):
+        gen.genealogy(str(p), sort=False)                       # child before its parents (create.jl:240)
+    with pytest.raises(KeyError):
+        gen.genealogy({"ind": [1, 2], "father": [0, 7], "mother": [0, 0], "sex": [1, 1]})   # unknown parent
+    with pytest.raises(ValueError):
+        gen.genealogy({"ind": [1, 1], "father": [0, 0], "mother": [0, 0], "sex": [1, 1]})   # duplicate ID
+    with pytest.raises(gen.GenlibError):
+        gen.genealogy({"ind": [1, 2], "father": [2, 1], "mother": [0, 0], "sex": [1, 1]})   # cycle
+    with pytest.raises(FileNotFoundError):
+        gen.genealogy(str(tmp_path / "missing.asc"))
+    (tmp_path / "bad.asc").write_text("h\n1 0 0\n")
+    with pytest.raises(ValueError):
+        gen.genealogy(str(tmp_path / "bad.asc"))
+    empty = gen.genealogy({"ind": [], "father": [], "mother": [], "sex": []})
+    assert len(empty) == 0 and gen.pro(empty).tolist() == []
+
+
+def test_loader_file_equals_columns_and_oracle(gen, ob, tmp_path):
+    s = gen.synth.generate(30000, 12, 500, alpha=0.05, demes=3, migration=0.1, overlap=3, seed=21)
+    path = str(tmp_path / "synth.asc")
+    s.to_csv(path)
+    a, b = gen.genealogy(path), gen.genealogy(s.as_columns())
+    o = ob.OraclePedigree.from_csv(path)
+    for x in (a, b):
+        assert np.array_equal(x.ids, o.ids) and np.array_equal(x.father, o.father) and np.array_equal(x.mother, o.mother)
+        assert np.array_equal(x.sex, o.sex)
+    assert np.array_equal(gen.pro(a), o.pro())
+    # a deep chain must not overflow any stack (the reference recurses, create.jl:196-209)
+    n = 200000
+    chain = gen.genealogy({"ind": np.arange(1, n + 1), "father": np.arange(0, n), "mother": np.zeros(n, int), "sex": np.ones(n, int)})
+    assert chain.ids[0] == 1 and chain.ids[-1] == n and chain.depth() == n
