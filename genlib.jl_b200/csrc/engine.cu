@@ -312,6 +312,11 @@ int launch_layers(genlib_engine &E, bool timed) {
             dim3 grid((unsigned)(L.rt_rows / kPTile), (unsigned)((a.own_nf + kFTile - 1) / kFTile));
             cross_kernel<T><<<grid, kThreads, cross_smem, E.stream>>>(A, ld, E.Rt, E.peers, a);
             launches++;
+            if (L.carried > 0 && a.own_nm > 0) {
+                dim3 mgrid((unsigned)((a.own_nm + 32 * kMirrorCols - 1) / (32 * kMirrorCols)), (unsigned)((L.rt_rows + kThreads / 32 - 1) / (kThreads / 32)));
+                mirror_kernel<T><<<mgrid, kThreads, 0, E.stream>>>(E.Rt, ld, E.peers, a);
+                launches++;
+            }
         }
         if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
         if (a.own_nf > 0) {

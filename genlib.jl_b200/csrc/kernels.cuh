@@ -7,8 +7,9 @@
 //
 //   cross_kernel  R[F, p] = 1/2 Psi[f_F, p] + 1/2 Psi[m_F, p]        (compute.jl:111-126)
 //                 for every couple F of the layer and every live column p; written
-//                   - rounded, as the rows/columns (new member x carried individual), and
+//                   - rounded, as the rows (new member x carried individual), and
 //                   - unrounded fp64, transposed, into the scratch block Rt[p, F].
+//   mirror_kernel the same values as the columns of the new members in the carried rows.
 //   couple_kernel V[F, G] = 1/2 Rt[f_F, G] + 1/2 Rt[m_F, G]         (compute.jl:130-147)
 //                 = the kinship of a member of F with a member of G when the F member has
 //                 the larger rank (it is "climbed first"); plus the diagonal value
@@ -105,10 +106,10 @@ cross_kernel(T *__restrict__ A, int64_t ld, double *__restrict__ Rt, PeerTable P
     if (!live_here) return;                              // hole in a fragmented slot range
     const int carried_here = L.any_carried ? __syncthreads_or(myflag & kFlagCarried) : 0;
     // per-column flags as bit masks in shared memory (read again after the tile barrier below)
-    __shared__ unsigned s_live[kPTile / 32], s_carr[kPTile / 32];
+    __shared__ unsigned s_live[kPTile / 32];
     {
-        const unsigned lm = __ballot_sync(0xffffffffu, myflag & kFlagLive), cm = __ballot_sync(0xffffffffu, myflag & kFlagCarried);
-        if (lane == 0 && warp < kPTile / 32) { s_live[warp] = lm; s_carr[warp] = cm; }
+        const unsigned lm = __ballot_sync(0xffffffffu, myflag & kFlagLive);
+        if (lane == 0 && warp < kPTile / 32) s_live[warp] = lm;
     }
 
     // ---- gather-average of the two parent rows (wherever they live: local HBM or a peer's,
@@ -164,19 +165,30 @@ cross_kernel(T *__restrict__ A, int64_t ld, double *__restrict__ Rt, PeerTable P
         if ((s_live[pl >> 5] >> (pl & 31)) & 1u)
             Rt[((size_t)pt * kPTile + pl) * L.nfo_pad + F0 + lane] = sR[lane * kSRStride + pl];
     }
-    // ---- mirror: columns of the new members in the rows of carried individuals (a peer
-    //      store when the carried row lives on another GPU) ----
-    if (carried_here) {
-        const int m0 = L.fam_start[L.own_f0 + F0];
-        const int Fe = L.own_f0 + min(F0 + kFTile, L.own_nf);
-        const int m1 = L.fam_start[Fe];
-        for (int pl = warp; pl < kPTile; pl += kThreads / 32) {
-            if (!((s_carr[pl >> 5] >> (pl & 31)) & 1u)) continue;
-            const size_t r = (size_t)pt * kPTile + pl;
-            T *row = static_cast<T *>(PT.A[L.live_owner[r]]) + (int64_t)L.live_lrow[r] * ld;
-            for (int m = m0 + lane; m < m1; m += 32)
-                row[L.mem_slot[m]] = (T)sR[(L.mem_fam[m] - L.own_f0 - F0) * kSRStride + pl];
-        }
+}
+
+// =====================================================================================
+// mirror_kernel: the columns of the new members in the rows of the CARRIED individuals,
+// Psi[c, i] = RN(R[F_i, c]) (compute.jl:119-126 by symmetry).  One warp per carried row: it reads
+// that row of the transposed cross block Rt[c, own couples] (contiguous) and writes the members'
+// columns (contiguous slots) -- a peer store when the carried row lives on another GPU.
+// grid (member chunks of 32 x kMirrorCols, live rows / 8).
+// =====================================================================================
+constexpr int kMirrorCols = 8;     // members per lane and CTA column chunk
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+mirror_kernel(const double *__restrict__ Rt, int64_t ld, PeerTable PT, LayerArgs L) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.y * (kThreads / 32) + warp;          // row of the live slot range
+    if (r >= L.rt_rows || !(L.flags[r] & kFlagCarried)) return;
+    T *row = static_cast<T *>(PT.A[L.live_owner[r]]) + (int64_t)L.live_lrow[r] * ld;
+    const double *src = Rt + (size_t)r * L.nfo_pad - L.own_f0;  // indexed by global couple
+    const int m0 = L.own_m0 + blockIdx.x * 32 * kMirrorCols, m1 = min(L.own_m0 + L.own_nm, m0 + 32 * kMirrorCols);
+#pragma unroll
+    for (int k = 0; k < kMirrorCols; k++) {
+        const int m = m0 + k * 32 + lane;
+        if (m < m1) row[L.mem_slot[m]] = (T)src[L.mem_fam[m]];
     }
 }
 
