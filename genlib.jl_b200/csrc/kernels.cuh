@@ -115,16 +115,23 @@ cross_kernel(T *__restrict__ A, int64_t ld, double *__restrict__ Rt, PeerTable P
     // ---- gather-average of the two parent rows (wherever they live: local HBM or a peer's,
     //      read through NVLink) ----
     const T *rf[4], *rm[4];
+    int mb[4], me[4], lr0[4];                            // members of the couple (rows to write), first local row
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         const int Fl = F0 + warp * 4 + q;
         rf[q] = nullptr; rm[q] = nullptr;
+        mb[q] = 0; me[q] = 0; lr0[q] = 0;
         if (Fl < L.own_nf) {
             const int F = L.own_f0 + Fl;
             const int of = L.fam_pf_owner[F], om = L.fam_pm_owner[F];
             if (of >= 0) rf[q] = static_cast<const T *>(PT.A[of]) + (int64_t)L.fam_pf_lrow[F] * ld + p0 + 4 * lane;
             if (om >= 0) rm[q] = static_cast<const T *>(PT.A[om]) + (int64_t)L.fam_pm_lrow[F] * ld + p0 + 4 * lane;
+            if (carried_here) { mb[q] = L.fam_start[F]; me[q] = L.fam_start[F + 1]; }
         }
+    }
+    if (carried_here) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) if (me[q] > mb[q]) lr0[q] = L.mem_lrow[mb[q]];
     }
     double x[4][4], y[4][4];
 #pragma unroll
@@ -146,13 +153,11 @@ cross_kernel(T *__restrict__ A, int64_t ld, double *__restrict__ Rt, PeerTable P
             // rows of the new members against this tile's columns (rounded once, compute.jl:296).
             // Columns that are not carried receive values nobody reads; new x new is
             // rewritten by expand_kernel afterwards.
-            const int Fl = F0 + warp * 4 + q;
-            if (Fl < L.own_nf) {
-                const int F = L.own_f0 + Fl;
-                const int m1 = L.fam_start[F + 1];
-                for (int m = L.fam_start[F]; m < m1; m++) {
-                    store4(A + (int64_t)L.mem_lrow[m] * ld + p0 + 4 * lane, r);
-                    const int go = L.mem_gowner[m];        // guest copy of the new row (multi-GPU)
+            for (int m = mb[q]; m < me[q]; m++) {
+                const int lr = m == mb[q] ? lr0[q] : L.mem_lrow[m];
+                store4(A + (int64_t)lr * ld + p0 + 4 * lane, r);
+                if (L.world > 1) {
+                    const int go = L.mem_gowner[m];        // guest copy of the new row (GENLIB_GUESTS=1)
                     if (go >= 0) store4(static_cast<T *>(PT.A[go]) + (int64_t)L.mem_glrow[m] * ld + p0 + 4 * lane, r);
                 }
             }
