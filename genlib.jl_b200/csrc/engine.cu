@@ -254,6 +254,7 @@ LayerArgs layer_args(const genlib_engine &E, int t) {
     a.own_f0 = fb[E.rank]; a.own_nf = fb[E.rank + 1] - fb[E.rank];
     a.own_m0 = mb[E.rank]; a.own_nm = mb[E.rank + 1] - mb[E.rank];
     a.nfo_pad = pad32(a.own_nf);
+    a.ftile_shift = E.world > 1 ? fb[(E.rank + 1) % E.world] / kFTile : 0;
     a.mem_ind = E.mem_ind.p + L.mem_off; a.mem_slot = E.mem_slot.p + L.mem_off; a.mem_fam = E.mem_fam.p + L.mem_off;
     a.mem_lrow = E.mem_lrow.p + L.mem_off;
     a.mem_gowner = E.mem_gowner.p + L.mem_off; a.mem_glrow = E.mem_glrow.p + L.mem_off;

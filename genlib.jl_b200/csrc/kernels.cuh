@@ -41,7 +41,7 @@ struct LayerArgs {
     int32_t n_new, n_fam, rt_lo, rt_rows, nf_pad, any_carried;
     // row sharding: this rank owns couples [own_f0, own_f0 + own_nf) and members
     // [own_m0, own_m0 + own_nm); nfo_pad = row stride of its transposed cross block
-    int32_t rank, world, own_f0, own_nf, own_m0, own_nm, nfo_pad;
+    int32_t rank, world, own_f0, own_nf, own_m0, own_nm, nfo_pad, ftile_shift;
     int32_t fam_base[kMaxWorld + 1];
     const int32_t *mem_ind, *mem_slot, *mem_fam, *mem_lrow;
     const int32_t *fam_pf, *fam_pm, *fam_start;
@@ -217,8 +217,11 @@ couple_kernel(int64_t ld, const double *__restrict__ Rt, T *__restrict__ Vt, T *
     T *sV = reinterpret_cast<T *>(smem_raw);                  // [kFTile][kCStride]
     __shared__ int s_skip[kFTile];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // rows: ALL couples F of the layer; columns: this rank's own couples G (local index gl)
-    const int F0 = blockIdx.y * kFTile, G0 = blockIdx.x * kCTile;
+    // rows: ALL couples F of the layer; columns: this rank's own couples G (local index gl).
+    // The row tiles are visited starting behind this rank's own range: at any moment the ranks
+    // push to DIFFERENT owners instead of all hitting the same GPU's NVLink ingress.
+    const int ytile = (int)((blockIdx.y + (unsigned)L.ftile_shift) % gridDim.y);
+    const int F0 = ytile * kFTile, G0 = blockIdx.x * kCTile;
     const int minG = L.fam_minrank[L.own_f0 + min(G0, max(L.own_nf - 1, 0))];   // increases inside the own range
     const int gl = G0 + 4 * lane;
     const bool col_ok = gl < L.nfo_pad;                       // nfo_pad is a multiple of 4
