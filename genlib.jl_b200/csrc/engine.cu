@@ -270,7 +270,6 @@ LayerArgs layer_args(const genlib_engine &E, int t) {
     a.mt_m0 = E.mt_m0.p + L.mtile_off; a.mt_cnt = E.mt_cnt.p + L.mtile_off;
     a.n_mtiles = L.n_mtiles;
     const int vec = 16 / (int)E.esize;
-    a.vrows = kERows;
     a.vstride = (std::max(L.max_tile_fam, 1) + vec - 1) / vec * vec + vec;
     return a;
 }

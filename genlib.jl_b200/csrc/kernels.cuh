@@ -51,12 +51,11 @@ struct LayerArgs {
     const int32_t *fam_minrank, *fam_maxrank;
     const int32_t *mt_minrank, *mt_maxrank, *mt_fam0, *mt_nfam, *mt_m0, *mt_cnt;
     int32_t n_mtiles;
-    int32_t vrows, vstride;     // staged couple tile of expand_kernel: rows, row stride (elements)
+    int32_t vstride;            // staged couple segment of expand_kernel: row stride (elements)
 };
 
 constexpr int kThreads = 256;
 constexpr int kSRStride = kPTile + 2;   // doubles; even => 16-byte aligned rows
-constexpr int kVStride = kMTile + 1;
 
 // ---- 4-wide row-segment access ------------------------------------------------------
 __device__ __forceinline__ void load4(const float *p, double (&d)[4]) {
