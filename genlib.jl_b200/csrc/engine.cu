@@ -513,6 +513,7 @@ int genlib_device_count(void) {
 int genlib_release_cache(void) {
     g_peer_maps.close_all();
     g_arenas.release_device(-1);
+    release_plan_cache();
     return GENLIB_OK;
 }
 
@@ -538,6 +539,7 @@ int genlib_plan_create(int32_t n, const int32_t *father, const int32_t *mother, 
     std::string err;
     int rc;
     try {
+        adopt_retired_storage(pl->p);        // the arrays of the last destroyed plan, already paged in
         rc = build_plan(n, father, mother, n_pro, proband, world, pl->p, err);
     } catch (const std::bad_alloc &) {
         return fail(GENLIB_ENOMEM, "out of host memory while planning");
@@ -548,7 +550,11 @@ int genlib_plan_create(int32_t n, const int32_t *father, const int32_t *mother, 
     return GENLIB_OK;
 }
 
-void genlib_plan_destroy(genlib_plan *plan) { delete plan; }
+void genlib_plan_destroy(genlib_plan *plan) {
+    if (!plan) return;
+    try { retire_storage(plan->p); } catch (...) {}
+    delete plan;
+}
 int32_t genlib_plan_n_unique(const genlib_plan *plan) { return plan ? plan->p.n_unique : -1; }
 int32_t genlib_plan_n_layers(const genlib_plan *plan) { return plan ? (int32_t)plan->p.layers.size() : -1; }
 int64_t genlib_plan_capacity(const genlib_plan *plan) { return plan ? plan->p.capacity : -1; }

@@ -4,6 +4,8 @@
 #include <algorithm>
 #include <climits>
 #include <cstdlib>
+#include <memory>
+#include <mutex>
 
 #include "../../include/genlib_cuda.h"
 
@@ -16,34 +18,117 @@ inline int32_t round_up(int64_t x, int64_t m) { return (int32_t)(((x + m - 1) / 
 // (father, mother) -> family id of the current layer.  Open addressing with a
 // generation stamp so the table is never cleared.
 struct FamilyTable {
-    std::vector<uint64_t> key;
-    std::vector<int32_t> val, stamp;
+    struct Bucket { uint64_t key; int32_t val, stamp; };      // 16 bytes: one cache line touch per probe
+    std::vector<Bucket> b;
     uint64_t mask = 0;
-    void reserve(size_t n) {
+    int32_t tick = 0;             // stamp of the current layer; never repeats while the table lives
+    void next_layer(size_t n) {   // empties the table (by stamp) and makes room for n keys
         size_t cap = 64;
         while (cap < 2 * n + 2) cap <<= 1;
-        if (cap > key.size()) { key.assign(cap, 0); val.assign(cap, 0); stamp.assign(cap, -1); }
-        mask = key.size() - 1;
+        if (cap > b.size() || tick == INT32_MAX) { b.assign(std::max(cap, b.size()), Bucket{0, 0, -1}); tick = 0; }
+        else tick++;
+        mask = b.size() - 1;
     }
     static uint64_t mix(uint64_t x) {
         x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33;
         x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33; return x;
     }
-    // returns the slot index of `k` (existing or fresh); *found tells which
-    size_t find(uint64_t k, int32_t tick, bool *found) {
+    void prefetch(uint64_t k) const { __builtin_prefetch(&b[mix(k) & mask], 1); }
+    // returns the bucket of `k` (existing or fresh); *found tells which
+    Bucket &find(uint64_t k, bool *found) {
         size_t h = mix(k) & mask;
-        while (stamp[h] == tick && key[h] != k) h = (h + 1) & mask;
-        *found = stamp[h] == tick;
-        if (!*found) { stamp[h] = tick; key[h] = k; }
-        return h;
+        while (b[h].stamp == tick && b[h].key != k) h = (h + 1) & mask;
+        *found = b[h].stamp == tick;
+        if (!*found) { b[h].stamp = tick; b[h].key = k; }
+        return b[h];
     }
 };
 
+// where an individual's row lives while it is in the frontier; one record so that the planner's
+// random accesses (by individual) cost one cache miss each
+struct Home {
+    int32_t slot = -1, lrow = -1;
+    int32_t last = -1;           // last layer that reads the row (INT_MAX for probands: kept to the end)
+    int8_t owner = 0;
+};
+
+// lowest-free-first allocator (global column slots; local rows per rank)
+struct Alloc {
+    std::vector<int32_t> freelist, merged;     // ascending
+    int32_t next_fresh = 0;
+    size_t cursor = 0;
+    void reset() { freelist.clear(); next_fresh = 0; cursor = 0; }
+    int32_t take() { return cursor < freelist.size() ? freelist[cursor++] : next_fresh++; }
+    void end_layer(std::vector<int32_t> &freed_sorted) {
+        freelist.erase(freelist.begin(), freelist.begin() + (ptrdiff_t)cursor);
+        cursor = 0;
+        if (!freed_sorted.empty()) {
+            merged.resize(freelist.size() + freed_sorted.size());
+            std::merge(freelist.begin(), freelist.end(), freed_sorted.begin(), freed_sorted.end(), merged.begin());
+            freelist.swap(merged);
+            freed_sorted.clear();
+        }
+    }
+};
+
+// The planner's temporaries; kept between calls for the same reason as the plan's arrays.
+struct Scratch {
+    std::vector<uint8_t> is_pro;
+    std::vector<int32_t> h, hist, ref_last, count, by_layer, cut_size, both_size;
+    std::vector<Home> home;
+    std::vector<size_t> lstart, pos, mem_pos_of;
+    std::vector<int64_t> d_cut, d_both;
+    std::vector<int32_t> born_layer, guest_count, live, next_live;
+    std::vector<int32_t> fam_of, fam_count, fam_first, order, newid, load, freed, cnt, ipos;
+    std::vector<int8_t> fam_own;
+    std::vector<std::vector<int32_t>> freed_rows;
+    Alloc slots;
+    std::vector<Alloc> rows;
+    FamilyTable table;
+};
+
+std::mutex g_pool_mu;
+std::unique_ptr<Scratch> g_scratch;
+std::unique_ptr<Plan> g_retired;
+
+std::unique_ptr<Scratch> take_scratch() {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    return g_scratch ? std::move(g_scratch) : std::unique_ptr<Scratch>(new Scratch);
+}
+void give_scratch(std::unique_ptr<Scratch> s) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (!g_scratch) g_scratch = std::move(s);
+}
+
 }  // namespace
+
+void adopt_retired_storage(Plan &into) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (g_retired) { into = std::move(*g_retired); g_retired.reset(); }
+}
+void retire_storage(Plan &from) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (!g_retired) { from.reset(); g_retired.reset(new Plan(std::move(from))); }
+}
+void release_plan_cache() {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    g_retired.reset(); g_scratch.reset();
+}
+
+static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const int32_t *mother, int32_t n_pro,
+                           const int32_t *proband, int32_t world, Plan &P, std::string &err);
 
 int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t n_pro,
                const int32_t *proband, int32_t world, Plan &P, std::string &err) {
-    P = Plan();
+    std::unique_ptr<Scratch> W = take_scratch();
+    const int rc = build_plan_with(*W, n, father, mother, n_pro, proband, world, P, err);
+    give_scratch(std::move(W));
+    return rc;
+}
+
+static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const int32_t *mother, int32_t n_pro,
+                           const int32_t *proband, int32_t world, Plan &P, std::string &err) {
+    P.reset();
     if (n < 0 || n_pro < 0 || world < 1 || (n > 0 && (!father || !mother)) || (n_pro > 0 && !proband)) {
         err = "genlib_plan_create: null pointer or negative size";
         return GENLIB_EINVAL;
@@ -61,7 +146,7 @@ int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t 
         }
     }
     // probands: first occurrence wins (intersect/union keep first-argument order, compute.jl:247,251)
-    std::vector<uint8_t> is_pro((size_t)n + 1, 0);
+    std::vector<uint8_t> &is_pro = W.is_pro; is_pro.assign((size_t)n + 1, 0);
     for (int32_t t = 0; t < n_pro; t++) {
         int32_t x = proband[t];
         if (x < 0 || x >= n) {
@@ -76,10 +161,10 @@ int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t 
     // height above the probands = longest downward path to one (compute.jl:236-241
     // builds the same levels by repeated _previous_generation).  Children have larger ranks,
     // so one reverse sweep finalises h[x] before x is visited.
-    std::vector<int32_t> h((size_t)n, -1);
+    std::vector<int32_t> &h = W.h; h.assign((size_t)n, -1);
     for (int32_t x : P.pro_ind) h[x] = 0;
     int32_t hmax = 0;
-    std::vector<int32_t> hist;
+    std::vector<int32_t> &hist = W.hist; hist.clear();
     for (int32_t x = n - 1; x >= 0; x--) {
         const int32_t hx = h[x];
         if (hx < 0) continue;
@@ -93,24 +178,27 @@ int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t 
     const int32_t S = hmax + 1;
     // layer = first raw level = S-1-h; last_read = layer of the last child born (engine eviction);
     // ref_last = last raw level (the reference keeps the individual in its cuts until then)
-    std::vector<int32_t> last_read((size_t)n, -1), ref_last((size_t)n, -1);
-    std::vector<int32_t> count((size_t)S + 1, 0);
+    std::vector<Home> &home = W.home; home.assign((size_t)n, Home());
+    std::vector<int32_t> &ref_last = W.ref_last; ref_last.assign((size_t)n, -1);
+    std::vector<int32_t> &count = W.count; count.assign((size_t)S + 1, 0);
     for (int32_t k = 0; k < S; k++) count[S - 1 - k] = hist[k];
     for (int32_t x : P.pro_ind) ref_last[x] = S - 1;
     for (int32_t x = n - 1; x >= 0; x--) {
         if (h[x] < 0) continue;
         const int32_t lx = S - 1 - h[x], rx = ref_last[x] - 1;
         const int32_t f = father[x], m = mother[x];
-        if (f >= 0) { if (last_read[f] < lx) last_read[f] = lx; if (ref_last[f] < rx) ref_last[f] = rx; }
-        if (m >= 0) { if (last_read[m] < lx) last_read[m] = lx; if (ref_last[m] < rx) ref_last[m] = rx; }
+        if (f >= 0) { if (home[f].last < lx) home[f].last = lx; if (ref_last[f] < rx) ref_last[f] = rx; }
+        if (m >= 0) { if (home[m].last < lx) home[m].last = lx; if (ref_last[m] < rx) ref_last[m] = rx; }
     }
+    for (int32_t x : P.pro_ind) home[x].last = INT_MAX;        // probands stay to the end
     // members of each layer in rank order + the reference's cut sizes (verbose lines, compute.jl:254-261)
-    std::vector<size_t> lstart((size_t)S + 1, 0);
+    std::vector<size_t> &lstart = W.lstart; lstart.assign((size_t)S + 1, 0);
     for (int32_t t = 0; t < S; t++) lstart[t + 1] = lstart[t] + count[t];
-    std::vector<int32_t> by_layer(lstart[S]);
-    std::vector<int64_t> d_cut((size_t)S + 2, 0), d_both((size_t)S + 2, 0);
+    std::vector<int32_t> &by_layer = W.by_layer; by_layer.resize(lstart[S]);
+    std::vector<int64_t> &d_cut = W.d_cut, &d_both = W.d_both;
+    d_cut.assign((size_t)S + 2, 0); d_both.assign((size_t)S + 2, 0);
     {
-        std::vector<size_t> pos(lstart.begin(), lstart.end() - 1);
+        std::vector<size_t> &pos = W.pos; pos.assign(lstart.begin(), lstart.end() - 1);
         for (int32_t x = 0; x < n; x++) {
             if (h[x] < 0) continue;
             const int32_t lx = S - 1 - h[x];
@@ -119,7 +207,8 @@ int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t 
             if (ref_last[x] > lx) { d_both[lx]++; d_both[ref_last[x]]--; }   // in cut[k] and cut[k+1]
         }
     }
-    std::vector<int32_t> cut_size((size_t)S, 0), both_size((size_t)S, 0);
+    std::vector<int32_t> &cut_size = W.cut_size, &both_size = W.both_size;
+    cut_size.assign((size_t)S, 0); both_size.assign((size_t)S, 0);
     {
         int64_t a = 0, b = 0;
         for (int32_t k = 0; k < S; k++) { a += d_cut[k]; b += d_both[k]; cut_size[k] = (int32_t)a; both_size[k] = (int32_t)b; }
@@ -132,47 +221,39 @@ int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t 
     // traffic of the same kernel, so they are OFF unless GENLIB_GUESTS=1.
     const bool use_guests = [] { const char *s = std::getenv("GENLIB_GUESTS"); return s && s[0] == '1'; }();
     P.layers.resize(S);
-    P.mem_ind.reserve(lstart[S] + 4 * (size_t)S); P.mem_slot.reserve(lstart[S] + 4 * (size_t)S);
-    P.mem_fam.reserve(lstart[S] + 4 * (size_t)S); P.mem_lrow.reserve(lstart[S] + 4 * (size_t)S);
-    std::vector<int32_t> slot_of((size_t)n, -1), lrow_of((size_t)n, -1);
-    std::vector<int8_t> owner_of((size_t)n, 0);
+    {   // upper bounds (untouched reserve costs nothing): members + alignment padding, couples + rank padding
+        const size_t mcap = lstart[S] + 4 * (size_t)S, fcap = lstart[S] + 4 * (size_t)world * (size_t)S;
+        for (auto *v : {&P.mem_ind, &P.mem_slot, &P.mem_fam, &P.mem_lrow, &P.mem_glrow}) v->reserve(mcap);
+        P.mem_gowner.reserve(mcap);
+        for (auto *v : {&P.fam_pf, &P.fam_pm, &P.fam_pf_lrow, &P.fam_pm_lrow, &P.fam_minrank, &P.fam_maxrank}) v->reserve(fcap);
+        P.fam_pf_owner.reserve(fcap); P.fam_pm_owner.reserve(fcap); P.fam_start.reserve(fcap + (size_t)S);
+    }
     // guest copies: the row of an individual born in layer t-1 is ALSO written, while it is
     // computed, into a spare row of the rank that owns a layer-t couple of which it is the
     // remote parent; that couple's cross kernel then reads locally instead of through NVLink.
     // Encoded until the end of planning: kGuestMark + parity * kGuestStride + index.
     constexpr int32_t kGuestMark = 1 << 30, kGuestStride = 1 << 28;
-    std::vector<int32_t> born_layer((size_t)n, -1);
-    std::vector<size_t> mem_pos_of((size_t)n, 0);
-    std::vector<int32_t> guest_count((size_t)world, 0);
+    const bool guests = use_guests && world > 1;
+    std::vector<int32_t> &born_layer = W.born_layer; born_layer.assign(guests ? (size_t)n : 0, -1);
+    std::vector<size_t> &mem_pos_of = W.mem_pos_of; mem_pos_of.assign(guests ? (size_t)n : 0, 0);
+    std::vector<int32_t> &guest_count = W.guest_count; guest_count.assign((size_t)world, 0);
     P.guest_cap.assign((size_t)world, 0);
-    std::vector<int32_t> live, next_live;        // individuals live before the current step
+    std::vector<int32_t> &live = W.live, &next_live = W.next_live;   // individuals live before the current step
+    live.clear(); next_live.clear();
     // lowest-free-first allocators: global column slots, and local rows per rank
-    struct Alloc {
-        std::vector<int32_t> freelist;           // ascending
-        int32_t next_fresh = 0;
-        size_t cursor = 0;
-        int32_t take() { return cursor < freelist.size() ? freelist[cursor++] : next_fresh++; }
-        void end_layer(std::vector<int32_t> &freed_sorted) {
-            freelist.erase(freelist.begin(), freelist.begin() + (ptrdiff_t)cursor);
-            cursor = 0;
-            if (!freed_sorted.empty()) {
-                std::vector<int32_t> merged(freelist.size() + freed_sorted.size());
-                std::merge(freelist.begin(), freelist.end(), freed_sorted.begin(), freed_sorted.end(), merged.begin());
-                freelist.swap(merged);
-                freed_sorted.clear();
-            }
-        }
-    };
-    Alloc slots;
-    std::vector<Alloc> rows((size_t)world);
-    std::vector<std::vector<int32_t>> freed_rows((size_t)world);
+    Alloc &slots = W.slots; slots.reset();
+    std::vector<Alloc> &rows = W.rows; rows.resize((size_t)world);
+    for (Alloc &a : rows) a.reset();
+    std::vector<std::vector<int32_t>> &freed_rows = W.freed_rows; freed_rows.resize((size_t)world);
+    for (auto &v : freed_rows) v.clear();
     P.rows_cap.assign((size_t)world, 0);
     P.rank_rt_elems.assign((size_t)world, 0);
     P.rank_v_elems.assign((size_t)world, 0);
-    FamilyTable table;
-    std::vector<int32_t> fam_of, fam_count, fam_first, order, newid, load((size_t)world);
-    std::vector<int8_t> fam_own;
-    std::vector<int32_t> freed;
+    FamilyTable &table = W.table;
+    std::vector<int32_t> &fam_of = W.fam_of, &fam_count = W.fam_count, &fam_first = W.fam_first, &order = W.order;
+    std::vector<int32_t> &newid = W.newid, &load = W.load, &freed = W.freed;
+    load.assign((size_t)world, 0);
+    std::vector<int8_t> &fam_own = W.fam_own;
     int32_t rr = 0;
 
     for (int32_t t = 0; t < S; t++) {
@@ -200,7 +281,7 @@ int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t 
         next_live.clear();
         if (!live.empty()) {
             int32_t lo = INT_MAX, hi = -1;
-            for (int32_t x : live) { lo = std::min(lo, slot_of[x]); hi = std::max(hi, slot_of[x]); }
+            for (int32_t x : live) { lo = std::min(lo, home[x].slot); hi = std::max(hi, home[x].slot); }
             L.rt_lo = (lo / kPTile) * kPTile;
             L.rt_rows = round_up(hi + 1, kPTile) - L.rt_lo;
             P.flags.resize(L.flag_off + (size_t)L.rt_rows, 0);
@@ -208,14 +289,14 @@ int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t 
             P.live_lrow.resize(L.flag_off + (size_t)L.rt_rows, 0);
             uint8_t *fl = P.flags.data() + L.flag_off;
             for (int32_t x : live) {
-                // read for the last time in step last_read[x]; probands stay to the end
-                const bool stays = is_pro[x] || last_read[x] > t;
-                const int32_t r = slot_of[x] - L.rt_lo;
+                const Home hx = home[x];
+                const bool stays = hx.last > t;      // read for the last time in step `last`
+                const int32_t r = hx.slot - L.rt_lo;
                 fl[r] = (uint8_t)(kFlagLive | (stays ? kFlagCarried : 0));
-                P.live_owner[L.flag_off + r] = owner_of[x];
-                P.live_lrow[L.flag_off + r] = lrow_of[x];
+                P.live_owner[L.flag_off + r] = hx.owner;
+                P.live_lrow[L.flag_off + r] = hx.lrow;
                 if (stays) { next_live.push_back(x); L.carried++; }
-                else if (world > 1) freed_rows[owner_of[x]].push_back(lrow_of[x]);
+                else if (world > 1) freed_rows[hx.owner].push_back(hx.lrow);
             }
             for (int32_t r = 0; r < L.rt_rows; r++)        // evicted slots, already in ascending order
                 if (fl[r] == kFlagLive) freed.push_back(L.rt_lo + r);
@@ -223,19 +304,23 @@ int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t 
 
         // ---- families: same (father, mother) => same cross row (compute.jl:111-126 gives
         //      full siblings identical kinship to everybody else) ----
-        table.reserve((size_t)nn);
+        table.next_layer((size_t)nn);
         fam_of.assign((size_t)nn, 0);
         fam_count.clear(); fam_first.clear();
+        auto couple_key = [&](int32_t x) {
+            return ((uint64_t)(uint32_t)(father[x] + 1) << 32) | (uint32_t)(mother[x] + 1);
+        };
+        constexpr int32_t kAhead = 16;
+        for (int32_t q = 0; q < std::min(nn, kAhead); q++) table.prefetch(couple_key(X[q]));
         for (int32_t q = 0; q < nn; q++) {
-            int32_t x = X[q];
-            uint64_t key = ((uint64_t)(uint32_t)(father[x] + 1) << 32) | (uint32_t)(mother[x] + 1);
+            if (q + kAhead < nn) table.prefetch(couple_key(X[q + kAhead]));
             bool found;
-            size_t hsl = table.find(key, t, &found);
-            if (found && fam_count[table.val[hsl]] < kMaxFamily) {
-                fam_of[q] = table.val[hsl];
+            FamilyTable::Bucket &bk = table.find(couple_key(X[q]), &found);
+            if (found && fam_count[bk.val] < kMaxFamily) {
+                fam_of[q] = bk.val;
             } else {
                 fam_of[q] = (int32_t)fam_count.size();
-                table.val[hsl] = fam_of[q];
+                bk.val = fam_of[q];
                 fam_count.push_back(0);
                 fam_first.push_back(q);
             }
@@ -255,15 +340,17 @@ int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t 
         int32_t nf = nf_real;
         if (world > 1) {
             std::fill(load.begin(), load.end(), 0);
-            std::vector<int32_t> cnt((size_t)world, 0);
+            std::vector<int32_t> &cnt = W.cnt; cnt.assign((size_t)world, 0);
             const int32_t cap = (nn + world - 1) / world + (nn + world - 1) / world / 8 + kMaxFamily;
             for (int32_t f = 0; f < nf_real; f++) {
                 const int32_t x = X[fam_first[f]];
                 const int32_t fa = father[x], mo = mother[x];
                 int32_t g;
-                if (fa >= 0 && mo >= 0) g = load[owner_of[mo]] < load[owner_of[fa]] ? owner_of[mo] : owner_of[fa];
-                else if (fa >= 0) g = owner_of[fa];
-                else if (mo >= 0) g = owner_of[mo];
+                if (fa >= 0 && mo >= 0) {
+                    const int32_t of = home[fa].owner, om = home[mo].owner;
+                    g = load[om] < load[of] ? om : of;
+                } else if (fa >= 0) g = home[fa].owner;
+                else if (mo >= 0) g = home[mo].owner;
                 else g = rr++ % world;
                 if (load[g] + fam_count[f] > cap) g = (int32_t)(std::min_element(load.begin(), load.end()) - load.begin());
                 fam_own[f] = (int8_t)g;
@@ -272,7 +359,7 @@ int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t 
             }
             for (int32_t g = 0; g < world; g++) fbase[g + 1] = round_up(fbase[g] + cnt[g], 4);
             nf = fbase[world];
-            std::vector<int32_t> pos(fbase, fbase + world);
+            std::vector<int32_t> &pos = W.ipos; pos.assign(fbase, fbase + world);
             for (int32_t f = 0; f < nf_real; f++) newid[f] = pos[fam_own[f]]++;     // rank-major, stable
         } else {
             fbase[1] = nf;
@@ -290,7 +377,7 @@ int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t 
         for (int32_t g = 0; g <= world; g++) mbase[g] = fstart[fbase[g]];
         order.assign((size_t)nn, 0);
         {
-            std::vector<int32_t> pos(fstart, fstart + nf);
+            std::vector<int32_t> &pos = W.ipos; pos.assign(fstart, fstart + nf);
             for (int32_t q = 0; q < nn; q++) order[pos[newid[fam_of[q]]]++] = q;
         }
         // ---- column slots (global) and local rows (per owner): lowest free first, then fresh ----
@@ -304,8 +391,9 @@ int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t 
                 const int32_t oq = order[q], x = X[oq], f = fam_of[oq];
                 const int32_t g = fam_own[f];
                 const int32_t s = slots.take(), lr = world > 1 ? rows[g].take() : s;   // one rank: row == slot
-                slot_of[x] = s; lrow_of[x] = lr; owner_of[x] = (int8_t)g;
-                born_layer[x] = t; mem_pos_of[x] = L.mem_off + (size_t)q;
+                Home &hx = home[x];
+                hx.slot = s; hx.lrow = lr; hx.owner = (int8_t)g;
+                if (guests) { born_layer[x] = t; mem_pos_of[x] = L.mem_off + (size_t)q; }
                 mi[q] = x; ms[q] = s; mf[q] = newid[f]; ml[q] = lr;
             }
         }
@@ -318,16 +406,16 @@ int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t 
             const int32_t x = X[fam_first[f]], fa = father[x], mo = mother[x];
             const size_t k = L.fam_off + (size_t)newid[f];
             const int32_t g = fam_own[f];
-            P.fam_pf[k] = fa >= 0 ? slot_of[fa] : -1;
-            P.fam_pm[k] = mo >= 0 ? slot_of[mo] : -1;
+            int32_t *ps[2] = {&P.fam_pf[k], &P.fam_pm[k]};
             int8_t *po[2] = {&P.fam_pf_owner[k], &P.fam_pm_owner[k]};
             int32_t *pl[2] = {&P.fam_pf_lrow[k], &P.fam_pm_lrow[k]};
             const int32_t par[2] = {fa, mo};
             for (int s = 0; s < 2; s++) {
                 const int32_t p = par[s];
-                if (p < 0) { *po[s] = -1; *pl[s] = -1; continue; }
-                *po[s] = owner_of[p]; *pl[s] = lrow_of[p];
-                if (world > 1 && use_guests && owner_of[p] != g && born_layer[p] == t - 1) {
+                if (p < 0) { *ps[s] = -1; *po[s] = -1; *pl[s] = -1; continue; }
+                const Home hp = home[p];
+                *ps[s] = hp.slot; *po[s] = hp.owner; *pl[s] = hp.lrow;
+                if (guests && hp.owner != g && born_layer[p] == t - 1) {
                     const size_t mp = mem_pos_of[p];
                     if (P.mem_gowner[mp] < 0) {                 // first remote consumer gets the copy
                         P.mem_gowner[mp] = (int8_t)g;
@@ -407,9 +495,8 @@ int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t 
     const size_t np = P.pro_ind.size();
     P.pro_slot.resize(np); P.pro_owner.resize(np); P.pro_lrow.resize(np);
     for (size_t u = 0; u < np; u++) {
-        P.pro_slot[u] = slot_of[P.pro_ind[u]];
-        P.pro_owner[u] = owner_of[P.pro_ind[u]];
-        P.pro_lrow[u] = lrow_of[P.pro_ind[u]];
+        const Home &hu = home[P.pro_ind[u]];
+        P.pro_slot[u] = hu.slot; P.pro_owner[u] = hu.owner; P.pro_lrow[u] = hu.lrow;
     }
     return GENLIB_OK;
 }

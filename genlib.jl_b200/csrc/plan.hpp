@@ -77,7 +77,29 @@ struct Plan {
     std::vector<int64_t> rows_cap;                     // per rank: home rows
     std::vector<int32_t> guest_cap;                    // per rank: guest rows per bank (two banks behind the home rows)
     std::vector<size_t> rank_rt_elems, rank_v_elems;   // per rank: max rt_rows*nfo_pad, max nf_own*nf_pad
+
+    // Every array above, for reset(): the storage of a destroyed plan is handed to the next
+    // genlib_plan_create, because first-touch page faults on a few hundred MB of fresh vectors
+    // cost more than the planning itself.
+    template <class F> void each_array(F &&f) {
+        f(layers); f(pro_ind); f(pro_slot); f(mem_ind); f(mem_slot); f(mem_fam); f(fam_pf); f(fam_pm);
+        f(fam_start); f(flags); f(fam_minrank); f(fam_maxrank); f(mtile_minrank); f(mtile_maxrank);
+        f(mtile_fam0); f(mtile_nfam); f(mtile_m0); f(mtile_cnt); f(fam_base); f(mem_base); f(mem_lrow);
+        f(fam_pf_owner); f(fam_pm_owner); f(fam_pf_lrow); f(fam_pm_lrow); f(live_owner); f(live_lrow);
+        f(pro_owner); f(pro_lrow); f(mem_gowner); f(mem_glrow); f(rows_cap); f(guest_cap);
+        f(rank_rt_elems); f(rank_v_elems);
+    }
+    void reset() {                     // empty plan, capacities kept
+        each_array([](auto &v) { v.clear(); });
+        n = n_unique = 0; world = 1; capacity = row_updates = 0; alg_elems = 0;
+        rt_elems_max = v_elems_max = 0;
+    }
 };
+
+// Recycling of plan storage across calls (bounded: one retired plan, one set of planner scratch).
+void adopt_retired_storage(Plan &into);   // moves a retired plan's (empty, reserved) arrays into `into`
+void retire_storage(Plan &from);          // keeps `from`'s arrays for the next adopt_retired_storage
+void release_plan_cache();                // frees what is kept (genlib_release_cache)
 
 inline int32_t pad32(int32_t x) { return ((x > 0 ? x : 1) + 31) / 32 * 32; }
 

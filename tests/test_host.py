@@ -109,6 +109,34 @@ def test_plan_invariants(gen):
     assert set(plan.proband_slots()) <= set(live.values())
 
 
+def _plan_dump(gen, ped, probands, world):
+    plan = gen.Plan(ped.father, ped.mother, ped.rank_of(probands), world=world)
+    out = [plan.capacity, plan.n_layers, plan.row_updates, plan.proband_slots().tolist()]
+    for t in range(plan.n_layers):
+        out.append(sorted((k, np.asarray(v).tolist()) for k, v in plan.layer_arrays(t).items()))
+        out.append(sorted((k, np.asarray(v).tolist()) for k, v in plan.layer_shard(t).items()))
+        out.append(sorted(plan.layer_info(t).items()))
+    return out
+
+
+@pytest.mark.parametrize("world", [1, 3])
+def test_recycled_plan_storage_changes_nothing(gen, world):
+    """A destroyed plan's arrays and the planner's scratch are reused by the next
+    genlib_plan_create; the schedule must not depend on what was planned before."""
+    from genlib_jl_b200 import _lib
+    big = gen.synth.generate(6000, 12, 300, alpha=0.05, demes=2, migration=0.1, overlap=2, seed=11)
+    small = gen.synth.generate(900, 25, 40, alpha=0.1, demes=1, migration=0.0, overlap=3, seed=12)
+    pb, ps = gen.genealogy(big.as_columns()), gen.genealogy(small.as_columns())
+    _lib.lib().genlib_release_cache()
+    fresh_small = _plan_dump(gen, ps, small.probands, world)
+    _lib.lib().genlib_release_cache()
+    fresh_big = _plan_dump(gen, pb, big.probands, world)        # retires the big plan's storage
+    assert _plan_dump(gen, ps, small.probands, world) == fresh_small   # small after big
+    assert _plan_dump(gen, pb, big.probands, world) == fresh_big       # big after small
+    assert _plan_dump(gen, pb, big.probands, 1 if world > 1 else 2) is not None
+    assert _plan_dump(gen, ps, small.probands, world) == fresh_small   # after a different world size
+
+
 @pytest.mark.parametrize("numerics", ["reference", "fp64"])
 def test_replayed_schedule_equals_oracle_geneaji(gen, ob, numerics):
     ped = gen.genealogy(gen.geneaJi)
