@@ -164,7 +164,7 @@ struct genlib_plan {
 
 struct genlib_engine {
     const genlib_plan *plan = nullptr;
-    int numerics = 0, device = 0;
+    int numerics = 0, device = 0, sm_count = 148;
     int rank = 0, world = 1;
     bool attached = false;                 // peers' arenas mapped (always true for one rank)
     size_t esize = 4;
@@ -286,7 +286,7 @@ int launch_layers(genlib_engine &E, bool timed) {
     const Plan &P = E.plan->p;
     T *A = static_cast<T *>(E.A);
     const int64_t ld = P.capacity;
-    const size_t cross_smem = (size_t)kFTile * kSRStride * sizeof(double);
+    const size_t cross_smem = cross_smem_bytes<T>();
     const int vec = 16 / (int)sizeof(T);
     int max_tile_fam = 1;
     for (const Layer &L : P.layers) max_tile_fam = std::max(max_tile_fam, L.max_tile_fam);
@@ -294,6 +294,7 @@ int launch_layers(genlib_engine &E, bool timed) {
     if (expand_smem_max > 227 * 1024) return fail(GENLIB_EINVAL, "couple tile too wide for the expand kernel");
     auto expand_fn = E.world > 1 ? expand_kernel<T, true> : expand_kernel<T, false>;
     CU(cudaFuncSetAttribute(expand_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem_max));
+    CU(cudaFuncSetAttribute(cross_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cross_smem));
     CU(cudaFuncSetAttribute(cross_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CU(cudaFuncSetAttribute(expand_fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     T *V = static_cast<T *>(E.Vrow), *Vt = static_cast<T *>(E.Vt), *Dg = static_cast<T *>(E.Dg);
@@ -309,7 +310,11 @@ int launch_layers(genlib_engine &E, bool timed) {
         LayerArgs a = layer_args(E, t);
         if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
         if (L.live_before > 0 && a.own_nf > 0) {
-            dim3 grid((unsigned)(L.rt_rows / kPTile), (unsigned)((a.own_nf + kFTile - 1) / kFTile));
+            // column tiles per CTA: long chunks amortise the pipeline fill, but keep >= ~4 waves of CTAs
+            const int64_t ptiles = L.rt_rows / kPTile, ftiles = (a.own_nf + kFTile - 1) / kFTile;
+            const int64_t want = ptiles * ftiles / (4 * 2 * (int64_t)E.sm_count);
+            a.pchunk = (int)std::max<int64_t>(std::min<int64_t>(4, ptiles), std::min<int64_t>(kMaxPChunk, want));
+            dim3 grid((unsigned)((ptiles + a.pchunk - 1) / a.pchunk), (unsigned)ftiles);
             cross_kernel<T><<<grid, kThreads, cross_smem, E.stream>>>(A, ld, E.Rt, E.peers, a);
             launches++;
             if (L.carried > 0 && a.own_nm > 0) {
@@ -403,6 +408,7 @@ int create_engine(const genlib_plan *plan, int numerics, int device, int rank, g
     E->plan = plan; E->numerics = numerics; E->rank = rank; E->world = P.world;
     E->esize = numerics == GENLIB_NUMERICS_FP64 ? 8 : 4;
     CU(cudaGetDevice(&E->device));
+    CU(cudaDeviceGetAttribute(&E->sm_count, cudaDevAttrMultiProcessorCount, E->device));
     const size_t need = engine_bytes(P, numerics, rank);
     const double t0 = now_ms();
     CU(cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking));

@@ -22,6 +22,7 @@
 // segments, shared-memory tile transposes, coalesced stores; no tensor cores.
 #pragma once
 #include <cuda_runtime.h>
+#include <climits>
 #include <cstdint>
 
 #include "plan.hpp"
@@ -52,10 +53,10 @@ struct LayerArgs {
     const int32_t *mt_minrank, *mt_maxrank, *mt_fam0, *mt_nfam, *mt_m0, *mt_cnt;
     int32_t n_mtiles;
     int32_t vstride;            // staged couple segment of expand_kernel: row stride (elements)
+    int32_t pchunk;             // live-column tiles per cross_kernel CTA (<= kMaxPChunk)
 };
 
 constexpr int kThreads = 256;
-constexpr int kSRStride = kPTile + 2;   // doubles; even => 16-byte aligned rows
 
 // ---- 4-wide row-segment access ------------------------------------------------------
 __device__ __forceinline__ void load4(const float *p, double (&d)[4]) {
@@ -87,87 +88,164 @@ __device__ __forceinline__ void store_vec4(double *p, const double (&v)[4]) {
 __device__ __forceinline__ double half_sum(double x, double y) { return fma(0.5, x, 0.5 * y); }
 
 // =====================================================================================
-// cross_kernel: grid (live column tiles, family tiles), 256 threads.
-// Tile = kFTile couples x kPTile live columns.  Warp w owns couples 4w..4w+3, lane l
-// owns columns 4l..4l+3 of the tile (one 128-bit load per parent row).
+// cross_kernel: grid (chunks of L.pchunk live-column tiles, own couple tiles), 256 threads.
+// Tile = kFTile couples x kPTile live columns.  A CTA keeps ONE couple tile (the 64 parent rows
+// are resolved once: local HBM or a peer's, read through NVLink) and streams the live column
+// tiles of its chunk through a kCrossStages-deep shared-memory ring with 16-byte cp.async, so
+// the bytes in flight per SM are a design parameter (2 stages x 32 KB x 2 CTAs) instead of a
+// consequence of occupancy -- the previous one-tile-per-CTA version waited on its own loads
+// (long-scoreboard stalls, 51 % of DRAM peak in profiles/r01/ncu_full_c3_summary.json).
+// The stage holds the RAW parent rows; the unrounded sums are formed when they are written:
+//   (a) transposed into Rt[p, F]: lane = couple, the column rotates with lane/8 so that the
+//       32 shared loads of a warp hit 32 banks (rows are padded by 16 bytes);
+//   (b) only in tiles with carried columns: rounded, as the rows of the couple's members.
 // =====================================================================================
-template <typename T>
-__global__ void __launch_bounds__(kThreads, 4)
-cross_kernel(T *__restrict__ A, int64_t ld, double *__restrict__ Rt, PeerTable PT, LayerArgs L) {
-    extern __shared__ double sR[];                       // [kFTile][kSRStride]
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int F0 = blockIdx.y * kFTile;                  // local couple index (own couples only)
-    const int pt = blockIdx.x;
-    const int p0 = L.rt_lo + pt * kPTile;
-    const uint8_t *fl = L.flags + (size_t)pt * kPTile;
-    const uint8_t myflag = fl[threadIdx.x & (kPTile - 1)];
-    const int live_here = __syncthreads_or(myflag & kFlagLive);
-    if (!live_here) return;                              // hole in a fragmented slot range
-    const int carried_here = L.any_carried ? __syncthreads_or(myflag & kFlagCarried) : 0;
-    // per-column flags as bit masks in shared memory (read again after the tile barrier below)
-    __shared__ unsigned s_live[kPTile / 32];
-    {
-        const unsigned lm = __ballot_sync(0xffffffffu, myflag & kFlagLive);
-        if (lane == 0 && warp < kPTile / 32) s_live[warp] = lm;
-    }
+constexpr int kCrossStages = 3;
+constexpr int kMaxPChunk = 32;               // column tiles per CTA (upper bound of L.pchunk)
+template <typename T> __host__ __device__ constexpr int cross_row_bytes() { return kPTile * (int)sizeof(T) + 16; }
+template <typename T> __host__ __device__ constexpr int cross_stage_bytes() { return 2 * kFTile * cross_row_bytes<T>(); }
+template <typename T> constexpr size_t cross_smem_bytes() { return (size_t)kCrossStages * cross_stage_bytes<T>(); }
 
-    // ---- gather-average of the two parent rows (wherever they live: local HBM or a peer's,
-    //      read through NVLink) ----
-    const T *rf[4], *rm[4];
-    int mb[4], me[4], lr0[4];                            // members of the couple (rows to write), first local row
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void cp_async16_to(unsigned smem, const void *gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void zero16_shared(unsigned smem) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};\n" ::"r"(smem), "r"(0) : "memory");
+}
+__device__ __forceinline__ void lds4(const float *p, double (&d)[4]) {
+    const float4 v = *reinterpret_cast<const float4 *>(p);
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+}
+__device__ __forceinline__ void lds4(const double *p, double (&d)[4]) {
+    const double2 a = reinterpret_cast<const double2 *>(p)[0], b = reinterpret_cast<const double2 *>(p)[1];
+    d[0] = a.x; d[1] = a.y; d[2] = b.x; d[3] = b.y;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 2 : 1)
+cross_kernel(T *__restrict__ A, int64_t ld, double *__restrict__ Rt, PeerTable PT, LayerArgs L) {
+    extern __shared__ __align__(16) unsigned char cross_smem[];      // [stage][father rows | mother rows][row bytes]
+    __shared__ const T *s_row[2 * kFTile];                           // parent rows at the chunk's first column
+    __shared__ __align__(16) uint8_t s_flag[kMaxPChunk * kPTile];    // column flags of the chunk
+    __shared__ int s_tile[kMaxPChunk];                               // live tiles: index | carried << 8
+    __shared__ int s_ntile;
+    constexpr int RB = cross_row_bytes<T>(), STAGE = cross_stage_bytes<T>();
+    constexpr int CPR = kPTile * (int)sizeof(T) / 16;                // 16-byte chunks per row
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int F0 = blockIdx.y * kFTile;                              // local couple index (own couples only)
+    const int t0 = blockIdx.x * L.pchunk;
+    const int nt_all = min(L.pchunk, L.rt_rows / kPTile - t0);
+    const int c0 = t0 * kPTile;                                      // first column of the chunk, from rt_lo
+
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(L.flags + c0);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_flag);
+        for (int i = tid; i < nt_all * (kPTile / 16); i += kThreads) dst[i] = __ldg(src + i);
+    }
+    if (tid < 2 * kFTile) {
+        const int Fl = F0 + (tid & (kFTile - 1));
+        const T *row = nullptr;
+        if (Fl < L.own_nf) {
+            const int F = L.own_f0 + Fl;
+            const int o = tid < kFTile ? L.fam_pf_owner[F] : L.fam_pm_owner[F];
+            if (o >= 0) {
+                const int lr = tid < kFTile ? L.fam_pf_lrow[F] : L.fam_pm_lrow[F];
+                row = static_cast<const T *>(PT.A[o]) + (int64_t)lr * ld + L.rt_lo + c0;
+            }
+        }
+        s_row[tid] = row;
+    }
+    __syncthreads();
+    if (warp == 0) {                                                 // holes of a fragmented slot range are skipped
+        int info = 0;
+        if (lane < nt_all) {
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(s_flag + lane * kPTile);
+            uint32_t acc = 0;
+            for (int k = 0; k < kPTile / 4; k++) acc |= w[(k + lane) & (kPTile / 4 - 1)];
+            info = ((acc & 0x01010101u * kFlagLive) ? 1 : 0) | ((acc & 0x01010101u * kFlagCarried) ? 0x100 : 0);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, info & 1);
+        if (info & 1) s_tile[__popc(m & ((1u << lane) - 1u))] = lane | (info & 0x100);
+        if (lane == 0) s_ntile = __popc(m);
+    }
+    __syncthreads();
+    const int nt = s_ntile;
+    if (nt == 0) return;
+
+    int mb[4], me[4];                                                // members of the warp's 4 couples (rows to write)
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         const int Fl = F0 + warp * 4 + q;
-        rf[q] = nullptr; rm[q] = nullptr;
-        mb[q] = 0; me[q] = 0; lr0[q] = 0;
-        if (Fl < L.own_nf) {
-            const int F = L.own_f0 + Fl;
-            const int of = L.fam_pf_owner[F], om = L.fam_pm_owner[F];
-            if (of >= 0) rf[q] = static_cast<const T *>(PT.A[of]) + (int64_t)L.fam_pf_lrow[F] * ld + p0 + 4 * lane;
-            if (om >= 0) rm[q] = static_cast<const T *>(PT.A[om]) + (int64_t)L.fam_pm_lrow[F] * ld + p0 + 4 * lane;
-            if (carried_here) { mb[q] = L.fam_start[F]; me[q] = L.fam_start[F + 1]; }
+        mb[q] = 0; me[q] = 0;
+        if (L.any_carried && Fl < L.own_nf) { mb[q] = L.fam_start[L.own_f0 + Fl]; me[q] = L.fam_start[L.own_f0 + Fl + 1]; }
+    }
+
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(cross_smem);
+    auto issue = [&](int k) {                                        // k-th live tile -> stage k % kCrossStages
+        const int ti = s_tile[k] & 0xff;
+        const unsigned stage = sbase + (unsigned)(k % kCrossStages) * STAGE;
+#pragma unroll
+        for (int i = 0; i < 2 * kFTile * CPR / kThreads; i++) {
+            const int id = tid + i * kThreads, row = id / CPR, c = id % CPR;
+            const T *src = s_row[row];
+            const unsigned dst = stage + (unsigned)(row * RB + c * 16);
+            if (src) cp_async16_to(dst, src + ti * kPTile + c * (16 / (int)sizeof(T)));
+            else zero16_shared(dst);                                 // unknown parent: contributes 0 (compute.jl:111-126)
         }
+    };
+#pragma unroll
+    for (int k = 0; k < kCrossStages - 1; k++) {
+        if (k < nt) issue(k);
+        cp_async_commit();
     }
-    if (carried_here) {
+    const int rot0 = lane >> 3;
+    for (int k = 0; k < nt; k++) {
+        cp_async_wait<kCrossStages - 2>();
+        __syncthreads();                                             // tile k landed; stage (k-1) % S is free again
+        if (k + kCrossStages - 1 < nt) issue(k + kCrossStages - 1);
+        cp_async_commit();
+        const int tinfo = s_tile[k], ti = tinfo & 0xff;
+        const unsigned char *st = cross_smem + (k % kCrossStages) * STAGE;
+        const uint8_t *fl = s_flag + ti * kPTile;
+        // ---- transposed, unrounded: Rt[p, F] for every live column p of the tile ----
+        {
+            const T *xr = reinterpret_cast<const T *>(st + lane * RB);
+            const T *yr = reinterpret_cast<const T *>(st + (kFTile + lane) * RB);
+            double *rt = Rt + (size_t)(c0 + ti * kPTile) * L.nfo_pad + F0 + lane;
 #pragma unroll
-        for (int q = 0; q < 4; q++) if (me[q] > mb[q]) lr0[q] = L.mem_lrow[mb[q]];
-    }
-    double x[4][4], y[4][4];
+            for (int g = 0; g < kPTile / 32; g++) {
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-#pragma unroll
-        for (int k = 0; k < 4; k++) { x[q][k] = 0.0; y[q][k] = 0.0; }
-        if (rf[q]) load4(rf[q], x[q]);
-        if (rm[q]) load4(rm[q], y[q]);
-    }
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        double r[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) r[k] = half_sum(x[q][k], y[q][k]);
-        double2 *dst = reinterpret_cast<double2 *>(sR + (warp * 4 + q) * kSRStride + 4 * lane);
-        dst[0] = make_double2(r[0], r[1]);
-        dst[1] = make_double2(r[2], r[3]);
-        if (carried_here) {
-            // rows of the new members against this tile's columns (rounded once, compute.jl:296).
-            // Columns that are not carried receive values nobody reads; new x new is
-            // rewritten by expand_kernel afterwards.
-            for (int m = mb[q]; m < me[q]; m++) {
-                const int lr = m == mb[q] ? lr0[q] : L.mem_lrow[m];
-                store4(A + (int64_t)lr * ld + p0 + 4 * lane, r);
-                if (L.world > 1) {
-                    const int go = L.mem_gowner[m];        // guest copy of the new row (GENLIB_GUESTS=1)
-                    if (go >= 0) store4(static_cast<T *>(PT.A[go]) + (int64_t)L.mem_glrow[m] * ld + p0 + 4 * lane, r);
+                for (int j = 0; j < 4; j++) {
+                    const int col = warp * (kPTile / 8) + g * 4 + ((j + rot0) & 3);
+                    if (fl[col] & kFlagLive) rt[(size_t)col * L.nfo_pad] = half_sum((double)xr[col], (double)yr[col]);
                 }
             }
         }
-    }
-    __syncthreads();
-
-    // ---- transposed, unrounded: Rt[p, F] for every live column p of the tile ----
-    for (int pl = warp; pl < kPTile; pl += kThreads / 32) {
-        if ((s_live[pl >> 5] >> (pl & 31)) & 1u)
-            Rt[((size_t)pt * kPTile + pl) * L.nfo_pad + F0 + lane] = sR[lane * kSRStride + pl];
+        // ---- rows of the new members against this tile's columns (rounded once, compute.jl:296).
+        //      Columns that are not carried receive values nobody reads; new x new is rewritten
+        //      by expand_kernel afterwards. ----
+        if (tinfo & 0x100) {
+            const int64_t col0 = (int64_t)L.rt_lo + c0 + ti * kPTile + 4 * lane;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (me[q] <= mb[q]) continue;
+                double x[4], y[4], r[4];
+                lds4(reinterpret_cast<const T *>(st + (warp * 4 + q) * RB) + 4 * lane, x);
+                lds4(reinterpret_cast<const T *>(st + (kFTile + warp * 4 + q) * RB) + 4 * lane, y);
+#pragma unroll
+                for (int e = 0; e < 4; e++) r[e] = half_sum(x[e], y[e]);
+                for (int m = mb[q]; m < me[q]; m++) {
+                    store4(A + (int64_t)L.mem_lrow[m] * ld + col0, r);
+                    if (L.world > 1) {
+                        const int go = L.mem_gowner[m];          // guest copy of the new row (GENLIB_GUESTS=1)
+                        if (go >= 0) store4(static_cast<T *>(PT.A[go]) + (int64_t)L.mem_glrow[m] * ld + col0, r);
+                    }
+                }
+            }
+        }
     }
 }
 
@@ -221,8 +299,13 @@ couple_kernel(int64_t ld, const double *__restrict__ Rt, T *__restrict__ Vt, T *
     // push to DIFFERENT owners instead of all hitting the same GPU's NVLink ingress.
     const int ytile = (int)((blockIdx.y + (unsigned)L.ftile_shift) % gridDim.y);
     const int F0 = ytile * kFTile, G0 = blockIdx.x * kCTile;
-    const int minG = L.fam_minrank[L.own_f0 + min(G0, max(L.own_nf - 1, 0))];   // increases inside the own range
     const int gl = G0 + 4 * lane;
+    int minG = INT_MAX;                                       // lowest rank among the members of the tile's column couples
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (gl + k < L.own_nf) minG = min(minG, L.fam_minrank[L.own_f0 + gl + k]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) minG = min(minG, __shfl_xor_sync(0xffffffffu, minG, o));
     const bool col_ok = gl < L.nfo_pad;                       // nfo_pad is a multiple of 4
 #pragma unroll
     for (int q = 0; q < 4; q++) {
@@ -289,9 +372,6 @@ __device__ __forceinline__ void cp_async(void *smem, const void *gmem) {
     else
         asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(s), "l"(gmem), "n"(BYTES) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 // per warp and stage: Vab[kERows][vstride], Vba[kERows][vstride], famJ/rankJ/slotJ[kMTile]
 template <typename T>

@@ -71,6 +71,44 @@ struct Alloc {
     }
 };
 
+// Column slots are handed out in whole LINES of kSlotLine consecutive slots (128 bytes of a float
+// row): the members of a layer fill free lines in ascending order, so every group of four members
+// sits in four consecutive, 16-byte aligned columns (the 128-bit stores of expand_kernel) and the
+// scattered 4-byte column writes of mirror_kernel fill whole 32-byte sectors.  A line returns to the
+// free list only when every individual in it has been evicted (lowest free line first).
+struct LineAlloc {
+    std::vector<int32_t> freelist, merged;     // free lines, ascending
+    std::vector<int32_t> live;                 // per line: individuals still in the frontier
+    int32_t next_fresh = 0;                    // first line never used
+    size_t cursor = 0;
+    int32_t cur = -1, pos = kSlotLine;
+    void reset() { freelist.clear(); live.clear(); next_fresh = 0; cursor = 0; cur = -1; pos = kSlotLine; }
+    int32_t take() {
+        if (pos == kSlotLine) {
+            cur = cursor < freelist.size() ? freelist[cursor++] : next_fresh++;
+            pos = 0;
+            if ((size_t)cur >= live.size()) live.resize((size_t)cur + 1024, 0);
+        }
+        live[cur]++;
+        return cur * kSlotLine + pos++;
+    }
+    // `slot` was evicted; its line goes to `freed_lines` when it was the last one
+    void release(int32_t slot, std::vector<int32_t> &freed_lines) {
+        if (--live[slot / kSlotLine] == 0) freed_lines.push_back(slot / kSlotLine);
+    }
+    void end_layer(std::vector<int32_t> &freed_lines_sorted) {
+        pos = kSlotLine;                           // the next layer starts a new line
+        freelist.erase(freelist.begin(), freelist.begin() + (ptrdiff_t)cursor);
+        cursor = 0;
+        if (!freed_lines_sorted.empty()) {
+            merged.resize(freelist.size() + freed_lines_sorted.size());
+            std::merge(freelist.begin(), freelist.end(), freed_lines_sorted.begin(), freed_lines_sorted.end(), merged.begin());
+            freelist.swap(merged);
+            freed_lines_sorted.clear();
+        }
+    }
+};
+
 // The planner's temporaries; kept between calls for the same reason as the plan's arrays.
 struct Scratch {
     std::vector<uint8_t> is_pro;
@@ -80,9 +118,10 @@ struct Scratch {
     std::vector<int64_t> d_cut, d_both;
     std::vector<int32_t> born_layer, guest_count, live, next_live;
     std::vector<int32_t> fam_of, fam_count, fam_first, order, newid, load, freed, cnt, ipos;
+    std::vector<int32_t> fam_key;
     std::vector<int8_t> fam_own;
     std::vector<std::vector<int32_t>> freed_rows;
-    Alloc slots;
+    LineAlloc slots;
     std::vector<Alloc> rows;
     FamilyTable table;
 };
@@ -241,7 +280,7 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
     std::vector<int32_t> &live = W.live, &next_live = W.next_live;   // individuals live before the current step
     live.clear(); next_live.clear();
     // lowest-free-first allocators: global column slots, and local rows per rank
-    Alloc &slots = W.slots; slots.reset();
+    LineAlloc &slots = W.slots; slots.reset();
     std::vector<Alloc> &rows = W.rows; rows.resize((size_t)world);
     for (Alloc &a : rows) a.reset();
     std::vector<std::vector<int32_t>> &freed_rows = W.freed_rows; freed_rows.resize((size_t)world);
@@ -298,8 +337,8 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
                 if (stays) { next_live.push_back(x); L.carried++; }
                 else if (world > 1) freed_rows[hx.owner].push_back(hx.lrow);
             }
-            for (int32_t r = 0; r < L.rt_rows; r++)        // evicted slots, already in ascending order
-                if (fl[r] == kFlagLive) freed.push_back(L.rt_lo + r);
+            for (int32_t r = 0; r < L.rt_rows; r++)        // evicted slots in ascending order -> freed lines, ascending
+                if (fl[r] == kFlagLive) slots.release(L.rt_lo + r, freed);
         }
 
         // ---- families: same (father, mother) => same cross row (compute.jl:111-126 gives
@@ -340,7 +379,6 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         int32_t nf = nf_real;
         if (world > 1) {
             std::fill(load.begin(), load.end(), 0);
-            std::vector<int32_t> &cnt = W.cnt; cnt.assign((size_t)world, 0);
             const int32_t cap = (nn + world - 1) / world + (nn + world - 1) / world / 8 + kMaxFamily;
             for (int32_t f = 0; f < nf_real; f++) {
                 const int32_t x = X[fam_first[f]];
@@ -355,12 +393,35 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
                 if (load[g] + fam_count[f] > cap) g = (int32_t)(std::min_element(load.begin(), load.end()) - load.begin());
                 fam_own[f] = (int8_t)g;
                 load[g] += fam_count[f];
-                cnt[g]++;
             }
-            for (int32_t g = 0; g < world; g++) fbase[g + 1] = round_up(fbase[g] + cnt[g], 4);
+        }
+        // ---- couple order inside a rank's range: by the layer in which the couple's longest-lived
+        //      member leaves the frontier, then by rank (stable).  A line of column slots then holds
+        //      individuals that are evicted together, so whole lines come back (LineAlloc) and the
+        //      live slot range stays dense in pedigrees with overlapping generations.  When all
+        //      couples of the layer leave together (discrete generations) this is the rank order. ----
+        constexpr int32_t kKeys = 64;
+        std::vector<int32_t> &fam_key = W.fam_key;
+        fam_key.assign((size_t)nf_real, 0);
+        int32_t key_lo = kKeys, key_hi = -1;
+        for (int32_t q = 0; q < nn; q++) {
+            const int32_t key = std::min(home[X[q]].last - t, kKeys - 1);       // >= 1: somebody is born later, or proband
+            int32_t &fk = fam_key[fam_of[q]];
+            fk = std::max(fk, key);
+        }
+        for (int32_t f = 0; f < nf_real; f++) { key_lo = std::min(key_lo, fam_key[f]); key_hi = std::max(key_hi, fam_key[f]); }
+        if (world > 1 || key_lo != key_hi) {
+            std::vector<int32_t> &cnt = W.cnt; cnt.assign((size_t)world * kKeys, 0);
+            for (int32_t f = 0; f < nf_real; f++) cnt[(size_t)fam_own[f] * kKeys + fam_key[f]]++;
+            for (int32_t g = 0; g < world; g++) {
+                int32_t at = fbase[g];
+                for (int32_t k = 0; k < kKeys; k++) { const int32_t c = cnt[(size_t)g * kKeys + k]; cnt[(size_t)g * kKeys + k] = at; at += c; }
+                // every rank's range starts at a multiple of 4 (16-byte aligned couple columns); the
+                // gaps are empty dummy couples
+                fbase[g + 1] = world > 1 ? round_up(at, 4) : at;
+            }
             nf = fbase[world];
-            std::vector<int32_t> &pos = W.ipos; pos.assign(fbase, fbase + world);
-            for (int32_t f = 0; f < nf_real; f++) newid[f] = pos[fam_own[f]]++;     // rank-major, stable
+            for (int32_t f = 0; f < nf_real; f++) newid[f] = cnt[(size_t)fam_own[f] * kKeys + fam_key[f]]++;   // stable
         } else {
             fbase[1] = nf;
             for (int32_t f = 0; f < nf_real; f++) newid[f] = f;
@@ -432,7 +493,7 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
             const int32_t *mi = P.mem_ind.data() + L.mem_off;
             for (int32_t f = 0; f < nf; f++) {
                 const bool empty = fstart[f + 1] == fstart[f];          // dummy couple: outranks nobody
-                P.fam_minrank[L.fam_off + f] = empty ? INT_MAX : mi[fstart[f]];   // increasing inside a rank's range
+                P.fam_minrank[L.fam_off + f] = empty ? INT_MAX : mi[fstart[f]];
                 P.fam_maxrank[L.fam_off + f] = empty ? -1 : mi[fstart[f + 1] - 1];
             }
         }
@@ -477,7 +538,7 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         for (int32_t q = 0; q < nn; q++) next_live.push_back(X[q]);
         live.swap(next_live);
     }
-    P.capacity = round_up(std::max(slots.next_fresh, 1), kPTile);
+    P.capacity = round_up(std::max<int64_t>((int64_t)slots.next_fresh * kSlotLine, 1), kPTile);
     for (int32_t g = 0; g < world; g++) P.rows_cap[g] = world > 1 ? std::max(rows[g].next_fresh, 1) : P.capacity;
     // resolve the guest rows: they sit behind the home rows of their rank, two banks (layer parity)
     auto resolve = [&](int32_t owner, int32_t &lr) {

