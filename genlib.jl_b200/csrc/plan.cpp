@@ -46,6 +46,10 @@ struct FamilyTable {
 
 // where an individual's row lives while it is in the frontier; one record so that the planner's
 // random accesses (by individual) cost one cache miss each
+struct Pre {
+    int32_t h = -1, minch = INT_MAX, rl = INT_MAX - 1;
+};
+
 struct Home {
     int32_t slot = -1, lrow = -1;
     int32_t last = -1;           // last layer that reads the row (INT_MAX for probands: kept to the end)
@@ -112,7 +116,8 @@ struct LineAlloc {
 // The planner's temporaries; kept between calls for the same reason as the plan's arrays.
 struct Scratch {
     std::vector<uint8_t> is_pro;
-    std::vector<int32_t> h, hist, ref_last, count, by_layer, cut_size, both_size;
+    std::vector<Pre> pre;
+    std::vector<int32_t> hist, count, by_layer, cut_size, both_size;
     std::vector<Home> home;
     std::vector<size_t> lstart, pos, mem_pos_of;
     std::vector<int64_t> d_cut, d_both;
@@ -197,53 +202,54 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
     P.n_unique = (int32_t)P.pro_ind.size();
     if (P.n_unique == 0) return GENLIB_OK;
 
-    // height above the probands = longest downward path to one (compute.jl:236-241
-    // builds the same levels by repeated _previous_generation).  Children have larger ranks,
-    // so one reverse sweep finalises h[x] before x is visited.
-    std::vector<int32_t> &h = W.h; h.assign((size_t)n, -1);
-    for (int32_t x : P.pro_ind) h[x] = 0;
+    // One reverse sweep (children have larger ranks, so an individual is final when it is visited):
+    //   h     height above the probands = longest downward path to one (compute.jl:236-241 builds
+    //         the same levels by repeated _previous_generation); layer = first raw level = S-1-h
+    //   minch lowest height among the children: the last child is born in layer S-1-minch, after
+    //         which the engine evicts the row
+    //   rl    S-1 - (last raw level): the reference keeps the individual in its cuts until then
+    std::vector<Pre> &pre = W.pre; pre.assign((size_t)n, Pre());
+    for (int32_t x : P.pro_ind) { pre[x].h = 0; pre[x].rl = 0; }
     int32_t hmax = 0;
     std::vector<int32_t> &hist = W.hist; hist.clear();
     for (int32_t x = n - 1; x >= 0; x--) {
-        const int32_t hx = h[x];
-        if (hx < 0) continue;
-        if (hx >= (int32_t)hist.size()) hist.resize((size_t)hx + 64, 0);
-        hist[hx]++;
-        hmax = std::max(hmax, hx);
-        const int32_t f = father[x], m = mother[x];
-        if (f >= 0 && h[f] <= hx) h[f] = hx + 1;
-        if (m >= 0 && h[m] <= hx) h[m] = hx + 1;
+        const Pre px = pre[x];
+        if (px.h < 0) continue;
+        if (px.h >= (int32_t)hist.size()) hist.resize((size_t)px.h + 64, 0);
+        hist[px.h]++;
+        hmax = std::max(hmax, px.h);
+        const int32_t par[2] = {father[x], mother[x]};
+        for (int32_t p : par) {
+            if (p < 0) continue;
+            Pre &pp = pre[p];
+            if (pp.h <= px.h) pp.h = px.h + 1;
+            if (pp.minch > px.h) pp.minch = px.h;
+            if (pp.rl > px.rl + 1) pp.rl = px.rl + 1;
+        }
     }
     const int32_t S = hmax + 1;
-    // layer = first raw level = S-1-h; last_read = layer of the last child born (engine eviction);
-    // ref_last = last raw level (the reference keeps the individual in its cuts until then)
-    std::vector<Home> &home = W.home; home.assign((size_t)n, Home());
-    std::vector<int32_t> &ref_last = W.ref_last; ref_last.assign((size_t)n, -1);
     std::vector<int32_t> &count = W.count; count.assign((size_t)S + 1, 0);
     for (int32_t k = 0; k < S; k++) count[S - 1 - k] = hist[k];
-    for (int32_t x : P.pro_ind) ref_last[x] = S - 1;
-    for (int32_t x = n - 1; x >= 0; x--) {
-        if (h[x] < 0) continue;
-        const int32_t lx = S - 1 - h[x], rx = ref_last[x] - 1;
-        const int32_t f = father[x], m = mother[x];
-        if (f >= 0) { if (home[f].last < lx) home[f].last = lx; if (ref_last[f] < rx) ref_last[f] = rx; }
-        if (m >= 0) { if (home[m].last < lx) home[m].last = lx; if (ref_last[m] < rx) ref_last[m] = rx; }
-    }
-    for (int32_t x : P.pro_ind) home[x].last = INT_MAX;        // probands stay to the end
-    // members of each layer in rank order + the reference's cut sizes (verbose lines, compute.jl:254-261)
+    // members of each layer in rank order, where each row is read for the last time, and the
+    // reference's cut sizes (verbose lines, compute.jl:254-261)
     std::vector<size_t> &lstart = W.lstart; lstart.assign((size_t)S + 1, 0);
     for (int32_t t = 0; t < S; t++) lstart[t + 1] = lstart[t] + count[t];
     std::vector<int32_t> &by_layer = W.by_layer; by_layer.resize(lstart[S]);
     std::vector<int64_t> &d_cut = W.d_cut, &d_both = W.d_both;
     d_cut.assign((size_t)S + 2, 0); d_both.assign((size_t)S + 2, 0);
+    std::vector<Home> &home = W.home; home.resize((size_t)n);     // entries outside the plan are never read
     {
         std::vector<size_t> &pos = W.pos; pos.assign(lstart.begin(), lstart.end() - 1);
         for (int32_t x = 0; x < n; x++) {
-            if (h[x] < 0) continue;
-            const int32_t lx = S - 1 - h[x];
+            const Pre px = pre[x];
+            if (px.h < 0) continue;
+            const int32_t lx = S - 1 - px.h, ref_last = S - 1 - px.rl;
             by_layer[pos[lx]++] = x;
-            d_cut[lx]++; d_cut[ref_last[x] + 1]--;                 // in cut[k] for layer <= k <= ref_last
-            if (ref_last[x] > lx) { d_both[lx]++; d_both[ref_last[x]]--; }   // in cut[k] and cut[k+1]
+            Home &hx = home[x];
+            hx.slot = -1; hx.lrow = -1; hx.owner = 0;
+            hx.last = is_pro[x] ? INT_MAX : S - 1 - px.minch;     // probands stay to the end
+            d_cut[lx]++; d_cut[ref_last + 1]--;                    // in cut[k] for layer <= k <= ref_last
+            if (ref_last > lx) { d_both[lx]++; d_both[ref_last]--; }   // in cut[k] and cut[k+1]
         }
     }
     std::vector<int32_t> &cut_size = W.cut_size, &both_size = W.both_size;
