@@ -112,6 +112,25 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 __device__ __forceinline__ void cp_async16_to(unsigned smem, const void *gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem), "l"(gmem) : "memory");
 }
+// mbarrier + bulk-copy (TMA, SASS UBLKCP) helpers
+__device__ __forceinline__ void mbar_init(unsigned bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+// global -> shared bulk copy (16-byte aligned, size a multiple of 16), completes on `bar`
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void zero16_shared(unsigned smem) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};\n" ::"r"(smem), "r"(0) : "memory");
 }
@@ -132,8 +151,9 @@ cross_kernel(T *__restrict__ A, int64_t ld, double *__restrict__ Rt, PeerTable P
     __shared__ __align__(16) uint8_t s_flag[kMaxPChunk * kPTile];    // column flags of the chunk
     __shared__ int s_tile[kMaxPChunk];                               // live tiles: index | carried << 8
     __shared__ int s_ntile;
+    __shared__ __align__(8) unsigned long long s_bar[kCrossStages];  // "stage filled" mbarriers
     constexpr int RB = cross_row_bytes<T>(), STAGE = cross_stage_bytes<T>();
-    constexpr int CPR = kPTile * (int)sizeof(T) / 16;                // 16-byte chunks per row
+    constexpr unsigned ROWB = kPTile * (unsigned)sizeof(T);          // bytes of one row segment
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int F0 = blockIdx.y * kFTile;                              // local couple index (own couples only)
     const int t0 = blockIdx.x * L.pchunk;
@@ -157,6 +177,11 @@ cross_kernel(T *__restrict__ A, int64_t ld, double *__restrict__ Rt, PeerTable P
             }
         }
         s_row[tid] = row;
+    }
+    if (tid == 0) {
+#pragma unroll
+        for (int st = 0; st < kCrossStages; st++) mbar_init((unsigned)__cvta_generic_to_shared(&s_bar[st]), 2 * kFTile);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     if (warp == 0) {                                                 // holes of a fragmented slot range are skipped
@@ -184,29 +209,35 @@ cross_kernel(T *__restrict__ A, int64_t ld, double *__restrict__ Rt, PeerTable P
     }
 
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(cross_smem);
+    const unsigned bar0 = (unsigned)__cvta_generic_to_shared(&s_bar[0]);
+    // One bulk copy (TMA) per parent row and tile: 512-byte (1 KB) requests, which is what NVLink
+    // wants for the rows that live on a peer -- 16-byte cp.async reached only ~300 GB/s there.
+    // Lanes 0..7 of every warp issue one row each and arrive on the stage's mbarrier.
     auto issue = [&](int k) {                                        // k-th live tile -> stage k % kCrossStages
-        const int ti = s_tile[k] & 0xff;
-        const unsigned stage = sbase + (unsigned)(k % kCrossStages) * STAGE;
-#pragma unroll
-        for (int i = 0; i < 2 * kFTile * CPR / kThreads; i++) {
-            const int id = tid + i * kThreads, row = id / CPR, c = id % CPR;
+        if (lane < 2 * kFTile / (kThreads / 32)) {
+            const int row = warp * (2 * kFTile / (kThreads / 32)) + lane;
+            const int ti = s_tile[k] & 0xff;
+            const unsigned bar = bar0 + 8u * (unsigned)(k % kCrossStages);
+            const unsigned dst = sbase + (unsigned)(k % kCrossStages) * STAGE + (unsigned)(row * RB);
             const T *src = s_row[row];
-            const unsigned dst = stage + (unsigned)(row * RB + c * 16);
-            if (src) cp_async16_to(dst, src + ti * kPTile + c * (16 / (int)sizeof(T)));
-            else zero16_shared(dst);                                 // unknown parent: contributes 0 (compute.jl:111-126)
+            if (src) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of the stage
+                mbar_arrive_expect_tx(bar, ROWB);
+                bulk_g2s(dst, src + ti * kPTile, ROWB, bar);
+            } else {                                                 // unknown parent: contributes 0 (compute.jl:111-126)
+                for (unsigned c = 0; c < ROWB; c += 16) zero16_shared(dst + c);
+                mbar_arrive_expect_tx(bar, 0);
+            }
         }
     };
 #pragma unroll
-    for (int k = 0; k < kCrossStages - 1; k++) {
+    for (int k = 0; k < kCrossStages - 1; k++)
         if (k < nt) issue(k);
-        cp_async_commit();
-    }
     const int rot0 = lane >> 3;
     for (int k = 0; k < nt; k++) {
-        cp_async_wait<kCrossStages - 2>();
-        __syncthreads();                                             // tile k landed; stage (k-1) % S is free again
+        mbar_wait(bar0 + 8u * (unsigned)(k % kCrossStages), (unsigned)(k / kCrossStages) & 1u);   // tile k landed
+        __syncthreads();                                             // everybody is done with stage (k-1) % S
         if (k + kCrossStages - 1 < nt) issue(k + kCrossStages - 1);
-        cp_async_commit();
         const int tinfo = s_tile[k], ti = tinfo & 0xff;
         const unsigned char *st = cross_smem + (k % kCrossStages) * STAGE;
         const uint8_t *fl = s_flag + ti * kPTile;
