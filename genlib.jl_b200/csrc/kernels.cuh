@@ -318,7 +318,7 @@ constexpr int kCTile = 128;
 constexpr int kCStride = kCTile + 1;
 
 template <typename T>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 couple_kernel(int64_t ld, const double *__restrict__ Rt, T *__restrict__ Vt, T *__restrict__ Dg, PeerTable PT,
               LayerArgs L) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -338,38 +338,57 @@ couple_kernel(int64_t ld, const double *__restrict__ Rt, T *__restrict__ Vt, T *
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) minG = min(minG, __shfl_xor_sync(0xffffffffu, minG, o));
     const bool col_ok = gl < L.nfo_pad;                       // nfo_pad is a multiple of 4
+    // phase 1: the four rows of this warp -- couple, parents, skip; the couple diagonal
+    int pfs[4], pms[4];
+    bool skips[4];
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         const int fl = warp * 4 + q, F = F0 + fl;
-        bool skip = true;
+        skips[q] = true; pfs[q] = -1; pms[q] = -1;
         if (F < L.n_fam && G0 < L.own_nf) {
-            const int pf = L.fam_pf[F], pm = L.fam_pm[F];
-            if (blockIdx.x == 0 && lane == 0 && F >= L.own_f0 && F < L.own_f0 + L.own_nf) {
-                double d = 0.5;                               // diagonal of the couple's members
-                if (pf >= 0 && pm >= 0)
-                    d = fma(0.5, (double)(static_cast<const T *>(PT.A[L.fam_pf_owner[F]]) + (int64_t)L.fam_pf_lrow[F] * ld)[pm], 0.5);
-                Dg[F] = (T)d;
-            }
-            skip = L.fam_maxrank[F] <= minG;                  // nobody in F outranks anybody in the tile
-            if (!skip && col_ok) {
-                double a[4] = {0.0, 0.0, 0.0, 0.0}, b[4] = {0.0, 0.0, 0.0, 0.0};
-                if (pf >= 0) load4(Rt + (size_t)(pf - L.rt_lo) * L.nfo_pad + gl, a);
-                if (pm >= 0) load4(Rt + (size_t)(pm - L.rt_lo) * L.nfo_pad + gl, b);
-                T v[4];
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    v[k] = (T)half_sum(a[k], b[k]);
-                    sV[fl * kCStride + 4 * lane + k] = v[k];
-                }
-                // V[F, own G] goes to the rank that owns couple F (its row block of V): local, or
-                // a 16-byte peer store over NVLink
-                int o = 0;
-                while (o + 1 < L.world && F >= L.fam_base[o + 1]) o++;
-                T *vrow = static_cast<T *>(PT.Vrow[o]) + (size_t)(F - L.fam_base[o]) * L.nf_pad + L.own_f0;
-                if (gl < L.own_nf) store_vec4(vrow + gl, v);   // never into the next rank's couple columns
-            }
+            pfs[q] = L.fam_pf[F]; pms[q] = L.fam_pm[F];
+            skips[q] = L.fam_maxrank[F] <= minG;              // nobody in F outranks anybody in the tile
         }
-        if (lane == 0) s_skip[fl] = skip;
+        if (lane == 0) s_skip[fl] = skips[q];
+    }
+    if (blockIdx.x == 0 && lane < 4) {                        // diagonal of the couple's members
+        const int F = F0 + warp * 4 + lane;
+        if (F >= L.own_f0 && F < L.own_f0 + L.own_nf) {
+            const int pf = L.fam_pf[F], pm = L.fam_pm[F];
+            double d = 0.5;
+            if (pf >= 0 && pm >= 0)
+                d = fma(0.5, (double)(static_cast<const T *>(PT.A[L.fam_pf_owner[F]]) + (int64_t)L.fam_pf_lrow[F] * ld)[pm], 0.5);
+            Dg[F] = (T)d;
+        }
+    }
+    // phase 2: all parent-row loads of the warp in flight together (two 128-bit loads per row and parent)
+    double a[4][4], b[4][4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) { a[q][k] = 0.0; b[q][k] = 0.0; }
+        if (!skips[q] && col_ok) {
+            if (pfs[q] >= 0) load4(Rt + (size_t)(pfs[q] - L.rt_lo) * L.nfo_pad + gl, a[q]);
+            if (pms[q] >= 0) load4(Rt + (size_t)(pms[q] - L.rt_lo) * L.nfo_pad + gl, b[q]);
+        }
+    }
+    // phase 3: V[F, own G] goes to the rank that owns couple F (its row block of V): local, or a
+    // 16-byte peer store over NVLink; the tile is kept in shared memory for the transposed copy
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int fl = warp * 4 + q, F = F0 + fl;
+        if (!skips[q] && col_ok) {
+            T v[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                v[k] = (T)half_sum(a[q][k], b[q][k]);
+                sV[fl * kCStride + 4 * lane + k] = v[k];
+            }
+            int o = 0;
+            while (o + 1 < L.world && F >= L.fam_base[o + 1]) o++;
+            T *vrow = static_cast<T *>(PT.Vrow[o]) + (size_t)(F - L.fam_base[o]) * L.nf_pad + L.own_f0;
+            if (gl < L.own_nf) store_vec4(vrow + gl, v);       // never into the next rank's couple columns
+        }
     }
     __syncthreads();
     // transposed, local: Vt[own G, F0 .. F0+32), one couple column per warp iteration, lane = couple row
