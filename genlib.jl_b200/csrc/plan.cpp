@@ -4,8 +4,10 @@
 #include <algorithm>
 #include <climits>
 #include <cstdlib>
+#include <atomic>
 #include <memory>
 #include <mutex>
+#include <thread>
 
 #include "../../include/genlib_cuda.h"
 
@@ -122,13 +124,13 @@ struct Scratch {
     std::vector<size_t> lstart, pos, mem_pos_of;
     std::vector<int64_t> d_cut, d_both;
     std::vector<int32_t> born_layer, guest_count, live, next_live;
-    std::vector<int32_t> fam_of, fam_count, fam_first, order, newid, load, freed, cnt, ipos;
-    std::vector<int32_t> fam_key;
+    std::vector<int32_t> fam_of, fam_count, fam_first, fam_key, fam_n;   // couples of every layer (grouped ahead by helper threads)
+    std::vector<int32_t> order, newid, load, freed, cnt, ipos;
+    std::vector<FamilyTable> tables;          // one per planning thread
     std::vector<int8_t> fam_own;
     std::vector<std::vector<int32_t>> freed_rows;
     LineAlloc slots;
     std::vector<Alloc> rows;
-    FamilyTable table;
 };
 
 std::mutex g_pool_mu;
@@ -294,12 +296,85 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
     P.rows_cap.assign((size_t)world, 0);
     P.rank_rt_elems.assign((size_t)world, 0);
     P.rank_v_elems.assign((size_t)world, 0);
-    FamilyTable &table = W.table;
-    std::vector<int32_t> &fam_of = W.fam_of, &fam_count = W.fam_count, &fam_first = W.fam_first, &order = W.order;
+    std::vector<int32_t> &order = W.order;
     std::vector<int32_t> &newid = W.newid, &load = W.load, &freed = W.freed;
     load.assign((size_t)world, 0);
     std::vector<int8_t> &fam_own = W.fam_own;
     int32_t rr = 0;
+
+    // ---- couples: same (father, mother) => same cross row (compute.jl:111-126 gives full siblings
+    //      identical kinship to everybody else), split at kMaxFamily members; and the layer in which the
+    //      couple's longest-lived member leaves the frontier.  A layer's couples depend on nothing but
+    //      the pre-pass, so helper threads group the layers ahead of the sequential slot assignment. ----
+    constexpr int32_t kKeys = 64;
+    const size_t M = lstart[S];
+    W.fam_of.resize(M); W.fam_count.resize(M); W.fam_first.resize(M); W.fam_key.resize(M);
+    W.fam_n.assign((size_t)S, 0);
+    auto group_layer = [&](int32_t t, FamilyTable &table) {
+        const int32_t *X = by_layer.data() + lstart[t];
+        const int32_t nn = count[t];
+        int32_t *fam_of = W.fam_of.data() + lstart[t], *fam_count = W.fam_count.data() + lstart[t];
+        int32_t *fam_first = W.fam_first.data() + lstart[t], *fam_key = W.fam_key.data() + lstart[t];
+        table.next_layer((size_t)nn);
+        auto couple_key = [&](int32_t x) {
+            return ((uint64_t)(uint32_t)(father[x] + 1) << 32) | (uint32_t)(mother[x] + 1);
+        };
+        constexpr int32_t kAhead = 16;
+        int32_t nfr = 0;
+        for (int32_t q = 0; q < std::min(nn, kAhead); q++) table.prefetch(couple_key(X[q]));
+        for (int32_t q = 0; q < nn; q++) {
+            if (q + kAhead < nn) table.prefetch(couple_key(X[q + kAhead]));
+            bool found;
+            FamilyTable::Bucket &bk = table.find(couple_key(X[q]), &found);
+            const int32_t key = std::min(home[X[q]].last - t, kKeys - 1);   // >= 1: somebody is born later, or proband
+            if (found && fam_count[bk.val] < kMaxFamily) {
+                fam_of[q] = bk.val;
+                fam_key[bk.val] = std::max(fam_key[bk.val], key);
+            } else {
+                fam_of[q] = nfr;
+                bk.val = nfr;
+                fam_count[nfr] = 0;
+                fam_first[nfr] = q;
+                fam_key[nfr] = key;
+                nfr++;
+            }
+            fam_count[fam_of[q]]++;
+        }
+        W.fam_n[t] = nfr;
+    };
+    int n_threads = 1;
+    if (M >= 200000) {
+        const char *env = std::getenv("GENLIB_PLAN_THREADS");
+        const int hw = (int)std::thread::hardware_concurrency();
+        // measured on a 16-core B200 host: C3 40 -> 32 ms with one helper, nothing more with three
+        n_threads = env ? std::atoi(env) : std::min(2, hw / world);
+        n_threads = std::max(1, std::min(n_threads, 16));
+    }
+    if (W.tables.size() < (size_t)n_threads) W.tables.resize((size_t)n_threads);
+    std::vector<std::atomic<int>> grouped((size_t)S);
+    for (auto &g : grouped) g.store(0, std::memory_order_relaxed);
+    std::atomic<int32_t> next_job{0};
+    std::atomic<bool> group_failed{false};
+    auto run_job = [&](int32_t t, int id) {
+        try { group_layer(t, W.tables[(size_t)id]); } catch (...) { group_failed.store(true); }
+        grouped[(size_t)t].store(1, std::memory_order_release);
+    };
+    struct Helpers {
+        std::vector<std::thread> th;
+        void join_all() { for (auto &t : th) if (t.joinable()) t.join(); th.clear(); }
+        ~Helpers() { join_all(); }
+    } helpers;
+    for (int id = 1; id < n_threads; id++) {
+        try {
+            helpers.th.emplace_back([&, id] {
+                for (;;) {
+                    const int32_t t = next_job.fetch_add(1);
+                    if (t >= S) break;
+                    run_job(t, id);
+                }
+            });
+        } catch (...) { break; }                 // no thread: the planning thread does the jobs itself
+    }
 
     for (int32_t t = 0; t < S; t++) {
         Layer &L = P.layers[t];
@@ -347,31 +422,15 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
                 if (fl[r] == kFlagLive) slots.release(L.rt_lo + r, freed);
         }
 
-        // ---- families: same (father, mother) => same cross row (compute.jl:111-126 gives
-        //      full siblings identical kinship to everybody else) ----
-        table.next_layer((size_t)nn);
-        fam_of.assign((size_t)nn, 0);
-        fam_count.clear(); fam_first.clear();
-        auto couple_key = [&](int32_t x) {
-            return ((uint64_t)(uint32_t)(father[x] + 1) << 32) | (uint32_t)(mother[x] + 1);
-        };
-        constexpr int32_t kAhead = 16;
-        for (int32_t q = 0; q < std::min(nn, kAhead); q++) table.prefetch(couple_key(X[q]));
-        for (int32_t q = 0; q < nn; q++) {
-            if (q + kAhead < nn) table.prefetch(couple_key(X[q + kAhead]));
-            bool found;
-            FamilyTable::Bucket &bk = table.find(couple_key(X[q]), &found);
-            if (found && fam_count[bk.val] < kMaxFamily) {
-                fam_of[q] = bk.val;
-            } else {
-                fam_of[q] = (int32_t)fam_count.size();
-                bk.val = fam_of[q];
-                fam_count.push_back(0);
-                fam_first.push_back(q);
-            }
-            fam_count[fam_of[q]]++;
+        // ---- couples of the layer (grouped by group_layer, possibly on a helper thread) ----
+        while (!grouped[t].load(std::memory_order_acquire)) {
+            const int32_t j = next_job.load() < S ? next_job.fetch_add(1) : S;
+            if (j < S) run_job(j, 0); else std::this_thread::yield();
         }
-        const int32_t nf_real = (int32_t)fam_count.size();
+        if (group_failed.load()) { helpers.join_all(); throw std::bad_alloc(); }
+        const int32_t *fam_of = W.fam_of.data() + lstart[t], *fam_count = W.fam_count.data() + lstart[t];
+        const int32_t *fam_first = W.fam_first.data() + lstart[t], *fam_key = W.fam_key.data() + lstart[t];
+        const int32_t nf_real = W.fam_n[t];
 
         // ---- row owners: a couple's children live with one of their parents' rows (the other
         //      parent row is read through NVLink); spill to the least loaded rank past +12.5 %.
@@ -406,15 +465,7 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         //      individuals that are evicted together, so whole lines come back (LineAlloc) and the
         //      live slot range stays dense in pedigrees with overlapping generations.  When all
         //      couples of the layer leave together (discrete generations) this is the rank order. ----
-        constexpr int32_t kKeys = 64;
-        std::vector<int32_t> &fam_key = W.fam_key;
-        fam_key.assign((size_t)nf_real, 0);
         int32_t key_lo = kKeys, key_hi = -1;
-        for (int32_t q = 0; q < nn; q++) {
-            const int32_t key = std::min(home[X[q]].last - t, kKeys - 1);       // >= 1: somebody is born later, or proband
-            int32_t &fk = fam_key[fam_of[q]];
-            fk = std::max(fk, key);
-        }
         for (int32_t f = 0; f < nf_real; f++) { key_lo = std::min(key_lo, fam_key[f]); key_hi = std::max(key_hi, fam_key[f]); }
         if (world > 1 || key_lo != key_hi) {
             std::vector<int32_t> &cnt = W.cnt; cnt.assign((size_t)world * kKeys, 0);

@@ -119,6 +119,28 @@ def _plan_dump(gen, ped, probands, world):
     return out
 
 
+@pytest.mark.parametrize("world", [1, 2])
+def test_plan_does_not_depend_on_helper_threads(gen, world, monkeypatch):
+    """Couples are grouped ahead by helper threads (GENLIB_PLAN_THREADS) on large pedigrees."""
+    s = gen.synth.generate(400000, 10, 8000, alpha=0.02, demes=4, migration=0.05, overlap=2, seed=21)
+    ped = gen.genealogy(s.as_columns())
+    ranks = ped.rank_of(s.probands)
+    plans = []
+    for threads in ("1", "3"):
+        monkeypatch.setenv("GENLIB_PLAN_THREADS", threads)
+        plans.append(gen.Plan(ped.father, ped.mother, ranks, world=world))
+    a, b = plans
+    assert (a.capacity, a.n_layers, a.row_updates) == (b.capacity, b.n_layers, b.row_updates)
+    assert a.row_updates >= 200000                       # large enough for the threaded path
+    for t in range(a.n_layers):
+        for getter in ("layer_arrays", "layer_shard"):
+            x, y = getattr(a, getter)(t), getattr(b, getter)(t)
+            assert x.keys() == y.keys()
+            for k in x:
+                assert np.array_equal(x[k], y[k]), (t, k)
+        assert a.layer_info(t) == b.layer_info(t)
+
+
 @pytest.mark.parametrize("world", [1, 3])
 def test_recycled_plan_storage_changes_nothing(gen, world):
     """A destroyed plan's arrays and the planner's scratch are reused by the next
