@@ -298,7 +298,8 @@ int launch_layers(genlib_engine &E, bool timed) {
     CU(cudaFuncSetAttribute(cross_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CU(cudaFuncSetAttribute(expand_fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     T *V = static_cast<T *>(E.Vrow), *Vt = static_cast<T *>(E.Vt), *Dg = static_cast<T *>(E.Dg);
-    const size_t couple_smem = sizeof(T) * kFTile * kCStride;
+    constexpr int kCRows = couple_rows<T>();
+    const size_t couple_smem = sizeof(T) * kCRows * kCStride;
     CU(cudaFuncSetAttribute(couple_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)couple_smem));
     CU(cudaFuncSetAttribute(couple_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     int launches = 0;
@@ -325,7 +326,7 @@ int launch_layers(genlib_engine &E, bool timed) {
         }
         if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
         if (a.own_nf > 0) {
-            dim3 grid((unsigned)((a.nfo_pad + kCTile - 1) / kCTile), (unsigned)((L.n_fam + kFTile - 1) / kFTile));
+            dim3 grid((unsigned)((a.nfo_pad + kCTile - 1) / kCTile), (unsigned)((L.n_fam + kCRows - 1) / kCRows));
             couple_kernel<T><<<grid, kThreads, couple_smem, E.stream>>>(ld, E.Rt, Vt, Dg, E.peers, a);
             launches++;
         }

@@ -316,20 +316,23 @@ mirror_kernel(const double *__restrict__ Rt, int64_t ld, PeerTable PT, LayerArgs
 // =====================================================================================
 constexpr int kCTile = 128;
 constexpr int kCStride = kCTile + 1;
+// couple rows per CTA: several passes of kFTile rows, so that the transposed copy goes out in 512-byte runs
+template <typename T> __host__ __device__ constexpr int couple_rows() { return (sizeof(T) == 4 ? 4 : 2) * kFTile; }
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 3)
 couple_kernel(int64_t ld, const double *__restrict__ Rt, T *__restrict__ Vt, T *__restrict__ Dg, PeerTable PT,
               LayerArgs L) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *sV = reinterpret_cast<T *>(smem_raw);                  // [kFTile][kCStride]
-    __shared__ int s_skip[kFTile];
+    constexpr int kCRows = couple_rows<T>();
+    T *sV = reinterpret_cast<T *>(smem_raw);                  // [kCRows][kCStride]
+    __shared__ int s_skip[kCRows];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // rows: ALL couples F of the layer; columns: this rank's own couples G (local index gl).
     // The row tiles are visited starting behind this rank's own range: at any moment the ranks
     // push to DIFFERENT owners instead of all hitting the same GPU's NVLink ingress.
-    const int ytile = (int)((blockIdx.y + (unsigned)L.ftile_shift) % gridDim.y);
-    const int F0 = ytile * kFTile, G0 = blockIdx.x * kCTile;
+    const int ytile = (int)((blockIdx.y + (unsigned)L.ftile_shift * kFTile / kCRows) % gridDim.y);
+    const int F0 = ytile * kCRows, G0 = blockIdx.x * kCTile;
     const int gl = G0 + 4 * lane;
     int minG = INT_MAX;                                       // lowest rank among the members of the tile's column couples
 #pragma unroll
@@ -338,12 +341,14 @@ couple_kernel(int64_t ld, const double *__restrict__ Rt, T *__restrict__ Vt, T *
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) minG = min(minG, __shfl_xor_sync(0xffffffffu, minG, o));
     const bool col_ok = gl < L.nfo_pad;                       // nfo_pad is a multiple of 4
+#pragma unroll 1
+    for (int half = 0; half < kCRows / kFTile; half++) {
     // phase 1: the four rows of this warp -- couple, parents, skip; the couple diagonal
     int pfs[4], pms[4];
     bool skips[4];
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-        const int fl = warp * 4 + q, F = F0 + fl;
+        const int fl = half * kFTile + warp * 4 + q, F = F0 + fl;
         skips[q] = true; pfs[q] = -1; pms[q] = -1;
         if (F < L.n_fam && G0 < L.own_nf) {
             pfs[q] = L.fam_pf[F]; pms[q] = L.fam_pm[F];
@@ -352,7 +357,7 @@ couple_kernel(int64_t ld, const double *__restrict__ Rt, T *__restrict__ Vt, T *
         if (lane == 0) s_skip[fl] = skips[q];
     }
     if (blockIdx.x == 0 && lane < 4) {                        // diagonal of the couple's members
-        const int F = F0 + warp * 4 + lane;
+        const int F = F0 + half * kFTile + warp * 4 + lane;
         if (F >= L.own_f0 && F < L.own_f0 + L.own_nf) {
             const int pf = L.fam_pf[F], pm = L.fam_pm[F];
             double d = 0.5;
@@ -376,7 +381,7 @@ couple_kernel(int64_t ld, const double *__restrict__ Rt, T *__restrict__ Vt, T *
     // 16-byte peer store over NVLink; the tile is kept in shared memory for the transposed copy
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-        const int fl = warp * 4 + q, F = F0 + fl;
+        const int fl = half * kFTile + warp * 4 + q, F = F0 + fl;
         if (!skips[q] && col_ok) {
             T v[4];
 #pragma unroll
@@ -390,12 +395,20 @@ couple_kernel(int64_t ld, const double *__restrict__ Rt, T *__restrict__ Vt, T *
             if (gl < L.own_nf) store_vec4(vrow + gl, v);       // never into the next rank's couple columns
         }
     }
+    }
     __syncthreads();
-    // transposed, local: Vt[own G, F0 .. F0+32), one couple column per warp iteration, lane = couple row
-    const bool row_ok = (F0 + lane < L.n_fam) && !s_skip[lane];
+    // transposed, local: Vt[own G, F0 .. F0 + kCRows), one couple column per warp iteration, lane = couple
+    // row (the passes back to back: one contiguous run per column)
+    bool row_ok[kCRows / kFTile];
+#pragma unroll
+    for (int h = 0; h < kCRows / kFTile; h++) row_ok[h] = (F0 + h * kFTile + lane < L.n_fam) && !s_skip[h * kFTile + lane];
     const int gl_end = min(kCTile, L.own_nf - G0);
-    for (int g = warp; g < gl_end; g += kThreads / 32)
-        if (row_ok) Vt[(size_t)(G0 + g) * L.nf_pad + F0 + lane] = sV[lane * kCStride + g];
+    for (int g = warp; g < gl_end; g += kThreads / 32) {
+        T *dst = Vt + (size_t)(G0 + g) * L.nf_pad + F0 + lane;
+#pragma unroll
+        for (int h = 0; h < kCRows / kFTile; h++)
+            if (row_ok[h]) dst[h * kFTile] = sV[(h * kFTile + lane) * kCStride + g];
+    }
 }
 
 // =====================================================================================
