@@ -233,10 +233,10 @@ def main():
     i_t = intra_ms.sum() * 1e-3
     achieved = cross_bytes[launched].sum() * K / c_t / 1e9 if c_t > 0 else 0.0
     whole = (cross_bytes.sum() + intra_bytes.sum()) * K / (total_ms * 1e-3) / 1e9
-    # DRAM traffic per launch from `ncu --set full` (profiles/r01/ncu_full_c3_v9_summary.json): a
-    # 39208 x 39114 layer moved 6.165 GB read + 6.110 GB written for 24.54 GB of algorithmic bytes
+    # DRAM traffic per launch from `ncu --set full` (profiles/r01/ncu_full_c3_final_summary.json): a
+    # 39208 x 39114 layer moved 6.166 GB read + 6.111 GB written for 24.54 GB of algorithmic bytes
     # (couples halve the rows that are read and written); scaled to the average launch.
-    traffic_ratio = (6.164859e9 + 6.109968e9) / (4 * 4.0 * 39208 * 39114) if args.numerics == "reference" else None
+    traffic_ratio = (6.165890e9 + 6.110764e9) / (4 * 4.0 * 39208 * 39114) if args.numerics == "reference" else None
     roofline = {"bound": "hbm", "kernel": "cross_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak,
                 "traffic": (traffic_ratio * float(cross_bytes[launched].mean())) if (traffic_ratio and launched.any()) else None,
