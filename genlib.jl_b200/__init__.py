@@ -8,7 +8,8 @@ Usage mirrors the reference (`import GenLib as gen`):
 import os as _os
 
 from .pedigree import Individual, Pedigree, founder, genealogy, pro  # noqa: F401
-from .engine import Engine, PinnedMatrix, Plan, f, phi, phi_arrays, phi_distributed, phiMean  # noqa: F401
+from .engine import (Engine, KinshipMatrix, PinnedMatrix, Plan, f, phi, phi_arrays, phi_distributed,  # noqa: F401
+                     phiMean, sparse_phi)
 from . import synth  # noqa: F401
 from ._lib import GenlibError, LIB_PATH, lib  # noqa: F401
 

@@ -294,14 +294,17 @@ int launch_layers(genlib_engine &E, bool timed) {
     if (expand_smem_max > 227 * 1024) return fail(GENLIB_EINVAL, "couple tile too wide for the expand kernel");
     auto expand_fn = E.world > 1 ? expand_kernel<T, true> : expand_kernel<T, false>;
     CU(cudaFuncSetAttribute(expand_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem_max));
-    CU(cudaFuncSetAttribute(cross_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cross_smem));
-    CU(cudaFuncSetAttribute(cross_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    const bool stored = P.schedule == kScheduleSparsePhi;      // sparse_phi's arithmetic (Float32 halves of stored values)
+    auto cross_fn = stored ? cross_kernel<T, true> : cross_kernel<T, false>;
+    auto couple_fn = stored ? couple_kernel<T, true> : couple_kernel<T, false>;
+    CU(cudaFuncSetAttribute(cross_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cross_smem));
+    CU(cudaFuncSetAttribute(cross_fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CU(cudaFuncSetAttribute(expand_fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     T *V = static_cast<T *>(E.Vrow), *Vt = static_cast<T *>(E.Vt), *Dg = static_cast<T *>(E.Dg);
     constexpr int kCRows = couple_rows<T>();
     const size_t couple_smem = sizeof(T) * kCRows * kCStride;
-    CU(cudaFuncSetAttribute(couple_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)couple_smem));
-    CU(cudaFuncSetAttribute(couple_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CU(cudaFuncSetAttribute(couple_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)couple_smem));
+    CU(cudaFuncSetAttribute(couple_fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     int launches = 0;
     size_t ev = 0;
     for (int t = 0; t < (int)P.layers.size(); t++) {
@@ -316,7 +319,7 @@ int launch_layers(genlib_engine &E, bool timed) {
             const int64_t want = ptiles * ftiles / (4 * 2 * (int64_t)E.sm_count);
             a.pchunk = (int)std::max<int64_t>(std::min<int64_t>(4, ptiles), std::min<int64_t>(kMaxPChunk, want));
             dim3 grid((unsigned)((ptiles + a.pchunk - 1) / a.pchunk), (unsigned)ftiles);
-            cross_kernel<T><<<grid, kThreads, cross_smem, E.stream>>>(A, ld, E.Rt, E.peers, a);
+            cross_fn<<<grid, kThreads, cross_smem, E.stream>>>(A, ld, E.Rt, E.peers, a);
             launches++;
             if (L.carried > 0 && a.own_nm > 0) {
                 dim3 mgrid((unsigned)((a.own_nm + 32 * kMirrorCols - 1) / (32 * kMirrorCols)), (unsigned)((L.rt_rows + kThreads / 32 - 1) / (kThreads / 32)));
@@ -327,7 +330,7 @@ int launch_layers(genlib_engine &E, bool timed) {
         if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
         if (a.own_nf > 0) {
             dim3 grid((unsigned)((a.nfo_pad + kCTile - 1) / kCTile), (unsigned)((L.n_fam + kCRows - 1) / kCRows));
-            couple_kernel<T><<<grid, kThreads, couple_smem, E.stream>>>(ld, E.Rt, Vt, Dg, E.peers, a);
+            couple_fn<<<grid, kThreads, couple_smem, E.stream>>>(ld, E.Rt, Vt, Dg, E.peers, a);
             launches++;
         }
         if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
@@ -396,6 +399,8 @@ int create_engine(const genlib_plan *plan, int numerics, int device, int rank, g
     *out = nullptr;
     if (numerics != GENLIB_NUMERICS_REFERENCE && numerics != GENLIB_NUMERICS_FP64) return fail(GENLIB_EINVAL, "unknown numerics mode");
     const Plan &P = plan->p;
+    if (P.schedule == kScheduleSparsePhi && numerics != GENLIB_NUMERICS_REFERENCE)
+        return fail(GENLIB_EINVAL, "the sparse_phi schedule stores Float32 (numerics must be GENLIB_NUMERICS_REFERENCE)");
     if (rank < 0 || rank >= P.world) return fail(GENLIB_EINVAL, "rank outside the plan's world");
     if (P.world > kMaxWorld) return fail(GENLIB_EINVAL, "the engine supports at most 16 ranks");
     if (P.n_unique == 0) return fail(GENLIB_EINVAL, "empty proband list: nothing to run");
@@ -538,6 +543,11 @@ int genlib_pinned_free(void *ptr) {
 
 int genlib_plan_create(int32_t n, const int32_t *father, const int32_t *mother, int32_t n_pro,
                        const int32_t *proband, int32_t world, genlib_plan **out) {
+    return genlib_plan_create_scheduled(n, father, mother, n_pro, proband, world, GENLIB_SCHEDULE_PHI, out);
+}
+
+int genlib_plan_create_scheduled(int32_t n, const int32_t *father, const int32_t *mother, int32_t n_pro,
+                                 const int32_t *proband, int32_t world, int schedule, genlib_plan **out) {
     if (!out) return fail(GENLIB_EINVAL, "genlib_plan_create: out is null");
     *out = nullptr;
     std::unique_ptr<genlib_plan> pl(new (std::nothrow) genlib_plan);
@@ -547,7 +557,7 @@ int genlib_plan_create(int32_t n, const int32_t *father, const int32_t *mother, 
     int rc;
     try {
         adopt_retired_storage(pl->p);        // the arrays of the last destroyed plan, already paged in
-        rc = build_plan(n, father, mother, n_pro, proband, world, pl->p, err);
+        rc = build_plan(n, father, mother, n_pro, proband, world, schedule, pl->p, err);
     } catch (const std::bad_alloc &) {
         return fail(GENLIB_ENOMEM, "out of host memory while planning");
     }
@@ -563,6 +573,7 @@ void genlib_plan_destroy(genlib_plan *plan) {
     delete plan;
 }
 int32_t genlib_plan_n_unique(const genlib_plan *plan) { return plan ? plan->p.n_unique : -1; }
+int32_t genlib_plan_schedule(const genlib_plan *plan) { return plan ? plan->p.schedule : -1; }
 int32_t genlib_plan_n_layers(const genlib_plan *plan) { return plan ? (int32_t)plan->p.layers.size() : -1; }
 int64_t genlib_plan_capacity(const genlib_plan *plan) { return plan ? plan->p.capacity : -1; }
 int64_t genlib_plan_row_updates(const genlib_plan *plan) { return plan ? plan->p.row_updates : -1; }

@@ -86,6 +86,16 @@ __device__ __forceinline__ void store_vec4(double *p, const double (&v)[4]) {
 }
 // 1/2 x + 1/2 y with ONE binary64 rounding (1/2 y is exact), = Julia's `0 + x/2 + y/2`
 __device__ __forceinline__ double half_sum(double x, double y) { return fma(0.5, x, 0.5 * y); }
+// sparse_phi's `phi[..] / 2` is a FLOAT32 division of a stored Float32 (compute.jl:350-389): it rounds
+// when the stored value is a subnormal with an odd last bit; the sum is Float64 as above.
+__device__ __forceinline__ double half_sum_stored(double x, double y) {
+    return (double)__fmul_rn((float)x, 0.5f) + (double)__fmul_rn((float)y, 0.5f);
+}
+template <bool STORED>
+__device__ __forceinline__ double half_sum_mode(double x, double y) {
+    if constexpr (STORED) return half_sum_stored(x, y);
+    else return half_sum(x, y);
+}
 
 // =====================================================================================
 // cross_kernel: grid (chunks of L.pchunk live-column tiles, own couple tiles), 256 threads.
@@ -143,7 +153,7 @@ __device__ __forceinline__ void lds4(const double *p, double (&d)[4]) {
     d[0] = a.x; d[1] = a.y; d[2] = b.x; d[3] = b.y;
 }
 
-template <typename T>
+template <typename T, bool STORED>     // STORED: the sparse_phi schedule (Float32 halves of stored values)
 __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 2 : 1)
 cross_kernel(T *__restrict__ A, int64_t ld, double *__restrict__ Rt, PeerTable PT, LayerArgs L) {
     extern __shared__ __align__(16) unsigned char cross_smem[];      // [stage][father rows | mother rows][row bytes]
@@ -251,7 +261,7 @@ cross_kernel(T *__restrict__ A, int64_t ld, double *__restrict__ Rt, PeerTable P
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const int col = warp * (kPTile / 8) + g * 4 + ((j + rot0) & 3);
-                    if (fl[col] & kFlagLive) rt[(size_t)col * L.nfo_pad] = half_sum((double)xr[col], (double)yr[col]);
+                    if (fl[col] & kFlagLive) rt[(size_t)col * L.nfo_pad] = half_sum_mode<STORED>((double)xr[col], (double)yr[col]);
                 }
             }
         }
@@ -267,7 +277,7 @@ cross_kernel(T *__restrict__ A, int64_t ld, double *__restrict__ Rt, PeerTable P
                 lds4(reinterpret_cast<const T *>(st + (warp * 4 + q) * RB) + 4 * lane, x);
                 lds4(reinterpret_cast<const T *>(st + (kFTile + warp * 4 + q) * RB) + 4 * lane, y);
 #pragma unroll
-                for (int e = 0; e < 4; e++) r[e] = half_sum(x[e], y[e]);
+                for (int e = 0; e < 4; e++) r[e] = half_sum_mode<STORED>(x[e], y[e]);
                 for (int m = mb[q]; m < me[q]; m++) {
                     store4(A + (int64_t)L.mem_lrow[m] * ld + col0, r);
                     if (L.world > 1) {
@@ -319,7 +329,7 @@ constexpr int kCStride = kCTile + 1;
 // couple rows per CTA: several passes of kFTile rows, so that the transposed copy goes out in 512-byte runs
 template <typename T> __host__ __device__ constexpr int couple_rows() { return (sizeof(T) == 4 ? 4 : 2) * kFTile; }
 
-template <typename T>
+template <typename T, bool STORED>
 __global__ void __launch_bounds__(kThreads, 3)
 couple_kernel(int64_t ld, const double *__restrict__ Rt, T *__restrict__ Vt, T *__restrict__ Dg, PeerTable PT,
               LayerArgs L) {
@@ -362,7 +372,7 @@ couple_kernel(int64_t ld, const double *__restrict__ Rt, T *__restrict__ Vt, T *
             const int pf = L.fam_pf[F], pm = L.fam_pm[F];
             double d = 0.5;
             if (pf >= 0 && pm >= 0)
-                d = fma(0.5, (double)(static_cast<const T *>(PT.A[L.fam_pf_owner[F]]) + (int64_t)L.fam_pf_lrow[F] * ld)[pm], 0.5);
+                d = half_sum_mode<STORED>((double)(static_cast<const T *>(PT.A[L.fam_pf_owner[F]]) + (int64_t)L.fam_pf_lrow[F] * ld)[pm], 1.0);
             Dg[F] = (T)d;
         }
     }
@@ -375,6 +385,10 @@ couple_kernel(int64_t ld, const double *__restrict__ Rt, T *__restrict__ Vt, T *
         if (!skips[q] && col_ok) {
             if (pfs[q] >= 0) load4(Rt + (size_t)(pfs[q] - L.rt_lo) * L.nfo_pad + gl, a[q]);
             if (pms[q] >= 0) load4(Rt + (size_t)(pms[q] - L.rt_lo) * L.nfo_pad + gl, b[q]);
+            if constexpr (STORED) {                              // the STORED (Float32) cross values (compute.jl:331, 363-395)
+#pragma unroll
+                for (int k = 0; k < 4; k++) { a[q][k] = (double)(T)a[q][k]; b[q][k] = (double)(T)b[q][k]; }
+            }
         }
     }
     // phase 3: V[F, own G] goes to the rank that owns couple F (its row block of V): local, or a
@@ -386,7 +400,7 @@ couple_kernel(int64_t ld, const double *__restrict__ Rt, T *__restrict__ Vt, T *
             T v[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                v[k] = (T)half_sum(a[q][k], b[q][k]);
+                v[k] = (T)half_sum_mode<STORED>(a[q][k], b[q][k]);
                 sV[fl * kCStride + 4 * lane + k] = v[k];
             }
             int o = 0;

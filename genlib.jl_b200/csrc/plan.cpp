@@ -119,6 +119,7 @@ struct LineAlloc {
 struct Scratch {
     std::vector<uint8_t> is_pro;
     std::vector<Pre> pre;
+    std::vector<int32_t> seq_order, orient, cstart, clist, depth;   // sparse_phi schedule
     std::vector<int32_t> hist, count, by_layer, cut_size, both_size;
     std::vector<Home> home;
     std::vector<size_t> lstart, pos, mem_pos_of;
@@ -162,19 +163,21 @@ void release_plan_cache() {
 }
 
 static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const int32_t *mother, int32_t n_pro,
-                           const int32_t *proband, int32_t world, Plan &P, std::string &err);
+                           const int32_t *proband, int32_t world, int schedule, Plan &P, std::string &err);
 
 int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t n_pro,
-               const int32_t *proband, int32_t world, Plan &P, std::string &err) {
+               const int32_t *proband, int32_t world, int schedule, Plan &P, std::string &err) {
     std::unique_ptr<Scratch> W = take_scratch();
-    const int rc = build_plan_with(*W, n, father, mother, n_pro, proband, world, P, err);
+    const int rc = build_plan_with(*W, n, father, mother, n_pro, proband, world, schedule, P, err);
     give_scratch(std::move(W));
     return rc;
 }
 
 static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const int32_t *mother, int32_t n_pro,
-                           const int32_t *proband, int32_t world, Plan &P, std::string &err) {
+                           const int32_t *proband, int32_t world, int schedule, Plan &P, std::string &err) {
     P.reset();
+    if (schedule != kSchedulePhi && schedule != kScheduleSparsePhi) { err = "unknown schedule"; return GENLIB_EINVAL; }
+    P.schedule = schedule;
     if (n < 0 || n_pro < 0 || world < 1 || (n > 0 && (!father || !mother)) || (n_pro > 0 && !proband)) {
         err = "genlib_plan_create: null pointer or negative size";
         return GENLIB_EINVAL;
@@ -229,6 +232,70 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
             if (pp.rl > px.rl + 1) pp.rl = px.rl + 1;
         }
     }
+    // Schedule of sparse_phi (compute.jl:335-439): individuals are processed in the order of a queue
+    // that starts with the founders and receives a child when its last parent has been processed --
+    // i.e. by depth below the founders, ties in queue order -- and of a pair, the one processed LATER
+    // is climbed.  The layer is then the depth, `seq` (the position in that queue) replaces the rank
+    // wherever the kernels decide who is climbed, and eviction is sparse_phi's own rule (:400-430).
+    // The sweep above marked the ancestors of the probands (branching, :323); re-label them.
+    const bool by_seq = schedule == kScheduleSparsePhi;         // members of a layer in processing order
+    std::vector<int32_t> &seq_order = W.seq_order; seq_order.clear();
+    std::vector<int32_t> &orient = W.orient;
+    if (schedule == kScheduleSparsePhi) {
+        std::vector<int32_t> &cstart = W.cstart, &clist = W.clist, &depth = W.depth;
+        cstart.assign((size_t)n + 2, 0);
+        depth.assign((size_t)n, 0);
+        int32_t dmax = 0;
+        for (int32_t x = 0; x < n; x++) {                       // parents precede children
+            if (pre[x].h < 0) continue;
+            const int32_t f = father[x], m = mother[x];
+            int32_t d = 0;
+            if (f >= 0) { d = std::max(d, depth[f] + 1); cstart[(size_t)f + 2]++; }
+            if (m >= 0 && m != f) { d = std::max(d, depth[m] + 1); cstart[(size_t)m + 2]++; }
+            depth[x] = d; dmax = std::max(dmax, d);
+        }
+        for (int32_t x = 0; x < n; x++) cstart[(size_t)x + 2] += cstart[(size_t)x + 1];
+        clist.resize((size_t)cstart[(size_t)n + 1]);
+        for (int32_t x = 0; x < n; x++) {                       // children lists in rank order (_index_pedigree, :176-183)
+            if (pre[x].h < 0) continue;
+            const int32_t f = father[x], m = mother[x];
+            if (f >= 0) clist[(size_t)cstart[(size_t)f + 1]++] = x;
+            if (m >= 0 && m != f) clist[(size_t)cstart[(size_t)m + 1]++] = x;
+        }                                                       // now children of p = clist[cstart[p] .. cstart[p+1])
+        orient.assign((size_t)n, -1);
+        seq_order.reserve(hist.empty() ? 0 : (size_t)n);
+        for (int32_t x = 0; x < n; x++)                         // founder(isolated_pedigree): rank order (:335-339)
+            if (pre[x].h >= 0 && father[x] < 0 && mother[x] < 0) seq_order.push_back(x);
+        for (size_t head = 0; head < seq_order.size(); head++) {
+            const int32_t i = seq_order[head];
+            orient[i] = (int32_t)head;                          // processed: founder_index != 0 from here on
+            for (int32_t k = cstart[i]; k < cstart[(size_t)i + 1]; k++) {
+                const int32_t c = clist[(size_t)k], f = father[c], m = mother[c];
+                if (f >= 0 && m >= 0 && f != m) { if (orient[f] >= 0 && orient[m] >= 0) seq_order.push_back(c); }
+                else seq_order.push_back(c);
+            }
+        }
+        int32_t last_depth = 0;
+        for (int32_t i : seq_order) {                           // the queue order is sorted by depth (asserted, not assumed)
+            if (depth[i] < last_depth) { err = "sparse_phi schedule: queue order is not sorted by depth"; return GENLIB_EINVAL; }
+            last_depth = depth[i];
+        }
+        std::fill(hist.begin(), hist.end(), 0);
+        hist.resize((size_t)dmax + 1, 0);
+        hmax = dmax;
+        for (int32_t x = 0; x < n; x++) {
+            if (pre[x].h < 0) continue;
+            pre[x].h = dmax - depth[x];                          // layer = S-1-h = depth
+            pre[x].minch = INT_MAX;
+            pre[x].rl = pre[x].h;                                // the reference's cut counts do not apply
+            hist[(size_t)pre[x].h]++;
+        }
+        for (int32_t x = 0; x < n; x++) {                       // last child: the deepest one
+            if (pre[x].h < 0) continue;
+            const int32_t par[2] = {father[x], mother[x]};
+            for (int32_t p : par) if (p >= 0 && pre[p].minch > pre[x].h) pre[p].minch = pre[x].h;
+        }
+    }
     const int32_t S = hmax + 1;
     std::vector<int32_t> &count = W.count; count.assign((size_t)S + 1, 0);
     for (int32_t k = 0; k < S; k++) count[S - 1 - k] = hist[k];
@@ -242,7 +309,9 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
     std::vector<Home> &home = W.home; home.resize((size_t)n);     // entries outside the plan are never read
     {
         std::vector<size_t> &pos = W.pos; pos.assign(lstart.begin(), lstart.end() - 1);
-        for (int32_t x = 0; x < n; x++) {
+        const int32_t n_visit = by_seq ? (int32_t)seq_order.size() : n;
+        for (int32_t v = 0; v < n_visit; v++) {
+            const int32_t x = by_seq ? seq_order[(size_t)v] : v;
             const Pre px = pre[x];
             if (px.h < 0) continue;
             const int32_t lx = S - 1 - px.h, ref_last = S - 1 - px.rl;
@@ -512,7 +581,7 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
                 Home &hx = home[x];
                 hx.slot = s; hx.lrow = lr; hx.owner = (int8_t)g;
                 if (guests) { born_layer[x] = t; mem_pos_of[x] = L.mem_off + (size_t)q; }
-                mi[q] = x; ms[q] = s; mf[q] = newid[f]; ml[q] = lr;
+                mi[q] = by_seq ? orient[x] : x; ms[q] = s; mf[q] = newid[f]; ml[q] = lr;
             }
         }
         P.fam_pf.resize(L.fam_off + (size_t)nf, -1); P.fam_pm.resize(L.fam_off + (size_t)nf, -1);

@@ -25,6 +25,13 @@ constexpr int kMaxFamily = 32;   // sibships larger than this are split (bounds 
 constexpr int kSlotLine = 32;     // column slots are allocated and recycled in lines of this many (128 B of a float row)
 constexpr int kMaxTileFam = 64;  // couples per member tile (bounds the couple tile staged by the expand kernel)
 
+// Which reference function's floating-point schedule the plan reproduces:
+//   phi        (compute.jl:233-304)  layers by height above the probands, the higher RANK is climbed,
+//                                    one Float32 rounding per step (unrounded Float64 inside a step)
+//   sparse_phi (compute.jl:321-447)  layers by depth below the founders, the individual processed
+//                                    later by its queue is climbed, every stored entry is Float32
+constexpr int kSchedulePhi = 0, kScheduleSparsePhi = 1;
+
 constexpr uint8_t kFlagLive = 1;     // slot holds an individual that is live before the step
 constexpr uint8_t kFlagCarried = 2;  // ... and stays live after it
 
@@ -45,7 +52,7 @@ struct Layer {
 };
 
 struct Plan {
-    int32_t n = 0, n_unique = 0, world = 1;
+    int32_t n = 0, n_unique = 0, world = 1, schedule = kSchedulePhi;
     int64_t capacity = 0;             // W, multiple of kPTile; also the leading dimension
     int64_t row_updates = 0;
     double alg_elems = 0;
@@ -92,7 +99,7 @@ struct Plan {
     }
     void reset() {                     // empty plan, capacities kept
         each_array([](auto &v) { v.clear(); });
-        n = n_unique = 0; world = 1; capacity = row_updates = 0; alg_elems = 0;
+        n = n_unique = 0; world = 1; schedule = kSchedulePhi; capacity = row_updates = 0; alg_elems = 0;
         rt_elems_max = v_elems_max = 0;
     }
 };
@@ -109,6 +116,6 @@ int set_error(int code, const std::string &msg);
 
 // Returns 0 or a GENLIB_E* status; `err` receives a message.
 int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t n_pro,
-               const int32_t *proband, int32_t world, Plan &plan, std::string &err);
+               const int32_t *proband, int32_t world, int schedule, Plan &plan, std::string &err);
 
 }  // namespace genlib

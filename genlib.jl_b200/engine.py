@@ -20,17 +20,19 @@ from .pedigree import Pedigree, pro
 class Plan:
     """Host schedule (levels, Kirkpatrick frontier, slots). Needs no GPU."""
 
-    def __init__(self, father, mother, proband_ranks, world: int = 1):
+    def __init__(self, father, mother, proband_ranks, world: int = 1, schedule: str = "phi"):
         self.father = np.ascontiguousarray(father, np.int32)
         self.mother = np.ascontiguousarray(mother, np.int32)
         self.probands = np.ascontiguousarray(proband_ranks, np.int32)
         if len(self.father) != len(self.mother):
             raise ValueError("father and mother must have the same length")
         h = C.c_void_p()
-        check(lib().genlib_plan_create(len(self.father), ptr(self.father), ptr(self.mother),
-                                       len(self.probands), ptr(self.probands), world, C.byref(h)))
+        check(lib().genlib_plan_create_scheduled(len(self.father), ptr(self.father), ptr(self.mother),
+                                                 len(self.probands), ptr(self.probands), world,
+                                                 _lib.SCHEDULES[schedule], C.byref(h)))
         self._h = h
         self.world = world
+        self.schedule = schedule
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -322,8 +324,77 @@ def f(pedigree: Pedigree, IDs, *, device: int = -1) -> np.ndarray:
     return out
 
 
+class KinshipMatrix:
+    """gen.KinshipMatrix (src/compute.jl:31-46): the kinships `sparse_phi` keeps, indexed by ID.
+
+    Only the probands are left when `sparse_phi` returns, each with its self-kinship and its
+    non-zero kinships towards higher-ranked probands (src/compute.jl:363-395)."""
+
+    def __init__(self, ids: np.ndarray, ranks: np.ndarray, dense: np.ndarray):
+        order = np.argsort(ranks, kind="stable")
+        self._ids = np.asarray(ids)[order]
+        self._pos = {int(i): k for k, i in enumerate(self._ids)}
+        self._dense = np.ascontiguousarray(np.asarray(dense, np.float32)[np.ix_(order, order)])
+
+    def __getitem__(self, key) -> np.float32:
+        a, b = key
+        return self._dense[self._pos[int(a)], self._pos[int(b)]]     # KeyError on an unknown ID, like the Dict
+
+    @property
+    def stored(self) -> int:
+        """Entries the reference's Dict-of-Dicts holds: the diagonal and the non-zero pairs, once each."""
+        return int(np.count_nonzero(np.triu(self._dense, 1))) + len(self._ids)
+
+    def to_dict(self) -> dict:
+        """{lower-ranked ID: {higher-ranked ID: kinship}}, the layout of `KinshipMatrix.dict`."""
+        out = {}
+        for k, i in enumerate(self._ids):
+            row = self._dense[k]
+            out[int(i)] = {int(self._ids[j]): row[j] for j in range(k, len(self._ids)) if j == k or row[j] != 0}
+        return out
+
+    def __len__(self) -> int:
+        return len(self._ids)
+
+    def __repr__(self) -> str:                                            # src/compute.jl:42-46
+        return f"{len(self)}\u00d7{len(self)} KinshipMatrix with {self.stored} stored entries."
+
+
+def sparse_phi(pedigree: Pedigree, probandIDs=None, *, device: int = -1) -> KinshipMatrix:
+    """gen.sparse_phi(pedigree, probandIDs = pro(pedigree)) (src/compute.jl:321-447) on the GPU.
+
+    Same engine, planned for sparse_phi's own floating-point schedule (processing order of its
+    queue, the later-processed individual of a pair is climbed, every stored kinship a Float32),
+    so the values are bit-identical to the reference's KinshipMatrix.  SURVEY.md 8(f) N2."""
+    ids = pro(pedigree) if probandIDs is None else np.asarray(probandIDs, np.int64)
+    ranks = pedigree.rank_of(ids)                                         # KeyError on an unknown ID
+    _, first = np.unique(ranks, return_index=True)                        # duplicates collapse (Dict keys)
+    first.sort()
+    plan = Plan(pedigree.father, pedigree.mother, ranks, schedule="sparse_phi")
+    n = plan.n_unique
+    if n == 0:
+        return KinshipMatrix(np.zeros(0, np.int64), np.zeros(0, np.int32), np.zeros((0, 0), np.float32))
+    eng = Engine(plan, "reference", device)
+    try:
+        eng.run()
+        dense = eng.fetch()
+    finally:
+        eng.close()
+    return KinshipMatrix(np.asarray(ids)[first], ranks[first], dense)
+
+
 def phiMean(phi_matrix) -> np.float32:
-    """gen.phiMean(::Matrix{Float32}) (src/compute.jl:454-459), host side."""
+    """gen.phiMean(::Matrix{Float32}) (src/compute.jl:454-459) and gen.phiMean(::KinshipMatrix)
+    (:466-472), host side.  The reference sums the KinshipMatrix in Dict iteration order; here the
+    stored entries are summed in rank order (Float32), which is the same number whenever the sum is
+    exact -- e.g. the reference's own test, test/runtests.jl:55."""
+    if isinstance(phi_matrix, KinshipMatrix):
+        d, n = phi_matrix._dense, len(phi_matrix)
+        total = np.float32(0)
+        for k in range(n):
+            total = np.float32(total + d[k, k:].sum(dtype=np.float32))
+        total = np.float32(total - np.trace(d, dtype=np.float32))
+        return np.float32(total / (n * (n - 1) / 2))
     m = np.asarray(phi_matrix, np.float32)
     total = m.sum(dtype=np.float32) - np.trace(m, dtype=np.float32)
     return np.float32(total / np.float32(m.size - m.shape[0]))

@@ -90,4 +90,46 @@ function phi(pedigree::GenLib.Pedigree, probandIDs::Vector{Int} = GenLib.pro(ped
     end
 end
 
+"""
+    sparse_phi(pedigree, probandIDs = pro(pedigree)) -> GenLib.KinshipMatrix
+
+`gen.sparse_phi` (src/compute.jl:321-447) on the GPU: the same engine, planned for sparse_phi's own
+floating-point schedule (`GENLIB_SCHEDULE_SPARSE_PHI`), so the values are the reference's bits.  The
+dense result is folded back into the reference's `KinshipMatrix` (Dict keyed lower rank -> higher rank,
+zeros not stored, src/compute.jl:31-40, 391-394).
+"""
+function sparse_phi(pedigree::GenLib.Pedigree, probandIDs::Vector{Int} = GenLib.pro(pedigree); device::Integer = -1)
+    father, mother = flatten(pedigree)
+    ranks = Int32[pedigree[ID].rank - 1 for ID in probandIDs]           # KeyError on unknown ID
+    plan = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:genlib_plan_create_scheduled, libgenlib[]), Cint,
+                (Int32, Ptr{Int32}, Ptr{Int32}, Int32, Ptr{Int32}, Int32, Cint, Ptr{Ptr{Cvoid}}),
+                length(father), father, mother, length(ranks), ranks, 1, 1, plan))
+    try
+        n = ccall((:genlib_plan_n_unique, libgenlib[]), Int32, (Ptr{Cvoid},), plan[])
+        dense = Matrix{Float32}(undef, n, n)
+        engine = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:genlib_engine_create, libgenlib[]), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Ptr{Cvoid}}),
+                    plan[], 0, device, engine))
+        try
+            check(ccall((:genlib_engine_run, libgenlib[]), Cint, (Ptr{Cvoid}, Cint), engine[], 0))
+            GC.@preserve dense check(ccall((:genlib_engine_fetch, libgenlib[]), Cint,
+                                           (Ptr{Cvoid}, Ptr{Cvoid}, Cint), engine[], dense, 0))
+        finally
+            ccall((:genlib_engine_destroy, libgenlib[]), Cvoid, (Ptr{Cvoid},), engine[])
+        end
+        unique_IDs = unique(probandIDs)                                  # output order = first occurrence
+        isolated = GenLib.branching(pedigree, pro = probandIDs)          # sparse_phi's ranks (src/compute.jl:323)
+        rank = Dict{Int32, Int}(ID => isolated[ID].rank for ID in unique_IDs)
+        dict = Dict{Int32, Dict{Int32, Float32}}(rank[ID] => Dict{Int32, Float32}() for ID in unique_IDs)
+        for (a, IDa) in enumerate(unique_IDs), (b, IDb) in enumerate(unique_IDs)
+            (ra, rb) = (rank[IDa], rank[IDb])
+            (ra == rb || (ra < rb && dense[a, b] != 0)) && (dict[ra][rb] = dense[a, b])
+        end
+        return GenLib.KinshipMatrix(dict, rank)
+    finally
+        ccall((:genlib_plan_destroy, libgenlib[]), Cvoid, (Ptr{Cvoid},), plan[])
+    end
+end
+
 end # module

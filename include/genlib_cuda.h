@@ -127,6 +127,18 @@ int genlib_pedigree_ranks(const genlib_pedigree *ped, int64_t n, const int64_t *
  * for that many ranks. */
 int genlib_plan_create(int32_t n, const int32_t *father, const int32_t *mother, int32_t n_pro,
                        const int32_t *proband, int32_t world, genlib_plan **out);
+/* The same plan for the floating-point schedule of another reference function:
+ *   GENLIB_SCHEDULE_PHI         phi, src/compute.jl:233-304 (= genlib_plan_create)
+ *   GENLIB_SCHEDULE_SPARSE_PHI  sparse_phi, src/compute.jl:321-447: individuals are processed by a
+ *       queue from the founders (:335-339, :431-439), of a pair the one processed later is climbed
+ *       (:363-395), every stored kinship is a Float32 (:331), rows are evicted when the last child has
+ *       been processed (:400-430).  The engine then returns, densely, the values `sparse_phi` keeps
+ *       for the probands; numerics must be GENLIB_NUMERICS_REFERENCE. */
+#define GENLIB_SCHEDULE_PHI 0
+#define GENLIB_SCHEDULE_SPARSE_PHI 1
+int genlib_plan_create_scheduled(int32_t n, const int32_t *father, const int32_t *mother, int32_t n_pro,
+                                 const int32_t *proband, int32_t world, int schedule, genlib_plan **out);
+int32_t genlib_plan_schedule(const genlib_plan *plan);
 void genlib_plan_destroy(genlib_plan *plan);
 int32_t genlib_plan_n_unique(const genlib_plan *plan);
 int32_t genlib_plan_n_layers(const genlib_plan *plan);

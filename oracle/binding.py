@@ -44,6 +44,8 @@ def lib():
         L.oracle_phi_ranks.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                        C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_int,
                                        C.c_void_p, C.c_int]
+        L.oracle_sparse_phi_ranks.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                              C.POINTER(C.c_int), C.POINTER(C.c_int64)]
         L.oracle_set_time_budget.argtypes = [C.c_double]
         L.oracle_phi_mean.restype = C.c_double
         L.oracle_phi_mean.argtypes = [C.c_void_p, C.c_int]
@@ -147,6 +149,22 @@ def phi_ranks(father, mother, pro_ranks, nthreads: int = 0, max_steps: int = -1)
         u = nu.value
         res = out.reshape(-1)[: u * u].reshape(u, u).copy()
     return res, steps[:rc].copy()
+
+
+def sparse_phi_ranks(father, mother, pro_ranks):
+    """gen.sparse_phi on flat rank arrays: (dense n_unique x n_unique Float32 values of the
+    KinshipMatrix, number of stored entries).  src/compute.jl:321-447."""
+    father = np.ascontiguousarray(father, np.int32)
+    mother = np.ascontiguousarray(mother, np.int32)
+    pro = np.ascontiguousarray(pro_ranks, np.int32)
+    nu, stored = C.c_int(0), C.c_int64(0)
+    out = np.zeros((len(pro), len(pro)), np.float32)
+    rc = lib().oracle_sparse_phi_ranks(len(father), _p(father), _p(mother), len(pro), _p(pro), _p(out),
+                                       C.byref(nu), C.byref(stored))
+    if rc < 0:
+        raise KeyError(f"oracle_sparse_phi_ranks status {rc}")
+    u = nu.value
+    return out.reshape(-1)[: u * u].reshape(u, u).copy(), int(stored.value)
 
 
 def bounded_steps(father, mother, pro_ranks, seconds: float, nthreads: int = 0):

@@ -23,6 +23,7 @@
  *   src/compute.jl:236-251  cut vertices                  -> build_cuts()
  *   src/compute.jl:271-302  step loop, threaded pair loop -> oracle_phi_ranks()
  *   src/compute.jl:454-459  phiMean                       -> oracle_phi_mean()
+ *   src/compute.jl:321-447  sparse_phi ("next" row N2)     -> oracle_sparse_phi_ranks()
  *
  * Parity pinning: geneaJi is pinned by the reference's own known-answer test
  * (test/runtests.jl:47-53, checked in tests/test_oracle.py).  genea140 has no
@@ -507,4 +508,125 @@ int oracle_num_threads(void) {
     if (sched_getaffinity(0, sizeof set, &set) == 0) { int c = CPU_COUNT(&set); if (c > 0) return c; }
     long c = sysconf(_SC_NPROCESSORS_ONLN);
     return c > 0 ? (int)c : 1;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * gen.sparse_phi(pedigree, probandIDs) -- src/compute.jl:321-447, restated on rank arrays.
+ *
+ * The reference keeps Dict{rank, Dict{rank, Float32}} keyed lower rank -> higher rank and never
+ * stores a zero (:391-394); a missing entry contributes nothing (:350-358, :367-389).  Here the
+ * same values live in a dense symmetric Float32 matrix over the LIVE individuals (0 = missing),
+ * which is the same arithmetic: adding a stored 0/2 or skipping a missing key both leave the
+ * Float64 accumulator unchanged.  Everything else is line by line:
+ *   :323      branching(pedigree, pro = probandIDs): only ancestors of the probands
+ *   :176-183  children lists in rank order (_index_pedigree)
+ *   :335-339  the queue starts with the founders of the isolated pedigree
+ *   :349-361  self kinship 0.5 + phi[father, mother] / 2
+ *   :363-395  kinship with every individual still to visit, `x / 2` is a FLOAT32 division,
+ *             the accumulator is Float64, the store rounds to Float32
+ *   :397-430  children_to_process, eviction of non-proband parents
+ *   :431-439  a child enters the queue when both known parents are processed
+ * out: n_unique x n_unique (probands in first-occurrence order), stored: entries a
+ * KinshipMatrix would hold (diagonal + non-zero upper pairs), for the `show` line (:42-46).
+ * Returns 0 or a negative ORACLE_* code.
+ * --------------------------------------------------------------------------------------------- */
+int oracle_sparse_phi_ranks(int n, const int32_t *father, const int32_t *mother, int n_pro,
+                            const int32_t *pro_rank, float *out, int *n_unique, int64_t *stored) {
+    uint8_t *is_pro = calloc((size_t)n + 1, 1), *keep = calloc((size_t)n + 1, 1);
+    int32_t *uniq = malloc((size_t)(n_pro + 1) * sizeof *uniq);
+    int nu = 0;
+    for (int t = 0; t < n_pro; t++) {
+        if (pro_rank[t] < 0 || pro_rank[t] >= n) { free(is_pro); free(keep); free(uniq); return -ORACLE_EKEY; }
+        if (!is_pro[pro_rank[t]]) { is_pro[pro_rank[t]] = 1; uniq[nu++] = pro_rank[t]; }
+    }
+    if (n_unique) *n_unique = nu;
+    /* :323 branching: ancestors of the probands (parents have lower ranks) */
+    for (int t = 0; t < nu; t++) keep[uniq[t]] = 1;
+    for (int x = n - 1; x >= 0; x--) if (keep[x]) {
+        if (father[x] >= 0) keep[father[x]] = 1;
+        if (mother[x] >= 0) keep[mother[x]] = 1;
+    }
+    /* :176-183 children in rank order */
+    int32_t *cstart = calloc((size_t)n + 2, sizeof *cstart);
+    for (int x = 0; x < n; x++) if (keep[x]) {
+        if (father[x] >= 0) cstart[father[x] + 1]++;
+        if (mother[x] >= 0) cstart[mother[x] + 1]++;
+    }
+    for (int x = 0; x < n; x++) cstart[x + 1] += cstart[x];
+    int32_t *clist = malloc(((size_t)cstart[n] + 1) * sizeof *clist), *cfill = malloc(((size_t)n + 1) * sizeof *cfill);
+    memcpy(cfill, cstart, (size_t)n * sizeof *cfill);
+    for (int x = 0; x < n; x++) if (keep[x]) {
+        if (father[x] >= 0) clist[cfill[father[x]]++] = x;
+        if (mother[x] >= 0) clist[cfill[mother[x]]++] = x;
+    }
+    /* the queue order does not depend on the values: run it once to size the live set */
+    int32_t *queue = malloc(((size_t)n + 1) * sizeof *queue), *todo = malloc(((size_t)n + 1) * sizeof *todo);
+    uint8_t *done = calloc((size_t)n + 1, 1);
+    int qn = 0;
+    for (int x = 0; x < n; x++) if (keep[x] && father[x] < 0 && mother[x] < 0) queue[qn++] = x;   /* :335-339 */
+    int live = 0, max_live = 0;
+    for (int h = 0; h < qn; h++) {
+        int i = queue[h];
+        live++; if (live > max_live) max_live = live;
+        done[i] = 1;
+        todo[i] = cstart[i + 1] - cstart[i];
+        int par[2] = { father[i], mother[i] };
+        for (int s = 0; s < 2; s++) if (par[s] >= 0 && !is_pro[par[s]] && --todo[par[s]] == 0) live--;
+        for (int k = cstart[i]; k < cstart[i + 1]; k++) {       /* :431-439 */
+            int c = clist[k];
+            if (father[c] >= 0 && mother[c] >= 0) { if (done[father[c]] && done[mother[c]]) queue[qn++] = c; }
+            else queue[qn++] = c;
+        }
+    }
+    const size_t W = (size_t)max_live + 1;
+    float *M = calloc(W * W, sizeof *M);                         /* kinships of the live individuals */
+    int32_t *slot = malloc(((size_t)n + 1) * sizeof *slot), *free_slots = malloc(W * sizeof *free_slots);
+    int32_t *visit = malloc(W * sizeof *visit), *vpos = malloc(((size_t)n + 1) * sizeof *vpos);   /* ranks_to_visit */
+    if (!M || !slot || !free_slots || !visit || !vpos) return -ORACLE_ENOMEM;
+    int nfree = 0, nvisit = 0;
+    for (size_t k = 0; k < W; k++) free_slots[nfree++] = (int32_t)(W - 1 - k);
+    memset(done, 0, (size_t)n + 1);
+    for (int h = 0; h < qn; h++) {
+        const int i = queue[h], f = father[i], m = mother[i];
+        const int si = free_slots[--nfree];
+        slot[i] = si;
+        for (size_t k = 0; k < W; k++) { M[(size_t)si * W + k] = 0.f; M[k * W + (size_t)si] = 0.f; }
+        double coefficient = 0.5;                                /* :349-361 */
+        if (f >= 0 && m >= 0) coefficient += (double)(float)(M[(size_t)slot[f] * W + slot[m]] / 2.0f);
+        M[(size_t)si * W + si] = (float)coefficient;
+        for (int v = 0; v < nvisit; v++) {                       /* :363-395 */
+            const int j = visit[v], sj = slot[j];
+            coefficient = 0.;
+            if (f >= 0) coefficient += (double)(float)(M[(size_t)sj * W + slot[f]] / 2.0f);
+            if (m >= 0) coefficient += (double)(float)(M[(size_t)sj * W + slot[m]] / 2.0f);
+            if (coefficient > 0.) { const float c32 = (float)coefficient; M[(size_t)sj * W + si] = c32; M[(size_t)si * W + sj] = c32; }
+        }
+        vpos[i] = nvisit; visit[nvisit++] = i;                   /* :397-399 */
+        done[i] = 1;
+        todo[i] = cstart[i + 1] - cstart[i];
+        int par[2] = { f, m };
+        for (int s = 0; s < 2; s++) {                            /* :400-430 */
+            const int p = par[s];
+            if (p < 0 || is_pro[p]) continue;
+            if (--todo[p] == 0) {
+                const int last = visit[--nvisit];                /* delete!(ranks_to_visit, p) */
+                visit[vpos[p]] = last; vpos[last] = vpos[p];
+                free_slots[nfree++] = slot[p];                   /* its row and column are dropped */
+                slot[p] = -1;
+            }
+        }
+    }
+    if (out) {
+        int64_t nz = 0;
+        for (int a = 0; a < nu; a++)
+            for (int b = 0; b < nu; b++) {
+                const float v = M[(size_t)slot[uniq[a]] * W + slot[uniq[b]]];
+                out[(size_t)a * nu + b] = v;
+                if (a == b || (uniq[a] < uniq[b] && v != 0.f)) nz++;
+            }
+        if (stored) *stored = nz;
+    }
+    free(is_pro); free(keep); free(uniq); free(cstart); free(clist); free(cfill); free(queue); free(todo);
+    free(done); free(M); free(slot); free(free_slots); free(visit); free(vpos);
+    return ORACLE_OK;
 }

@@ -33,12 +33,18 @@ def replay(plan, numerics: str = "reference", check_poison: bool = True, on_laye
         zero = np.zeros((1, len(live)))
         rows_f = np.where(pf[:, None] >= 0, Al[np.maximum(pf, 0)], zero)
         rows_m = np.where(pm[:, None] >= 0, Al[np.maximum(pm, 0)], zero)
-        R = 0.5 * rows_f + 0.5 * rows_m                    # (nf, |live|)
+        sparse = getattr(plan, "schedule", "phi") == "sparse_phi"
+        if sparse:      # `x / 2` is a Float32 division of a stored Float32 (compute.jl:350-389), the sum Float64
+            R = (rows_f.astype(np.float32) * np.float32(0.5)).astype(np.float64) \
+                + (rows_m.astype(np.float32) * np.float32(0.5)).astype(np.float64)
+        else:
+            R = 0.5 * rows_f + 0.5 * rows_m                # (nf, |live|)
         if check_poison and len(live):
             assert not np.isnan(R).any(), f"layer {t}: cross block read an unwritten entry"
-        # Rt indexed by slot for the intra gather
+        # Rt indexed by slot for the intra gather; the sparse_phi schedule reads the STORED (Float32)
+        # cross values there (compute.jl:331, 363-395), phi the unrounded ones (compute.jl:107, 296)
         Rt = np.full((W, nf), np.nan)
-        Rt[live] = R.T
+        Rt[live] = R.T.astype(np.float32).astype(np.float64) if sparse else R.T
         # rows/columns new x carried, rounded once
         if len(carried):
             pos = np.searchsorted(live, carried)
@@ -47,8 +53,12 @@ def replay(plan, numerics: str = "reference", check_poison: bool = True, on_laye
             A[np.ix_(carried, slot)] = blk.T
         # ---- intra: V[F, G] = 1/2 Rt[pf F, G] + 1/2 Rt[pm F, G] ----
         zf = np.zeros((1, nf))
-        V = 0.5 * np.where(pf[:, None] >= 0, Rt[np.maximum(pf, 0)], zf) \
-            + 0.5 * np.where(pm[:, None] >= 0, Rt[np.maximum(pm, 0)], zf)   # (nf, nf)
+        Vf, Vm = np.where(pf[:, None] >= 0, Rt[np.maximum(pf, 0)], zf), np.where(pm[:, None] >= 0, Rt[np.maximum(pm, 0)], zf)
+        if sparse:
+            V = (Vf.astype(np.float32) * np.float32(0.5)).astype(np.float64) \
+                + (Vm.astype(np.float32) * np.float32(0.5)).astype(np.float64)
+        else:
+            V = 0.5 * Vf + 0.5 * Vm                         # (nf, nf)
         if check_poison:
             assert not np.isnan(V).any(), f"layer {t}: intra block read an unwritten entry"
         Vab = V[np.ix_(fam, fam)]                          # row member climbed first
@@ -57,7 +67,8 @@ def replay(plan, numerics: str = "reference", check_poison: bool = True, on_laye
         both = (pf >= 0) & (pm >= 0)
         dv = np.full(nf, 0.5)
         if both.any():
-            dv[both] = 0.5 + 0.5 * A[pf[both], pm[both]].astype(np.float64)
+            dv[both] = 0.5 + ((A[pf[both], pm[both]].astype(np.float32) * np.float32(0.5)).astype(np.float64) if sparse
+                              else 0.5 * A[pf[both], pm[both]].astype(np.float64))
         blk[np.arange(n), np.arange(n)] = dv[fam]
         A[np.ix_(slot, slot)] = blk.astype(T)
         if on_layer is not None:

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from plan_replay import replay
-from util import exact_kinship, random_pedigree
+from util import exact_kinship, ladder_pedigree, random_pedigree
 
 pytestmark = pytest.mark.gpu
 
@@ -235,3 +235,78 @@ def test_inbreeding_f(gen, ob):
         x = ped[int(ID)]
         want = 0.0 if x.father is None or x.mother is None else o.phi_pair(x.father.ID, x.mother.ID)
         assert v == np.float32(want)
+
+
+# ---- gen.sparse_phi: the same engine on sparse_phi's own schedule ----------
+
+def test_sparse_phi_geneaji_golden(gen):
+    ped = gen.genealogy(gen.geneaJi)
+    k = gen.sparse_phi(ped)
+    assert gen.phiMean(k) == np.float32(0.171875)                                # test/runtests.jl:55
+    assert repr(k) == "3×3 KinshipMatrix with 6 stored entries."                # :56
+    assert k[1, 2] == np.float32(0.37109375)                                     # :57
+    assert_bit_equal(np.array([[k[a, b] for b in (1, 2, 29)] for a in (1, 2, 29)], np.float32), GENEAJI_PHI)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_sparse_phi_random_pedigrees(gen, ob, seed):
+    rng = np.random.default_rng(300 + seed)
+    n = int(rng.integers(100, 1500))
+    rec = random_pedigree(rng, n, int(rng.integers(3, 30)), window=int(rng.choice([0, 0, 40, 120])))
+    ped = gen.genealogy(rec)
+    pro = rng.permutation(ped.ids)[: int(rng.integers(2, min(n, 200)))]
+    ranks = ped.rank_of(pro)
+    want, stored = ob.sparse_phi_ranks(ped.father, ped.mother, ranks)
+    k = gen.sparse_phi(ped, pro)
+    order = np.argsort(ranks, kind="stable")                                     # the KinshipMatrix is kept in rank order
+    assert_bit_equal(k._dense, np.ascontiguousarray(want[np.ix_(order, order)]))
+    assert k.stored == stored and len(k) == len(pro)
+    assert k[int(pro[0]), int(pro[-1])] == want[0, -1]
+
+
+def test_sparse_phi_deep_pedigrees_and_subnormals(gen, ob):
+    s = gen.synth.generate(16 * 60, 60, 16, alpha=0.2, overlap=1, seed=11)
+    ped = gen.genealogy(s.as_columns())
+    ranks = ped.rank_of(s.probands)
+    want, _ = ob.sparse_phi_ranks(ped.father, ped.mother, ranks)
+    plan = gen.Plan(ped.father, ped.mother, ranks, schedule="sparse_phi")
+    eng = gen.Engine(plan)
+    eng.run()
+    assert_bit_equal(eng.fetch(), want)
+    eng.close()
+    assert not np.array_equal(gen.phi(ped, s.probands), want)                    # phi rounds elsewhere
+    cols, pro = ladder_pedigree(73)                                              # Float32 halving of subnormals
+    ped = gen.genealogy(cols)
+    ranks = ped.rank_of(pro)
+    want, _ = ob.sparse_phi_ranks(ped.father, ped.mother, ranks)
+    plan = gen.Plan(ped.father, ped.mother, ranks, schedule="sparse_phi")
+    eng = gen.Engine(plan)
+    eng.run()
+    assert_bit_equal(eng.fetch(), want)
+    eng.close()
+    dense, _ = ob.phi_ranks(ped.father, ped.mother, ranks)
+    assert_bit_equal(gen.phi(ped, pro), dense)
+    assert not np.array_equal(dense, want)
+    with pytest.raises(Exception):
+        gen.Engine(plan, "fp64")                                                 # sparse_phi stores Float32
+
+
+def test_sparse_phi_genea140_and_scaled_configs(gen, ob):
+    ped = gen.genealogy(gen.genea140)
+    pro = gen.pro(ped)
+    ranks = ped.rank_of(pro)
+    want, stored = ob.sparse_phi_ranks(ped.father, ped.mother, ranks)
+    k = gen.sparse_phi(ped)
+    order = np.argsort(ranks, kind="stable")
+    assert_bit_equal(k._dense, np.ascontiguousarray(want[np.ix_(order, order)]))
+    assert k.stored == stored
+    for name, scale in (("C3", 0.02), ("C5", 0.02)):
+        s = gen.synth.config(name, scale)
+        ped = gen.genealogy(s.as_columns())
+        ranks = ped.rank_of(s.probands)
+        want, _ = ob.sparse_phi_ranks(ped.father, ped.mother, ranks)
+        plan = gen.Plan(ped.father, ped.mother, ranks, schedule="sparse_phi")
+        eng = gen.Engine(plan)
+        eng.run()
+        assert_bit_equal(eng.fetch(), want)
+        eng.close()

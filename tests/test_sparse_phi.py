@@ -1,0 +1,94 @@
+"""`gen.sparse_phi`: oracle restatement of src/compute.jl:321-447 pinned to the
+reference's known answers, the planner's sparse_phi schedule replayed on the CPU, the KinshipMatrix
+mirror.  The GPU half is in test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+from plan_replay import replay
+from util import ladder_pedigree, random_pedigree
+
+
+def test_oracle_sparse_phi_geneaji_golden(gen, ob):
+    ped = gen.genealogy(gen.geneaJi)
+    ranks = ped.rank_of(gen.pro(ped))
+    dense, stored = ob.sparse_phi_ranks(ped.father, ped.mother, ranks)
+    k = gen.KinshipMatrix(gen.pro(ped), ranks, dense)
+    assert gen.phiMean(k) == np.float32(0.171875)                                # test/runtests.jl:55
+    assert repr(k) == "3×3 KinshipMatrix with 6 stored entries." and stored == 6   # :56
+    assert k[1, 2] == np.float32(0.37109375) and k[2, 1] == k[1, 2]              # :57
+    # keyed lower rank -> higher rank (compute.jl:36-40); 29 is a founder, so it ranks first
+    assert k.to_dict() == {29: {29: np.float32(0.53515625), 1: np.float32(0.072265625), 2: np.float32(0.072265625)},
+                           1: {1: np.float32(0.591796875), 2: np.float32(0.37109375)}, 2: {2: np.float32(0.591796875)}}
+    with pytest.raises(KeyError):
+        k[1, 3]
+
+
+def test_oracle_sparse_phi_equals_phi_where_nothing_rounds(gen, ob):
+    """Shallow pedigrees: every value is a short dyadic fraction, so both reference functions
+    (and the exact recursion behind test_oracle.py) give the same matrix."""
+    s = gen.synth.generate(900, 6, 25, alpha=0.1, demes=1, overlap=2, seed=4)      # 6 generations: <= 13 halvings
+    ped = gen.genealogy(s.as_columns())
+    ranks = ped.rank_of(s.probands)
+    dense, _ = ob.phi_ranks(ped.father, ped.mother, ranks)
+    sparse, stored = ob.sparse_phi_ranks(ped.father, ped.mother, ranks)
+    assert np.array_equal(dense, sparse)
+    assert stored == 25 + np.count_nonzero(np.triu(sparse, 1))
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_replayed_sparse_schedule_equals_oracle_random(gen, ob, seed):
+    rng = np.random.default_rng(100 + seed)
+    n = int(rng.integers(60, 600))
+    rec = random_pedigree(rng, n, int(rng.integers(3, 12)), window=int(rng.choice([0, 0, 30, 80])))
+    ped = gen.genealogy(rec)
+    pro = rng.permutation(ped.ids)[: int(rng.integers(2, 40))]
+    pro = np.concatenate([pro, pro[:2]])                                         # duplicates collapse
+    ranks = ped.rank_of(pro)
+    want, _ = ob.sparse_phi_ranks(ped.father, ped.mother, ranks)
+    plan = gen.Plan(ped.father, ped.mother, ranks, schedule="sparse_phi")
+    assert np.array_equal(replay(plan), want)
+
+
+def test_sparse_schedule_differs_from_phi_and_keeps_subnormals(gen, ob):
+    """Deep pedigrees: the two reference functions round at different points (per individual vs
+    per step), and sparse_phi halves in Float32, which matters once values are subnormal."""
+    s = gen.synth.generate(16 * 60, 60, 16, alpha=0.2, overlap=1, seed=11)
+    ped = gen.genealogy(s.as_columns())
+    ranks = ped.rank_of(s.probands)
+    want, _ = ob.sparse_phi_ranks(ped.father, ped.mother, ranks)
+    dense, _ = ob.phi_ranks(ped.father, ped.mother, ranks)
+    assert not np.array_equal(want, dense)
+    assert np.array_equal(replay(gen.Plan(ped.father, ped.mother, ranks, schedule="sparse_phi")), want)
+    assert not np.array_equal(replay(gen.Plan(ped.father, ped.mother, ranks)), want)      # phi's schedule is another one
+    # lineages 73 generations apart: single-bit subnormals, halved in Float32 (compute.jl:350-389)
+    cols, pro = ladder_pedigree(73)
+    ped = gen.genealogy(cols)
+    ranks = ped.rank_of(pro)
+    want, _ = ob.sparse_phi_ranks(ped.father, ped.mother, ranks)
+    dense, _ = ob.phi_ranks(ped.father, ped.mother, ranks)
+    tiny = np.float32(np.finfo(np.float32).tiny)
+    assert ((want > 0) & (want < tiny)).any()                                    # gradual underflow reached
+    assert not np.array_equal(want, dense)                                       # 0 here, one ulp of a subnormal there
+    assert np.array_equal(replay(gen.Plan(ped.father, ped.mother, ranks, schedule="sparse_phi")), want)
+    assert np.array_equal(replay(gen.Plan(ped.father, ped.mother, ranks)), dense)
+
+
+def test_sparse_schedule_layers_are_depths(gen):
+    s = gen.synth.generate(3000, 9, 150, alpha=0.05, demes=2, migration=0.1, overlap=3, seed=8)
+    ped = gen.genealogy(s.as_columns())
+    ranks = ped.rank_of(s.probands)
+    plan = gen.Plan(ped.father, ped.mother, ranks, schedule="sparse_phi")
+    dense_plan = gen.Plan(ped.father, ped.mother, ranks)
+    assert plan.row_updates == dense_plan.row_updates                            # same ancestors (branching, compute.jl:323)
+    last = -1
+    seen = 0
+    for t in range(plan.n_layers):
+        seq = np.sort(plan.layer_arrays(t)["member_ind"])
+        if len(seq):
+            assert seq[0] == last + 1 and np.array_equal(seq, np.arange(seq[0], seq[0] + len(seq)))   # queue order, by depth
+            last = int(seq[-1]); seen += len(seq)
+    assert seen == plan.row_updates
+    first = plan.layer_arrays(0)
+    assert np.all(first["fam_father_slot"] == -1) and np.all(first["fam_mother_slot"] == -1)   # layer 0 = founders
+    with pytest.raises(Exception):
+        gen.Plan(ped.father, ped.mother, ranks, schedule="nope")

@@ -56,3 +56,29 @@ def exact_kinship(father: np.ndarray, mother: np.ndarray):
         return v
 
     return phi
+
+
+def ladder_pedigree(K: int):
+    """Three lineages from one founder couple / a half-sib, K generations each, always married to
+    fresh founders, and nine children of the last members of the first two lineages.
+
+    Kinships between the lineages halve every generation (2**-(2K+3) after K), so around K = 73 they
+    are Float32 subnormals with a single low bit, and a child of two lineages sums TWO such halves:
+    `x / 2` in Float32 (what sparse_phi does) and in Float64 (what phi does) then differ.
+    Returns (columns dict, probands)."""
+    ind, fa, mo, sex = [], [], [], []
+
+    def add(f, m, s):
+        ind.append(len(ind) + 1); fa.append(f); mo.append(m); sex.append(s)
+        return ind[-1]
+
+    p1, p2, q = add(0, 0, 1), add(0, 0, 2), add(0, 0, 2)
+    A, B, Cc = [add(p1, p2, 1)], [add(p1, p2, 2)], [add(p1, q, 2)]
+    for _ in range(K):
+        A.append(add(A[-1], add(0, 0, 2), 1))
+        B.append(add(add(0, 0, 1), B[-1], 2))
+        Cc.append(add(add(0, 0, 1), Cc[-1], 2))
+    D = [add(A[-1 - i], B[-1 - j], 1) for i in range(3) for j in range(3)]
+    cols = {"ind": np.array(ind, np.int64), "father": np.array(fa, np.int64), "mother": np.array(mo, np.int64),
+            "sex": np.array(sex, np.int32)}
+    return cols, np.array(D + [Cc[-1], Cc[-2], Cc[-3], A[-1], B[-1]], np.int64)
