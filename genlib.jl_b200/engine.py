@@ -245,18 +245,20 @@ def phi(pedigree: Pedigree, probandIDs=None, *, verbose: bool = False, compute: 
 
 
 def phi_distributed(pedigree: Pedigree, probandIDs=None, *, numerics="reference", dtype=np.float32,
-                    device: Optional[int] = None, gather: bool = True, return_stats: bool = False):
+                    device: Optional[int] = None, gather: bool = True, return_stats: bool = False,
+                    schedule: str = "phi"):
     """gen.phi on all ranks of a `torch.distributed` job (one process per GPU of one box).
 
     Every rank builds the same plan, owns a share of the frontier rows, reads parent rows and
     pushes couple-matrix rows through NVLink peer mappings.  Collective: call on every rank.
     gather=True returns the full matrix on rank 0 (None elsewhere); gather=False returns
-    (own_proband_indices, own_rows) on every rank."""
+    (own_proband_indices, own_rows) on every rank.  schedule="sparse_phi" gives the values of
+    gen.sparse_phi instead (dense, in proband order)."""
     import torch.distributed as dist
     rank, world = dist.get_rank(), dist.get_world_size()
     IDs = pro(pedigree) if probandIDs is None else np.asarray(probandIDs, np.int64)
     ranks = pedigree.rank_of(IDs)
-    plan = Plan(pedigree.father, pedigree.mother, ranks, world=world)
+    plan = Plan(pedigree.father, pedigree.mother, ranks, world=world, schedule=schedule)
     n = plan.n_unique
     if n == 0:
         res = np.zeros((0, 0), dtype)

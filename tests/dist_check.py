@@ -66,6 +66,20 @@ def main():
         s = gen.synth.config(name, scale)
         ped = gen.genealogy(s.as_columns())
         check(f"{name} x{scale}", ped, s.probands)
+    # gen.sparse_phi's schedule on the sharded engine: against the oracle's restatement of sparse_phi
+    for seed in range(3):
+        rng = np.random.default_rng(4000 + seed)
+        rec = random_pedigree(rng, int(rng.integers(300, 1500)), int(rng.integers(4, 40)), p_single=0.15,
+                              p_none=0.03, window=int(rng.choice([0, 60, 300])))
+        ped = gen.genealogy(rec)
+        pro = rng.permutation(ped.ids)[: int(rng.integers(5, 200))]
+        got = gen.phi_distributed(ped, pro, device=local, schedule="sparse_phi")
+        if rank == 0:
+            want, _ = ob.sparse_phi_ranks(ped.father, ped.mother, ped.rank_of(pro))
+            ok = got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+            print(f"[dist x{world}] sparse_phi schedule, random {seed}: {'ok' if ok else 'MISMATCH'} ({got.shape[0]}x{got.shape[0]})", flush=True)
+            if not ok:
+                failures.append(f"sparse {seed}")
     dist.barrier()
     flag = torch.tensor([len(failures)], device="cuda")
     dist.broadcast(flag, 0)
