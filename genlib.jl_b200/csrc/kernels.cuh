@@ -450,10 +450,10 @@ __device__ __forceinline__ void cp_async(void *smem, const void *gmem) {
         asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(s), "l"(gmem), "n"(BYTES) : "memory");
 }
 
-// per warp and stage: Vab[kERows][vstride], Vba[kERows][vstride], famJ/rankJ/slotJ[kMTile]
+// per warp and stage: Vab[kERows][vstride], Vba[kERows][vstride]
 template <typename T>
 __host__ __device__ inline size_t expand_stage_bytes(int vstride) {
-    return 2 * (size_t)kERows * vstride * sizeof(T) + 3 * kMTile * sizeof(int32_t);
+    return 2 * (size_t)kERows * vstride * sizeof(T);
 }
 
 template <typename T>
@@ -509,7 +509,7 @@ __device__ __forceinline__ void expand_step(const unsigned (&go)[4], const int (
 }
 
 template <typename T, bool GUESTS>
-__global__ void __launch_bounds__(kExpandThreads)
+__global__ void __launch_bounds__(kExpandThreads, 6)
 expand_kernel(T *__restrict__ A, int64_t ld, const T *__restrict__ V, const T *__restrict__ Vt,
               const T *__restrict__ Dg, PeerTable PT, LayerArgs L) {
     constexpr int kVec = 16 / sizeof(T);
@@ -524,7 +524,6 @@ expand_kernel(T *__restrict__ A, int64_t ld, const T *__restrict__ V, const T *_
     const unsigned mine = (unsigned)__cvta_generic_to_shared(smem_raw) + (unsigned)warp * 2u * stage_bytes;
     const unsigned row_bytes = (unsigned)L.vstride * (unsigned)sizeof(T);
     const unsigned vba_off = kERows * row_bytes;
-    const unsigned meta_off = 2 * vba_off;
 
     // ---- the warp's rows: couple, rank, row pointer (registers) ----
     const int mrow = row0 + min(lane, nr - 1);
@@ -576,8 +575,23 @@ expand_kernel(T *__restrict__ A, int64_t ld, const T *__restrict__ V, const T *_
     }
     const T *vsrc = V + (size_t)(f0 - L.own_f0) * L.nf_pad + lane * kVec;     // V, Vt hold own couple rows
     const T *vtsrc = Vt + (size_t)(f0 - L.own_f0) * L.nf_pad + lane * kVec;
-    const int32_t *msrc = L.mem_fam + 4 * lane;
-    const long long mstride1 = L.mem_ind - L.mem_fam, mstride2 = L.mem_slot - L.mem_fam;
+    // column metadata of a step (couple, rank, slot of the lane's four members) goes straight into
+    // registers, one step ahead: three 128-bit loads per lane instead of a round trip through shared
+    // memory (the shared-memory pipe is this kernel's busiest unit)
+    auto load_meta = [&](int J, int4 &g, int4 &r, int4 &sl) {
+        const int mJ0 = __shfl_sync(0xffffffffu, t_m0, J - Jbeg), mJ1 = mJ0 + __shfl_sync(0xffffffffu, t_cnt, J - Jbeg);
+        const int j0 = mJ0 + 4 * lane;
+        if (j0 + 3 < mJ1) {
+            g = __ldg(reinterpret_cast<const int4 *>(L.mem_fam + j0));
+            r = __ldg(reinterpret_cast<const int4 *>(L.mem_ind + j0));
+            sl = __ldg(reinterpret_cast<const int4 *>(L.mem_slot + j0));
+        } else if (j0 < mJ1) {                              // ragged end of the tile: clamped
+            const int m1 = min(j0 + 1, mJ1 - 1), m2 = min(j0 + 2, mJ1 - 1), m3 = min(j0 + 3, mJ1 - 1);
+            g = make_int4(L.mem_fam[j0], L.mem_fam[m1], L.mem_fam[m2], L.mem_fam[m3]);
+            r = make_int4(L.mem_ind[j0], L.mem_ind[m1], L.mem_ind[m2], L.mem_ind[m3]);
+            sl = make_int4(L.mem_slot[j0], L.mem_slot[m1], L.mem_slot[m2], L.mem_slot[m3]);
+        }
+    };
 
     auto prefetch = [&](int J, int buf) {
         const unsigned stage = mine + (unsigned)buf * stage_bytes;
@@ -591,30 +605,15 @@ expand_kernel(T *__restrict__ A, int64_t ld, const T *__restrict__ V, const T *_
                 if (info & 0x200) cp_async16_s(dst + vba_off, b);
             }
         }
-        // column metadata: 4 members per lane (clamped at the ragged end of the tile)
-        const int mJ0 = __shfl_sync(0xffffffffu, t_m0, J - Jbeg), mJ1 = mJ0 + __shfl_sync(0xffffffffu, t_cnt, J - Jbeg);
-        const unsigned mdst = stage + meta_off + 16u * (unsigned)lane;
-        if (mJ0 + 4 * lane + 3 < mJ1) {
-            cp_async16_s(mdst, msrc + mJ0);
-            cp_async16_s(mdst + kMTile * 4u, msrc + mJ0 + mstride1);
-            cp_async16_s(mdst + 2u * kMTile * 4u, msrc + mJ0 + mstride2);
-        } else {
-            int32_t *metaJ = reinterpret_cast<int32_t *>(smem_raw + (stage + meta_off - (unsigned)__cvta_generic_to_shared(smem_raw)));
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int m = min(mJ0 + 4 * lane + k, mJ1 - 1);
-                cp_async<4>(metaJ + 4 * lane + k, L.mem_fam + m);
-                cp_async<4>(metaJ + kMTile + 4 * lane + k, L.mem_ind + m);
-                cp_async<4>(metaJ + 2 * kMTile + 4 * lane + k, L.mem_slot + m);
-            }
-        }
         cp_async_commit();
     };
 
     prefetch(Jbeg, 0);
+    int4 gj = make_int4(0, 0, 0, 0), rj4 = gj, sj4 = gj, gjn = gj, rjn = gj, sjn = gj;
+    load_meta(Jbeg, gj, rj4, sj4);
     int buf = 0;
     for (int J = Jbeg; J < Jend; J++, buf ^= 1) {
-        if (J + 1 < Jend) { prefetch(J + 1, buf ^ 1); cp_async_wait<1>(); }
+        if (J + 1 < Jend) { prefetch(J + 1, buf ^ 1); load_meta(J + 1, gjn, rjn, sjn); cp_async_wait<1>(); }
         else cp_async_wait<0>();
         __syncwarp();                                      // other lanes' copies are visible
         const unsigned stage = mine + (unsigned)buf * stage_bytes;
@@ -622,9 +621,6 @@ expand_kernel(T *__restrict__ A, int64_t ld, const T *__restrict__ V, const T *_
         const int j0 = mJ0 + 4 * lane;
         const int c0 = __shfl_sync(0xffffffffu, t_c0, J - Jbeg);
         if (j0 < mJ1) {
-            const int4 gj = lds_int4(stage + meta_off + 16u * lane);
-            const int4 rj4 = lds_int4(stage + meta_off + kMTile * 4u + 16u * lane);
-            const int4 sj4 = lds_int4(stage + meta_off + 2u * kMTile * 4u + 16u * lane);
             const unsigned go[4] = {stage + (unsigned)(gj.x - c0) * (unsigned)sizeof(T), stage + (unsigned)(gj.y - c0) * (unsigned)sizeof(T),
                                     stage + (unsigned)(gj.z - c0) * (unsigned)sizeof(T), stage + (unsigned)(gj.w - c0) * (unsigned)sizeof(T)};
             const int rj[4] = {rj4.x, rj4.y, rj4.z, rj4.w}, sj[4] = {sj4.x, sj4.y, sj4.z, sj4.w};
@@ -641,6 +637,7 @@ expand_kernel(T *__restrict__ A, int64_t ld, const T *__restrict__ V, const T *_
             }
         }
         __syncwarp();                                      // stage free before it is refilled
+        gj = gjn; rj4 = rjn; sj4 = sjn;
     }
 }
 
