@@ -96,6 +96,16 @@ class ShardedReplay:
         self.A = [np.full((max(plan.rank_rows(g), 1), self.W), np.nan, self.T) for g in range(self.G)]
         self.es = np.dtype(self.T).itemsize
         self.exchange = exchange
+        self.sparse = getattr(plan, "schedule", "phi") == "sparse_phi"
+
+    def half_sum(self, x, y):
+        """phi: 1/2 x + 1/2 y in Float64.  sparse_phi: the halves are Float32 divisions of STORED
+        Float32 values (compute.jl:350-389), the sum is Float64."""
+        if self.sparse:
+            h = np.float32(0.5)
+            return (np.asarray(x, np.float64).astype(np.float32) * h).astype(np.float64) \
+                + (np.asarray(y, np.float64).astype(np.float32) * h).astype(np.float64)
+        return 0.5 * np.asarray(x, np.float64) + 0.5 * np.asarray(y, np.float64)
 
     def note(self, src, dst, nbytes):
         if self.exchange is not None and src != dst and nbytes:
@@ -131,7 +141,7 @@ class ShardedReplay:
             fo, mo = sh["fam_father_owner"][F], sh["fam_mother_owner"][F]
             x = self.row(fo, sh["fam_father_lrow"][F], live, g) if fo >= 0 else 0.0
             y = self.row(mo, sh["fam_mother_lrow"][F], live, g) if mo >= 0 else 0.0
-            R[F - F0] = 0.5 * x + 0.5 * y                       # one rounding (1/2 y is exact)
+            R[F - F0] = self.half_sum(x, y)                     # one rounding (1/2 y is exact)
         if len(live):
             assert not np.isnan(R).any(), f"layer {self.t} rank {g}: cross block read an unwritten entry"
         self.Rt[g] = R
@@ -164,7 +174,7 @@ class ShardedReplay:
         for F in range(self.nf):
             x = Rg[:, self.pos_in_live[pf[F]]] if pf[F] >= 0 else zero
             y = Rg[:, self.pos_in_live[pm[F]]] if pm[F] >= 0 else zero
-            v = 0.5 * x + 0.5 * y                               # V[F, G0:G1]
+            v = self.half_sum(x, y)                             # V[F, G0:G1] (sparse_phi: from the rounded cross values)
             o = self.owner_of_fam[F]
             self.pushes.append((o, F - sh["fam_base"][o], G0, G1, v))
             self.Vt[g][:, F] = v
@@ -186,7 +196,7 @@ class ShardedReplay:
         for q in range(M0, M1):                                 # diagonal: 1/2 + 1/2 Psi[father, mother]
             F, d = fam[q], 0.5
             if pf[F] >= 0 and pm[F] >= 0:
-                d = 0.5 + 0.5 * float(self.row(sh["fam_father_owner"][F], sh["fam_father_lrow"][F], [pm[F]], g)[0])
+                d = float(self.half_sum(self.row(sh["fam_father_owner"][F], sh["fam_father_lrow"][F], [pm[F]], g)[0], 1.0))
             blk[q - M0, q] = d
         assert not np.isnan(blk).any(), f"layer {self.t} rank {g}: expand read an unwritten couple entry"
         self.A[g][np.ix_(sh["member_lrow"][M0:M1], a["member_slot"])] = blk.astype(self.T)

@@ -38,6 +38,20 @@ def test_sharded_replay_random(gen, ob, seed):
         assert sum(traffic) > 0                         # the shards do talk to each other
 
 
+@pytest.mark.parametrize("seed", range(4))
+def test_sharded_replay_sparse_phi_schedule(gen, ob, seed):
+    """gen.sparse_phi's schedule (queue order, Float32 stores and halves) on 2 and 3 ranks."""
+    rng = np.random.default_rng(700 + seed)
+    rec = random_pedigree(rng, int(rng.integers(80, 500)), int(rng.integers(3, 12)), window=int(rng.choice([0, 40, 90])))
+    ped = gen.genealogy(rec)
+    pro = rng.permutation(ped.ids)[: int(rng.integers(2, 40))]
+    ranks = ped.rank_of(pro)
+    want, _ = ob.sparse_phi_ranks(ped.father, ped.mother, ranks)
+    for world in (2, 3):
+        plan = gen.Plan(ped.father, ped.mother, ranks, world=world, schedule="sparse_phi")
+        assert np.array_equal(replay_sharded(plan), want)
+
+
 @pytest.mark.parametrize("guests", ["0", "1"])
 def test_guest_rows_replay(gen, ob, guests, monkeypatch):
     """GENLIB_GUESTS=1: a new row is also written to the rank that will read it as a remote parent."""
