@@ -162,6 +162,8 @@ struct genlib_plan {
     double ms_plan = 0;
 };
 
+constexpr int kMaxGroups = 8;    // couple groups per layer (multi-GPU software pipeline of cross and couple)
+
 struct genlib_engine {
     const genlib_plan *plan = nullptr;
     int numerics = 0, device = 0, sm_count = 148;
@@ -169,6 +171,9 @@ struct genlib_engine {
     bool attached = false;                 // peers' arenas mapped (always true for one rank)
     size_t esize = 4;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t side_stream = nullptr;    // multi-GPU: couple_kernel of one couple group runs beside cross_kernel of the next
+    cudaEvent_t group_ev[kMaxGroups + 1] = {};
+    bool piped = false;
     Arena arena;
     void *A = nullptr;                     // this rank's frontier rows: rows_cap x capacity
     double *Rt = nullptr;                  // transposed cross block: live slots x own couples (fp64)
@@ -195,6 +200,8 @@ struct genlib_engine {
         for (auto e : events) cudaEventDestroy(e);
         if (stream) cudaStreamSynchronize(stream);
         if (copy_stream) cudaStreamSynchronize(copy_stream);
+        if (side_stream) { cudaStreamSynchronize(side_stream); cudaStreamDestroy(side_stream); }
+        for (auto e : group_ev) if (e) cudaEventDestroy(e);
         g_arenas.release(arena);
         if (stream) cudaStreamDestroy(stream);
         if (copy_stream) cudaStreamDestroy(copy_stream);
@@ -297,7 +304,8 @@ int launch_layers(genlib_engine &E, bool timed) {
     const bool stored = P.schedule == kScheduleSparsePhi;      // sparse_phi's arithmetic (Float32 halves of stored values)
     auto cross_fn = stored ? cross_kernel<T, true> : cross_kernel<T, false>;
     auto couple_fn = stored ? couple_kernel<T, true> : couple_kernel<T, false>;
-    CU(cudaFuncSetAttribute(cross_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cross_smem));
+    const size_t cross_smem_piped = std::max<size_t>(cross_smem, 120 * 1024);    // one CTA per SM
+    CU(cudaFuncSetAttribute(cross_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cross_smem_piped));
     CU(cudaFuncSetAttribute(cross_fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CU(cudaFuncSetAttribute(expand_fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     T *V = static_cast<T *>(E.Vrow), *Vt = static_cast<T *>(E.Vt), *Dg = static_cast<T *>(E.Dg);
@@ -313,26 +321,54 @@ int launch_layers(genlib_engine &E, bool timed) {
         if (E.layer_limit >= 0 && t >= E.layer_limit) break;
         LayerArgs a = layer_args(E, t);
         if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
-        if (L.live_before > 0 && a.own_nf > 0) {
-            // column tiles per CTA: long chunks amortise the pipeline fill, but keep >= ~4 waves of CTAs
-            const int64_t ptiles = L.rt_rows / kPTile, ftiles = (a.own_nf + kFTile - 1) / kFTile;
-            const int64_t want = ptiles * ftiles / (4 * 2 * (int64_t)E.sm_count);
-            a.pchunk = (int)std::max<int64_t>(std::min<int64_t>(4, ptiles), std::min<int64_t>(kMaxPChunk, want));
-            dim3 grid((unsigned)((ptiles + a.pchunk - 1) / a.pchunk), (unsigned)ftiles);
-            cross_fn<<<grid, kThreads, cross_smem, E.stream>>>(A, ld, E.Rt, E.peers, a);
-            launches++;
-            if (L.carried > 0 && a.own_nm > 0) {
+        // Couple groups (GENLIB_PIPE=1, several ranks): cross_kernel fills the columns of Rt that belong to a
+        // group of own couples and couple_kernel consumes exactly those columns.  Cross is bound by NVLink
+        // INGRESS (remote parent rows), couple by NVLink EGRESS (rows of V pushed to their owners), so
+        // couple(group g) runs on a second, high-priority stream beside cross(group g + 1); cross then asks
+        // for enough shared memory to keep ONE of its CTAs per SM, which leaves room for couple's.
+        const int64_t ftiles = (a.own_nf + kFTile - 1) / kFTile;
+        const int per_ctile = kCTile / kFTile;
+        int groups = 1;
+        if (E.piped && L.live_before > 0) groups = (int)std::max<int64_t>(1, std::min<int64_t>(kMaxGroups, ftiles / (16 * per_ctile)));
+        const int64_t group_tiles = ((ftiles + groups - 1) / groups + per_ctile - 1) / per_ctile * per_ctile;
+        const bool piped = groups > 1;
+        for (int g = 0; g < groups && a.own_nf > 0; g++) {
+            const int64_t ft0 = g * group_tiles, ft1 = std::min<int64_t>(ftiles, ft0 + group_tiles);
+            if (ft0 >= ft1) break;
+            const bool last = ft1 >= ftiles;
+            a.ctile0 = (int32_t)ft0;
+            if (L.live_before > 0) {
+                // column tiles per CTA: long chunks amortise the pipeline fill, but keep >= ~4 waves of CTAs
+                const int64_t ptiles = L.rt_rows / kPTile;
+                const int64_t want = ptiles * (ft1 - ft0) / (4 * 2 * (int64_t)E.sm_count);
+                a.pchunk = (int)std::max<int64_t>(std::min<int64_t>(4, ptiles), std::min<int64_t>(kMaxPChunk, want));
+                dim3 grid((unsigned)((ptiles + a.pchunk - 1) / a.pchunk), (unsigned)(ft1 - ft0));
+                cross_fn<<<grid, kThreads, piped ? cross_smem_piped : cross_smem, E.stream>>>(A, ld, E.Rt, E.peers, a);
+                launches++;
+            }
+            if (last && L.live_before > 0 && L.carried > 0 && a.own_nm > 0) {
                 dim3 mgrid((unsigned)((a.own_nm + 32 * kMirrorCols - 1) / (32 * kMirrorCols)), (unsigned)((L.rt_rows + kThreads / 32 - 1) / (kThreads / 32)));
                 mirror_kernel<T><<<mgrid, kThreads, 0, E.stream>>>(E.Rt, ld, E.peers, a);
                 launches++;
             }
-        }
-        if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
-        if (a.own_nf > 0) {
-            dim3 grid((unsigned)((a.nfo_pad + kCTile - 1) / kCTile), (unsigned)((L.n_fam + kCRows - 1) / kCRows));
-            couple_fn<<<grid, kThreads, couple_smem, E.stream>>>(ld, E.Rt, Vt, Dg, E.peers, a);
+            if (last && timed) CU(cudaEventRecord(E.events[ev++], E.stream));
+            cudaStream_t cs = E.stream;
+            if (piped) {
+                CU(cudaEventRecord(E.group_ev[g], E.stream));
+                CU(cudaStreamWaitEvent(E.side_stream, E.group_ev[g], 0));
+                cs = E.side_stream;
+            }
+            const int64_t ct0 = ft0 / per_ctile, ct1 = (std::min<int64_t>(ft1 * kFTile, a.nfo_pad) + kCTile - 1) / kCTile;
+            dim3 cgrid((unsigned)(ct1 - ct0), (unsigned)((L.n_fam + kCRows - 1) / kCRows));
+            couple_fn<<<cgrid, kThreads, couple_smem, cs>>>(ld, E.Rt, Vt, Dg, E.peers, a);
             launches++;
         }
+        if (a.own_nf <= 0 && timed) CU(cudaEventRecord(E.events[ev++], E.stream));
+        if (piped) {                                         // join: the layer's V is complete on the main stream
+            CU(cudaEventRecord(E.group_ev[kMaxGroups], E.side_stream));
+            CU(cudaStreamWaitEvent(E.stream, E.group_ev[kMaxGroups], 0));
+        }
+        a.ctile0 = 0;
         if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
         launch_barrier(E);                 // every rank's row block of V is complete (peer stores landed)
         if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
@@ -419,6 +455,16 @@ int create_engine(const genlib_plan *plan, int numerics, int device, int rank, g
     const double t0 = now_ms();
     CU(cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&E->copy_stream, cudaStreamNonBlocking));
+    {
+        const char *env = std::getenv("GENLIB_PIPE");
+        E->piped = E->world > 1 && env && env[0] == '1';
+    }
+    if (E->piped) {
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));      // hi = numerically lowest = highest priority
+        CU(cudaStreamCreateWithPriority(&E->side_stream, cudaStreamNonBlocking, hi));
+        for (auto &e : E->group_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     {
         cudaError_t ce = g_arenas.acquire(E->device, need, E->arena);
         if (ce != cudaSuccess) {

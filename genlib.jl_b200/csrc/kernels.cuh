@@ -54,6 +54,8 @@ struct LayerArgs {
     int32_t n_mtiles;
     int32_t vstride;            // staged couple segment of expand_kernel: row stride (elements)
     int32_t pchunk;             // live-column tiles per cross_kernel CTA (<= kMaxPChunk)
+    int32_t ctile0;             // first own-couple tile of this launch: cross_kernel tiles of kFTile (blockIdx.y + ctile0),
+                                // couple_kernel column tiles of kCTile (blockIdx.x + ctile0 * kFTile / kCTile)
 };
 
 constexpr int kThreads = 256;
@@ -165,7 +167,7 @@ cross_kernel(T *__restrict__ A, int64_t ld, double *__restrict__ Rt, PeerTable P
     constexpr int RB = cross_row_bytes<T>(), STAGE = cross_stage_bytes<T>();
     constexpr unsigned ROWB = kPTile * (unsigned)sizeof(T);          // bytes of one row segment
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int F0 = blockIdx.y * kFTile;                              // local couple index (own couples only)
+    const int F0 = (blockIdx.y + L.ctile0) * kFTile;                 // local couple index (own couples only)
     const int t0 = blockIdx.x * L.pchunk;
     const int nt_all = min(L.pchunk, L.rt_rows / kPTile - t0);
     const int c0 = t0 * kPTile;                                      // first column of the chunk, from rt_lo
@@ -342,7 +344,7 @@ couple_kernel(int64_t ld, const double *__restrict__ Rt, T *__restrict__ Vt, T *
     // The row tiles are visited starting behind this rank's own range: at any moment the ranks
     // push to DIFFERENT owners instead of all hitting the same GPU's NVLink ingress.
     const int ytile = (int)((blockIdx.y + (unsigned)L.ftile_shift * kFTile / kCRows) % gridDim.y);
-    const int F0 = ytile * kCRows, G0 = blockIdx.x * kCTile;
+    const int F0 = ytile * kCRows, G0 = (blockIdx.x + L.ctile0 * kFTile / kCTile) * kCTile;
     const int gl = G0 + 4 * lane;
     int minG = INT_MAX;                                       // lowest rank among the members of the tile's column couples
 #pragma unroll
@@ -366,7 +368,7 @@ couple_kernel(int64_t ld, const double *__restrict__ Rt, T *__restrict__ Vt, T *
         }
         if (lane == 0) s_skip[fl] = skips[q];
     }
-    if (blockIdx.x == 0 && lane < 4) {                        // diagonal of the couple's members
+    if (G0 == 0 && lane < 4) {                                // diagonal of the couple's members
         const int F = F0 + half * kFTile + warp * 4 + lane;
         if (F >= L.own_f0 && F < L.own_f0 + L.own_nf) {
             const int pf = L.fam_pf[F], pm = L.fam_pm[F];
