@@ -327,6 +327,7 @@ int launch_layers(genlib_engine &E, bool timed) {
         // couple(group g) runs on a second, high-priority stream beside cross(group g + 1); cross then asks
         // for enough shared memory to keep ONE of its CTAs per SM, which leaves room for couple's.
         const int64_t ftiles = (a.own_nf + kFTile - 1) / kFTile;
+        if (ftiles > 65535 || (L.n_fam + kCRows - 1) / kCRows > 65535) return fail(GENLIB_EINVAL, "layer too wide for one cross/couple launch");
         const int per_ctile = kCTile / kFTile;
         int groups = 1;
         if (E.piped && L.live_before > 0) groups = (int)std::max<int64_t>(1, std::min<int64_t>(kMaxGroups, ftiles / (16 * per_ctile)));
