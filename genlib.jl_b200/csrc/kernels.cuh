@@ -18,8 +18,11 @@
 //
 // Arithmetic is binary64 in the reference's grouping; storage type T is float
 // (GENLIB_NUMERICS_REFERENCE: one RN32 per step, like compute.jl:296) or double.
-// All three are HBM-bound streaming kernels: 128-bit loads of contiguous row
-// segments, shared-memory tile transposes, coalesced stores; no tensor cores.
+// STORED = true selects the arithmetic of gen.sparse_phi instead (compute.jl:321-447: every
+// stored kinship is a Float32 and is halved in Float32; the plan then orders the layers and the
+// members by sparse_phi's queue, see plan.hpp).
+// All are HBM-bound streaming kernels: TMA bulk copies (cross) / 128-bit loads of contiguous
+// row segments, shared-memory tile transposes, coalesced stores; no tensor cores.
 #pragma once
 #include <cuda_runtime.h>
 #include <climits>
