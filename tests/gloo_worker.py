@@ -29,10 +29,10 @@ def run(rank: int, world: int, port: int, out_path: str):
                               p_none=0.03, window=int(rng.choice([0, 50])))
         ped = gen.genealogy(rec)
         cases.append((f"random{k}", ped, rng.permutation(ped.ids)[: int(rng.integers(4, 40))], rec))
-    for case in cases:
+    for case, schedule in [(c, sch) for c in cases for sch in ("phi", "sparse_phi")]:
         name, ped, pro = case[0], case[1], case[2]
         IDs = gen.pro(ped) if pro is None else pro
-        plan = gen.Plan(ped.father, ped.mother, ped.rank_of(IDs), world=world)
+        plan = gen.Plan(ped.father, ped.mother, ped.rank_of(IDs), world=world, schedule=schedule)
         # every rank must have built the same schedule
         sig = hashlib.sha256()
         for t in range(plan.n_layers):
@@ -78,7 +78,9 @@ def run(rank: int, world: int, port: int, out_path: str):
         for idx, rows in parts:
             got[idx] = rows
         if rank == 0:
-            if name == "geneaJi":
+            if schedule == "sparse_phi":           # gen.sparse_phi's own values (src/compute.jl:321-447)
+                want, _ = ob.sparse_phi_ranks(ped.father, ped.mother, ped.rank_of(IDs))
+            elif name == "geneaJi":
                 want = ob.OraclePedigree.from_csv(gen.geneaJi).phi()
             else:
                 rec = case[3]
