@@ -92,3 +92,23 @@ def test_sparse_schedule_layers_are_depths(gen):
     assert np.all(first["fam_father_slot"] == -1) and np.all(first["fam_mother_slot"] == -1)   # layer 0 = founders
     with pytest.raises(Exception):
         gen.Plan(ped.father, ped.mother, ranks, schedule="nope")
+
+
+@pytest.mark.parametrize("schedule", ["phi", "sparse_phi"])
+def test_edge_cases_both_schedules(gen, ob, schedule):
+    """Empty / founder-only / duplicate proband lists, a single individual, a 3000-generation chain."""
+    want_of = (lambda f, m, p: ob.sparse_phi_ranks(f, m, p)[0]) if schedule == "sparse_phi" \
+        else (lambda f, m, p: ob.phi_ranks(f, m, p)[0])
+    f, m = np.array([-1, -1, 0, 0, 2], np.int32), np.array([-1, -1, 1, 1, 3], np.int32)
+    for pro in ([], [0], [0, 1], [4], [4, 4, 2], [0, 1, 2, 3, 4]):
+        p = np.array(pro, np.int32)
+        plan = gen.Plan(f, m, p, schedule=schedule)
+        assert plan.n_unique == len(set(pro))
+        if plan.n_unique:
+            assert np.array_equal(replay(plan), want_of(f, m, p))
+    one = np.array([-1], np.int32)
+    assert np.array_equal(replay(gen.Plan(one, one, np.array([0], np.int32), schedule=schedule)), np.array([[0.5]], np.float32))
+    n = 3000
+    f, m, p = np.arange(-1, n - 1, dtype=np.int32), np.full(n, -1, np.int32), np.array([n - 1, n - 2, 5], np.int32)
+    plan = gen.Plan(f, m, p, schedule=schedule)
+    assert plan.n_layers == n and np.array_equal(replay(plan), want_of(f, m, p))
