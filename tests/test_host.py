@@ -227,6 +227,31 @@ def test_loader_edge_cases(gen, tmp_path):
     assert len(empty) == 0 and gen.pro(empty).tolist() == []
 
 
+def test_loader_id_maps_agree(gen):
+    """Small integer IDs go through a direct table, sparse or negative ones through the hash map:
+    the same pedigree under a relabelling must give the same ranks, parents and errors."""
+    s = gen.synth.generate(20000, 10, 300, alpha=0.05, demes=2, migration=0.1, overlap=2, seed=31)
+    dense = gen.genealogy(s.as_columns())
+
+    def relabel(x, f):
+        x = np.asarray(x, np.int64)
+        return np.where(x > 0, f(x), 0)
+
+    for f in (lambda x: x * 1000003 + 17, lambda x: -x - 5, lambda x: x + (1 << 40)):
+        cols = {"ind": relabel(s.ind, f), "father": relabel(s.father, f), "mother": relabel(s.mother, f), "sex": s.sex}
+        other = gen.genealogy(cols)
+        assert np.array_equal(other.father, dense.father) and np.array_equal(other.mother, dense.mother)
+        assert np.array_equal(other.ids, relabel(dense.ids, f))
+        pro = relabel(s.probands, f)
+        assert np.array_equal(other.rank_of(pro), dense.rank_of(s.probands))
+        with pytest.raises(KeyError):
+            other.rank_of(np.array([3], np.int64))               # not an ID of the relabelled pedigree
+    with pytest.raises(KeyError):
+        dense.rank_of(np.array([10 ** 12], np.int64))
+    with pytest.raises(KeyError):
+        dense.rank_of(np.array([-1], np.int64))
+
+
 def test_loader_file_equals_columns_and_oracle(gen, ob, tmp_path):
     s = gen.synth.generate(30000, 12, 500, alpha=0.05, demes=3, migration=0.1, overlap=3, seed=21)
     path = str(tmp_path / "synth.asc")
