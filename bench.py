@@ -241,6 +241,7 @@ def main():
                 "frac": achieved / peak,
                 "traffic": (traffic_ratio * float(cross_bytes[launched].mean())) if (traffic_ratio and launched.any()) else None,
                 "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, one launch, scaled by algorithmic bytes",
+                "achieved_dram": (traffic_ratio * achieved) if traffic_ratio else None,      # GB/s of measured DRAM bytes
                 "dram_frac": (traffic_ratio * achieved / peak) if traffic_ratio else None,   # measured DRAM bytes / time / peak
                 "peak_source": peak_src,
                 "launches": int(launched.sum()) * K,
