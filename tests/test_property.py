@@ -10,16 +10,18 @@ from plan_replay import replay, replay_sharded
 
 @st.composite
 def pedigrees(draw):
-    n = draw(st.integers(2, 48))
+    n = draw(st.integers(2, 72))
     n_founders = draw(st.integers(1, min(n, 8)))
     father, mother = [-1] * n, [-1] * n
     sex = [draw(st.integers(1, 2)) for _ in range(n)]
     sex[0] = 1
     if n > 1:
         sex[1] = 2
+    window = draw(st.sampled_from([0, 0, 3, 5, 8]))         # > 0: deep, narrow pedigrees (lossy Float32 stores)
     for i in range(n_founders, n):
-        males = [j for j in range(i) if sex[j] == 1]
-        females = [j for j in range(i) if sex[j] == 2]
+        lo = max(0, i - window) if window else 0
+        males = [j for j in range(lo, i) if sex[j] == 1]
+        females = [j for j in range(lo, i) if sex[j] == 2]
         kind = draw(st.integers(0, 9))                      # 0: no parent, 1: father only, 2: mother only, else both
         if kind != 0 and kind != 2 and males:
             father[i] = draw(st.sampled_from(males))
