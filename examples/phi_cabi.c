@@ -32,13 +32,14 @@ int main(int argc, char **argv) {
     CHECK(genlib_genealogy_csv(argv[1], 1, &ped));                 /* gen.genealogy(path), src/create.jl:131-189 */
     const int64_t n = genlib_pedigree_n(ped);
     int32_t *father = malloc((size_t)n * sizeof *father), *mother = malloc((size_t)n * sizeof *mother);
-    int64_t *pro = malloc((size_t)n * sizeof *pro);
-    CHECK(genlib_pedigree_arrays(ped, NULL, father, mother, NULL));
+    int64_t *pro = malloc((size_t)n * sizeof *pro), *ids = malloc((size_t)n * sizeof *ids);
+    CHECK(genlib_pedigree_arrays(ped, ids, father, mother, NULL));
     const int64_t n_pro = genlib_pedigree_pro(ped, pro);           /* gen.pro(ped), src/identify.jl:35-39 */
     int32_t *ranks = malloc((size_t)n_pro * sizeof *ranks);
     CHECK(genlib_pedigree_ranks(ped, n_pro, pro, ranks));
     genlib_plan *plan = NULL;
-    CHECK(genlib_plan_create_scheduled((int32_t)n, father, mother, (int32_t)n_pro, ranks, 1, schedule, &plan));
+    /* the IDs order the founders in sparse_phi's queue (src/identify.jl:15-19); phi ignores them */
+    CHECK(genlib_plan_create_ex((int32_t)n, father, mother, ids, (int32_t)n_pro, ranks, 1, schedule, &plan));
     const int32_t nu = genlib_plan_n_unique(plan);
     float *phi = malloc((size_t)nu * nu * sizeof *phi);
     genlib_engine *eng = NULL;
@@ -52,6 +53,6 @@ int main(int argc, char **argv) {
     genlib_engine_destroy(eng);
     genlib_plan_destroy(plan);
     genlib_pedigree_destroy(ped);
-    free(father); free(mother); free(pro); free(ranks); free(phi);
+    free(father); free(mother); free(pro); free(ids); free(ranks); free(phi);
     return 0;
 }

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgenlib_cuda.so")
 
 OK, EINVAL, EKEY, EORDER, ECUDA, ENOMEM, ECOMM = range(7)
-SCHEDULES = {"phi": 0, "sparse_phi": 1}
+SCHEDULES = {"phi": 0, "sparse_phi": 1, "sparse_phi_symmetric": 2}
 NUMERICS = {"reference": 0, "fp64": 1, 0: 0, 1: 1}
 DTYPES = {np.dtype(np.float32): 0, np.dtype(np.float64): 1}
 
@@ -65,6 +65,8 @@ SYMBOLS = {
     "genlib_pedigree_ranks": (C.c_int, [_P, C.c_int64, _P, _P]),
     "genlib_plan_create": (C.c_int, [C.c_int32, _P, _P, C.c_int32, _P, C.c_int32, C.POINTER(_P)]),
     "genlib_plan_create_scheduled": (C.c_int, [C.c_int32, _P, _P, C.c_int32, _P, C.c_int32, C.c_int, C.POINTER(_P)]),
+    "genlib_plan_create_ex": (C.c_int, [C.c_int32, _P, _P, _P, C.c_int32, _P, C.c_int32, C.c_int, C.POINTER(_P)]),
+    "genlib_plan_layer_ranks": (C.c_int, [_P, C.c_int32, _P]),
     "genlib_plan_schedule": (C.c_int32, [_P]),
     "genlib_plan_destroy": (None, [_P]),
     "genlib_plan_n_unique": (C.c_int32, [_P]),

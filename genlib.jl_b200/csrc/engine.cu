@@ -187,7 +187,7 @@ struct genlib_engine {
     DevBuf<int32_t> mem_ind, mem_slot, mem_fam, mem_lrow, fam_pf, fam_pm, fam_pf_lrow, fam_pm_lrow, fam_start,
         fam_minrank, fam_maxrank, mt_min, mt_max, mt_fam0, mt_nfam, mt_m0, mt_cnt, pro_slot, own_pro_row, live_lrow;
     DevBuf<int8_t> fam_pf_owner, fam_pm_owner, live_owner, mem_gowner;
-    DevBuf<int32_t> mem_glrow;
+    DevBuf<int32_t> mem_glrow, mem_rank;
     DevBuf<uint8_t> flags;
     DevBuf<double> acc;
     std::vector<int32_t> own_pro;          // proband indices (output rows) this rank owns, ascending
@@ -244,6 +244,7 @@ size_t engine_bytes(const Plan &P, int numerics, int g) {
          2 * DevBuf<int32_t>::padded(P.pro_slot.size()) + DevBuf<int32_t>::padded(P.live_lrow.size()) +
          2 * DevBuf<int8_t>::padded(P.fam_pf.size()) + DevBuf<int8_t>::padded(P.live_owner.size()) +
          DevBuf<int8_t>::padded(P.mem_gowner.size()) + DevBuf<int32_t>::padded(P.mem_glrow.size()) +
+         DevBuf<int32_t>::padded(P.mem_rank.size()) +
          DevBuf<uint8_t>::padded(P.flags.size()) + DevBuf<double>::padded(2);
     return b;
 }
@@ -301,7 +302,7 @@ int launch_layers(genlib_engine &E, bool timed) {
     if (expand_smem_max > 227 * 1024) return fail(GENLIB_EINVAL, "couple tile too wide for the expand kernel");
     auto expand_fn = E.world > 1 ? expand_kernel<T, true> : expand_kernel<T, false>;
     CU(cudaFuncSetAttribute(expand_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem_max));
-    const bool stored = P.schedule == kScheduleSparsePhi;      // sparse_phi's arithmetic (Float32 halves of stored values)
+    const bool stored = sparse_schedule(P.schedule);           // sparse_phi's arithmetic (Float32 halves of stored values)
     auto cross_fn = stored ? cross_kernel<T, true> : cross_kernel<T, false>;
     auto couple_fn = stored ? couple_kernel<T, true> : couple_kernel<T, false>;
     const size_t cross_smem_piped = std::max<size_t>(cross_smem, 120 * 1024);    // one CTA per SM
@@ -380,6 +381,12 @@ int launch_layers(genlib_engine &E, bool timed) {
             const size_t smem = (size_t)kEWarps * 2 * expand_stage_bytes<T>(a.vstride);
             expand_fn<<<grid, kExpandThreads, smem, E.stream>>>(A, ld, V, Vt, Dg, E.peers, a);
             launches++;
+            if (P.schedule == kScheduleSparsePhi && L.n_new > 1) {      // the reference's misfiled kinships read as 0
+                if (E.world > 1 && P.guest_cap[E.rank] > 0) return fail(GENLIB_EINVAL, "sparse_phi schedule with guest rows is not supported");
+                dim3 mgrid((unsigned)a.own_nm, (unsigned)std::min<int64_t>((L.n_new + 4 * kThreads - 1) / (4 * kThreads), 65535));
+                misfile_kernel<T><<<mgrid, kThreads, 0, E.stream>>>(A, ld, E.mem_rank.p + L.mem_off, a);
+                launches++;
+            }
         }
         if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
         launch_barrier(E);                 // all new rows exist everywhere before the next layer reads them
@@ -436,7 +443,7 @@ int create_engine(const genlib_plan *plan, int numerics, int device, int rank, g
     *out = nullptr;
     if (numerics != GENLIB_NUMERICS_REFERENCE && numerics != GENLIB_NUMERICS_FP64) return fail(GENLIB_EINVAL, "unknown numerics mode");
     const Plan &P = plan->p;
-    if (P.schedule == kScheduleSparsePhi && numerics != GENLIB_NUMERICS_REFERENCE)
+    if (sparse_schedule(P.schedule) && numerics != GENLIB_NUMERICS_REFERENCE)
         return fail(GENLIB_EINVAL, "the sparse_phi schedule stores Float32 (numerics must be GENLIB_NUMERICS_REFERENCE)");
     if (rank < 0 || rank >= P.world) return fail(GENLIB_EINVAL, "rank outside the plan's world");
     if (P.world > kMaxWorld) return fail(GENLIB_EINVAL, "the engine supports at most 16 ranks");
@@ -502,6 +509,7 @@ int create_engine(const genlib_plan *plan, int numerics, int device, int rank, g
         E->fam_pf_owner.place(cur, P.fam_pf_owner.size()); E->fam_pm_owner.place(cur, P.fam_pm_owner.size());
         E->live_owner.place(cur, P.live_owner.size());
         E->mem_gowner.place(cur, P.mem_gowner.size()); E->mem_glrow.place(cur, P.mem_glrow.size());
+        E->mem_rank.place(cur, P.mem_rank.size());
         E->flags.place(cur, P.flags.size()); E->acc.place(cur, 2);
         if ((size_t)(cur - base) > need) return fail(GENLIB_EINVAL, "internal: arena layout overflow");
         if ((size_t)(static_cast<unsigned char *>(E->A) - base) != off_A() ||
@@ -538,6 +546,7 @@ int create_engine(const genlib_plan *plan, int numerics, int device, int rank, g
     CU(E->live_lrow.upload(P.live_lrow, E->stream));
     CU(E->mem_gowner.upload(P.mem_gowner, E->stream));
     CU(E->mem_glrow.upload(P.mem_glrow, E->stream));
+    CU(E->mem_rank.upload(P.mem_rank, E->stream));
     CU(E->flags.upload(P.flags, E->stream));
     CU(cudaStreamSynchronize(E->stream));
     E->peers.A[rank] = E->A; E->peers.Vrow[rank] = E->Vrow; E->bars.flags[rank] = E->bar_flags;
@@ -595,6 +604,11 @@ int genlib_plan_create(int32_t n, const int32_t *father, const int32_t *mother, 
 
 int genlib_plan_create_scheduled(int32_t n, const int32_t *father, const int32_t *mother, int32_t n_pro,
                                  const int32_t *proband, int32_t world, int schedule, genlib_plan **out) {
+    return genlib_plan_create_ex(n, father, mother, nullptr, n_pro, proband, world, schedule, out);
+}
+
+int genlib_plan_create_ex(int32_t n, const int32_t *father, const int32_t *mother, const int64_t *ids, int32_t n_pro,
+                          const int32_t *proband, int32_t world, int schedule, genlib_plan **out) {
     if (!out) return fail(GENLIB_EINVAL, "genlib_plan_create: out is null");
     *out = nullptr;
     std::unique_ptr<genlib_plan> pl(new (std::nothrow) genlib_plan);
@@ -604,7 +618,7 @@ int genlib_plan_create_scheduled(int32_t n, const int32_t *father, const int32_t
     int rc;
     try {
         adopt_retired_storage(pl->p);        // the arrays of the last destroyed plan, already paged in
-        rc = build_plan(n, father, mother, n_pro, proband, world, schedule, pl->p, err);
+        rc = build_plan(n, father, mother, ids, n_pro, proband, world, schedule, pl->p, err);
     } catch (const std::bad_alloc &) {
         return fail(GENLIB_ENOMEM, "out of host memory while planning");
     }
@@ -656,6 +670,15 @@ int genlib_plan_layer_arrays(const genlib_plan *plan, int32_t layer, int32_t *me
         if (fam_father_slot) fam_father_slot[f] = P.fam_pf[L.fam_off + f];
         if (fam_mother_slot) fam_mother_slot[f] = P.fam_pm[L.fam_off + f];
     }
+    return GENLIB_OK;
+}
+
+int genlib_plan_layer_ranks(const genlib_plan *plan, int32_t layer, int32_t *member_rank) {
+    if (!plan || !member_rank || layer < 0 || layer >= (int32_t)plan->p.layers.size()) return fail(GENLIB_EINVAL, "bad layer");
+    const Plan &P = plan->p;
+    const Layer &L = P.layers[layer];
+    for (int32_t q = 0; q < L.n_new; q++)
+        member_rank[q] = P.mem_rank.empty() ? P.mem_ind[L.mem_off + q] : P.mem_rank[L.mem_off + q];
     return GENLIB_OK;
 }
 

@@ -647,6 +647,24 @@ expand_kernel(T *__restrict__ A, int64_t ld, const T *__restrict__ V, const T *_
 }
 
 // =====================================================================================
+// misfile_kernel (GENLIB_SCHEDULE_SPARSE_PHI only).  sparse_phi FILES a kinship under
+// phi[earlier processed][later processed] (compute.jl:393) but every look-up reads
+// phi[lower rank][higher rank] (:36-40, :350-358, :367-389): between two individuals whose queue
+// order inverts their rank order the stored value is never found again and the reference goes on
+// as if the pair were unrelated.  Both orders follow the depth, so this only happens between the
+// members of ONE layer; the frontier keeps what a look-up finds, 0.  grid (own rows, column chunks).
+// =====================================================================================
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+misfile_kernel(T *__restrict__ A, int64_t ld, const int32_t *__restrict__ mem_rank, LayerArgs L) {
+    const int i = L.own_m0 + blockIdx.x;
+    const int seq_i = L.mem_ind[i], rank_i = mem_rank[i];
+    T *row = A + (int64_t)L.mem_lrow[i] * ld;
+    for (int j = blockIdx.y * kThreads + threadIdx.x; j < L.n_new; j += gridDim.y * kThreads)
+        if (j != i && ((seq_i > L.mem_ind[j]) != (rank_i > mem_rank[j]))) row[L.mem_slot[j]] = (T)0;
+}
+
+// =====================================================================================
 // proband gather (compute.jl:303: the last frontier, rows/columns in probandIDs order).
 // rows[] are LOCAL rows of this rank's probands, cols[] the global slots of all probands.
 // =====================================================================================

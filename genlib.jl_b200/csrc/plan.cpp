@@ -162,21 +162,21 @@ void release_plan_cache() {
     g_retired.reset(); g_scratch.reset();
 }
 
-static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const int32_t *mother, int32_t n_pro,
-                           const int32_t *proband, int32_t world, int schedule, Plan &P, std::string &err);
+static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const int32_t *mother, const int64_t *ids,
+                           int32_t n_pro, const int32_t *proband, int32_t world, int schedule, Plan &P, std::string &err);
 
-int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t n_pro,
+int build_plan(int32_t n, const int32_t *father, const int32_t *mother, const int64_t *ids, int32_t n_pro,
                const int32_t *proband, int32_t world, int schedule, Plan &P, std::string &err) {
     std::unique_ptr<Scratch> W = take_scratch();
-    const int rc = build_plan_with(*W, n, father, mother, n_pro, proband, world, schedule, P, err);
+    const int rc = build_plan_with(*W, n, father, mother, ids, n_pro, proband, world, schedule, P, err);
     give_scratch(std::move(W));
     return rc;
 }
 
-static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const int32_t *mother, int32_t n_pro,
-                           const int32_t *proband, int32_t world, int schedule, Plan &P, std::string &err) {
+static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const int32_t *mother, const int64_t *ids,
+                           int32_t n_pro, const int32_t *proband, int32_t world, int schedule, Plan &P, std::string &err) {
     P.reset();
-    if (schedule != kSchedulePhi && schedule != kScheduleSparsePhi) { err = "unknown schedule"; return GENLIB_EINVAL; }
+    if (schedule != kSchedulePhi && !sparse_schedule(schedule)) { err = "unknown schedule"; return GENLIB_EINVAL; }
     P.schedule = schedule;
     if (n < 0 || n_pro < 0 || world < 1 || (n > 0 && (!father || !mother)) || (n_pro > 0 && !proband)) {
         err = "genlib_plan_create: null pointer or negative size";
@@ -238,10 +238,10 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
     // is climbed.  The layer is then the depth, `seq` (the position in that queue) replaces the rank
     // wherever the kernels decide who is climbed, and eviction is sparse_phi's own rule (:400-430).
     // The sweep above marked the ancestors of the probands (branching, :323); re-label them.
-    const bool by_seq = schedule == kScheduleSparsePhi;         // members of a layer in processing order
+    const bool by_seq = sparse_schedule(schedule);              // members of a layer in processing order
     std::vector<int32_t> &seq_order = W.seq_order; seq_order.clear();
     std::vector<int32_t> &orient = W.orient;
-    if (schedule == kScheduleSparsePhi) {
+    if (by_seq) {
         std::vector<int32_t> &cstart = W.cstart, &clist = W.clist, &depth = W.depth;
         cstart.assign((size_t)n + 2, 0);
         depth.assign((size_t)n, 0);
@@ -264,8 +264,12 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         }                                                       // now children of p = clist[cstart[p] .. cstart[p+1])
         orient.assign((size_t)n, -1);
         seq_order.reserve(hist.empty() ? 0 : (size_t)n);
-        for (int32_t x = 0; x < n; x++)                         // founder(isolated_pedigree): rank order (:335-339)
+        for (int32_t x = 0; x < n; x++)                         // founder(isolated_pedigree) (:335-339) ...
             if (pre[x].h >= 0 && father[x] < 0 && mother[x] < 0) seq_order.push_back(x);
+        if (ids)                                                // ... is sorted by ID (identify.jl:15-19)
+            std::sort(seq_order.begin(), seq_order.end(), [ids](int32_t a, int32_t b) {
+                return ids[a] != ids[b] ? ids[a] < ids[b] : a < b;
+            });
         for (size_t head = 0; head < seq_order.size(); head++) {
             const int32_t i = seq_order[head];
             orient[i] = (int32_t)head;                          // processed: founder_index != 0 from here on
@@ -340,6 +344,7 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
     {   // upper bounds (untouched reserve costs nothing): members + alignment padding, couples + rank padding
         const size_t mcap = lstart[S] + 4 * (size_t)S, fcap = lstart[S] + 4 * (size_t)world * (size_t)S;
         for (auto *v : {&P.mem_ind, &P.mem_slot, &P.mem_fam, &P.mem_lrow, &P.mem_glrow}) v->reserve(mcap);
+        if (by_seq) P.mem_rank.reserve(mcap);
         P.mem_gowner.reserve(mcap);
         for (auto *v : {&P.fam_pf, &P.fam_pm, &P.fam_pf_lrow, &P.fam_pm_lrow, &P.fam_minrank, &P.fam_maxrank}) v->reserve(fcap);
         P.fam_pf_owner.reserve(fcap); P.fam_pm_owner.reserve(fcap); P.fam_start.reserve(fcap + (size_t)S);
@@ -458,6 +463,7 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         while (P.mem_ind.size() % 4) {
             P.mem_ind.push_back(0); P.mem_slot.push_back(0); P.mem_fam.push_back(0); P.mem_lrow.push_back(0);
             P.mem_gowner.push_back(-1); P.mem_glrow.push_back(-1);
+            if (by_seq) P.mem_rank.push_back(0);
         }
         L.mem_off = P.mem_ind.size();
         L.fam_off = P.fam_pf.size();
@@ -571,6 +577,7 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         P.mem_ind.resize(L.mem_off + (size_t)nn); P.mem_slot.resize(L.mem_off + (size_t)nn);
         P.mem_fam.resize(L.mem_off + (size_t)nn); P.mem_lrow.resize(L.mem_off + (size_t)nn);
         P.mem_gowner.resize(L.mem_off + (size_t)nn, -1); P.mem_glrow.resize(L.mem_off + (size_t)nn, -1);
+        if (by_seq) P.mem_rank.resize(L.mem_off + (size_t)nn);
         {
             int32_t *mi = P.mem_ind.data() + L.mem_off, *ms = P.mem_slot.data() + L.mem_off;
             int32_t *mf = P.mem_fam.data() + L.mem_off, *ml = P.mem_lrow.data() + L.mem_off;
@@ -582,6 +589,7 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
                 hx.slot = s; hx.lrow = lr; hx.owner = (int8_t)g;
                 if (guests) { born_layer[x] = t; mem_pos_of[x] = L.mem_off + (size_t)q; }
                 mi[q] = by_seq ? orient[x] : x; ms[q] = s; mf[q] = newid[f]; ml[q] = lr;
+                if (by_seq) P.mem_rank[L.mem_off + (size_t)q] = x;
             }
         }
         P.fam_pf.resize(L.fam_off + (size_t)nf, -1); P.fam_pm.resize(L.fam_off + (size_t)nf, -1);

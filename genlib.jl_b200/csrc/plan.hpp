@@ -30,7 +30,12 @@ constexpr int kMaxTileFam = 64;  // couples per member tile (bounds the couple t
 //                                    one Float32 rounding per step (unrounded Float64 inside a step)
 //   sparse_phi (compute.jl:321-447)  layers by depth below the founders, the individual processed
 //                                    later by its queue is climbed, every stored entry is Float32
-constexpr int kSchedulePhi = 0, kScheduleSparsePhi = 1;
+//   sparse_phi, symmetric            the same schedule, but every kinship is filed where it is looked up:
+//                                    the reference files phi[earlier][later] and reads phi[lower rank][higher
+//                                    rank] (compute.jl:393 vs :367-389), losing the pairs whose queue order
+//                                    inverts their rank order; kScheduleSparsePhi reproduces that loss
+constexpr int kSchedulePhi = 0, kScheduleSparsePhi = 1, kScheduleSparsePhiSymmetric = 2;
+inline bool sparse_schedule(int s) { return s == kScheduleSparsePhi || s == kScheduleSparsePhiSymmetric; }
 
 constexpr uint8_t kFlagLive = 1;     // slot holds an individual that is live before the step
 constexpr uint8_t kFlagCarried = 2;  // ... and stays live after it
@@ -61,6 +66,7 @@ struct Plan {
     std::vector<int32_t> pro_ind, pro_slot;
     // concatenated per-layer arrays
     std::vector<int32_t> mem_ind, mem_slot, mem_fam;   // family-major order inside a layer
+    std::vector<int32_t> mem_rank;                     // sparse_phi schedules: the members' pedigree ranks (mem_ind = queue position)
     std::vector<int32_t> fam_pf, fam_pm, fam_start;    // parents as slots (-1 = none)
     std::vector<uint8_t> flags;
     std::vector<int32_t> fam_minrank, fam_maxrank;     // rank range of a couple's members
@@ -90,7 +96,7 @@ struct Plan {
     // genlib_plan_create, because first-touch page faults on a few hundred MB of fresh vectors
     // cost more than the planning itself.
     template <class F> void each_array(F &&f) {
-        f(layers); f(pro_ind); f(pro_slot); f(mem_ind); f(mem_slot); f(mem_fam); f(fam_pf); f(fam_pm);
+        f(layers); f(pro_ind); f(pro_slot); f(mem_ind); f(mem_rank); f(mem_slot); f(mem_fam); f(fam_pf); f(fam_pm);
         f(fam_start); f(flags); f(fam_minrank); f(fam_maxrank); f(mtile_minrank); f(mtile_maxrank);
         f(mtile_fam0); f(mtile_nfam); f(mtile_m0); f(mtile_cnt); f(fam_base); f(mem_base); f(mem_lrow);
         f(fam_pf_owner); f(fam_pm_owner); f(fam_pf_lrow); f(fam_pm_lrow); f(live_owner); f(live_lrow);
@@ -115,7 +121,9 @@ inline int32_t pad32(int32_t x) { return ((x > 0 ? x : 1) + 31) / 32 * 32; }
 int set_error(int code, const std::string &msg);
 
 // Returns 0 or a GENLIB_E* status; `err` receives a message.
-int build_plan(int32_t n, const int32_t *father, const int32_t *mother, int32_t n_pro,
+// `ids` (nullable, by rank) orders the founders in sparse_phi's queue (founder() sorts by ID,
+// identify.jl:15-19); without it they are taken in rank order.
+int build_plan(int32_t n, const int32_t *father, const int32_t *mother, const int64_t *ids, int32_t n_pro,
                const int32_t *proband, int32_t world, int schedule, Plan &plan, std::string &err);
 
 }  // namespace genlib

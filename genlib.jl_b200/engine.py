@@ -20,16 +20,20 @@ from .pedigree import Pedigree, pro
 class Plan:
     """Host schedule (levels, Kirkpatrick frontier, slots). Needs no GPU."""
 
-    def __init__(self, father, mother, proband_ranks, world: int = 1, schedule: str = "phi"):
+    def __init__(self, father, mother, proband_ranks, world: int = 1, schedule: str = "phi", ids=None):
         self.father = np.ascontiguousarray(father, np.int32)
         self.mother = np.ascontiguousarray(mother, np.int32)
         self.probands = np.ascontiguousarray(proband_ranks, np.int32)
         if len(self.father) != len(self.mother):
             raise ValueError("father and mother must have the same length")
+        # sparse_phi's queue starts with the founders sorted by ID (identify.jl:15-19)
+        self.ids = None if ids is None else np.ascontiguousarray(ids, np.int64)
+        if self.ids is not None and len(self.ids) != len(self.father):
+            raise ValueError("ids must have one entry per individual")
         h = C.c_void_p()
-        check(lib().genlib_plan_create_scheduled(len(self.father), ptr(self.father), ptr(self.mother),
-                                                 len(self.probands), ptr(self.probands), world,
-                                                 _lib.SCHEDULES[schedule], C.byref(h)))
+        check(lib().genlib_plan_create_ex(len(self.father), ptr(self.father), ptr(self.mother), ptr(self.ids),
+                                          len(self.probands), ptr(self.probands), world,
+                                          _lib.SCHEDULES[schedule], C.byref(h)))
         self._h = h
         self.world = world
         self.schedule = schedule
@@ -66,6 +70,9 @@ class Plan:
         flags = np.zeros(max(self.capacity, 1), np.uint8)
         check(lib().genlib_plan_layer_flags(self._h, layer, ptr(flags)))
         out["live_flags"] = flags
+        out["member_rank"] = np.zeros(n, np.int32)
+        if n:
+            check(lib().genlib_plan_layer_ranks(self._h, layer, ptr(out["member_rank"])))
         return out
 
     def layer_shard(self, layer: int) -> dict:
@@ -258,7 +265,8 @@ def phi_distributed(pedigree: Pedigree, probandIDs=None, *, numerics="reference"
     rank, world = dist.get_rank(), dist.get_world_size()
     IDs = pro(pedigree) if probandIDs is None else np.asarray(probandIDs, np.int64)
     ranks = pedigree.rank_of(IDs)
-    plan = Plan(pedigree.father, pedigree.mother, ranks, world=world, schedule=schedule)
+    plan = Plan(pedigree.father, pedigree.mother, ranks, world=world, schedule=schedule,
+                ids=pedigree.ids if schedule != "phi" else None)
     n = plan.n_unique
     if n == 0:
         res = np.zeros((0, 0), dtype)
@@ -327,10 +335,16 @@ def f(pedigree: Pedigree, IDs, *, device: int = -1) -> np.ndarray:
 
 
 class KinshipMatrix:
-    """gen.KinshipMatrix (src/compute.jl:31-46): the kinships `sparse_phi` keeps, indexed by ID.
+    """gen.KinshipMatrix (src/compute.jl:31-46): what `sparse_phi` returns, indexed by ID.
 
-    Only the probands are left when `sparse_phi` returns, each with its self-kinship and its
-    non-zero kinships towards higher-ranked probands (src/compute.jl:363-395)."""
+    `k[ID1, ID2]` is the reference's getindex (:36-40): the entry filed under phi[lower rank][higher
+    rank], 0 when there is none.  The reference files a kinship under phi[earlier processed][later
+    processed] (:393); where sparse_phi's queue order inverts the rank order of two individuals of one
+    depth the value is never found again, reads as 0 here as there, and is missing from everything
+    computed from it.  `stored` counts the entries a look-up can find (the diagonal and the non-zero
+    lower->higher pairs); the reference's `show` line (:42-46) also counts misfiled and orphaned keys,
+    which no look-up ever reads -- they coincide when the queue order follows the ranks (e.g. the
+    reference's own test, test/runtests.jl:56)."""
 
     def __init__(self, ids: np.ndarray, ranks: np.ndarray, dense: np.ndarray):
         order = np.argsort(ranks, kind="stable")
@@ -344,11 +358,10 @@ class KinshipMatrix:
 
     @property
     def stored(self) -> int:
-        """Entries the reference's Dict-of-Dicts holds: the diagonal and the non-zero pairs, once each."""
         return int(np.count_nonzero(np.triu(self._dense, 1))) + len(self._ids)
 
     def to_dict(self) -> dict:
-        """{lower-ranked ID: {higher-ranked ID: kinship}}, the layout of `KinshipMatrix.dict`."""
+        """{lower-ranked ID: {higher-ranked ID: kinship}}: the entries of `KinshipMatrix.dict` a look-up finds."""
         out = {}
         for k, i in enumerate(self._ids):
             row = self._dense[k]
@@ -362,17 +375,21 @@ class KinshipMatrix:
         return f"{len(self)}\u00d7{len(self)} KinshipMatrix with {self.stored} stored entries."
 
 
-def sparse_phi(pedigree: Pedigree, probandIDs=None, *, device: int = -1) -> KinshipMatrix:
+def sparse_phi(pedigree: Pedigree, probandIDs=None, *, device: int = -1, symmetric: bool = False) -> KinshipMatrix:
     """gen.sparse_phi(pedigree, probandIDs = pro(pedigree)) (src/compute.jl:321-447) on the GPU.
 
-    Same engine, planned for sparse_phi's own floating-point schedule (processing order of its
-    queue, the later-processed individual of a pair is climbed, every stored kinship a Float32),
-    so the values are bit-identical to the reference's KinshipMatrix.  SURVEY.md 8(f) N2."""
+    Same engine, planned for sparse_phi's own floating-point schedule: founders in ID order
+    (identify.jl:15-19), then its queue; the later-processed individual of a pair is climbed; every
+    stored kinship is a Float32 and is halved in Float32; kinships the reference misfiles (see
+    KinshipMatrix) read as 0.  Look-ups are bit-identical to the reference's KinshipMatrix.
+    symmetric=True keeps the misfiled kinships instead (the consistent variant of the schedule).
+    SURVEY.md 8(f) N2."""
     ids = pro(pedigree) if probandIDs is None else np.asarray(probandIDs, np.int64)
     ranks = pedigree.rank_of(ids)                                         # KeyError on an unknown ID
     _, first = np.unique(ranks, return_index=True)                        # duplicates collapse (Dict keys)
     first.sort()
-    plan = Plan(pedigree.father, pedigree.mother, ranks, schedule="sparse_phi")
+    plan = Plan(pedigree.father, pedigree.mother, ranks, ids=pedigree.ids,
+                schedule="sparse_phi_symmetric" if symmetric else "sparse_phi")
     n = plan.n_unique
     if n == 0:
         return KinshipMatrix(np.zeros(0, np.int64), np.zeros(0, np.int32), np.zeros((0, 0), np.float32))

@@ -94,17 +94,23 @@ end
     sparse_phi(pedigree, probandIDs = pro(pedigree)) -> GenLib.KinshipMatrix
 
 `gen.sparse_phi` (src/compute.jl:321-447) on the GPU: the same engine, planned for sparse_phi's own
-floating-point schedule (`GENLIB_SCHEDULE_SPARSE_PHI`), so the values are the reference's bits.  The
-dense result is folded back into the reference's `KinshipMatrix` (Dict keyed lower rank -> higher rank,
-zeros not stored, src/compute.jl:31-40, 391-394).
+floating-point schedule (`GENLIB_SCHEDULE_SPARSE_PHI`), so every look-up `ϕ[ID₁, ID₂]` returns the
+reference's bits -- including the 0 the reference returns for a kinship it filed under
+`ϕ[earlier][later]` but looks up under `ϕ[lower rank][higher rank]` (src/compute.jl:393 vs :36-40).
+`symmetric = true` keeps those kinships (`GENLIB_SCHEDULE_SPARSE_PHI_SYMMETRIC`).  The dense result is
+folded back into the reference's `KinshipMatrix` (Dict keyed lower rank -> higher rank, zeros not
+stored, src/compute.jl:31-40, 391-394); misfiled and orphaned keys, which no look-up reads, are not
+recreated, so `show` may count fewer entries than the reference's.
 """
-function sparse_phi(pedigree::GenLib.Pedigree, probandIDs::Vector{Int} = GenLib.pro(pedigree); device::Integer = -1)
+function sparse_phi(pedigree::GenLib.Pedigree, probandIDs::Vector{Int} = GenLib.pro(pedigree);
+                    device::Integer = -1, symmetric::Bool = false)
     father, mother = flatten(pedigree)
     ranks = Int32[pedigree[ID].rank - 1 for ID in probandIDs]           # KeyError on unknown ID
+    ids = Int64[individual.ID for individual in values(pedigree)]      # founder() sorts by ID (src/identify.jl:15-19)
     plan = Ref{Ptr{Cvoid}}(C_NULL)
-    check(ccall((:genlib_plan_create_scheduled, libgenlib[]), Cint,
-                (Int32, Ptr{Int32}, Ptr{Int32}, Int32, Ptr{Int32}, Int32, Cint, Ptr{Ptr{Cvoid}}),
-                length(father), father, mother, length(ranks), ranks, 1, 1, plan))
+    check(ccall((:genlib_plan_create_ex, libgenlib[]), Cint,
+                (Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Int64}, Int32, Ptr{Int32}, Int32, Cint, Ptr{Ptr{Cvoid}}),
+                length(father), father, mother, ids, length(ranks), ranks, 1, symmetric ? 2 : 1, plan))
     try
         n = ccall((:genlib_plan_n_unique, libgenlib[]), Int32, (Ptr{Cvoid},), plan[])
         dense = Matrix{Float32}(undef, n, n)

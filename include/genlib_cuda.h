@@ -133,11 +133,25 @@ int genlib_plan_create(int32_t n, const int32_t *father, const int32_t *mother, 
  *       queue from the founders (:335-339, :431-439), of a pair the one processed later is climbed
  *       (:363-395), every stored kinship is a Float32 (:331), rows are evicted when the last child has
  *       been processed (:400-430).  The engine then returns, densely, the values `sparse_phi` keeps
- *       for the probands; numerics must be GENLIB_NUMERICS_REFERENCE. */
+ *       for the probands; numerics must be GENLIB_NUMERICS_REFERENCE.
+ *   GENLIB_SCHEDULE_SPARSE_PHI_SYMMETRIC  the same schedule with every kinship filed where it is looked
+ *       up.  The reference files phi[rank of the earlier processed][rank of the later] (:393) and reads
+ *       phi[lower rank][higher rank] (:36-40, :367-389); when the queue order of two individuals of the
+ *       same depth inverts their rank order the value is never found again and the reference carries on
+ *       as if they were unrelated.  GENLIB_SCHEDULE_SPARSE_PHI reproduces that (bit-identical to the
+ *       reference's KinshipMatrix look-ups); this variant keeps those kinships. */
 #define GENLIB_SCHEDULE_PHI 0
 #define GENLIB_SCHEDULE_SPARSE_PHI 1
+#define GENLIB_SCHEDULE_SPARSE_PHI_SYMMETRIC 2
 int genlib_plan_create_scheduled(int32_t n, const int32_t *father, const int32_t *mother, int32_t n_pro,
                                  const int32_t *proband, int32_t world, int schedule, genlib_plan **out);
+/* The same with the individuals' IDs (by rank; may be NULL).  sparse_phi seeds its queue with
+ * founder(isolated_pedigree), which is sorted by ID (src/identify.jl:15-19 via src/compute.jl:335-339):
+ * the sparse_phi schedules need the IDs to process the founders in that order.  Without them the
+ * founders are taken in rank order, which is the reference's order only when founder IDs ascend with
+ * the rank.  Ignored by GENLIB_SCHEDULE_PHI. */
+int genlib_plan_create_ex(int32_t n, const int32_t *father, const int32_t *mother, const int64_t *ids,
+                          int32_t n_pro, const int32_t *proband, int32_t world, int schedule, genlib_plan **out);
 int32_t genlib_plan_schedule(const genlib_plan *plan);
 void genlib_plan_destroy(genlib_plan *plan);
 int32_t genlib_plan_n_unique(const genlib_plan *plan);
@@ -154,6 +168,9 @@ int64_t genlib_plan_device_bytes(const genlib_plan *plan, int numerics, int32_t 
 int genlib_plan_layer_arrays(const genlib_plan *plan, int32_t layer, int32_t *member_ind,
                              int32_t *member_slot, int32_t *member_fam, int32_t *fam_father_slot,
                              int32_t *fam_mother_slot, int32_t *member_owner);
+/* Pedigree rank of each member (n_new entries).  For GENLIB_SCHEDULE_PHI this equals member_ind; for
+ * the sparse_phi schedules member_ind is the position in sparse_phi's queue. */
+int genlib_plan_layer_ranks(const genlib_plan *plan, int32_t layer, int32_t *member_rank);
 /* Row sharding of a layer (plans built with world > 1; world == 1 puts everything on rank 0):
  * fam_base / mem_base have world + 1 entries (rank g owns couples [fam_base[g], fam_base[g+1])
  * and members [mem_base[g], mem_base[g+1])); member_lrow is the local row of each member on

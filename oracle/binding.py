@@ -44,8 +44,8 @@ def lib():
         L.oracle_phi_ranks.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                        C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_int,
                                        C.c_void_p, C.c_int]
-        L.oracle_sparse_phi_ranks.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
-                                              C.POINTER(C.c_int), C.POINTER(C.c_int64)]
+        L.oracle_sparse_phi_ranks.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                              C.c_int, C.c_void_p, C.POINTER(C.c_int), C.c_void_p, C.c_void_p]
         L.oracle_set_time_budget.argtypes = [C.c_double]
         L.oracle_phi_mean.restype = C.c_double
         L.oracle_phi_mean.argtypes = [C.c_void_p, C.c_int]
@@ -151,20 +151,30 @@ def phi_ranks(father, mother, pro_ranks, nthreads: int = 0, max_steps: int = -1)
     return res, steps[:rc].copy()
 
 
-def sparse_phi_ranks(father, mother, pro_ranks):
-    """gen.sparse_phi on flat rank arrays: (dense n_unique x n_unique Float32 values of the
-    KinshipMatrix, number of stored entries).  src/compute.jl:321-447."""
+def sparse_phi_ranks(father, mother, pro_ranks, ids=None, directed: bool = True, full: bool = False):
+    """gen.sparse_phi on flat rank arrays, transliterated (src/compute.jl:321-447): the dense
+    n_unique x n_unique Float32 matrix `getindex` would return and the number of stored entries of
+    the `show` line.  `ids` (by rank) orders the founders in the queue like founder() does
+    (identify.jl:15-19; None: rank order).  directed=False is the consistent variant that files every
+    kinship where it is looked up.  full=True returns a dict instead of the count: stored, findable,
+    misfiled, orphans, sum (all stored values, float64) and diag."""
     father = np.ascontiguousarray(father, np.int32)
     mother = np.ascontiguousarray(mother, np.int32)
     pro = np.ascontiguousarray(pro_ranks, np.int32)
-    nu, stored = C.c_int(0), C.c_int64(0)
+    ids = None if ids is None else np.ascontiguousarray(ids, np.int64)
+    nu = C.c_int(0)
+    counts, sums = np.zeros(4, np.int64), np.zeros(2, np.float64)
     out = np.zeros((len(pro), len(pro)), np.float32)
-    rc = lib().oracle_sparse_phi_ranks(len(father), _p(father), _p(mother), len(pro), _p(pro), _p(out),
-                                       C.byref(nu), C.byref(stored))
+    rc = lib().oracle_sparse_phi_ranks(len(father), _p(father), _p(mother), _p(ids), len(pro), _p(pro),
+                                       int(directed), _p(out), C.byref(nu), _p(counts), _p(sums))
     if rc < 0:
         raise KeyError(f"oracle_sparse_phi_ranks status {rc}")
     u = nu.value
-    return out.reshape(-1)[: u * u].reshape(u, u).copy(), int(stored.value)
+    dense = out.reshape(-1)[: u * u].reshape(u, u).copy()
+    if full:
+        return dense, {"stored": int(counts[0]), "findable": int(counts[1]), "misfiled": int(counts[2]),
+                       "orphans": int(counts[3]), "sum": float(sums[0]), "diag": float(sums[1])}
+    return dense, int(counts[0])
 
 
 def bounded_steps(father, mother, pro_ranks, seconds: float, nthreads: int = 0):
@@ -194,3 +204,46 @@ def phi_mean(phi: np.ndarray) -> float:
 
 def num_threads() -> int:
     return lib().oracle_num_threads()
+
+
+# ---- benchmark workloads without the product library ---------------------------------------------
+def _synth():
+    """genlib.jl_b200/synth.py loaded by path: pure NumPy, does not import the package and so never
+    maps libgenlib_cuda.so into a process that only runs the oracle (bench.py --impl reference)."""
+    import importlib.util
+    import sys
+    name = "_genlib_synth_for_oracle"
+    if name not in sys.modules:
+        path = os.path.join(os.path.dirname(_HERE), "genlib.jl_b200", "synth.py")
+        spec = importlib.util.spec_from_file_location(name, path)
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        spec.loader.exec_module(mod)
+    return sys.modules[name]
+
+
+def workload(name: str, scale: float = 1.0):
+    """The named benchmark pedigree through the ORACLE's loader (create.jl:131-254 restated):
+    (father ranks, mother ranks, proband ranks in output order, description)."""
+    if name == "genea140":
+        ped = OraclePedigree.from_csv(os.path.join(os.path.dirname(_HERE), "tests", "data", "genea140.csv"))
+        pro = ped.pro()
+        desc = "genea140 (41523 individuals, 140 probands)"
+    else:
+        s = _synth().config(name, scale)
+        ped = OraclePedigree.from_arrays(s.ind, s.father, s.mother, s.sex)
+        pro = s.probands
+        p = s.params
+        desc = (f"{name} synthetic: {p['n_individuals']} individuals, {p['generations']} generations, "
+                f"{p['n_probands']} probands, alpha={p['alpha']}, demes={p['demes']}, migration={p['migration']}, "
+                f"overlap={p['overlap']}, seed={p['seed']}" + (f", scale={scale}" if scale != 1 else ""))
+    ranks = np.array([lib().oracle_rank_of(ped._h, int(i)) for i in pro], np.int32)
+    if (ranks < 0).any():
+        raise KeyError("unknown proband ID")
+    return ped.father, ped.mother, ranks, desc
+
+
+def matrix_sha256(m: np.ndarray) -> str:
+    """sha256 of the raw Float32 buffer of a (symmetric) kinship matrix."""
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(m, np.float32).tobytes()).hexdigest()

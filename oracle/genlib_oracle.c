@@ -511,27 +511,49 @@ int oracle_num_threads(void) {
 }
 
 /* ---------------------------------------------------------------------------------------------
- * gen.sparse_phi(pedigree, probandIDs) -- src/compute.jl:321-447, restated on rank arrays.
+ * gen.sparse_phi(pedigree, probandIDs) -- src/compute.jl:321-447, transliterated on rank arrays.
  *
- * The reference keeps Dict{rank, Dict{rank, Float32}} keyed lower rank -> higher rank and never
- * stores a zero (:391-394); a missing entry contributes nothing (:350-358, :367-389).  Here the
- * same values live in a dense symmetric Float32 matrix over the LIVE individuals (0 = missing),
- * which is the same arithmetic: adding a stored 0/2 or skipping a missing key both leave the
- * Float64 accumulator unchanged.  Everything else is line by line:
- *   :323      branching(pedigree, pro = probandIDs): only ancestors of the probands
+ * The reference keeps phi = Dict{rank, Dict{rank, Float32}}.  Two properties of that code decide
+ * the values and are kept literally here (`directed` != 0):
+ *   - the queue is seeded with founder(isolated_pedigree), i.e. the founders sorted by ID
+ *     (src/identify.jl:15-19 via :335-339) -- `ids` gives the ID of every rank;
+ *   - a kinship is STORED under phi[rank_j][rank_i] with j the individual processed earlier (:393),
+ *     but every LOOK-UP (:350-358, :367-389) and getindex (:36-40) reads phi[lower rank][higher
+ *     rank].  When the queue order of two individuals of the same depth inverts their rank order the
+ *     stored value is never found again: the reference silently treats that kinship as absent (0).
+ *     Such entries still count for the `show` line (:42-46) and the sums of phiMean (:466-472), and
+ *     the clean-up (:407-411, :421-425) only deletes keys filed under a LOWER rank, so the inner
+ *     dictionaries of the probands can keep keys of individuals that are long gone ("orphans").
+ * `directed` == 0 stores symmetrically instead: the mathematically consistent variant of the same
+ * schedule (engine: GENLIB_SCHEDULE_SPARSE_PHI_SYMMETRIC); no kinship is lost.
+ *
+ * phi[a][b] lives in val/has[slot a][slot b] over the LIVE individuals (a slot is cleared when it is
+ * handed out again); keys whose individual has been dropped are only counted (orphans).  Other lines:
+ *   :323      branching(pedigree, pro = probandIDs): only ancestors of the probands (ranks keep
+ *             their order, src/extract.jl:136-159)
  *   :176-183  children lists in rank order (_index_pedigree)
- *   :335-339  the queue starts with the founders of the isolated pedigree
  *   :349-361  self kinship 0.5 + phi[father, mother] / 2
- *   :363-395  kinship with every individual still to visit, `x / 2` is a FLOAT32 division,
- *             the accumulator is Float64, the store rounds to Float32
+ *   :363-395  kinship with every individual still to visit: `x / 2` is a FLOAT32 division, the
+ *             accumulator is Float64, the store rounds to Float32; zeros are not stored
  *   :397-430  children_to_process, eviction of non-proband parents
  *   :431-439  a child enters the queue when both known parents are processed
- * out: n_unique x n_unique (probands in first-occurrence order), stored: entries a
- * KinshipMatrix would hold (diagonal + non-zero upper pairs), for the `show` line (:42-46).
+ * out: n_unique x n_unique by getindex (:36-40), probands in first-occurrence order.
+ * counts (nullable, 4 entries): [0] stored entries of the `show` line, [1] of those, entries a
+ * look-up can find (diagonal + lower->higher keys between probands), [2] misfiled entries between
+ * live individuals, [3] orphan keys.  sums (nullable, 2 doubles): sum of all stored values and of
+ * the diagonal, Float64 accumulation (phiMean :466-472 sums the same multiset in Dict order).
  * Returns 0 or a negative ORACLE_* code.
  * --------------------------------------------------------------------------------------------- */
-int oracle_sparse_phi_ranks(int n, const int32_t *father, const int32_t *mother, int n_pro,
-                            const int32_t *pro_rank, float *out, int *n_unique, int64_t *stored) {
+typedef struct { int64_t id; int32_t rank; } founder_key;
+static int cmp_founder(const void *a, const void *b) {
+    const founder_key *x = a, *y = b;
+    if (x->id != y->id) return x->id < y->id ? -1 : 1;
+    return (x->rank > y->rank) - (x->rank < y->rank);
+}
+
+int oracle_sparse_phi_ranks(int n, const int32_t *father, const int32_t *mother, const int64_t *ids,
+                            int n_pro, const int32_t *pro_rank, int directed, float *out, int *n_unique,
+                            int64_t *counts, double *sums) {
     uint8_t *is_pro = calloc((size_t)n + 1, 1), *keep = calloc((size_t)n + 1, 1);
     int32_t *uniq = malloc((size_t)(n_pro + 1) * sizeof *uniq);
     int nu = 0;
@@ -563,7 +585,14 @@ int oracle_sparse_phi_ranks(int n, const int32_t *father, const int32_t *mother,
     int32_t *queue = malloc(((size_t)n + 1) * sizeof *queue), *todo = malloc(((size_t)n + 1) * sizeof *todo);
     uint8_t *done = calloc((size_t)n + 1, 1);
     int qn = 0;
-    for (int x = 0; x < n; x++) if (keep[x] && father[x] < 0 && mother[x] < 0) queue[qn++] = x;   /* :335-339 */
+    {   /* :335-339 founder(isolated_pedigree) = sort(founder IDs), identify.jl:15-19 */
+        founder_key *fk = malloc(((size_t)n + 1) * sizeof *fk);
+        int nf = 0;
+        for (int x = 0; x < n; x++) if (keep[x] && father[x] < 0 && mother[x] < 0) { fk[nf].id = ids ? ids[x] : x; fk[nf].rank = x; nf++; }
+        qsort(fk, (size_t)nf, sizeof *fk, cmp_founder);
+        for (int k = 0; k < nf; k++) queue[qn++] = fk[k].rank;
+        free(fk);
+    }
     int live = 0, max_live = 0;
     for (int h = 0; h < qn; h++) {
         int i = queue[h];
@@ -579,27 +608,50 @@ int oracle_sparse_phi_ranks(int n, const int32_t *father, const int32_t *mother,
         }
     }
     const size_t W = (size_t)max_live + 1;
-    float *M = calloc(W * W, sizeof *M);                         /* kinships of the live individuals */
+    float *val = calloc(W * W, sizeof *val);                     /* phi[a][b] = val[slot a][slot b] if has[..] */
+    uint8_t *has = calloc(W * W, 1);
     int32_t *slot = malloc(((size_t)n + 1) * sizeof *slot), *free_slots = malloc(W * sizeof *free_slots);
     int32_t *visit = malloc(W * sizeof *visit), *vpos = malloc(((size_t)n + 1) * sizeof *vpos);   /* ranks_to_visit */
-    if (!M || !slot || !free_slots || !visit || !vpos) return -ORACLE_ENOMEM;
+    int64_t *orphans = calloc((size_t)n + 1, sizeof *orphans);   /* keys of dropped individuals left in phi[x] */
+    double *orphan_sum = calloc((size_t)n + 1, sizeof *orphan_sum);
+    if (!val || !has || !slot || !free_slots || !visit || !vpos || !orphans || !orphan_sum) return -ORACLE_ENOMEM;
     int nfree = 0, nvisit = 0;
     for (size_t k = 0; k < W; k++) free_slots[nfree++] = (int32_t)(W - 1 - k);
     memset(done, 0, (size_t)n + 1);
+#define HAS(a, b) has[(size_t)slot[a] * W + (size_t)slot[b]]
+#define VAL(a, b) val[(size_t)slot[a] * W + (size_t)slot[b]]
+    /* the key the reference looks up for the pair {a, b}: phi[lower rank][higher rank] */
+#define LOOK(a, b, acc) do { const int lo_ = (a) < (b) ? (a) : (b), hi_ = (a) < (b) ? (b) : (a);       \
+        if (HAS(lo_, hi_)) (acc) += (double)(float)(VAL(lo_, hi_) / 2.0f); } while (0)
     for (int h = 0; h < qn; h++) {
         const int i = queue[h], f = father[i], m = mother[i];
         const int si = free_slots[--nfree];
         slot[i] = si;
-        for (size_t k = 0; k < W; k++) { M[(size_t)si * W + k] = 0.f; M[k * W + (size_t)si] = 0.f; }
+        for (size_t k = 0; k < W; k++) { has[(size_t)si * W + k] = 0; has[k * W + (size_t)si] = 0; }   /* phi[rank_i] = Dict() */
+        orphans[i] = 0; orphan_sum[i] = 0.;
         double coefficient = 0.5;                                /* :349-361 */
-        if (f >= 0 && m >= 0) coefficient += (double)(float)(M[(size_t)slot[f] * W + slot[m]] / 2.0f);
-        M[(size_t)si * W + si] = (float)coefficient;
+        if (f >= 0 && m >= 0) {
+            if (directed) { if (f < m) { if (HAS(f, m)) coefficient += (double)(float)(VAL(f, m) / 2.0f); }
+                            else { if (HAS(m, f)) coefficient += (double)(float)(VAL(m, f) / 2.0f); } }
+            else LOOK(f, m, coefficient);
+        }
+        VAL(i, i) = (float)coefficient; HAS(i, i) = 1;
         for (int v = 0; v < nvisit; v++) {                       /* :363-395 */
-            const int j = visit[v], sj = slot[j];
+            const int j = visit[v];
             coefficient = 0.;
-            if (f >= 0) coefficient += (double)(float)(M[(size_t)sj * W + slot[f]] / 2.0f);
-            if (m >= 0) coefficient += (double)(float)(M[(size_t)sj * W + slot[m]] / 2.0f);
-            if (coefficient > 0.) { const float c32 = (float)coefficient; M[(size_t)sj * W + si] = c32; M[(size_t)si * W + sj] = c32; }
+            if (f >= 0) {
+                if (j < f) { if (HAS(j, f)) coefficient += (double)(float)(VAL(j, f) / 2.0f); }
+                else { if (HAS(f, j)) coefficient += (double)(float)(VAL(f, j) / 2.0f); }
+            }
+            if (m >= 0) {
+                if (j < m) { if (HAS(j, m)) coefficient += (double)(float)(VAL(j, m) / 2.0f); }
+                else { if (HAS(m, j)) coefficient += (double)(float)(VAL(m, j) / 2.0f); }
+            }
+            if (coefficient > 0.) {
+                if (directed) { VAL(j, i) = (float)coefficient; HAS(j, i) = 1; }          /* :393, whatever the ranks */
+                else if (j < i) { VAL(j, i) = (float)coefficient; HAS(j, i) = 1; }
+                else { VAL(i, j) = (float)coefficient; HAS(i, j) = 1; }
+            }
         }
         vpos[i] = nvisit; visit[nvisit++] = i;                   /* :397-399 */
         done[i] = 1;
@@ -611,22 +663,43 @@ int oracle_sparse_phi_ranks(int n, const int32_t *father, const int32_t *mother,
             if (--todo[p] == 0) {
                 const int last = visit[--nvisit];                /* delete!(ranks_to_visit, p) */
                 visit[vpos[p]] = last; vpos[last] = vpos[p];
-                free_slots[nfree++] = slot[p];                   /* its row and column are dropped */
+                for (int v = 0; v < nvisit; v++) {               /* only keys under a LOWER rank are deleted (:407-411) */
+                    const int j = visit[v];
+                    if (j > p && HAS(j, p)) { orphans[j]++; orphan_sum[j] += (double)VAL(j, p); }
+                }
+                free_slots[nfree++] = slot[p];                   /* empty!(phi[p]); delete!(phi, p) */
                 slot[p] = -1;
             }
         }
     }
     if (out) {
-        int64_t nz = 0;
         for (int a = 0; a < nu; a++)
-            for (int b = 0; b < nu; b++) {
-                const float v = M[(size_t)slot[uniq[a]] * W + slot[uniq[b]]];
-                out[(size_t)a * nu + b] = v;
-                if (a == b || (uniq[a] < uniq[b] && v != 0.f)) nz++;
+            for (int b = 0; b < nu; b++) {                       /* getindex, :36-40 */
+                const int lo = uniq[a] < uniq[b] ? uniq[a] : uniq[b], hi = uniq[a] < uniq[b] ? uniq[b] : uniq[a];
+                out[(size_t)a * nu + b] = HAS(lo, hi) ? VAL(lo, hi) : 0.f;
             }
-        if (stored) *stored = nz;
     }
+    if (counts || sums) {
+        int64_t nz = 0, findable = 0, misfiled = 0, norph = 0;
+        double total = 0., diag = 0.;
+        for (int v = 0; v < nvisit; v++) {                       /* what is left in phi: the probands */
+            const int a = visit[v];
+            norph += orphans[a]; total += orphan_sum[a];
+            for (int w = 0; w < nvisit; w++) {
+                const int b = visit[w];
+                if (!HAS(a, b)) continue;
+                nz++; total += (double)VAL(a, b);
+                if (a == b) diag += (double)VAL(a, b);
+                if (a <= b) findable++; else misfiled++;
+            }
+        }
+        if (counts) { counts[0] = nz + norph; counts[1] = findable; counts[2] = misfiled; counts[3] = norph; }
+        if (sums) { sums[0] = total; sums[1] = diag; }
+    }
+#undef HAS
+#undef VAL
+#undef LOOK
     free(is_pro); free(keep); free(uniq); free(cstart); free(clist); free(cfill); free(queue); free(todo);
-    free(done); free(M); free(slot); free(free_slots); free(visit); free(vpos);
+    free(done); free(val); free(has); free(slot); free(free_slots); free(visit); free(vpos); free(orphans); free(orphan_sum);
     return ORACLE_OK;
 }

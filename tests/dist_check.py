@@ -75,7 +75,7 @@ def main():
         pro = rng.permutation(ped.ids)[: int(rng.integers(5, 200))]
         got = gen.phi_distributed(ped, pro, device=local, schedule="sparse_phi")
         if rank == 0:
-            want, _ = ob.sparse_phi_ranks(ped.father, ped.mother, ped.rank_of(pro))
+            want, _ = ob.sparse_phi_ranks(ped.father, ped.mother, ped.rank_of(pro), ids=ped.ids)
             ok = got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32))
             print(f"[dist x{world}] sparse_phi schedule, random {seed}: {'ok' if ok else 'MISMATCH'} ({got.shape[0]}x{got.shape[0]})", flush=True)
             if not ok:

@@ -32,7 +32,7 @@ def run(rank: int, world: int, port: int, out_path: str):
     for case, schedule in [(c, sch) for c in cases for sch in ("phi", "sparse_phi")]:
         name, ped, pro = case[0], case[1], case[2]
         IDs = gen.pro(ped) if pro is None else pro
-        plan = gen.Plan(ped.father, ped.mother, ped.rank_of(IDs), world=world, schedule=schedule)
+        plan = gen.Plan(ped.father, ped.mother, ped.rank_of(IDs), world=world, schedule=schedule, ids=ped.ids)
         # every rank must have built the same schedule
         sig = hashlib.sha256()
         for t in range(plan.n_layers):
@@ -79,7 +79,7 @@ def run(rank: int, world: int, port: int, out_path: str):
             got[idx] = rows
         if rank == 0:
             if schedule == "sparse_phi":           # gen.sparse_phi's own values (src/compute.jl:321-447)
-                want, _ = ob.sparse_phi_ranks(ped.father, ped.mother, ped.rank_of(IDs))
+                want, _ = ob.sparse_phi_ranks(ped.father, ped.mother, ped.rank_of(IDs), ids=ped.ids)
             elif name == "geneaJi":
                 want = ob.OraclePedigree.from_csv(gen.geneaJi).phi()
             else:

@@ -33,7 +33,7 @@ def replay(plan, numerics: str = "reference", check_poison: bool = True, on_laye
         zero = np.zeros((1, len(live)))
         rows_f = np.where(pf[:, None] >= 0, Al[np.maximum(pf, 0)], zero)
         rows_m = np.where(pm[:, None] >= 0, Al[np.maximum(pm, 0)], zero)
-        sparse = getattr(plan, "schedule", "phi") == "sparse_phi"
+        sparse = getattr(plan, "schedule", "phi").startswith("sparse_phi")
         if sparse:      # `x / 2` is a Float32 division of a stored Float32 (compute.jl:350-389), the sum Float64
             R = (rows_f.astype(np.float32) * np.float32(0.5)).astype(np.float64) \
                 + (rows_m.astype(np.float32) * np.float32(0.5)).astype(np.float64)
@@ -69,6 +69,11 @@ def replay(plan, numerics: str = "reference", check_poison: bool = True, on_laye
         if both.any():
             dv[both] = 0.5 + ((A[pf[both], pm[both]].astype(np.float32) * np.float32(0.5)).astype(np.float64) if sparse
                               else 0.5 * A[pf[both], pm[both]].astype(np.float64))
+        if getattr(plan, "schedule", "phi") == "sparse_phi":
+            # the reference files phi[earlier][later] and reads phi[lower rank][higher rank]
+            # (compute.jl:393 vs :367-389): a pair whose queue order inverts its rank order reads as 0
+            rk = arr["member_rank"]
+            blk = np.where(hi == (rk[:, None] > rk[None, :]), blk, 0.0)
         blk[np.arange(n), np.arange(n)] = dv[fam]
         A[np.ix_(slot, slot)] = blk.astype(T)
         if on_layer is not None:
@@ -96,7 +101,7 @@ class ShardedReplay:
         self.A = [np.full((max(plan.rank_rows(g), 1), self.W), np.nan, self.T) for g in range(self.G)]
         self.es = np.dtype(self.T).itemsize
         self.exchange = exchange
-        self.sparse = getattr(plan, "schedule", "phi") == "sparse_phi"
+        self.sparse = getattr(plan, "schedule", "phi").startswith("sparse_phi")
 
     def half_sum(self, x, y):
         """phi: 1/2 x + 1/2 y in Float64.  sparse_phi: the halves are Float32 divisions of STORED
@@ -192,7 +197,11 @@ class ShardedReplay:
             return
         fam, ind, pf, pm = a["member_fam"], a["member_ind"], a["fam_father_slot"], a["fam_mother_slot"]
         fl = fam[M0:M1] - sh["fam_base"][g]
-        blk = np.where(ind[M0:M1, None] > ind[None, :], self.Vrow[g][fl][:, fam], self.Vt[g][fl][:, fam])
+        hi = ind[M0:M1, None] > ind[None, :]
+        blk = np.where(hi, self.Vrow[g][fl][:, fam], self.Vt[g][fl][:, fam])
+        if getattr(self.plan, "schedule", "phi") == "sparse_phi":       # misfiled kinships read as 0 (compute.jl:393)
+            rk = a["member_rank"]
+            blk = np.where(hi == (rk[M0:M1, None] > rk[None, :]), blk, 0.0)
         for q in range(M0, M1):                                 # diagonal: 1/2 + 1/2 Psi[father, mother]
             F, d = fam[q], 0.5
             if pf[F] >= 0 and pm[F] >= 0:

@@ -46,9 +46,9 @@ def test_sharded_replay_sparse_phi_schedule(gen, ob, seed):
     ped = gen.genealogy(rec)
     pro = rng.permutation(ped.ids)[: int(rng.integers(2, 40))]
     ranks = ped.rank_of(pro)
-    want, _ = ob.sparse_phi_ranks(ped.father, ped.mother, ranks)
+    want, _ = ob.sparse_phi_ranks(ped.father, ped.mother, ranks, ids=ped.ids)
     for world in (2, 3):
-        plan = gen.Plan(ped.father, ped.mother, ranks, world=world, schedule="sparse_phi")
+        plan = gen.Plan(ped.father, ped.mother, ranks, world=world, schedule="sparse_phi", ids=ped.ids)
         assert np.array_equal(replay_sharded(plan), want)
 
 

@@ -256,20 +256,47 @@ def test_sparse_phi_random_pedigrees(gen, ob, seed):
     ped = gen.genealogy(rec)
     pro = rng.permutation(ped.ids)[: int(rng.integers(2, min(n, 200)))]
     ranks = ped.rank_of(pro)
-    want, stored = ob.sparse_phi_ranks(ped.father, ped.mother, ranks)
+    want, info = ob.sparse_phi_ranks(ped.father, ped.mother, ranks, ids=ped.ids, full=True)
     k = gen.sparse_phi(ped, pro)
     order = np.argsort(ranks, kind="stable")                                     # the KinshipMatrix is kept in rank order
     assert_bit_equal(k._dense, np.ascontiguousarray(want[np.ix_(order, order)]))
-    assert k.stored == stored and len(k) == len(pro)
+    assert k.stored == info["findable"] and len(k) == len(pro)
     assert k[int(pro[0]), int(pro[-1])] == want[0, -1]
+    # the consistent variant of the schedule: nothing misfiled (compute.jl:393), founders still by ID
+    sym = ob.sparse_phi_ranks(ped.father, ped.mother, ranks, ids=ped.ids, directed=False)[0]
+    k = gen.sparse_phi(ped, pro, symmetric=True)
+    assert_bit_equal(k._dense, np.ascontiguousarray(sym[np.ix_(order, order)]))
+
+
+def test_sparse_phi_misfiled_kinship_and_founder_id_order(gen, ob):
+    """The two properties of the reference's sparse_phi that the first round missed: kinships filed
+    under phi[earlier][later] but looked up under phi[lower rank][higher rank] are lost
+    (compute.jl:393), and the founders enter the queue sorted by ID (identify.jl:15-19)."""
+    cols = {"ind": np.array([1, 2, 3, 4, 5, 6, 7]), "father": np.array([0, 0, 0, 0, 3, 1, 5]),
+            "mother": np.array([0, 0, 0, 0, 4, 3, 6]), "sex": np.array([1, 2, 1, 2, 1, 2, 1], np.int32)}
+    ped = gen.genealogy(cols)
+    k = gen.sparse_phi(ped, [5, 6, 7])
+    assert k[5, 6] == 0 and k[7, 7] == np.float32(0.5)               # the reference loses phi[5, 6] = 1/8
+    k = gen.sparse_phi(ped, [5, 6, 7], symmetric=True)
+    assert k[5, 6] == np.float32(0.125) and k[7, 7] == np.float32(0.5625)
+    for seed, n, window in ((303, 400, 40), (305, 2000, 40), (302, 1000, 120)):
+        rng = np.random.default_rng(seed)
+        ped = gen.genealogy(random_pedigree(rng, n, 8 if n < 2000 else 10, window=window))
+        pro = rng.permutation(ped.ids)[:100]
+        ranks = ped.rank_of(pro)
+        order = np.argsort(ranks, kind="stable")
+        for symmetric in (False, True):
+            want = ob.sparse_phi_ranks(ped.father, ped.mother, ranks, ids=ped.ids, directed=not symmetric)[0]
+            k = gen.sparse_phi(ped, pro, symmetric=symmetric)
+            assert_bit_equal(k._dense, np.ascontiguousarray(want[np.ix_(order, order)]))
 
 
 def test_sparse_phi_deep_pedigrees_and_subnormals(gen, ob):
     s = gen.synth.generate(16 * 60, 60, 16, alpha=0.2, overlap=1, seed=11)
     ped = gen.genealogy(s.as_columns())
     ranks = ped.rank_of(s.probands)
-    want, _ = ob.sparse_phi_ranks(ped.father, ped.mother, ranks)
-    plan = gen.Plan(ped.father, ped.mother, ranks, schedule="sparse_phi")
+    want, _ = ob.sparse_phi_ranks(ped.father, ped.mother, ranks, ids=ped.ids)
+    plan = gen.Plan(ped.father, ped.mother, ranks, schedule="sparse_phi", ids=ped.ids)
     eng = gen.Engine(plan)
     eng.run()
     assert_bit_equal(eng.fetch(), want)
@@ -278,8 +305,8 @@ def test_sparse_phi_deep_pedigrees_and_subnormals(gen, ob):
     cols, pro = ladder_pedigree(73)                                              # Float32 halving of subnormals
     ped = gen.genealogy(cols)
     ranks = ped.rank_of(pro)
-    want, _ = ob.sparse_phi_ranks(ped.father, ped.mother, ranks)
-    plan = gen.Plan(ped.father, ped.mother, ranks, schedule="sparse_phi")
+    want, _ = ob.sparse_phi_ranks(ped.father, ped.mother, ranks, ids=ped.ids)
+    plan = gen.Plan(ped.father, ped.mother, ranks, schedule="sparse_phi", ids=ped.ids)
     eng = gen.Engine(plan)
     eng.run()
     assert_bit_equal(eng.fetch(), want)
@@ -295,17 +322,17 @@ def test_sparse_phi_genea140_and_scaled_configs(gen, ob):
     ped = gen.genealogy(gen.genea140)
     pro = gen.pro(ped)
     ranks = ped.rank_of(pro)
-    want, stored = ob.sparse_phi_ranks(ped.father, ped.mother, ranks)
+    want, info = ob.sparse_phi_ranks(ped.father, ped.mother, ranks, ids=ped.ids, full=True)
     k = gen.sparse_phi(ped)
     order = np.argsort(ranks, kind="stable")
     assert_bit_equal(k._dense, np.ascontiguousarray(want[np.ix_(order, order)]))
-    assert k.stored == stored
+    assert k.stored == info["findable"]
     for name, scale in (("C3", 0.02), ("C5", 0.02)):
         s = gen.synth.config(name, scale)
         ped = gen.genealogy(s.as_columns())
         ranks = ped.rank_of(s.probands)
-        want, _ = ob.sparse_phi_ranks(ped.father, ped.mother, ranks)
-        plan = gen.Plan(ped.father, ped.mother, ranks, schedule="sparse_phi")
+        want, _ = ob.sparse_phi_ranks(ped.father, ped.mother, ranks, ids=ped.ids)
+        plan = gen.Plan(ped.father, ped.mother, ranks, schedule="sparse_phi", ids=ped.ids)
         eng = gen.Engine(plan)
         eng.run()
         assert_bit_equal(eng.fetch(), want)

@@ -45,8 +45,8 @@ def test_any_small_pedigree_both_schedules(gen, ob, ped, world):
     pedg = gen.genealogy(cols)
     ranks = pedg.rank_of(ids[probands])
     want = {"phi": ob.phi_ranks(pedg.father, pedg.mother, ranks)[0],
-            "sparse_phi": ob.sparse_phi_ranks(pedg.father, pedg.mother, ranks)[0]}
+            "sparse_phi": ob.sparse_phi_ranks(pedg.father, pedg.mother, ranks, ids=pedg.ids)[0]}
     for schedule in ("phi", "sparse_phi"):
-        plan = gen.Plan(pedg.father, pedg.mother, ranks, world=world, schedule=schedule)
+        plan = gen.Plan(pedg.father, pedg.mother, ranks, world=world, schedule=schedule, ids=pedg.ids)
         got = replay(plan) if world == 1 else replay_sharded(plan)
         assert np.array_equal(got, want[schedule]), (schedule, world)
