@@ -11,11 +11,14 @@ gen.phi(ped, probands) -- over one synthetic pedigree.  `value` counts the pass
 with the schedule already resident in HBM (CUDA events on the engine's
 stream); `e2e` is the public call with HOST buffers: planning, H2D of the
 schedule, all layers, proband gather and D2H into pinned host memory.
-Prints ONE JSON line (rank 0).
+Both arms print the sha256 of the proband matrix they produced
+(`output_sha256`) next to the committed golden one (tests/golden/, made by the
+oracle alone).  Prints ONE JSON line (rank 0).
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -90,30 +93,76 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+# ---- what both arms agree on -------------------------------------------------------------------
+def workload_desc(name: str, scale: float) -> str:
+    if name == "genea140":
+        return "genea140 (41523 individuals, 140 probands)"
+    sys.path.insert(0, os.path.join(ROOT, "genlib.jl_b200"))
+    from oracle.binding import _synth
+    p = dict(_synth().CONFIGS[name])
+    if scale != 1.0:
+        p["n_individuals"] = max(p["generations"] * 4, int(round(p["n_individuals"] * scale)))
+        p["n_probands"] = max(2, int(round(p["n_probands"] * scale)))
+    return (f"{name} synthetic: {p['n_individuals']} individuals, {p['generations']} generations, "
+            f"{p['n_probands']} probands, alpha={p['alpha']}, demes={p['demes']}, migration={p['migration']}, "
+            f"overlap={p['overlap']}, seed={p['seed']}" + (f", scale={scale}" if scale != 1 else ""))
+
+
+def shared_config(args, row_updates: int) -> dict:
+    """The `config` object: identical in both arms for the same command line."""
+    return {"workload": workload_desc(args.workload, args.scale), "numerics": args.numerics,
+            "row_updates_per_step": int(row_updates), "output": "n_probands x n_probands Float32, host memory",
+            "l2": "working set >> L2 (no flush needed)"}
+
+
+def golden_record(args):
+    name = f"{args.workload.lower()}_full.sha256" if args.scale == 1.0 else f"{args.workload.lower()}_x{args.scale:g}.sha256"
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", name)) as fh:
+            return json.load(fh)
+    except Exception:
+        return None
+
+
+def rows_digest(rows: np.ndarray) -> bytes:
+    """Concatenated sha256 digests of the rows (32 bytes each): ranks hash their own rows, the
+    digest of the concatenation in proband order is independent of how the rows were sharded."""
+    return b"".join(hashlib.sha256(np.ascontiguousarray(r).tobytes()).digest() for r in rows)
+
+
+def parity_fields(args, full_sha, rows_sha):
+    g = golden_record(args) if args.numerics == "reference" else None
+    out = {"output_sha256": full_sha, "output_rows_sha256": rows_sha,
+           "golden_sha256": g["sha256"] if g else None, "golden_rows_sha256": g.get("rows_sha256") if g else None}
+    if g and full_sha is not None:
+        out["matches_golden"] = full_sha == g["sha256"]
+    elif g and g.get("rows_sha256") and rows_sha is not None:
+        out["matches_golden"] = rows_sha == g["rows_sha256"]
+    else:
+        out["matches_golden"] = None
+    return out
+
+
 def build_workload(args):
+    """The product's own loader (C++), for the GPU arm."""
     import genlib_b200 as gen
     if args.workload == "genea140":
         ped = gen.genealogy(gen.genea140)
         pro = gen.pro(ped)
-        desc = "genea140 (41523 individuals, 140 probands)"
     else:
         s = gen.synth.config(args.workload, args.scale)
         ped = gen.genealogy(s.as_columns())
         pro = s.probands
-        p = s.params
-        desc = (f"{args.workload} synthetic: {p['n_individuals']} individuals, {p['generations']} generations, "
-                f"{p['n_probands']} probands, alpha={p['alpha']}, demes={p['demes']}, migration={p['migration']}, "
-                f"overlap={p['overlap']}, seed={p['seed']}" + (f", scale={args.scale}" if args.scale != 1 else ""))
-    return gen, ped, ped.rank_of(pro), desc
+    return gen, ped, ped.rank_of(pro)
 
 
-def cpu_baseline(ped, ranks, seconds):
-    """The oracle (C restatement of src/compute.jl:233-304, all host threads) on a bounded
-    sample: the first generation steps of the SAME workload until `seconds` have elapsed."""
+# ---- the reference arm: the oracle on the host cores, no product library in the process -----------
+def cpu_sample(father, mother, ranks, seconds):
+    """Bounded sample: the first generation steps of the workload until `seconds` have elapsed."""
     from oracle import binding as ob
     cores = ob.num_threads()
     t0 = time.time()
-    steps = ob.bounded_steps(ped.father, ped.mother, ranks, seconds, nthreads=cores)
+    steps = ob.bounded_steps(father, mother, ranks, seconds, nthreads=cores)
     wall = time.time() - t0
     secs = float(steps[:, 5].sum()) if len(steps) else 0.0
     rows = float(steps[:, 4].sum()) if len(steps) else 0.0
@@ -125,28 +174,59 @@ def cpu_baseline(ped, ranks, seconds):
             "seconds": secs}
 
 
+def cpu_baseline(ped, ranks, seconds):
+    return cpu_sample(ped.father, ped.mother, ranks, seconds)
+
+
 def run_reference(args, rank, world):
+    """ONE complete pass of the whole workload through the oracle (all host threads): an unsampled
+    CPU figure and the sha256 of its matrix.  C4 does not fit a host (2 x 71 GB step matrices):
+    there, and with --ref-mode sample, K bounded samples of the first steps are timed instead."""
     if rank != 0:
         return
-    gen, ped, ranks, desc = build_workload(args)
-    # each "step" of this arm is one bounded sample; W warm-up + K timed samples
-    per = max(1.0, args.cpu_seconds / max(1, args.steps))
+    from oracle import binding as ob
+    father, mother, ranks, _ = ob.workload(args.workload, args.scale)
+    cores = ob.num_threads()
+    full = args.ref_mode == "full" or (args.ref_mode == "auto" and not (args.workload == "C4" and args.scale > 0.25))
     for _ in range(min(args.warmup, 1)):
-        cpu_baseline(ped, ranks, min(per, 2.0))
-    vals, last = [], None
-    t0 = time.time()
-    for _ in range(args.steps):
-        last = cpu_baseline(ped, ranks, per)
-        vals.append(last["value"])
-    ms = (time.time() - t0) * 1e3 / max(1, args.steps)
-    v = float(np.mean(vals))
-    last["value"] = v
-    emit(({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
-                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-                      "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                      "config": {"workload": desc}, "cpu_baseline": last,
-                      "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                      "gpu_launches": 0}))
+        cpu_sample(father, mother, ranks, 2.0)                      # pages the pedigree in, spins the cores up
+    if full:
+        t0 = time.time()
+        phi, steps = ob.phi_ranks(father, mother, ranks, nthreads=cores)
+        wall = time.time() - t0
+        rows = int(steps[:, 4].sum())
+        value, ms, k = rows / wall, wall * 1e3, 1
+        base = {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": (f"the WHOLE workload, once: {len(steps)} generation steps, {rows} row-updates, "
+                           f"{steps[:, 3].sum():.3g} pair evaluations, {wall:.1f} s wall (loops {steps[:, 5].sum():.1f} s); "
+                           "C restatement of the reference algorithm (Julia is not installable here)"),
+                "seconds": wall}
+        par = parity_fields(args, ob.matrix_sha256(phi), hashlib.sha256(rows_digest(phi)).hexdigest())
+    else:
+        per = max(1.0, args.cpu_seconds / max(1, args.steps))
+        vals, base = [], None
+        t0 = time.time()
+        for _ in range(args.steps):
+            base = cpu_sample(father, mother, ranks, per)
+            vals.append(base["value"])
+        ms, k = (time.time() - t0) * 1e3 / max(1, args.steps), args.steps
+        value = float(np.mean(vals))
+        base["value"] = value
+        rows = 0
+        par = parity_fields(args, None, None)
+    if not rows:                                                    # row-updates of a full pass, for `config`
+        rows = ob.row_updates(father, mother, ranks)
+    cfg = shared_config(args, rows)
+    emit({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+          "steps": k, "steps_requested": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": ms,
+          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": data_tag(args),
+          "config": cfg, "cpu_baseline": base, "parity": par,
+          "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+          "gpu_launches": 0})
+
+
+def data_tag(args):
+    return "synthetic" if args.workload != "genea140" else "genea140.csv"
 
 
 _REAL_STDOUT = None
@@ -168,6 +248,50 @@ def emit(line: dict):
     out.flush()
 
 
+# ---- roofline of the layer kernel ------------------------------------------------------------------
+def roofline_record(infos, layer_ms, K, esize, peak, peak_src, world, args):
+    """infos: per-layer dicts of this rank (summed over ranks by the caller for N > 1: dram/l2/nvlink
+    bytes); layer_ms: (K, n_layers) device time of the layer kernel (slowest rank)."""
+    dram = np.array([i["dram_read_bytes"] + i["dram_write_bytes"] for i in infos])
+    l2 = np.array([i["l2_bytes"] for i in infos])
+    nvl = np.array([i["nvlink_bytes"] for i in infos])
+    alg = np.array([esize * i["alg_elems"] for i in infos])
+    launched = np.array([i["n_new"] > 0 for i in infos])
+    t = float(layer_ms[:, launched].sum()) * 1e-3
+    achieved = float(dram[launched].sum()) * K / t / 1e9 if t > 0 else 0.0
+    rec = {"bound": "hbm", "kernel": "layer_kernel", "achieved": achieved, "peak": peak * world, "unit": "GB/s",
+           "frac": achieved / (peak * world),
+           "bytes": "required DRAM bytes of the step from the plan: parent rows of the couples over the live columns "
+                    "read once + new rows (and their mirror columns in carried rows) written once; the transposed "
+                    "strip scratch stays in L2 and is not counted",
+           "peak_source": (f"{world} x " if world > 1 else "") + peak_src,
+           "launches": int(launched.sum()) * K,
+           "avg_launch_ms": float(layer_ms[:, launched].mean()) if launched.any() else 0.0,
+           "required_bytes_per_launch": float(dram[launched].mean()) if launched.any() else 0.0,
+           "l2_scratch_bytes_per_launch": float(l2[launched].mean()) if launched.any() else 0.0,
+           "nvlink_bytes_per_step": float(nvl.sum()),
+           "share_of_step": 1.0,
+           "survey_model": {"bytes": "s*(4nL+3n^2) per layer (SURVEY.md 8d): counts a row per individual and three passes "
+                                     "over the intra-layer block; the engine moves less (one row per couple, one pass)",
+                            "achieved": float(alg.sum()) * K / t / 1e9 if t > 0 else 0.0,
+                            "frac": (float(alg.sum()) * K / t / 1e9 / (peak * world)) if t > 0 else 0.0}}
+    # measured DRAM bytes of one launch, from a committed `ncu --set full` capture of this exact workload
+    rec["traffic"], rec["traffic_source"] = None, "no ncu capture of this workload / GPU count under profiles/"
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02", "ncu_traffic.json")) as fh:
+            cap = json.load(fh)
+        key = f"{args.workload}:{args.scale:g}:{args.numerics}:{world}"
+        if key in cap:
+            c = cap[key]
+            rec["traffic"] = c["dram_bytes"]
+            rec["traffic_source"] = c["source"]
+            rec["traffic_layer"] = c["layer"]
+            rec["traffic_required_bytes_same_launch"] = float(dram[c["layer"]])
+    except Exception:
+        pass
+    return rec
+
+
 def main():
     quiet_stdout()
     ap = argparse.ArgumentParser()
@@ -178,8 +302,10 @@ def main():
     ap.add_argument("--workload", default="C3", choices=["C3", "C4", "C5", "genea140"])
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--numerics", default="reference", choices=["reference", "fp64"])
-    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU baseline budget (0 = skip)")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU baseline budget of the GPU arm (0 = skip)")
+    ap.add_argument("--ref-mode", default="auto", choices=["auto", "full", "sample"],
+                    help="reference arm: one full pass (sha256, unsampled) or bounded samples")
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--layers-json", default="", help="write per-layer timings here")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -191,7 +317,7 @@ def main():
         from bench_dist import main_dist          # sharded path (one rank per GPU)
         return main_dist(args, rank, world, local, sys.modules[__name__])
 
-    gen, ped, ranks, desc = build_workload(args)
+    gen, ped, ranks = build_workload(args)
     if gen.lib().genlib_device_count() < 1:
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
     esize = 4 if args.numerics == "reference" else 8
@@ -200,10 +326,11 @@ def main():
     eng = gen.Engine(plan, numerics=args.numerics, device=local)
     setup_s = time.time() - t0
     rows = plan.row_updates
-    for _ in range(max(args.warmup, 3)):
+    W = max(args.warmup, 3)
+    for _ in range(W):
         eng.run()
     K = args.steps
-    cross_ms, couple_ms, expand_ms, step_ms = [], [], [], []
+    layer_ms, step_ms = [], []
     with ClockSampler(local) as clocks:
         time.sleep(0.6)                      # let nvidia-smi start sampling
         n0 = len(clocks.rows)
@@ -213,57 +340,25 @@ def main():
         t0 = time.time()
         for _ in range(K):
             step_ms.append(eng.run(time_layers=True))
-            infos = [eng.layer_info(t) for t in range(plan.n_layers)]
-            cross_ms.append([i["ms_cross"] for i in infos])
-            couple_ms.append([i["ms_couple"] for i in infos])
-            expand_ms.append([i["ms_expand"] for i in infos])
+            layer_ms.append([eng.layer_info(t)["ms_layer"] for t in range(plan.n_layers)])
         wall_ms = (time.time() - t0) * 1e3
     stats = eng.stats()
+    infos = [eng.layer_info(t) for t in range(plan.n_layers)]
     total_ms = float(np.sum(step_ms))
     value = rows * K / (total_ms * 1e-3)
-    infos = plan.layers()
-    cross_ms, couple_ms, expand_ms = np.array(cross_ms), np.array(couple_ms), np.array(expand_ms)
-    intra_ms = couple_ms + expand_ms
-    # dominant kernel: cross_kernel.  Algorithmic bytes per launch = s * 4 n L.
-    cross_bytes = np.array([esize * 4.0 * i["n_new"] * i["live_before"] for i in infos])
-    intra_bytes = np.array([esize * 3.0 * i["n_new"] ** 2 for i in infos])
-    launched = cross_bytes > 0
+    layer_ms = np.array(layer_ms)
     peak, peak_src = measured_peaks()
-    c_t = cross_ms[:, launched].sum() * 1e-3
-    i_t = intra_ms.sum() * 1e-3
-    achieved = cross_bytes[launched].sum() * K / c_t / 1e9 if c_t > 0 else 0.0
-    whole = (cross_bytes.sum() + intra_bytes.sum()) * K / (total_ms * 1e-3) / 1e9
-    # DRAM traffic per launch from `ncu --set full` (profiles/r01/ncu_full_c3_final_summary.json): a
-    # 39208 x 39114 layer moved 6.166 GB read + 6.111 GB written for 24.54 GB of algorithmic bytes
-    # (couples halve the rows that are read and written); scaled to the average launch.
-    traffic_ratio = (6.165890e9 + 6.110764e9) / (4 * 4.0 * 39208 * 39114) if args.numerics == "reference" else None
-    roofline = {"bound": "hbm", "kernel": "cross_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak,
-                "traffic": (traffic_ratio * float(cross_bytes[launched].mean())) if (traffic_ratio and launched.any()) else None,
-                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, one launch, scaled by algorithmic bytes",
-                "achieved_dram": (traffic_ratio * achieved) if traffic_ratio else None,      # GB/s of measured DRAM bytes
-                "dram_frac": (traffic_ratio * achieved / peak) if traffic_ratio else None,   # measured DRAM bytes / time / peak
-                "peak_source": peak_src,
-                "launches": int(launched.sum()) * K,
-                "avg_launch_ms": float(cross_ms[:, launched].mean()) if launched.any() else 0.0,
-                "alg_bytes_per_launch": float(cross_bytes[launched].mean()) if launched.any() else 0.0,
-                "share_of_step": c_t / (total_ms * 1e-3),
-                "intra_kernels": {"achieved": intra_bytes.sum() * K / i_t / 1e9 if i_t > 0 else 0.0,
-                                  "share_of_step": i_t / (total_ms * 1e-3),
-                                  "couple_share": float(couple_ms.sum() / total_ms),
-                                  "expand_share": float(expand_ms.sum() / total_ms)},
-                "whole_step": {"achieved": whole, "frac": whole / peak,
-                               "frac_of_8TBs_nominal": whole / 8000.0}}
+    roofline = roofline_record(infos, layer_ms, K, esize, peak, peak_src, 1, args)
+    roofline["share_of_step"] = float(layer_ms.sum() / total_ms)
     if args.layers_json:
         with open(args.layers_json, "w") as fh:
-            json.dump([{**i, "ms_cross": float(cross_ms[:, t].mean()), "ms_couple": float(couple_ms[:, t].mean()),
-                        "ms_expand": float(expand_ms[:, t].mean())} for t, i in enumerate(infos)], fh, indent=1)
+            json.dump([{**i, "ms_layer": float(layer_ms[:, t].mean())} for t, i in enumerate(infos)], fh, indent=1)
     eng.close()
 
     # ---- end to end: the public call with host buffers, pinned output ----
     n = plan.n_unique
     pinned = gen.PinnedMatrix(n, np.float32)
-    e2e_t, h2d, d2h = [], 0, 0
+    e2e_t, h2d, d2h, st = [], 0, 0, None
     for it in range(args.e2e_steps + 1):
         t0 = time.time()
         _, st = gen.phi_arrays(ped.father, ped.mother, ranks, numerics=args.numerics, device=local,
@@ -276,19 +371,19 @@ def main():
     e2e = {"value": rows / float(np.mean(e2e_t)), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": int(d2h), "ms_per_call": float(np.mean(e2e_t)) * 1e3,
            "breakdown_ms": {k: st[k] for k in ("ms_plan", "ms_upload", "ms_kernels", "ms_fetch")}}
+    parity = parity_fields(args, hashlib.sha256(pinned.array.tobytes()).hexdigest(),
+                           hashlib.sha256(rows_digest(pinned.array)).hexdigest())
     checksum = float(pinned.array.astype(np.float64).sum())
     pinned.free()
 
     base = cpu_baseline(ped, ranks, args.cpu_seconds) if args.cpu_seconds > 0 else None
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": max(args.warmup, 3),
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic" if args.workload != "genea140" else "genea140.csv",
-            "config": {"workload": desc, "numerics": args.numerics, "storage_bytes": esize,
-                       "row_updates_per_step": int(rows), "layers": plan.n_layers, "capacity_slots": int(plan.capacity),
-                       "device_bytes": int(stats["device_bytes"]), "l2": "working set >> L2 (no flush needed)",
-                       "alg_bytes_per_step": float(stats["alg_bytes"]), "setup_s": setup_s,
-                       "host_wall_ms_per_step": wall_ms / K, "output_checksum": checksum},
-            "roofline": roofline, "cpu_baseline": base, "e2e": e2e,
+            "dtype": "f64", "data": data_tag(args), "config": shared_config(args, rows),
+            "engine": {"storage_bytes": esize, "layers": plan.n_layers, "capacity_slots": int(plan.capacity),
+                       "device_bytes": int(stats["device_bytes"]), "alg_bytes_per_step": float(stats["alg_bytes"]),
+                       "setup_s": setup_s, "host_wall_ms_per_step": wall_ms / K, "output_checksum": checksum},
+            "roofline": roofline, "cpu_baseline": base, "e2e": e2e, "parity": parity,
             "gpu_launches": int(stats["kernel_launches"]) * K, "clocks": clocks.summary()}
     emit(line)
 

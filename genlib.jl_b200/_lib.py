@@ -28,8 +28,9 @@ class GenlibError(RuntimeError):
 class LayerInfo(C.Structure):
     _fields_ = [("n_new", C.c_int32), ("n_fam", C.c_int32), ("live_before", C.c_int32),
                 ("carried", C.c_int32), ("ref_founders", C.c_int32), ("ref_probands", C.c_int32),
-                ("ref_both", C.c_int32), ("reserved", C.c_int32), ("alg_elems", C.c_double),
-                ("ms_cross", C.c_double), ("ms_couple", C.c_double), ("ms_expand", C.c_double), ("ms_wait", C.c_double)]
+                ("ref_both", C.c_int32), ("strip_width", C.c_int32), ("alg_elems", C.c_double),
+                ("ms_layer", C.c_double), ("ms_wait", C.c_double), ("dram_read_bytes", C.c_double),
+                ("dram_write_bytes", C.c_double), ("l2_bytes", C.c_double), ("nvlink_bytes", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
@@ -76,7 +77,7 @@ SYMBOLS = {
     "genlib_plan_layer_info": (C.c_int, [_P, C.c_int32, C.POINTER(LayerInfo)]),
     "genlib_plan_device_bytes": (C.c_int64, [_P, C.c_int, C.c_int32]),
     "genlib_plan_layer_arrays": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P]),
-    "genlib_plan_layer_shard": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "genlib_plan_layer_shard": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P, _P]),
     "genlib_plan_layer_live_rows": (C.c_int, [_P, C.c_int32, _P, _P]),
     "genlib_plan_rank_rows": (C.c_int64, [_P, C.c_int32]),
     "genlib_plan_world": (C.c_int32, [_P]),

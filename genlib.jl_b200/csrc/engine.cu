@@ -18,6 +18,7 @@
 
 #include "../../include/genlib_cuda.h"
 #include "kernels.cuh"
+#include "layer_kernel.cuh"
 #include "plan.hpp"
 
 using namespace genlib;
@@ -162,7 +163,13 @@ struct genlib_plan {
     double ms_plan = 0;
 };
 
-constexpr int kMaxGroups = 8;    // couple groups per layer (multi-GPU software pipeline of cross and couple)
+// launch shape of one layer's persistent kernel (layer_kernel.cuh)
+struct LayerLaunch {
+    StripArgs s{};
+    int grid = 0;
+    size_t smem = 0;
+    size_t sync_off = 0;                   // ints, into the engine's sync region
+};
 
 struct genlib_engine {
     const genlib_plan *plan = nullptr;
@@ -171,23 +178,24 @@ struct genlib_engine {
     bool attached = false;                 // peers' arenas mapped (always true for one rank)
     size_t esize = 4;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
-    cudaStream_t side_stream = nullptr;    // multi-GPU: couple_kernel of one couple group runs beside cross_kernel of the next
-    cudaEvent_t group_ev[kMaxGroups + 1] = {};
-    bool piped = false;
     Arena arena;
     void *A = nullptr;                     // this rank's frontier rows: rows_cap x capacity
-    double *Rt = nullptr;                  // transposed cross block: live slots x own couples (fp64)
-    void *Vrow = nullptr, *Vt = nullptr, *Dg = nullptr;   // V[own F, G], V[G, own F], couple diagonal
+    void *Q = nullptr;                     // strip buffers: transposed parent-row pairs, pinned in L2
+    size_t q_bytes = 0;
+    int32_t *sync = nullptr;               // unit counters and strip completion counts of every layer
+    size_t sync_ints = 0;
+    std::vector<LayerLaunch> launch;
+    bool info_ready = false;               // per-layer byte accounting filled in
     unsigned *bar_flags = nullptr;
     unsigned char *fetch_stage[2] = {nullptr, nullptr};
     PeerTable peers{};
     BarrierTable bars{};
-    void *peer_base[kMaxWorld] = {};       // cudaIpcOpenMemHandle mappings (to close)
     unsigned epoch = 0;
+    long long barrier_timeout = (long long)20e9;   // cycles an inter-GPU barrier may wait (GENLIB_BARRIER_TIMEOUT_S)
     DevBuf<int32_t> mem_ind, mem_slot, mem_fam, mem_lrow, fam_pf, fam_pm, fam_pf_lrow, fam_pm_lrow, fam_start,
-        fam_minrank, fam_maxrank, mt_min, mt_max, mt_fam0, mt_nfam, mt_m0, mt_cnt, pro_slot, own_pro_row, live_lrow;
-    DevBuf<int8_t> fam_pf_owner, fam_pm_owner, live_owner, mem_gowner;
-    DevBuf<int32_t> mem_glrow, mem_rank;
+        mt_fam0, mt_nfam, mt_m0, mt_cnt, pro_slot, own_pro_row, live_lrow, tile_map;
+    DevBuf<int8_t> fam_pf_owner, fam_pm_owner, live_owner;
+    DevBuf<int32_t> mem_rank;
     DevBuf<uint8_t> flags;
     DevBuf<double> acc;
     std::vector<int32_t> own_pro;          // proband indices (output rows) this rank owns, ascending
@@ -200,8 +208,6 @@ struct genlib_engine {
         for (auto e : events) cudaEventDestroy(e);
         if (stream) cudaStreamSynchronize(stream);
         if (copy_stream) cudaStreamSynchronize(copy_stream);
-        if (side_stream) { cudaStreamSynchronize(side_stream); cudaStreamDestroy(side_stream); }
-        for (auto e : group_ev) if (e) cudaEventDestroy(e);
         g_arenas.release(arena);
         if (stream) cudaStreamDestroy(stream);
         if (copy_stream) cudaStreamDestroy(copy_stream);
@@ -220,32 +226,94 @@ void fill_info(const Layer &L, genlib_layer_info *o) {
 size_t pad256(size_t b) { return (std::max<size_t>(b, 1) + 255) / 256 * 256; }
 
 size_t plan_index_bytes(const Plan &P) {
-    return (P.mem_ind.size() * 4 + P.fam_pf.size() * 6 + P.fam_start.size() + P.mtile_minrank.size() * 6 +
-            P.pro_slot.size() * 2 + P.live_lrow.size()) * sizeof(int32_t) + P.fam_pf.size() * 2 + P.live_owner.size() + P.flags.size();
+    return (P.mem_ind.size() * 4 + P.mem_rank.size() + P.fam_pf.size() * 4 + P.fam_start.size() + P.mtile_fam0.size() * 4 +
+            P.pro_slot.size() * 2 + P.live_lrow.size() + P.tile_map.size()) * sizeof(int32_t) + P.fam_pf.size() * 2 + P.live_owner.size() + P.flags.size();
 }
 
-// Arena layout of rank g.  The first three regions are what peers address (barrier flags,
-// frontier rows, row block of V), so their offsets must be computable by every rank.
+// Arena layout of rank g.  The first two regions are what peers address (barrier flags, frontier rows).
 constexpr size_t kFlagBytes = 256;
-size_t total_rows(const Plan &P, int g) { return (size_t)P.rows_cap[g] + 2 * (size_t)P.guest_cap[g]; }
+size_t total_rows(const Plan &P, int g) { return (size_t)P.rows_cap[g]; }
 size_t a_bytes(const Plan &P, size_t es, int g) { return pad256(total_rows(P, g) * (size_t)P.capacity * es); }
-size_t v_bytes(const Plan &P, size_t es, int g) { return pad256(P.rank_v_elems[g] * es); }
 size_t off_A() { return kFlagBytes; }
-size_t off_Vrow(const Plan &P, size_t es, int g) { return kFlagBytes + a_bytes(P, es, g); }
 
-size_t engine_bytes(const Plan &P, int numerics, int g) {
+// ---- launch shapes ---------------------------------------------------------------------------
+// The strip buffers live in the part of L2 that can be set aside for persisting lines (79 of 126 MB
+// on B200, profiles/r02/l2strip.txt); what the buffers of a layer may take of it:
+constexpr size_t kStripBudget = (size_t)72 << 20;
+constexpr int kCtasPerSm = 2;
+constexpr size_t kUnitBytes = (size_t)256 << 10;          // work handed out per atomic: ~6 us of one SM's bandwidth
+
+LayerLaunch shape_layer(const Plan &P, int t, int rank, size_t es, int sm_count) {
+    const Layer &L = P.layers[t];
+    LayerLaunch out;
+    StripArgs &s = out.s;
+    const int32_t *fb = P.fam_base.data() + L.base_off, *mb = P.mem_base.data() + L.base_off;
+    const int64_t own_nf = fb[rank + 1] - fb[rank], own_nm = mb[rank + 1] - mb[rank];
+    if (L.n_new == 0 || own_nf <= 0) return out;
+    const int64_t rt_rows = L.live_before > 0 ? L.rt_rows : 0, ptiles = rt_rows / kPTile;
+    const int64_t q_rows = L.live_before > 0 ? (int64_t)L.n_live_tiles * kPTile : 0;     // rows of a strip buffer
+    const size_t pair = 2 * es;
+    // strip width: the widest one whose buffers fit the persisting part of L2 three times (and whose
+    // staged tile fits shared memory: 128 parent rows x sw pairs <= 64 KB)
+    int sw = es == 4 ? kMaxStrip : kMaxStrip / 2;
+    while (sw > 8 && (size_t)q_rows * sw * pair * 3 > kStripBudget) sw >>= 1;
+    const size_t strip_bytes = std::max<size_t>((size_t)q_rows * sw * pair, 256);
+    s.sw = sw;
+    s.ft = std::min(sw, es == 4 ? 32 : 16);
+    s.nbuf = (int)std::max<size_t>(2, std::min<size_t>(6, kStripBudget / strip_bytes));
+    s.n_strips = (int)((own_nf + sw - 1) / sw);
+    s.qstride = (int64_t)(strip_bytes / pair);
+    const int grid_max = kCtasPerSm * sm_count;
+    const double rows_per_strip = (double)own_nm / (double)own_nf * sw;        // members of a strip
+    // producer units: 2 ft parent rows x pchunk column tiles
+    if (ptiles > 0) {
+        int64_t pc = (int64_t)(kUnitBytes / ((size_t)2 * s.ft * kPTile * es));
+        pc = std::min<int64_t>(pc, ptiles * (sw / s.ft) * s.n_strips / (2 * grid_max));      // but at least two waves of units
+        s.pchunk = (int)std::max<int64_t>(std::min<int64_t>(2, ptiles), std::min<int64_t>(pc, kMaxPChunk));
+        s.n_pchunks = (int)((ptiles + s.pchunk - 1) / s.pchunk);
+    } else { s.pchunk = 1; s.n_pchunks = 0; }
+    // consumer units: the strip's member rows x gt member tiles
+    {
+        int64_t gt = (int64_t)((double)kUnitBytes / std::max(1.0, rows_per_strip * kMTile * es));
+        gt = std::min<int64_t>(gt, (int64_t)L.n_mtiles * s.n_strips / (2 * grid_max));
+        s.gt = (int)std::max<int64_t>(1, std::min<int64_t>(gt, 64));
+        s.n_cunits = (L.n_mtiles + s.gt - 1) / s.gt;
+    }
+    // mirror units: blocks of live-range rows
+    if (L.carried > 0 && rt_rows > 0) {
+        int64_t mr = (int64_t)((double)kUnitBytes / std::max(1.0, rows_per_strip * es));
+        s.mrows = (int)std::max<int64_t>(64, std::min<int64_t>(mr, 8192));
+        s.n_munits = (int)((rt_rows + s.mrows - 1) / s.mrows);
+    } else { s.mrows = 1; s.n_munits = 0; }
+    const size_t stage = (size_t)2 * s.ft * (kPTile * es + 16);
+    s.stages = (int)std::max<size_t>(2, std::min<size_t>(kMaxStages, ((size_t)100 << 10) / stage));
+    out.smem = std::max((size_t)s.stages * stage, layer_consumer_bytes(sw, es));
+    const int64_t units = (int64_t)s.n_strips * ((int64_t)(sw / s.ft) * s.n_pchunks + s.n_cunits + s.n_munits);
+    s.n_units = (int32_t)std::min<int64_t>(units, INT32_MAX);
+    out.grid = (int)std::min<int64_t>(units, grid_max);
+    s.timeout_cycles = (long long)8e9;                     // ~4 s: a lost dependency becomes GENLIB_ECUDA, not a hang
+    return out;
+}
+
+size_t strip_buffer_bytes(const LayerLaunch &ll, size_t es) { return (size_t)ll.s.nbuf * (size_t)ll.s.qstride * 2 * es; }
+
+size_t engine_bytes(const Plan &P, int numerics, int g, int sm_count = 148) {
     const size_t es = numerics == GENLIB_NUMERICS_FP64 ? 8 : 4;
-    size_t b = kFlagBytes + a_bytes(P, es, g) + 2 * v_bytes(P, es, g);          // flags, A, Vrow, Vt
-    b += pad256(P.rank_rt_elems[g] * sizeof(double));                          // Rt
-    b += pad256(P.fam_pf.size() * es);                                         // Dg
+    size_t q = 256, sync_ints = 0;
+    for (int t = 0; t < (int)P.layers.size(); t++) {
+        const LayerLaunch ll = shape_layer(P, t, g, es, sm_count);
+        if (ll.grid == 0) continue;
+        q = std::max(q, strip_buffer_bytes(ll, es));
+        sync_ints += 2 + 2 * (size_t)ll.s.n_strips;
+    }
+    size_t b = kFlagBytes + a_bytes(P, es, g) + pad256(q) + pad256(sync_ints * sizeof(int32_t));
     b += 2 * pad256(kFetchStageBytes);                                         // proband staging
-    b += 4 * DevBuf<int32_t>::padded(P.mem_ind.size()) + 6 * DevBuf<int32_t>::padded(P.fam_pf.size()) +
-         DevBuf<int32_t>::padded(P.fam_start.size()) + 6 * DevBuf<int32_t>::padded(P.mtile_minrank.size()) +
-         2 * DevBuf<int32_t>::padded(P.pro_slot.size()) + DevBuf<int32_t>::padded(P.live_lrow.size()) +
-         2 * DevBuf<int8_t>::padded(P.fam_pf.size()) + DevBuf<int8_t>::padded(P.live_owner.size()) +
-         DevBuf<int8_t>::padded(P.mem_gowner.size()) + DevBuf<int32_t>::padded(P.mem_glrow.size()) +
-         DevBuf<int32_t>::padded(P.mem_rank.size()) +
-         DevBuf<uint8_t>::padded(P.flags.size()) + DevBuf<double>::padded(2);
+    b += 4 * DevBuf<int32_t>::padded(P.mem_ind.size()) + DevBuf<int32_t>::padded(P.mem_rank.size()) +
+         4 * DevBuf<int32_t>::padded(P.fam_pf.size()) + DevBuf<int32_t>::padded(P.fam_start.size()) +
+         4 * DevBuf<int32_t>::padded(P.mtile_fam0.size()) + 2 * DevBuf<int32_t>::padded(P.pro_slot.size()) +
+         DevBuf<int32_t>::padded(P.live_lrow.size()) + DevBuf<int32_t>::padded(P.tile_map.size()) +
+         2 * DevBuf<int8_t>::padded(P.fam_pf.size()) +
+         DevBuf<int8_t>::padded(P.live_owner.size()) + DevBuf<uint8_t>::padded(P.flags.size()) + DevBuf<double>::padded(4);
     return b;
 }
 
@@ -254,38 +322,32 @@ LayerArgs layer_args(const genlib_engine &E, int t) {
     const Layer &L = P.layers[t];
     LayerArgs a;
     std::memset(&a, 0, sizeof a);
-    a.n_new = L.n_new; a.n_fam = L.n_fam; a.rt_lo = L.rt_lo; a.rt_rows = L.rt_rows; a.nf_pad = L.nf_pad;
+    a.n_new = L.n_new; a.n_fam = L.n_fam; a.rt_lo = L.rt_lo; a.rt_rows = L.live_before > 0 ? L.rt_rows : 0; a.nf_pad = L.nf_pad;
     a.any_carried = L.carried > 0;
     a.rank = E.rank; a.world = E.world;
     const int32_t *fb = P.fam_base.data() + L.base_off, *mb = P.mem_base.data() + L.base_off;
     for (int g = 0; g <= E.world; g++) a.fam_base[g] = fb[g];
     a.own_f0 = fb[E.rank]; a.own_nf = fb[E.rank + 1] - fb[E.rank];
     a.own_m0 = mb[E.rank]; a.own_nm = mb[E.rank + 1] - mb[E.rank];
-    a.nfo_pad = pad32(a.own_nf);
-    a.ftile_shift = E.world > 1 ? fb[(E.rank + 1) % E.world] / kFTile : 0;
     a.mem_ind = E.mem_ind.p + L.mem_off; a.mem_slot = E.mem_slot.p + L.mem_off; a.mem_fam = E.mem_fam.p + L.mem_off;
     a.mem_lrow = E.mem_lrow.p + L.mem_off;
-    a.mem_gowner = E.mem_gowner.p + L.mem_off; a.mem_glrow = E.mem_glrow.p + L.mem_off;
     a.fam_pf = E.fam_pf.p + L.fam_off; a.fam_pm = E.fam_pm.p + L.fam_off;
     a.fam_pf_owner = E.fam_pf_owner.p + L.fam_off; a.fam_pm_owner = E.fam_pm_owner.p + L.fam_off;
     a.fam_pf_lrow = E.fam_pf_lrow.p + L.fam_off; a.fam_pm_lrow = E.fam_pm_lrow.p + L.fam_off;
     a.fam_start = E.fam_start.p + L.fam_off + t;
     a.flags = E.flags.p + L.flag_off;
     a.live_owner = E.live_owner.p + L.flag_off; a.live_lrow = E.live_lrow.p + L.flag_off;
-    a.fam_minrank = E.fam_minrank.p + L.fam_off; a.fam_maxrank = E.fam_maxrank.p + L.fam_off;
-    a.mt_minrank = E.mt_min.p + L.mtile_off; a.mt_maxrank = E.mt_max.p + L.mtile_off;
+    a.tile_map = E.tile_map.p + L.tile_off;
     a.mt_fam0 = E.mt_fam0.p + L.mtile_off; a.mt_nfam = E.mt_nfam.p + L.mtile_off;
     a.mt_m0 = E.mt_m0.p + L.mtile_off; a.mt_cnt = E.mt_cnt.p + L.mtile_off;
     a.n_mtiles = L.n_mtiles;
-    const int vec = 16 / (int)E.esize;
-    a.vstride = (std::max(L.max_tile_fam, 1) + vec - 1) / vec * vec + vec;
     return a;
 }
 
 int launch_barrier(genlib_engine &E) {
     if (E.world == 1) return GENLIB_OK;
     E.epoch++;
-    barrier_kernel<<<1, 32, 0, E.stream>>>(E.bars, E.rank, E.world, E.epoch, (long long)20e9);
+    barrier_kernel<<<1, 32, 0, E.stream>>>(E.bars, E.rank, E.world, E.epoch, E.barrier_timeout);
     return GENLIB_OK;
 }
 
@@ -294,26 +356,13 @@ int launch_layers(genlib_engine &E, bool timed) {
     const Plan &P = E.plan->p;
     T *A = static_cast<T *>(E.A);
     const int64_t ld = P.capacity;
-    const size_t cross_smem = cross_smem_bytes<T>();
-    const int vec = 16 / (int)sizeof(T);
-    int max_tile_fam = 1;
-    for (const Layer &L : P.layers) max_tile_fam = std::max(max_tile_fam, L.max_tile_fam);
-    const size_t expand_smem_max = (size_t)kEWarps * 2 * expand_stage_bytes<T>((max_tile_fam + vec - 1) / vec * vec + vec);
-    if (expand_smem_max > 227 * 1024) return fail(GENLIB_EINVAL, "couple tile too wide for the expand kernel");
-    auto expand_fn = E.world > 1 ? expand_kernel<T, true> : expand_kernel<T, false>;
-    CU(cudaFuncSetAttribute(expand_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)expand_smem_max));
     const bool stored = sparse_schedule(P.schedule);           // sparse_phi's arithmetic (Float32 halves of stored values)
-    auto cross_fn = stored ? cross_kernel<T, true> : cross_kernel<T, false>;
-    auto couple_fn = stored ? couple_kernel<T, true> : couple_kernel<T, false>;
-    const size_t cross_smem_piped = std::max<size_t>(cross_smem, 120 * 1024);    // one CTA per SM
-    CU(cudaFuncSetAttribute(cross_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cross_smem_piped));
-    CU(cudaFuncSetAttribute(cross_fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    CU(cudaFuncSetAttribute(expand_fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    T *V = static_cast<T *>(E.Vrow), *Vt = static_cast<T *>(E.Vt), *Dg = static_cast<T *>(E.Dg);
-    constexpr int kCRows = couple_rows<T>();
-    const size_t couple_smem = sizeof(T) * kCRows * kCStride;
-    CU(cudaFuncSetAttribute(couple_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)couple_smem));
-    CU(cudaFuncSetAttribute(couple_fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    auto layer_fn = stored ? layer_kernel<T, true> : layer_kernel<T, false>;
+    size_t smem_max = 0;
+    for (const LayerLaunch &ll : E.launch) smem_max = std::max(smem_max, ll.smem);
+    CU(cudaFuncSetAttribute(layer_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    CU(cudaFuncSetAttribute(layer_fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CU(cudaMemsetAsync(E.sync, 0, std::max<size_t>(E.sync_ints, 1) * sizeof(int32_t), E.stream));
     int launches = 0;
     size_t ev = 0;
     for (int t = 0; t < (int)P.layers.size(); t++) {
@@ -321,75 +370,21 @@ int launch_layers(genlib_engine &E, bool timed) {
         if (L.n_new == 0) continue;
         if (E.layer_limit >= 0 && t >= E.layer_limit) break;
         LayerArgs a = layer_args(E, t);
+        LayerLaunch &ll = E.launch[t];
         if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
-        // Couple groups (GENLIB_PIPE=1, several ranks): cross_kernel fills the columns of Rt that belong to a
-        // group of own couples and couple_kernel consumes exactly those columns.  Cross is bound by NVLink
-        // INGRESS (remote parent rows), couple by NVLink EGRESS (rows of V pushed to their owners), so
-        // couple(group g) runs on a second, high-priority stream beside cross(group g + 1); cross then asks
-        // for enough shared memory to keep ONE of its CTAs per SM, which leaves room for couple's.
-        const int64_t ftiles = (a.own_nf + kFTile - 1) / kFTile;
-        if (ftiles > 65535 || (L.n_fam + kCRows - 1) / kCRows > 65535) return fail(GENLIB_EINVAL, "layer too wide for one cross/couple launch");
-        const int per_ctile = kCTile / kFTile;
-        int groups = 1;
-        if (E.piped && L.live_before > 0) groups = (int)std::max<int64_t>(1, std::min<int64_t>(kMaxGroups, ftiles / (16 * per_ctile)));
-        const int64_t group_tiles = ((ftiles + groups - 1) / groups + per_ctile - 1) / per_ctile * per_ctile;
-        const bool piped = groups > 1;
-        for (int g = 0; g < groups && a.own_nf > 0; g++) {
-            const int64_t ft0 = g * group_tiles, ft1 = std::min<int64_t>(ftiles, ft0 + group_tiles);
-            if (ft0 >= ft1) break;
-            const bool last = ft1 >= ftiles;
-            a.ctile0 = (int32_t)ft0;
-            if (L.live_before > 0) {
-                // column tiles per CTA: long chunks amortise the pipeline fill, but keep >= ~4 waves of CTAs
-                const int64_t ptiles = L.rt_rows / kPTile;
-                const int64_t want = ptiles * (ft1 - ft0) / (4 * 2 * (int64_t)E.sm_count);
-                a.pchunk = (int)std::max<int64_t>(std::min<int64_t>(4, ptiles), std::min<int64_t>(kMaxPChunk, want));
-                dim3 grid((unsigned)((ptiles + a.pchunk - 1) / a.pchunk), (unsigned)(ft1 - ft0));
-                cross_fn<<<grid, kThreads, piped ? cross_smem_piped : cross_smem, E.stream>>>(A, ld, E.Rt, E.peers, a);
-                launches++;
-            }
-            if (last && L.live_before > 0 && L.carried > 0 && a.own_nm > 0) {
-                dim3 mgrid((unsigned)((a.own_nm + 32 * kMirrorCols - 1) / (32 * kMirrorCols)), (unsigned)((L.rt_rows + kThreads / 32 - 1) / (kThreads / 32)));
-                mirror_kernel<T><<<mgrid, kThreads, 0, E.stream>>>(E.Rt, ld, E.peers, a);
-                launches++;
-            }
-            if (last && timed) CU(cudaEventRecord(E.events[ev++], E.stream));
-            cudaStream_t cs = E.stream;
-            if (piped) {
-                CU(cudaEventRecord(E.group_ev[g], E.stream));
-                CU(cudaStreamWaitEvent(E.side_stream, E.group_ev[g], 0));
-                cs = E.side_stream;
-            }
-            const int64_t ct0 = ft0 / per_ctile, ct1 = (std::min<int64_t>(ft1 * kFTile, a.nfo_pad) + kCTile - 1) / kCTile;
-            dim3 cgrid((unsigned)(ct1 - ct0), (unsigned)((L.n_fam + kCRows - 1) / kCRows));
-            couple_fn<<<cgrid, kThreads, couple_smem, cs>>>(ld, E.Rt, Vt, Dg, E.peers, a);
+        if (ll.grid > 0) {
+            ll.s.Q = E.Q;
+            ll.s.sync = E.sync + ll.sync_off;
+            layer_fn<<<ll.grid, kLayerThreads, ll.smem, E.stream>>>(A, ld, E.peers, a, ll.s);
             launches++;
-        }
-        if (a.own_nf <= 0 && timed) CU(cudaEventRecord(E.events[ev++], E.stream));
-        if (piped) {                                         // join: the layer's V is complete on the main stream
-            CU(cudaEventRecord(E.group_ev[kMaxGroups], E.side_stream));
-            CU(cudaStreamWaitEvent(E.stream, E.group_ev[kMaxGroups], 0));
-        }
-        a.ctile0 = 0;
-        if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
-        launch_barrier(E);                 // every rank's row block of V is complete (peer stores landed)
-        if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
-        if (a.own_nm > 0) {
-            const int rows_per_cta = kEWarps * kERows;
-            dim3 grid((unsigned)((L.n_mtiles + kEChunk - 1) / kEChunk), (unsigned)((a.own_nm + rows_per_cta - 1) / rows_per_cta));
-            if (grid.y > 65535) return fail(GENLIB_EINVAL, "layer too wide for one expand launch");
-            const size_t smem = (size_t)kEWarps * 2 * expand_stage_bytes<T>(a.vstride);
-            expand_fn<<<grid, kExpandThreads, smem, E.stream>>>(A, ld, V, Vt, Dg, E.peers, a);
-            launches++;
-            if (P.schedule == kScheduleSparsePhi && L.n_new > 1) {      // the reference's misfiled kinships read as 0
-                if (E.world > 1 && P.guest_cap[E.rank] > 0) return fail(GENLIB_EINVAL, "sparse_phi schedule with guest rows is not supported");
+            if (P.schedule == kScheduleSparsePhi && L.n_new > 1 && a.own_nm > 0) {   // the reference's misfiled kinships read as 0
                 dim3 mgrid((unsigned)a.own_nm, (unsigned)std::min<int64_t>((L.n_new + 4 * kThreads - 1) / (4 * kThreads), 65535));
                 misfile_kernel<T><<<mgrid, kThreads, 0, E.stream>>>(A, ld, E.mem_rank.p + L.mem_off, a);
                 launches++;
             }
         }
         if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
-        launch_barrier(E);                 // all new rows exist everywhere before the next layer reads them
+        launch_barrier(E);                 // all new rows (and mirrored columns) exist everywhere before the next layer reads them
         if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
     }
     CU(cudaGetLastError());
@@ -409,33 +404,71 @@ int fetch_rows(genlib_engine &E, O *out) {
     int32_t rows_per = (int32_t)std::max<size_t>(1, std::min<size_t>((size_t)nown, kFetchStageBytes / row_bytes));
     if ((size_t)rows_per * row_bytes > kFetchStageBytes) return fail(GENLIB_EINVAL, "proband row does not fit the staging buffer");
     rows_per = std::min(rows_per, 65535);
-    O *stage[2] = {nullptr, nullptr};
-    cudaEvent_t done[2], copied[2];
-    for (int b = 0; b < 2; b++) {
-        stage[b] = reinterpret_cast<O *>(E.fetch_stage[b]);
-        CU(cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
+    O *stage[2] = {reinterpret_cast<O *>(E.fetch_stage[0]), reinterpret_cast<O *>(E.fetch_stage[1])};
+    cudaEvent_t done[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
+    cudaError_t ce = cudaSuccess;
+    for (int b = 0; b < 2 && ce == cudaSuccess; b++) {
+        ce = cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming);
     }
-    int rc = GENLIB_OK;
     int blk = 0;
-    for (int32_t r0 = 0; r0 < nown; r0 += rows_per, blk++) {
+    for (int32_t r0 = 0; r0 < nown && ce == cudaSuccess; r0 += rows_per, blk++) {
         const int b = blk & 1;
         const int32_t nr = std::min(rows_per, nown - r0);
-        if (blk >= 2 && cudaStreamWaitEvent(E.stream, copied[b], 0) != cudaSuccess) { rc = GENLIB_ECUDA; break; }
+        if (blk >= 2 && (ce = cudaStreamWaitEvent(E.stream, copied[b], 0)) != cudaSuccess) break;
         dim3 grid((unsigned)std::min<int32_t>((n + 255) / 256, 64), (unsigned)nr);
         gather_kernel<T, O><<<grid, 256, 0, E.stream>>>(static_cast<const T *>(E.A), P.capacity, E.own_pro_row.p, E.pro_slot.p,
                                                        n, r0, nr, stage[b]);
         cudaEventRecord(done[b], E.stream);
         cudaStreamWaitEvent(E.copy_stream, done[b], 0);
-        if (cudaMemcpyAsync(out + (size_t)r0 * n, stage[b], (size_t)nr * row_bytes, cudaMemcpyDeviceToHost, E.copy_stream) != cudaSuccess) { rc = GENLIB_ECUDA; break; }
+        ce = cudaMemcpyAsync(out + (size_t)r0 * n, stage[b], (size_t)nr * row_bytes, cudaMemcpyDeviceToHost, E.copy_stream);
         cudaEventRecord(copied[b], E.copy_stream);
     }
-    cudaError_t e1 = cudaStreamSynchronize(E.stream), e2 = cudaStreamSynchronize(E.copy_stream);
-    for (int b = 0; b < 2; b++) { cudaEventDestroy(done[b]); cudaEventDestroy(copied[b]); }
-    if (rc != GENLIB_OK || e1 != cudaSuccess || e2 != cudaSuccess)
-        return fail(GENLIB_ECUDA, std::string("proband fetch failed: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    const cudaError_t e1 = cudaStreamSynchronize(E.stream), e2 = cudaStreamSynchronize(E.copy_stream);
+    for (int b = 0; b < 2; b++) { if (done[b]) cudaEventDestroy(done[b]); if (copied[b]) cudaEventDestroy(copied[b]); }
+    if (ce != cudaSuccess || e1 != cudaSuccess || e2 != cudaSuccess)
+        return fail(GENLIB_ECUDA, std::string("proband fetch failed: ") + cudaGetErrorString(ce != cudaSuccess ? ce : e1 != cudaSuccess ? e1 : e2));
     E.stats.d2h_bytes += (int64_t)nown * (int64_t)row_bytes;
     return GENLIB_OK;
+}
+
+// Compulsory traffic of every layer on this rank (genlib_layer_info), from the plan.
+void account_layers(genlib_engine &E) {
+    if (E.info_ready) return;
+    const Plan &P = E.plan->p;
+    const double es = (double)E.esize;
+    for (size_t t = 0; t < P.layers.size(); t++) {
+        const Layer &L = P.layers[t];
+        genlib_layer_info &o = E.info[t];
+        if (L.n_new == 0) continue;
+        const int32_t *fb = P.fam_base.data() + L.base_off, *mb = P.mem_base.data() + L.base_off;
+        const int64_t f0 = fb[E.rank], f1 = fb[E.rank + 1], own_nm = mb[E.rank + 1] - mb[E.rank];
+        int64_t rows_local = 0, rows_remote = 0;
+        for (int64_t F = f0; F < f1; F++) {
+            const int8_t of = P.fam_pf_owner[L.fam_off + F], om = P.fam_pm_owner[L.fam_off + F];
+            if (of >= 0) (of == E.rank ? rows_local : rows_remote)++;
+            if (om >= 0) (om == E.rank ? rows_local : rows_remote)++;
+        }
+        int64_t parents_all = 0;
+        for (int64_t F = 0; F < L.n_fam; F++) parents_all += (P.fam_pf[L.fam_off + F] >= 0) + (P.fam_pm[L.fam_off + F] >= 0);
+        int64_t carried_remote = 0;
+        if (E.world > 1 && L.carried > 0)
+            for (int32_t r = 0; r < L.rt_rows; r++)
+                if ((P.flags[L.flag_off + r] & kFlagCarried) && P.live_owner[L.flag_off + r] != E.rank) carried_remote++;
+        const double live = L.live_before, carried = L.carried;
+        const LayerLaunch &ll = E.launch[t];
+        o.strip_width = ll.s.sw;
+        // DRAM: the parent rows of own couples over the live columns, read once; own members' rows
+        // (new x new, new x carried) and their columns in the carried rows, written once
+        o.dram_read_bytes = (double)rows_local * live * es;
+        o.dram_write_bytes = (double)own_nm * ((double)L.n_new + carried) * es + ((double)(L.carried - carried_remote)) * (double)own_nm * es;
+        // L2: the strip buffers, written once and read back per couple of the layer
+        o.l2_bytes = (double)(rows_local + rows_remote > 0 ? (f1 - f0) : 0) * live * 2 * es +
+                     (double)parents_all * (double)(ll.s.n_strips * (int64_t)ll.s.sw) * 2 * es + carried * (double)(f1 - f0) * 2 * es;
+        // NVLink: remote parent rows read, own members' columns pushed into carried rows that live elsewhere
+        o.nvlink_bytes = (double)rows_remote * live * es + (double)carried_remote * (double)own_nm * es;
+    }
+    E.info_ready = true;
 }
 
 int create_engine(const genlib_plan *plan, int numerics, int device, int rank, genlib_engine **out) {
@@ -459,20 +492,26 @@ int create_engine(const genlib_plan *plan, int numerics, int device, int rank, g
     E->esize = numerics == GENLIB_NUMERICS_FP64 ? 8 : 4;
     CU(cudaGetDevice(&E->device));
     CU(cudaDeviceGetAttribute(&E->sm_count, cudaDevAttrMultiProcessorCount, E->device));
-    const size_t need = engine_bytes(P, numerics, rank);
+    {
+        const char *env = std::getenv("GENLIB_BARRIER_TIMEOUT_S");       // inter-GPU barrier: seconds before GENLIB_ECOMM
+        const double sec = env ? std::atof(env) : 10.0;
+        E->barrier_timeout = (long long)(std::max(sec, 0.001) * 2e9);
+    }
     const double t0 = now_ms();
+    // launch shapes, strip buffers, sync words
+    E->launch.resize(P.layers.size());
+    E->q_bytes = 256;
+    for (int t = 0; t < (int)P.layers.size(); t++) {
+        LayerLaunch &ll = E->launch[t];
+        ll = shape_layer(P, t, rank, E->esize, E->sm_count);
+        if (ll.grid == 0) continue;
+        E->q_bytes = std::max(E->q_bytes, strip_buffer_bytes(ll, E->esize));
+        ll.sync_off = E->sync_ints;
+        E->sync_ints += 2 + 2 * (size_t)ll.s.n_strips;
+    }
+    const size_t need = engine_bytes(P, numerics, rank, E->sm_count);
     CU(cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&E->copy_stream, cudaStreamNonBlocking));
-    {
-        const char *env = std::getenv("GENLIB_PIPE");
-        E->piped = E->world > 1 && env && env[0] == '1';
-    }
-    if (E->piped) {
-        int lo = 0, hi = 0;
-        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));      // hi = numerically lowest = highest priority
-        CU(cudaStreamCreateWithPriority(&E->side_stream, cudaStreamNonBlocking, hi));
-        for (auto &e : E->group_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    }
     {
         cudaError_t ce = g_arenas.acquire(E->device, need, E->arena);
         if (ce != cudaSuccess) {
@@ -489,32 +528,44 @@ int create_engine(const genlib_plan *plan, int numerics, int device, int rank, g
         auto take = [&](size_t bytes) { unsigned char *p = cur; cur += pad256(bytes); return p; };
         E->bar_flags = reinterpret_cast<unsigned *>(take(kFlagBytes));
         E->A = take(total_rows(P, rank) * (size_t)P.capacity * E->esize);
-        E->Vrow = take(P.rank_v_elems[rank] * E->esize);
-        E->Vt = take(P.rank_v_elems[rank] * E->esize);
-        E->Rt = reinterpret_cast<double *>(take(P.rank_rt_elems[rank] * sizeof(double)));
-        E->Dg = take(P.fam_pf.size() * E->esize);
+        E->Q = take(E->q_bytes);
+        E->sync = reinterpret_cast<int32_t *>(take(E->sync_ints * sizeof(int32_t)));
         E->fetch_stage[0] = take(kFetchStageBytes);
         E->fetch_stage[1] = take(kFetchStageBytes);
         E->mem_ind.place(cur, P.mem_ind.size()); E->mem_slot.place(cur, P.mem_slot.size()); E->mem_fam.place(cur, P.mem_fam.size());
-        E->mem_lrow.place(cur, P.mem_lrow.size());
+        E->mem_lrow.place(cur, P.mem_lrow.size()); E->mem_rank.place(cur, P.mem_rank.size());
         E->fam_pf.place(cur, P.fam_pf.size()); E->fam_pm.place(cur, P.fam_pm.size());
         E->fam_pf_lrow.place(cur, P.fam_pf_lrow.size()); E->fam_pm_lrow.place(cur, P.fam_pm_lrow.size());
-        E->fam_minrank.place(cur, P.fam_minrank.size()); E->fam_maxrank.place(cur, P.fam_maxrank.size());
         E->fam_start.place(cur, P.fam_start.size());
-        E->mt_min.place(cur, P.mtile_minrank.size()); E->mt_max.place(cur, P.mtile_maxrank.size());
         E->mt_fam0.place(cur, P.mtile_fam0.size()); E->mt_nfam.place(cur, P.mtile_nfam.size());
         E->mt_m0.place(cur, P.mtile_m0.size()); E->mt_cnt.place(cur, P.mtile_cnt.size());
         E->pro_slot.place(cur, P.pro_slot.size()); E->own_pro_row.place(cur, P.pro_slot.size());
-        E->live_lrow.place(cur, P.live_lrow.size());
+        E->live_lrow.place(cur, P.live_lrow.size()); E->tile_map.place(cur, P.tile_map.size());
         E->fam_pf_owner.place(cur, P.fam_pf_owner.size()); E->fam_pm_owner.place(cur, P.fam_pm_owner.size());
         E->live_owner.place(cur, P.live_owner.size());
-        E->mem_gowner.place(cur, P.mem_gowner.size()); E->mem_glrow.place(cur, P.mem_glrow.size());
-        E->mem_rank.place(cur, P.mem_rank.size());
-        E->flags.place(cur, P.flags.size()); E->acc.place(cur, 2);
+        E->flags.place(cur, P.flags.size()); E->acc.place(cur, 4);
         if ((size_t)(cur - base) > need) return fail(GENLIB_EINVAL, "internal: arena layout overflow");
-        if ((size_t)(static_cast<unsigned char *>(E->A) - base) != off_A() ||
-            (size_t)(static_cast<unsigned char *>(E->Vrow) - base) != off_Vrow(P, E->esize, rank))
+        if ((size_t)(static_cast<unsigned char *>(E->A) - base) != off_A())
             return fail(GENLIB_EINVAL, "internal: peer-visible arena offsets drifted");
+    }
+    // The strip buffers stay in L2: a persisting access-policy window on the engine's stream
+    // (everything else streams through the rest of the cache).
+    {
+        int max_persist = 0, max_window = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, E->device);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, E->device);
+        const char *env = std::getenv("GENLIB_L2_PERSIST");                // "0": leave the cache policy alone
+        if (max_persist > 0 && max_window > 0 && !(env && env[0] == '0')) {
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+            cudaStreamAttrValue attr;
+            std::memset(&attr, 0, sizeof attr);
+            attr.accessPolicyWindow.base_ptr = E->Q;
+            attr.accessPolicyWindow.num_bytes = std::min<size_t>(E->q_bytes, (size_t)max_window);
+            attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)max_persist / (double)std::max<size_t>(E->q_bytes, 1));
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+            if (cudaStreamSetAttribute(E->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+        }
     }
     // this rank's probands, in output order
     std::vector<int32_t> own_rows;
@@ -525,6 +576,7 @@ int create_engine(const genlib_plan *plan, int numerics, int device, int rank, g
     CU(E->mem_slot.upload(P.mem_slot, E->stream));
     CU(E->mem_fam.upload(P.mem_fam, E->stream));
     CU(E->mem_lrow.upload(P.mem_lrow, E->stream));
+    CU(E->mem_rank.upload(P.mem_rank, E->stream));
     CU(E->fam_pf.upload(P.fam_pf, E->stream));
     CU(E->fam_pm.upload(P.fam_pm, E->stream));
     CU(E->fam_pf_lrow.upload(P.fam_pf_lrow, E->stream));
@@ -532,10 +584,6 @@ int create_engine(const genlib_plan *plan, int numerics, int device, int rank, g
     CU(E->fam_pf_owner.upload(P.fam_pf_owner, E->stream));
     CU(E->fam_pm_owner.upload(P.fam_pm_owner, E->stream));
     CU(E->fam_start.upload(P.fam_start, E->stream));
-    CU(E->fam_minrank.upload(P.fam_minrank, E->stream));
-    CU(E->fam_maxrank.upload(P.fam_maxrank, E->stream));
-    CU(E->mt_min.upload(P.mtile_minrank, E->stream));
-    CU(E->mt_max.upload(P.mtile_maxrank, E->stream));
     CU(E->mt_fam0.upload(P.mtile_fam0, E->stream));
     CU(E->mt_nfam.upload(P.mtile_nfam, E->stream));
     CU(E->mt_m0.upload(P.mtile_m0, E->stream));
@@ -544,16 +592,14 @@ int create_engine(const genlib_plan *plan, int numerics, int device, int rank, g
     CU(E->own_pro_row.upload(own_rows, E->stream));
     CU(E->live_owner.upload(P.live_owner, E->stream));
     CU(E->live_lrow.upload(P.live_lrow, E->stream));
-    CU(E->mem_gowner.upload(P.mem_gowner, E->stream));
-    CU(E->mem_glrow.upload(P.mem_glrow, E->stream));
-    CU(E->mem_rank.upload(P.mem_rank, E->stream));
+    CU(E->tile_map.upload(P.tile_map, E->stream));
     CU(E->flags.upload(P.flags, E->stream));
     CU(cudaStreamSynchronize(E->stream));
-    E->peers.A[rank] = E->A; E->peers.Vrow[rank] = E->Vrow; E->bars.flags[rank] = E->bar_flags;
+    E->peers.A[rank] = E->A; E->bars.flags[rank] = E->bar_flags;
     E->attached = P.world == 1;
     E->info.resize(P.layers.size());
     for (size_t t = 0; t < P.layers.size(); t++) fill_info(P.layers[t], &E->info[t]);
-    E->events.resize(P.layers.size() * 6 + 2);
+    E->events.resize(P.layers.size() * 3 + 2);
     for (auto &e : E->events) CU(cudaEventCreate(&e));
     genlib_stats &s = E->stats;
     s.n_unique = P.n_unique; s.n_layers = (int32_t)P.layers.size(); s.row_updates = P.row_updates;
@@ -647,7 +693,7 @@ int genlib_plan_layer_info(const genlib_plan *plan, int32_t layer, genlib_layer_
 
 int64_t genlib_plan_device_bytes(const genlib_plan *plan, int numerics, int32_t rank) {
     if (!plan || rank < 0 || rank >= plan->p.world || plan->p.n_unique == 0) return plan ? 0 : -1;
-    return (int64_t)engine_bytes(plan->p, numerics, rank);
+    return (int64_t)engine_bytes(plan->p, numerics, rank);      // strip buffers sized for 148 SMs
 }
 
 int genlib_plan_layer_arrays(const genlib_plan *plan, int32_t layer, int32_t *member_ind,
@@ -684,8 +730,7 @@ int genlib_plan_layer_ranks(const genlib_plan *plan, int32_t layer, int32_t *mem
 
 int genlib_plan_layer_shard(const genlib_plan *plan, int32_t layer, int32_t *fam_base, int32_t *mem_base,
                             int32_t *member_lrow, int32_t *fam_father_owner, int32_t *fam_father_lrow,
-                            int32_t *fam_mother_owner, int32_t *fam_mother_lrow, int32_t *member_guest_owner,
-                            int32_t *member_guest_lrow) {
+                            int32_t *fam_mother_owner, int32_t *fam_mother_lrow) {
     if (!plan || layer < 0 || layer >= (int32_t)plan->p.layers.size()) return fail(GENLIB_EINVAL, "bad layer");
     const Plan &P = plan->p;
     const Layer &L = P.layers[layer];
@@ -693,11 +738,8 @@ int genlib_plan_layer_shard(const genlib_plan *plan, int32_t layer, int32_t *fam
         if (fam_base) fam_base[g] = P.fam_base[L.base_off + g];
         if (mem_base) mem_base[g] = P.mem_base[L.base_off + g];
     }
-    for (int32_t q = 0; q < L.n_new; q++) {
+    for (int32_t q = 0; q < L.n_new; q++)
         if (member_lrow) member_lrow[q] = P.mem_lrow[L.mem_off + q];
-        if (member_guest_owner) member_guest_owner[q] = P.mem_gowner[L.mem_off + q];
-        if (member_guest_lrow) member_guest_lrow[q] = P.mem_glrow[L.mem_off + q];
-    }
     for (int32_t f = 0; f < L.n_fam; f++) {
         if (fam_father_owner) fam_father_owner[f] = P.fam_pf_owner[L.fam_off + f];
         if (fam_father_lrow) fam_father_lrow[f] = P.fam_pf_lrow[L.fam_off + f];
@@ -773,7 +815,6 @@ int genlib_engine_ipc_attach(genlib_engine *eng, const void *handles, size_t str
     if (eng->attached) return GENLIB_OK;
     DeviceGuard guard;
     if (int rc = guard.enter(eng->device)) return rc;
-    const Plan &P = eng->plan->p;
     for (int g = 0; g < eng->world; g++) {
         if (g == eng->rank) continue;
         void *base = nullptr;
@@ -782,11 +823,9 @@ int genlib_engine_ipc_attach(genlib_engine *eng, const void *handles, size_t str
             cudaGetLastError();
             return fail(GENLIB_ECOMM, std::string("cudaIpcOpenMemHandle(rank ") + std::to_string(g) + "): " + cudaGetErrorString(ce));
         }
-        eng->peer_base[g] = base;
         unsigned char *b = static_cast<unsigned char *>(base);
         eng->bars.flags[g] = reinterpret_cast<unsigned *>(b);
         eng->peers.A[g] = b + off_A();
-        eng->peers.Vrow[g] = b + off_Vrow(P, eng->esize, g);
     }
     eng->attached = true;
     return GENLIB_OK;
@@ -828,16 +867,23 @@ int genlib_engine_run(genlib_engine *eng, int time_layers) {
         for (size_t t = 0; t < E.info.size(); t++) {
             if (E.info[t].n_new == 0) continue;
             if (E.layer_limit >= 0 && (int32_t)t >= E.layer_limit) break;
-            float a = 0, b = 0, w1 = 0, c = 0, w2 = 0;
+            float a = 0, w = 0;
             CU(cudaEventElapsedTime(&a, E.events[ev], E.events[ev + 1]));
-            CU(cudaEventElapsedTime(&b, E.events[ev + 1], E.events[ev + 2]));
-            CU(cudaEventElapsedTime(&w1, E.events[ev + 2], E.events[ev + 3]));
-            CU(cudaEventElapsedTime(&c, E.events[ev + 3], E.events[ev + 4]));
-            CU(cudaEventElapsedTime(&w2, E.events[ev + 4], E.events[ev + 5]));
-            ev += 6;
-            E.info[t].ms_cross = a; E.info[t].ms_couple = b; E.info[t].ms_expand = c;
-            E.info[t].ms_wait = w1 + w2;
+            CU(cudaEventElapsedTime(&w, E.events[ev + 1], E.events[ev + 2]));
+            ev += 3;
+            E.info[t].ms_layer = a; E.info[t].ms_wait = w;
         }
+    }
+    {
+        int32_t errw = 0;                                     // a dependency inside a layer kernel timed out
+        for (const LayerLaunch &ll : E.launch)
+            if (ll.grid > 0) {
+                int32_t w2[2] = {0, 0};
+                CU(cudaMemcpy(w2, E.sync + ll.sync_off, sizeof w2, cudaMemcpyDeviceToHost));
+                errw |= w2[1];
+                if (errw) break;
+            }
+        if (errw) return fail(GENLIB_ECUDA, "a unit of the layer kernel waited too long for its strip (internal error)");
     }
     if (E.world > 1) {
         unsigned errw = 0;
@@ -848,8 +894,9 @@ int genlib_engine_run(genlib_engine *eng, int time_layers) {
     return GENLIB_OK;
 }
 
-int genlib_engine_layer_info(const genlib_engine *eng, int32_t layer, genlib_layer_info *out) {
+int genlib_engine_layer_info(genlib_engine *eng, int32_t layer, genlib_layer_info *out) {
     if (!eng || !out || layer < 0 || layer >= (int32_t)eng->info.size()) return fail(GENLIB_EINVAL, "bad layer");
+    account_layers(*eng);
     *out = eng->info[layer];
     return GENLIB_OK;
 }

@@ -122,9 +122,9 @@ struct Scratch {
     std::vector<int32_t> seq_order, orient, cstart, clist, depth;   // sparse_phi schedule
     std::vector<int32_t> hist, count, by_layer, cut_size, both_size;
     std::vector<Home> home;
-    std::vector<size_t> lstart, pos, mem_pos_of;
+    std::vector<size_t> lstart, pos;
     std::vector<int64_t> d_cut, d_both;
-    std::vector<int32_t> born_layer, guest_count, live, next_live;
+    std::vector<int32_t> live, next_live;
     std::vector<int32_t> fam_of, fam_count, fam_first, fam_key, fam_n;   // couples of every layer (grouped ahead by helper threads)
     std::vector<int32_t> order, newid, load, freed, cnt, ipos;
     std::vector<FamilyTable> tables;          // one per planning thread
@@ -335,30 +335,14 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
     }
 
     if (world > 127) { err = "at most 127 ranks"; return GENLIB_EINVAL; }
-    // Guest copies (below) trade NVLink reads in cross_kernel for NVLink writes in expand_kernel.
-    // Measured on 4 x B200 (C3): cross 1.21 -> 0.73 ms per layer, expand 0.47 -> 0.86 ms, whole pass
-    // 43.0 -> 46.5 ms: the volume is the same and in-kernel peer traffic does not overlap the HBM
-    // traffic of the same kernel, so they are OFF unless GENLIB_GUESTS=1.
-    const bool use_guests = [] { const char *s = std::getenv("GENLIB_GUESTS"); return s && s[0] == '1'; }();
     P.layers.resize(S);
     {   // upper bounds (untouched reserve costs nothing): members + alignment padding, couples + rank padding
         const size_t mcap = lstart[S] + 4 * (size_t)S, fcap = lstart[S] + 4 * (size_t)world * (size_t)S;
-        for (auto *v : {&P.mem_ind, &P.mem_slot, &P.mem_fam, &P.mem_lrow, &P.mem_glrow}) v->reserve(mcap);
+        for (auto *v : {&P.mem_ind, &P.mem_slot, &P.mem_fam, &P.mem_lrow}) v->reserve(mcap);
         if (by_seq) P.mem_rank.reserve(mcap);
-        P.mem_gowner.reserve(mcap);
-        for (auto *v : {&P.fam_pf, &P.fam_pm, &P.fam_pf_lrow, &P.fam_pm_lrow, &P.fam_minrank, &P.fam_maxrank}) v->reserve(fcap);
+        for (auto *v : {&P.fam_pf, &P.fam_pm, &P.fam_pf_lrow, &P.fam_pm_lrow}) v->reserve(fcap);
         P.fam_pf_owner.reserve(fcap); P.fam_pm_owner.reserve(fcap); P.fam_start.reserve(fcap + (size_t)S);
     }
-    // guest copies: the row of an individual born in layer t-1 is ALSO written, while it is
-    // computed, into a spare row of the rank that owns a layer-t couple of which it is the
-    // remote parent; that couple's cross kernel then reads locally instead of through NVLink.
-    // Encoded until the end of planning: kGuestMark + parity * kGuestStride + index.
-    constexpr int32_t kGuestMark = 1 << 30, kGuestStride = 1 << 28;
-    const bool guests = use_guests && world > 1;
-    std::vector<int32_t> &born_layer = W.born_layer; born_layer.assign(guests ? (size_t)n : 0, -1);
-    std::vector<size_t> &mem_pos_of = W.mem_pos_of; mem_pos_of.assign(guests ? (size_t)n : 0, 0);
-    std::vector<int32_t> &guest_count = W.guest_count; guest_count.assign((size_t)world, 0);
-    P.guest_cap.assign((size_t)world, 0);
     std::vector<int32_t> &live = W.live, &next_live = W.next_live;   // individuals live before the current step
     live.clear(); next_live.clear();
     // allocators: global column slots (lines, lowest free first) and local rows per rank (stack)
@@ -368,8 +352,6 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
     std::vector<std::vector<int32_t>> &freed_rows = W.freed_rows; freed_rows.resize((size_t)world);
     for (auto &v : freed_rows) v.clear();
     P.rows_cap.assign((size_t)world, 0);
-    P.rank_rt_elems.assign((size_t)world, 0);
-    P.rank_v_elems.assign((size_t)world, 0);
     std::vector<int32_t> &order = W.order;
     std::vector<int32_t> &newid = W.newid, &load = W.load, &freed = W.freed;
     load.assign((size_t)world, 0);
@@ -462,13 +444,12 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         // member arrays of a layer start 16-byte aligned (the expand kernel copies them in 16-byte chunks)
         while (P.mem_ind.size() % 4) {
             P.mem_ind.push_back(0); P.mem_slot.push_back(0); P.mem_fam.push_back(0); P.mem_lrow.push_back(0);
-            P.mem_gowner.push_back(-1); P.mem_glrow.push_back(-1);
             if (by_seq) P.mem_rank.push_back(0);
         }
         L.mem_off = P.mem_ind.size();
         L.fam_off = P.fam_pf.size();
         L.flag_off = P.flags.size();
-        L.mtile_off = P.mtile_minrank.size();
+        L.mtile_off = P.mtile_fam0.size();
         L.base_off = P.fam_base.size();
 
         // ---- live range and flags (state BEFORE the step) ----
@@ -495,6 +476,14 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
             }
             for (int32_t r = 0; r < L.rt_rows; r++)        // evicted slots in ascending order -> freed lines, ascending
                 if (fl[r] == kFlagLive) slots.release(L.rt_lo + r, freed);
+            // the strip buffers of the layer kernel hold the live tiles only (holes of a fragmented range cost nothing)
+            L.tile_off = P.tile_map.size();
+            P.tile_map.resize(L.tile_off + (size_t)(L.rt_rows / kPTile), -1);
+            for (int32_t tl = 0; tl < L.rt_rows / kPTile; tl++) {
+                bool any = false;
+                for (int32_t r = tl * kPTile; r < (tl + 1) * kPTile && !any; r++) any = fl[r] != 0;
+                if (any) P.tile_map[L.tile_off + (size_t)tl] = L.n_live_tiles++;
+            }
         }
 
         // ---- couples of the layer (grouped by group_layer, possibly on a helper thread) ----
@@ -576,7 +565,6 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         // ---- column slots (global, in lines) and local rows (per owner) ----
         P.mem_ind.resize(L.mem_off + (size_t)nn); P.mem_slot.resize(L.mem_off + (size_t)nn);
         P.mem_fam.resize(L.mem_off + (size_t)nn); P.mem_lrow.resize(L.mem_off + (size_t)nn);
-        P.mem_gowner.resize(L.mem_off + (size_t)nn, -1); P.mem_glrow.resize(L.mem_off + (size_t)nn, -1);
         if (by_seq) P.mem_rank.resize(L.mem_off + (size_t)nn);
         {
             int32_t *mi = P.mem_ind.data() + L.mem_off, *ms = P.mem_slot.data() + L.mem_off;
@@ -587,7 +575,6 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
                 const int32_t s = slots.take(), lr = world > 1 ? rows[g].take() : s;   // one rank: row == slot
                 Home &hx = home[x];
                 hx.slot = s; hx.lrow = lr; hx.owner = (int8_t)g;
-                if (guests) { born_layer[x] = t; mem_pos_of[x] = L.mem_off + (size_t)q; }
                 mi[q] = by_seq ? orient[x] : x; ms[q] = s; mf[q] = newid[f]; ml[q] = lr;
                 if (by_seq) P.mem_rank[L.mem_off + (size_t)q] = x;
             }
@@ -595,12 +582,9 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         P.fam_pf.resize(L.fam_off + (size_t)nf, -1); P.fam_pm.resize(L.fam_off + (size_t)nf, -1);
         P.fam_pf_owner.resize(L.fam_off + (size_t)nf, -1); P.fam_pm_owner.resize(L.fam_off + (size_t)nf, -1);
         P.fam_pf_lrow.resize(L.fam_off + (size_t)nf, -1); P.fam_pm_lrow.resize(L.fam_off + (size_t)nf, -1);
-        P.fam_minrank.resize(L.fam_off + (size_t)nf); P.fam_maxrank.resize(L.fam_off + (size_t)nf);
-        std::fill(guest_count.begin(), guest_count.end(), 0);
         for (int32_t f = 0; f < nf_real; f++) {
             const int32_t x = X[fam_first[f]], fa = father[x], mo = mother[x];
             const size_t k = L.fam_off + (size_t)newid[f];
-            const int32_t g = fam_own[f];
             int32_t *ps[2] = {&P.fam_pf[k], &P.fam_pm[k]};
             int8_t *po[2] = {&P.fam_pf_owner[k], &P.fam_pm_owner[k]};
             int32_t *pl[2] = {&P.fam_pf_lrow[k], &P.fam_pm_lrow[k]};
@@ -610,41 +594,16 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
                 if (p < 0) { *ps[s] = -1; *po[s] = -1; *pl[s] = -1; continue; }
                 const Home hp = home[p];
                 *ps[s] = hp.slot; *po[s] = hp.owner; *pl[s] = hp.lrow;
-                if (guests && hp.owner != g && born_layer[p] == t - 1) {
-                    const size_t mp = mem_pos_of[p];
-                    if (P.mem_gowner[mp] < 0) {                 // first remote consumer gets the copy
-                        P.mem_gowner[mp] = (int8_t)g;
-                        P.mem_glrow[mp] = kGuestMark + (t & 1) * kGuestStride + guest_count[g]++;
-                    }
-                    if (P.mem_gowner[mp] == g) { *po[s] = (int8_t)g; *pl[s] = P.mem_glrow[mp]; }
-                }
             }
         }
-        for (int32_t g = 0; g < world; g++) P.guest_cap[g] = std::max(P.guest_cap[g], guest_count[g]);
-        // V[F, G] ("a member of F is climbed first", compute.jl:130-138) is read only when some
-        // member of F outranks some member of G; the kernels skip the rest by these ranges.
-        {
-            const int32_t *mi = P.mem_ind.data() + L.mem_off;
-            for (int32_t f = 0; f < nf; f++) {
-                const bool empty = fstart[f + 1] == fstart[f];          // dummy couple: outranks nobody
-                P.fam_minrank[L.fam_off + f] = empty ? INT_MAX : mi[fstart[f]];
-                P.fam_maxrank[L.fam_off + f] = empty ? -1 : mi[fstart[f + 1] - 1];
-            }
-        }
-        // member tiles = the column steps of the expand kernel: at most kMTile members and at most
-        // kMaxTileFam couples (bounds the staged couple tile), starting at multiples of 4; per tile
-        // the rank range (lets the kernel skip one orientation) and the couple range
+        // member tiles = the column blocks the layer kernel writes at a time: at most kMTile members and at
+        // most kMaxTileFam couples (bounds the staged couple tile), cut at multiples of 8 members (whole
+        // 32-byte sectors of a float row on both sides of the cut)
         L.n_mtiles = 0;
         for (int32_t q0 = 0; q0 < nn;) {
             const int32_t *mf = P.mem_fam.data() + L.mem_off;
             int32_t q1 = std::min(nn, q0 + kMTile);
-            while (q1 > q0 + 4 && mf[q1 - 1] - mf[q0] >= kMaxTileFam) q1 = std::max(q0 + 4, (q1 - 1) & ~3);
-            int32_t lo = INT_MAX, hi = -1;
-            for (int32_t q = q0; q < q1; q++) {
-                int32_t x = P.mem_ind[L.mem_off + q];
-                lo = std::min(lo, x); hi = std::max(hi, x);
-            }
-            P.mtile_minrank.push_back(lo); P.mtile_maxrank.push_back(hi);
+            while (q1 > q0 + 8 && mf[q1 - 1] - mf[q0] >= kMaxTileFam) q1 = std::max(q0 + 8, (q1 - 1) & ~7);
             const int32_t f0 = mf[q0], f1 = mf[q1 - 1];
             P.mtile_fam0.push_back(f0); P.mtile_nfam.push_back(f1 - f0 + 1);
             P.mtile_m0.push_back(q0); P.mtile_cnt.push_back(q1 - q0);
@@ -655,13 +614,6 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         L.alg_elems = 4.0 * nn * (double)L.live_before + 3.0 * (double)nn * nn;
         P.alg_elems += L.alg_elems;
         P.row_updates += nn;
-        P.rt_elems_max = std::max(P.rt_elems_max, (size_t)L.rt_rows * (size_t)L.nf_pad);
-        P.v_elems_max = std::max(P.v_elems_max, (size_t)nf * (size_t)L.nf_pad);
-        for (int32_t g = 0; g < world; g++) {
-            const int32_t nfo = fbase[g + 1] - fbase[g];
-            P.rank_rt_elems[g] = std::max(P.rank_rt_elems[g], (size_t)L.rt_rows * (size_t)pad32(nfo));
-            P.rank_v_elems[g] = std::max(P.rank_v_elems[g], (size_t)std::max(nfo, 1) * (size_t)L.nf_pad);
-        }
 
         // ---- after the step: evicted slots / rows become reusable from the next layer on ----
         slots.end_layer(freed);
@@ -671,19 +623,6 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
     }
     P.capacity = round_up(std::max<int64_t>((int64_t)slots.next_fresh * kSlotLine, 1), kPTile);
     for (int32_t g = 0; g < world; g++) P.rows_cap[g] = world > 1 ? std::max(rows[g].next_fresh, 1) : P.capacity;
-    // resolve the guest rows: they sit behind the home rows of their rank, two banks (layer parity)
-    auto resolve = [&](int32_t owner, int32_t &lr) {
-        if (lr >= kGuestMark) {
-            const int32_t v = lr - kGuestMark, par = v / kGuestStride, idx = v % kGuestStride;
-            lr = (int32_t)P.rows_cap[owner] + par * P.guest_cap[owner] + idx;
-        }
-    };
-    for (size_t k = 0; k < P.fam_pf_lrow.size(); k++) {
-        if (P.fam_pf_owner[k] >= 0) resolve(P.fam_pf_owner[k], P.fam_pf_lrow[k]);
-        if (P.fam_pm_owner[k] >= 0) resolve(P.fam_pm_owner[k], P.fam_pm_lrow[k]);
-    }
-    for (size_t k = 0; k < P.mem_glrow.size(); k++)
-        if (P.mem_gowner[k] >= 0) resolve(P.mem_gowner[k], P.mem_glrow[k]);
     const size_t np = P.pro_ind.size();
     P.pro_slot.resize(np); P.pro_owner.resize(np); P.pro_lrow.resize(np);
     for (size_t u = 0; u < np; u++) {

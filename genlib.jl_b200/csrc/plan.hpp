@@ -18,12 +18,12 @@
 
 namespace genlib {
 
-constexpr int kPTile = 128;      // frontier columns per cross-kernel tile (and slot-range alignment)
-constexpr int kFTile = 32;       // families per cross-kernel tile
-constexpr int kMTile = 128;      // member columns per expand step (4 per lane)
+constexpr int kPTile = 128;      // frontier columns per producer tile (and slot-range alignment)
+constexpr int kFTile = 32;       // couples per producer tile (upper bound)
+constexpr int kMTile = 128;      // member columns per consumer tile (4 per lane)
 constexpr int kMaxFamily = 32;   // sibships larger than this are split (bounds per-tile work)
 constexpr int kSlotLine = 32;     // column slots are allocated and recycled in lines of this many (128 B of a float row)
-constexpr int kMaxTileFam = 64;  // couples per member tile (bounds the couple tile staged by the expand kernel)
+constexpr int kMaxTileFam = 64;  // couples per member tile (bounds the couple tile staged by the layer kernel)
 
 // Which reference function's floating-point schedule the plan reproduces:
 //   phi        (compute.jl:233-304)  layers by height above the probands, the higher RANK is climbed,
@@ -45,6 +45,8 @@ struct Layer {
     int32_t live_before = 0, carried = 0;
     int32_t ref_founders = 0, ref_probands = 0, ref_both = 0;
     int32_t rt_lo = 0, rt_rows = 0;   // live slots lie in [rt_lo, rt_lo + rt_rows), both multiples of kPTile
+    int32_t n_live_tiles = 0;         // tiles of kPTile slots in that range that hold a live individual
+    size_t tile_off = 0;              // into tile_map (rt_rows / kPTile entries)
     int32_t nf_pad = 0;               // row stride of the transposed cross block (families, multiple of 32)
     int32_t n_mtiles = 0;
     int32_t max_tile_fam = 0;         // most couples in one member tile
@@ -61,7 +63,6 @@ struct Plan {
     int64_t capacity = 0;             // W, multiple of kPTile; also the leading dimension
     int64_t row_updates = 0;
     double alg_elems = 0;
-    size_t rt_elems_max = 0;          // max over layers of rt_rows * nf_pad
     std::vector<Layer> layers;
     std::vector<int32_t> pro_ind, pro_slot;
     // concatenated per-layer arrays
@@ -69,11 +70,9 @@ struct Plan {
     std::vector<int32_t> mem_rank;                     // sparse_phi schedules: the members' pedigree ranks (mem_ind = queue position)
     std::vector<int32_t> fam_pf, fam_pm, fam_start;    // parents as slots (-1 = none)
     std::vector<uint8_t> flags;
-    std::vector<int32_t> fam_minrank, fam_maxrank;     // rank range of a couple's members
-    std::vector<int32_t> mtile_minrank, mtile_maxrank; // rank range of a member tile
+    std::vector<int32_t> tile_map;                     // per tile of a layer's live range: its index among the live tiles (-1: hole)
     std::vector<int32_t> mtile_fam0, mtile_nfam;       // couple range of a member tile
     std::vector<int32_t> mtile_m0, mtile_cnt;          // first member and size of a member tile
-    size_t v_elems_max = 0;           // max over layers of n_fam * nf_pad (world == 1)
     // ---- row sharding (world ranks; world == 1 puts everything on rank 0) ----
     // Couples are numbered rank-major inside a layer: rank g owns couples
     // [fam_base[g], fam_base[g+1]) and members [mem_base[g], mem_base[g+1]), and holds the
@@ -86,27 +85,21 @@ struct Plan {
     std::vector<int32_t> live_lrow;
     std::vector<int8_t> pro_owner;
     std::vector<int32_t> pro_lrow;
-    std::vector<int8_t> mem_gowner;                    // parallel to mem_ind: rank holding a guest copy of the row (-1 none)
-    std::vector<int32_t> mem_glrow;                    //                      and its row there
-    std::vector<int64_t> rows_cap;                     // per rank: home rows
-    std::vector<int32_t> guest_cap;                    // per rank: guest rows per bank (two banks behind the home rows)
-    std::vector<size_t> rank_rt_elems, rank_v_elems;   // per rank: max rt_rows*nfo_pad, max nf_own*nf_pad
+    std::vector<int64_t> rows_cap;                     // per rank: rows of the frontier it holds
 
     // Every array above, for reset(): the storage of a destroyed plan is handed to the next
     // genlib_plan_create, because first-touch page faults on a few hundred MB of fresh vectors
     // cost more than the planning itself.
     template <class F> void each_array(F &&f) {
         f(layers); f(pro_ind); f(pro_slot); f(mem_ind); f(mem_rank); f(mem_slot); f(mem_fam); f(fam_pf); f(fam_pm);
-        f(fam_start); f(flags); f(fam_minrank); f(fam_maxrank); f(mtile_minrank); f(mtile_maxrank);
+        f(fam_start); f(flags); f(tile_map);
         f(mtile_fam0); f(mtile_nfam); f(mtile_m0); f(mtile_cnt); f(fam_base); f(mem_base); f(mem_lrow);
         f(fam_pf_owner); f(fam_pm_owner); f(fam_pf_lrow); f(fam_pm_lrow); f(live_owner); f(live_lrow);
-        f(pro_owner); f(pro_lrow); f(mem_gowner); f(mem_glrow); f(rows_cap); f(guest_cap);
-        f(rank_rt_elems); f(rank_v_elems);
+        f(pro_owner); f(pro_lrow); f(rows_cap);
     }
     void reset() {                     // empty plan, capacities kept
         each_array([](auto &v) { v.clear(); });
         n = n_unique = 0; world = 1; schedule = kSchedulePhi; capacity = row_updates = 0; alg_elems = 0;
-        rt_elems_max = v_elems_max = 0;
     }
 };
 

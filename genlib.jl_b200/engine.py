@@ -80,15 +80,13 @@ class Plan:
         info = self.layer_info(layer)
         n, nf, w = info["n_new"], info["n_fam"], self.world
         out = {"fam_base": np.zeros(w + 1, np.int32), "mem_base": np.zeros(w + 1, np.int32),
-               "member_lrow": np.zeros(n, np.int32), "member_guest_owner": np.zeros(n, np.int32),
-               "member_guest_lrow": np.zeros(n, np.int32)}
+               "member_lrow": np.zeros(n, np.int32)}
         out.update({k: np.zeros(nf, np.int32) for k in ("fam_father_owner", "fam_father_lrow",
                                                         "fam_mother_owner", "fam_mother_lrow")})
         check(lib().genlib_plan_layer_shard(self._h, layer, ptr(out["fam_base"]), ptr(out["mem_base"]),
                                             ptr(out["member_lrow"]), ptr(out["fam_father_owner"]),
                                             ptr(out["fam_father_lrow"]), ptr(out["fam_mother_owner"]),
-                                            ptr(out["fam_mother_lrow"]), ptr(out["member_guest_owner"]),
-                                            ptr(out["member_guest_lrow"])))
+                                            ptr(out["fam_mother_lrow"])))
         cap = max(self.capacity, 1)
         out["live_owner"], out["live_lrow"] = np.zeros(cap, np.int32), np.zeros(cap, np.int32)
         check(lib().genlib_plan_layer_live_rows(self._h, layer, ptr(out["live_owner"]), ptr(out["live_lrow"])))

@@ -17,8 +17,9 @@ const libgenlib = Ref{String}(get(ENV, "GENLIB_CUDA_LIB", "libgenlib_cuda.so"))
 
 struct LayerInfo            # genlib_layer_info, include/genlib_cuda.h
     n_new::Int32; n_fam::Int32; live_before::Int32; carried::Int32
-    ref_founders::Int32; ref_probands::Int32; ref_both::Int32; reserved::Int32
-    alg_elems::Float64; ms_cross::Float64; ms_couple::Float64; ms_expand::Float64; ms_wait::Float64
+    ref_founders::Int32; ref_probands::Int32; ref_both::Int32; strip_width::Int32
+    alg_elems::Float64; ms_layer::Float64; ms_wait::Float64
+    dram_read_bytes::Float64; dram_write_bytes::Float64; l2_bytes::Float64; nvlink_bytes::Float64
 end
 
 struct Stats                # genlib_stats

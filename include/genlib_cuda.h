@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GENLIB_ABI_VERSION 1
+#define GENLIB_ABI_VERSION 2
 
 /* status codes (0 = ok) */
 #define GENLIB_OK 0
@@ -61,12 +61,15 @@ typedef struct genlib_layer_info {
     int32_t ref_founders; /* |cut[k]|   -- "founders" of the verbose line, compute.jl:258 */
     int32_t ref_probands; /* |cut[k+1]| -- "probands", compute.jl:259                     */
     int32_t ref_both;     /* |cut[k] n cut[k+1]|, compute.jl:260                          */
-    int32_t reserved;
+    int32_t strip_width;  /* engine: couples per strip of the layer kernel               */
     double alg_elems;     /* 4*n*L + 3*n^2; bytes = elems * sizeof(storage) */
-    double ms_cross;      /* device time of cross_kernel (when timed)                    */
-    double ms_couple;     /* ... of couple_kernel                                        */
-    double ms_expand;     /* ... of expand_kernel                                        */
-    double ms_wait;       /* ... spent in the two inter-GPU barriers (multi-GPU)         */
+    double ms_layer;      /* engine: device time of the layer kernel (when timed)        */
+    double ms_wait;       /* ... spent in the inter-GPU barrier that ends the layer      */
+    /* engine, this rank: the traffic the step cannot avoid, from the plan */
+    double dram_read_bytes;  /* parent rows of own couples over the live columns, once   */
+    double dram_write_bytes; /* own members' rows and their columns in carried rows, once */
+    double l2_bytes;         /* strip buffers written and read back (L2-resident scratch) */
+    double nvlink_bytes;     /* parent rows / carried rows that live on another GPU      */
 } genlib_layer_info;
 
 typedef struct genlib_stats {
@@ -174,13 +177,10 @@ int genlib_plan_layer_ranks(const genlib_plan *plan, int32_t layer, int32_t *mem
 /* Row sharding of a layer (plans built with world > 1; world == 1 puts everything on rank 0):
  * fam_base / mem_base have world + 1 entries (rank g owns couples [fam_base[g], fam_base[g+1])
  * and members [mem_base[g], mem_base[g+1])); member_lrow is the local row of each member on
- * its owner; the parents of each couple are given as (rank, local row) of the copy to read,
- * -1 = none; member_guest_* name the rank and row of the guest copy a member's row is also
- * written to while it is computed (-1 = none). */
+ * its owner; the parents of each couple are given as (rank, local row), -1 = none. */
 int genlib_plan_layer_shard(const genlib_plan *plan, int32_t layer, int32_t *fam_base, int32_t *mem_base,
                             int32_t *member_lrow, int32_t *fam_father_owner, int32_t *fam_father_lrow,
-                            int32_t *fam_mother_owner, int32_t *fam_mother_lrow, int32_t *member_guest_owner,
-                            int32_t *member_guest_lrow);
+                            int32_t *fam_mother_owner, int32_t *fam_mother_lrow);
 /* Owner rank and local row of whoever is live in each slot before the step (capacity entries). */
 int genlib_plan_layer_live_rows(const genlib_plan *plan, int32_t layer, int32_t *live_owner, int32_t *live_lrow);
 /* Local rows rank `rank` needs. */
@@ -204,9 +204,9 @@ int genlib_phi(int32_t n, const int32_t *father, const int32_t *mother, int32_t 
 int genlib_engine_create(const genlib_plan *plan, int numerics, int device, genlib_engine **out);
 void genlib_engine_destroy(genlib_engine *eng);
 /* Run every layer on the engine's stream and wait.  time_layers != 0 brackets
- * every kernel with CUDA events (per-layer ms in genlib_engine_layer_info). */
+ * every layer with CUDA events (per-layer ms in genlib_engine_layer_info). */
 int genlib_engine_run(genlib_engine *eng, int time_layers);
-int genlib_engine_layer_info(const genlib_engine *eng, int32_t layer, genlib_layer_info *out);
+int genlib_engine_layer_info(genlib_engine *eng, int32_t layer, genlib_layer_info *out);
 int genlib_engine_stats(const genlib_engine *eng, genlib_stats *out);
 /* Gather proband rows/columns and stream them to host memory.  A sharded engine writes only
  * the rows of the probands it owns, compactly: n_own x n_unique elements, in the order of

@@ -46,6 +46,8 @@ def lib():
                                        C.c_void_p, C.c_int]
         L.oracle_sparse_phi_ranks.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                               C.c_int, C.c_void_p, C.POINTER(C.c_int), C.c_void_p, C.c_void_p]
+        L.oracle_row_updates.restype = C.c_int64
+        L.oracle_row_updates.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.oracle_set_time_budget.argtypes = [C.c_double]
         L.oracle_phi_mean.restype = C.c_double
         L.oracle_phi_mean.argtypes = [C.c_void_p, C.c_int]
@@ -195,6 +197,14 @@ def bounded_steps(father, mother, pro_ranks, seconds: float, nthreads: int = 0):
     if rc < 0:
         raise KeyError(f"oracle_phi_ranks status {rc}")
     return steps[:rc].copy()
+
+
+def row_updates(father, mother, pro_ranks) -> int:
+    """Individuals born over a complete gen.phi call (the benchmark's unit of work)."""
+    father = np.ascontiguousarray(father, np.int32)
+    mother = np.ascontiguousarray(mother, np.int32)
+    pro = np.ascontiguousarray(pro_ranks, np.int32)
+    return int(lib().oracle_row_updates(len(father), _p(father), _p(mother), len(pro), _p(pro)))
 
 
 def phi_mean(phi: np.ndarray) -> float:

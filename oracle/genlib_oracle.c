@@ -477,6 +477,28 @@ int oracle_phi_ranks(int n, const int32_t *father, const int32_t *mother, int n_
     return (max_steps >= 0 || g_time_budget > 0) ? steps_done : S - 1;
 }
 
+/* Row-updates of a complete gen.phi call = individuals that enter a cut after the first one
+ * (compute.jl:243-251), without computing any kinship. */
+int64_t oracle_row_updates(int n, const int32_t *father, const int32_t *mother, int n_pro, const int32_t *pro_rank) {
+    ivec pro = {0};
+    for (int t = 0; t < n_pro; t++) {
+        if (pro_rank[t] < 0 || pro_rank[t] >= n) { free(pro.v); return -ORACLE_EKEY; }
+        iv_push(&pro, pro_rank[t]);
+    }
+    cuts_t c = build_cuts(n, father, mother, &pro);
+    free(pro.v);
+    uint8_t *seen = calloc((size_t)n + 1, 1);
+    int64_t rows = 0;
+    for (int k = 0; k < c.S; k++)
+        for (int t = 0; t < c.cut[k].n; t++) {
+            const int x = c.cut[k].v[t];
+            if (!seen[x]) { seen[x] = 1; if (k > 0) rows++; }
+        }
+    free(seen);
+    cuts_free(&c);
+    return rows;
+}
+
 /* gen.phi(ped, probandIDs): IDs -> ranks (KeyError on unknown ID, create.jl:70
  * reached from compute.jl:196), then the core above. */
 int oracle_phi(const oracle_ped *p, int n_pro, const int64_t *proband_ids, float *out,

@@ -1,6 +1,6 @@
 """One rank of the world_size-2 CPU test (gloo): each process simulates ONLY its own rank of the
 row-sharded schedule with NumPy and exchanges what the GPU kernels move through NVLink peer
-memory (frontier rows, carried mirror stores, couple-matrix pushes) through torch.distributed."""
+memory (parent rows read from peers, mirror stores into carried rows) through torch.distributed."""
 import os
 import sys
 
@@ -53,23 +53,12 @@ def run(rank: int, world: int, port: int, out_path: str):
         for t in range(plan.n_layers):
             if not R.begin(t):
                 continue
-            sync_rows()
-            R.cross(rank)
-            writes = [None] * world            # row writes + mirror stores into carried rows (maybe remote)
+            sync_rows()                        # parent rows (and the diagonal's entry) may live on a peer
+            R.step(rank)
+            writes = [None] * world            # mirror stores into carried rows (maybe remote)
             dist.all_gather_object(writes, R.writes)
             R.writes = [w for ws in writes for w in ws]
-            R.apply_cross_writes(only={rank})
-            R.couple(rank)
-            pushes = [None] * world            # couple-matrix rows pushed to their owners
-            dist.all_gather_object(pushes, R.pushes)
-            R.pushes = [p for ps in pushes for p in ps]
-            R.apply_pushes(only={rank})
-            sync_rows()                        # diagonal reads a parent row that may be remote
-            R.expand(rank)
-            gw = [None] * world                # guest copies of new rows, pushed to the rank that needs them
-            dist.all_gather_object(gw, R.guest_writes)
-            R.guest_writes = [x for xs in gw for x in xs]
-            R.apply_guest_writes(only={rank})
+            R.apply_writes(only={rank})
             dist.barrier()
         parts = [None] * world
         dist.all_gather_object(parts, R.result_rows(rank))

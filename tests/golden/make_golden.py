@@ -6,8 +6,10 @@
 Each workload is built by the oracle's own loader (no product library in the process), run
 through the full reference algorithm (oracle/genlib_oracle.c = src/compute.jl:233-304 restated),
 and the sha256 of the raw n x n Float32 matrix goes to tests/golden/<name>_full.sha256 together
-with sum / trace (float64 accumulation) and the run time.  bench.py prints the sha256 of what the
+with `rows_sha256` (sha256 of the concatenated per-row sha256 digests: what ranks that hold row
+shards can compute without gathering the matrix), sum / trace (float64 accumulation) and the run time.  bench.py prints the sha256 of what the
 GPU fetched (`output_sha256`) next to the golden one; tests/test_gpu_parity.py compares them."""
+import hashlib
 import json
 import os
 import sys
@@ -37,7 +39,8 @@ def main():
         t0 = time.time()
         phi, steps = ob.phi_ranks(father, mother, ranks)
         dt = time.time() - t0
-        rec = {"sha256": ob.matrix_sha256(phi), "workload": desc, "n": int(phi.shape[0]),
+        rows_sha = hashlib.sha256(b"".join(hashlib.sha256(np.ascontiguousarray(r).tobytes()).digest() for r in phi)).hexdigest()
+        rec = {"sha256": ob.matrix_sha256(phi), "rows_sha256": rows_sha, "workload": desc, "n": int(phi.shape[0]),
                "sum": float(phi.astype(np.float64).sum()), "trace": float(np.trace(phi.astype(np.float64))),
                "row_updates": int(steps[:, 4].sum()), "oracle_seconds": dt, "oracle_threads": ob.num_threads(),
                "source": "oracle/genlib_oracle.c oracle_phi_ranks (C restatement of src/compute.jl:233-304)"}

@@ -86,14 +86,15 @@ def replay(plan, numerics: str = "reference", check_poison: bool = True, on_laye
 
 
 class ShardedReplay:
-    """Row-sharded schedule, rank by rank (NumPy, fp64 arithmetic in the kernels' grouping).
+    """The row-sharded schedule as the layer kernel (csrc/layer_kernel.cuh) executes it, rank by rank.
 
-    `ranks` = the ranks this object simulates (all of them by default).  A[g] is rank g's
-    rows_cap[g] x W frontier block, NaN where nothing was written.  Phases of one layer, in the
-    order the engine launches them: cross(g) -> apply_cross_writes -> couple(g) -> apply_pushes
-    -> expand(g).  Remote accesses go through self.A / self.push, so a multi-process test only
-    has to exchange those between phases.
-    """
+    `A[g]` is rank g's rows_cap[g] x W frontier block, NaN where nothing was written.  One layer on
+    rank g (`step`): the parent rows of g's own couples are read over the live columns (a remote
+    row is a peer read) -- that is the strip buffer Q[p][F] = (Psi[f_F, p], Psi[m_F, p]); from it
+    come the members' rows against the carried columns, the members' columns in the carried rows
+    (a peer store when the carried row lives elsewhere: `writes`, applied by `apply_writes`) and,
+    for EVERY couple G of the layer, both groupings of the four entries of (F, G), of which the
+    ranks pick one per member pair.  Every rank writes only rows it owns, except for the mirror."""
 
     def __init__(self, plan, numerics="reference", exchange=None):
         self.plan, self.T = plan, (np.float32 if numerics == "reference" else np.float64)
@@ -112,6 +113,11 @@ class ShardedReplay:
                 + (np.asarray(y, np.float64).astype(np.float32) * h).astype(np.float64)
         return 0.5 * np.asarray(x, np.float64) + 0.5 * np.asarray(y, np.float64)
 
+    def inner(self, x, y):
+        """An intermediate kinship: unrounded Float64 in phi, a stored Float32 in sparse_phi."""
+        v = self.half_sum(x, y)
+        return v.astype(np.float32).astype(np.float64) if self.sparse else v
+
     def note(self, src, dst, nbytes):
         if self.exchange is not None and src != dst and nbytes:
             self.exchange(self.t, int(src), int(dst), int(nbytes))
@@ -124,102 +130,67 @@ class ShardedReplay:
         self.n, self.nf = self.info["n_new"], self.info["n_fam"]
         self.live = np.nonzero(a["live_flags"] & 1)[0]
         self.carried = np.nonzero(a["live_flags"] & 2)[0]
-        self.pos_in_live = np.full(self.W, -1)
+        self.pos_in_live = np.full(self.W + 1, len(self.live))          # slot -> column of the strip buffer (-1 -> zero column)
         self.pos_in_live[self.live] = np.arange(len(self.live))
         fb, mb = sh["fam_base"], sh["mem_base"]
         assert fb[0] == 0 and fb[-1] == self.nf and mb[-1] == self.n and np.all(np.diff(a["member_fam"]) >= 0)
-        self.owner_of_fam = np.repeat(np.arange(self.G), np.diff(fb))
-        self.Rt, self.writes, self.pushes, self.guest_writes = {}, [], [], []
-        self.Vrow = {g: np.full((fb[g + 1] - fb[g], self.nf), np.nan) for g in range(self.G)}
-        self.Vt = {g: np.full((fb[g + 1] - fb[g], self.nf), np.nan) for g in range(self.G)}
+        self.writes = []
         return self.n > 0
 
     def row(self, owner, lr, cols, reader):
         self.note(owner, reader, len(cols) * self.es)
         return self.A[owner][lr, cols].astype(np.float64)
 
-    def cross(self, g):
+    def step(self, g):
         a, sh, live = self.arr, self.sh, self.live
         F0, F1 = sh["fam_base"][g], sh["fam_base"][g + 1]
-        R = np.zeros((F1 - F0, len(live)))
+        M0, M1 = sh["mem_base"][g], sh["mem_base"][g + 1]
+        if F1 == F0:
+            return
+        # ---- producer: Q[p][F] = (father row, mother row) of the own couples, raw stored values ----
+        X, Y = np.zeros((F1 - F0, len(live) + 1)), np.zeros((F1 - F0, len(live) + 1))   # last column: "no such parent"
         for F in range(F0, F1):
             fo, mo = sh["fam_father_owner"][F], sh["fam_mother_owner"][F]
-            x = self.row(fo, sh["fam_father_lrow"][F], live, g) if fo >= 0 else 0.0
-            y = self.row(mo, sh["fam_mother_lrow"][F], live, g) if mo >= 0 else 0.0
-            R[F - F0] = self.half_sum(x, y)                     # one rounding (1/2 y is exact)
+            if fo >= 0:
+                X[F - F0, :-1] = self.row(fo, sh["fam_father_lrow"][F], live, g)
+            if mo >= 0:
+                Y[F - F0, :-1] = self.row(mo, sh["fam_mother_lrow"][F], live, g)
         if len(live):
-            assert not np.isnan(R).any(), f"layer {self.t} rank {g}: cross block read an unwritten entry"
-        self.Rt[g] = R
-        M0, M1 = sh["mem_base"][g], sh["mem_base"][g + 1]
-        if len(self.carried) and M1 > M0:                       # rows/columns new x carried, rounded once
-            blk = R[a["member_fam"][M0:M1] - F0][:, self.pos_in_live[self.carried]].astype(self.T)
-            self.writes.append((g, sh["member_lrow"][M0:M1], self.carried, blk))
-            for k in range(M0, M1):                              # the same row segment into the guest copy
-                go = sh["member_guest_owner"][k]
-                if go >= 0:
-                    self.writes.append((go, np.array([sh["member_guest_lrow"][k]]), self.carried, blk[k - M0][None, :]))
-                    self.note(g, go, len(self.carried) * self.es)
-            for k, c in enumerate(self.carried):                # mirror into the carried rows (peer store)
+            assert not np.isnan(X).any() and not np.isnan(Y).any(), f"layer {self.t} rank {g}: a parent row has an unwritten live entry"
+        fam, ind = a["member_fam"], a["member_ind"]
+        fl = fam[M0:M1] - F0
+        if len(self.carried) and M1 > M0:                       # new x carried, rounded once; and its mirror
+            cpos = self.pos_in_live[self.carried]
+            blk = self.half_sum(X[:, cpos], Y[:, cpos])[fl].astype(self.T)
+            self.A[g][np.ix_(sh["member_lrow"][M0:M1], self.carried)] = blk
+            for k, c in enumerate(self.carried):                # a peer store when the carried row lives elsewhere
                 co, cl = sh["live_owner"][c], sh["live_lrow"][c]
                 self.writes.append((co, np.array([cl]), a["member_slot"][M0:M1], blk[:, k][None, :]))
                 self.note(g, co, (M1 - M0) * self.es)
-
-    def apply_cross_writes(self, only=None):
-        for g, rows_, cols_, blk in self.writes:
-            if only is None or g in only:
-                self.A[g][np.ix_(rows_, cols_)] = blk
-
-    def couple(self, g):
-        a, sh = self.arr, self.sh
-        G0, G1 = sh["fam_base"][g], sh["fam_base"][g + 1]
-        if G1 == G0:
-            return
-        Rg, pf, pm = self.Rt[g], a["fam_father_slot"], a["fam_mother_slot"]
-        zero = np.zeros(G1 - G0)
-        for F in range(self.nf):
-            x = Rg[:, self.pos_in_live[pf[F]]] if pf[F] >= 0 else zero
-            y = Rg[:, self.pos_in_live[pm[F]]] if pm[F] >= 0 else zero
-            v = self.half_sum(x, y)                             # V[F, G0:G1] (sparse_phi: from the rounded cross values)
-            o = self.owner_of_fam[F]
-            self.pushes.append((o, F - sh["fam_base"][o], G0, G1, v))
-            self.Vt[g][:, F] = v
-            self.note(g, o, (G1 - G0) * self.es)
-
-    def apply_pushes(self, only=None):
-        for o, fl, G0, G1, v in self.pushes:
-            if only is None or o in only:
-                self.Vrow[o][fl, G0:G1] = v
-
-    def expand(self, g):
-        a, sh = self.arr, self.sh
-        M0, M1 = sh["mem_base"][g], sh["mem_base"][g + 1]
+        # ---- consumer: for every couple G of the layer, both groupings of the four entries of (F, G) ----
+        pf, pm = a["fam_father_slot"], a["fam_mother_slot"]
+        gf, gm = self.pos_in_live[pf], self.pos_in_live[pm]     # slot -1 -> the zero column
+        ax, ay, cx, cy = X[:, gf], Y[:, gf], X[:, gm], Y[:, gm]
+        Vf = self.half_sum(self.inner(ax, cx), self.inner(ay, cy)).astype(self.T)   # the strip couple's member is climbed first
+        Vg = self.half_sum(self.inner(ax, ay), self.inner(cx, cy)).astype(self.T)   # the tile couple's member is climbed first
         if M1 == M0:
             return
-        fam, ind, pf, pm = a["member_fam"], a["member_ind"], a["fam_father_slot"], a["fam_mother_slot"]
-        fl = fam[M0:M1] - sh["fam_base"][g]
         hi = ind[M0:M1, None] > ind[None, :]
-        blk = np.where(hi, self.Vrow[g][fl][:, fam], self.Vt[g][fl][:, fam])
+        blk = np.where(hi, Vf[fl][:, fam], Vg[fl][:, fam])
         if getattr(self.plan, "schedule", "phi") == "sparse_phi":       # misfiled kinships read as 0 (compute.jl:393)
             rk = a["member_rank"]
-            blk = np.where(hi == (rk[M0:M1, None] > rk[None, :]), blk, 0.0)
+            blk = np.where(hi == (rk[M0:M1, None] > rk[None, :]), blk, 0)
         for q in range(M0, M1):                                 # diagonal: 1/2 + 1/2 Psi[father, mother]
             F, d = fam[q], 0.5
             if pf[F] >= 0 and pm[F] >= 0:
                 d = float(self.half_sum(self.row(sh["fam_father_owner"][F], sh["fam_father_lrow"][F], [pm[F]], g)[0], 1.0))
-            blk[q - M0, q] = d
-        assert not np.isnan(blk).any(), f"layer {self.t} rank {g}: expand read an unwritten couple entry"
-        self.A[g][np.ix_(sh["member_lrow"][M0:M1], a["member_slot"])] = blk.astype(self.T)
-        for q in range(M0, M1):                                 # guest copies on other ranks (peer stores)
-            go = sh["member_guest_owner"][q]
-            if go >= 0:
-                self.guest_writes.append((go, int(sh["member_guest_lrow"][q]), a["member_slot"], blk[q - M0].astype(self.T)))
-                self.note(g, go, self.n * self.es)
+            blk[q - M0, q] = self.T(d)
+        self.A[g][np.ix_(sh["member_lrow"][M0:M1], a["member_slot"])] = blk
 
-    def apply_guest_writes(self, only=None):
-        for go, gl, cols, vals in self.guest_writes:
-            if only is None or go in only:
-                self.A[go][gl, cols] = vals
-        self.guest_writes = []
+    def apply_writes(self, only=None):
+        for g, rows_, cols_, blk in self.writes:
+            if only is None or g in only:
+                self.A[g][np.ix_(rows_, cols_)] = blk
 
     def result_rows(self, g):
         ps = self.plan.proband_slots()
@@ -236,14 +207,8 @@ def replay_sharded(plan, numerics: str = "reference", exchange=None) -> np.ndarr
         if not R.begin(t):
             continue
         for g in range(R.G):
-            R.cross(g)
-        R.apply_cross_writes()
-        for g in range(R.G):
-            R.couple(g)
-        R.apply_pushes()
-        for g in range(R.G):
-            R.expand(g)
-        R.apply_guest_writes()
+            R.step(g)
+        R.apply_writes()
     n = plan.n_unique
     out = np.zeros((n, n), R.T)
     for g in range(R.G):

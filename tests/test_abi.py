@@ -24,12 +24,12 @@ def test_header_and_library_agree(gen):
     L = C.CDLL(gen.LIB_PATH)
     for n in names:
         assert hasattr(L, n), f"{n} not exported"
-    assert gen.lib().genlib_version() == 1
+    assert gen.lib().genlib_version() == 2
 
 
 def test_layer_info_struct_layout(gen):
     from genlib_jl_b200 import _lib
-    assert C.sizeof(_lib.LayerInfo) == 72 and C.sizeof(_lib.Stats) == 96
+    assert C.sizeof(_lib.LayerInfo) == 88 and C.sizeof(_lib.Stats) == 96
 
 
 def test_no_cpu_fallback(gen):

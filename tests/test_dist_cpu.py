@@ -52,19 +52,6 @@ def test_sharded_replay_sparse_phi_schedule(gen, ob, seed):
         assert np.array_equal(replay_sharded(plan), want)
 
 
-@pytest.mark.parametrize("guests", ["0", "1"])
-def test_guest_rows_replay(gen, ob, guests, monkeypatch):
-    """GENLIB_GUESTS=1: a new row is also written to the rank that will read it as a remote parent."""
-    monkeypatch.setenv("GENLIB_GUESTS", guests)
-    s = gen.synth.generate(3000, 8, 120, alpha=0.05, demes=2, migration=0.1, overlap=2, seed=4)
-    ped = gen.genealogy(s.as_columns())
-    want = ob.OraclePedigree.from_arrays(s.ind, s.father, s.mother, s.sex).phi(s.probands)
-    plan = gen.Plan(ped.father, ped.mother, ped.rank_of(s.probands), world=4)
-    n_guest = sum(int((plan.layer_shard(t)["member_guest_owner"] >= 0).sum()) for t in range(plan.n_layers))
-    assert (n_guest > 0) == (guests == "1")
-    assert np.array_equal(replay_sharded(plan), want)
-
-
 def test_shard_invariants(gen):
     s = gen.synth.generate(6000, 10, 300, alpha=0.05, demes=2, migration=0.1, overlap=2, seed=3)
     ped = gen.genealogy(s.as_columns())
@@ -92,10 +79,6 @@ def test_shard_invariants(gen):
                 assert (int(o), int(r)) not in live_rows
                 live_rows.add((int(o), int(r)))
                 used[o].add(int(r))
-            # a guest copy lives on another rank, behind that rank's home rows
-            for o, go, gl in zip(arr["member_owner"], sh["member_guest_owner"], sh["member_guest_lrow"]):
-                assert go == -1 or (go != o and 0 <= gl < rows[go])
-        # home rows come first; the two banks of guest rows sit behind them
         assert all((max(u) + 1 if u else 1) <= r for u, r in zip(used, rows))
         owner, lrow = plan.proband_rows()
         assert len(owner) == plan.n_unique and (owner >= 0).all() and (owner < world).all()

@@ -171,7 +171,8 @@ def test_out_dtype_and_mean(gen):
     assert abs(mean - want) < 1e-15
     assert abs(mean - 0.0011437357710109676) < 1e-15
     infos = [eng.layer_info(t) for t in range(plan.n_layers)]
-    assert all(i["ms_expand"] > 0 for i in infos)
+    assert all(i["ms_layer"] > 0 and i["dram_write_bytes"] > 0 and i["strip_width"] > 0 for i in infos)
+    assert all(i["dram_read_bytes"] > 0 and i["l2_bytes"] > 0 for i in infos[1:]) and infos[0]["dram_read_bytes"] == 0
     eng.close()
 
 
