@@ -192,8 +192,8 @@ struct genlib_engine {
     BarrierTable bars{};
     unsigned epoch = 0;
     long long barrier_timeout = (long long)20e9;   // cycles an inter-GPU barrier may wait (GENLIB_BARRIER_TIMEOUT_S)
-    DevBuf<int32_t> mem_ind, mem_slot, mem_fam, mem_lrow, fam_pf, fam_pm, fam_pf_lrow, fam_pm_lrow, fam_start,
-        mt_fam0, mt_nfam, mt_m0, mt_cnt, pro_slot, own_pro_row, live_lrow, tile_map;
+    DevBuf<int32_t> mem_ind, mem_slot, mem_fam, mem_lrow, fam_pf, fam_pm, fam_qf, fam_qm, fam_pf_lrow, fam_pm_lrow, fam_start,
+        mt_fam0, mt_nfam, mt_m0, mt_cnt, pro_slot, own_pro_row, live_lrow, tile_map, live_tiles;
     DevBuf<int8_t> fam_pf_owner, fam_pm_owner, live_owner;
     DevBuf<int32_t> mem_rank;
     DevBuf<uint8_t> flags;
@@ -226,8 +226,8 @@ void fill_info(const Layer &L, genlib_layer_info *o) {
 size_t pad256(size_t b) { return (std::max<size_t>(b, 1) + 255) / 256 * 256; }
 
 size_t plan_index_bytes(const Plan &P) {
-    return (P.mem_ind.size() * 4 + P.mem_rank.size() + P.fam_pf.size() * 4 + P.fam_start.size() + P.mtile_fam0.size() * 4 +
-            P.pro_slot.size() * 2 + P.live_lrow.size() + P.tile_map.size()) * sizeof(int32_t) + P.fam_pf.size() * 2 + P.live_owner.size() + P.flags.size();
+    return (P.mem_ind.size() * 4 + P.mem_rank.size() + P.fam_pf.size() * 6 + P.fam_start.size() + P.mtile_fam0.size() * 4 +
+            P.pro_slot.size() * 2 + P.live_lrow.size() + P.tile_map.size() + P.live_tiles.size()) * sizeof(int32_t) + P.fam_pf.size() * 2 + P.live_owner.size() + P.flags.size();
 }
 
 // Arena layout of rank g.  The first two regions are what peers address (barrier flags, frontier rows).
@@ -240,8 +240,11 @@ size_t off_A() { return kFlagBytes; }
 // The strip buffers live in the part of L2 that can be set aside for persisting lines (79 of 126 MB
 // on B200, profiles/r02/l2strip.txt); what the buffers of a layer may take of it:
 constexpr size_t kStripBudget = (size_t)72 << 20;
-constexpr int kCtasPerSm = 2;
-constexpr size_t kUnitBytes = (size_t)256 << 10;          // work handed out per atomic: ~6 us of one SM's bandwidth
+
+int env_int(const char *name, int dflt) {
+    const char *s = std::getenv(name);
+    return s && *s ? std::atoi(s) : dflt;
+}
 
 LayerLaunch shape_layer(const Plan &P, int t, int rank, size_t es, int sm_count) {
     const Layer &L = P.layers[t];
@@ -250,48 +253,42 @@ LayerLaunch shape_layer(const Plan &P, int t, int rank, size_t es, int sm_count)
     const int32_t *fb = P.fam_base.data() + L.base_off, *mb = P.mem_base.data() + L.base_off;
     const int64_t own_nf = fb[rank + 1] - fb[rank], own_nm = mb[rank + 1] - mb[rank];
     if (L.n_new == 0 || own_nf <= 0) return out;
-    const int64_t rt_rows = L.live_before > 0 ? L.rt_rows : 0, ptiles = rt_rows / kPTile;
-    const int64_t q_rows = L.live_before > 0 ? (int64_t)L.n_live_tiles * kPTile : 0;     // rows of a strip buffer
+    const bool live = L.live_before > 0;
+    const int64_t rt_rows = live ? L.rt_rows : 0;
+    const int64_t q_rows = live ? (int64_t)L.n_live_tiles * kPTile : 0;     // rows of a strip buffer
     const size_t pair = 2 * es;
     // strip width: the widest one whose buffers fit the persisting part of L2 three times (and whose
-    // staged tile fits shared memory: 128 parent rows x sw pairs <= 64 KB)
-    int sw = es == 4 ? kMaxStrip : kMaxStrip / 2;
+    // staged tile fits shared memory: 128 parent-row segments of sw pairs <= 64 KB)
+    int sw = std::min(es == 4 ? kMaxStrip : kMaxStrip / 2, std::max(8, env_int("GENLIB_MAX_SW", kMaxStrip)));
     while (sw > 8 && (size_t)q_rows * sw * pair * 3 > kStripBudget) sw >>= 1;
     const size_t strip_bytes = std::max<size_t>((size_t)q_rows * sw * pair, 256);
     s.sw = sw;
     s.ft = std::min(sw, es == 4 ? 32 : 16);
-    s.nbuf = (int)std::max<size_t>(2, std::min<size_t>(6, kStripBudget / strip_bytes));
+    s.nbuf = (int)std::max<size_t>(2, std::min<size_t>((size_t)std::max(2, env_int("GENLIB_MAX_NBUF", 6)), kStripBudget / strip_bytes));
     s.n_strips = (int)((own_nf + sw - 1) / sw);
     s.qstride = (int64_t)(strip_bytes / pair);
-    const int grid_max = kCtasPerSm * sm_count;
+    // producer items: 2 ft parent rows x one live tile; consumer items: member tiles, then blocks of carried rows
+    s.n_pitems = live ? (sw / s.ft) * L.n_live_tiles : 0;
     const double rows_per_strip = (double)own_nm / (double)own_nf * sw;        // members of a strip
-    // producer units: 2 ft parent rows x pchunk column tiles
-    if (ptiles > 0) {
-        int64_t pc = (int64_t)(kUnitBytes / ((size_t)2 * s.ft * kPTile * es));
-        pc = std::min<int64_t>(pc, ptiles * (sw / s.ft) * s.n_strips / (2 * grid_max));      // but at least two waves of units
-        s.pchunk = (int)std::max<int64_t>(std::min<int64_t>(2, ptiles), std::min<int64_t>(pc, kMaxPChunk));
-        s.n_pchunks = (int)((ptiles + s.pchunk - 1) / s.pchunk);
-    } else { s.pchunk = 1; s.n_pchunks = 0; }
-    // consumer units: the strip's member rows x gt member tiles
-    {
-        int64_t gt = (int64_t)((double)kUnitBytes / std::max(1.0, rows_per_strip * kMTile * es));
-        gt = std::min<int64_t>(gt, (int64_t)L.n_mtiles * s.n_strips / (2 * grid_max));
-        s.gt = (int)std::max<int64_t>(1, std::min<int64_t>(gt, 64));
-        s.n_cunits = (L.n_mtiles + s.gt - 1) / s.gt;
+    int n_mblocks = 0;
+    s.mrows = 1;
+    if (L.carried > 0 && rt_rows > 0) {                     // ~64 KB of mirrored columns per block
+        const int64_t mr = (int64_t)(65536.0 / std::max(1.0, rows_per_strip * es));
+        s.mrows = (int)std::max<int64_t>(32, std::min<int64_t>(mr, 4096));
+        n_mblocks = (int)((rt_rows + s.mrows - 1) / s.mrows);
     }
-    // mirror units: blocks of live-range rows
-    if (L.carried > 0 && rt_rows > 0) {
-        int64_t mr = (int64_t)((double)kUnitBytes / std::max(1.0, rows_per_strip * es));
-        s.mrows = (int)std::max<int64_t>(64, std::min<int64_t>(mr, 8192));
-        s.n_munits = (int)((rt_rows + s.mrows - 1) / s.mrows);
-    } else { s.mrows = 1; s.n_munits = 0; }
+    s.n_citems = L.n_mtiles + n_mblocks;
+    // one producer and one consumer CTA per SM
+    const int per_role = std::max(1, env_int("GENLIB_CTAS_PER_ROLE", sm_count));
+    s.n_prod = std::min(per_role, s.n_pitems);
+    s.n_cons = std::min(per_role, s.n_citems);
+    s.rot_p = s.n_prod > 0 ? s.n_pitems % s.n_prod : 0;
+    s.rot_c = s.n_citems % s.n_cons;
     const size_t stage = (size_t)2 * s.ft * (kPTile * es + 16);
     s.stages = (int)std::max<size_t>(2, std::min<size_t>(kMaxStages, ((size_t)100 << 10) / stage));
     out.smem = std::max((size_t)s.stages * stage, layer_consumer_bytes(sw, es));
-    const int64_t units = (int64_t)s.n_strips * ((int64_t)(sw / s.ft) * s.n_pchunks + s.n_cunits + s.n_munits);
-    s.n_units = (int32_t)std::min<int64_t>(units, INT32_MAX);
-    out.grid = (int)std::min<int64_t>(units, grid_max);
-    s.timeout_cycles = (long long)8e9;                     // ~4 s: a lost dependency becomes GENLIB_ECUDA, not a hang
+    out.grid = s.n_prod + s.n_cons;
+    s.timeout_cycles = (long long)4e9;                     // ~2 s: a lost dependency becomes GENLIB_ECUDA, not a hang
     return out;
 }
 
@@ -309,9 +306,10 @@ size_t engine_bytes(const Plan &P, int numerics, int g, int sm_count = 148) {
     size_t b = kFlagBytes + a_bytes(P, es, g) + pad256(q) + pad256(sync_ints * sizeof(int32_t));
     b += 2 * pad256(kFetchStageBytes);                                         // proband staging
     b += 4 * DevBuf<int32_t>::padded(P.mem_ind.size()) + DevBuf<int32_t>::padded(P.mem_rank.size()) +
-         4 * DevBuf<int32_t>::padded(P.fam_pf.size()) + DevBuf<int32_t>::padded(P.fam_start.size()) +
+         6 * DevBuf<int32_t>::padded(P.fam_pf.size()) + DevBuf<int32_t>::padded(P.fam_start.size()) +
          4 * DevBuf<int32_t>::padded(P.mtile_fam0.size()) + 2 * DevBuf<int32_t>::padded(P.pro_slot.size()) +
          DevBuf<int32_t>::padded(P.live_lrow.size()) + DevBuf<int32_t>::padded(P.tile_map.size()) +
+         DevBuf<int32_t>::padded(P.live_tiles.size()) +
          2 * DevBuf<int8_t>::padded(P.fam_pf.size()) +
          DevBuf<int8_t>::padded(P.live_owner.size()) + DevBuf<uint8_t>::padded(P.flags.size()) + DevBuf<double>::padded(4);
     return b;
@@ -332,6 +330,7 @@ LayerArgs layer_args(const genlib_engine &E, int t) {
     a.mem_ind = E.mem_ind.p + L.mem_off; a.mem_slot = E.mem_slot.p + L.mem_off; a.mem_fam = E.mem_fam.p + L.mem_off;
     a.mem_lrow = E.mem_lrow.p + L.mem_off;
     a.fam_pf = E.fam_pf.p + L.fam_off; a.fam_pm = E.fam_pm.p + L.fam_off;
+    a.fam_qf = E.fam_qf.p + L.fam_off; a.fam_qm = E.fam_qm.p + L.fam_off;
     a.fam_pf_owner = E.fam_pf_owner.p + L.fam_off; a.fam_pm_owner = E.fam_pm_owner.p + L.fam_off;
     a.fam_pf_lrow = E.fam_pf_lrow.p + L.fam_off; a.fam_pm_lrow = E.fam_pm_lrow.p + L.fam_off;
     a.fam_start = E.fam_start.p + L.fam_off + t;
@@ -375,6 +374,7 @@ int launch_layers(genlib_engine &E, bool timed) {
         if (ll.grid > 0) {
             ll.s.Q = E.Q;
             ll.s.sync = E.sync + ll.sync_off;
+            ll.s.live_tiles = E.live_tiles.p + L.ltile_off;
             layer_fn<<<ll.grid, kLayerThreads, ll.smem, E.stream>>>(A, ld, E.peers, a, ll.s);
             launches++;
             if (P.schedule == kScheduleSparsePhi && L.n_new > 1 && a.own_nm > 0) {   // the reference's misfiled kinships read as 0
@@ -535,12 +535,14 @@ int create_engine(const genlib_plan *plan, int numerics, int device, int rank, g
         E->mem_ind.place(cur, P.mem_ind.size()); E->mem_slot.place(cur, P.mem_slot.size()); E->mem_fam.place(cur, P.mem_fam.size());
         E->mem_lrow.place(cur, P.mem_lrow.size()); E->mem_rank.place(cur, P.mem_rank.size());
         E->fam_pf.place(cur, P.fam_pf.size()); E->fam_pm.place(cur, P.fam_pm.size());
+        E->fam_qf.place(cur, P.fam_qf.size()); E->fam_qm.place(cur, P.fam_qm.size());
         E->fam_pf_lrow.place(cur, P.fam_pf_lrow.size()); E->fam_pm_lrow.place(cur, P.fam_pm_lrow.size());
         E->fam_start.place(cur, P.fam_start.size());
         E->mt_fam0.place(cur, P.mtile_fam0.size()); E->mt_nfam.place(cur, P.mtile_nfam.size());
         E->mt_m0.place(cur, P.mtile_m0.size()); E->mt_cnt.place(cur, P.mtile_cnt.size());
         E->pro_slot.place(cur, P.pro_slot.size()); E->own_pro_row.place(cur, P.pro_slot.size());
         E->live_lrow.place(cur, P.live_lrow.size()); E->tile_map.place(cur, P.tile_map.size());
+        E->live_tiles.place(cur, P.live_tiles.size());
         E->fam_pf_owner.place(cur, P.fam_pf_owner.size()); E->fam_pm_owner.place(cur, P.fam_pm_owner.size());
         E->live_owner.place(cur, P.live_owner.size());
         E->flags.place(cur, P.flags.size()); E->acc.place(cur, 4);
@@ -579,6 +581,8 @@ int create_engine(const genlib_plan *plan, int numerics, int device, int rank, g
     CU(E->mem_rank.upload(P.mem_rank, E->stream));
     CU(E->fam_pf.upload(P.fam_pf, E->stream));
     CU(E->fam_pm.upload(P.fam_pm, E->stream));
+    CU(E->fam_qf.upload(P.fam_qf, E->stream));
+    CU(E->fam_qm.upload(P.fam_qm, E->stream));
     CU(E->fam_pf_lrow.upload(P.fam_pf_lrow, E->stream));
     CU(E->fam_pm_lrow.upload(P.fam_pm_lrow, E->stream));
     CU(E->fam_pf_owner.upload(P.fam_pf_owner, E->stream));
@@ -593,6 +597,7 @@ int create_engine(const genlib_plan *plan, int numerics, int device, int rank, g
     CU(E->live_owner.upload(P.live_owner, E->stream));
     CU(E->live_lrow.upload(P.live_lrow, E->stream));
     CU(E->tile_map.upload(P.tile_map, E->stream));
+    CU(E->live_tiles.upload(P.live_tiles, E->stream));
     CU(E->flags.upload(P.flags, E->stream));
     CU(cudaStreamSynchronize(E->stream));
     E->peers.A[rank] = E->A; E->bars.flags[rank] = E->bar_flags;

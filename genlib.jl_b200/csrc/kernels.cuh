@@ -31,6 +31,7 @@ struct LayerArgs {
     int32_t fam_base[kMaxWorld + 1];
     const int32_t *mem_ind, *mem_slot, *mem_fam, *mem_lrow;     // members: rank (or queue position), column slot, couple, local row
     const int32_t *fam_pf, *fam_pm, *fam_start;                  // couples: parent slots (-1 none), first member
+    const int32_t *fam_qf, *fam_qm;                              // couples: the parents' rows in a strip buffer (-1 none)
     const int8_t *fam_pf_owner, *fam_pm_owner, *live_owner;      // where the parents' / the live individuals' rows are
     const int32_t *fam_pf_lrow, *fam_pm_lrow, *live_lrow;
     const uint8_t *flags;                                        // per slot of the live range: kFlagLive | kFlagCarried
@@ -97,12 +98,15 @@ __device__ __forceinline__ void mbar_init(unsigned bar, int count) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+// returns false when the phase did not complete within ~2^26 polls (a lost bulk copy must not hang the device)
+__device__ __forceinline__ bool mbar_wait(unsigned bar, unsigned parity) {
     unsigned ok;
-    do {
+    for (unsigned spins = 0; spins < (1u << 26); spins++) {
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    } while (!ok);
+        if (ok) return true;
+    }
+    return false;
 }
 // global -> shared bulk copy (16-byte aligned, size a multiple of 16), completes on `bar`
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {

@@ -340,7 +340,7 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         const size_t mcap = lstart[S] + 4 * (size_t)S, fcap = lstart[S] + 4 * (size_t)world * (size_t)S;
         for (auto *v : {&P.mem_ind, &P.mem_slot, &P.mem_fam, &P.mem_lrow}) v->reserve(mcap);
         if (by_seq) P.mem_rank.reserve(mcap);
-        for (auto *v : {&P.fam_pf, &P.fam_pm, &P.fam_pf_lrow, &P.fam_pm_lrow}) v->reserve(fcap);
+        for (auto *v : {&P.fam_pf, &P.fam_pm, &P.fam_pf_lrow, &P.fam_pm_lrow, &P.fam_qf, &P.fam_qm}) v->reserve(fcap);
         P.fam_pf_owner.reserve(fcap); P.fam_pm_owner.reserve(fcap); P.fam_start.reserve(fcap + (size_t)S);
     }
     std::vector<int32_t> &live = W.live, &next_live = W.next_live;   // individuals live before the current step
@@ -478,11 +478,15 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
                 if (fl[r] == kFlagLive) slots.release(L.rt_lo + r, freed);
             // the strip buffers of the layer kernel hold the live tiles only (holes of a fragmented range cost nothing)
             L.tile_off = P.tile_map.size();
+            L.ltile_off = P.live_tiles.size();
             P.tile_map.resize(L.tile_off + (size_t)(L.rt_rows / kPTile), -1);
             for (int32_t tl = 0; tl < L.rt_rows / kPTile; tl++) {
-                bool any = false;
-                for (int32_t r = tl * kPTile; r < (tl + 1) * kPTile && !any; r++) any = fl[r] != 0;
-                if (any) P.tile_map[L.tile_off + (size_t)tl] = L.n_live_tiles++;
+                uint8_t any = 0;
+                for (int32_t r = tl * kPTile; r < (tl + 1) * kPTile; r++) any |= fl[r];
+                if (any) {
+                    P.tile_map[L.tile_off + (size_t)tl] = L.n_live_tiles++;
+                    P.live_tiles.push_back(tl | ((any & kFlagCarried) ? kTileCarried : 0));
+                }
             }
         }
 
@@ -582,18 +586,22 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         P.fam_pf.resize(L.fam_off + (size_t)nf, -1); P.fam_pm.resize(L.fam_off + (size_t)nf, -1);
         P.fam_pf_owner.resize(L.fam_off + (size_t)nf, -1); P.fam_pm_owner.resize(L.fam_off + (size_t)nf, -1);
         P.fam_pf_lrow.resize(L.fam_off + (size_t)nf, -1); P.fam_pm_lrow.resize(L.fam_off + (size_t)nf, -1);
+        P.fam_qf.resize(L.fam_off + (size_t)nf, -1); P.fam_qm.resize(L.fam_off + (size_t)nf, -1);
         for (int32_t f = 0; f < nf_real; f++) {
             const int32_t x = X[fam_first[f]], fa = father[x], mo = mother[x];
             const size_t k = L.fam_off + (size_t)newid[f];
             int32_t *ps[2] = {&P.fam_pf[k], &P.fam_pm[k]};
             int8_t *po[2] = {&P.fam_pf_owner[k], &P.fam_pm_owner[k]};
             int32_t *pl[2] = {&P.fam_pf_lrow[k], &P.fam_pm_lrow[k]};
+            int32_t *pq[2] = {&P.fam_qf[k], &P.fam_qm[k]};
             const int32_t par[2] = {fa, mo};
             for (int s = 0; s < 2; s++) {
                 const int32_t p = par[s];
-                if (p < 0) { *ps[s] = -1; *po[s] = -1; *pl[s] = -1; continue; }
+                if (p < 0) { *ps[s] = -1; *po[s] = -1; *pl[s] = -1; *pq[s] = -1; continue; }
                 const Home hp = home[p];
                 *ps[s] = hp.slot; *po[s] = hp.owner; *pl[s] = hp.lrow;
+                const int32_t rel = hp.slot - L.rt_lo;             // the parent is live: its tile is in the map
+                *pq[s] = P.tile_map[L.tile_off + (size_t)(rel / kPTile)] * kPTile + rel % kPTile;
             }
         }
         // member tiles = the column blocks the layer kernel writes at a time: at most kMTile members and at

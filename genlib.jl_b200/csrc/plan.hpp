@@ -37,6 +37,7 @@ constexpr int kMaxTileFam = 64;  // couples per member tile (bounds the couple t
 constexpr int kSchedulePhi = 0, kScheduleSparsePhi = 1, kScheduleSparsePhiSymmetric = 2;
 inline bool sparse_schedule(int s) { return s == kScheduleSparsePhi || s == kScheduleSparsePhiSymmetric; }
 
+constexpr int32_t kTileCarried = 1 << 30;   // live_tiles entry: the tile has a carried column
 constexpr uint8_t kFlagLive = 1;     // slot holds an individual that is live before the step
 constexpr uint8_t kFlagCarried = 2;  // ... and stays live after it
 
@@ -47,6 +48,7 @@ struct Layer {
     int32_t rt_lo = 0, rt_rows = 0;   // live slots lie in [rt_lo, rt_lo + rt_rows), both multiples of kPTile
     int32_t n_live_tiles = 0;         // tiles of kPTile slots in that range that hold a live individual
     size_t tile_off = 0;              // into tile_map (rt_rows / kPTile entries)
+    size_t ltile_off = 0;             // into live_tiles (n_live_tiles entries)
     int32_t nf_pad = 0;               // row stride of the transposed cross block (families, multiple of 32)
     int32_t n_mtiles = 0;
     int32_t max_tile_fam = 0;         // most couples in one member tile
@@ -69,8 +71,10 @@ struct Plan {
     std::vector<int32_t> mem_ind, mem_slot, mem_fam;   // family-major order inside a layer
     std::vector<int32_t> mem_rank;                     // sparse_phi schedules: the members' pedigree ranks (mem_ind = queue position)
     std::vector<int32_t> fam_pf, fam_pm, fam_start;    // parents as slots (-1 = none)
+    std::vector<int32_t> fam_qf, fam_qm;               // parents as rows of the layer kernel's strip buffers (-1 = none)
     std::vector<uint8_t> flags;
     std::vector<int32_t> tile_map;                     // per tile of a layer's live range: its index among the live tiles (-1: hole)
+    std::vector<int32_t> live_tiles;                   // the inverse: live tiles in order, | kTileCarried if a column is carried
     std::vector<int32_t> mtile_fam0, mtile_nfam;       // couple range of a member tile
     std::vector<int32_t> mtile_m0, mtile_cnt;          // first member and size of a member tile
     // ---- row sharding (world ranks; world == 1 puts everything on rank 0) ----
@@ -92,7 +96,8 @@ struct Plan {
     // cost more than the planning itself.
     template <class F> void each_array(F &&f) {
         f(layers); f(pro_ind); f(pro_slot); f(mem_ind); f(mem_rank); f(mem_slot); f(mem_fam); f(fam_pf); f(fam_pm);
-        f(fam_start); f(flags); f(tile_map);
+        f(fam_qf); f(fam_qm);
+        f(fam_start); f(flags); f(tile_map); f(live_tiles);
         f(mtile_fam0); f(mtile_nfam); f(mtile_m0); f(mtile_cnt); f(fam_base); f(mem_base); f(mem_lrow);
         f(fam_pf_owner); f(fam_pm_owner); f(fam_pf_lrow); f(fam_pm_lrow); f(live_owner); f(live_lrow);
         f(pro_owner); f(pro_lrow); f(rows_cap);
