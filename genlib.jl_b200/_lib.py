@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgenlib_cuda.so")
+LIB_PATH = os.environ.get("GENLIB_CUDA_LIB") or os.path.join(_HERE, "libgenlib_cuda.so")
 
 OK, EINVAL, EKEY, EORDER, ECUDA, ENOMEM, ECOMM = range(7)
 SCHEDULES = {"phi": 0, "sparse_phi": 1, "sparse_phi_symmetric": 2}

@@ -186,14 +186,17 @@ struct genlib_engine {
     size_t sync_ints = 0;
     std::vector<LayerLaunch> launch;
     bool info_ready = false;               // per-layer byte accounting filled in
+#ifdef GENLIB_PROFILE
+    long long *prof = nullptr;             // 8 cycle counters per CTA of one layer (GENLIB_PROF_LAYER)
+#endif
     unsigned *bar_flags = nullptr;
     unsigned char *fetch_stage[2] = {nullptr, nullptr};
     PeerTable peers{};
     BarrierTable bars{};
     unsigned epoch = 0;
     long long barrier_timeout = (long long)20e9;   // cycles an inter-GPU barrier may wait (GENLIB_BARRIER_TIMEOUT_S)
-    DevBuf<int32_t> mem_ind, mem_slot, mem_fam, mem_lrow, fam_pf, fam_pm, fam_qf, fam_qm, fam_pf_lrow, fam_pm_lrow, fam_start,
-        mt_fam0, mt_nfam, mt_m0, mt_cnt, pro_slot, own_pro_row, live_lrow, tile_map, live_tiles;
+    DevBuf<int32_t> mem_ind, mem_slot, mem_fam, mem_lrow, fam_pf, fam_pm, fam_q, fam_pf_lrow, fam_pm_lrow, fam_start,
+        mt_desc, pro_slot, own_pro_row, live_lrow, tile_map, live_tiles;
     DevBuf<int8_t> fam_pf_owner, fam_pm_owner, live_owner;
     DevBuf<int32_t> mem_rank;
     DevBuf<uint8_t> flags;
@@ -226,7 +229,7 @@ void fill_info(const Layer &L, genlib_layer_info *o) {
 size_t pad256(size_t b) { return (std::max<size_t>(b, 1) + 255) / 256 * 256; }
 
 size_t plan_index_bytes(const Plan &P) {
-    return (P.mem_ind.size() * 4 + P.mem_rank.size() + P.fam_pf.size() * 6 + P.fam_start.size() + P.mtile_fam0.size() * 4 +
+    return (P.mem_ind.size() * 4 + P.mem_rank.size() + P.fam_pf.size() * 6 + P.fam_start.size() + P.mtile_desc.size() +
             P.pro_slot.size() * 2 + P.live_lrow.size() + P.tile_map.size() + P.live_tiles.size()) * sizeof(int32_t) + P.fam_pf.size() * 2 + P.live_owner.size() + P.flags.size();
 }
 
@@ -306,8 +309,8 @@ size_t engine_bytes(const Plan &P, int numerics, int g, int sm_count = 148) {
     size_t b = kFlagBytes + a_bytes(P, es, g) + pad256(q) + pad256(sync_ints * sizeof(int32_t));
     b += 2 * pad256(kFetchStageBytes);                                         // proband staging
     b += 4 * DevBuf<int32_t>::padded(P.mem_ind.size()) + DevBuf<int32_t>::padded(P.mem_rank.size()) +
-         6 * DevBuf<int32_t>::padded(P.fam_pf.size()) + DevBuf<int32_t>::padded(P.fam_start.size()) +
-         4 * DevBuf<int32_t>::padded(P.mtile_fam0.size()) + 2 * DevBuf<int32_t>::padded(P.pro_slot.size()) +
+         4 * DevBuf<int32_t>::padded(P.fam_pf.size()) + DevBuf<int32_t>::padded(P.fam_q.size()) + DevBuf<int32_t>::padded(P.fam_start.size()) +
+         DevBuf<int32_t>::padded(P.mtile_desc.size()) + 2 * DevBuf<int32_t>::padded(P.pro_slot.size()) +
          DevBuf<int32_t>::padded(P.live_lrow.size()) + DevBuf<int32_t>::padded(P.tile_map.size()) +
          DevBuf<int32_t>::padded(P.live_tiles.size()) +
          2 * DevBuf<int8_t>::padded(P.fam_pf.size()) +
@@ -330,15 +333,14 @@ LayerArgs layer_args(const genlib_engine &E, int t) {
     a.mem_ind = E.mem_ind.p + L.mem_off; a.mem_slot = E.mem_slot.p + L.mem_off; a.mem_fam = E.mem_fam.p + L.mem_off;
     a.mem_lrow = E.mem_lrow.p + L.mem_off;
     a.fam_pf = E.fam_pf.p + L.fam_off; a.fam_pm = E.fam_pm.p + L.fam_off;
-    a.fam_qf = E.fam_qf.p + L.fam_off; a.fam_qm = E.fam_qm.p + L.fam_off;
+    a.fam_q = reinterpret_cast<const int2 *>(E.fam_q.p) + L.fam_off;
     a.fam_pf_owner = E.fam_pf_owner.p + L.fam_off; a.fam_pm_owner = E.fam_pm_owner.p + L.fam_off;
     a.fam_pf_lrow = E.fam_pf_lrow.p + L.fam_off; a.fam_pm_lrow = E.fam_pm_lrow.p + L.fam_off;
     a.fam_start = E.fam_start.p + L.fam_off + t;
     a.flags = E.flags.p + L.flag_off;
     a.live_owner = E.live_owner.p + L.flag_off; a.live_lrow = E.live_lrow.p + L.flag_off;
     a.tile_map = E.tile_map.p + L.tile_off;
-    a.mt_fam0 = E.mt_fam0.p + L.mtile_off; a.mt_nfam = E.mt_nfam.p + L.mtile_off;
-    a.mt_m0 = E.mt_m0.p + L.mtile_off; a.mt_cnt = E.mt_cnt.p + L.mtile_off;
+    a.mt_desc = reinterpret_cast<const int4 *>(E.mt_desc.p) + L.mtile_off;
     a.n_mtiles = L.n_mtiles;
     return a;
 }
@@ -375,6 +377,11 @@ int launch_layers(genlib_engine &E, bool timed) {
             ll.s.Q = E.Q;
             ll.s.sync = E.sync + ll.sync_off;
             ll.s.live_tiles = E.live_tiles.p + L.ltile_off;
+#ifdef GENLIB_PROFILE
+            ll.s.prof = (t == env_int("GENLIB_PROF_LAYER", 5)) ? E.prof : nullptr;
+#else
+            ll.s.prof = nullptr;
+#endif
             layer_fn<<<ll.grid, kLayerThreads, ll.smem, E.stream>>>(A, ld, E.peers, a, ll.s);
             launches++;
             if (P.schedule == kScheduleSparsePhi && L.n_new > 1 && a.own_nm > 0) {   // the reference's misfiled kinships read as 0
@@ -389,6 +396,21 @@ int launch_layers(genlib_engine &E, bool timed) {
     }
     CU(cudaGetLastError());
     E.stats.kernel_launches = launches;
+#ifdef GENLIB_PROFILE
+    {
+        CU(cudaStreamSynchronize(E.stream));
+        std::vector<long long> h(8 * 2 * 160);
+        CU(cudaMemcpy(h.data(), E.prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        const LayerLaunch &pl = E.launch[env_int("GENLIB_PROF_LAYER", 5)];
+        double acc[2][8] = {};
+        for (int b = 0; b < pl.grid; b++) for (int i = 0; i < 8; i++) acc[b >= pl.s.n_prod][i] += (double)h[(size_t)b * 8 + i];
+        std::fprintf(stderr, "[prof] producers %d consumers %d strips %d (avg kcycles per CTA)\n", pl.s.n_prod, pl.s.n_cons, pl.s.n_strips);
+        std::fprintf(stderr, "[prof] producer: other %.0f wait_consumers %.0f mbar %.0f issue %.0f transpose %.0f member_rows %.0f\n",
+                     acc[0][0] / pl.s.n_prod / 1e3, acc[0][1] / pl.s.n_prod / 1e3, acc[0][2] / pl.s.n_prod / 1e3, acc[0][3] / pl.s.n_prod / 1e3, acc[0][4] / pl.s.n_prod / 1e3, acc[0][5] / pl.s.n_prod / 1e3);
+        std::fprintf(stderr, "[prof] consumer: other %.0f wait_producers %.0f switch %.0f stage_wait %.0f compute %.0f stage_issue %.0f expand %.0f mirror %.0f\n",
+                     acc[1][0] / pl.s.n_cons / 1e3, acc[1][1] / pl.s.n_cons / 1e3, acc[1][2] / pl.s.n_cons / 1e3, acc[1][3] / pl.s.n_cons / 1e3, acc[1][4] / pl.s.n_cons / 1e3, acc[1][5] / pl.s.n_cons / 1e3, acc[1][6] / pl.s.n_cons / 1e3, acc[1][7] / pl.s.n_cons / 1e3);
+    }
+#endif
     return GENLIB_OK;
 }
 
@@ -535,11 +557,10 @@ int create_engine(const genlib_plan *plan, int numerics, int device, int rank, g
         E->mem_ind.place(cur, P.mem_ind.size()); E->mem_slot.place(cur, P.mem_slot.size()); E->mem_fam.place(cur, P.mem_fam.size());
         E->mem_lrow.place(cur, P.mem_lrow.size()); E->mem_rank.place(cur, P.mem_rank.size());
         E->fam_pf.place(cur, P.fam_pf.size()); E->fam_pm.place(cur, P.fam_pm.size());
-        E->fam_qf.place(cur, P.fam_qf.size()); E->fam_qm.place(cur, P.fam_qm.size());
+        E->fam_q.place(cur, P.fam_q.size());
         E->fam_pf_lrow.place(cur, P.fam_pf_lrow.size()); E->fam_pm_lrow.place(cur, P.fam_pm_lrow.size());
         E->fam_start.place(cur, P.fam_start.size());
-        E->mt_fam0.place(cur, P.mtile_fam0.size()); E->mt_nfam.place(cur, P.mtile_nfam.size());
-        E->mt_m0.place(cur, P.mtile_m0.size()); E->mt_cnt.place(cur, P.mtile_cnt.size());
+        E->mt_desc.place(cur, P.mtile_desc.size());
         E->pro_slot.place(cur, P.pro_slot.size()); E->own_pro_row.place(cur, P.pro_slot.size());
         E->live_lrow.place(cur, P.live_lrow.size()); E->tile_map.place(cur, P.tile_map.size());
         E->live_tiles.place(cur, P.live_tiles.size());
@@ -581,17 +602,13 @@ int create_engine(const genlib_plan *plan, int numerics, int device, int rank, g
     CU(E->mem_rank.upload(P.mem_rank, E->stream));
     CU(E->fam_pf.upload(P.fam_pf, E->stream));
     CU(E->fam_pm.upload(P.fam_pm, E->stream));
-    CU(E->fam_qf.upload(P.fam_qf, E->stream));
-    CU(E->fam_qm.upload(P.fam_qm, E->stream));
+    CU(E->fam_q.upload(P.fam_q, E->stream));
     CU(E->fam_pf_lrow.upload(P.fam_pf_lrow, E->stream));
     CU(E->fam_pm_lrow.upload(P.fam_pm_lrow, E->stream));
     CU(E->fam_pf_owner.upload(P.fam_pf_owner, E->stream));
     CU(E->fam_pm_owner.upload(P.fam_pm_owner, E->stream));
     CU(E->fam_start.upload(P.fam_start, E->stream));
-    CU(E->mt_fam0.upload(P.mtile_fam0, E->stream));
-    CU(E->mt_nfam.upload(P.mtile_nfam, E->stream));
-    CU(E->mt_m0.upload(P.mtile_m0, E->stream));
-    CU(E->mt_cnt.upload(P.mtile_cnt, E->stream));
+    CU(E->mt_desc.upload(P.mtile_desc, E->stream));
     CU(E->pro_slot.upload(P.pro_slot, E->stream));
     CU(E->own_pro_row.upload(own_rows, E->stream));
     CU(E->live_owner.upload(P.live_owner, E->stream));
@@ -600,6 +617,10 @@ int create_engine(const genlib_plan *plan, int numerics, int device, int rank, g
     CU(E->live_tiles.upload(P.live_tiles, E->stream));
     CU(E->flags.upload(P.flags, E->stream));
     CU(cudaStreamSynchronize(E->stream));
+#ifdef GENLIB_PROFILE
+    CU(cudaMalloc(&E->prof, 8 * 2 * 160 * sizeof(long long)));
+    CU(cudaMemset(E->prof, 0, 8 * 2 * 160 * sizeof(long long)));
+#endif
     E->peers.A[rank] = E->A; E->bars.flags[rank] = E->bar_flags;
     E->attached = P.world == 1;
     E->info.resize(P.layers.size());
@@ -888,7 +909,7 @@ int genlib_engine_run(genlib_engine *eng, int time_layers) {
                 errw |= w2[1];
                 if (errw) break;
             }
-        if (errw) return fail(GENLIB_ECUDA, "a unit of the layer kernel waited too long for its strip (internal error)");
+        if (errw) return fail(GENLIB_ECUDA, "the layer kernel reported error " + std::to_string(errw) + " (1: a strip dependency did not arrive, 2: a bulk copy did not complete)");
     }
     if (E.world > 1) {
         unsigned errw = 0;

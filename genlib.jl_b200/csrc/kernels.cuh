@@ -31,12 +31,12 @@ struct LayerArgs {
     int32_t fam_base[kMaxWorld + 1];
     const int32_t *mem_ind, *mem_slot, *mem_fam, *mem_lrow;     // members: rank (or queue position), column slot, couple, local row
     const int32_t *fam_pf, *fam_pm, *fam_start;                  // couples: parent slots (-1 none), first member
-    const int32_t *fam_qf, *fam_qm;                              // couples: the parents' rows in a strip buffer (-1 none)
+    const int2 *fam_q;                                           // couples: the parents' rows in a strip buffer (-1 none)
     const int8_t *fam_pf_owner, *fam_pm_owner, *live_owner;      // where the parents' / the live individuals' rows are
     const int32_t *fam_pf_lrow, *fam_pm_lrow, *live_lrow;
     const uint8_t *flags;                                        // per slot of the live range: kFlagLive | kFlagCarried
     const int32_t *tile_map;                                     // per tile of the live range: index among the live tiles (-1: hole)
-    const int32_t *mt_fam0, *mt_nfam, *mt_m0, *mt_cnt;           // member tiles: couple range, member range
+    const int4 *mt_desc;                                         // member tiles: first couple, couples, first member, members
     int32_t n_mtiles;
 };
 

@@ -39,6 +39,14 @@
 // a wait that lasts seconds raises the layer's error word instead of hanging the device.
 #pragma once
 #include "kernels.cuh"
+#if defined(GENLIB_CHECK)
+#include <cassert>
+#define CHECK(cond) assert(cond)
+#elif defined(GENLIB_SOFTCHECK)       // record the source line of a violated bound in the layer's error word, go on
+#define CHECK(cond) do { if (!(cond)) atomicMax(S.sync + 1, 100000 + __LINE__); } while (0)
+#else
+#define CHECK(cond) do { } while (0)
+#endif
 
 namespace genlib {
 
@@ -67,6 +75,7 @@ struct StripArgs {
     int32_t *sync;       // [1] error word, [2 + s] producers done with strip s, [2 + n_strips + s] consumers done
     const int32_t *live_tiles;   // the live tiles of the layer's slot range: index | kTileCarried
     long long timeout_cycles;
+    long long *prof;             // -DGENLIB_PROFILE: 8 cycle counters per CTA (else unused)
 };
 
 template <typename T> struct PairOf;
@@ -92,9 +101,10 @@ __device__ __forceinline__ void couple_pair(double ax, double ay, double cx, dou
 }
 
 inline size_t layer_ring_bytes(int ft, int stages, size_t es) { return (size_t)stages * 2 * ft * (kPTile * es + 16); }
-// consumer: staged parent-row segments of a couple tile (2 x kMaxTileFam rows x sw pairs) + Va | Vb
+// consumer: staged parent-row segments of a couple tile (2 x kMaxTileFam rows x sw pairs), Va | Vb, a ring of
+// three tiles' metadata, the strip's member rows
 inline size_t layer_consumer_bytes(int sw, size_t es) {
-    return (size_t)2 * kMaxTileFam * sw * 2 * es + (size_t)2 * sw * kVPitch * es;
+    return (size_t)2 * kMaxTileFam * sw * 2 * es + (size_t)2 * sw * kVPitch * es + (size_t)3 * 4 * kMTile * 4 + (size_t)kLayerThreads * 16;
 }
 
 // The items of strip s that CTA k of a role with n CTAs takes: first, first + n, ... below n_items.
@@ -102,6 +112,18 @@ __device__ __forceinline__ int first_item(int k, int s, int rot, int n) {
     int f = (k - (int)(((long long)s * rot) % n)) % n;
     return f < 0 ? f + n : f;
 }
+
+// Optional cycle accounting per CTA and phase (-DGENLIB_PROFILE): thread 0's clock64 between phase marks,
+// summed into S.prof[blockIdx.x * 8 + phase]; scripts/prof_layers.py prints them.
+#ifdef GENLIB_PROFILE
+#define PROF_DECL long long prof_t = clock64(), prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define PROF_MARK(ph) do { const long long now_ = clock64(); prof_acc[ph] += now_ - prof_t; prof_t = now_; } while (0)
+#define PROF_FLUSH() do { if (tid == 0 && S.prof) for (int i_ = 0; i_ < 8; i_++) S.prof[(size_t)blockIdx.x * 8 + i_] = prof_acc[i_]; } while (0)
+#else
+#define PROF_DECL
+#define PROF_MARK(ph) do { } while (0)
+#define PROF_FLUSH() do { } while (0)
+#endif
 
 template <typename T, bool STORED>
 __global__ void __launch_bounds__(kLayerThreads, 2)
@@ -115,6 +137,7 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
     const int sw = S.sw, ft = S.ft, NS = S.n_strips;
     int *const err = S.sync + 1, *const done_p = S.sync + 2, *const done_c = S.sync + 2 + NS;
     P2 *const Qall = static_cast<P2 *>(S.Q);
+    PROF_DECL
 
     // Thread 0 spins, everybody follows.  A dependency that does not arrive in time sets the layer's error
     // word (genlib_engine_run then fails with GENLIB_ECUDA); once it is set nobody waits any more, so a
@@ -150,6 +173,7 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
         int is = 0, ii = first_item(k, 0, S.rot_p, NP);
         while (is < NS && ii >= NI) { is++; ii = first_item(k, is, S.rot_p, NP); }
         int cs = is, ci = ii;
+        int issue_tile = is < NS ? S.live_tiles[ii / npt] & (kTileCarried - 1) : 0;   // tile of the item at the issue cursor
         int rows_of = -1;                                          // strip whose parent rows are in s_row
         unsigned n_issued = 0, n_done = 0;
         const int rpw = 2 * ft / kLayerWarps;                      // rows each warp issues
@@ -176,7 +200,7 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
         auto issue = [&]() {                                       // item (is, ii) -> ring slot n_issued % stages
             if (lane < rpw) {
                 const unsigned slot = n_issued % (unsigned)S.stages;
-                const int pt = ii % npt, tile = S.live_tiles[ii / npt] & (kTileCarried - 1);
+                const int pt = ii % npt, tile = issue_tile;
                 const int row = warp * rpw + lane;                 // 0 .. 2 ft - 1: fathers, then mothers
                 const unsigned bar = bar0 + 8u * slot;
                 const unsigned dst = sbase + slot * (unsigned)STAGE + (unsigned)(row * RB);
@@ -194,6 +218,7 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
             n_issued++;
             ii += NP;
             while (is < NS && ii >= NI) { is++; ii = first_item(k, is, S.rot_p, NP); }
+            if (is < NS) issue_tile = S.live_tiles[ii / npt] & (kTileCarried - 1);   // in flight until the next issue
         };
         auto try_issue = [&]() {                                   // uniform over the CTA
             if (is >= NS) return;
@@ -214,15 +239,20 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
             if (cs != cur) {                                       // count off the strips that are behind us
                 for (int s = max(cur, 0); s < cs; s++) count_off(done_p + s);
                 cur = cs;
+                PROF_MARK(0);
                 wait_for(done_c + (cs - S.nbuf), cs >= S.nbuf ? S.n_cons : 0);    // the strip that used this buffer is consumed
+                PROF_MARK(1);
             }
             int ncs = cs, nci = ci + NP;                           // the item after this one
             while (ncs < NS && nci >= NI) { ncs++; nci = first_item(k, ncs, S.rot_p, NP); }
             const int tinfo_next = ncs < NS ? S.live_tiles[nci / npt] : 0;
             const unsigned slot = n_done % (unsigned)S.stages;
+            PROF_MARK(0);
             if (!mbar_wait(bar0 + 8u * slot, (n_done / (unsigned)S.stages) & 1u)) atomicExch(err, 2);
             __syncthreads();                                       // everybody is done with the stage refilled next
+            PROF_MARK(2);
             try_issue();
+            PROF_MARK(3);
             const int pt = ci % npt, lt = ci / npt;
             const int tile = tinfo & (kTileCarried - 1);
             const unsigned char *st = dyn_smem + slot * STAGE;
@@ -241,12 +271,14 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
                         const int c4 = (j + hi) & 3;
                         const int col = warp * (kPTile / 8) + gq * 4 + c4;
                         if ((w >> (8 * c4)) & kFlagLive) {
+                            CHECK(((size_t)lt * kPTile + col) * sw + pt * ft + f < (size_t)S.qstride);
                             P2 v; v.x = xr[col]; v.y = yr[col];
                             q[(size_t)col * sw] = v;
                         }
                     }
                 }
             }
+            PROF_MARK(4);
             // ---- rows of the new members against this tile's carried columns (rounded once, compute.jl:296).
             //      Columns that are not carried receive values nobody reads. ----
             if (tinfo & kTileCarried) {
@@ -261,86 +293,136 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
                     lds4(reinterpret_cast<const T *>(st + (ft + fi) * RB) + 4 * lane, y);
 #pragma unroll
                     for (int e = 0; e < 4; e++) rr[e] = half_sum_mode<STORED>(x[e], y[e]);
+                    CHECK(col0 + 3 < ld && mb >= 0 && me <= L.n_new);
                     for (int m = mb; m < me; m++) store4(A + (int64_t)L.mem_lrow[m] * ld + col0, rr);
                 }
             }
+            PROF_MARK(5);
             n_done++;
             cs = ncs; ci = nci;
             tinfo = tinfo_next;
             live4 = cs < NS ? tile_flags(tinfo) : 0u;
         }
         for (int s = max(cur, 0); s < NS; s++) count_off(done_p + s);
+        PROF_MARK(0);
+        PROF_FLUSH();
         return;
     }
 
     // ===== consumer: couple tiles -> the strip members' rows; carried rows <- the strip members' columns =====
+    // Nothing the inner loops need comes from a dependent global load: tile descriptors travel three items
+    // ahead in registers, a tile's metadata (its couples' strip-buffer rows, its members' couple / rank /
+    // slot) two items ahead into a shared-memory ring with cp.async, its segments one item ahead, and the
+    // strip's member rows one strip ahead.
     const int k = blockIdx.x - S.n_prod, NC = S.n_cons, NI = S.n_citems;
-    P2 *const stg = reinterpret_cast<P2 *>(dyn_smem);                               // [2 g + parent][f]
-    T *const Va = reinterpret_cast<T *>(dyn_smem + (size_t)2 * kMaxTileFam * sw * sizeof(P2));   // [f][g]: F climbed first
-    T *const Vb = Va + (size_t)sw * kVPitch;                                        // [f][g]: G climbed first
-    const unsigned stg_s = (unsigned)__cvta_generic_to_shared(stg);
+    constexpr int kMetaSlots = 3, kMetaInts = 4 * kMTile;          // per slot: qrow[128] | couple[128] | rank[128] | slot[128]
+    constexpr int kRowCache = kLayerThreads;                       // strip member rows kept in shared memory at a time
+    struct RowMeta { unsigned rowoff; int rank; long long bytes; };   // Va row offset, rank, byte offset of the frontier row
+    unsigned char *sm = dyn_smem;
+    P2 *const stg = reinterpret_cast<P2 *>(sm);                    // [2 g + parent][f]
+    sm += (size_t)2 * kMaxTileFam * sw * sizeof(P2);
+    T *const Va = reinterpret_cast<T *>(sm);                       // [f][g]: the strip couple's member is climbed first
+    T *const Vb = Va + (size_t)sw * kVPitch;                       // [f][g]: the tile couple's member is climbed first
+    sm += (size_t)2 * sw * kVPitch * sizeof(T);
+    int *const meta = reinterpret_cast<int *>(sm);
+    sm += (size_t)kMetaSlots * kMetaInts * sizeof(int);
+    RowMeta *const rowmeta = reinterpret_cast<RowMeta *>(sm);
+    const unsigned stg_s = (unsigned)__cvta_generic_to_shared(stg), meta_s = (unsigned)__cvta_generic_to_shared(meta);
     const unsigned va_s = (unsigned)__cvta_generic_to_shared(Va), vb_s = (unsigned)__cvta_generic_to_shared(Vb);
     const int lsw = 31 - __clz(sw);                                // sw is a power of two
-    // Two threads per staged row (one parent of one couple of the tile): one look-up, then the 16-byte copies.
-    const int row_bytes = sw * (int)sizeof(P2), half_bytes = row_bytes / 2;
-    auto stage_tile = [&](const P2 *Q, int fJ0, int nfJ) {
-        const int row = tid >> 1, part = tid & 1;
-        if (row < 2 * nfJ) {
-            const int G = fJ0 + (row >> 1);
-            const int q = (row & 1) ? L.fam_qm[G] : L.fam_qf[G];
-            const unsigned dst = stg_s + (unsigned)(row * row_bytes + part * half_bytes);
-            if (q >= 0) {
-                const unsigned char *src = reinterpret_cast<const unsigned char *>(Q + (size_t)q * sw) + part * half_bytes;
-                for (int c = 0; c < half_bytes; c += 16) cp_async16_to(dst + c, src + c);
-            } else {
-                for (int c = 0; c < half_bytes; c += 16) zero16_shared(dst + c);   // unknown parent: contributes 0
+    const int row_bytes = sw * (int)sizeof(P2);
+
+    struct Cur { int s, it; };                                     // an item of this CTA: strip, index in the strip
+    auto advance = [&](Cur c) {
+        c.it += NC;
+        while (c.s < NS && c.it >= NI) { c.s++; c.it = first_item(k, c.s, S.rot_c, NC); }
+        return c;
+    };
+    auto is_tile = [&](Cur c) { return c.s < NS && c.it < L.n_mtiles; };
+    auto fetch_desc = [&](Cur c) { return is_tile(c) ? __ldg(L.mt_desc + c.it) : make_int4(0, 0, 0, 0); };
+    // metadata of tile `d` -> ring slot (cp.async; the caller commits)
+    auto fetch_meta = [&](int4 d, int slot) {
+        CHECK(d.y >= 1 && d.y <= kMaxTileFam && d.w >= 1 && d.w <= kMTile && d.x >= 0 && d.x + d.y <= L.n_fam && d.z >= 0 && d.z + d.w <= L.n_new);
+        const unsigned base = meta_s + (unsigned)(slot * kMetaInts * (int)sizeof(int));
+        if (tid < d.y)                                             // the couples' (father, mother) rows in the strip buffers
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(base + 8u * tid), "l"(L.fam_q + d.x + tid) : "memory");
+        const int nchunk = (d.w + 3) >> 2;                         // member columns: couple, rank, slot in 16-byte chunks
+        if (tid < 3 * nchunk) {
+            const int arr = tid / nchunk, c = tid - arr * nchunk;
+            const int32_t *src = (arr == 0 ? L.mem_fam : arr == 1 ? L.mem_ind : L.mem_slot) + d.z + 4 * c;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(base + (unsigned)((kMTile * (1 + arr) + 4 * c) * 4)), "l"(src) : "memory");
+        }
+    };
+    // the two parent-row segments of every couple of the tile -> stg: a warp copies a whole segment per step
+    auto stage_tile = [&](const P2 *Q, int nfJ, int slot) {
+        const int *qrow = meta + slot * kMetaInts;
+        const int per = row_bytes / 16;                            // lanes per segment (4 ... 32)
+        const int seg_per_step = 32 / per, sub = lane / per, part = lane - sub * per;
+        for (int r0 = warp * seg_per_step; r0 < 2 * nfJ; r0 += kLayerWarps * seg_per_step) {
+            const int r = r0 + sub;
+            if (r < 2 * nfJ) {
+                const int q = qrow[r];
+                CHECK(q >= -1 && (long long)q * sw < S.qstride);
+                const unsigned dst = stg_s + (unsigned)(r * row_bytes + part * 16);
+                if (q >= 0) cp_async16_to(dst, reinterpret_cast<const unsigned char *>(Q + (size_t)q * sw) + part * 16);
+                else zero16_shared(dst);                           // unknown parent: contributes 0
             }
         }
-        cp_async_commit();
     };
-    // a member tile's descriptor and the lane's four member columns in it
-    struct TileCtx { int fJ0, nfJ, mJ0, cntJ, gj[4], rj[4], sj[4]; };
-    auto load_ctx = [&](TileCtx &c, int J) {
-        c.fJ0 = L.mt_fam0[J]; c.nfJ = L.mt_nfam[J]; c.mJ0 = L.mt_m0[J]; c.cntJ = L.mt_cnt[J];
-    };
-    auto load_cols = [&](TileCtx &c) {
-        const int j0 = c.mJ0 + 4 * lane;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int j = min(j0 + q, c.mJ0 + c.cntJ - 1);
-            c.gj[q] = L.mem_fam[j] - c.fJ0; c.rj[q] = L.mem_ind[j]; c.sj[q] = L.mem_slot[j];
-        }
-    };
+
+    // ---- the strip's member rows: prefetched one strip ahead (registers), cached in shared memory ----
     int cur = -1;                                                  // strip this CTA is in
-    int F0 = 0, nFs = 0, ms0 = 0, ms1 = 0, n_rows = 0, share = 1, pass_rows = kLayerWarps;
-    int my_f = 0, my_rank = 0, my_lrow = 0;
-    auto load_member_rows = [&](int i0) {
-        const int im = min(i0 + lane, ms1 - 1);
-        my_f = L.mem_fam[im] - F0; my_rank = L.mem_ind[im]; my_lrow = L.mem_lrow[im];
+    int F0 = 0, nFs = 0, ms0 = 0, ms1 = 0, n_rows = 0;
+    int pre_s = -1, pre_ms0 = 0, pre_ms1 = 0, pre_f = 0, pre_rank = 0, pre_lrow = 0;   // strip pre_s: bounds, row ms0 + tid
+    int pre2_s = -1, pre2_ms0 = 0, pre2_ms1 = 0;                   // strip pre2_s: bounds only
+    auto strip_bounds = [&](int st, int &b0, int &b1) {
+        const int f0 = L.own_f0 + st * sw, nf = min(sw, L.own_nf - st * sw);
+        b0 = L.fam_start[f0]; b1 = L.fam_start[f0 + nf];
     };
-    int s = 0, it = first_item(k, 0, S.rot_c, NC);
-    while (s < NS && it >= NI) { s++; it = first_item(k, s, S.rot_c, NC); }
-    bool staged = false;                                           // the current item (a tile) has been staged ahead (cx is loaded)
-    TileCtx cx, nx;
-    while (s < NS) {
+    auto strip_row = [&](int st, int b0, int b1, int first, int &f, int &rk, int &lr) {   // row first + tid of strip st
+        const int im = min(b0 + first + tid, b1 - 1);
+        f = L.mem_fam[im] - (L.own_f0 + st * sw); rk = L.mem_ind[im]; lr = L.mem_lrow[im];
+    };
+    auto put_row = [&](int f, int rk, int lr) {
+        RowMeta m; m.rowoff = (unsigned)(f * kVPitch * (int)sizeof(T)); m.rank = rk; m.bytes = (long long)lr * ld * (long long)sizeof(T);
+        rowmeta[tid] = m;
+    };
+
+    Cur c0; c0.s = 0; c0.it = first_item(k, 0, S.rot_c, NC);
+    while (c0.s < NS && c0.it >= NI) { c0.s++; c0.it = first_item(k, c0.s, S.rot_c, NC); }
+    Cur c1 = advance(c0), c2 = advance(c1), c3 = advance(c2);
+    int4 d0 = fetch_desc(c0), d1 = fetch_desc(c1), d2 = fetch_desc(c2);
+    unsigned n_item = 0;                                           // items done: item j's metadata sits in ring slot j % 3
+    if (is_tile(c0)) fetch_meta(d0, 0);
+    if (is_tile(c1)) fetch_meta(d1, 1);
+    cp_async_commit();
+    bool staged = false;                                           // the segments of c0 are on their way (or there)
+    while (c0.s < NS) {
+        const int s = c0.s, it = c0.it;
         if (s != cur) {
             for (int t = max(cur, 0); t < s; t++) count_off(done_c + t);
             cur = s;
             F0 = L.own_f0 + s * sw;
             nFs = min(sw, L.own_nf - s * sw);
-            ms0 = L.fam_start[F0]; ms1 = L.fam_start[F0 + nFs];
+            int rf, rk, rl;
+            if (pre_s == s) { ms0 = pre_ms0; ms1 = pre_ms1; rf = pre_f; rk = pre_rank; rl = pre_lrow; }
+            else { strip_bounds(s, ms0, ms1); strip_row(s, ms0, ms1, 0, rf, rk, rl); }
             n_rows = ms1 - ms0;
-            // the warp's rows: an even share of the strip's member rows (at most 32 at a time), their metadata
-            // spread over the lanes; a strip of up to 256 rows (the usual case) keeps them in registers
-            share = max(1, min(32, (n_rows + kLayerWarps - 1) / kLayerWarps));
-            pass_rows = share * kLayerWarps;
-            if (n_rows > 0) load_member_rows(ms0 + warp * share);
+            put_row(rf, rk, rl);                                   // (read after the barriers below)
+            // the next strip's rows, and the bounds of the one after, are fetched now and used a strip later
+            if (s + 1 < NS) {
+                if (pre2_s == s + 1) { pre_ms0 = pre2_ms0; pre_ms1 = pre2_ms1; } else strip_bounds(s + 1, pre_ms0, pre_ms1);
+                strip_row(s + 1, pre_ms0, pre_ms1, 0, pre_f, pre_rank, pre_lrow);
+                pre_s = s + 1;
+                if (s + 2 < NS) { strip_bounds(s + 2, pre2_ms0, pre2_ms1); pre2_s = s + 2; }
+            }
+            PROF_MARK(2);
             if (!staged) wait_for(done_p + s, S.n_prod);          // the strip's pairs are complete (in L2)
+            else __syncthreads();
+            PROF_MARK(1);
         }
         const P2 *const Q = Qall + (size_t)(s % S.nbuf) * S.qstride;
-        // the item after this one (maybe in the next strip)
-        int ns = s, nit = it + NC;
-        while (ns < NS && nit >= NI) { ns++; nit = first_item(k, ns, S.rot_c, NC); }
+        const int slot0 = (int)(n_item % kMetaSlots);
 
         if (it >= L.n_mtiles) {
             // ---- a block of carried rows: the strip members' columns, Psi[c, i] = RN(hs(Q[c][F_i])) ----
@@ -348,6 +430,7 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
             for (int row = r0 + warp; row < r1; row += kLayerWarps) {
                 if (!(L.flags[row] & kFlagCarried)) continue;
                 T *dst = static_cast<T *>(PT.A[L.live_owner[row]]) + (int64_t)L.live_lrow[row] * ld;
+                CHECK(L.tile_map[row / kPTile] >= 0 && L.live_owner[row] >= 0 && L.live_lrow[row] >= 0);
                 const P2 *q = Q + ((size_t)L.tile_map[row / kPTile] * kPTile + (size_t)(row % kPTile)) * sw;
                 T v0 = (T)0, v1 = (T)0;
                 if (lane < nFs) { const P2 p = __ldcg(q + lane); v0 = (T)half_sum_mode<STORED>((double)p.x, (double)p.y); }
@@ -359,18 +442,35 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
                     if (m < ms1) dst[L.mem_slot[mm]] = fi < 32 ? a : b;
                 }
             }
+            // keep the pipeline of descriptors and metadata moving
+            const int4 d3 = fetch_desc(c3);
+            if (is_tile(c2)) fetch_meta(d2, (int)((n_item + 2) % kMetaSlots));
+            cp_async_commit();
             staged = false;
-        } else {
-            // ---- a member tile J: stage its couples' segments (unless done ahead), form Va | Vb, expand ----
-            if (!staged) { load_ctx(cx, it); stage_tile(Q, cx.fJ0, cx.nfJ); load_cols(cx); }
-            const int nfJ = cx.nfJ;
-            const int j0 = cx.mJ0 + 4 * lane, ncol = min(4, cx.mJ0 + cx.cntJ - j0);
+            c0 = c1; c1 = c2; c2 = c3; c3 = advance(c3);
+            d0 = d1; d1 = d2; d2 = d3;
+            n_item++;
+            PROF_MARK(7);
+            continue;
+        }
+
+        // ---- a member tile: its couples' segments (staged ahead unless the strip was not ready), Va | Vb, expansion ----
+        const int fJ0 = d0.x, nfJ = d0.y, mJ0 = d0.z, cntJ = d0.w;
+        if (!staged) {
             cp_async_wait<0>();
-            __syncthreads();                                       // the tile's segments are staged; the previous item is written
-#pragma unroll 2
-            for (int e = tid; e < (nfJ << lsw); e += kLayerThreads) {
-                const int g = e >> lsw, fl = e & (sw - 1);
-                if (fl < nFs) {
+            __syncthreads();                                       // the tile's metadata is in the ring
+            stage_tile(Q, nfJ, slot0);
+            cp_async_commit();
+        }
+        PROF_MARK(0);
+        cp_async_wait<0>();
+        __syncthreads();                                           // segments staged, the next tile's metadata landed, the previous item is written
+        PROF_MARK(3);
+        {
+            const int fl = tid & (sw - 1), g0 = tid >> lsw, gstep = kLayerThreads >> lsw;
+            if (fl < nFs) {
+#pragma unroll 4
+                for (int g = g0; g < nfJ; g += gstep) {
                     const P2 a = stg[(2 * g) * sw + fl], c = stg[(2 * g + 1) * sw + fl];
                     T vf, vg;
                     couple_pair<T, STORED>((double)a.x, (double)a.y, (double)c.x, (double)c.y, vf, vg);
@@ -378,66 +478,111 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
                     Vb[fl * kVPitch + g] = vg;
                 }
             }
-            __syncthreads();                                       // Va | Vb complete, the staging area is free
-            // stage the next tile, and fetch its columns, while this one is expanded (same strip, or the
-            // next one if its producers are done)
-            staged = false;
-            if (ns < NS && nit < L.n_mtiles) {
-                bool ready = ns == s;
-                if (!ready) {                                      // peek: do not wait here, the expansion comes first
-                    if (tid == 0) s_ready = ld_acquire_gpu(done_p + ns) >= S.n_prod;
-                    __syncthreads();
-                    ready = s_ready != 0;
-                }
-                if (ready) {
-                    load_ctx(nx, nit);
-                    stage_tile(Qall + (size_t)(ns % S.nbuf) * S.qstride, nx.fJ0, nx.nfJ);
-                    load_cols(nx);
-                    staged = true;
-                }
+        }
+        __syncthreads();                                           // Va | Vb complete, the staging area is free
+        PROF_MARK(4);
+        // the pipeline: descriptor of item +3, metadata of item +2, segments of item +1 (if its strip is produced)
+        const int4 d3 = fetch_desc(c3);
+        if (is_tile(c2)) fetch_meta(d2, (int)((n_item + 2) % kMetaSlots));
+        staged = false;
+        if (is_tile(c1)) {
+            bool ready = c1.s == s;
+            if (!ready) {                                          // peek: do not wait here, the expansion comes first
+                if (tid == 0) s_ready = ld_acquire_gpu(done_p + c1.s) >= S.n_prod;
+                __syncthreads();
+                ready = s_ready != 0;
             }
-            int gj[4], rj[4], sj[4];
+            if (ready) { stage_tile(Qall + (size_t)(c1.s % S.nbuf) * S.qstride, d1.y, (int)((n_item + 1) % kMetaSlots)); staged = true; }
+        }
+        cp_async_commit();
+        PROF_MARK(5);
+        // ---- expansion: the lane's four member columns, the warp's share of the strip's rows, four rows at a time ----
+        {
+            const int *mcol = meta + slot0 * kMetaInts + kMTile;
+            const int4 cg = *reinterpret_cast<const int4 *>(mcol + 4 * lane);
+            const int4 cr = *reinterpret_cast<const int4 *>(mcol + kMTile + 4 * lane);
+            const int4 cs4 = *reinterpret_cast<const int4 *>(mcol + 2 * kMTile + 4 * lane);
+            const int ncol = min(4, cntJ - 4 * lane);
+            // columns past the end of the tile repeat the lane's first one (what the ring holds there is stale)
+            const int gq[4] = {cg.x, ncol > 1 ? cg.y : cg.x, ncol > 2 ? cg.z : cg.x, ncol > 3 ? cg.w : cg.x};
+            const int rj[4] = {cr.x, ncol > 1 ? cr.y : cr.x, ncol > 2 ? cr.z : cr.x, ncol > 3 ? cr.w : cr.x};
+            const int sj[4] = {cs4.x, cs4.y, cs4.z, cs4.w};
+            unsigned off[4];
 #pragma unroll
-            for (int q = 0; q < 4; q++) { gj[q] = cx.gj[q]; rj[q] = cx.rj[q]; sj[q] = cx.sj[q]; }
+            for (int q = 0; q < 4; q++) off[q] = ncol > 0 ? (unsigned)((gq[q] - fJ0) * (int)sizeof(T)) : 0u;
             const bool vec = ncol == 4 && ((sj[0] & 3) == 0) && sj[1] == sj[0] + 1 && sj[2] == sj[0] + 2 && sj[3] == sj[0] + 3;
-            unsigned off[4];                                       // the lane's columns inside a couple-tile row
+            unsigned char *const Ab = reinterpret_cast<unsigned char *>(A);
+            for (int pass0 = 0; pass0 < n_rows; pass0 += kRowCache) {
+                if (pass0 > 0 || n_rows > kRowCache) {             // a strip with more rows than the cache: reload it per pass
+                    __syncthreads();
+                    int rf, rk, rl;
+                    strip_row(s, ms0, ms1, pass0, rf, rk, rl);
+                    put_row(rf, rk, rl);
+                    __syncthreads();
+                }
+                const int nrp = min(kRowCache, n_rows - pass0);
+                const int share = (nrp + kLayerWarps - 1) / kLayerWarps;
+                const int rbeg = warp * share, rend = min(nrp, rbeg + share);
+                if (ncol > 0) {
+                    int r = rbeg;
+                    for (; r + 4 <= rend; r += 4) {
+                        RowMeta m[4];
 #pragma unroll
-            for (int q = 0; q < 4; q++) off[q] = (unsigned)(gj[q] * (int)sizeof(T));
-            for (int i0 = ms0 + warp * share; i0 < ms1; i0 += pass_rows) {
-                if (n_rows > pass_rows) load_member_rows(i0);
-                const int nrow = min(share, ms1 - i0);
-                const int dk0 = i0 - j0;                           // row rr meets the lane's column q when dk0 + rr == q
-#pragma unroll 2
-                for (int rr = 0; rr < nrow; rr++) {                // (every lane takes part in the shuffles)
-                    const int fi = __shfl_sync(0xffffffffu, my_f, rr), ri = __shfl_sync(0xffffffffu, my_rank, rr);
-                    const int lrow = __shfl_sync(0xffffffffu, my_lrow, rr);
-                    if (ncol <= 0) continue;
-                    const unsigned rowoff = (unsigned)(fi * kVPitch * (int)sizeof(T));
-                    T v[4];
+                        for (int u = 0; u < 4; u++) {
+                            m[u] = rowmeta[r + u];
+                            CHECK(m[u].rowoff < (unsigned)(sw * kVPitch * (int)sizeof(T)) && m[u].bytes >= 0);
+                        }
+                        CHECK(off[0] < 260u && off[1] < 260u && off[2] < 260u && off[3] < 260u);
+                        CHECK(sj[0] >= 0 && sj[0] < ld);
+                        T v[4][4];
 #pragma unroll
-                    for (int q = 0; q < 4; q++)                    // the higher rank is climbed first (compute.jl:130-147)
-                        v[q] = lds<T>((ri > rj[q] ? va_s : vb_s) + rowoff + off[q]);
-                    if ((unsigned)(dk0 + rr) < 4u) {               // own diagonal entry (compute.jl:148-155)
-                        const int F = F0 + fi, pf = L.fam_pf[F], pm = L.fam_pm[F];
-                        double d = 0.5;
-                        if (pf >= 0 && pm >= 0)
-                            d = half_sum_mode<STORED>((double)(static_cast<const T *>(PT.A[L.fam_pf_owner[F]]) + (int64_t)L.fam_pf_lrow[F] * ld)[pm], 1.0);
+                        for (int u = 0; u < 4; u++)
 #pragma unroll
-                        for (int q = 0; q < 4; q++) if (dk0 + rr == q) v[q] = (T)d;
+                            for (int q = 0; q < 4; q++)            // the higher rank is climbed first (compute.jl:130-147)
+                                v[u][q] = lds<T>((m[u].rank > rj[q] ? va_s : vb_s) + m[u].rowoff + off[q]);
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            T *row = reinterpret_cast<T *>(Ab + m[u].bytes);
+                            if (vec) store_vec4(row + sj[0], v[u]);
+                            else {
+#pragma unroll
+                                for (int q = 0; q < 4; q++) if (q < ncol) row[sj[q]] = v[u][q];
+                            }
+                        }
                     }
-                    T *row = A + (int64_t)lrow * ld;
-                    if (vec) store_vec4(row + sj[0], v);
-                    else {
+                    for (; r < rend; r++) {
+                        const RowMeta m = rowmeta[r];
+                        CHECK(m.rowoff < (unsigned)(sw * kVPitch * (int)sizeof(T)) && m.bytes >= 0);
+                        T *row = reinterpret_cast<T *>(Ab + m.bytes);
 #pragma unroll
-                        for (int q = 0; q < 4; q++) if (q < ncol) row[sj[q]] = v[q];
+                        for (int q = 0; q < 4; q++)
+                            if (q < ncol) row[sj[q]] = lds<T>((m.rank > rj[q] ? va_s : vb_s) + m.rowoff + off[q]);
                     }
+                }
+                // own diagonal entries (compute.jl:148-155): rows of this pass that are also columns of this tile,
+                // written over the row segments above (__syncwarp orders the warp's stores)
+                __syncwarp();
+                const int dlo = max(ms0 + pass0 + rbeg, mJ0), dhi = min(ms0 + pass0 + rend, mJ0 + cntJ);
+                for (int i = dlo + lane; i < dhi; i += 32) {
+                    const RowMeta m = rowmeta[i - ms0 - pass0];
+                    const int F = F0 + (int)(m.rowoff / (unsigned)(kVPitch * (int)sizeof(T)));
+                    CHECK(F >= 0 && F < L.n_fam && i - mJ0 >= 0 && i - mJ0 < kMTile);
+                    const int pf = L.fam_pf[F], pm = L.fam_pm[F];
+                    double d = 0.5;
+                    if (pf >= 0 && pm >= 0)
+                        d = half_sum_mode<STORED>((double)(static_cast<const T *>(PT.A[L.fam_pf_owner[F]]) + (int64_t)L.fam_pf_lrow[F] * ld)[pm], 1.0);
+                    reinterpret_cast<T *>(Ab + m.bytes)[meta[slot0 * kMetaInts + 3 * kMTile + (i - mJ0)]] = (T)d;
                 }
             }
         }
-        if (staged) cx = nx;
-        s = ns; it = nit;
+        c0 = c1; c1 = c2; c2 = c3; c3 = advance(c3);
+        d0 = d1; d1 = d2; d2 = d3;
+        n_item++;
+        PROF_MARK(6);
     }
     for (int t = max(cur, 0); t < NS; t++) count_off(done_c + t);
+    PROF_MARK(0);
+    PROF_FLUSH();
 }
 
 }  // namespace genlib

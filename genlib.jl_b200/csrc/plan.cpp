@@ -340,7 +340,8 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         const size_t mcap = lstart[S] + 4 * (size_t)S, fcap = lstart[S] + 4 * (size_t)world * (size_t)S;
         for (auto *v : {&P.mem_ind, &P.mem_slot, &P.mem_fam, &P.mem_lrow}) v->reserve(mcap);
         if (by_seq) P.mem_rank.reserve(mcap);
-        for (auto *v : {&P.fam_pf, &P.fam_pm, &P.fam_pf_lrow, &P.fam_pm_lrow, &P.fam_qf, &P.fam_qm}) v->reserve(fcap);
+        for (auto *v : {&P.fam_pf, &P.fam_pm, &P.fam_pf_lrow, &P.fam_pm_lrow}) v->reserve(fcap);
+        P.fam_q.reserve(2 * fcap);
         P.fam_pf_owner.reserve(fcap); P.fam_pm_owner.reserve(fcap); P.fam_start.reserve(fcap + (size_t)S);
     }
     std::vector<int32_t> &live = W.live, &next_live = W.next_live;   // individuals live before the current step
@@ -449,7 +450,7 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         L.mem_off = P.mem_ind.size();
         L.fam_off = P.fam_pf.size();
         L.flag_off = P.flags.size();
-        L.mtile_off = P.mtile_fam0.size();
+        L.mtile_off = P.mtile_desc.size() / 4;
         L.base_off = P.fam_base.size();
 
         // ---- live range and flags (state BEFORE the step) ----
@@ -586,14 +587,14 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         P.fam_pf.resize(L.fam_off + (size_t)nf, -1); P.fam_pm.resize(L.fam_off + (size_t)nf, -1);
         P.fam_pf_owner.resize(L.fam_off + (size_t)nf, -1); P.fam_pm_owner.resize(L.fam_off + (size_t)nf, -1);
         P.fam_pf_lrow.resize(L.fam_off + (size_t)nf, -1); P.fam_pm_lrow.resize(L.fam_off + (size_t)nf, -1);
-        P.fam_qf.resize(L.fam_off + (size_t)nf, -1); P.fam_qm.resize(L.fam_off + (size_t)nf, -1);
+        P.fam_q.resize(2 * (L.fam_off + (size_t)nf), -1);
         for (int32_t f = 0; f < nf_real; f++) {
             const int32_t x = X[fam_first[f]], fa = father[x], mo = mother[x];
             const size_t k = L.fam_off + (size_t)newid[f];
             int32_t *ps[2] = {&P.fam_pf[k], &P.fam_pm[k]};
             int8_t *po[2] = {&P.fam_pf_owner[k], &P.fam_pm_owner[k]};
             int32_t *pl[2] = {&P.fam_pf_lrow[k], &P.fam_pm_lrow[k]};
-            int32_t *pq[2] = {&P.fam_qf[k], &P.fam_qm[k]};
+            int32_t *pq[2] = {&P.fam_q[2 * k], &P.fam_q[2 * k + 1]};
             const int32_t par[2] = {fa, mo};
             for (int s = 0; s < 2; s++) {
                 const int32_t p = par[s];
@@ -613,8 +614,7 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
             int32_t q1 = std::min(nn, q0 + kMTile);
             while (q1 > q0 + 8 && mf[q1 - 1] - mf[q0] >= kMaxTileFam) q1 = std::max(q0 + 8, (q1 - 1) & ~7);
             const int32_t f0 = mf[q0], f1 = mf[q1 - 1];
-            P.mtile_fam0.push_back(f0); P.mtile_nfam.push_back(f1 - f0 + 1);
-            P.mtile_m0.push_back(q0); P.mtile_cnt.push_back(q1 - q0);
+            for (int32_t v : {f0, f1 - f0 + 1, q0, q1 - q0}) P.mtile_desc.push_back(v);
             L.max_tile_fam = std::max(L.max_tile_fam, f1 - f0 + 1);
             L.n_mtiles++;
             q0 = q1;
@@ -631,6 +631,23 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
     }
     P.capacity = round_up(std::max<int64_t>((int64_t)slots.next_fresh * kSlotLine, 1), kPTile);
     for (int32_t g = 0; g < world; g++) P.rows_cap[g] = world > 1 ? std::max(rows[g].next_fresh, 1) : P.capacity;
+    if (std::getenv("GENLIB_PLAN_VERIFY")) {                 // debugging aid: index ranges the layer kernel relies on
+        for (int32_t t = 0; t < S; t++) {
+            const Layer &L = P.layers[t];
+            const int64_t qrows = (int64_t)L.n_live_tiles * kPTile;
+            for (int32_t f = 0; f < L.n_fam; f++)
+                for (int s2 = 0; s2 < 2; s2++) {
+                    const int32_t q = P.fam_q[2 * (L.fam_off + (size_t)f) + s2];
+                    const int32_t slot = s2 ? P.fam_pm[L.fam_off + f] : P.fam_pf[L.fam_off + f];
+                    if (q < -1 || q >= qrows || (q < 0) != (slot < 0)) { err = "verify: fam_q out of range in layer " + std::to_string(t) + " couple " + std::to_string(f) + " q " + std::to_string(q) + " qrows " + std::to_string(qrows) + " slot " + std::to_string(slot) + " rt_lo " + std::to_string(L.rt_lo); return GENLIB_EINVAL; }
+                }
+            for (int32_t j = 0; j < L.n_mtiles; j++) {
+                const int32_t *d = &P.mtile_desc[4 * (L.mtile_off + (size_t)j)];
+                if (d[0] < 0 || d[1] < 1 || d[1] > kMaxTileFam || d[0] + d[1] > L.n_fam || d[2] < 0 || d[3] < 1 || d[3] > kMTile || d[2] + d[3] > L.n_new || (d[2] & 7))
+                    { err = "verify: tile descriptor in layer " + std::to_string(t) + " tile " + std::to_string(j) + ": " + std::to_string(d[0]) + " " + std::to_string(d[1]) + " " + std::to_string(d[2]) + " " + std::to_string(d[3]); return GENLIB_EINVAL; }
+            }
+        }
+    }
     const size_t np = P.pro_ind.size();
     P.pro_slot.resize(np); P.pro_owner.resize(np); P.pro_lrow.resize(np);
     for (size_t u = 0; u < np; u++) {

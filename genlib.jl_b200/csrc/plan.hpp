@@ -71,12 +71,11 @@ struct Plan {
     std::vector<int32_t> mem_ind, mem_slot, mem_fam;   // family-major order inside a layer
     std::vector<int32_t> mem_rank;                     // sparse_phi schedules: the members' pedigree ranks (mem_ind = queue position)
     std::vector<int32_t> fam_pf, fam_pm, fam_start;    // parents as slots (-1 = none)
-    std::vector<int32_t> fam_qf, fam_qm;               // parents as rows of the layer kernel's strip buffers (-1 = none)
+    std::vector<int32_t> fam_q;                        // 2 per couple: father, mother as rows of the layer kernel's strip buffers (-1 = none)
     std::vector<uint8_t> flags;
     std::vector<int32_t> tile_map;                     // per tile of a layer's live range: its index among the live tiles (-1: hole)
     std::vector<int32_t> live_tiles;                   // the inverse: live tiles in order, | kTileCarried if a column is carried
-    std::vector<int32_t> mtile_fam0, mtile_nfam;       // couple range of a member tile
-    std::vector<int32_t> mtile_m0, mtile_cnt;          // first member and size of a member tile
+    std::vector<int32_t> mtile_desc;                   // 4 per member tile: first couple, couples, first member, members
     // ---- row sharding (world ranks; world == 1 puts everything on rank 0) ----
     // Couples are numbered rank-major inside a layer: rank g owns couples
     // [fam_base[g], fam_base[g+1]) and members [mem_base[g], mem_base[g+1]), and holds the
@@ -96,9 +95,9 @@ struct Plan {
     // cost more than the planning itself.
     template <class F> void each_array(F &&f) {
         f(layers); f(pro_ind); f(pro_slot); f(mem_ind); f(mem_rank); f(mem_slot); f(mem_fam); f(fam_pf); f(fam_pm);
-        f(fam_qf); f(fam_qm);
+        f(fam_q);
         f(fam_start); f(flags); f(tile_map); f(live_tiles);
-        f(mtile_fam0); f(mtile_nfam); f(mtile_m0); f(mtile_cnt); f(fam_base); f(mem_base); f(mem_lrow);
+        f(mtile_desc); f(fam_base); f(mem_base); f(mem_lrow);
         f(fam_pf_owner); f(fam_pm_owner); f(fam_pf_lrow); f(fam_pm_lrow); f(live_owner); f(live_lrow);
         f(pro_owner); f(pro_lrow); f(rows_cap);
     }
