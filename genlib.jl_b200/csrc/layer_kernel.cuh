@@ -88,15 +88,17 @@ __device__ __forceinline__ int ld_acquire_gpu(const int *p) {
     return v;
 }
 
-// the two groupings of the four frontier entries of a couple pair (see the header)
+// The two groupings of the four frontier entries of a couple pair (see the header).  hs(x, y) = RN(x/2 + y/2)
+// = RN(x + y) / 2 (scaling by a power of two commutes with rounding: binary64 cannot underflow here), so
+// hs(hs(a, b), hs(c, d)) = RN(RN(a + b) + RN(c + d)) / 4 bit for bit: three additions and one exact product.
 template <typename T, bool STORED>
 __device__ __forceinline__ void couple_pair(double ax, double ay, double cx, double cy, T &f_climbed, T &g_climbed) {
     if constexpr (STORED) {      // sparse_phi: every intermediate kinship is a stored Float32 (compute.jl:331, 363-395)
         f_climbed = (T)half_sum_stored((double)(T)half_sum_stored(ax, cx), (double)(T)half_sum_stored(ay, cy));
         g_climbed = (T)half_sum_stored((double)(T)half_sum_stored(ax, ay), (double)(T)half_sum_stored(cx, cy));
     } else {
-        f_climbed = (T)half_sum(half_sum(ax, cx), half_sum(ay, cy));
-        g_climbed = (T)half_sum(half_sum(ax, ay), half_sum(cx, cy));
+        f_climbed = (T)__dmul_rn(0.25, __dadd_rn(__dadd_rn(ax, cx), __dadd_rn(ay, cy)));
+        g_climbed = (T)__dmul_rn(0.25, __dadd_rn(__dadd_rn(ax, ay), __dadd_rn(cx, cy)));
     }
 }
 
@@ -152,9 +154,19 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
         }
         __syncthreads();
     };
-    auto count_off = [&](int *counter) {                           // this CTA's share of the strip is done
+    // A producer's share of the strip is done: its pairs were written with ordinary stores and will be read with
+    // bulk copies (async proxy), so every writer orders its stores against that proxy before the CTA's release.
+    auto produced = [&](int *counter) {
+        asm volatile("fence.proxy.async.global;" ::: "memory");
         __syncthreads();
         if (tid == 0) { __threadfence(); atomicAdd(counter, 1); }
+    };
+    // A consumer's share is done: its copies of the strip's pairs have landed in shared memory (it waited for
+    // them), which is all the producers that will overwrite the buffer need to know -- no fence: the rows it
+    // wrote are read by the next kernel at the earliest.
+    auto consumed = [&](int *counter) {
+        __syncthreads();
+        if (tid == 0) atomicAdd(counter, 1);
     };
 
     if ((int)blockIdx.x < S.n_prod) {
@@ -178,7 +190,7 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
         unsigned n_issued = 0, n_done = 0;
         const int rpw = 2 * ft / kLayerWarps;                      // rows each warp issues
         const int cpw = ft / kLayerWarps;                          // couples per warp for the member rows
-        const int f = lane % ft, hi = lane >> 3;
+        const int f = lane % ft;
         auto row_of = [&](int s) -> const T * {                    // thread tid < 2 sw: parent row tid of strip s
             const bool mo = tid >= sw;
             const int Fl = s * sw + (mo ? tid - sw : tid);
@@ -206,12 +218,14 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
                 const unsigned dst = sbase + slot * (unsigned)STAGE + (unsigned)(row * RB);
                 const int fi = pt * ft + (row < ft ? row : row - ft);
                 const T *src = s_row[(row < ft ? 0 : sw) + fi];
+                // (the stage was last READ with ordinary loads, before the barrier we come from: a bulk copy may
+                //  overwrite it without a proxy fence; only the zero fill below WRITES it through the generic proxy)
                 if (src) {
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic accesses of the stage
                     mbar_arrive_expect_tx(bar, ROWB);
                     bulk_g2s(dst, src + tile * kPTile, ROWB, bar);
                 } else {                                           // unknown parent: contributes 0 (compute.jl:111-126)
                     for (unsigned c = 0; c < ROWB; c += 16) zero16_shared(dst + c);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     mbar_arrive_expect_tx(bar, 0);
                 }
             }
@@ -237,7 +251,7 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
         uint32_t live4 = cs < NS ? tile_flags(tinfo) : 0u;
         while (cs < NS) {
             if (cs != cur) {                                       // count off the strips that are behind us
-                for (int s = max(cur, 0); s < cs; s++) count_off(done_p + s);
+                for (int s = max(cur, 0); s < cs; s++) produced(done_p + s);
                 cur = cs;
                 PROF_MARK(0);
                 wait_for(done_c + (cs - S.nbuf), cs >= S.nbuf ? S.n_cons : 0);    // the strip that used this buffer is consumed
@@ -257,25 +271,32 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
             const int tile = tinfo & (kTileCarried - 1);
             const unsigned char *st = dyn_smem + slot * STAGE;
             P2 *const Q = Qall + (size_t)(cs % S.nbuf) * S.qstride;
-            // ---- transposed and interleaved: Q[p][F] = (father row, mother row) at column p.  Lane = couple
-            //      (ft of them) x column; the column rotates with lane / 8 so that the 32 shared loads of a warp
-            //      hit 32 banks (rows are padded by 16 bytes). ----
+            // ---- transposed and interleaved: Q[p][F] = (father row, mother row) at column p.  A lane takes one
+            //      couple and four columns at a time: two 128-bit shared loads (a quarter warp spans the 32 banks:
+            //      rows are padded by 16 bytes), four 8-byte stores that the lanes of a warp lay side by side. ----
             {
-                const T *xr = reinterpret_cast<const T *>(st + f * RB);
-                const T *yr = reinterpret_cast<const T *>(st + (ft + f) * RB);
+                const int gpi = 32 / ft;                           // column groups a warp handles per step
+                const unsigned char *xr = st + f * RB, *yr = st + (ft + f) * RB;
                 P2 *q = Q + (size_t)lt * kPTile * sw + pt * ft + f;
-#pragma unroll
-                for (int gq = 0; gq < kPTile / 32; gq++) {
+                for (int gq = lane / ft; gq < 4; gq += gpi) {
                     const uint32_t w = __shfl_sync(0xffffffffu, live4, gq);
-                    for (int j = 0; j < ft / 8; j++) {
-                        const int c4 = (j + hi) & 3;
-                        const int col = warp * (kPTile / 8) + gq * 4 + c4;
-                        if ((w >> (8 * c4)) & kFlagLive) {
-                            CHECK(((size_t)lt * kPTile + col) * sw + pt * ft + f < (size_t)S.qstride);
-                            P2 v; v.x = xr[col]; v.y = yr[col];
-                            q[(size_t)col * sw] = v;
-                        }
+                    const int col = warp * (kPTile / 8) + gq * 4;
+                    T x[4], y[4];
+                    if constexpr (sizeof(T) == 4) {
+                        const float4 a4 = *reinterpret_cast<const float4 *>(xr + col * 4), b4 = *reinterpret_cast<const float4 *>(yr + col * 4);
+                        x[0] = a4.x; x[1] = a4.y; x[2] = a4.z; x[3] = a4.w; y[0] = b4.x; y[1] = b4.y; y[2] = b4.z; y[3] = b4.w;
+                    } else {
+                        const double2 a0 = *reinterpret_cast<const double2 *>(xr + col * 8), a1 = *reinterpret_cast<const double2 *>(xr + col * 8 + 16);
+                        const double2 b0 = *reinterpret_cast<const double2 *>(yr + col * 8), b1 = *reinterpret_cast<const double2 *>(yr + col * 8 + 16);
+                        x[0] = a0.x; x[1] = a0.y; x[2] = a1.x; x[3] = a1.y; y[0] = b0.x; y[1] = b0.y; y[2] = b1.x; y[3] = b1.y;
                     }
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; c4++)
+                        if ((w >> (8 * c4)) & kFlagLive) {
+                            CHECK(((size_t)lt * kPTile + col + c4) * sw + pt * ft + f < (size_t)S.qstride);
+                            P2 v; v.x = x[c4]; v.y = y[c4];
+                            q[(size_t)(col + c4) * sw] = v;
+                        }
                 }
             }
             PROF_MARK(4);
@@ -303,7 +324,7 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
             tinfo = tinfo_next;
             live4 = cs < NS ? tile_flags(tinfo) : 0u;
         }
-        for (int s = max(cur, 0); s < NS; s++) count_off(done_p + s);
+        for (int s = max(cur, 0); s < NS; s++) produced(done_p + s);
         PROF_MARK(0);
         PROF_FLUSH();
         return;
@@ -353,7 +374,17 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
             asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(base + (unsigned)((kMTile * (1 + arr) + 4 * c) * 4)), "l"(src) : "memory");
         }
     };
-    // the two parent-row segments of every couple of the tile -> stg: a warp copies a whole segment per step
+    // the two parent-row segments of every couple of the tile -> stg: one TMA bulk copy per segment, issued by
+    // the first 2 * kMaxTileFam threads (one each), all completing on one mbarrier phase per tile
+    const unsigned sbar = (unsigned)__cvta_generic_to_shared(&s_bar[0]);
+    if (tid == 0) {
+        mbar_init(sbar, 2 * kMaxTileFam);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    unsigned n_staged = 0, n_landed = 0;                           // tiles whose copies were issued / awaited
+#ifndef GENLIB_STAGE_TMA
+    // (16-byte cp.async through the LSU: the TMA unit is left to the producers, whose requests are as small)
     auto stage_tile = [&](const P2 *Q, int nfJ, int slot) {
         const int *qrow = meta + slot * kMetaInts;
         const int per = row_bytes / 16;                            // lanes per segment (4 ... 32)
@@ -368,7 +399,33 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
                 else zero16_shared(dst);                           // unknown parent: contributes 0
             }
         }
+        n_staged++;
     };
+    auto await_tile = [&]() { n_landed++; };                       // (cp_async_wait<0> by the caller covers the segments)
+#else
+    auto stage_tile = [&](const P2 *Q, int nfJ, int slot) {
+        if (tid < 2 * kMaxTileFam) {
+            const int q = tid < 2 * nfJ ? meta[slot * kMetaInts + tid] : -1;
+            CHECK(q >= -1 && (long long)q * sw < S.qstride);
+            const unsigned dst = stg_s + (unsigned)(tid * row_bytes);
+            if (q >= 0) {                                          // (write after read of the staging area: no proxy fence)
+                mbar_arrive_expect_tx(sbar, (unsigned)row_bytes);
+                bulk_g2s(dst, Q + (size_t)q * sw, (unsigned)row_bytes, sbar);
+            } else {
+                if (tid < 2 * nfJ) {                               // unknown parent: contributes 0
+                    for (int c = 0; c < row_bytes; c += 16) zero16_shared(dst + c);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                }
+                mbar_arrive_expect_tx(sbar, 0);
+            }
+        }
+        n_staged++;
+    };
+    auto await_tile = [&]() {                                      // all threads
+        if (!mbar_wait(sbar, n_landed & 1u)) atomicExch(err, 2);
+        n_landed++;
+    };
+#endif
 
     // ---- the strip's member rows: prefetched one strip ahead (registers), cached in shared memory ----
     int cur = -1;                                                  // strip this CTA is in
@@ -400,7 +457,7 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
     while (c0.s < NS) {
         const int s = c0.s, it = c0.it;
         if (s != cur) {
-            for (int t = max(cur, 0); t < s; t++) count_off(done_c + t);
+            for (int t = max(cur, 0); t < s; t++) consumed(done_c + t);
             cur = s;
             F0 = L.own_f0 + s * sw;
             nFs = min(sw, L.own_nf - s * sw);
@@ -463,8 +520,9 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
             cp_async_commit();
         }
         PROF_MARK(0);
-        cp_async_wait<0>();
-        __syncthreads();                                           // segments staged, the next tile's metadata landed, the previous item is written
+        cp_async_wait<0>();                                        // the next tile's metadata (own copies) ...
+        await_tile();                                              // ... and this tile's segments have landed
+        __syncthreads();                                           // for everybody; the previous item is written
         PROF_MARK(3);
         {
             const int fl = tid & (sw - 1), g0 = tid >> lsw, gstep = kLayerThreads >> lsw;
@@ -580,7 +638,7 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
         n_item++;
         PROF_MARK(6);
     }
-    for (int t = max(cur, 0); t < NS; t++) count_off(done_c + t);
+    for (int t = max(cur, 0); t < NS; t++) consumed(done_c + t);
     PROF_MARK(0);
     PROF_FLUSH();
 }
