@@ -266,7 +266,7 @@ LayerLaunch shape_layer(const Plan &P, int t, int rank, size_t es, int sm_count)
     while (sw > 8 && (size_t)q_rows * sw * pair * 3 > kStripBudget) sw >>= 1;
     const size_t strip_bytes = std::max<size_t>((size_t)q_rows * sw * pair, 256);
     s.sw = sw;
-    s.ft = std::min(sw, es == 4 ? 32 : 16);
+    s.ft = std::min(sw, std::max(8, env_int("GENLIB_FT", es == 4 ? 32 : 16)));
     s.nbuf = (int)std::max<size_t>(2, std::min<size_t>((size_t)std::max(2, env_int("GENLIB_MAX_NBUF", 6)), kStripBudget / strip_bytes));
     s.n_strips = (int)((own_nf + sw - 1) / sw);
     s.qstride = (int64_t)(strip_bytes / pair);
@@ -288,7 +288,7 @@ LayerLaunch shape_layer(const Plan &P, int t, int rank, size_t es, int sm_count)
     s.rot_p = s.n_prod > 0 ? s.n_pitems % s.n_prod : 0;
     s.rot_c = s.n_citems % s.n_cons;
     const size_t stage = (size_t)2 * s.ft * (kPTile * es + 16);
-    s.stages = (int)std::max<size_t>(2, std::min<size_t>(kMaxStages, ((size_t)100 << 10) / stage));
+    s.stages = (int)std::max<size_t>(2, std::min<size_t>((size_t)std::min(kMaxStages, env_int("GENLIB_STAGES", kMaxStages)), ((size_t)100 << 10) / stage));
     out.smem = std::max((size_t)s.stages * stage, layer_consumer_bytes(sw, es));
     out.grid = s.n_prod + s.n_cons;
     s.timeout_cycles = (long long)4e9;                     // ~2 s: a lost dependency becomes GENLIB_ECUDA, not a hang

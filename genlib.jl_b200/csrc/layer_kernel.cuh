@@ -383,7 +383,7 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
     }
     __syncthreads();
     unsigned n_staged = 0, n_landed = 0;                           // tiles whose copies were issued / awaited
-#ifndef GENLIB_STAGE_TMA
+#ifdef GENLIB_STAGE_LDGSTS
     // (16-byte cp.async through the LSU: the TMA unit is left to the producers, whose requests are as small)
     auto stage_tile = [&](const P2 *Q, int nfJ, int slot) {
         const int *qrow = meta + slot * kMetaInts;
@@ -404,15 +404,16 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
     auto await_tile = [&]() { n_landed++; };                       // (cp_async_wait<0> by the caller covers the segments)
 #else
     auto stage_tile = [&](const P2 *Q, int nfJ, int slot) {
-        if (tid < 2 * kMaxTileFam) {
-            const int q = tid < 2 * nfJ ? meta[slot * kMetaInts + tid] : -1;
+        if (lane < 2 * kMaxTileFam / kLayerWarps) {                // 16 lanes of every warp: the issue is serial per warp
+            const int r = warp * (2 * kMaxTileFam / kLayerWarps) + lane;
+            const int q = r < 2 * nfJ ? meta[slot * kMetaInts + r] : -1;
             CHECK(q >= -1 && (long long)q * sw < S.qstride);
-            const unsigned dst = stg_s + (unsigned)(tid * row_bytes);
+            const unsigned dst = stg_s + (unsigned)(r * row_bytes);
             if (q >= 0) {                                          // (write after read of the staging area: no proxy fence)
                 mbar_arrive_expect_tx(sbar, (unsigned)row_bytes);
                 bulk_g2s(dst, Q + (size_t)q * sw, (unsigned)row_bytes, sbar);
             } else {
-                if (tid < 2 * nfJ) {                               // unknown parent: contributes 0
+                if (r < 2 * nfJ) {                                 // unknown parent: contributes 0
                     for (int c = 0; c < row_bytes; c += 16) zero16_shared(dst + c);
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 }
