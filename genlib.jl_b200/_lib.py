@@ -86,6 +86,8 @@ SYMBOLS = {
     "genlib_plan_proband_slots": (C.c_int, [_P, _P]),
     "genlib_phi": (C.c_int, [C.c_int32, _P, _P, C.c_int32, _P, _P, C.c_int, C.c_int, C.c_int,
                              C.POINTER(Stats)]),
+    "genlib_phi_multi": (C.c_int, [C.c_int32, _P, _P, C.c_int32, _P, _P, C.c_int, C.c_int, C.c_int32, _P,
+                                   C.POINTER(Stats)]),
     "genlib_engine_create": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P)]),
     "genlib_engine_destroy": (None, [_P]),
     "genlib_engine_run": (C.c_int, [_P, C.c_int]),

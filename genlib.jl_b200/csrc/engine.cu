@@ -14,6 +14,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/genlib_cuda.h"
@@ -197,7 +198,8 @@ struct genlib_engine {
     long long barrier_timeout = (long long)20e9;   // cycles an inter-GPU barrier may wait (GENLIB_BARRIER_TIMEOUT_S)
     DevBuf<int32_t> mem_ind, mem_slot, mem_fam, mem_lrow, fam_pf, fam_pm, fam_q, fam_pf_lrow, fam_pm_lrow, fam_start,
         mt_desc, pro_slot, own_pro_row, live_lrow, tile_map, live_tiles;
-    DevBuf<int8_t> fam_pf_owner, fam_pm_owner, live_owner;
+    DevBuf<int8_t> fam_pf_owner, fam_pm_owner, live_owner, pro_owner;
+    DevBuf<int32_t> pro_lrow;
     DevBuf<int32_t> mem_rank;
     DevBuf<uint8_t> flags;
     DevBuf<double> acc;
@@ -314,7 +316,8 @@ size_t engine_bytes(const Plan &P, int numerics, int g, int sm_count = 148) {
          DevBuf<int32_t>::padded(P.live_lrow.size()) + DevBuf<int32_t>::padded(P.tile_map.size()) +
          DevBuf<int32_t>::padded(P.live_tiles.size()) +
          2 * DevBuf<int8_t>::padded(P.fam_pf.size()) +
-         DevBuf<int8_t>::padded(P.live_owner.size()) + DevBuf<uint8_t>::padded(P.flags.size()) + DevBuf<double>::padded(4);
+         DevBuf<int8_t>::padded(P.live_owner.size()) + DevBuf<uint8_t>::padded(P.flags.size()) + DevBuf<double>::padded(4) +
+         DevBuf<int8_t>::padded(P.pro_owner.size()) + DevBuf<int32_t>::padded(P.pro_lrow.size());
     return b;
 }
 
@@ -454,6 +457,44 @@ int fetch_rows(genlib_engine &E, O *out) {
     return GENLIB_OK;
 }
 
+// Output rows [u0, u1) of the proband matrix, whoever owns them (peer reads), to host memory at their
+// final place: out + u * n.  Used when one process drives all devices (genlib_phi_multi).
+template <typename T, typename O>
+int fetch_block(genlib_engine &E, int32_t u0, int32_t u1, O *out) {
+    const Plan &P = E.plan->p;
+    const int32_t n = P.n_unique;
+    if (n == 0 || u1 <= u0) return GENLIB_OK;
+    const size_t row_bytes = (size_t)n * sizeof(O);
+    int32_t rows_per = (int32_t)std::max<size_t>(1, std::min<size_t>((size_t)(u1 - u0), kFetchStageBytes / row_bytes));
+    if ((size_t)rows_per * row_bytes > kFetchStageBytes) return fail(GENLIB_EINVAL, "proband row does not fit the staging buffer");
+    rows_per = std::min(rows_per, 65535);
+    O *stage[2] = {reinterpret_cast<O *>(E.fetch_stage[0]), reinterpret_cast<O *>(E.fetch_stage[1])};
+    cudaEvent_t done[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
+    cudaError_t ce = cudaSuccess;
+    for (int b = 0; b < 2 && ce == cudaSuccess; b++) {
+        ce = cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming);
+    }
+    int blk = 0;
+    for (int32_t r0 = u0; r0 < u1 && ce == cudaSuccess; r0 += rows_per, blk++) {
+        const int b = blk & 1;
+        const int32_t nr = std::min(rows_per, u1 - r0);
+        if (blk >= 2 && (ce = cudaStreamWaitEvent(E.stream, copied[b], 0)) != cudaSuccess) break;
+        dim3 grid((unsigned)std::min<int32_t>((n + 255) / 256, 64), (unsigned)nr);
+        gather_peer_kernel<T, O><<<grid, 256, 0, E.stream>>>(E.peers, P.capacity, E.pro_owner.p, E.pro_lrow.p, E.pro_slot.p, n, r0, nr, stage[b]);
+        cudaEventRecord(done[b], E.stream);
+        cudaStreamWaitEvent(E.copy_stream, done[b], 0);
+        ce = cudaMemcpyAsync(out + (size_t)r0 * n, stage[b], (size_t)nr * row_bytes, cudaMemcpyDeviceToHost, E.copy_stream);
+        cudaEventRecord(copied[b], E.copy_stream);
+    }
+    const cudaError_t e1 = cudaStreamSynchronize(E.stream), e2 = cudaStreamSynchronize(E.copy_stream);
+    for (int b = 0; b < 2; b++) { if (done[b]) cudaEventDestroy(done[b]); if (copied[b]) cudaEventDestroy(copied[b]); }
+    if (ce != cudaSuccess || e1 != cudaSuccess || e2 != cudaSuccess)
+        return fail(GENLIB_ECUDA, std::string("proband fetch failed: ") + cudaGetErrorString(ce != cudaSuccess ? ce : e1 != cudaSuccess ? e1 : e2));
+    E.stats.d2h_bytes += (int64_t)(u1 - u0) * (int64_t)row_bytes;
+    return GENLIB_OK;
+}
+
 // Compulsory traffic of every layer on this rank (genlib_layer_info), from the plan.
 void account_layers(genlib_engine &E) {
     if (E.info_ready) return;
@@ -567,6 +608,7 @@ int create_engine(const genlib_plan *plan, int numerics, int device, int rank, g
         E->fam_pf_owner.place(cur, P.fam_pf_owner.size()); E->fam_pm_owner.place(cur, P.fam_pm_owner.size());
         E->live_owner.place(cur, P.live_owner.size());
         E->flags.place(cur, P.flags.size()); E->acc.place(cur, 4);
+        E->pro_owner.place(cur, P.pro_owner.size()); E->pro_lrow.place(cur, P.pro_lrow.size());
         if ((size_t)(cur - base) > need) return fail(GENLIB_EINVAL, "internal: arena layout overflow");
         if ((size_t)(static_cast<unsigned char *>(E->A) - base) != off_A())
             return fail(GENLIB_EINVAL, "internal: peer-visible arena offsets drifted");
@@ -616,6 +658,8 @@ int create_engine(const genlib_plan *plan, int numerics, int device, int rank, g
     CU(E->tile_map.upload(P.tile_map, E->stream));
     CU(E->live_tiles.upload(P.live_tiles, E->stream));
     CU(E->flags.upload(P.flags, E->stream));
+    CU(E->pro_owner.upload(P.pro_owner, E->stream));
+    CU(E->pro_lrow.upload(P.pro_lrow, E->stream));
     CU(cudaStreamSynchronize(E->stream));
 #ifdef GENLIB_PROFILE
     CU(cudaMalloc(&E->prof, 8 * 2 * 160 * sizeof(long long)));
@@ -1002,6 +1046,92 @@ int genlib_engine_read_block(genlib_engine *eng, int32_t n_slots, const int32_t 
     CU(cudaMemcpyAsync(out, dout, (size_t)n_slots * n_slots * sizeof(double), cudaMemcpyDeviceToHost, eng->stream));
     CU(cudaStreamSynchronize(eng->stream));
     cudaFree(dslots); cudaFree(dout);
+    return GENLIB_OK;
+}
+
+int genlib_phi_multi(int32_t n, const int32_t *father, const int32_t *mother, int32_t n_pro,
+                     const int32_t *proband, void *out, int out_dtype, int numerics, int32_t n_dev,
+                     const int32_t *devices, genlib_stats *stats) {
+    if (n_dev < 1 || n_dev > kMaxWorld || !devices) return fail(GENLIB_EINVAL, "genlib_phi_multi: 1 .. 16 devices");
+    if (out_dtype != GENLIB_F32 && out_dtype != GENLIB_F64) return fail(GENLIB_EINVAL, "unknown out_dtype");
+    if (n_dev == 1) return genlib_phi(n, father, mother, n_pro, proband, out, out_dtype, numerics, devices[0], stats);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(GENLIB_ECUDA, "no CUDA device: libgenlib_cuda has no CPU fallback");
+    for (int g = 0; g < n_dev; g++) {
+        if (devices[g] < 0 || devices[g] >= ndev) return fail(GENLIB_EINVAL, "genlib_phi_multi: no such device");
+        for (int h = 0; h < g; h++) if (devices[h] == devices[g]) return fail(GENLIB_EINVAL, "genlib_phi_multi: a device is listed twice");
+    }
+    genlib_plan *plan = nullptr;
+    int rc = genlib_plan_create(n, father, mother, n_pro, proband, n_dev, &plan);       // ONE plan for all ranks
+    if (rc != GENLIB_OK) return rc;
+    struct PlanGuard { genlib_plan *p; ~PlanGuard() { genlib_plan_destroy(p); } } pguard{plan};
+    if (plan->p.n_unique == 0) {
+        if (stats) { std::memset(stats, 0, sizeof *stats); stats->ms_plan = plan->ms_plan; }
+        return GENLIB_OK;
+    }
+    if (!out) return fail(GENLIB_EINVAL, "genlib_phi_multi: out is null");
+    int prev_dev = -1;
+    cudaGetDevice(&prev_dev);
+    struct DevRestore { int d; ~DevRestore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_dev};
+    // every device sees every other device's memory (NVLink peer access)
+    for (int g = 0; g < n_dev; g++) {
+        if (cudaSetDevice(devices[g]) != cudaSuccess) return fail(GENLIB_ECUDA, "cudaSetDevice failed");
+        for (int h = 0; h < n_dev; h++) {
+            if (h == g) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, devices[g], devices[h]);
+            if (!can) return fail(GENLIB_ECOMM, "devices " + std::to_string(devices[g]) + " and " + std::to_string(devices[h]) + " have no peer access");
+            const cudaError_t ce = cudaDeviceEnablePeerAccess(devices[h], 0);
+            if (ce != cudaSuccess && ce != cudaErrorPeerAccessAlreadyEnabled) return fail(GENLIB_ECOMM, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(ce));
+            cudaGetLastError();
+        }
+    }
+    // one host thread per device: engine (upload of the plan), then, all together, the layers and the fetch
+    std::vector<genlib_engine *> eng((size_t)n_dev, nullptr);
+    std::vector<int> status((size_t)n_dev, GENLIB_OK);
+    std::vector<std::string> message((size_t)n_dev);
+    auto on_all = [&](auto &&fn) {
+        std::vector<std::thread> th;
+        for (int g = 0; g < n_dev; g++)
+            th.emplace_back([&, g] { status[(size_t)g] = fn(g); if (status[(size_t)g] != GENLIB_OK) message[(size_t)g] = g_err; });
+        for (auto &t : th) t.join();
+        for (int g = 0; g < n_dev; g++) if (status[(size_t)g] != GENLIB_OK) return fail(status[(size_t)g], "device " + std::to_string(devices[g]) + ": " + message[(size_t)g]);
+        return (int)GENLIB_OK;
+    };
+    struct EngGuard { std::vector<genlib_engine *> &e; ~EngGuard() { for (auto *x : e) genlib_engine_destroy(x); } } eguard{eng};
+    rc = on_all([&](int g) { return create_engine(plan, numerics, devices[g], g, &eng[(size_t)g]); });
+    if (rc != GENLIB_OK) return rc;
+    for (int g = 0; g < n_dev; g++) {                           // plain peer pointers instead of IPC mappings
+        for (int h = 0; h < n_dev; h++) { eng[(size_t)g]->peers.A[h] = eng[(size_t)h]->A; eng[(size_t)g]->bars.flags[h] = eng[(size_t)h]->bar_flags; }
+        eng[(size_t)g]->attached = true;
+    }
+    rc = on_all([&](int g) { return genlib_engine_run(eng[(size_t)g], 0); });
+    if (rc != GENLIB_OK) return rc;
+    const int32_t nu = plan->p.n_unique;
+    const double t0 = now_ms();
+    rc = on_all([&](int g) {                                    // contiguous row blocks, one PCIe link each
+        genlib_engine &E = *eng[(size_t)g];
+        DeviceGuard guard;
+        if (int r = guard.enter(E.device)) return r;
+        const int32_t u0 = (int32_t)((int64_t)nu * g / n_dev), u1 = (int32_t)((int64_t)nu * (g + 1) / n_dev);
+        if (numerics == GENLIB_NUMERICS_FP64)
+            return out_dtype == GENLIB_F64 ? fetch_block<double, double>(E, u0, u1, (double *)out) : fetch_block<double, float>(E, u0, u1, (float *)out);
+        return out_dtype == GENLIB_F64 ? fetch_block<float, double>(E, u0, u1, (double *)out) : fetch_block<float, float>(E, u0, u1, (float *)out);
+    });
+    if (rc != GENLIB_OK) return rc;
+    if (stats) {
+        *stats = eng[0]->stats;
+        stats->ms_fetch = now_ms() - t0;
+        for (int g = 1; g < n_dev; g++) {
+            stats->ms_kernels = std::max(stats->ms_kernels, eng[(size_t)g]->stats.ms_kernels);
+            stats->ms_upload = std::max(stats->ms_upload, eng[(size_t)g]->stats.ms_upload);
+            stats->device_bytes = std::max(stats->device_bytes, eng[(size_t)g]->stats.device_bytes);
+            stats->h2d_bytes += eng[(size_t)g]->stats.h2d_bytes;
+            stats->d2h_bytes += eng[(size_t)g]->stats.d2h_bytes;
+            stats->kernel_launches += eng[(size_t)g]->stats.kernel_launches;
+        }
+    }
     return GENLIB_OK;
 }
 

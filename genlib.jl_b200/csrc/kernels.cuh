@@ -165,6 +165,21 @@ __global__ void gather_kernel(const T *__restrict__ A, int64_t ld, const int32_t
         dst[v] = (O)row[cols[v]];
 }
 
+// The same for ANY proband row of a sharded frontier: row u lives on rank owner[u] at local row lrow[u]
+// (a peer read over NVLink unless it is this rank's own).  One process, several devices: every device
+// assembles a contiguous block of output rows and copies it to the host over its own PCIe link.
+template <typename T, typename O>
+__global__ void gather_peer_kernel(PeerTable PT, int64_t ld, const int8_t *__restrict__ owner, const int32_t *__restrict__ lrow,
+                                   const int32_t *__restrict__ cols, int32_t P, int32_t row0, int32_t nrows,
+                                   O *__restrict__ out) {
+    if (blockIdx.y >= (unsigned)nrows) return;
+    const int u = row0 + blockIdx.y;
+    const T *row = static_cast<const T *>(PT.A[owner[u]]) + (int64_t)lrow[u] * ld;
+    O *dst = out + (size_t)blockIdx.y * P;
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < P; v += gridDim.x * blockDim.x)
+        dst[v] = (O)row[cols[v]];
+}
+
 // sum and trace of the proband block, binary64 accumulation (phiMean, compute.jl:454-459);
 // one rank: rows == cols == the proband slots
 template <typename T>

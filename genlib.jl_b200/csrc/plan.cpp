@@ -10,6 +10,8 @@
 #include <thread>
 
 #include "../../include/genlib_cuda.h"
+#include <chrono>
+#include <cstdio>
 
 namespace genlib {
 
@@ -175,6 +177,9 @@ int build_plan(int32_t n, const int32_t *father, const int32_t *mother, const in
 
 static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const int32_t *mother, const int64_t *ids,
                            int32_t n_pro, const int32_t *proband, int32_t world, int schedule, Plan &P, std::string &err) {
+    const bool timing = std::getenv("GENLIB_PLAN_TIMING") != nullptr;     // debugging aid: phase times on stderr
+    auto t_last = std::chrono::steady_clock::now();
+#define PLAN_T(name) do { if (timing) { auto t_now = std::chrono::steady_clock::now(); std::fprintf(stderr, "[plan] %-12s %.2f ms\n", name, std::chrono::duration<double, std::milli>(t_now - t_last).count()); t_last = t_now; } } while (0)
     P.reset();
     if (schedule != kSchedulePhi && !sparse_schedule(schedule)) { err = "unknown schedule"; return GENLIB_EINVAL; }
     P.schedule = schedule;
@@ -206,6 +211,7 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
     }
     P.n_unique = (int32_t)P.pro_ind.size();
     if (P.n_unique == 0) return GENLIB_OK;
+    PLAN_T("validate");
 
     // One reverse sweep (children have larger ranks, so an individual is final when it is visited):
     //   h     height above the probands = longest downward path to one (compute.jl:236-241 builds
@@ -300,6 +306,7 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
             for (int32_t p : par) if (p >= 0 && pre[p].minch > pre[x].h) pre[p].minch = pre[x].h;
         }
     }
+    PLAN_T("heights");
     const int32_t S = hmax + 1;
     std::vector<int32_t> &count = W.count; count.assign((size_t)S + 1, 0);
     for (int32_t k = 0; k < S; k++) count[S - 1 - k] = hist[k];
@@ -334,6 +341,7 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         for (int32_t k = 0; k < S; k++) { a += d_cut[k]; b += d_both[k]; cut_size[k] = (int32_t)a; both_size[k] = (int32_t)b; }
     }
 
+    PLAN_T("buckets");
     if (world > 127) { err = "at most 127 ranks"; return GENLIB_EINVAL; }
     P.layers.resize(S);
     {   // upper bounds (untouched reserve costs nothing): members + alignment padding, couples + rank padding
@@ -629,6 +637,7 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         for (int32_t q = 0; q < nn; q++) next_live.push_back(X[q]);
         live.swap(next_live);
     }
+    PLAN_T("layers");
     P.capacity = round_up(std::max<int64_t>((int64_t)slots.next_fresh * kSlotLine, 1), kPTile);
     for (int32_t g = 0; g < world; g++) P.rows_cap[g] = world > 1 ? std::max(rows[g].next_fresh, 1) : P.capacity;
     if (std::getenv("GENLIB_PLAN_VERIFY")) {                 // debugging aid: index ranges the layer kernel relies on

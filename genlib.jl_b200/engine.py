@@ -222,8 +222,9 @@ class PinnedMatrix:
 
 def phi(pedigree: Pedigree, probandIDs=None, *, verbose: bool = False, compute: bool = True,
         numerics="reference", dtype=np.float32, device: int = -1, out: Optional[np.ndarray] = None,
-        return_stats: bool = False):
-    """gen.phi(pedigree, probandIDs; verbose, compute) on the B200 engine."""
+        return_stats: bool = False, devices=None):
+    """gen.phi(pedigree, probandIDs; verbose, compute) on the B200 engine.  `devices=[0, 1, ...]` shards
+    the frontier over several GPUs of the box from this one process (genlib_phi_multi)."""
     IDs = pro(pedigree) if probandIDs is None else np.asarray(probandIDs, np.int64)
     ranks = pedigree.rank_of(IDs)                       # KeyError, like pedigree[ID]
     plan = Plan(pedigree.father, pedigree.mother, ranks)
@@ -239,6 +240,13 @@ def phi(pedigree: Pedigree, probandIDs=None, *, verbose: bool = False, compute: 
     if verbose:
         for line in plan.verbose_lines(running=True):
             print(line)
+    if devices is not None and len(devices) > 1:
+        if out is None:
+            out = np.empty((n, n), dtype)
+        res, stats = phi_arrays(pedigree.father, pedigree.mother, ranks, numerics=numerics, out=out, devices=devices)
+        return (res, stats) if return_stats else res
+    if devices is not None and len(devices) == 1:
+        device = int(devices[0])
     eng = Engine(plan, numerics=numerics, device=device)
     try:
         eng.run()
@@ -297,8 +305,9 @@ def phi_distributed(pedigree: Pedigree, probandIDs=None, *, numerics="reference"
 
 
 def phi_arrays(father, mother, proband_ranks, *, numerics="reference", dtype=np.float32,
-               device: int = -1, out: Optional[np.ndarray] = None):
-    """One-shot C-ABI call `genlib_phi` on flat arrays (what the Julia shim ccalls)."""
+               device: int = -1, out: Optional[np.ndarray] = None, devices=None):
+    """One-shot C-ABI call `genlib_phi` on flat arrays (what the Julia shim ccalls); with
+    `devices=[...]` the same through `genlib_phi_multi` (one process, several GPUs)."""
     father = np.ascontiguousarray(father, np.int32)
     mother = np.ascontiguousarray(mother, np.int32)
     pr = np.ascontiguousarray(proband_ranks, np.int32)
@@ -306,8 +315,14 @@ def phi_arrays(father, mother, proband_ranks, *, numerics="reference", dtype=np.
     if out is None:
         out = np.empty((n_unique, n_unique), dtype)
     st = Stats()
-    check(lib().genlib_phi(len(father), ptr(father), ptr(mother), len(pr), ptr(pr), ptr(out),
-                           _lib.DTYPES[np.dtype(out.dtype)], _lib.NUMERICS[numerics], device, C.byref(st)))
+    if devices is not None:
+        dv = np.ascontiguousarray(devices, np.int32)
+        check(lib().genlib_phi_multi(len(father), ptr(father), ptr(mother), len(pr), ptr(pr), ptr(out),
+                                     _lib.DTYPES[np.dtype(out.dtype)], _lib.NUMERICS[numerics], len(dv), ptr(dv),
+                                     C.byref(st)))
+    else:
+        check(lib().genlib_phi(len(father), ptr(father), ptr(mother), len(pr), ptr(pr), ptr(out),
+                               _lib.DTYPES[np.dtype(out.dtype)], _lib.NUMERICS[numerics], device, C.byref(st)))
     return out, st.as_dict()
 
 

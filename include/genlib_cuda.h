@@ -199,6 +199,15 @@ int genlib_phi(int32_t n, const int32_t *father, const int32_t *mother, int32_t 
                const int32_t *proband, void *out, int out_dtype, int numerics, int device,
                genlib_stats *stats);
 
+/* The same call on SEVERAL devices of one box, from one process (`n_dev, devices`):
+ * one plan, the frontier's rows sharded over the devices, one host thread per device, NVLink peer
+ * access between all of them (cudaDeviceEnablePeerAccess), no MPI / IPC.  Every device assembles a
+ * contiguous block of output rows and copies it into `out` over its own PCIe link.  The result is
+ * bitwise the single-device one.  n_dev = 1 is genlib_phi on devices[0]. */
+int genlib_phi_multi(int32_t n, const int32_t *father, const int32_t *mother, int32_t n_pro,
+                     const int32_t *proband, void *out, int out_dtype, int numerics, int32_t n_dev,
+                     const int32_t *devices, genlib_stats *stats);
+
 /* ---- handle API: keep the schedule on the device, run, fetch ---------------
  * (what the benchmark and a multi-call Julia session use) */
 int genlib_engine_create(const genlib_plan *plan, int numerics, int device, genlib_engine **out);

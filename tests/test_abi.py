@@ -86,7 +86,11 @@ def test_plain_c_client_on_gpu(tmp_path):
     exe, csv = _build_c_client(tmp_path)
     want = np.array([[0.591796875, 0.37109375, 0.072265625], [0.37109375, 0.591796875, 0.072265625],
                      [0.072265625, 0.072265625, 0.53515625]])                  # test/runtests.jl:51-52
-    for args in ([exe, csv], [exe, csv, "sparse"]):
+    import genlib_b200 as gen
+    runs = [[exe, csv], [exe, csv, "sparse"], [exe, csv, "devices=0"]]
+    if gen.lib().genlib_device_count() >= 2:                                   # one process, two GPUs (genlib_phi_multi)
+        runs.append([exe, csv, "devices=0,1"])
+    for args in runs:
         res = subprocess.run(args, capture_output=True, text=True)
         assert res.returncode == 0, res.stderr
         got = np.array([[float(v) for v in line.split()] for line in res.stdout.splitlines()])

@@ -226,6 +226,29 @@ def test_multi_gpu_equals_single_gpu(gen):
     assert res.returncode == 0 and "dist_check: all equal" in res.stdout, (res.stdout + res.stderr)[-3000:]
 
 
+def test_one_process_several_devices(gen, ob):
+    """genlib_phi_multi (one process, one host thread per device, NVLink peer access) == one device,
+    bit for bit; on a 1-GPU box the call degenerates to genlib_phi."""
+    ngpu = gen.lib().genlib_device_count()
+    devs = list(range(min(ngpu, 4)))
+    ped = gen.genealogy(gen.genea140)
+    want = gen.phi(ped)
+    assert_bit_equal(gen.phi(ped, devices=devs), want)
+    assert_bit_equal(gen.phi(ped, devices=devs[::-1], numerics="fp64"), want)
+    s = gen.synth.config("C3", 0.05)
+    ped = gen.genealogy(s.as_columns())
+    want = ob.OraclePedigree.from_arrays(s.ind, s.father, s.mother, s.sex).phi(s.probands)
+    got, stats = gen.phi(ped, s.probands, devices=devs, return_stats=True)
+    assert_bit_equal(got, want)
+    assert stats["d2h_bytes"] == got.nbytes
+    rng = np.random.default_rng(77)
+    ped = gen.genealogy(random_pedigree(rng, 900, 12, p_single=0.15, p_none=0.03, window=60))
+    pro = rng.permutation(ped.ids)[:150]
+    assert_bit_equal(gen.phi(ped, pro, devices=devs), gen.phi(ped, pro))
+    with pytest.raises(Exception):
+        gen.phi(ped, pro, devices=[0, 0])
+
+
 def test_inbreeding_f(gen, ob):
     """gen.f (src/compute.jl:500-511) from one engine sweep; known answers of test/runtests.jl:47-48."""
     ped = gen.genealogy(gen.geneaJi)
