@@ -99,6 +99,7 @@ SYMBOLS = {
     "genlib_engine_ipc_export": (C.c_int, [_P, _P]),
     "genlib_engine_ipc_attach": (C.c_int, [_P, _P, C.c_size_t]),
     "genlib_engine_phi_mean": (C.c_int, [_P, C.POINTER(C.c_double)]),
+    "genlib_engine_row_sums": (C.c_int, [_P, _P]),
     "genlib_engine_set_layer_limit": (C.c_int, [_P, C.c_int32]),
     "genlib_engine_read_block": (C.c_int, [_P, C.c_int32, _P, _P]),
 }

@@ -262,10 +262,12 @@ LayerLaunch shape_layer(const Plan &P, int t, int rank, size_t es, int sm_count)
     const int64_t rt_rows = live ? L.rt_rows : 0;
     const int64_t q_rows = live ? (int64_t)L.n_live_tiles * kPTile : 0;     // rows of a strip buffer
     const size_t pair = 2 * es;
-    // strip width: the widest one whose buffers fit the persisting part of L2 three times (and whose
-    // staged tile fits shared memory: 128 parent-row segments of sw pairs <= 64 KB)
+    // strip width: the widest one whose buffers fit the persisting part of L2 at least `min_buf` times (and
+    // whose staged tile fits shared memory: 128 parent-row segments of sw pairs <= 64 KB).  A wide strip
+    // amortises the per-tile work of the consumers; more buffers give the producers more room to run ahead.
+    const size_t min_buf = (size_t)std::max(2, env_int("GENLIB_MIN_NBUF", 2));
     int sw = std::min(es == 4 ? kMaxStrip : kMaxStrip / 2, std::max(8, env_int("GENLIB_MAX_SW", kMaxStrip)));
-    while (sw > 8 && (size_t)q_rows * sw * pair * 3 > kStripBudget) sw >>= 1;
+    while (sw > 8 && (size_t)q_rows * sw * pair * min_buf > kStripBudget) sw >>= 1;
     const size_t strip_bytes = std::max<size_t>((size_t)q_rows * sw * pair, 256);
     s.sw = sw;
     s.ft = std::min(sw, std::max(8, env_int("GENLIB_FT", es == 4 ? 32 : 16)));
@@ -993,25 +995,42 @@ int genlib_engine_fetch(genlib_engine *eng, void *out, int out_dtype) {
     return rc;
 }
 
-int genlib_engine_phi_mean(genlib_engine *eng, double *out) {
-    if (!eng || !out) return fail(GENLIB_EINVAL, "null argument");
-    if (!eng->ran) return fail(GENLIB_EINVAL, "genlib_engine_phi_mean before genlib_engine_run");
-    if (eng->world != 1) return fail(GENLIB_EINVAL, "genlib_engine_phi_mean: single-rank engines only");
+int genlib_engine_row_sums(genlib_engine *eng, double *out) {
+    if (!eng || (!out && !eng->own_pro.empty())) return fail(GENLIB_EINVAL, "null argument");
+    if (!eng->ran) return fail(GENLIB_EINVAL, "genlib_engine_row_sums before genlib_engine_run");
     DeviceGuard guard;
     if (int rc = guard.enter(eng->device)) return rc;
     const Plan &P = eng->plan->p;
-    const int32_t n = P.n_unique;
-    if (n < 2) { *out = 0.0; return GENLIB_OK; }
-    CU(cudaMemsetAsync(eng->acc.p, 0, 2 * sizeof(double), eng->stream));
-    const unsigned grid = (unsigned)std::min<int32_t>(n, 148 * 8);
-    if (eng->numerics == GENLIB_NUMERICS_FP64)
-        mean_kernel<double><<<grid, kThreads, 0, eng->stream>>>((const double *)eng->A, P.capacity, eng->pro_slot.p, n, eng->acc.p);
-    else
-        mean_kernel<float><<<grid, kThreads, 0, eng->stream>>>((const float *)eng->A, P.capacity, eng->pro_slot.p, n, eng->acc.p);
-    double h[2] = {0, 0};
-    CU(cudaMemcpyAsync(h, eng->acc.p, sizeof h, cudaMemcpyDeviceToHost, eng->stream));
-    CU(cudaStreamSynchronize(eng->stream));
-    *out = (h[0] - h[1]) / ((double)n * n - n);
+    const int32_t n = P.n_unique, nown = (int32_t)eng->own_pro.size();
+    if (nown == 0) return GENLIB_OK;
+    double *dsum = nullptr;
+    int32_t *didx = nullptr;
+    CU(cudaMalloc(&dsum, (size_t)nown * 2 * sizeof(double)));
+    if (cudaMalloc(&didx, (size_t)nown * sizeof(int32_t)) != cudaSuccess) { cudaFree(dsum); return fail(GENLIB_ENOMEM, "out of device memory"); }
+    cudaError_t ce = cudaMemcpyAsync(didx, eng->own_pro.data(), (size_t)nown * sizeof(int32_t), cudaMemcpyHostToDevice, eng->stream);
+    if (ce == cudaSuccess) {
+        if (eng->numerics == GENLIB_NUMERICS_FP64)
+            rowsum_kernel<double><<<(unsigned)nown, kThreads, 0, eng->stream>>>((const double *)eng->A, P.capacity, eng->own_pro_row.p, didx, eng->pro_slot.p, n, dsum);
+        else
+            rowsum_kernel<float><<<(unsigned)nown, kThreads, 0, eng->stream>>>((const float *)eng->A, P.capacity, eng->own_pro_row.p, didx, eng->pro_slot.p, n, dsum);
+        ce = cudaMemcpyAsync(out, dsum, (size_t)nown * 2 * sizeof(double), cudaMemcpyDeviceToHost, eng->stream);
+    }
+    const cudaError_t e2 = cudaStreamSynchronize(eng->stream);
+    cudaFree(dsum); cudaFree(didx);
+    if (ce != cudaSuccess || e2 != cudaSuccess) return fail(GENLIB_ECUDA, std::string("row sums: ") + cudaGetErrorString(ce != cudaSuccess ? ce : e2));
+    return GENLIB_OK;
+}
+
+int genlib_engine_phi_mean(genlib_engine *eng, double *out) {
+    if (!eng || !out) return fail(GENLIB_EINVAL, "null argument");
+    if (eng->world != 1) return fail(GENLIB_EINVAL, "genlib_engine_phi_mean: one rank only; sharded engines combine genlib_engine_row_sums in proband order");
+    const int32_t n = eng->plan->p.n_unique;
+    if (n < 2) { *out = 0.0; return eng->ran ? (int)GENLIB_OK : fail(GENLIB_EINVAL, "genlib_engine_phi_mean before genlib_engine_run"); }
+    std::vector<double> sums((size_t)n * 2);
+    if (int rc = genlib_engine_row_sums(eng, sums.data())) return rc;
+    double total = 0.0, diag = 0.0;
+    for (int32_t r = 0; r < n; r++) { total += sums[2 * (size_t)r]; diag += sums[2 * (size_t)r + 1]; }   // proband order: deterministic
+    *out = (total - diag) / ((double)n * n - n);
     return GENLIB_OK;
 }
 

@@ -180,28 +180,26 @@ __global__ void gather_peer_kernel(PeerTable PT, int64_t ld, const int8_t *__res
         dst[v] = (O)row[cols[v]];
 }
 
-// sum and trace of the proband block, binary64 accumulation (phiMean, compute.jl:454-459);
-// one rank: rows == cols == the proband slots
+// Row sums of the proband block for phiMean (src/compute.jl:454-459), deterministic: one CTA per own
+// proband row, every thread adds its columns in ascending order in binary64, then a fixed shuffle /
+// shared-memory tree.  out[2 r] = sum over all proband columns of row r, out[2 r + 1] = its diagonal entry.
+// The host adds the rows in proband order, so the mean does not depend on the number of ranks.
 template <typename T>
-__global__ void mean_kernel(const T *__restrict__ A, int64_t ld, const int32_t *__restrict__ slots,
-                            int32_t P, double *__restrict__ acc /* [0]=sum, [1]=trace */) {
-    __shared__ double ssum[kThreads / 32], str[kThreads / 32];
-    double s = 0.0, tr = 0.0;
-    for (int u = blockIdx.x; u < P; u += gridDim.x) {
-        const T *row = A + (int64_t)slots[u] * ld;
-        for (int v = threadIdx.x; v < P; v += blockDim.x) {
-            const double x = (double)row[slots[v]];
-            s += x;
-            if (u == v) tr += x;
-        }
-    }
-    for (int o = 16; o > 0; o >>= 1) { s += __shfl_down_sync(0xffffffffu, s, o); tr += __shfl_down_sync(0xffffffffu, tr, o); }
-    if ((threadIdx.x & 31) == 0) { ssum[threadIdx.x >> 5] = s; str[threadIdx.x >> 5] = tr; }
+__global__ void __launch_bounds__(kThreads)
+rowsum_kernel(const T *__restrict__ A, int64_t ld, const int32_t *__restrict__ own_rows, const int32_t *__restrict__ own_index,
+              const int32_t *__restrict__ slots, int32_t P, double *__restrict__ out) {
+    __shared__ double part[kThreads / 32];
+    const int r = blockIdx.x;
+    const T *row = A + (int64_t)own_rows[r] * ld;
+    double s = 0.0;
+    for (int v = threadIdx.x; v < P; v += kThreads) s += (double)row[slots[v]];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int w = 1; w < kThreads / 32; w++) { s += ssum[w]; tr += str[w]; }
-        atomicAdd(acc, s);
-        atomicAdd(acc + 1, tr);
+        for (int w = 1; w < kThreads / 32; w++) s += part[w];
+        out[2 * r] = s;
+        out[2 * r + 1] = (double)row[slots[own_index[r]]];
     }
 }
 

@@ -441,8 +441,12 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         } catch (...) { break; }                 // no thread: the planning thread does the jobs itself
     }
 
+    double lt_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    auto lt_last = std::chrono::steady_clock::now();
+#define LT(k) do { if (timing) { auto n_ = std::chrono::steady_clock::now(); lt_acc[k] += std::chrono::duration<double, std::milli>(n_ - lt_last).count(); lt_last = n_; } } while (0)
     for (int32_t t = 0; t < S; t++) {
         Layer &L = P.layers[t];
+        LT(7);
         const int32_t *X = by_layer.data() + lstart[t];
         const int32_t nn = count[t];
         L.n_new = nn;
@@ -499,6 +503,7 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
             }
         }
 
+        LT(0);
         // ---- couples of the layer (grouped by group_layer, possibly on a helper thread) ----
         while (!grouped[t].load(std::memory_order_acquire)) {
             const int32_t j = next_job.load() < S ? next_job.fetch_add(1) : S;
@@ -509,6 +514,7 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         const int32_t *fam_first = W.fam_first.data() + lstart[t], *fam_key = W.fam_key.data() + lstart[t];
         const int32_t nf_real = W.fam_n[t];
 
+        LT(1);
         // ---- row owners: a couple's children live with one of their parents' rows (the other
         //      parent row is read through NVLink); spill to the least loaded rank past +12.5 %.
         //      Couples are renumbered rank-major; every rank's range starts at a multiple of 4
@@ -575,6 +581,7 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
             std::vector<int32_t> &pos = W.ipos; pos.assign(fstart, fstart + nf);
             for (int32_t q = 0; q < nn; q++) order[pos[newid[fam_of[q]]]++] = q;
         }
+        LT(2);
         // ---- column slots (global, in lines) and local rows (per owner) ----
         P.mem_ind.resize(L.mem_off + (size_t)nn); P.mem_slot.resize(L.mem_off + (size_t)nn);
         P.mem_fam.resize(L.mem_off + (size_t)nn); P.mem_lrow.resize(L.mem_off + (size_t)nn);
@@ -592,6 +599,7 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
                 if (by_seq) P.mem_rank[L.mem_off + (size_t)q] = x;
             }
         }
+        LT(3);
         P.fam_pf.resize(L.fam_off + (size_t)nf, -1); P.fam_pm.resize(L.fam_off + (size_t)nf, -1);
         P.fam_pf_owner.resize(L.fam_off + (size_t)nf, -1); P.fam_pm_owner.resize(L.fam_off + (size_t)nf, -1);
         P.fam_pf_lrow.resize(L.fam_off + (size_t)nf, -1); P.fam_pm_lrow.resize(L.fam_off + (size_t)nf, -1);
@@ -613,6 +621,7 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
                 *pq[s] = P.tile_map[L.tile_off + (size_t)(rel / kPTile)] * kPTile + rel % kPTile;
             }
         }
+        LT(4);
         // member tiles = the column blocks the layer kernel writes at a time: at most kMTile members and at
         // most kMaxTileFam couples (bounds the staged couple tile), cut at multiples of 8 members (whole
         // 32-byte sectors of a float row on both sides of the cut)
@@ -631,12 +640,14 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         P.alg_elems += L.alg_elems;
         P.row_updates += nn;
 
+        LT(5);
         // ---- after the step: evicted slots / rows become reusable from the next layer on ----
         slots.end_layer(freed);
         for (int32_t g = 0; g < world && world > 1; g++) rows[g].end_layer(freed_rows[g]);
         for (int32_t q = 0; q < nn; q++) next_live.push_back(X[q]);
         live.swap(next_live);
     }
+    if (timing) std::fprintf(stderr, "[plan]   live/flags %.2f  wait-group %.2f  owners/order %.2f  slots %.2f  couples %.2f  tiles %.2f  end %.2f\n", lt_acc[0], lt_acc[1], lt_acc[2], lt_acc[3], lt_acc[4], lt_acc[5], lt_acc[7]);
     PLAN_T("layers");
     P.capacity = round_up(std::max<int64_t>((int64_t)slots.next_fresh * kSlotLine, 1), kPTile);
     for (int32_t g = 0; g < world; g++) P.rows_cap[g] = world > 1 ? std::max(rows[g].next_fresh, 1) : P.capacity;

@@ -192,6 +192,15 @@ class Engine:
         check(lib().genlib_engine_phi_mean(self._h, C.byref(v)))
         return v.value
 
+    def row_sums(self) -> np.ndarray:
+        """(n_own, 2): per own proband row, the sum over all proband columns and the diagonal entry
+        (binary64, fixed order).  Ranks' rows added in proband order give a rank-count-independent mean."""
+        n = lib().genlib_engine_own_probands(self._h, None)
+        out = np.zeros((n, 2), np.float64)
+        if n:
+            check(lib().genlib_engine_row_sums(self._h, ptr(out)))
+        return out
+
     def read_block(self, slots) -> np.ndarray:
         slots = np.ascontiguousarray(slots, np.int32)
         out = np.zeros((len(slots), len(slots)), np.float64)

@@ -234,8 +234,14 @@ int genlib_engine_create_dist(const genlib_plan *plan, int numerics, int device,
 int genlib_engine_ipc_export(genlib_engine *eng, void *handle64);
 int genlib_engine_ipc_attach(genlib_engine *eng, const void *handles, size_t stride);
 /* Mean off-diagonal kinship of the proband matrix, reduced on the device
- * (consumer of the path: phiMean, src/compute.jl:454-459). */
+ * (consumer of the path: phiMean, src/compute.jl:454-459): binary64 accumulation in a FIXED order
+ * (columns ascending per thread, fixed tree per row, rows in proband order), so the value is
+ * reproducible.  One rank only; sharded engines combine genlib_engine_row_sums. */
 int genlib_engine_phi_mean(genlib_engine *eng, double *out);
+/* Per own proband row (genlib_engine_own_probands order): out[2 r] = sum of the row over all proband
+ * columns, out[2 r + 1] = its diagonal entry.  Adding the rows of all ranks in proband order gives
+ * the same bits whatever the number of ranks. */
+int genlib_engine_row_sums(genlib_engine *eng, double *out);
 /* Debug/test: stop genlib_engine_run after `n_layers` layers (< 0: no limit). */
 int genlib_engine_set_layer_limit(genlib_engine *eng, int32_t n_layers);
 /* Debug/test: copy the frontier entry block [slots x slots] (as double). */
