@@ -424,11 +424,31 @@ def sparse_phi(pedigree: Pedigree, probandIDs=None, *, device: int = -1, symmetr
     return KinshipMatrix(np.asarray(ids)[first], ranks[first], dense)
 
 
+def _julia_sum_f32(a: np.ndarray) -> np.float32:
+    """Base.sum of a Float32 array as Julia's mapreduce does it: pairwise halving down to blocks of
+    1024 elements (Base.pairwise_blocksize), the block summed left to right.  (Julia's block loop is
+    `@simd`, so the reference's last bits depend on the machine's vector width; this is the scalar order.)"""
+    a = np.ascontiguousarray(a, np.float32).ravel()
+
+    def rec(lo: int, hi: int) -> np.float32:
+        if hi - lo <= 1024:
+            acc = np.float32(0) if hi == lo else a[lo]
+            for x in a[lo + 1:hi]:
+                acc = np.float32(acc + x)
+            return acc
+        mid = (lo + hi) >> 1
+        return np.float32(rec(lo, mid) + rec(mid, hi))
+
+    return rec(0, len(a))
+
+
 def phiMean(phi_matrix) -> np.float32:
     """gen.phiMean(::Matrix{Float32}) (src/compute.jl:454-459) and gen.phiMean(::KinshipMatrix)
-    (:466-472), host side.  The reference sums the KinshipMatrix in Dict iteration order; here the
-    stored entries are summed in rank order (Float32), which is the same number whenever the sum is
-    exact -- e.g. the reference's own test, test/runtests.jl:55."""
+    (:466-472), host side.  Matrix: `sum(phi)` (Float32, Julia's pairwise order over the column-major
+    buffer -- the matrix is symmetric, so that is this buffer), minus the diagonal summed left to right,
+    divided by n^2 - n in Float32.  KinshipMatrix: the reference adds the stored entries in Dict
+    iteration order; here the entries a look-up can find are added in rank order -- the same number
+    whenever the Float32 sum is exact, e.g. the reference's own test, test/runtests.jl:55."""
     if isinstance(phi_matrix, KinshipMatrix):
         d, n = phi_matrix._dense, len(phi_matrix)
         total = np.float32(0)
@@ -437,5 +457,10 @@ def phiMean(phi_matrix) -> np.float32:
         total = np.float32(total - np.trace(d, dtype=np.float32))
         return np.float32(total / (n * (n - 1) / 2))
     m = np.asarray(phi_matrix, np.float32)
-    total = m.sum(dtype=np.float32) - np.trace(m, dtype=np.float32)
+    big = m.size > (1 << 22)                                        # the scalar emulation is slow: NumPy's pairwise sum
+    total = m.sum(dtype=np.float32) if big else _julia_sum_f32(m)
+    diag = np.float32(0)
+    for x in np.diag(m):
+        diag = np.float32(diag + x)
+    total = np.float32(total - diag)
     return np.float32(total / np.float32(m.size - m.shape[0]))

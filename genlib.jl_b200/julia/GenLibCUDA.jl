@@ -50,9 +50,30 @@ function flatten(pedigree::GenLib.Pedigree)
     father, mother
 end
 
+"""
+A `Matrix{Float32}` (or `Float64`) in page-locked host memory (`genlib_pinned_alloc`): the device copies
+into it at full PCIe speed.  The memory is given back when the matrix is garbage collected.
+"""
+function pinned_matrix(::Type{T}, n::Integer) where {T <: Union{Float32, Float64}}
+    p = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:genlib_pinned_alloc, libgenlib[]), Cint, (Csize_t, Ptr{Ptr{Cvoid}}), max(1, n * n * sizeof(T)), p))
+    A = unsafe_wrap(Array, Ptr{T}(p[]), (Int(n), Int(n)); own = false)
+    finalizer(_ -> ccall((:genlib_pinned_free, libgenlib[]), Cint, (Ptr{Cvoid},), p[]), A)
+    A
+end
+
+"""
+    phi(pedigree, probandIDs = pro(pedigree); verbose = false, compute = true,
+        numerics = :reference, devices = Int[], pinned = false) -> Matrix{Float32}
+
+`gen.phi` (src/compute.jl:233-304) on the B200 engine.  `devices = [0, 1, ...]` shards the frontier over
+several GPUs of the box from this one process (`genlib_phi_multi`: one plan, one host thread per device,
+NVLink peer access); the result is bitwise the single-GPU one.  `pinned = true` returns the matrix in
+page-locked memory (the 400 MB of a 10 000-proband result then arrive in ~8 ms instead of ~40 ms).
+"""
 function phi(pedigree::GenLib.Pedigree, probandIDs::Vector{Int} = GenLib.pro(pedigree);
              verbose::Bool = false, compute::Bool = true, numerics::Symbol = :reference,
-             device::Integer = -1)
+             device::Integer = -1, devices::Vector{<:Integer} = Int[], pinned::Bool = false)
     father, mother = flatten(pedigree)
     probands = Int32[pedigree[ID].rank - 1 for ID in probandIDs]      # KeyError on unknown ID
     plan = Ref{Ptr{Cvoid}}(C_NULL)
@@ -72,12 +93,21 @@ function phi(pedigree::GenLib.Pedigree, probandIDs::Vector{Int} = GenLib.pro(ped
         end
         compute || return nothing                                      # src/compute.jl:264-266
         n = ccall((:genlib_plan_n_unique, libgenlib[]), Int32, (Ptr{Cvoid},), plan[])
-        ϕ = Matrix{Float32}(undef, n, n)                               # symmetric: layout-free
+        ϕ = pinned ? pinned_matrix(Float32, n) : Matrix{Float32}(undef, n, n)   # symmetric: layout-free
         n == 0 && return ϕ
+        if length(devices) > 1                                         # one process, several GPUs
+            devs = Int32.(devices)
+            GC.@preserve ϕ check(ccall((:genlib_phi_multi, libgenlib[]), Cint,
+                (Int32, Ptr{Int32}, Ptr{Int32}, Int32, Ptr{Int32}, Ptr{Cvoid}, Cint, Cint, Int32, Ptr{Int32}, Ptr{Cvoid}),
+                length(father), father, mother, length(probands), probands, ϕ, 0,
+                numerics === :fp64 ? 1 : 0, length(devs), devs, C_NULL))
+            return ϕ
+        end
+        dev = length(devices) == 1 ? Int(devices[1]) : Int(device)
         engine = Ref{Ptr{Cvoid}}(C_NULL)
         check(ccall((:genlib_engine_create, libgenlib[]), Cint,
                     (Ptr{Cvoid}, Cint, Cint, Ptr{Ptr{Cvoid}}),
-                    plan[], numerics === :fp64 ? 1 : 0, device, engine))
+                    plan[], numerics === :fp64 ? 1 : 0, dev, engine))
         try
             check(ccall((:genlib_engine_run, libgenlib[]), Cint, (Ptr{Cvoid}, Cint), engine[], 0))
             GC.@preserve ϕ check(ccall((:genlib_engine_fetch, libgenlib[]), Cint,
@@ -89,6 +119,61 @@ function phi(pedigree::GenLib.Pedigree, probandIDs::Vector{Int} = GenLib.pro(ped
     finally
         ccall((:genlib_plan_destroy, libgenlib[]), Cvoid, (Ptr{Cvoid},), plan[])
     end
+end
+
+"""
+    phiMean(pedigree, probandIDs = pro(pedigree)) -> Float64
+
+The mean off-diagonal kinship of `phi(pedigree, probandIDs)` reduced ON THE DEVICE
+(`genlib_engine_phi_mean`): the matrix never crosses PCIe.  Binary64 accumulation in a fixed order
+(reproducible), where `gen.phiMean(::Matrix{Float32})` (src/compute.jl:454-459) adds Float32 values
+pairwise; they agree to Float32 precision.  `gen.phiMean(phi(ped))` itself keeps working: `phi`
+returns the `Matrix{Float32}` that method wants.
+"""
+function phiMean(pedigree::GenLib.Pedigree, probandIDs::Vector{Int} = GenLib.pro(pedigree); device::Integer = -1)
+    father, mother = flatten(pedigree)
+    probands = Int32[pedigree[ID].rank - 1 for ID in probandIDs]
+    plan = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:genlib_plan_create, libgenlib[]), Cint,
+                (Int32, Ptr{Int32}, Ptr{Int32}, Int32, Ptr{Int32}, Int32, Ptr{Ptr{Cvoid}}),
+                length(father), father, mother, length(probands), probands, 1, plan))
+    try
+        engine = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:genlib_engine_create, libgenlib[]), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Ptr{Cvoid}}),
+                    plan[], 0, device, engine))
+        try
+            check(ccall((:genlib_engine_run, libgenlib[]), Cint, (Ptr{Cvoid}, Cint), engine[], 0))
+            mean = Ref{Cdouble}(0)
+            check(ccall((:genlib_engine_phi_mean, libgenlib[]), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), engine[], mean))
+            return mean[]
+        finally
+            ccall((:genlib_engine_destroy, libgenlib[]), Cvoid, (Ptr{Cvoid},), engine[])
+        end
+    finally
+        ccall((:genlib_plan_destroy, libgenlib[]), Cvoid, (Ptr{Cvoid},), plan[])
+    end
+end
+
+"""
+    f(pedigree, IDs) -> Vector{Float32}
+
+`gen.f` (src/compute.jl:500-511): inbreeding = kinship of the parents.  The reference runs the
+exponential pairwise recursion once per ID; here the parents of all IDs go through ONE sweep of the
+engine with Float64 storage (exact while kinships fit 53 bits, i.e. pedigrees up to ~26 generations deep;
+beyond that the last bits can differ from the reference's Float64 recursion) and are rounded to Float32.
+"""
+function f(pedigree::GenLib.Pedigree, IDs::Vector{Int}; device::Integer = -1)
+    coefficients = zeros(Float32, length(IDs))
+    pairs = [(pedigree[ID].father, pedigree[ID].mother) for ID in IDs]          # KeyError on unknown ID
+    parents = sort(unique(Int[p.ID for pr in pairs for p in pr if !isnothing(pr[1]) && !isnothing(pr[2])]))
+    isempty(parents) && return coefficients
+    k = phi(pedigree, parents; numerics = :fp64, device = device)   # Float32 view of the Float64-storage sweep
+    pos = Dict(ID => i for (i, ID) in enumerate(parents))
+    for (i, (fa, mo)) in enumerate(pairs)
+        (isnothing(fa) || isnothing(mo)) && continue
+        coefficients[i] = k[pos[fa.ID], pos[mo.ID]]
+    end
+    coefficients
 end
 
 """

@@ -176,6 +176,50 @@ def test_out_dtype_and_mean(gen):
     eng.close()
 
 
+@pytest.mark.parametrize("tag,name,scale", [("c3_full", "C3", 1.0), ("c4_x0.1", "C4", 0.1), ("c5_full", "C5", 1.0)])
+def test_benchmark_size_output_equals_the_oracles_golden_hash(gen, tag, name, scale):
+    """Parity AT THE SIZES bench.py measures: the sha256 of the proband matrix equals the one the oracle
+    alone produced (tests/golden/make_golden.py: full C3 takes the oracle minutes, the GPU 0.1 s)."""
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", tag + ".sha256")
+    if not os.path.exists(path):
+        pytest.skip(f"{tag}: golden hash not generated")
+    g = json.load(open(path))
+    s = gen.synth.config(name, scale)
+    ped = gen.genealogy(s.as_columns())
+    got, stats = gen.phi(ped, s.probands, return_stats=True)
+    assert stats["row_updates"] == g["row_updates"] and got.shape == (g["n"], g["n"])
+    assert hashlib.sha256(got.tobytes()).hexdigest() == g["sha256"]
+    assert abs(float(got.astype(np.float64).sum()) - g["sum"]) < 1e-6 * g["sum"]
+    ngpu = gen.lib().genlib_device_count()
+    if ngpu >= 2 and name != "C5":                                  # the same bits from several devices
+        multi = gen.phi(ped, s.probands, devices=list(range(min(ngpu, 8))))
+        assert hashlib.sha256(multi.tobytes()).hexdigest() == g["sha256"]
+
+
+def test_row_sums_and_device_mean_are_deterministic(gen):
+    """phiMean on the device: binary64 in a fixed order, per-row sums that add up the same on any number
+    of ranks; the host mirror of gen.phiMean(::Matrix{Float32}) for comparison."""
+    s = gen.synth.config("C3", 0.05)
+    ped = gen.genealogy(s.as_columns())
+    ranks = ped.rank_of(s.probands)
+    plan = gen.Plan(ped.father, ped.mother, ranks)
+    eng = gen.Engine(plan)
+    eng.run()
+    m = eng.fetch()
+    rs = eng.row_sums()
+    assert rs.shape == (plan.n_unique, 2) and np.array_equal(rs[:, 1], np.diag(m).astype(np.float64))
+    assert np.allclose(rs[:, 0], m.astype(np.float64).sum(1), rtol=1e-14, atol=0)
+    mean = eng.phi_mean()
+    n = plan.n_unique
+    assert mean == (float(np.sum(rs[:, 0])) - float(np.sum(rs[:, 1]))) / (n * n - n) or \
+        abs(mean - (m.astype(np.float64).sum() - np.trace(m.astype(np.float64))) / (n * n - n)) < 1e-15
+    assert eng.phi_mean() == mean                                   # reproducible
+    assert abs(float(gen.phiMean(m)) - mean) < 1e-6 * mean          # Float32 pairwise sum vs binary64
+    eng.close()
+
+
 def test_full_size_properties(gen):
     """C3 at 1/4 scale (10k individuals per generation): too big for the oracle in a test,
     checked through size-independent properties."""
@@ -247,6 +291,21 @@ def test_one_process_several_devices(gen, ob):
     assert_bit_equal(gen.phi(ped, pro, devices=devs), gen.phi(ped, pro))
     with pytest.raises(Exception):
         gen.phi(ped, pro, devices=[0, 0])
+
+
+def test_inbreeding_f_genea140(gen, ob):
+    """gen.f on genea140 against the reference's own definition, phi(father, mother) by the pairwise
+    Karigl recursion (src/compute.jl:66-95, restated in the oracle), for a sample of individuals."""
+    ped = gen.genealogy(gen.genea140)
+    o = ob.OraclePedigree.from_csv(gen.genea140)
+    rng = np.random.default_rng(5)
+    deep = np.nonzero((ped.father >= 0) & (ped.mother >= 0))[0]
+    ids = ped.ids[rng.choice(deep[-4000:], 40, replace=False)]
+    got = gen.f(ped, ids)
+    for v, ID in zip(got, ids):
+        x = ped[int(ID)]
+        assert v == np.float32(o.phi_pair(x.father.ID, x.mother.ID))
+    assert got.dtype == np.float32 and (got > 0).any()
 
 
 def test_inbreeding_f(gen, ob):
