@@ -325,7 +325,7 @@ def main():
     plan = gen.Plan(ped.father, ped.mother, ranks)
     eng = gen.Engine(plan, numerics=args.numerics, device=local)
     setup_s = time.time() - t0
-    rows = plan.row_updates
+    rows = plan.metric_row_updates
     W = max(args.warmup, 3)
     for _ in range(W):
         eng.run()

@@ -39,7 +39,7 @@ def main_dist(args, rank, world, local, B):
     t0 = time.time()
     plan, eng = make_engine()
     setup_s = time.time() - t0
-    rows = plan.row_updates
+    rows = plan.metric_row_updates
     W = max(args.warmup, 3)
     for _ in range(W):
         eng.run()

@@ -242,9 +242,11 @@ size_t a_bytes(const Plan &P, size_t es, int g) { return pad256(total_rows(P, g)
 size_t off_A() { return kFlagBytes; }
 
 // ---- launch shapes ---------------------------------------------------------------------------
-// The strip buffers live in the part of L2 that can be set aside for persisting lines (79 of 126 MB
-// on B200, profiles/r02/l2strip.txt); what the buffers of a layer may take of it:
-constexpr size_t kStripBudget = (size_t)72 << 20;
+// The strip buffers are meant to stay in the 126 MB L2; what the buffers of a layer may take of it.  Four
+// buffers of a full-width C3 strip (20 MB each) measured best: the slack between the producers and the consumers
+// is worth more than the part of the oldest buffer that spills to DRAM (C3: 72.3 ms with four or five buffers,
+// 84.9 ms with three kept in a persisting access-policy window; profiles/r02/README.md).
+constexpr size_t kStripBudget = (size_t)96 << 20;
 
 int env_int(const char *name, int dflt) {
     const char *s = std::getenv(name);
@@ -266,12 +268,18 @@ LayerLaunch shape_layer(const Plan &P, int t, int rank, size_t es, int sm_count)
     // whose staged tile fits shared memory: 128 parent-row segments of sw pairs <= 64 KB).  A wide strip
     // amortises the per-tile work of the consumers; more buffers give the producers more room to run ahead.
     const size_t min_buf = (size_t)std::max(2, env_int("GENLIB_MIN_NBUF", 2));
-    int sw = std::min(es == 4 ? kMaxStrip : kMaxStrip / 2, std::max(8, env_int("GENLIB_MAX_SW", kMaxStrip)));
-    while (sw > 8 && (size_t)q_rows * sw * pair * min_buf > kStripBudget) sw >>= 1;
+    // consumer groups per CTA, each with its own items and shared memory (two only fit with narrower strips)
+    const int groups = std::max(1, std::min(kConsGroups, env_int("GENLIB_CONS_GROUPS", kConsGroups)));
+    const int sw_cap = (es == 4 ? kMaxStrip : kMaxStrip / 2) / groups;
+    const size_t budget = (size_t)std::max(16, env_int("GENLIB_STRIP_BUDGET_MB", (int)(kStripBudget >> 20))) << 20;
+    int sw = std::min(sw_cap, std::max(8, env_int("GENLIB_MAX_SW", kMaxStrip)));
+    while (sw > 8 && (size_t)q_rows * sw * pair * min_buf > budget) sw >>= 1;
     const size_t strip_bytes = std::max<size_t>((size_t)q_rows * sw * pair, 256);
     s.sw = sw;
-    s.ft = std::min(sw, std::max(8, env_int("GENLIB_FT", es == 4 ? 32 : 16)));
-    s.nbuf = (int)std::max<size_t>(2, std::min<size_t>((size_t)std::max(2, env_int("GENLIB_MAX_NBUF", 6)), kStripBudget / strip_bytes));
+    // couples per producer item: 32 rows of 512 B (float) / 16 rows of 1 KB (double); at most two items per live tile
+    s.ft = std::max(sw / 2, std::min(sw, std::max(8, env_int("GENLIB_FT", es == 4 ? 32 : 16))));
+    if (s.ft > 32) s.ft = 32;
+    s.nbuf = (int)std::max<size_t>(2, std::min<size_t>((size_t)std::max(2, env_int("GENLIB_MAX_NBUF", 8)), budget / strip_bytes));
     s.n_strips = (int)((own_nf + sw - 1) / sw);
     s.qstride = (int64_t)(strip_bytes / pair);
     // producer items: 2 ft parent rows x one live tile; consumer items: member tiles, then blocks of carried rows
@@ -279,22 +287,25 @@ LayerLaunch shape_layer(const Plan &P, int t, int rank, size_t es, int sm_count)
     const double rows_per_strip = (double)own_nm / (double)own_nf * sw;        // members of a strip
     int n_mblocks = 0;
     s.mrows = 1;
-    if (L.carried > 0 && rt_rows > 0) {                     // ~64 KB of mirrored columns per block
+    if (L.carried > 0 && rt_rows > 0) {                     // ~64 KB of mirrored columns per block, whole warps' worth of rows
         const int64_t mr = (int64_t)(65536.0 / std::max(1.0, rows_per_strip * es));
-        s.mrows = (int)std::max<int64_t>(32, std::min<int64_t>(mr, 4096));
+        s.mrows = (int)std::max<int64_t>(32, std::min<int64_t>(mr, 4096)) / 32 * 32;
         n_mblocks = (int)((rt_rows + s.mrows - 1) / s.mrows);
     }
     s.n_citems = L.n_mtiles + n_mblocks;
-    // one producer and one consumer CTA per SM
-    const int per_role = std::max(1, env_int("GENLIB_CTAS_PER_ROLE", sm_count));
-    s.n_prod = std::min(per_role, s.n_pitems);
-    s.n_cons = std::min(per_role, s.n_citems);
-    s.rot_p = s.n_prod > 0 ? s.n_pitems % s.n_prod : 0;
-    s.rot_c = s.n_citems % s.n_cons;
+    // one CTA per SM: four producer warps and a consumer group of sixteen
+    const int ctas = std::max(1, std::min(sm_count, env_int("GENLIB_CTAS_PER_ROLE", sm_count)));
+    s.n_prod = std::min(ctas, s.n_pitems);
+    s.groups = groups;
+    s.n_cons = std::min(ctas * groups, s.n_citems);
     const size_t stage = (size_t)2 * s.ft * (kPTile * es + 16);
-    s.stages = (int)std::max<size_t>(2, std::min<size_t>((size_t)std::min(kMaxStages, env_int("GENLIB_STAGES", kMaxStages)), ((size_t)100 << 10) / stage));
-    out.smem = std::max((size_t)s.stages * stage, layer_consumer_bytes(sw, es));
-    out.grid = s.n_prod + s.n_cons;
+    const size_t cons_bytes = layer_consumer_bytes(sw, es);
+    const size_t smem_cap = (size_t)227 * 1024 - 2048;      // (static shared memory and the driver's share)
+    s.stages = (int)std::max<size_t>(2, std::min<size_t>((size_t)std::min(kMaxStages, env_int("GENLIB_STAGES", kMaxStages)), (smem_cap - groups * cons_bytes) / stage));
+    s.cons_bytes = (int32_t)cons_bytes;
+    s.ring_off = (int32_t)(groups * cons_bytes);
+    out.smem = groups * cons_bytes + (size_t)s.stages * stage;
+    out.grid = std::max(s.n_prod, (s.n_cons + groups - 1) / groups);
     s.timeout_cycles = (long long)4e9;                     // ~2 s: a lost dependency becomes GENLIB_ECUDA, not a hang
     return out;
 }
@@ -404,11 +415,11 @@ int launch_layers(genlib_engine &E, bool timed) {
 #ifdef GENLIB_PROFILE
     {
         CU(cudaStreamSynchronize(E.stream));
-        std::vector<long long> h(8 * 2 * 160);
+        std::vector<long long> h(8 * 2 * 160);                      // [CTA][role][phase]
         CU(cudaMemcpy(h.data(), E.prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         const LayerLaunch &pl = E.launch[env_int("GENLIB_PROF_LAYER", 5)];
         double acc[2][8] = {};
-        for (int b = 0; b < pl.grid; b++) for (int i = 0; i < 8; i++) acc[b >= pl.s.n_prod][i] += (double)h[(size_t)b * 8 + i];
+        for (int b = 0; b < pl.grid; b++) for (int r = 0; r < 2; r++) for (int i = 0; i < 8; i++) acc[r][i] += (double)h[((size_t)b * 2 + r) * 8 + i];
         std::fprintf(stderr, "[prof] producers %d consumers %d strips %d (avg kcycles per CTA)\n", pl.s.n_prod, pl.s.n_cons, pl.s.n_strips);
         std::fprintf(stderr, "[prof] producer: other %.0f wait_consumers %.0f mbar %.0f issue %.0f transpose %.0f member_rows %.0f\n",
                      acc[0][0] / pl.s.n_prod / 1e3, acc[0][1] / pl.s.n_prod / 1e3, acc[0][2] / pl.s.n_prod / 1e3, acc[0][3] / pl.s.n_prod / 1e3, acc[0][4] / pl.s.n_prod / 1e3, acc[0][5] / pl.s.n_prod / 1e3);
@@ -546,6 +557,7 @@ int create_engine(const genlib_plan *plan, int numerics, int device, int rank, g
     if (rank < 0 || rank >= P.world) return fail(GENLIB_EINVAL, "rank outside the plan's world");
     if (P.world > kMaxWorld) return fail(GENLIB_EINVAL, "the engine supports at most 16 ranks");
     if (P.n_unique == 0) return fail(GENLIB_EINVAL, "empty proband list: nothing to run");
+    if (P.capacity >= ((int64_t)1 << 24)) return fail(GENLIB_EINVAL, "frontier wider than 2^24 slots: shard the probands");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(GENLIB_ECUDA, "no CUDA device: libgenlib_cuda has no CPU fallback");
@@ -615,14 +627,14 @@ int create_engine(const genlib_plan *plan, int numerics, int device, int rank, g
         if ((size_t)(static_cast<unsigned char *>(E->A) - base) != off_A())
             return fail(GENLIB_EINVAL, "internal: peer-visible arena offsets drifted");
     }
-    // The strip buffers stay in L2: a persisting access-policy window on the engine's stream
-    // (everything else streams through the rest of the cache).
+    // Optional (GENLIB_L2_PERSIST=1): a persisting access-policy window for the strip buffers on the engine's
+    // stream.  Off by default: it limits the buffers to the 79 MB that can persist and measured slower.
     {
         int max_persist = 0, max_window = 0;
         cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, E->device);
         cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, E->device);
-        const char *env = std::getenv("GENLIB_L2_PERSIST");                // "0": leave the cache policy alone
-        if (max_persist > 0 && max_window > 0 && !(env && env[0] == '0')) {
+        const char *env = std::getenv("GENLIB_L2_PERSIST");                // "1": persisting window (measured slower, see kStripBudget)
+        if (max_persist > 0 && max_window > 0 && env && env[0] == '1') {
             cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
             cudaStreamAttrValue attr;
             std::memset(&attr, 0, sizeof attr);

@@ -11,15 +11,16 @@
 // through a transposed scratch -- but the scratch never leaves the 126 MB L2:
 //
 //   strip     = up to 64 of this rank's couples; the strips are processed in order.
-//   PRODUCER  CTAs (one per SM) read the strip's parent rows -- TMA bulk copies into a shared-memory ring that
-//             runs on across strips, from local HBM or a peer's over NVLink -- and write them transposed and
-//             interleaved,
+//   CTA       = one per SM, 12 warps: 4 PRODUCER warps and a CONSUMER group of 8 warps.
+//   PRODUCER  warps read the strip's parent rows -- TMA bulk copies into a shared-memory ring that runs on
+//             across strips, from local HBM or a peer's over NVLink, handed from warp to warp with full /
+//             empty mbarriers (no CTA barrier) -- and write them transposed and interleaved,
 //                 Q[p][F] = (Psi[f_F, p], Psi[m_F, p])          for every live column p,
 //             into one of a few strip buffers that are pinned in L2 (persisting access-policy window);
 //             where the step carries columns over they also write the members' rows against them.
-//   CONSUMER  CTAs (the other one on every SM) take tiles of couples G (ALL couples of the layer), stage
-//             Q[f_G][strip], Q[m_G][strip] -- two contiguous segments per couple, L2 hits -- which hold all
-//             four entries of every (F, G) pair in BOTH groupings,
+//   CONSUMER  groups take tiles of couples G (ALL couples of the layer), stage Q[f_G][strip], Q[m_G][strip]
+//             -- two contiguous segments per couple, L2 hits -- which hold all four entries of every (F, G)
+//             pair in BOTH groupings,
 //                 a = (Psi[f_F,f_G], Psi[m_F,f_G]), c = (Psi[f_F,m_G], Psi[m_F,m_G])
 //                 F climbed: hs(hs(a.x, c.x), hs(a.y, c.y))     G climbed: hs(hs(a.x, a.y), hs(c.x, c.y))
 //             (hs(x, y) = 1/2 x + 1/2 y, one binary64 rounding), round ONCE to the storage type
@@ -31,13 +32,15 @@
 // row; nothing but stored frontier rows crosses NVLink.  DRAM sees the compulsory traffic only: the parent
 // rows once, the new rows once.
 //
-// Flow control is static: within a strip the items (producer: column tiles, consumer: member tiles and
-// blocks of carried rows) are dealt round-robin to the CTAs of the role, the deal rotating from strip to
-// strip so that remainders even out.  Every CTA of a role counts itself off on the strip's counter when
-// its share is done; consumers start a strip when all producers have counted off, producers reuse a strip
-// buffer when all consumers of the strip that used it before have.  All CTAs are resident (two per SM), and
-// a wait that lasts seconds raises the layer's error word instead of hanging the device.
+// Flow control is static: the items of a role (producer: column tiles of a strip, consumer: member tiles and
+// blocks of carried rows) are numbered strip after strip and dealt round-robin to the CTAs.  Every producer
+// warp / consumer group counts itself off on the strip's counter when its share is done; consumers start a
+// strip when all producers have counted off, producers reuse a strip buffer when all consumers of the strip
+// that used it before have.  All CTAs are resident (one per SM), and a wait that lasts seconds raises the
+// layer's error word instead of hanging the device.
 #pragma once
+#include <type_traits>
+
 #include "kernels.cuh"
 #if defined(GENLIB_CHECK)
 #include <cassert>
@@ -50,32 +53,39 @@
 
 namespace genlib {
 
-constexpr int kLayerThreads = 256;
-constexpr int kLayerWarps = kLayerThreads / 32;
+#ifndef GENLIB_CONS_GROUPS
+#define GENLIB_CONS_GROUPS 1
+#endif
+constexpr int kConsGroups = GENLIB_CONS_GROUPS, kGroupWarps = 8, kProdWarps = 4;   // consumer groups per CTA, warps per group
+constexpr int kConsWarps = kConsGroups * kGroupWarps;
+constexpr int kGroupThreads = kGroupWarps * 32, kConsThreads = kConsWarps * 32, kProdThreads = kProdWarps * 32;
+constexpr int kLayerThreads = kConsThreads + kProdThreads;
 constexpr int kMaxStrip = 64;                   // couples per strip (upper bound of StripArgs::sw)
 constexpr int kVPitch = kMaxTileFam + 1;        // row pitch of the staged couple tile (65: conflict-free)
 constexpr int kMaxStages = 4;
-
+constexpr int kRowCache = kGroupThreads;         // strip member rows a consumer group keeps in shared memory at a time
+constexpr int kProdCols = kPTile / kProdWarps;  // columns of a tile that one producer warp transposes
 
 struct StripArgs {
     int32_t sw;          // strip width: couples per strip (8, 16, 32 or 64)
-    int32_t ft;          // couples per producer item (8, 16 or 32; divides sw)
+    int32_t ft;          // couples per producer item (8, 16 or 32; sw or sw / 2)
     int32_t n_strips;    // strips of this rank's couples
     int32_t nbuf;        // strip buffers in rotation
     int32_t stages;      // ring stages
-    int32_t n_prod;      // producer CTAs (0 when nothing is live); the grid is n_prod + n_cons
-    int32_t n_cons;      // consumer CTAs
+    int32_t n_prod;      // CTAs whose producer warps have items (0 when nothing is live)
+    int32_t n_cons;      // consumer groups that have items (groups per CTA of them live on one SM)
+    int32_t groups;      // consumer groups per CTA in use (<= kConsGroups; two need strips of <= 32 couples: shared memory)
+    int32_t cons_bytes;  // dynamic shared memory of one consumer group
     int32_t n_pitems;    // producer items per strip: (sw / ft) * live tiles
     int32_t n_citems;    // consumer items per strip: member tiles + blocks of carried rows
     int32_t mrows;       // live-range rows per block of carried rows
-    int32_t rot_p;       // rotation of the deal per strip (items % CTAs of the role)
-    int32_t rot_c;
+    int32_t ring_off;    // byte offset of the producer ring in dynamic shared memory (after the consumer's part)
     int64_t qstride;     // pairs per strip buffer (live tiles * kPTile * sw)
     void *Q;             // strip buffers
-    int32_t *sync;       // [1] error word, [2 + s] producers done with strip s, [2 + n_strips + s] consumers done
+    int32_t *sync;       // [1] error word, [2 + s] producer warps done with strip s, [2 + n_strips + s] consumer groups done
     const int32_t *live_tiles;   // the live tiles of the layer's slot range: index | kTileCarried
     long long timeout_cycles;
-    long long *prof;             // -DGENLIB_PROFILE: 8 cycle counters per CTA (else unused)
+    long long *prof;             // -DGENLIB_PROFILE: 8 cycle counters per CTA and role (else unused)
 };
 
 template <typename T> struct PairOf;
@@ -86,6 +96,14 @@ __device__ __forceinline__ int ld_acquire_gpu(const int *p) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// barrier of one consumer group only (the producer warps never meet anybody)
+__device__ __forceinline__ void group_sync(int grp) {
+    if constexpr (kConsGroups == 1) asm volatile("bar.sync 1, %0;" ::"n"(kGroupThreads) : "memory");
+    else asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kGroupThreads) : "memory");
 }
 
 // The two groupings of the four frontier entries of a couple pair (see the header).  hs(x, y) = RN(x/2 + y/2)
@@ -104,151 +122,166 @@ __device__ __forceinline__ void couple_pair(double ax, double ay, double cx, dou
 
 inline size_t layer_ring_bytes(int ft, int stages, size_t es) { return (size_t)stages * 2 * ft * (kPTile * es + 16); }
 // consumer: staged parent-row segments of a couple tile (2 x kMaxTileFam rows x sw pairs), Va | Vb, a ring of
-// three tiles' metadata, the strip's member rows
+// three tiles' metadata, the strip's member rows (row descriptor + column slot)
 inline size_t layer_consumer_bytes(int sw, size_t es) {
-    return (size_t)2 * kMaxTileFam * sw * 2 * es + (size_t)2 * sw * kVPitch * es + (size_t)3 * 4 * kMTile * 4 + (size_t)kLayerThreads * 16;
+    const size_t b = (size_t)2 * kMaxTileFam * sw * 2 * es + (size_t)2 * sw * kVPitch * es + (size_t)3 * 4 * kMTile * 4 +
+                     (size_t)kRowCache * 16 + (size_t)kRowCache * 4;
+    return (b + 127) / 128 * 128;
 }
 
-// The items of strip s that CTA k of a role with n CTAs takes: first, first + n, ... below n_items.
-__device__ __forceinline__ int first_item(int k, int s, int rot, int n) {
-    int f = (k - (int)(((long long)s * rot) % n)) % n;
-    return f < 0 ? f + n : f;
-}
-
-// Optional cycle accounting per CTA and phase (-DGENLIB_PROFILE): thread 0's clock64 between phase marks,
-// summed into S.prof[blockIdx.x * 8 + phase]; scripts/prof_layers.py prints them.
+// Optional cycle accounting per CTA, role and phase (-DGENLIB_PROFILE): one thread's clock64 between phase
+// marks (producer warp 0 / consumer thread 0), summed into S.prof[(2 * blockIdx.x + role) * 8 + phase].
 #ifdef GENLIB_PROFILE
 #define PROF_DECL long long prof_t = clock64(), prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #define PROF_MARK(ph) do { const long long now_ = clock64(); prof_acc[ph] += now_ - prof_t; prof_t = now_; } while (0)
-#define PROF_FLUSH() do { if (tid == 0 && S.prof) for (int i_ = 0; i_ < 8; i_++) S.prof[(size_t)blockIdx.x * 8 + i_] = prof_acc[i_]; } while (0)
+#define PROF_FLUSH(role, who) do { if ((who) && S.prof) for (int i_ = 0; i_ < 8; i_++) S.prof[((size_t)blockIdx.x * 2 + (role)) * 8 + i_] = prof_acc[i_]; } while (0)
 #else
 #define PROF_DECL
 #define PROF_MARK(ph) do { } while (0)
-#define PROF_FLUSH() do { } while (0)
+#define PROF_FLUSH(role, who) do { } while (0)
 #endif
 
 template <typename T, bool STORED>
-__global__ void __launch_bounds__(kLayerThreads, 2)
+__global__ void __launch_bounds__(kLayerThreads, 1)
 layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs S) {
     using P2 = typename PairOf<T>::type;
-    extern __shared__ __align__(16) unsigned char dyn_smem[];     // producer: the ring; consumer: staged segments | Va | Vb
-    __shared__ const T *s_row[2 * kMaxStrip];                     // producer: parent rows of the strip being read
-    __shared__ __align__(8) unsigned long long s_bar[kMaxStages]; // producer: "stage filled" mbarriers
-    __shared__ int s_ready;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    extern __shared__ __align__(128) unsigned char dyn_smem[];    // consumer: staged segments | Va | Vb | metadata; then the producer ring
+    __shared__ __align__(8) unsigned long long s_full[kMaxStages];   // producer ring: "stage filled" (bulk copies landed)
+    __shared__ __align__(8) unsigned long long s_empty[kMaxStages];  // producer ring: "stage read by every producer warp"
+    __shared__ __align__(8) unsigned long long s_cbar[kConsGroups];  // consumer group: "tile segments landed"
+    __shared__ int s_ready[kConsGroups];
+    __shared__ int s_ptinfo[kProdWarps][kMaxStages];                 // producer: live_tiles entry of the item in a ring slot
+    const int warp_all = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int sw = S.sw, ft = S.ft, NS = S.n_strips;
     int *const err = S.sync + 1, *const done_p = S.sync + 2, *const done_c = S.sync + 2 + NS;
     P2 *const Qall = static_cast<P2 *>(S.Q);
-    PROF_DECL
-
-    // Thread 0 spins, everybody follows.  A dependency that does not arrive in time sets the layer's error
-    // word (genlib_engine_run then fails with GENLIB_ECUDA); once it is set nobody waits any more, so a
-    // broken schedule drains in seconds instead of hanging the device.
-    auto wait_for = [&](const int *counter, int target) {
-        if (tid == 0 && target > 0) {
-            const long long t0 = clock64();
-            while (ld_acquire_gpu(counter) < target) {
-                if (clock64() - t0 > S.timeout_cycles || ld_acquire_gpu(err) != 0) { atomicExch(err, 1); break; }
-                __nanosleep(100);
-            }
+    if (threadIdx.x == 0) {
+        for (int st = 0; st < kMaxStages; st++) {
+            mbar_init((unsigned)__cvta_generic_to_shared(&s_full[st]), 2 * ft);
+            mbar_init((unsigned)__cvta_generic_to_shared(&s_empty[st]), kProdWarps);
         }
-        __syncthreads();
-    };
-    // A producer's share of the strip is done: its pairs were written with ordinary stores and will be read with
-    // bulk copies (async proxy), so every writer orders its stores against that proxy before the CTA's release.
-    auto produced = [&](int *counter) {
-        asm volatile("fence.proxy.async.global;" ::: "memory");
-        __syncthreads();
-        if (tid == 0) { __threadfence(); atomicAdd(counter, 1); }
-    };
-    // A consumer's share is done: its copies of the strip's pairs have landed in shared memory (it waited for
-    // them), which is all the producers that will overwrite the buffer need to know -- no fence: the rows it
-    // wrote are read by the next kernel at the earliest.
-    auto consumed = [&](int *counter) {
-        __syncthreads();
-        if (tid == 0) atomicAdd(counter, 1);
-    };
+        for (int g = 0; g < kConsGroups; g++) mbar_init((unsigned)__cvta_generic_to_shared(&s_cbar[g]), 2 * kMaxTileFam);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();                                              // the only CTA-wide barrier: the roles part here
 
-    if ((int)blockIdx.x < S.n_prod) {
-        // =============== producer: parent rows -> Q[p][F] pairs (+ member rows x carried columns) ===============
-        const int k = blockIdx.x, NP = S.n_prod, NI = S.n_pitems;
-        const int npt = sw / ft;                                   // items per live tile
+    if (warp_all >= kConsWarps) {
+        // =============== producer warp: parent rows -> Q[p][F] pairs (+ member rows x carried columns) ===============
+        // The four warps share the ring and nothing else: warp w issues the copies of rows [w rpw, (w + 1) rpw) of
+        // every item and transposes columns [w kProdCols, (w + 1) kProdCols) of it.  A dependency that does not
+        // arrive in time sets the layer's error word (genlib_engine_run then fails with GENLIB_ECUDA); once it is
+        // set nobody waits any more, so a broken schedule drains in seconds instead of hanging the device.
+        const int pw = warp_all - kConsWarps, k = blockIdx.x, NP = S.n_prod, NI = S.n_pitems;
+        if (k >= NP) return;
+        PROF_DECL
+        const int npt = sw / ft, lnpt = npt > 1 ? 1 : 0;          // items per live tile: 1 or 2
         const int RB = kPTile * (int)sizeof(T) + 16, STAGE = 2 * ft * RB;
         const unsigned ROWB = kPTile * (unsigned)sizeof(T);
-        const unsigned sbase = (unsigned)__cvta_generic_to_shared(dyn_smem);
-        const unsigned bar0 = (unsigned)__cvta_generic_to_shared(&s_bar[0]);
-        if (tid == 0) {
-            for (int st = 0; st < S.stages; st++) mbar_init(bar0 + 8u * st, 2 * ft);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        // two cursors over this CTA's items, strip after strip: `is/ii` is being read (TMA issued), `cs/ci` written
-        int is = 0, ii = first_item(k, 0, S.rot_p, NP);
-        while (is < NS && ii >= NI) { is++; ii = first_item(k, is, S.rot_p, NP); }
-        int cs = is, ci = ii;
-        int issue_tile = is < NS ? S.live_tiles[ii / npt] & (kTileCarried - 1) : 0;   // tile of the item at the issue cursor
-        int rows_of = -1;                                          // strip whose parent rows are in s_row
-        unsigned n_issued = 0, n_done = 0;
-        const int rpw = 2 * ft / kLayerWarps;                      // rows each warp issues
-        const int cpw = ft / kLayerWarps;                          // couples per warp for the member rows
-        const int f = lane % ft;
-        auto row_of = [&](int s) -> const T * {                    // thread tid < 2 sw: parent row tid of strip s
-            const bool mo = tid >= sw;
-            const int Fl = s * sw + (mo ? tid - sw : tid);
-            if (s >= NS || Fl >= L.own_nf) return nullptr;
+        unsigned char *const ring = dyn_smem + S.ring_off;
+        const unsigned rbase = (unsigned)__cvta_generic_to_shared(ring);
+        const unsigned full0 = (unsigned)__cvta_generic_to_shared(&s_full[0]), empty0 = (unsigned)__cvta_generic_to_shared(&s_empty[0]);
+        const int rpw = 2 * ft / kProdWarps;                       // rows of an item whose copies this warp issues
+        const int myrow = pw * rpw + lane;                         // (lanes < rpw) 0 .. 2 ft - 1: fathers, then mothers
+        const bool issuer = lane < rpw, mo = myrow >= ft;
+        const int myf = mo ? myrow - ft : myrow;
+        const int cpw = ft / kProdWarps;                           // couples of an item whose member rows this warp writes
+
+        auto wait_for = [&](const int *counter, int target) {      // lane 0 spins, the warp follows
+            if (lane == 0 && target > 0) {
+                const long long t0 = clock64();
+                while (ld_acquire_gpu(counter) < target) {
+                    if (clock64() - t0 > S.timeout_cycles || ld_acquire_gpu(err) != 0) { atomicExch(err, 1); break; }
+                    __nanosleep(100);
+                }
+            }
+            __syncwarp();
+        };
+        // This warp's share of a strip is done: its pairs were written with ordinary stores and will be read with
+        // bulk copies (async proxy), so every writer orders its stores against that proxy before the warp's release.
+        auto produced = [&](int *counter) {
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) { __threadfence(); atomicAdd(counter, 1); }
+        };
+        // the parent row this lane copies for items of strip s, half pt (nullptr: unknown parent, or not an issuer)
+        auto row_ptr = [&](int s, int pt) -> const T * {
+            if (!issuer || s >= NS) return nullptr;
+            const int Fl = s * sw + pt * ft + myf;
+            if (Fl >= L.own_nf) return nullptr;
             const int F = L.own_f0 + Fl;
             const int o = mo ? L.fam_pm_owner[F] : L.fam_pf_owner[F];
             if (o < 0) return nullptr;
             return static_cast<const T *>(PT.A[o]) + (int64_t)(mo ? L.fam_pm_lrow[F] : L.fam_pf_lrow[F]) * ld + L.rt_lo;
         };
-        const T *pre_row = nullptr;                                // the same for strip pre_s, fetched a strip ahead
-        int pre_s = -1;
-        auto load_rows = [&](int s) {                              // all threads; the caller syncs
-            if (tid < 2 * sw) {
-                s_row[tid] = pre_s == s ? pre_row : row_of(s);
-                pre_row = row_of(s + 1);                           // in flight while strip s is read
+        // members of the couples whose rows this warp writes against carried columns: lane j < npt cpw holds couple
+        // (pt = j / cpw, qd = j % cpw) of strip s: its member range and the rows of its first two members
+        struct MemInfo { int mb, me, lr0, lr1; };
+        auto mem_info = [&](int s) {
+            MemInfo m; m.mb = 0; m.me = 0; m.lr0 = 0; m.lr1 = 0;
+            if (L.any_carried && lane < npt * cpw && s < NS) {
+                const int pt = lane / cpw, qd = lane - pt * cpw;
+                const int Fl = s * sw + pt * ft + pw * cpw + qd;
+                if (Fl < L.own_nf) {
+                    m.mb = L.fam_start[L.own_f0 + Fl]; m.me = L.fam_start[L.own_f0 + Fl + 1];
+                    if (m.me > m.mb) m.lr0 = L.mem_lrow[m.mb];
+                    if (m.me > m.mb + 1) m.lr1 = L.mem_lrow[m.mb + 1];
+                }
             }
-            pre_s = s + 1;
+            return m;
         };
-        auto issue = [&]() {                                       // item (is, ii) -> ring slot n_issued % stages
-            if (lane < rpw) {
-                const unsigned slot = n_issued % (unsigned)S.stages;
-                const int pt = ii % npt, tile = issue_tile;
-                const int row = warp * rpw + lane;                 // 0 .. 2 ft - 1: fathers, then mothers
-                const unsigned bar = bar0 + 8u * slot;
-                const unsigned dst = sbase + slot * (unsigned)STAGE + (unsigned)(row * RB);
-                const int fi = pt * ft + (row < ft ? row : row - ft);
-                const T *src = s_row[(row < ft ? 0 : sw) + fi];
-                // (the stage was last READ with ordinary loads, before the barrier we come from: a bulk copy may
-                //  overwrite it without a proxy fence; only the zero fill below WRITES it through the generic proxy)
+        // the items of this CTA, strip after strip: item g = s NI + i belongs to CTA g mod NP
+        auto advance = [&](int &s, int &i) { i += NP; while (s < NS && i >= NI) { i -= NI; s++; } };
+        int is = 0, ii = k;                                        // issue cursor (copies under way)
+        while (is < NS && ii >= NI) { ii -= NI; is++; }
+        int cs = is, ci = ii;                                      // write cursor
+        int rs = -1;                                               // strip whose rows are in rp0 / rp1; np0 / np1: strip rs + 1
+        const T *rp0 = nullptr, *rp1 = nullptr, *np0 = nullptr, *np1 = nullptr;
+        int islot = 0;                                             // ring slot of the next issue ...
+        unsigned iuse = 0;                                         // ... and how often it has been filled before
+        int itile = is < NS ? S.live_tiles[ii >> lnpt] : 0;        // live_tiles entry of the item at the issue cursor
+        auto issue = [&]() {                                       // warp-collective
+            if (is >= NS) return;
+            if (rs != is) {                                        // rows of a new strip (fetched a strip ahead)
+                if (rs >= 0 && is == rs + 1) { rp0 = np0; rp1 = np1; }
+                else { rp0 = row_ptr(is, 0); rp1 = npt > 1 ? row_ptr(is, 1) : nullptr; }
+                rs = is;
+                np0 = row_ptr(is + 1, 0); np1 = npt > 1 ? row_ptr(is + 1, 1) : nullptr;
+            }
+            const unsigned fullb = full0 + 8u * islot;
+            // every producer warp has read what the slot held before (they arrive after their last shared load;
+            // the bulk copy below may then overwrite it without a proxy fence)
+            if (iuse > 0 && !mbar_wait(empty0 + 8u * islot, (iuse - 1) & 1u)) atomicExch(err, 2);
+            if (lane == 0) s_ptinfo[pw][islot] = itile;
+            if (issuer) {
+                const T *src = (ii & (npt - 1)) ? rp1 : rp0;
+                const unsigned dst = rbase + (unsigned)(islot * STAGE + myrow * RB);
                 if (src) {
-                    mbar_arrive_expect_tx(bar, ROWB);
-                    bulk_g2s(dst, src + tile * kPTile, ROWB, bar);
+                    mbar_arrive_expect_tx(fullb, ROWB);
+                    bulk_g2s(dst, src + (size_t)(itile & (kTileCarried - 1)) * kPTile, ROWB, fullb);
                 } else {                                           // unknown parent: contributes 0 (compute.jl:111-126)
                     for (unsigned c = 0; c < ROWB; c += 16) zero16_shared(dst + c);
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    mbar_arrive_expect_tx(bar, 0);
+                    mbar_arrive_expect_tx(fullb, 0);
                 }
             }
-            n_issued++;
-            ii += NP;
-            while (is < NS && ii >= NI) { is++; ii = first_item(k, is, S.rot_p, NP); }
-            if (is < NS) issue_tile = S.live_tiles[ii / npt] & (kTileCarried - 1);   // in flight until the next issue
+            __syncwarp();
+            if (++islot == S.stages) { islot = 0; iuse++; }
+            advance(is, ii);
+            if (is < NS) itile = S.live_tiles[ii >> lnpt];         // in flight until the next issue
         };
-        auto try_issue = [&]() {                                   // uniform over the CTA
-            if (is >= NS) return;
-            if (rows_of != is) { __syncthreads(); load_rows(is); rows_of = is; __syncthreads(); }
-            issue();
-        };
-        __syncthreads();
-        for (int n = 0; n < S.stages - 1; n++) try_issue();
-        int cur = -1;                                              // strip this CTA is writing
-        // the item being written: its tile (| kTileCarried) and the flags of the warp's 16 columns (lane & 3 holds
-        // the word of column group lane & 3); both are fetched one item ahead
+        // flags of the warp's kProdCols columns of a tile: lane & 7 holds the word of column group lane & 7
         auto tile_flags = [&](int tinfo) {
-            return __ldg(reinterpret_cast<const uint32_t *>(L.flags + (tinfo & (kTileCarried - 1)) * kPTile) + warp * 4 + (lane & 3));
+            return __ldg(reinterpret_cast<const uint32_t *>(L.flags + (size_t)(tinfo & (kTileCarried - 1)) * kPTile) + pw * (kProdCols / 4) + (lane & (kProdCols / 4 - 1)));
         };
-        int tinfo = cs < NS ? S.live_tiles[ci / npt] : 0;
-        uint32_t live4 = cs < NS ? tile_flags(tinfo) : 0u;
+        for (int n = 0; n < S.stages - 1; n++) issue();
+        int cslot = 0;
+        unsigned cuse = 0;
+        int cur = -1;                                              // strip this warp is writing
+        int ms = -1;                                               // strip of cmi; nmi: strip ms + 1
+        MemInfo cmi = mem_info(NS), nmi = cmi;
+        int tinfo = cs < NS ? S.live_tiles[ci >> lnpt] : 0;
+        uint32_t live8 = cs < NS ? tile_flags(tinfo) : 0u;
+        constexpr uint32_t kLive4 = 0x01010101u * kFlagLive;
         while (cs < NS) {
             if (cs != cur) {                                       // count off the strips that are behind us
                 for (int s = max(cur, 0); s < cs; s++) produced(done_p + s);
@@ -256,31 +289,60 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
                 PROF_MARK(0);
                 wait_for(done_c + (cs - S.nbuf), cs >= S.nbuf ? S.n_cons : 0);    // the strip that used this buffer is consumed
                 PROF_MARK(1);
+                if (L.any_carried) {
+                    cmi = (ms >= 0 && cs == ms + 1) ? nmi : mem_info(cs);
+                    ms = cs;
+                    nmi = mem_info(cs + 1);
+                }
             }
-            int ncs = cs, nci = ci + NP;                           // the item after this one
-            while (ncs < NS && nci >= NI) { ncs++; nci = first_item(k, ncs, S.rot_p, NP); }
-            const int tinfo_next = ncs < NS ? S.live_tiles[nci / npt] : 0;
-            const unsigned slot = n_done % (unsigned)S.stages;
-            PROF_MARK(0);
-            if (!mbar_wait(bar0 + 8u * slot, (n_done / (unsigned)S.stages) & 1u)) atomicExch(err, 2);
-            __syncthreads();                                       // everybody is done with the stage refilled next
+            if (!mbar_wait(full0 + 8u * cslot, cuse & 1u)) atomicExch(err, 2);
             PROF_MARK(2);
-            try_issue();
+            issue();                                               // refills the slot everybody left an item ago
             PROF_MARK(3);
-            const int pt = ci % npt, lt = ci / npt;
+            const int pt = ci & (npt - 1), lt = ci >> lnpt;
             const int tile = tinfo & (kTileCarried - 1);
-            const unsigned char *st = dyn_smem + slot * STAGE;
+            const unsigned char *st = ring + cslot * STAGE;
             P2 *const Q = Qall + (size_t)(cs % S.nbuf) * S.qstride;
             // ---- transposed and interleaved: Q[p][F] = (father row, mother row) at column p.  A lane takes one
             //      couple and four columns at a time: two 128-bit shared loads (a quarter warp spans the 32 banks:
-            //      rows are padded by 16 bytes), four 8-byte stores that the lanes of a warp lay side by side. ----
-            {
-                const int gpi = 32 / ft;                           // column groups a warp handles per step
+            //      rows are padded by 16 bytes), four 8-byte stores that the lanes of a warp lay side by side.
+            //      Columns nobody lives in are skipped (their pairs are never read). ----
+            bool done = false;
+            if constexpr (sizeof(T) == 4) {
+                if (ft == 32) {                                    // the common shape: lane = couple, offsets are immediates
+                    auto fast = [&](auto SWC) {
+                        constexpr int SW = decltype(SWC)::value;
+                        const unsigned char *xr = st + lane * RB + pw * (kProdCols * 4), *yr = xr + 32 * RB;
+                        P2 *q = Q + ((size_t)lt * kPTile + pw * kProdCols) * SW + pt * 32 + lane;
+#pragma unroll
+                        for (int g = 0; g < kProdCols / 4; g++) {
+                            const uint32_t lv = __shfl_sync(0xffffffffu, live8, g) & kLive4;
+                            if (lv == 0u) continue;
+                            const float4 a4 = *reinterpret_cast<const float4 *>(xr + g * 16), b4 = *reinterpret_cast<const float4 *>(yr + g * 16);
+                            P2 *qq = q + g * 4 * SW;
+                            CHECK(((size_t)lt * kPTile + pw * kProdCols + g * 4 + 3) * SW + pt * 32 + lane < (size_t)S.qstride);
+                            if (lv == kLive4) {
+                                qq[0] = make_float2(a4.x, b4.x); qq[SW] = make_float2(a4.y, b4.y);
+                                qq[2 * SW] = make_float2(a4.z, b4.z); qq[3 * SW] = make_float2(a4.w, b4.w);
+                            } else {
+                                if (lv & 0x1u) qq[0] = make_float2(a4.x, b4.x);
+                                if (lv & 0x100u) qq[SW] = make_float2(a4.y, b4.y);
+                                if (lv & 0x10000u) qq[2 * SW] = make_float2(a4.z, b4.z);
+                                if (lv & 0x1000000u) qq[3 * SW] = make_float2(a4.w, b4.w);
+                            }
+                        }
+                    };
+                    if (sw == 64) { fast(std::integral_constant<int, 64>{}); done = true; }
+                    else if (sw == 32) { fast(std::integral_constant<int, 32>{}); done = true; }
+                }
+            }
+            if (!done) {
+                const int f = lane % ft, gpi = 32 / ft;            // column groups the warp handles per step
                 const unsigned char *xr = st + f * RB, *yr = st + (ft + f) * RB;
                 P2 *q = Q + (size_t)lt * kPTile * sw + pt * ft + f;
-                for (int gq = lane / ft; gq < 4; gq += gpi) {
-                    const uint32_t w = __shfl_sync(0xffffffffu, live4, gq);
-                    const int col = warp * (kPTile / 8) + gq * 4;
+                for (int g = lane / ft; g < kProdCols / 4; g += gpi) {
+                    const uint32_t w = __shfl_sync(0xffffffffu, live8, g);
+                    const int col = pw * kProdCols + g * 4;
                     T x[4], y[4];
                     if constexpr (sizeof(T) == 4) {
                         const float4 a4 = *reinterpret_cast<const float4 *>(xr + col * 4), b4 = *reinterpret_cast<const float4 *>(yr + col * 4);
@@ -303,11 +365,11 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
             // ---- rows of the new members against this tile's carried columns (rounded once, compute.jl:296).
             //      Columns that are not carried receive values nobody reads. ----
             if (tinfo & kTileCarried) {
-                const int64_t col0 = (int64_t)L.rt_lo + tile * kPTile + 4 * lane;
+                const int64_t col0 = (int64_t)L.rt_lo + (int64_t)tile * kPTile + 4 * lane;
                 for (int qd = 0; qd < cpw; qd++) {
-                    const int fi = warp * cpw + qd, Fl = cs * sw + pt * ft + fi;
-                    if (Fl >= L.own_nf) continue;
-                    const int mb = L.fam_start[L.own_f0 + Fl], me = L.fam_start[L.own_f0 + Fl + 1];
+                    const int j = pt * cpw + qd, fi = pw * cpw + qd;
+                    const int mb = __shfl_sync(0xffffffffu, cmi.mb, j), me = __shfl_sync(0xffffffffu, cmi.me, j);
+                    const int lr0 = __shfl_sync(0xffffffffu, cmi.lr0, j), lr1 = __shfl_sync(0xffffffffu, cmi.lr1, j);
                     if (me <= mb) continue;
                     double x[4], y[4], rr[4];
                     lds4(reinterpret_cast<const T *>(st + fi * RB) + 4 * lane, x);
@@ -315,31 +377,61 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
 #pragma unroll
                     for (int e = 0; e < 4; e++) rr[e] = half_sum_mode<STORED>(x[e], y[e]);
                     CHECK(col0 + 3 < ld && mb >= 0 && me <= L.n_new);
-                    for (int m = mb; m < me; m++) store4(A + (int64_t)L.mem_lrow[m] * ld + col0, rr);
+                    store4(A + (int64_t)lr0 * ld + col0, rr);
+                    if (me > mb + 1) store4(A + (int64_t)lr1 * ld + col0, rr);
+                    for (int m = mb + 2; m < me; m++) store4(A + (int64_t)L.mem_lrow[m] * ld + col0, rr);
                 }
             }
             PROF_MARK(5);
-            n_done++;
-            cs = ncs; ci = nci;
-            tinfo = tinfo_next;
-            live4 = cs < NS ? tile_flags(tinfo) : 0u;
+            __syncwarp();                                          // every lane has its values: the slot may be refilled
+            if (lane == 0) mbar_arrive(empty0 + 8u * cslot);
+            if (++cslot == S.stages) { cslot = 0; cuse++; }
+            advance(cs, ci);
+            if (cs < NS) {                                         // the next item's tile was noted when its copies were issued
+                tinfo = s_ptinfo[pw][cslot];
+                live8 = tile_flags(tinfo);
+            }
         }
         for (int s = max(cur, 0); s < NS; s++) produced(done_p + s);
         PROF_MARK(0);
-        PROF_FLUSH();
+        PROF_FLUSH(0, pw == 0 && lane == 0);
         return;
     }
 
-    // ===== consumer: couple tiles -> the strip members' rows; carried rows <- the strip members' columns =====
+    // ===== consumer group: couple tiles -> the strip members' rows; carried rows <- the strip members' columns =====
     // Nothing the inner loops need comes from a dependent global load: tile descriptors travel three items
     // ahead in registers, a tile's metadata (its couples' strip-buffer rows, its members' couple / rank /
     // slot) two items ahead into a shared-memory ring with cp.async, its segments one item ahead, and the
     // strip's member rows one strip ahead.
-    const int k = blockIdx.x - S.n_prod, NC = S.n_cons, NI = S.n_citems;
+    // A CTA may run several groups side by side; each is its own consumer (own items, own shared memory, own barrier).
+    const int grp = kConsGroups == 1 ? 0 : warp_all / kGroupWarps;
+    const int tid = threadIdx.x - grp * kGroupThreads, warp = warp_all - grp * kGroupWarps;
+    const int k = blockIdx.x * S.groups + grp, NC = S.n_cons, NI = S.n_citems;
+    if (grp >= S.groups || k >= NC) return;
+    auto cons_sync = [&]() { group_sync(grp); };
+    PROF_DECL
+    // Thread 0 spins, the group follows (see the producer's wait_for for the time-out).
+    auto wait_for = [&](const int *counter, int target) {
+        if (tid == 0 && target > 0) {
+            const long long t0 = clock64();
+            while (ld_acquire_gpu(counter) < target) {
+                if (clock64() - t0 > S.timeout_cycles || ld_acquire_gpu(err) != 0) { atomicExch(err, 1); break; }
+                __nanosleep(100);
+            }
+        }
+        cons_sync();
+    };
+    // A group's share of a strip is done: its copies of the strip's pairs have landed in shared memory (it waited
+    // for them), which is all the producers that will overwrite the buffer need to know -- no fence: the rows it
+    // wrote are read by the next kernel at the earliest.
+    auto consumed = [&](int *counter) {
+        cons_sync();
+        if (tid == 0) atomicAdd(counter, 1);
+    };
+    const int prod_arrivals = S.n_prod * kProdWarps;               // what done_p[s] reaches when strip s is complete
     constexpr int kMetaSlots = 3, kMetaInts = 4 * kMTile;          // per slot: qrow[128] | couple[128] | rank[128] | slot[128]
-    constexpr int kRowCache = kLayerThreads;                       // strip member rows kept in shared memory at a time
     struct RowMeta { unsigned rowoff; int rank; long long bytes; };   // Va row offset, rank, byte offset of the frontier row
-    unsigned char *sm = dyn_smem;
+    unsigned char *sm = dyn_smem + (size_t)grp * S.cons_bytes;
     P2 *const stg = reinterpret_cast<P2 *>(sm);                    // [2 g + parent][f]
     sm += (size_t)2 * kMaxTileFam * sw * sizeof(P2);
     T *const Va = reinterpret_cast<T *>(sm);                       // [f][g]: the strip couple's member is climbed first
@@ -348,15 +440,17 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
     int *const meta = reinterpret_cast<int *>(sm);
     sm += (size_t)kMetaSlots * kMetaInts * sizeof(int);
     RowMeta *const rowmeta = reinterpret_cast<RowMeta *>(sm);
+    sm += (size_t)kRowCache * sizeof(RowMeta);
+    int *const colmeta = reinterpret_cast<int *>(sm);              // the same members as COLUMNS: slot | strip couple << 24
     const unsigned stg_s = (unsigned)__cvta_generic_to_shared(stg), meta_s = (unsigned)__cvta_generic_to_shared(meta);
     const unsigned va_s = (unsigned)__cvta_generic_to_shared(Va), vb_s = (unsigned)__cvta_generic_to_shared(Vb);
     const int lsw = 31 - __clz(sw);                                // sw is a power of two
     const int row_bytes = sw * (int)sizeof(P2);
 
     struct Cur { int s, it; };                                     // an item of this CTA: strip, index in the strip
-    auto advance = [&](Cur c) {
+    auto advance = [&](Cur c) {                                    // item g = s NI + it belongs to CTA g mod NC
         c.it += NC;
-        while (c.s < NS && c.it >= NI) { c.s++; c.it = first_item(k, c.s, S.rot_c, NC); }
+        while (c.s < NS && c.it >= NI) { c.it -= NI; c.s++; }
         return c;
     };
     auto is_tile = [&](Cur c) { return c.s < NS && c.it < L.n_mtiles; };
@@ -375,37 +469,12 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
         }
     };
     // the two parent-row segments of every couple of the tile -> stg: one TMA bulk copy per segment, issued by
-    // the first 2 * kMaxTileFam threads (one each), all completing on one mbarrier phase per tile
-    const unsigned sbar = (unsigned)__cvta_generic_to_shared(&s_bar[0]);
-    if (tid == 0) {
-        mbar_init(sbar, 2 * kMaxTileFam);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
+    // the first lanes of every warp (one each), all completing on one mbarrier phase per tile
+    const unsigned sbar = (unsigned)__cvta_generic_to_shared(&s_cbar[grp]);
     unsigned n_staged = 0, n_landed = 0;                           // tiles whose copies were issued / awaited
-#ifdef GENLIB_STAGE_LDGSTS
-    // (16-byte cp.async through the LSU: the TMA unit is left to the producers, whose requests are as small)
     auto stage_tile = [&](const P2 *Q, int nfJ, int slot) {
-        const int *qrow = meta + slot * kMetaInts;
-        const int per = row_bytes / 16;                            // lanes per segment (4 ... 32)
-        const int seg_per_step = 32 / per, sub = lane / per, part = lane - sub * per;
-        for (int r0 = warp * seg_per_step; r0 < 2 * nfJ; r0 += kLayerWarps * seg_per_step) {
-            const int r = r0 + sub;
-            if (r < 2 * nfJ) {
-                const int q = qrow[r];
-                CHECK(q >= -1 && (long long)q * sw < S.qstride);
-                const unsigned dst = stg_s + (unsigned)(r * row_bytes + part * 16);
-                if (q >= 0) cp_async16_to(dst, reinterpret_cast<const unsigned char *>(Q + (size_t)q * sw) + part * 16);
-                else zero16_shared(dst);                           // unknown parent: contributes 0
-            }
-        }
-        n_staged++;
-    };
-    auto await_tile = [&]() { n_landed++; };                       // (cp_async_wait<0> by the caller covers the segments)
-#else
-    auto stage_tile = [&](const P2 *Q, int nfJ, int slot) {
-        if (lane < 2 * kMaxTileFam / kLayerWarps) {                // 16 lanes of every warp: the issue is serial per warp
-            const int r = warp * (2 * kMaxTileFam / kLayerWarps) + lane;
+        if (lane < 2 * kMaxTileFam / kGroupWarps) {                 // the issue is serial per warp
+            const int r = warp * (2 * kMaxTileFam / kGroupWarps) + lane;
             const int q = r < 2 * nfJ ? meta[slot * kMetaInts + r] : -1;
             CHECK(q >= -1 && (long long)q * sw < S.qstride);
             const unsigned dst = stg_s + (unsigned)(r * row_bytes);
@@ -426,28 +495,28 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
         if (!mbar_wait(sbar, n_landed & 1u)) atomicExch(err, 2);
         n_landed++;
     };
-#endif
 
     // ---- the strip's member rows: prefetched one strip ahead (registers), cached in shared memory ----
-    int cur = -1;                                                  // strip this CTA is in
+    int cur = -1;                                                  // strip this group is in
     int F0 = 0, nFs = 0, ms0 = 0, ms1 = 0, n_rows = 0;
-    int pre_s = -1, pre_ms0 = 0, pre_ms1 = 0, pre_f = 0, pre_rank = 0, pre_lrow = 0;   // strip pre_s: bounds, row ms0 + tid
+    int pre_s = -1, pre_ms0 = 0, pre_ms1 = 0, pre_f = 0, pre_rank = 0, pre_lrow = 0, pre_slot = 0;   // strip pre_s: bounds, row ms0 + tid
     int pre2_s = -1, pre2_ms0 = 0, pre2_ms1 = 0;                   // strip pre2_s: bounds only
     auto strip_bounds = [&](int st, int &b0, int &b1) {
         const int f0 = L.own_f0 + st * sw, nf = min(sw, L.own_nf - st * sw);
         b0 = L.fam_start[f0]; b1 = L.fam_start[f0 + nf];
     };
-    auto strip_row = [&](int st, int b0, int b1, int first, int &f, int &rk, int &lr) {   // row first + tid of strip st
+    auto strip_row = [&](int st, int b0, int b1, int first, int &f, int &rk, int &lr, int &sl) {   // row first + tid of strip st
         const int im = min(b0 + first + tid, b1 - 1);
-        f = L.mem_fam[im] - (L.own_f0 + st * sw); rk = L.mem_ind[im]; lr = L.mem_lrow[im];
+        f = L.mem_fam[im] - (L.own_f0 + st * sw); rk = L.mem_ind[im]; lr = L.mem_lrow[im]; sl = L.mem_slot[im];
     };
-    auto put_row = [&](int f, int rk, int lr) {
+    auto put_row = [&](int f, int rk, int lr, int sl) {
         RowMeta m; m.rowoff = (unsigned)(f * kVPitch * (int)sizeof(T)); m.rank = rk; m.bytes = (long long)lr * ld * (long long)sizeof(T);
         rowmeta[tid] = m;
+        colmeta[tid] = sl | (f << 24);
     };
 
-    Cur c0; c0.s = 0; c0.it = first_item(k, 0, S.rot_c, NC);
-    while (c0.s < NS && c0.it >= NI) { c0.s++; c0.it = first_item(k, c0.s, S.rot_c, NC); }
+    Cur c0; c0.s = 0; c0.it = k;
+    while (c0.s < NS && c0.it >= NI) { c0.it -= NI; c0.s++; }
     Cur c1 = advance(c0), c2 = advance(c1), c3 = advance(c2);
     int4 d0 = fetch_desc(c0), d1 = fetch_desc(c1), d2 = fetch_desc(c2);
     unsigned n_item = 0;                                           // items done: item j's metadata sits in ring slot j % 3
@@ -462,42 +531,56 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
             cur = s;
             F0 = L.own_f0 + s * sw;
             nFs = min(sw, L.own_nf - s * sw);
-            int rf, rk, rl;
-            if (pre_s == s) { ms0 = pre_ms0; ms1 = pre_ms1; rf = pre_f; rk = pre_rank; rl = pre_lrow; }
-            else { strip_bounds(s, ms0, ms1); strip_row(s, ms0, ms1, 0, rf, rk, rl); }
+            int rf, rk, rl, rsl;
+            if (pre_s == s) { ms0 = pre_ms0; ms1 = pre_ms1; rf = pre_f; rk = pre_rank; rl = pre_lrow; rsl = pre_slot; }
+            else { strip_bounds(s, ms0, ms1); strip_row(s, ms0, ms1, 0, rf, rk, rl, rsl); }
             n_rows = ms1 - ms0;
-            put_row(rf, rk, rl);                                   // (read after the barriers below)
+            put_row(rf, rk, rl, rsl);                              // (read after the barriers below)
             // the next strip's rows, and the bounds of the one after, are fetched now and used a strip later
             if (s + 1 < NS) {
                 if (pre2_s == s + 1) { pre_ms0 = pre2_ms0; pre_ms1 = pre2_ms1; } else strip_bounds(s + 1, pre_ms0, pre_ms1);
-                strip_row(s + 1, pre_ms0, pre_ms1, 0, pre_f, pre_rank, pre_lrow);
+                strip_row(s + 1, pre_ms0, pre_ms1, 0, pre_f, pre_rank, pre_lrow, pre_slot);
                 pre_s = s + 1;
                 if (s + 2 < NS) { strip_bounds(s + 2, pre2_ms0, pre2_ms1); pre2_s = s + 2; }
             }
             PROF_MARK(2);
-            if (!staged) wait_for(done_p + s, S.n_prod);          // the strip's pairs are complete (in L2)
-            else __syncthreads();
+            if (!staged) wait_for(done_p + s, prod_arrivals);     // the strip's pairs are complete (in L2)
+            else cons_sync();
             PROF_MARK(1);
         }
         const P2 *const Q = Qall + (size_t)(s % S.nbuf) * S.qstride;
         const int slot0 = (int)(n_item % kMetaSlots);
 
         if (it >= L.n_mtiles) {
-            // ---- a block of carried rows: the strip members' columns, Psi[c, i] = RN(hs(Q[c][F_i])) ----
+            // ---- a block of carried rows: the strip members' columns, Psi[c, i] = RN(hs(Q[c][F_i])).  A warp takes 32
+            //      rows of the live range at a time: their flags / homes / tiles in one coalesced load each. ----
             const int r0 = (it - L.n_mtiles) * S.mrows, r1 = min(L.rt_rows, r0 + S.mrows);
-            for (int row = r0 + warp; row < r1; row += kLayerWarps) {
-                if (!(L.flags[row] & kFlagCarried)) continue;
-                T *dst = static_cast<T *>(PT.A[L.live_owner[row]]) + (int64_t)L.live_lrow[row] * ld;
-                CHECK(L.tile_map[row / kPTile] >= 0 && L.live_owner[row] >= 0 && L.live_lrow[row] >= 0);
-                const P2 *q = Q + ((size_t)L.tile_map[row / kPTile] * kPTile + (size_t)(row % kPTile)) * sw;
-                T v0 = (T)0, v1 = (T)0;
-                if (lane < nFs) { const P2 p = __ldcg(q + lane); v0 = (T)half_sum_mode<STORED>((double)p.x, (double)p.y); }
-                if (lane + 32 < nFs) { const P2 p = __ldcg(q + lane + 32); v1 = (T)half_sum_mode<STORED>((double)p.x, (double)p.y); }
-                for (int m = ms0 + lane; m < ((n_rows + 31) & ~31) + ms0; m += 32) {
-                    const int mm = min(m, ms1 - 1);
-                    const int fi = L.mem_fam[mm] - F0;
-                    const T a = __shfl_sync(0xffffffffu, v0, fi & 31), b = __shfl_sync(0xffffffffu, v1, fi & 31);
-                    if (m < ms1) dst[L.mem_slot[mm]] = fi < 32 ? a : b;
+            const bool cached = n_rows <= kRowCache;               // the strip's members sit in rowmeta / colmeta
+            for (int base = r0 + warp * 32; base < r1; base += kGroupWarps * 32) {
+                const int myr = base + lane;
+                int fl = 0, own = 0, lrw = 0, tm = 0;
+                if (myr < r1) fl = L.flags[myr];
+                if (fl & kFlagCarried) { own = L.live_owner[myr]; lrw = L.live_lrow[myr]; tm = L.tile_map[myr / kPTile]; }
+                unsigned todo = __ballot_sync(0xffffffffu, (fl & kFlagCarried) != 0);
+                while (todo) {
+                    const int j = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int row = base + j;
+                    const int o = __shfl_sync(0xffffffffu, own, j), lr = __shfl_sync(0xffffffffu, lrw, j), t = __shfl_sync(0xffffffffu, tm, j);
+                    CHECK(t >= 0 && o >= 0 && lr >= 0);
+                    T *dst = static_cast<T *>(PT.A[o]) + (int64_t)lr * ld;
+                    const P2 *q = Q + ((size_t)t * kPTile + (size_t)(row % kPTile)) * sw;
+                    T v0 = (T)0, v1 = (T)0;
+                    if (lane < nFs) { const P2 p = __ldcg(q + lane); v0 = (T)half_sum_mode<STORED>((double)p.x, (double)p.y); }
+                    if (lane + 32 < nFs) { const P2 p = __ldcg(q + lane + 32); v1 = (T)half_sum_mode<STORED>((double)p.x, (double)p.y); }
+                    for (int m = lane; m < ((n_rows + 31) & ~31); m += 32) {
+                        const int mm = min(m, n_rows - 1);
+                        int fi, sl;
+                        if (cached) { const int cm = colmeta[mm]; fi = cm >> 24; sl = cm & 0xffffff; }
+                        else { fi = L.mem_fam[ms0 + mm] - F0; sl = L.mem_slot[ms0 + mm]; }
+                        const T a = __shfl_sync(0xffffffffu, v0, fi & 31), b = __shfl_sync(0xffffffffu, v1, fi & 31);
+                        if (m < n_rows) dst[sl] = fi < 32 ? a : b;
+                    }
                 }
             }
             // keep the pipeline of descriptors and metadata moving
@@ -516,17 +599,21 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
         const int fJ0 = d0.x, nfJ = d0.y, mJ0 = d0.z, cntJ = d0.w;
         if (!staged) {
             cp_async_wait<0>();
-            __syncthreads();                                       // the tile's metadata is in the ring
+            cons_sync();                                           // the tile's metadata is in the ring
             stage_tile(Q, nfJ, slot0);
             cp_async_commit();
         }
         PROF_MARK(0);
         cp_async_wait<0>();                                        // the next tile's metadata (own copies) ...
         await_tile();                                              // ... and this tile's segments have landed
-        __syncthreads();                                           // for everybody; the previous item is written
+        cons_sync();                                               // for everybody; the previous item is written
         PROF_MARK(3);
+        // is the next item's strip produced?  Asked now, answered after the arithmetic (an L2 round trip)
+        const bool peek_next = is_tile(c1) && c1.s != s;
+        int peek = 0;
+        if (tid == 0 && peek_next) peek = ld_acquire_gpu(done_p + c1.s);
         {
-            const int fl = tid & (sw - 1), g0 = tid >> lsw, gstep = kLayerThreads >> lsw;
+            const int fl = tid & (sw - 1), g0 = tid >> lsw, gstep = kGroupThreads >> lsw;
             if (fl < nFs) {
 #pragma unroll 4
                 for (int g = g0; g < nfJ; g += gstep) {
@@ -538,7 +625,7 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
                 }
             }
         }
-        __syncthreads();                                           // Va | Vb complete, the staging area is free
+        cons_sync();                                               // Va | Vb complete, the staging area is free
         PROF_MARK(4);
         // the pipeline: descriptor of item +3, metadata of item +2, segments of item +1 (if its strip is produced)
         const int4 d3 = fetch_desc(c3);
@@ -546,10 +633,10 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
         staged = false;
         if (is_tile(c1)) {
             bool ready = c1.s == s;
-            if (!ready) {                                          // peek: do not wait here, the expansion comes first
-                if (tid == 0) s_ready = ld_acquire_gpu(done_p + c1.s) >= S.n_prod;
-                __syncthreads();
-                ready = s_ready != 0;
+            if (!ready) {                                          // do not wait here, the expansion comes first
+                if (tid == 0) s_ready[grp] = peek >= prod_arrivals;
+                cons_sync();
+                ready = s_ready[grp] != 0;
             }
             if (ready) { stage_tile(Qall + (size_t)(c1.s % S.nbuf) * S.qstride, d1.y, (int)((n_item + 1) % kMetaSlots)); staged = true; }
         }
@@ -573,14 +660,14 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
             unsigned char *const Ab = reinterpret_cast<unsigned char *>(A);
             for (int pass0 = 0; pass0 < n_rows; pass0 += kRowCache) {
                 if (pass0 > 0 || n_rows > kRowCache) {             // a strip with more rows than the cache: reload it per pass
-                    __syncthreads();
-                    int rf, rk, rl;
-                    strip_row(s, ms0, ms1, pass0, rf, rk, rl);
-                    put_row(rf, rk, rl);
-                    __syncthreads();
+                    cons_sync();
+                    int rf, rk, rl, rsl;
+                    strip_row(s, ms0, ms1, pass0, rf, rk, rl, rsl);
+                    put_row(rf, rk, rl, rsl);
+                    cons_sync();
                 }
                 const int nrp = min(kRowCache, n_rows - pass0);
-                const int share = (nrp + kLayerWarps - 1) / kLayerWarps;
+                const int share = (nrp + kGroupWarps - 1) / kGroupWarps;
                 const int rbeg = warp * share, rend = min(nrp, rbeg + share);
                 if (ncol > 0) {
                     int r = rbeg;
@@ -641,7 +728,7 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
     }
     for (int t = max(cur, 0); t < NS; t++) consumed(done_c + t);
     PROF_MARK(0);
-    PROF_FLUSH();
+    PROF_FLUSH(1, tid == 0);
 }
 
 }  // namespace genlib

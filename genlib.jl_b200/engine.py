@@ -46,7 +46,13 @@ class Plan:
     n_unique = property(lambda s: lib().genlib_plan_n_unique(s._h))
     n_layers = property(lambda s: lib().genlib_plan_n_layers(s._h))
     capacity = property(lambda s: lib().genlib_plan_capacity(s._h))
-    row_updates = property(lambda s: lib().genlib_plan_row_updates(s._h))
+    row_updates = property(lambda s: lib().genlib_plan_row_updates(s._h))     # rows the engine writes (every layer)
+
+    @property
+    def metric_row_updates(self) -> int:
+        """The benchmark's unit: proband-ancestors born AFTER the top level -- what the
+        reference's steps compute (compute.jl:276-302); the top level is only the initial 1/2 I."""
+        return int(self.row_updates - (self.layer_info(0)["n_new"] if self.n_layers > 0 else 0))
 
     def device_bytes(self, numerics="reference", rank: int = 0) -> int:
         return lib().genlib_plan_device_bytes(self._h, _lib.NUMERICS[numerics], rank)

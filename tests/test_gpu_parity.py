@@ -189,7 +189,9 @@ def test_benchmark_size_output_equals_the_oracles_golden_hash(gen, tag, name, sc
     s = gen.synth.config(name, scale)
     ped = gen.genealogy(s.as_columns())
     got, stats = gen.phi(ped, s.probands, return_stats=True)
-    assert stats["row_updates"] == g["row_updates"] and got.shape == (g["n"], g["n"])
+    # (the golden record counts the individuals born after the top level, like the oracle's steps)
+    top = gen.Plan(ped.father, ped.mother, ped.rank_of(s.probands)).layer_info(0)["n_new"]
+    assert stats["row_updates"] - top == g["row_updates"] and got.shape == (g["n"], g["n"])
     assert hashlib.sha256(got.tobytes()).hexdigest() == g["sha256"]
     assert abs(float(got.astype(np.float64).sum()) - g["sum"]) < 1e-6 * g["sum"]
     ngpu = gen.lib().genlib_device_count()
