@@ -294,7 +294,11 @@ LayerLaunch shape_layer(const Plan &P, int t, int rank, size_t es, int sm_count)
     }
     s.n_citems = L.n_mtiles + n_mblocks;
     // one CTA per SM: four producer warps and a consumer group of sixteen
-    const int ctas = std::max(1, std::min(sm_count, env_int("GENLIB_CTAS_PER_ROLE", sm_count)));
+    // Layers with few items per strip run faster on 7/8 of the SMs (C5: 148 CTAs 246 ms, 128 to 136 CTAs 148 ms;
+    // genea140: 8.9 -> 6.4 ms): every CTA takes part in every strip's hand-over, whether it has an item there or
+    // not.  Layers with several items per CTA and strip want every SM (C3: 70.8 ms on 148, 74.3 ms on 132).
+    const int few = (sw / s.ft) * L.n_live_tiles < 3 * sm_count / 2 ? sm_count - sm_count / 8 : sm_count;
+    const int ctas = std::max(1, std::min(sm_count, env_int("GENLIB_CTAS_PER_ROLE", few)));
     s.n_prod = std::min(ctas, s.n_pitems);
     s.groups = groups;
     s.n_cons = std::min(ctas * groups, s.n_citems);
@@ -314,12 +318,12 @@ size_t strip_buffer_bytes(const LayerLaunch &ll, size_t es) { return (size_t)ll.
 
 size_t engine_bytes(const Plan &P, int numerics, int g, int sm_count = 148) {
     const size_t es = numerics == GENLIB_NUMERICS_FP64 ? 8 : 4;
-    size_t q = 256, sync_ints = 0;
+    size_t q = 256, sync_ints = (P.layers.size() + 15) / 16 * 16;            // the layers' error words come first
     for (int t = 0; t < (int)P.layers.size(); t++) {
         const LayerLaunch ll = shape_layer(P, t, g, es, sm_count);
         if (ll.grid == 0) continue;
         q = std::max(q, strip_buffer_bytes(ll, es));
-        sync_ints += 2 + 2 * (size_t)ll.s.n_strips;
+        sync_ints += 16 * (size_t)ll.s.n_strips;
     }
     size_t b = kFlagBytes + a_bytes(P, es, g) + pad256(q) + pad256(sync_ints * sizeof(int32_t));
     b += 2 * pad256(kFetchStageBytes);                                         // proband staging
@@ -392,6 +396,7 @@ int launch_layers(genlib_engine &E, bool timed) {
         if (ll.grid > 0) {
             ll.s.Q = E.Q;
             ll.s.sync = E.sync + ll.sync_off;
+            ll.s.err = E.sync + t;
             ll.s.live_tiles = E.live_tiles.p + L.ltile_off;
 #ifdef GENLIB_PROFILE
             ll.s.prof = (t == env_int("GENLIB_PROF_LAYER", 5)) ? E.prof : nullptr;
@@ -578,13 +583,14 @@ int create_engine(const genlib_plan *plan, int numerics, int device, int rank, g
     // launch shapes, strip buffers, sync words
     E->launch.resize(P.layers.size());
     E->q_bytes = 256;
+    E->sync_ints = (P.layers.size() + 15) / 16 * 16;                          // the layers' error words come first
     for (int t = 0; t < (int)P.layers.size(); t++) {
         LayerLaunch &ll = E->launch[t];
         ll = shape_layer(P, t, rank, E->esize, E->sm_count);
         if (ll.grid == 0) continue;
         E->q_bytes = std::max(E->q_bytes, strip_buffer_bytes(ll, E->esize));
         ll.sync_off = E->sync_ints;
-        E->sync_ints += 2 + 2 * (size_t)ll.s.n_strips;
+        E->sync_ints += 16 * (size_t)ll.s.n_strips;
     }
     const size_t need = engine_bytes(P, numerics, rank, E->sm_count);
     CU(cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking));
@@ -960,13 +966,9 @@ int genlib_engine_run(genlib_engine *eng, int time_layers) {
     }
     {
         int32_t errw = 0;                                     // a dependency inside a layer kernel timed out
-        for (const LayerLaunch &ll : E.launch)
-            if (ll.grid > 0) {
-                int32_t w2[2] = {0, 0};
-                CU(cudaMemcpy(w2, E.sync + ll.sync_off, sizeof w2, cudaMemcpyDeviceToHost));
-                errw |= w2[1];
-                if (errw) break;
-            }
+        std::vector<int32_t> words(E.launch.size(), 0);
+        if (!words.empty()) CU(cudaMemcpy(words.data(), E.sync, words.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        for (int32_t w : words) if (w) { errw = w; break; }
         if (errw) return fail(GENLIB_ECUDA, "the layer kernel reported error " + std::to_string(errw) + " (1: a strip dependency did not arrive, 2: a bulk copy did not complete)");
     }
     if (E.world > 1) {

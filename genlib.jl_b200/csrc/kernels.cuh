@@ -61,12 +61,27 @@ __device__ __forceinline__ void store4(double *p, const double (&d)[4]) {
     reinterpret_cast<double2 *>(p)[0] = make_double2(d[0], d[1]);
     reinterpret_cast<double2 *>(p)[1] = make_double2(d[2], d[3]);
 }
+// New frontier rows are written once and read by the NEXT step's kernel at the earliest: streaming stores
+// (st.global.cs, evict-first) keep them from pushing the strip buffers out of L2.
+__device__ __forceinline__ void store4(float *p, const double (&d)[4], int) {
+    __stcs(reinterpret_cast<float4 *>(p), make_float4((float)d[0], (float)d[1], (float)d[2], (float)d[3]));
+}
+__device__ __forceinline__ void store4(double *p, const double (&d)[4], int) {
+    __stcs(reinterpret_cast<double2 *>(p), make_double2(d[0], d[1]));
+    __stcs(reinterpret_cast<double2 *>(p) + 1, make_double2(d[2], d[3]));
+}
 __device__ __forceinline__ void store_vec4(float *p, const float (&v)[4]) {
-    *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    __stcs(reinterpret_cast<float4 *>(p), make_float4(v[0], v[1], v[2], v[3]));
 }
 __device__ __forceinline__ void store_vec4(double *p, const double (&v)[4]) {
-    reinterpret_cast<double2 *>(p)[0] = make_double2(v[0], v[1]);
-    reinterpret_cast<double2 *>(p)[1] = make_double2(v[2], v[3]);
+    __stcs(reinterpret_cast<double2 *>(p), make_double2(v[0], v[1]));
+    __stcs(reinterpret_cast<double2 *>(p) + 1, make_double2(v[2], v[3]));
+}
+// an L2 cache policy for data that is read once (the parents' rows): evict first
+__device__ __forceinline__ unsigned long long policy_evict_first() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
 }
 // 1/2 x + 1/2 y with ONE binary64 rounding (1/2 y is exact), = Julia's `0 + x/2 + y/2`
 __device__ __forceinline__ double half_sum(double x, double y) { return fma(0.5, x, 0.5 * y); }
@@ -112,6 +127,10 @@ __device__ __forceinline__ bool mbar_wait(unsigned bar, unsigned parity) {
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_hint(unsigned dst, const void *src, unsigned bytes, unsigned bar, unsigned long long pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void zero16_shared(unsigned smem) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};\n" ::"r"(smem), "r"(0) : "memory");

@@ -45,8 +45,8 @@
 #if defined(GENLIB_CHECK)
 #include <cassert>
 #define CHECK(cond) assert(cond)
-#elif defined(GENLIB_SOFTCHECK)       // record the source line of a violated bound in the layer's error word, go on
-#define CHECK(cond) do { if (!(cond)) atomicMax(S.sync + 1, 100000 + __LINE__); } while (0)
+#elif defined(GENLIB_SOFTCHECK)       // record the source line of the FIRST violated bound in the layer's error word, go on
+#define CHECK(cond) do { if (!(cond)) atomicCAS(S.err, 0, 100000 + __LINE__); } while (0)
 #else
 #define CHECK(cond) do { } while (0)
 #endif
@@ -82,7 +82,8 @@ struct StripArgs {
     int32_t ring_off;    // byte offset of the producer ring in dynamic shared memory (after the consumer's part)
     int64_t qstride;     // pairs per strip buffer (live tiles * kPTile * sw)
     void *Q;             // strip buffers
-    int32_t *sync;       // [1] error word, [2 + s] producer warps done with strip s, [2 + n_strips + s] consumer groups done
+    int32_t *sync;       // strip s: [16 s] producer CTAs done, [16 s + 8] consumer groups done (a 32-byte sector each)
+    int32_t *err;        // the layer's error word
     const int32_t *live_tiles;   // the live tiles of the layer's slot range: index | kTileCarried
     long long timeout_cycles;
     long long *prof;             // -DGENLIB_PROFILE: 8 cycle counters per CTA and role (else unused)
@@ -151,11 +152,17 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
     __shared__ __align__(8) unsigned long long s_cbar[kConsGroups];  // consumer group: "tile segments landed"
     __shared__ int s_ready[kConsGroups];
     __shared__ int s_ptinfo[kProdWarps][kMaxStages];                 // producer: live_tiles entry of the item in a ring slot
+    __shared__ int s_pcount[8];                                      // producer: warps of this CTA done with strip s (slot s & 7)
+    __shared__ int s_cdone;                                          // producer: strips below this one are known to be consumed
     const int warp_all = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int sw = S.sw, ft = S.ft, NS = S.n_strips;
-    int *const err = S.sync + 1, *const done_p = S.sync + 2, *const done_c = S.sync + 2 + NS;
+    int *const err = S.err;
+    constexpr int kSyncStride = 16;                                // ints per strip: every counter has its own 32-byte sector
+    int *const done_p = S.sync, *const done_c = S.sync + 8;        // done_p[kSyncStride * s], done_c[kSyncStride * s]
     P2 *const Qall = static_cast<P2 *>(S.Q);
+    if (threadIdx.x < 8) s_pcount[threadIdx.x] = 0;
     if (threadIdx.x == 0) {
+        s_cdone = 0;
         for (int st = 0; st < kMaxStages; st++) {
             mbar_init((unsigned)__cvta_generic_to_shared(&s_full[st]), 2 * ft);
             mbar_init((unsigned)__cvta_generic_to_shared(&s_empty[st]), kProdWarps);
@@ -184,34 +191,55 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
         const int myrow = pw * rpw + lane;                         // (lanes < rpw) 0 .. 2 ft - 1: fathers, then mothers
         const bool issuer = lane < rpw, mo = myrow >= ft;
         const int myf = mo ? myrow - ft : myrow;
+        const unsigned long long read_once = policy_evict_first();  // the parents' rows pass through L2 once
         const int cpw = ft / kProdWarps;                           // couples of an item whose member rows this warp writes
 
-        auto wait_for = [&](const int *counter, int target) {      // lane 0 spins, the warp follows
-            if (lane == 0 && target > 0) {
-                const long long t0 = clock64();
-                while (ld_acquire_gpu(counter) < target) {
-                    if (clock64() - t0 > S.timeout_cycles || ld_acquire_gpu(err) != 0) { atomicExch(err, 1); break; }
-                    __nanosleep(100);
+        // Strip t is consumed (every consumer group has counted off; they do so in strip order): lane 0 asks the CTA's
+        // note first, then the counter in L2 -- whoever learns it leaves a note for the other producer warps.
+        auto wait_consumed = [&](int t) {
+            if (lane == 0 && t >= 0) {
+                if (*reinterpret_cast<volatile int *>(&s_cdone) <= t) {
+                    const long long t0 = clock64();
+                    unsigned polls = 0;
+                    while (ld_acquire_gpu(done_c + kSyncStride * t) < S.n_cons) {
+                        if (clock64() - t0 > S.timeout_cycles) { atomicCAS(err, 0, 1); break; }
+                        if ((++polls & 31u) == 0 && ld_acquire_gpu(err) != 0) break;   // somebody else gave up: drain
+                        __nanosleep(200);
+                    }
+                    atomicMax(&s_cdone, t + 1);
                 }
+                __threadfence_block();
             }
             __syncwarp();
         };
-        // This warp's share of a strip is done: its pairs were written with ordinary stores and will be read with
-        // bulk copies (async proxy), so every writer orders its stores against that proxy before the warp's release.
-        auto produced = [&](int *counter) {
+        // This warp's share of strip s is done; the CTA's last warp tells everybody.  Lane 0 releases the warp's pairs
+        // (ordinary stores that the consumers read with bulk copies: ordered against the async proxy by every writer)
+        // at gpu scope before it counts, the last warp once more after it has seen the others' counts.
+        auto produced = [&](int s) {
             asm volatile("fence.proxy.async.global;" ::: "memory");
             __syncwarp();
-            if (lane == 0) { __threadfence(); atomicAdd(counter, 1); }
+            if (lane == 0) {
+                __threadfence();
+                if (atomicAdd(&s_pcount[s & 7], 1) == kProdWarps - 1) {
+                    s_pcount[s & 7] = 0;
+                    __threadfence();
+                    atomicAdd(done_p + kSyncStride * s, 1);
+                }
+            }
         };
         // the parent row this lane copies for items of strip s, half pt (nullptr: unknown parent, or not an issuer)
-        auto row_ptr = [&](int s, int pt) -> const T * {
-            if (!issuer || s >= NS) return nullptr;
+        // (fetched raw a strip ahead -- no branch on what is loaded -- and resolved when the strip starts)
+        auto row_raw = [&](int s, int pt, int &o, int &lr) {
+            o = -1; lr = 0;
             const int Fl = s * sw + pt * ft + myf;
-            if (Fl >= L.own_nf) return nullptr;
-            const int F = L.own_f0 + Fl;
-            const int o = mo ? L.fam_pm_owner[F] : L.fam_pf_owner[F];
-            if (o < 0) return nullptr;
-            return static_cast<const T *>(PT.A[o]) + (int64_t)(mo ? L.fam_pm_lrow[F] : L.fam_pf_lrow[F]) * ld + L.rt_lo;
+            if (issuer && s < NS && Fl < L.own_nf) {
+                const int F = L.own_f0 + Fl;
+                o = mo ? L.fam_pm_owner[F] : L.fam_pf_owner[F];
+                lr = mo ? L.fam_pm_lrow[F] : L.fam_pf_lrow[F];
+            }
+        };
+        auto row_ptr = [&](int o, int lr) -> const T * {
+            return o >= 0 ? static_cast<const T *>(PT.A[o]) + (int64_t)lr * ld + L.rt_lo : nullptr;
         };
         // members of the couples whose rows this warp writes against carried columns: lane j < npt cpw holds couple
         // (pt = j / cpw, qd = j % cpw) of strip s: its member range and the rows of its first two members
@@ -234,30 +262,31 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
         int is = 0, ii = k;                                        // issue cursor (copies under way)
         while (is < NS && ii >= NI) { ii -= NI; is++; }
         int cs = is, ci = ii;                                      // write cursor
-        int rs = -1;                                               // strip whose rows are in rp0 / rp1; np0 / np1: strip rs + 1
-        const T *rp0 = nullptr, *rp1 = nullptr, *np0 = nullptr, *np1 = nullptr;
+        int rs = -1;                                               // strip whose rows are in rp0 / rp1; strip rs + 1: raw in no / nl
+        const T *rp0 = nullptr, *rp1 = nullptr;
+        int no0 = -1, no1 = -1, nl0 = 0, nl1 = 0;
         int islot = 0;                                             // ring slot of the next issue ...
         unsigned iuse = 0;                                         // ... and how often it has been filled before
         int itile = is < NS ? S.live_tiles[ii >> lnpt] : 0;        // live_tiles entry of the item at the issue cursor
         auto issue = [&]() {                                       // warp-collective
             if (is >= NS) return;
             if (rs != is) {                                        // rows of a new strip (fetched a strip ahead)
-                if (rs >= 0 && is == rs + 1) { rp0 = np0; rp1 = np1; }
-                else { rp0 = row_ptr(is, 0); rp1 = npt > 1 ? row_ptr(is, 1) : nullptr; }
+                if (!(rs >= 0 && is == rs + 1)) { row_raw(is, 0, no0, nl0); if (npt > 1) row_raw(is, 1, no1, nl1); }
+                rp0 = row_ptr(no0, nl0); rp1 = npt > 1 ? row_ptr(no1, nl1) : nullptr;
                 rs = is;
-                np0 = row_ptr(is + 1, 0); np1 = npt > 1 ? row_ptr(is + 1, 1) : nullptr;
+                row_raw(is + 1, 0, no0, nl0); if (npt > 1) row_raw(is + 1, 1, no1, nl1);
             }
             const unsigned fullb = full0 + 8u * islot;
             // every producer warp has read what the slot held before (they arrive after their last shared load;
             // the bulk copy below may then overwrite it without a proxy fence)
-            if (iuse > 0 && !mbar_wait(empty0 + 8u * islot, (iuse - 1) & 1u)) atomicExch(err, 2);
+            if (iuse > 0 && !mbar_wait(empty0 + 8u * islot, (iuse - 1) & 1u)) atomicCAS(err, 0, 2);
             if (lane == 0) s_ptinfo[pw][islot] = itile;
             if (issuer) {
                 const T *src = (ii & (npt - 1)) ? rp1 : rp0;
                 const unsigned dst = rbase + (unsigned)(islot * STAGE + myrow * RB);
                 if (src) {
                     mbar_arrive_expect_tx(fullb, ROWB);
-                    bulk_g2s(dst, src + (size_t)(itile & (kTileCarried - 1)) * kPTile, ROWB, fullb);
+                    bulk_g2s_hint(dst, src + (size_t)(itile & (kTileCarried - 1)) * kPTile, ROWB, fullb, read_once);
                 } else {                                           // unknown parent: contributes 0 (compute.jl:111-126)
                     for (unsigned c = 0; c < ROWB; c += 16) zero16_shared(dst + c);
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -284,10 +313,10 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
         constexpr uint32_t kLive4 = 0x01010101u * kFlagLive;
         while (cs < NS) {
             if (cs != cur) {                                       // count off the strips that are behind us
-                for (int s = max(cur, 0); s < cs; s++) produced(done_p + s);
+                for (int s = max(cur, 0); s < cs; s++) produced(s);
                 cur = cs;
                 PROF_MARK(0);
-                wait_for(done_c + (cs - S.nbuf), cs >= S.nbuf ? S.n_cons : 0);    // the strip that used this buffer is consumed
+                wait_consumed(cs - S.nbuf);                        // the strip that used this buffer before
                 PROF_MARK(1);
                 if (L.any_carried) {
                     cmi = (ms >= 0 && cs == ms + 1) ? nmi : mem_info(cs);
@@ -295,7 +324,7 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
                     nmi = mem_info(cs + 1);
                 }
             }
-            if (!mbar_wait(full0 + 8u * cslot, cuse & 1u)) atomicExch(err, 2);
+            if (!mbar_wait(full0 + 8u * cslot, cuse & 1u)) atomicCAS(err, 0, 2);
             PROF_MARK(2);
             issue();                                               // refills the slot everybody left an item ago
             PROF_MARK(3);
@@ -377,9 +406,9 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
 #pragma unroll
                     for (int e = 0; e < 4; e++) rr[e] = half_sum_mode<STORED>(x[e], y[e]);
                     CHECK(col0 + 3 < ld && mb >= 0 && me <= L.n_new);
-                    store4(A + (int64_t)lr0 * ld + col0, rr);
-                    if (me > mb + 1) store4(A + (int64_t)lr1 * ld + col0, rr);
-                    for (int m = mb + 2; m < me; m++) store4(A + (int64_t)L.mem_lrow[m] * ld + col0, rr);
+                    store4(A + (int64_t)lr0 * ld + col0, rr, 0);
+                    if (me > mb + 1) store4(A + (int64_t)lr1 * ld + col0, rr, 0);
+                    for (int m = mb + 2; m < me; m++) store4(A + (int64_t)L.mem_lrow[m] * ld + col0, rr, 0);
                 }
             }
             PROF_MARK(5);
@@ -392,7 +421,7 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
                 live8 = tile_flags(tinfo);
             }
         }
-        for (int s = max(cur, 0); s < NS; s++) produced(done_p + s);
+        for (int s = max(cur, 0); s < NS; s++) produced(s);
         PROF_MARK(0);
         PROF_FLUSH(0, pw == 0 && lane == 0);
         return;
@@ -414,9 +443,11 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
     auto wait_for = [&](const int *counter, int target) {
         if (tid == 0 && target > 0) {
             const long long t0 = clock64();
+            unsigned polls = 0;
             while (ld_acquire_gpu(counter) < target) {
-                if (clock64() - t0 > S.timeout_cycles || ld_acquire_gpu(err) != 0) { atomicExch(err, 1); break; }
-                __nanosleep(100);
+                if (clock64() - t0 > S.timeout_cycles) { atomicCAS(err, 0, 1); break; }
+                if ((++polls & 31u) == 0 && ld_acquire_gpu(err) != 0) break;   // somebody else gave up: drain
+                __nanosleep(200);
             }
         }
         cons_sync();
@@ -428,7 +459,7 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
         cons_sync();
         if (tid == 0) atomicAdd(counter, 1);
     };
-    const int prod_arrivals = S.n_prod * kProdWarps;               // what done_p[s] reaches when strip s is complete
+    const int prod_arrivals = S.n_prod;                            // what done_p[s] reaches when strip s is complete
     constexpr int kMetaSlots = 3, kMetaInts = 4 * kMTile;          // per slot: qrow[128] | couple[128] | rank[128] | slot[128]
     struct RowMeta { unsigned rowoff; int rank; long long bytes; };   // Va row offset, rank, byte offset of the frontier row
     unsigned char *sm = dyn_smem + (size_t)grp * S.cons_bytes;
@@ -492,7 +523,7 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
         n_staged++;
     };
     auto await_tile = [&]() {                                      // all threads
-        if (!mbar_wait(sbar, n_landed & 1u)) atomicExch(err, 2);
+        if (!mbar_wait(sbar, n_landed & 1u)) atomicCAS(err, 0, 2);
         n_landed++;
     };
 
@@ -527,7 +558,7 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
     while (c0.s < NS) {
         const int s = c0.s, it = c0.it;
         if (s != cur) {
-            for (int t = max(cur, 0); t < s; t++) consumed(done_c + t);
+            for (int t = max(cur, 0); t < s; t++) consumed(done_c + kSyncStride * t);
             cur = s;
             F0 = L.own_f0 + s * sw;
             nFs = min(sw, L.own_nf - s * sw);
@@ -536,15 +567,18 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
             else { strip_bounds(s, ms0, ms1); strip_row(s, ms0, ms1, 0, rf, rk, rl, rsl); }
             n_rows = ms1 - ms0;
             put_row(rf, rk, rl, rsl);                              // (read after the barriers below)
-            // the next strip's rows, and the bounds of the one after, are fetched now and used a strip later
-            if (s + 1 < NS) {
-                if (pre2_s == s + 1) { pre_ms0 = pre2_ms0; pre_ms1 = pre2_ms1; } else strip_bounds(s + 1, pre_ms0, pre_ms1);
-                strip_row(s + 1, pre_ms0, pre_ms1, 0, pre_f, pre_rank, pre_lrow, pre_slot);
-                pre_s = s + 1;
-                if (s + 2 < NS) { strip_bounds(s + 2, pre2_ms0, pre2_ms1); pre2_s = s + 2; }
+            // the rows of the strip this group visits next, and the bounds of the one after, are fetched now and used
+            // a strip later (the next items are known: c1, c2, c3)
+            const int ns = c1.s != s ? c1.s : c2.s != s ? c2.s : c3.s != s ? c3.s : s + 1;
+            const int ns2 = (c1.s != s && c1.s != ns) ? c1.s : (c2.s != s && c2.s != ns) ? c2.s : (c3.s != s && c3.s != ns) ? c3.s : ns + 1;
+            if (ns < NS) {
+                if (pre2_s == ns) { pre_ms0 = pre2_ms0; pre_ms1 = pre2_ms1; } else strip_bounds(ns, pre_ms0, pre_ms1);
+                strip_row(ns, pre_ms0, pre_ms1, 0, pre_f, pre_rank, pre_lrow, pre_slot);
+                pre_s = ns;
+                if (ns2 < NS) { strip_bounds(ns2, pre2_ms0, pre2_ms1); pre2_s = ns2; }
             }
             PROF_MARK(2);
-            if (!staged) wait_for(done_p + s, prod_arrivals);     // the strip's pairs are complete (in L2)
+            if (!staged) wait_for(done_p + kSyncStride * s, prod_arrivals);   // the strip's pairs are complete (in L2)
             else cons_sync();
             PROF_MARK(1);
         }
@@ -562,24 +596,41 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
                 if (myr < r1) fl = L.flags[myr];
                 if (fl & kFlagCarried) { own = L.live_owner[myr]; lrw = L.live_lrow[myr]; tm = L.tile_map[myr / kPTile]; }
                 unsigned todo = __ballot_sync(0xffffffffu, (fl & kFlagCarried) != 0);
-                while (todo) {
-                    const int j = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    const int row = base + j;
-                    const int o = __shfl_sync(0xffffffffu, own, j), lr = __shfl_sync(0xffffffffu, lrw, j), t = __shfl_sync(0xffffffffu, tm, j);
-                    CHECK(t >= 0 && o >= 0 && lr >= 0);
-                    T *dst = static_cast<T *>(PT.A[o]) + (int64_t)lr * ld;
-                    const P2 *q = Q + ((size_t)t * kPTile + (size_t)(row % kPTile)) * sw;
-                    T v0 = (T)0, v1 = (T)0;
-                    if (lane < nFs) { const P2 p = __ldcg(q + lane); v0 = (T)half_sum_mode<STORED>((double)p.x, (double)p.y); }
-                    if (lane + 32 < nFs) { const P2 p = __ldcg(q + lane + 32); v1 = (T)half_sum_mode<STORED>((double)p.x, (double)p.y); }
-                    for (int m = lane; m < ((n_rows + 31) & ~31); m += 32) {
-                        const int mm = min(m, n_rows - 1);
-                        int fi, sl;
-                        if (cached) { const int cm = colmeta[mm]; fi = cm >> 24; sl = cm & 0xffffff; }
-                        else { fi = L.mem_fam[ms0 + mm] - F0; sl = L.mem_slot[ms0 + mm]; }
-                        const T a = __shfl_sync(0xffffffffu, v0, fi & 31), b = __shfl_sync(0xffffffffu, v1, fi & 31);
-                        if (m < n_rows) dst[sl] = fi < 32 ? a : b;
+                while (todo) {                                     // four carried rows at a time: one L2 round trip for their pairs
+                    int jj[4];
+                    P2 p0[4], p1[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        jj[u] = todo ? __ffs(todo) - 1 : -1;
+                        todo &= todo - 1;                          // (0 stays 0)
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        p0[u].x = p0[u].y = p1[u].x = p1[u].y = (T)0;
+                        if (jj[u] >= 0) {
+                            const int t = __shfl_sync(0xffffffffu, tm, jj[u]);
+                            CHECK(t >= 0);
+                            const P2 *q = Q + ((size_t)t * kPTile + (size_t)((base + jj[u]) % kPTile)) * sw;
+                            if (lane < nFs) p0[u] = __ldcg(q + lane);
+                            if (lane + 32 < nFs) p1[u] = __ldcg(q + lane + 32);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        if (jj[u] < 0) continue;
+                        const int o = __shfl_sync(0xffffffffu, own, jj[u]), lr = __shfl_sync(0xffffffffu, lrw, jj[u]);
+                        CHECK(o >= 0 && lr >= 0);
+                        T *dst = static_cast<T *>(PT.A[o]) + (int64_t)lr * ld;
+                        const T v0 = (T)half_sum_mode<STORED>((double)p0[u].x, (double)p0[u].y);
+                        const T v1 = (T)half_sum_mode<STORED>((double)p1[u].x, (double)p1[u].y);
+                        for (int m = lane; m < ((n_rows + 31) & ~31); m += 32) {
+                            const int mm = min(m, n_rows - 1);
+                            int fi, sl;
+                            if (cached) { const int cm = colmeta[mm]; fi = cm >> 24; sl = cm & 0xffffff; }
+                            else { fi = L.mem_fam[ms0 + mm] - F0; sl = L.mem_slot[ms0 + mm]; }
+                            const T a = __shfl_sync(0xffffffffu, v0, fi & 31), b = __shfl_sync(0xffffffffu, v1, fi & 31);
+                            if (m < n_rows) __stcs(dst + sl, fi < 32 ? a : b);
+                        }
                     }
                 }
             }
@@ -611,7 +662,7 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
         // is the next item's strip produced?  Asked now, answered after the arithmetic (an L2 round trip)
         const bool peek_next = is_tile(c1) && c1.s != s;
         int peek = 0;
-        if (tid == 0 && peek_next) peek = ld_acquire_gpu(done_p + c1.s);
+        if (tid == 0 && peek_next) peek = ld_acquire_gpu(done_p + kSyncStride * c1.s);
         {
             const int fl = tid & (sw - 1), g0 = tid >> lsw, gstep = kGroupThreads >> lsw;
             if (fl < nFs) {
@@ -678,7 +729,7 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
                             m[u] = rowmeta[r + u];
                             CHECK(m[u].rowoff < (unsigned)(sw * kVPitch * (int)sizeof(T)) && m[u].bytes >= 0);
                         }
-                        CHECK(off[0] < 260u && off[1] < 260u && off[2] < 260u && off[3] < 260u);
+                        CHECK(off[0] < kVPitch * sizeof(T) && off[1] < kVPitch * sizeof(T) && off[2] < kVPitch * sizeof(T) && off[3] < kVPitch * sizeof(T));
                         CHECK(sj[0] >= 0 && sj[0] < ld);
                         T v[4][4];
 #pragma unroll
@@ -692,7 +743,7 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
                             if (vec) store_vec4(row + sj[0], v[u]);
                             else {
 #pragma unroll
-                                for (int q = 0; q < 4; q++) if (q < ncol) row[sj[q]] = v[u][q];
+                                for (int q = 0; q < 4; q++) if (q < ncol) __stcs(row + sj[q], v[u][q]);
                             }
                         }
                     }
@@ -702,7 +753,7 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
                         T *row = reinterpret_cast<T *>(Ab + m.bytes);
 #pragma unroll
                         for (int q = 0; q < 4; q++)
-                            if (q < ncol) row[sj[q]] = lds<T>((m.rank > rj[q] ? va_s : vb_s) + m.rowoff + off[q]);
+                            if (q < ncol) __stcs(row + sj[q], lds<T>((m.rank > rj[q] ? va_s : vb_s) + m.rowoff + off[q]));
                     }
                 }
                 // own diagonal entries (compute.jl:148-155): rows of this pass that are also columns of this tile,
@@ -726,7 +777,7 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
         n_item++;
         PROF_MARK(6);
     }
-    for (int t = max(cur, 0); t < NS; t++) consumed(done_c + t);
+    for (int t = max(cur, 0); t < NS; t++) consumed(done_c + kSyncStride * t);
     PROF_MARK(0);
     PROF_FLUSH(1, tid == 0);
 }
