@@ -247,6 +247,7 @@ size_t off_A() { return kFlagBytes; }
 // is worth more than the part of the oldest buffer that spills to DRAM (C3: 72.3 ms with four or five buffers,
 // 84.9 ms with three kept in a persisting access-policy window; profiles/r02/README.md).
 constexpr size_t kStripBudget = (size_t)96 << 20;
+constexpr int kMaxGangs = 16, kGangItems = 4;    // gangs of CTAs per layer (at most), producer items a strip should bring every CTA
 
 int env_int(const char *name, int dflt) {
     const char *s = std::getenv(name);
@@ -257,11 +258,10 @@ LayerLaunch shape_layer(const Plan &P, int t, int rank, size_t es, int sm_count)
     const Layer &L = P.layers[t];
     LayerLaunch out;
     StripArgs &s = out.s;
-    const int32_t *fb = P.fam_base.data() + L.base_off, *mb = P.mem_base.data() + L.base_off;
-    const int64_t own_nf = fb[rank + 1] - fb[rank], own_nm = mb[rank + 1] - mb[rank];
+    const int32_t *fb = P.fam_base.data() + L.base_off;
+    const int64_t own_nf = fb[rank + 1] - fb[rank];
     if (L.n_new == 0 || own_nf <= 0) return out;
     const bool live = L.live_before > 0;
-    const int64_t rt_rows = live ? L.rt_rows : 0;
     const int64_t q_rows = live ? (int64_t)L.n_live_tiles * kPTile : 0;     // rows of a strip buffer
     const size_t pair = 2 * es;
     // strip width: the widest one whose buffers fit the persisting part of L2 at least `min_buf` times (and
@@ -279,29 +279,36 @@ LayerLaunch shape_layer(const Plan &P, int t, int rank, size_t es, int sm_count)
     // couples per producer item: 32 rows of 512 B (float) / 16 rows of 1 KB (double); at most two items per live tile
     s.ft = std::max(sw / 2, std::min(sw, std::max(8, env_int("GENLIB_FT", es == 4 ? 32 : 16))));
     if (s.ft > 32) s.ft = 32;
-    s.nbuf = (int)std::max<size_t>(2, std::min<size_t>((size_t)std::max(2, env_int("GENLIB_MAX_NBUF", 8)), budget / strip_bytes));
     s.n_strips = (int)((own_nf + sw - 1) / sw);
     s.qstride = (int64_t)(strip_bytes / pair);
-    // producer items: 2 ft parent rows x one live tile; consumer items: member tiles, then blocks of carried rows
+    // producer items: 2 ft parent rows x one live tile; consumer items: the member tiles
     s.n_pitems = live ? (sw / s.ft) * L.n_live_tiles : 0;
-    const double rows_per_strip = (double)own_nm / (double)own_nf * sw;        // members of a strip
-    int n_mblocks = 0;
-    s.mrows = 1;
-    if (L.carried > 0 && rt_rows > 0) {                     // ~64 KB of mirrored columns per block, whole warps' worth of rows
-        const int64_t mr = (int64_t)(65536.0 / std::max(1.0, rows_per_strip * es));
-        s.mrows = (int)std::max<int64_t>(32, std::min<int64_t>(mr, 4096)) / 32 * 32;
-        n_mblocks = (int)((rt_rows + s.mrows - 1) / s.mrows);
+    s.n_citems = L.n_mtiles;
+    // One CTA per SM: four producer warps and a consumer group of eight.  Every CTA of a gang takes part in the
+    // hand-over of each of the gang's strips, whether it has an item there or not, and a switch of strips costs a
+    // CTA some microseconds of dependent loads: a strip should bring every CTA several items.  Layers with short
+    // strips (few live tiles) therefore split the CTAs into G gangs that work on G strips side by side
+    // (profiles/r02/README.md: C5 245 -> ... ms, genea140 7.3 -> ... ms); C3-sized layers stay with one gang.
+    const int max_buf = (int)std::max<size_t>(2, budget / strip_bytes);
+    int G = 1;
+    if (live) {
+        const int forced = env_int("GENLIB_GANGS", 0);
+        const int want_items = std::max(1, env_int("GENLIB_GANG_ITEMS", kGangItems));
+        if (forced > 0) G = forced;
+        else while (G < kMaxGangs && (int64_t)s.n_pitems * G < (int64_t)want_items * sm_count) G *= 2;
+        while (G > 1 && (2 * G > max_buf || s.n_strips < 2 * G || G > sm_count / 4)) G /= 2;
     }
-    s.n_citems = L.n_mtiles + n_mblocks;
-    // one CTA per SM: four producer warps and a consumer group of sixteen
-    // Layers with few items per strip run faster on 7/8 of the SMs (C5: 148 CTAs 246 ms, 128 to 136 CTAs 148 ms;
-    // genea140: 8.9 -> 6.4 ms): every CTA takes part in every strip's hand-over, whether it has an item there or
-    // not.  Layers with several items per CTA and strip want every SM (C3: 70.8 ms on 148, 74.3 ms on 132).
-    const int few = (sw / s.ft) * L.n_live_tiles < 3 * sm_count / 2 ? sm_count - sm_count / 8 : sm_count;
-    const int ctas = std::max(1, std::min(sm_count, env_int("GENLIB_CTAS_PER_ROLE", few)));
-    s.n_prod = std::min(ctas, s.n_pitems);
+    s.gangs = G;
+    // (at most eight buffers per gang: the producer warps of a CTA count themselves off in eight slots by strip)
+    s.nbuf = std::min(8 * G, std::max(2 * G, std::min(std::max(2 * G, env_int("GENLIB_MAX_NBUF", 8)), max_buf)) / G * G);
+    // (one gang) layers with few items per strip run faster on 7/8 of the SMs (C5: 148 CTAs 246 ms, 128 to 136 CTAs
+    // 148 ms; genea140: 8.9 -> 6.4 ms); layers with several items per CTA and strip want every SM (C3: 70.8 ms on
+    // 148, 74.3 ms on 132).
+    const int few = G == 1 && (sw / s.ft) * L.n_live_tiles < 3 * sm_count / 2 ? sm_count - sm_count / 8 : sm_count;
+    const int ctas = std::max(1, std::min(sm_count, env_int("GENLIB_CTAS_PER_ROLE", few))) / G;   // per gang
+    s.n_prod = G * std::min(ctas, s.n_pitems);
     s.groups = groups;
-    s.n_cons = std::min(ctas * groups, s.n_citems);
+    s.n_cons = G * std::min(ctas * groups, s.n_citems);
     const size_t stage = (size_t)2 * s.ft * (kPTile * es + 16);
     const size_t cons_bytes = layer_consumer_bytes(sw, es);
     const size_t smem_cap = (size_t)227 * 1024 - 2048;      // (static shared memory and the driver's share)
@@ -426,8 +433,8 @@ int launch_layers(genlib_engine &E, bool timed) {
         double acc[2][8] = {};
         for (int b = 0; b < pl.grid; b++) for (int r = 0; r < 2; r++) for (int i = 0; i < 8; i++) acc[r][i] += (double)h[((size_t)b * 2 + r) * 8 + i];
         std::fprintf(stderr, "[prof] producers %d consumers %d strips %d (avg kcycles per CTA)\n", pl.s.n_prod, pl.s.n_cons, pl.s.n_strips);
-        std::fprintf(stderr, "[prof] producer: other %.0f wait_consumers %.0f mbar %.0f issue %.0f transpose %.0f member_rows %.0f\n",
-                     acc[0][0] / pl.s.n_prod / 1e3, acc[0][1] / pl.s.n_prod / 1e3, acc[0][2] / pl.s.n_prod / 1e3, acc[0][3] / pl.s.n_prod / 1e3, acc[0][4] / pl.s.n_prod / 1e3, acc[0][5] / pl.s.n_prod / 1e3);
+        std::fprintf(stderr, "[prof] producer: other %.0f wait_consumers %.0f mbar %.0f issue %.0f transpose %.0f member_rows %.0f mirror %.0f\n",
+                     acc[0][0] / pl.s.n_prod / 1e3, acc[0][1] / pl.s.n_prod / 1e3, acc[0][2] / pl.s.n_prod / 1e3, acc[0][3] / pl.s.n_prod / 1e3, acc[0][4] / pl.s.n_prod / 1e3, acc[0][5] / pl.s.n_prod / 1e3, acc[0][6] / pl.s.n_prod / 1e3);
         std::fprintf(stderr, "[prof] consumer: other %.0f wait_producers %.0f switch %.0f stage_wait %.0f compute %.0f stage_issue %.0f expand %.0f mirror %.0f\n",
                      acc[1][0] / pl.s.n_cons / 1e3, acc[1][1] / pl.s.n_cons / 1e3, acc[1][2] / pl.s.n_cons / 1e3, acc[1][3] / pl.s.n_cons / 1e3, acc[1][4] / pl.s.n_cons / 1e3, acc[1][5] / pl.s.n_cons / 1e3, acc[1][6] / pl.s.n_cons / 1e3, acc[1][7] / pl.s.n_cons / 1e3);
     }
@@ -545,7 +552,7 @@ void account_layers(genlib_engine &E) {
         o.dram_write_bytes = (double)own_nm * ((double)L.n_new + carried) * es + ((double)(L.carried - carried_remote)) * (double)own_nm * es;
         // L2: the strip buffers, written once and read back per couple of the layer
         o.l2_bytes = (double)(rows_local + rows_remote > 0 ? (f1 - f0) : 0) * live * 2 * es +
-                     (double)parents_all * (double)(ll.s.n_strips * (int64_t)ll.s.sw) * 2 * es + carried * (double)(f1 - f0) * 2 * es;
+                     (double)parents_all * (double)(ll.s.n_strips * (int64_t)ll.s.sw) * 2 * es;
         // NVLink: remote parent rows read, own members' columns pushed into carried rows that live elsewhere
         o.nvlink_bytes = (double)rows_remote * live * es + (double)carried_remote * (double)own_nm * es;
     }

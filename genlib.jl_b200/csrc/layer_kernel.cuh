@@ -16,8 +16,9 @@
 //             across strips, from local HBM or a peer's over NVLink, handed from warp to warp with full /
 //             empty mbarriers (no CTA barrier) -- and write them transposed and interleaved,
 //                 Q[p][F] = (Psi[f_F, p], Psi[m_F, p])          for every live column p,
-//             into one of a few strip buffers that are pinned in L2 (persisting access-policy window);
-//             where the step carries columns over they also write the members' rows against them.
+//             into one of a few strip buffers that stay in L2; where the step carries individuals over they also
+//             write, from the same staged rows, the members' rows against the carried columns and the mirror
+//             image, the members' columns in the carried individuals' rows.
 //   CONSUMER  groups take tiles of couples G (ALL couples of the layer), stage Q[f_G][strip], Q[m_G][strip]
 //             -- two contiguous segments per couple, L2 hits -- which hold all four entries of every (F, G)
 //             pair in BOTH groupings,
@@ -25,15 +26,15 @@
 //                 F climbed: hs(hs(a.x, c.x), hs(a.y, c.y))     G climbed: hs(hs(a.x, a.y), hs(c.x, c.y))
 //             (hs(x, y) = 1/2 x + 1/2 y, one binary64 rounding), round ONCE to the storage type
 //             (compute.jl:296) and write the strip members' rows over the tile's member columns, picking
-//             the grouping by rank; the diagonal is 1/2 + 1/2 Psi[f, m] (compute.jl:148-155).  They also
-//             write the strip members' columns into the rows of the carried individuals (from Q[c][strip]).
+//             the grouping by rank; the diagonal is 1/2 + 1/2 Psi[f, m] (compute.jl:148-155).
 //
 // Every entry of the step is written exactly once, in contiguous row segments, by the rank that owns the
 // row; nothing but stored frontier rows crosses NVLink.  DRAM sees the compulsory traffic only: the parent
 // rows once, the new rows once.
 //
-// Flow control is static: the items of a role (producer: column tiles of a strip, consumer: member tiles and
-// blocks of carried rows) are numbered strip after strip and dealt round-robin to the CTAs.  Every producer
+// Flow control is static: the items of a role (producer: column tiles of a strip, consumer: member tiles) are numbered strip after strip and dealt round-robin to the CTAs.  A layer whose strips
+// hold too few items to occupy every SM splits the CTAs into GANGS that work on different strips side by side
+// (gang g takes strips g, g + G, ...): the hand-over of a strip then involves 1/G of the CTAs, G of them overlap.  Every producer
 // warp / consumer group counts itself off on the strip's counter when its share is done; consumers start a
 // strip when all producers have counted off, producers reuse a strip buffer when all consumers of the strip
 // that used it before have.  All CTAs are resident (one per SM), and a wait that lasts seconds raises the
@@ -70,15 +71,15 @@ struct StripArgs {
     int32_t sw;          // strip width: couples per strip (8, 16, 32 or 64)
     int32_t ft;          // couples per producer item (8, 16 or 32; sw or sw / 2)
     int32_t n_strips;    // strips of this rank's couples
-    int32_t nbuf;        // strip buffers in rotation
+    int32_t nbuf;        // strip buffers in rotation (a multiple of gangs: a buffer stays with one gang)
     int32_t stages;      // ring stages
-    int32_t n_prod;      // CTAs whose producer warps have items (0 when nothing is live)
-    int32_t n_cons;      // consumer groups that have items (groups per CTA of them live on one SM)
+    int32_t gangs;       // the CTAs work in this many independent gangs: gang g = CTA index mod gangs takes strips g, g + gangs, ...
+    int32_t n_prod;      // CTAs whose producer warps have items (0 when nothing is live; a multiple of gangs)
+    int32_t n_cons;      // consumer groups that have items (groups per CTA of them live on one SM; a multiple of gangs)
     int32_t groups;      // consumer groups per CTA in use (<= kConsGroups; two need strips of <= 32 couples: shared memory)
     int32_t cons_bytes;  // dynamic shared memory of one consumer group
     int32_t n_pitems;    // producer items per strip: (sw / ft) * live tiles
-    int32_t n_citems;    // consumer items per strip: member tiles + blocks of carried rows
-    int32_t mrows;       // live-range rows per block of carried rows
+    int32_t n_citems;    // consumer items per strip: the layer's member tiles
     int32_t ring_off;    // byte offset of the producer ring in dynamic shared memory (after the consumer's part)
     int64_t qstride;     // pairs per strip buffer (live tiles * kPTile * sw)
     void *Q;             // strip buffers
@@ -93,6 +94,15 @@ template <typename T> struct PairOf;
 template <> struct PairOf<float> { using type = float2; };
 template <> struct PairOf<double> { using type = double2; };
 
+// Polls read the counters RELAXED and acquire once when the wait is over: an acquire load invalidates the SM's whole
+// L1 (SASS CCTL.IVALL) every time it is issued, which a spinning thread does to every other warp of its SM (ncu: the
+// CCTL.IVALL of the wait loops held 17 % of all stall samples of a C5 layer).  The closing acquire is a load, not a
+// fence: a fence also waits for the thread's own outstanding row stores.
+__device__ __forceinline__ int ld_relaxed_gpu(const int *p) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ int ld_acquire_gpu(const int *p) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -123,10 +133,10 @@ __device__ __forceinline__ void couple_pair(double ax, double ay, double cx, dou
 
 inline size_t layer_ring_bytes(int ft, int stages, size_t es) { return (size_t)stages * 2 * ft * (kPTile * es + 16); }
 // consumer: staged parent-row segments of a couple tile (2 x kMaxTileFam rows x sw pairs), Va | Vb, a ring of
-// three tiles' metadata, the strip's member rows (row descriptor + column slot)
+// three tiles' metadata, the strip's member rows (row descriptors)
 inline size_t layer_consumer_bytes(int sw, size_t es) {
     const size_t b = (size_t)2 * kMaxTileFam * sw * 2 * es + (size_t)2 * sw * kVPitch * es + (size_t)3 * 4 * kMTile * 4 +
-                     (size_t)kRowCache * 16 + (size_t)kRowCache * 4;
+                     (size_t)kRowCache * 16;
     return (b + 127) / 128 * 128;
 }
 
@@ -178,8 +188,9 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
         // every item and transposes columns [w kProdCols, (w + 1) kProdCols) of it.  A dependency that does not
         // arrive in time sets the layer's error word (genlib_engine_run then fails with GENLIB_ECUDA); once it is
         // set nobody waits any more, so a broken schedule drains in seconds instead of hanging the device.
-        const int pw = warp_all - kConsWarps, k = blockIdx.x, NP = S.n_prod, NI = S.n_pitems;
-        if (k >= NP) return;
+        const int pw = warp_all - kConsWarps, G = S.gangs, NP = S.n_prod / G, NI = S.n_pitems;
+        if ((int)blockIdx.x >= S.n_prod) return;
+        const int gang = blockIdx.x % G, k = blockIdx.x / G;     // this CTA is producer k of NP in its gang
         PROF_DECL
         const int npt = sw / ft, lnpt = npt > 1 ? 1 : 0;          // items per live tile: 1 or 2
         const int RB = kPTile * (int)sizeof(T) + 16, STAGE = 2 * ft * RB;
@@ -201,11 +212,12 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
                 if (*reinterpret_cast<volatile int *>(&s_cdone) <= t) {
                     const long long t0 = clock64();
                     unsigned polls = 0;
-                    while (ld_acquire_gpu(done_c + kSyncStride * t) < S.n_cons) {
+                    while (ld_relaxed_gpu(done_c + kSyncStride * t) < S.n_cons / G) {
                         if (clock64() - t0 > S.timeout_cycles) { atomicCAS(err, 0, 1); break; }
-                        if ((++polls & 31u) == 0 && ld_acquire_gpu(err) != 0) break;   // somebody else gave up: drain
-                        __nanosleep(200);
+                        if ((++polls & 31u) == 0 && ld_relaxed_gpu(err) != 0) break;   // somebody else gave up: drain
+                        __nanosleep(100);
                     }
+                    ld_acquire_gpu(done_c + kSyncStride * t);
                     atomicMax(&s_cdone, t + 1);
                 }
                 __threadfence_block();
@@ -220,8 +232,8 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
             __syncwarp();
             if (lane == 0) {
                 __threadfence();
-                if (atomicAdd(&s_pcount[s & 7], 1) == kProdWarps - 1) {
-                    s_pcount[s & 7] = 0;
+                if (atomicAdd(&s_pcount[(s / G) & 7], 1) == kProdWarps - 1) {
+                    s_pcount[(s / G) & 7] = 0;
                     __threadfence();
                     atomicAdd(done_p + kSyncStride * s, 1);
                 }
@@ -257,10 +269,41 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
             }
             return m;
         };
-        // the items of this CTA, strip after strip: item g = s NI + i belongs to CTA g mod NP
-        auto advance = [&](int &s, int &i) { i += NP; while (s < NS && i >= NI) { i -= NI; s++; } };
-        int is = 0, ii = k;                                        // issue cursor (copies under way)
-        while (is < NS && ii >= NI) { ii -= NI; is++; }
+        // the same members as COLUMNS of the carried individuals' rows (the mirror image of the block above): the members
+        // of the ft couples of either half of strip s, in member order (= slot order), one per lane and chunk of 32:
+        // column slot | couple within the half << 24 (-1: none); the first two chunks of a half are kept in registers
+        // (a strip ahead), halves with more members than 64 look the rest up per item
+        struct MirInfo { int e0a, e1a, na, ba, e0b, e1b, nb, bb; };   // chunks 0 / 1, members, first member: halves a / b
+        auto mir_entry = [&](int F0h, int mb, int nm, int i) {      // member i of a half that starts at couple F0h, member mb
+            return i < nm ? (L.mem_slot[mb + i] | ((L.mem_fam[mb + i] - F0h) << 24)) : -1;
+        };
+        auto mir_info = [&](int s) {
+            MirInfo m; m.e0a = m.e1a = m.e0b = m.e1b = -1; m.na = m.nb = m.ba = m.bb = 0;
+            if (L.any_carried && s < NS) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int Fl = s * sw + h * ft;
+                    if (h < npt && Fl < L.own_nf) {
+                        const int F0h = L.own_f0 + Fl, mb = L.fam_start[F0h], nm = L.fam_start[L.own_f0 + min(Fl + ft, L.own_nf)] - mb;
+                        const int e0 = mir_entry(F0h, mb, nm, lane), e1 = mir_entry(F0h, mb, nm, 32 + lane);
+                        if (h == 0) { m.e0a = e0; m.e1a = e1; m.na = nm; m.ba = mb; } else { m.e0b = e0; m.e1b = e1; m.nb = nm; m.bb = mb; }
+                    }
+                }
+            }
+            return m;
+        };
+        // where the rows of the warp's kProdCols columns of a tile live (lane = column): read with the tile's flags
+        auto tile_rows = [&](int tinfo) -> T * {
+            if (tinfo & kTileCarried) {
+                const size_t at = (size_t)(tinfo & (kTileCarried - 1)) * kPTile + pw * kProdCols + lane;
+                return static_cast<T *>(PT.A[__ldg(L.live_owner + at)]) + (int64_t)__ldg(L.live_lrow + at) * ld;
+            }
+            return nullptr;
+        };
+        // the items of this CTA, strip after strip of its gang: item n = (s / G) NI + i belongs to CTA n mod NP of the gang
+        auto advance = [&](int &s, int &i) { i += NP; while (s < NS && i >= NI) { i -= NI; s += G; } };
+        int is = gang, ii = k;                                     // issue cursor (copies under way)
+        while (is < NS && ii >= NI) { ii -= NI; is += G; }
         int cs = is, ci = ii;                                      // write cursor
         int rs = -1;                                               // strip whose rows are in rp0 / rp1; strip rs + 1: raw in no / nl
         const T *rp0 = nullptr, *rp1 = nullptr;
@@ -271,10 +314,10 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
         auto issue = [&]() {                                       // warp-collective
             if (is >= NS) return;
             if (rs != is) {                                        // rows of a new strip (fetched a strip ahead)
-                if (!(rs >= 0 && is == rs + 1)) { row_raw(is, 0, no0, nl0); if (npt > 1) row_raw(is, 1, no1, nl1); }
+                if (!(rs >= 0 && is == rs + G)) { row_raw(is, 0, no0, nl0); if (npt > 1) row_raw(is, 1, no1, nl1); }
                 rp0 = row_ptr(no0, nl0); rp1 = npt > 1 ? row_ptr(no1, nl1) : nullptr;
                 rs = is;
-                row_raw(is + 1, 0, no0, nl0); if (npt > 1) row_raw(is + 1, 1, no1, nl1);
+                row_raw(is + G, 0, no0, nl0); if (npt > 1) row_raw(is + G, 1, no1, nl1);
             }
             const unsigned fullb = full0 + 8u * islot;
             // every producer warp has read what the slot held before (they arrive after their last shared load;
@@ -308,20 +351,25 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
         int cur = -1;                                              // strip this warp is writing
         int ms = -1;                                               // strip of cmi; nmi: strip ms + 1
         MemInfo cmi = mem_info(NS), nmi = cmi;
+        MirInfo cmr = mir_info(NS), nmr = cmr;
         int tinfo = cs < NS ? S.live_tiles[ci >> lnpt] : 0;
         uint32_t live8 = cs < NS ? tile_flags(tinfo) : 0u;
+        T *col_row = cs < NS ? tile_rows(tinfo) : nullptr;         // lane = column of the warp's share: where its row lives
         constexpr uint32_t kLive4 = 0x01010101u * kFlagLive;
         while (cs < NS) {
             if (cs != cur) {                                       // count off the strips that are behind us
-                for (int s = max(cur, 0); s < cs; s++) produced(s);
+                for (int s = cur < 0 ? gang : cur; s < cs; s += G) produced(s);
                 cur = cs;
                 PROF_MARK(0);
                 wait_consumed(cs - S.nbuf);                        // the strip that used this buffer before
                 PROF_MARK(1);
                 if (L.any_carried) {
-                    cmi = (ms >= 0 && cs == ms + 1) ? nmi : mem_info(cs);
+                    const bool seq = ms >= 0 && cs == ms + G;
+                    cmi = seq ? nmi : mem_info(cs);
+                    cmr = seq ? nmr : mir_info(cs);
                     ms = cs;
-                    nmi = mem_info(cs + 1);
+                    nmi = mem_info(cs + G);
+                    nmr = mir_info(cs + G);
                 }
             }
             if (!mbar_wait(full0 + 8u * cslot, cuse & 1u)) atomicCAS(err, 0, 2);
@@ -394,24 +442,83 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
             // ---- rows of the new members against this tile's carried columns (rounded once, compute.jl:296).
             //      Columns that are not carried receive values nobody reads. ----
             if (tinfo & kTileCarried) {
-                const int64_t col0 = (int64_t)L.rt_lo + (int64_t)tile * kPTile + 4 * lane;
-                for (int qd = 0; qd < cpw; qd++) {
-                    const int j = pt * cpw + qd, fi = pw * cpw + qd;
-                    const int mb = __shfl_sync(0xffffffffu, cmi.mb, j), me = __shfl_sync(0xffffffffu, cmi.me, j);
-                    const int lr0 = __shfl_sync(0xffffffffu, cmi.lr0, j), lr1 = __shfl_sync(0xffffffffu, cmi.lr1, j);
-                    if (me <= mb) continue;
-                    double x[4], y[4], rr[4];
-                    lds4(reinterpret_cast<const T *>(st + fi * RB) + 4 * lane, x);
-                    lds4(reinterpret_cast<const T *>(st + (ft + fi) * RB) + 4 * lane, y);
+                T *const Acol = A + (int64_t)L.rt_lo + (int64_t)tile * kPTile + 4 * lane;
+                CHECK((int64_t)L.rt_lo + (int64_t)tile * kPTile + 4 * lane + 3 < ld);
+                for (int qd = 0; qd < cpw; qd += 2) {              // two couples per step: their loads and sums overlap
+                    int cnt[2], lr0[2], lr1[2];
+                    double rr[2][4];
 #pragma unroll
-                    for (int e = 0; e < 4; e++) rr[e] = half_sum_mode<STORED>(x[e], y[e]);
-                    CHECK(col0 + 3 < ld && mb >= 0 && me <= L.n_new);
-                    store4(A + (int64_t)lr0 * ld + col0, rr, 0);
-                    if (me > mb + 1) store4(A + (int64_t)lr1 * ld + col0, rr, 0);
-                    for (int m = mb + 2; m < me; m++) store4(A + (int64_t)L.mem_lrow[m] * ld + col0, rr, 0);
+                    for (int u = 0; u < 2; u++) {
+                        const int j = pt * cpw + qd + u, fi = pw * cpw + qd + u;
+                        cnt[u] = __shfl_sync(0xffffffffu, cmi.me - cmi.mb, j);
+                        lr0[u] = __shfl_sync(0xffffffffu, cmi.lr0, j); lr1[u] = __shfl_sync(0xffffffffu, cmi.lr1, j);
+                        if (qd + u >= cpw) cnt[u] = 0;
+                        double x[4], y[4];
+                        lds4(reinterpret_cast<const T *>(st + min(fi, ft - 1) * RB) + 4 * lane, x);
+                        lds4(reinterpret_cast<const T *>(st + (ft + min(fi, ft - 1)) * RB) + 4 * lane, y);
+#pragma unroll
+                        for (int e = 0; e < 4; e++) rr[u][e] = half_sum_mode<STORED>(x[e], y[e]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        if (cnt[u] > 0) store4(Acol + (int64_t)lr0[u] * ld, rr[u], 0);
+                        if (cnt[u] > 1) store4(Acol + (int64_t)lr1[u] * ld, rr[u], 0);
+                        if (cnt[u] > 2) {
+                            const int mb = __shfl_sync(0xffffffffu, cmi.mb, pt * cpw + qd + u);
+                            CHECK(mb >= 0 && mb + cnt[u] <= L.n_new);
+                            for (int m = mb + 2; m < mb + cnt[u]; m++) store4(Acol + (int64_t)L.mem_lrow[m] * ld, rr[u], 0);
+                        }
+                    }
                 }
             }
             PROF_MARK(5);
+            // ---- and the mirror image: the carried individuals' rows against the columns of the new members.  Lane =
+            //      member (32 at a time, in slot order), four columns per shared load as above (members of a quarter warp
+            //      belong to at most 8 consecutive couples: no bank conflict); a store lays 32 members side by side in the
+            //      carried row: runs of 128 bytes that the halves of a strip and the neighbouring strips complete in L2. ----
+            if (tinfo & kTileCarried) {
+                const int nm = pt ? cmr.nb : cmr.na, mb = pt ? cmr.bb : cmr.ba;
+                for (int ch = 0; ch * 32 < nm; ch += 2) {          // two chunks of 32 members per pass
+                    int ea, eb;
+                    if (ch == 0) { ea = pt ? cmr.e0b : cmr.e0a; eb = pt ? cmr.e1b : cmr.e1a; }
+                    else {
+                        const int F0h = L.own_f0 + cs * sw + pt * ft;
+                        ea = mir_entry(F0h, mb, nm, ch * 32 + lane); eb = mir_entry(F0h, mb, nm, ch * 32 + 32 + lane);
+                    }
+                    const bool two = (ch + 1) * 32 < nm;           // (warp-uniform)
+                    const int sla = ea & 0xffffff, fa = ea >= 0 ? (ea >> 24) : 0, slb = eb & 0xffffff, fb = eb >= 0 ? (eb >> 24) : 0;
+                    CHECK((ea < 0 || (fa < ft && sla < ld)) && (eb < 0 || (fb < ft && slb < ld)));
+                    const T *xa = reinterpret_cast<const T *>(st + fa * RB) + pw * kProdCols, *xb = reinterpret_cast<const T *>(st + fb * RB) + pw * kProdCols;
+                    const int yoff = ft * RB / (int)sizeof(T);     // the mother's row, in elements
+#pragma unroll 2
+                    for (int g = 0; g < kProdCols / 4; g++) {
+                        const uint32_t w = __shfl_sync(0xffffffffu, live8, g);
+                        if ((w & (0x01010101u * kFlagCarried)) == 0u) continue;
+                        T *rp[4];
+#pragma unroll
+                        for (int c4 = 0; c4 < 4; c4++)
+                            rp[c4] = reinterpret_cast<T *>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(col_row), 4 * g + c4));
+                        double x[4], y[4];
+                        T va[4], vb[4];
+                        lds4(xa + 4 * g, x); lds4(xa + yoff + 4 * g, y);
+#pragma unroll
+                        for (int c4 = 0; c4 < 4; c4++) va[c4] = (T)half_sum_mode<STORED>(x[c4], y[c4]);
+                        if (two) {
+                            lds4(xb + 4 * g, x); lds4(xb + yoff + 4 * g, y);
+#pragma unroll
+                            for (int c4 = 0; c4 < 4; c4++) vb[c4] = (T)half_sum_mode<STORED>(x[c4], y[c4]);
+                        }
+#pragma unroll
+                        for (int c4 = 0; c4 < 4; c4++) {
+                            const bool on = ((w >> (8 * c4)) & kFlagCarried) != 0;
+                            CHECK(!on || rp[c4] != nullptr);
+                            if (on && ea >= 0) __stcs(rp[c4] + sla, va[c4]);
+                            if (two && on && eb >= 0) __stcs(rp[c4] + slb, vb[c4]);
+                        }
+                    }
+                }
+            }
+            PROF_MARK(6);
             __syncwarp();                                          // every lane has its values: the slot may be refilled
             if (lane == 0) mbar_arrive(empty0 + 8u * cslot);
             if (++cslot == S.stages) { cslot = 0; cuse++; }
@@ -419,15 +526,16 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
             if (cs < NS) {                                         // the next item's tile was noted when its copies were issued
                 tinfo = s_ptinfo[pw][cslot];
                 live8 = tile_flags(tinfo);
+                col_row = tile_rows(tinfo);
             }
         }
-        for (int s = max(cur, 0); s < NS; s++) produced(s);
+        for (int s = cur < 0 ? gang : cur; s < NS; s += G) produced(s);
         PROF_MARK(0);
         PROF_FLUSH(0, pw == 0 && lane == 0);
         return;
     }
 
-    // ===== consumer group: couple tiles -> the strip members' rows; carried rows <- the strip members' columns =====
+    // ===== consumer group: couple tiles -> the strip members' rows against all new members =====
     // Nothing the inner loops need comes from a dependent global load: tile descriptors travel three items
     // ahead in registers, a tile's metadata (its couples' strip-buffer rows, its members' couple / rank /
     // slot) two items ahead into a shared-memory ring with cp.async, its segments one item ahead, and the
@@ -435,8 +543,9 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
     // A CTA may run several groups side by side; each is its own consumer (own items, own shared memory, own barrier).
     const int grp = kConsGroups == 1 ? 0 : warp_all / kGroupWarps;
     const int tid = threadIdx.x - grp * kGroupThreads, warp = warp_all - grp * kGroupWarps;
-    const int k = blockIdx.x * S.groups + grp, NC = S.n_cons, NI = S.n_citems;
-    if (grp >= S.groups || k >= NC) return;
+    const int G = S.gangs, kk = blockIdx.x * S.groups + grp, NC = S.n_cons / G, NI = S.n_citems;
+    if (grp >= S.groups || kk >= S.n_cons) return;
+    const int gang = kk % G, k = kk / G;                           // this group is consumer k of NC in its gang
     auto cons_sync = [&]() { group_sync(grp); };
     PROF_DECL
     // Thread 0 spins, the group follows (see the producer's wait_for for the time-out).
@@ -444,11 +553,12 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
         if (tid == 0 && target > 0) {
             const long long t0 = clock64();
             unsigned polls = 0;
-            while (ld_acquire_gpu(counter) < target) {
+            while (ld_relaxed_gpu(counter) < target) {
                 if (clock64() - t0 > S.timeout_cycles) { atomicCAS(err, 0, 1); break; }
-                if ((++polls & 31u) == 0 && ld_acquire_gpu(err) != 0) break;   // somebody else gave up: drain
-                __nanosleep(200);
+                if ((++polls & 31u) == 0 && ld_relaxed_gpu(err) != 0) break;   // somebody else gave up: drain
+                __nanosleep(100);
             }
+            ld_acquire_gpu(counter);
         }
         cons_sync();
     };
@@ -459,7 +569,7 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
         cons_sync();
         if (tid == 0) atomicAdd(counter, 1);
     };
-    const int prod_arrivals = S.n_prod;                            // what done_p[s] reaches when strip s is complete
+    const int prod_arrivals = S.n_prod / G;                        // what done_p[s] reaches when strip s is complete
     constexpr int kMetaSlots = 3, kMetaInts = 4 * kMTile;          // per slot: qrow[128] | couple[128] | rank[128] | slot[128]
     struct RowMeta { unsigned rowoff; int rank; long long bytes; };   // Va row offset, rank, byte offset of the frontier row
     unsigned char *sm = dyn_smem + (size_t)grp * S.cons_bytes;
@@ -471,17 +581,15 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
     int *const meta = reinterpret_cast<int *>(sm);
     sm += (size_t)kMetaSlots * kMetaInts * sizeof(int);
     RowMeta *const rowmeta = reinterpret_cast<RowMeta *>(sm);
-    sm += (size_t)kRowCache * sizeof(RowMeta);
-    int *const colmeta = reinterpret_cast<int *>(sm);              // the same members as COLUMNS: slot | strip couple << 24
     const unsigned stg_s = (unsigned)__cvta_generic_to_shared(stg), meta_s = (unsigned)__cvta_generic_to_shared(meta);
     const unsigned va_s = (unsigned)__cvta_generic_to_shared(Va), vb_s = (unsigned)__cvta_generic_to_shared(Vb);
     const int lsw = 31 - __clz(sw);                                // sw is a power of two
     const int row_bytes = sw * (int)sizeof(P2);
 
     struct Cur { int s, it; };                                     // an item of this CTA: strip, index in the strip
-    auto advance = [&](Cur c) {                                    // item g = s NI + it belongs to CTA g mod NC
+    auto advance = [&](Cur c) {                                    // item n = (s / G) NI + it belongs to group n mod NC of the gang
         c.it += NC;
-        while (c.s < NS && c.it >= NI) { c.it -= NI; c.s++; }
+        while (c.s < NS && c.it >= NI) { c.it -= NI; c.s += G; }
         return c;
     };
     auto is_tile = [&](Cur c) { return c.s < NS && c.it < L.n_mtiles; };
@@ -530,24 +638,23 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
     // ---- the strip's member rows: prefetched one strip ahead (registers), cached in shared memory ----
     int cur = -1;                                                  // strip this group is in
     int F0 = 0, nFs = 0, ms0 = 0, ms1 = 0, n_rows = 0;
-    int pre_s = -1, pre_ms0 = 0, pre_ms1 = 0, pre_f = 0, pre_rank = 0, pre_lrow = 0, pre_slot = 0;   // strip pre_s: bounds, row ms0 + tid
+    int pre_s = -1, pre_ms0 = 0, pre_ms1 = 0, pre_f = 0, pre_rank = 0, pre_lrow = 0;   // strip pre_s: bounds, row ms0 + tid
     int pre2_s = -1, pre2_ms0 = 0, pre2_ms1 = 0;                   // strip pre2_s: bounds only
     auto strip_bounds = [&](int st, int &b0, int &b1) {
         const int f0 = L.own_f0 + st * sw, nf = min(sw, L.own_nf - st * sw);
         b0 = L.fam_start[f0]; b1 = L.fam_start[f0 + nf];
     };
-    auto strip_row = [&](int st, int b0, int b1, int first, int &f, int &rk, int &lr, int &sl) {   // row first + tid of strip st
+    auto strip_row = [&](int st, int b0, int b1, int first, int &f, int &rk, int &lr) {   // row first + tid of strip st
         const int im = min(b0 + first + tid, b1 - 1);
-        f = L.mem_fam[im] - (L.own_f0 + st * sw); rk = L.mem_ind[im]; lr = L.mem_lrow[im]; sl = L.mem_slot[im];
+        f = L.mem_fam[im] - (L.own_f0 + st * sw); rk = L.mem_ind[im]; lr = L.mem_lrow[im];
     };
-    auto put_row = [&](int f, int rk, int lr, int sl) {
+    auto put_row = [&](int f, int rk, int lr) {
         RowMeta m; m.rowoff = (unsigned)(f * kVPitch * (int)sizeof(T)); m.rank = rk; m.bytes = (long long)lr * ld * (long long)sizeof(T);
         rowmeta[tid] = m;
-        colmeta[tid] = sl | (f << 24);
     };
 
-    Cur c0; c0.s = 0; c0.it = k;
-    while (c0.s < NS && c0.it >= NI) { c0.it -= NI; c0.s++; }
+    Cur c0; c0.s = gang; c0.it = k;
+    while (c0.s < NS && c0.it >= NI) { c0.it -= NI; c0.s += G; }
     Cur c1 = advance(c0), c2 = advance(c1), c3 = advance(c2);
     int4 d0 = fetch_desc(c0), d1 = fetch_desc(c1), d2 = fetch_desc(c2);
     unsigned n_item = 0;                                           // items done: item j's metadata sits in ring slot j % 3
@@ -556,24 +663,24 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
     cp_async_commit();
     bool staged = false;                                           // the segments of c0 are on their way (or there)
     while (c0.s < NS) {
-        const int s = c0.s, it = c0.it;
+        const int s = c0.s;
         if (s != cur) {
-            for (int t = max(cur, 0); t < s; t++) consumed(done_c + kSyncStride * t);
+            for (int t = cur < 0 ? gang : cur; t < s; t += G) consumed(done_c + kSyncStride * t);
             cur = s;
             F0 = L.own_f0 + s * sw;
             nFs = min(sw, L.own_nf - s * sw);
-            int rf, rk, rl, rsl;
-            if (pre_s == s) { ms0 = pre_ms0; ms1 = pre_ms1; rf = pre_f; rk = pre_rank; rl = pre_lrow; rsl = pre_slot; }
-            else { strip_bounds(s, ms0, ms1); strip_row(s, ms0, ms1, 0, rf, rk, rl, rsl); }
+            int rf, rk, rl;
+            if (pre_s == s) { ms0 = pre_ms0; ms1 = pre_ms1; rf = pre_f; rk = pre_rank; rl = pre_lrow; }
+            else { strip_bounds(s, ms0, ms1); strip_row(s, ms0, ms1, 0, rf, rk, rl); }
             n_rows = ms1 - ms0;
-            put_row(rf, rk, rl, rsl);                              // (read after the barriers below)
+            put_row(rf, rk, rl);                                   // (read after the barriers below)
             // the rows of the strip this group visits next, and the bounds of the one after, are fetched now and used
             // a strip later (the next items are known: c1, c2, c3)
-            const int ns = c1.s != s ? c1.s : c2.s != s ? c2.s : c3.s != s ? c3.s : s + 1;
-            const int ns2 = (c1.s != s && c1.s != ns) ? c1.s : (c2.s != s && c2.s != ns) ? c2.s : (c3.s != s && c3.s != ns) ? c3.s : ns + 1;
+            const int ns = c1.s != s ? c1.s : c2.s != s ? c2.s : c3.s != s ? c3.s : s + G;
+            const int ns2 = (c1.s != s && c1.s != ns) ? c1.s : (c2.s != s && c2.s != ns) ? c2.s : (c3.s != s && c3.s != ns) ? c3.s : ns + G;
             if (ns < NS) {
                 if (pre2_s == ns) { pre_ms0 = pre2_ms0; pre_ms1 = pre2_ms1; } else strip_bounds(ns, pre_ms0, pre_ms1);
-                strip_row(ns, pre_ms0, pre_ms1, 0, pre_f, pre_rank, pre_lrow, pre_slot);
+                strip_row(ns, pre_ms0, pre_ms1, 0, pre_f, pre_rank, pre_lrow);
                 pre_s = ns;
                 if (ns2 < NS) { strip_bounds(ns2, pre2_ms0, pre2_ms1); pre2_s = ns2; }
             }
@@ -584,67 +691,6 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
         }
         const P2 *const Q = Qall + (size_t)(s % S.nbuf) * S.qstride;
         const int slot0 = (int)(n_item % kMetaSlots);
-
-        if (it >= L.n_mtiles) {
-            // ---- a block of carried rows: the strip members' columns, Psi[c, i] = RN(hs(Q[c][F_i])).  A warp takes 32
-            //      rows of the live range at a time: their flags / homes / tiles in one coalesced load each. ----
-            const int r0 = (it - L.n_mtiles) * S.mrows, r1 = min(L.rt_rows, r0 + S.mrows);
-            const bool cached = n_rows <= kRowCache;               // the strip's members sit in rowmeta / colmeta
-            for (int base = r0 + warp * 32; base < r1; base += kGroupWarps * 32) {
-                const int myr = base + lane;
-                int fl = 0, own = 0, lrw = 0, tm = 0;
-                if (myr < r1) fl = L.flags[myr];
-                if (fl & kFlagCarried) { own = L.live_owner[myr]; lrw = L.live_lrow[myr]; tm = L.tile_map[myr / kPTile]; }
-                unsigned todo = __ballot_sync(0xffffffffu, (fl & kFlagCarried) != 0);
-                while (todo) {                                     // four carried rows at a time: one L2 round trip for their pairs
-                    int jj[4];
-                    P2 p0[4], p1[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        jj[u] = todo ? __ffs(todo) - 1 : -1;
-                        todo &= todo - 1;                          // (0 stays 0)
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        p0[u].x = p0[u].y = p1[u].x = p1[u].y = (T)0;
-                        if (jj[u] >= 0) {
-                            const int t = __shfl_sync(0xffffffffu, tm, jj[u]);
-                            CHECK(t >= 0);
-                            const P2 *q = Q + ((size_t)t * kPTile + (size_t)((base + jj[u]) % kPTile)) * sw;
-                            if (lane < nFs) p0[u] = __ldcg(q + lane);
-                            if (lane + 32 < nFs) p1[u] = __ldcg(q + lane + 32);
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        if (jj[u] < 0) continue;
-                        const int o = __shfl_sync(0xffffffffu, own, jj[u]), lr = __shfl_sync(0xffffffffu, lrw, jj[u]);
-                        CHECK(o >= 0 && lr >= 0);
-                        T *dst = static_cast<T *>(PT.A[o]) + (int64_t)lr * ld;
-                        const T v0 = (T)half_sum_mode<STORED>((double)p0[u].x, (double)p0[u].y);
-                        const T v1 = (T)half_sum_mode<STORED>((double)p1[u].x, (double)p1[u].y);
-                        for (int m = lane; m < ((n_rows + 31) & ~31); m += 32) {
-                            const int mm = min(m, n_rows - 1);
-                            int fi, sl;
-                            if (cached) { const int cm = colmeta[mm]; fi = cm >> 24; sl = cm & 0xffffff; }
-                            else { fi = L.mem_fam[ms0 + mm] - F0; sl = L.mem_slot[ms0 + mm]; }
-                            const T a = __shfl_sync(0xffffffffu, v0, fi & 31), b = __shfl_sync(0xffffffffu, v1, fi & 31);
-                            if (m < n_rows) __stcs(dst + sl, fi < 32 ? a : b);
-                        }
-                    }
-                }
-            }
-            // keep the pipeline of descriptors and metadata moving
-            const int4 d3 = fetch_desc(c3);
-            if (is_tile(c2)) fetch_meta(d2, (int)((n_item + 2) % kMetaSlots));
-            cp_async_commit();
-            staged = false;
-            c0 = c1; c1 = c2; c2 = c3; c3 = advance(c3);
-            d0 = d1; d1 = d2; d2 = d3;
-            n_item++;
-            PROF_MARK(7);
-            continue;
-        }
 
         // ---- a member tile: its couples' segments (staged ahead unless the strip was not ready), Va | Vb, expansion ----
         const int fJ0 = d0.x, nfJ = d0.y, mJ0 = d0.z, cntJ = d0.w;
@@ -662,7 +708,7 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
         // is the next item's strip produced?  Asked now, answered after the arithmetic (an L2 round trip)
         const bool peek_next = is_tile(c1) && c1.s != s;
         int peek = 0;
-        if (tid == 0 && peek_next) peek = ld_acquire_gpu(done_p + kSyncStride * c1.s);
+        if (tid == 0 && peek_next) peek = ld_relaxed_gpu(done_p + kSyncStride * c1.s);
         {
             const int fl = tid & (sw - 1), g0 = tid >> lsw, gstep = kGroupThreads >> lsw;
             if (fl < nFs) {
@@ -685,7 +731,10 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
         if (is_tile(c1)) {
             bool ready = c1.s == s;
             if (!ready) {                                          // do not wait here, the expansion comes first
-                if (tid == 0) s_ready[grp] = peek >= prod_arrivals;
+                if (tid == 0) {
+                    s_ready[grp] = peek >= prod_arrivals;
+                    if (peek >= prod_arrivals) ld_acquire_gpu(done_p + kSyncStride * c1.s);   // (the peek was a relaxed load)
+                }
                 cons_sync();
                 ready = s_ready[grp] != 0;
             }
@@ -712,9 +761,9 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
             for (int pass0 = 0; pass0 < n_rows; pass0 += kRowCache) {
                 if (pass0 > 0 || n_rows > kRowCache) {             // a strip with more rows than the cache: reload it per pass
                     cons_sync();
-                    int rf, rk, rl, rsl;
-                    strip_row(s, ms0, ms1, pass0, rf, rk, rl, rsl);
-                    put_row(rf, rk, rl, rsl);
+                    int rf, rk, rl;
+                    strip_row(s, ms0, ms1, pass0, rf, rk, rl);
+                    put_row(rf, rk, rl);
                     cons_sync();
                 }
                 const int nrp = min(kRowCache, n_rows - pass0);
@@ -777,7 +826,7 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
         n_item++;
         PROF_MARK(6);
     }
-    for (int t = max(cur, 0); t < NS; t++) consumed(done_c + kSyncStride * t);
+    for (int t = cur < 0 ? gang : cur; t < NS; t += G) consumed(done_c + kSyncStride * t);
     PROF_MARK(0);
     PROF_FLUSH(1, tid == 0);
 }
