@@ -88,6 +88,7 @@ SYMBOLS = {
                              C.POINTER(Stats)]),
     "genlib_phi_multi": (C.c_int, [C.c_int32, _P, _P, C.c_int32, _P, _P, C.c_int, C.c_int, C.c_int32, _P,
                                    C.POINTER(Stats)]),
+    "genlib_plan_stream_selftest": (C.c_int, [C.c_int32, _P, _P, C.c_int32, _P, C.c_int32, C.c_double, _P, _P]),
     "genlib_engine_create": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P)]),
     "genlib_engine_destroy": (None, [_P]),
     "genlib_engine_run": (C.c_int, [_P, C.c_int]),

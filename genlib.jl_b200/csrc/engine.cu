@@ -172,7 +172,18 @@ struct LayerLaunch {
     size_t sync_off = 0;                   // ints, into the engine's sync region
 };
 
-struct genlib_engine {
+// the plan's index arrays on the device (views into the arena)
+struct IndexBufs {
+    DevBuf<int32_t> mem_ind, mem_slot, mem_fam, mem_lrow, fam_pf, fam_pm, fam_q, fam_pf_lrow, fam_pm_lrow, fam_start,
+        mt_desc, pro_slot, own_pro_row, live_lrow, tile_map, live_tiles;
+    DevBuf<int8_t> fam_pf_owner, fam_pm_owner, live_owner, pro_owner;
+    DevBuf<int32_t> pro_lrow;
+    DevBuf<int32_t> mem_rank;
+    DevBuf<uint8_t> flags;
+    DevBuf<double> acc;
+};
+
+struct genlib_engine : IndexBufs {
     const genlib_plan *plan = nullptr;
     int numerics = 0, device = 0, sm_count = 148;
     int rank = 0, world = 1;
@@ -196,13 +207,7 @@ struct genlib_engine {
     BarrierTable bars{};
     unsigned epoch = 0;
     long long barrier_timeout = (long long)20e9;   // cycles an inter-GPU barrier may wait (GENLIB_BARRIER_TIMEOUT_S)
-    DevBuf<int32_t> mem_ind, mem_slot, mem_fam, mem_lrow, fam_pf, fam_pm, fam_q, fam_pf_lrow, fam_pm_lrow, fam_start,
-        mt_desc, pro_slot, own_pro_row, live_lrow, tile_map, live_tiles;
-    DevBuf<int8_t> fam_pf_owner, fam_pm_owner, live_owner, pro_owner;
-    DevBuf<int32_t> pro_lrow;
-    DevBuf<int32_t> mem_rank;
-    DevBuf<uint8_t> flags;
-    DevBuf<double> acc;
+    bool streamed = false;                 // built on a plan that was still being made: sized by its bounds, uploaded layer by layer
     std::vector<int32_t> own_pro;          // proband indices (output rows) this rank owns, ascending
     std::vector<genlib_layer_info> info;
     std::vector<cudaEvent_t> events;
@@ -323,25 +328,55 @@ LayerLaunch shape_layer(const Plan &P, int t, int rank, size_t es, int sm_count)
 
 size_t strip_buffer_bytes(const LayerLaunch &ll, size_t es) { return (size_t)ll.s.nbuf * (size_t)ll.s.qstride * 2 * es; }
 
-size_t engine_bytes(const Plan &P, int numerics, int g, int sm_count = 148) {
-    const size_t es = numerics == GENLIB_NUMERICS_FP64 ? 8 : 4;
-    size_t q = 256, sync_ints = (P.layers.size() + 15) / 16 * 16;            // the layers' error words come first
+// Places the plan's index arrays behind `cur` (a null cursor just measures).  A streamed plan (PlanStream) is
+// sized by what its arrays have RESERVED: their final sizes are not known yet, the reserves are upper bounds.
+unsigned char *place_arrays(IndexBufs &B, const Plan &P, bool streamed, unsigned char *cur) {
+    auto cnt = [&](const auto &v) { return streamed ? v.capacity() : v.size(); };
+    const size_t npro = P.pro_ind.size();
+    B.mem_ind.place(cur, cnt(P.mem_ind)); B.mem_slot.place(cur, cnt(P.mem_slot)); B.mem_fam.place(cur, cnt(P.mem_fam));
+    B.mem_lrow.place(cur, cnt(P.mem_lrow)); B.mem_rank.place(cur, cnt(P.mem_rank));
+    B.fam_pf.place(cur, cnt(P.fam_pf)); B.fam_pm.place(cur, cnt(P.fam_pm));
+    B.fam_q.place(cur, cnt(P.fam_q));
+    B.fam_pf_lrow.place(cur, cnt(P.fam_pf_lrow)); B.fam_pm_lrow.place(cur, cnt(P.fam_pm_lrow));
+    B.fam_start.place(cur, cnt(P.fam_start));
+    B.mt_desc.place(cur, cnt(P.mtile_desc));
+    B.pro_slot.place(cur, npro); B.own_pro_row.place(cur, npro);
+    B.live_lrow.place(cur, cnt(P.live_lrow)); B.tile_map.place(cur, cnt(P.tile_map));
+    B.live_tiles.place(cur, cnt(P.live_tiles));
+    B.fam_pf_owner.place(cur, cnt(P.fam_pf_owner)); B.fam_pm_owner.place(cur, cnt(P.fam_pm_owner));
+    B.live_owner.place(cur, cnt(P.live_owner));
+    B.flags.place(cur, cnt(P.flags)); B.acc.place(cur, 4);
+    B.pro_owner.place(cur, npro); B.pro_lrow.place(cur, npro);
+    return cur;
+}
+
+// strip buffers and sync words of all layers: exact for a finished plan, bounds for a streamed one (shape_layer
+// never takes more: at most max(budget, two buffers of the narrowest strip), 16 words per strip of >= 8 couples)
+void scratch_sizes(const Plan &P, size_t es, int g, int sm_count, bool streamed, size_t &q_bytes, size_t &sync_ints) {
+    q_bytes = 256;
+    sync_ints = (P.layers.size() + 15) / 16 * 16;                             // the layers' error words come first
+    if (streamed) {
+        const size_t budget = (size_t)std::max(16, env_int("GENLIB_STRIP_BUDGET_MB", (int)(kStripBudget >> 20))) << 20;
+        q_bytes = std::max(budget, (size_t)2 * (size_t)P.capacity * 8 * 2 * es) + 256;
+        sync_ints += 16 * (P.fam_pf.capacity() / 8 + 2 * P.layers.size());
+        return;
+    }
     for (int t = 0; t < (int)P.layers.size(); t++) {
         const LayerLaunch ll = shape_layer(P, t, g, es, sm_count);
         if (ll.grid == 0) continue;
-        q = std::max(q, strip_buffer_bytes(ll, es));
+        q_bytes = std::max(q_bytes, strip_buffer_bytes(ll, es));
         sync_ints += 16 * (size_t)ll.s.n_strips;
     }
+}
+
+size_t engine_bytes(const Plan &P, int numerics, int g, int sm_count = 148, bool streamed = false) {
+    const size_t es = numerics == GENLIB_NUMERICS_FP64 ? 8 : 4;
+    size_t q, sync_ints;
+    scratch_sizes(P, es, g, sm_count, streamed, q, sync_ints);
     size_t b = kFlagBytes + a_bytes(P, es, g) + pad256(q) + pad256(sync_ints * sizeof(int32_t));
     b += 2 * pad256(kFetchStageBytes);                                         // proband staging
-    b += 4 * DevBuf<int32_t>::padded(P.mem_ind.size()) + DevBuf<int32_t>::padded(P.mem_rank.size()) +
-         4 * DevBuf<int32_t>::padded(P.fam_pf.size()) + DevBuf<int32_t>::padded(P.fam_q.size()) + DevBuf<int32_t>::padded(P.fam_start.size()) +
-         DevBuf<int32_t>::padded(P.mtile_desc.size()) + 2 * DevBuf<int32_t>::padded(P.pro_slot.size()) +
-         DevBuf<int32_t>::padded(P.live_lrow.size()) + DevBuf<int32_t>::padded(P.tile_map.size()) +
-         DevBuf<int32_t>::padded(P.live_tiles.size()) +
-         2 * DevBuf<int8_t>::padded(P.fam_pf.size()) +
-         DevBuf<int8_t>::padded(P.live_owner.size()) + DevBuf<uint8_t>::padded(P.flags.size()) + DevBuf<double>::padded(4) +
-         DevBuf<int8_t>::padded(P.pro_owner.size()) + DevBuf<int32_t>::padded(P.pro_lrow.size());
+    IndexBufs dummy;
+    b += (size_t)(place_arrays(dummy, P, streamed, nullptr) - (unsigned char *)nullptr);
     return b;
 }
 
@@ -380,47 +415,66 @@ int launch_barrier(genlib_engine &E) {
 }
 
 template <typename T>
-int launch_layers(genlib_engine &E, bool timed) {
-    const Plan &P = E.plan->p;
-    T *A = static_cast<T *>(E.A);
-    const int64_t ld = P.capacity;
-    const bool stored = sparse_schedule(P.schedule);           // sparse_phi's arithmetic (Float32 halves of stored values)
-    auto layer_fn = stored ? layer_kernel<T, true> : layer_kernel<T, false>;
-    size_t smem_max = 0;
-    for (const LayerLaunch &ll : E.launch) smem_max = std::max(smem_max, ll.smem);
+auto layer_function(const Plan &P) {
+    return sparse_schedule(P.schedule) ? layer_kernel<T, true> : layer_kernel<T, false>;   // sparse_phi's arithmetic (Float32 halves of stored values)
+}
+
+template <typename T>
+int prepare_launches(genlib_engine &E, size_t smem_max) {
+    auto layer_fn = layer_function<T>(E.plan->p);
     CU(cudaFuncSetAttribute(layer_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     CU(cudaFuncSetAttribute(layer_fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CU(cudaMemsetAsync(E.sync, 0, std::max<size_t>(E.sync_ints, 1) * sizeof(int32_t), E.stream));
+    return GENLIB_OK;
+}
+
+// one generation step: the layer kernel (and sparse_phi's misfiled pairs), then the inter-GPU barrier
+template <typename T>
+int launch_layer(genlib_engine &E, int t, bool timed, size_t &ev, int &launches) {
+    const Plan &P = E.plan->p;
+    const Layer &L = P.layers[t];
+    if (L.n_new == 0) return GENLIB_OK;
+    T *A = static_cast<T *>(E.A);
+    const int64_t ld = P.capacity;
+    auto layer_fn = layer_function<T>(P);
+    LayerArgs a = layer_args(E, t);
+    LayerLaunch &ll = E.launch[t];
+    if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
+    if (ll.grid > 0) {
+        ll.s.Q = E.Q;
+        ll.s.sync = E.sync + ll.sync_off;
+        ll.s.err = E.sync + t;
+        ll.s.live_tiles = E.live_tiles.p + L.ltile_off;
+#ifdef GENLIB_PROFILE
+        ll.s.prof = (t == env_int("GENLIB_PROF_LAYER", 5)) ? E.prof : nullptr;
+#else
+        ll.s.prof = nullptr;
+#endif
+        layer_fn<<<ll.grid, kLayerThreads, ll.smem, E.stream>>>(A, ld, E.peers, a, ll.s);
+        launches++;
+        if (P.schedule == kScheduleSparsePhi && L.n_new > 1 && a.own_nm > 0) {   // the reference's misfiled kinships read as 0
+            dim3 mgrid((unsigned)a.own_nm, (unsigned)std::min<int64_t>((L.n_new + 4 * kThreads - 1) / (4 * kThreads), 65535));
+            misfile_kernel<T><<<mgrid, kThreads, 0, E.stream>>>(A, ld, E.mem_rank.p + L.mem_off, a);
+            launches++;
+        }
+    }
+    if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
+    launch_barrier(E);                 // all new rows (and mirrored columns) exist everywhere before the next layer reads them
+    if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
+    return GENLIB_OK;
+}
+
+template <typename T>
+int launch_layers(genlib_engine &E, bool timed) {
+    const Plan &P = E.plan->p;
+    size_t smem_max = 0;
+    for (const LayerLaunch &ll : E.launch) smem_max = std::max(smem_max, ll.smem);
+    if (int rc = prepare_launches<T>(E, smem_max)) return rc;
     int launches = 0;
     size_t ev = 0;
     for (int t = 0; t < (int)P.layers.size(); t++) {
-        const Layer &L = P.layers[t];
-        if (L.n_new == 0) continue;
         if (E.layer_limit >= 0 && t >= E.layer_limit) break;
-        LayerArgs a = layer_args(E, t);
-        LayerLaunch &ll = E.launch[t];
-        if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
-        if (ll.grid > 0) {
-            ll.s.Q = E.Q;
-            ll.s.sync = E.sync + ll.sync_off;
-            ll.s.err = E.sync + t;
-            ll.s.live_tiles = E.live_tiles.p + L.ltile_off;
-#ifdef GENLIB_PROFILE
-            ll.s.prof = (t == env_int("GENLIB_PROF_LAYER", 5)) ? E.prof : nullptr;
-#else
-            ll.s.prof = nullptr;
-#endif
-            layer_fn<<<ll.grid, kLayerThreads, ll.smem, E.stream>>>(A, ld, E.peers, a, ll.s);
-            launches++;
-            if (P.schedule == kScheduleSparsePhi && L.n_new > 1 && a.own_nm > 0) {   // the reference's misfiled kinships read as 0
-                dim3 mgrid((unsigned)a.own_nm, (unsigned)std::min<int64_t>((L.n_new + 4 * kThreads - 1) / (4 * kThreads), 65535));
-                misfile_kernel<T><<<mgrid, kThreads, 0, E.stream>>>(A, ld, E.mem_rank.p + L.mem_off, a);
-                launches++;
-            }
-        }
-        if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
-        launch_barrier(E);                 // all new rows (and mirrored columns) exist everywhere before the next layer reads them
-        if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
+        if (int rc = launch_layer<T>(E, t, timed, ev, launches)) return rc;
     }
     CU(cudaGetLastError());
     E.stats.kernel_launches = launches;
@@ -439,6 +493,79 @@ int launch_layers(genlib_engine &E, bool timed) {
                      acc[1][0] / pl.s.n_cons / 1e3, acc[1][1] / pl.s.n_cons / 1e3, acc[1][2] / pl.s.n_cons / 1e3, acc[1][3] / pl.s.n_cons / 1e3, acc[1][4] / pl.s.n_cons / 1e3, acc[1][5] / pl.s.n_cons / 1e3, acc[1][6] / pl.s.n_cons / 1e3, acc[1][7] / pl.s.n_cons / 1e3);
     }
 #endif
+    return GENLIB_OK;
+}
+
+int upload_layers(genlib_engine &E, int t0, int t1);
+int upload_probands(genlib_engine &E);
+
+// what the kernels of a run left in their error words
+int check_device_errors(genlib_engine &E) {
+    int32_t errw = 0;                                     // a dependency inside a layer kernel timed out
+    std::vector<int32_t> words(E.launch.size(), 0);
+    if (!words.empty()) CU(cudaMemcpy(words.data(), E.sync, words.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    for (int32_t w : words) if (w) { errw = w; break; }
+    if (errw) return fail(GENLIB_ECUDA, "the layer kernel reported error " + std::to_string(errw) + " (1: a strip dependency did not arrive, 2: a bulk copy did not complete)");
+    if (E.world > 1) {
+        unsigned berr = 0;
+        CU(cudaMemcpy(&berr, E.bar_flags + kMaxWorld, sizeof berr, cudaMemcpyDeviceToHost));
+        if (berr) return fail(GENLIB_ECOMM, "a rank did not reach the inter-GPU barrier within the time limit");
+    }
+    return GENLIB_OK;
+}
+
+constexpr int kRestart = -1000;      // internal: a bound of the streamed plan did not hold, run again on the finished plan
+
+// The layers of a plan that is still being made (PlanStream): wait for a layer, upload its slice of the index
+// arrays, shape and launch it, while the planner works on the next ones.  The caller has registered as a consumer.
+template <typename T>
+int run_streamed(genlib_engine &E, PlanStream &ps) {
+    const Plan &P = E.plan->p;
+    const int S = (int)P.layers.size();
+    const size_t nev = E.events.size();
+    CU(cudaEventRecord(E.events[nev - 2], E.stream));
+    if (int rc = prepare_launches<T>(E, (size_t)227 * 1024 - 2048)) return rc;
+    int launches = 0, done = 0;
+    size_t ev = 0, sync_at = (P.layers.size() + 15) / 16 * 16;
+    while (done < S) {
+        ps.wait([&] { return ps.layers_done.load(std::memory_order_acquire) > done || ps.overflow.load() || ps.stage.load() == 2; });
+        // (after `overflow` nothing more is published: every consumer then launches the same layers, so the
+        //  inter-GPU barriers of a sharded run still pair up before it is abandoned)
+        const bool overflow = ps.overflow.load();
+        const int avail = ps.layers_done.load(std::memory_order_acquire);
+        if (avail == done && !overflow)
+            return ps.status.load() != GENLIB_OK ? ps.status.load() : fail(GENLIB_EINVAL, "internal: the planner ended before the last layer");
+        bool too_small = false;
+        if (int rc = upload_layers(E, done, avail)) return rc;
+        for (int t = done; t < avail; t++) {
+            LayerLaunch &ll = E.launch[(size_t)t];
+            ll = shape_layer(P, t, E.rank, E.esize, E.sm_count);
+            if (ll.grid > 0) {
+                ll.sync_off = sync_at;
+                sync_at += 16 * (size_t)ll.s.n_strips;
+                if (strip_buffer_bytes(ll, E.esize) > E.q_bytes || sync_at > E.sync_ints) too_small = true;   // (the bounds of scratch_sizes)
+            }
+            if (too_small && E.world == 1) break;
+            if (too_small) return fail(GENLIB_EINVAL, "internal: scratch bounds of a streamed, sharded plan");
+            fill_info(P.layers[(size_t)t], &E.info[(size_t)t]);
+            if (int rc = launch_layer<T>(E, t, false, ev, launches)) return rc;
+        }
+        done = avail;
+        if (overflow || too_small) { cudaStreamSynchronize(E.stream); return kRestart; }
+    }
+    CU(cudaGetLastError());
+    E.stats.kernel_launches = launches;
+    ps.wait([&] { return ps.stage.load() == 2; });              // the probands' homes close the plan
+    if (ps.status.load() != GENLIB_OK) return ps.status.load();
+    if (ps.overflow.load()) { cudaStreamSynchronize(E.stream); return kRestart; }
+    if (int rc = upload_probands(E)) return rc;
+    CU(cudaEventRecord(E.events[nev - 1], E.stream));
+    CU(cudaStreamSynchronize(E.stream));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, E.events[nev - 2], E.events[nev - 1]));
+    E.stats.ms_kernels = ms;                                    // first launch to last: includes waiting for the planner
+    E.stats.row_updates = P.row_updates; E.stats.alg_bytes = P.alg_elems * (double)E.esize;
+    E.stats.h2d_bytes = (int64_t)plan_index_bytes(P);
     return GENLIB_OK;
 }
 
@@ -559,7 +686,46 @@ void account_layers(genlib_engine &E) {
     E.info_ready = true;
 }
 
-int create_engine(const genlib_plan *plan, int numerics, int device, int rank, genlib_engine **out) {
+// this rank's probands in output order, and where their rows and columns are (needs the finished plan)
+int upload_probands(genlib_engine &E) {
+    const Plan &P = E.plan->p;
+    std::vector<int32_t> own_rows;
+    E.own_pro.clear();
+    for (size_t u = 0; u < P.pro_ind.size(); u++)
+        if (P.pro_owner[u] == E.rank) { E.own_pro.push_back((int32_t)u); own_rows.push_back(P.pro_lrow[u]); }
+    CU(E.pro_slot.upload(P.pro_slot, E.stream));
+    CU(E.own_pro_row.upload(own_rows, E.stream));
+    CU(E.pro_owner.upload(P.pro_owner, E.stream));
+    CU(E.pro_lrow.upload(P.pro_lrow, E.stream));
+    CU(cudaStreamSynchronize(E.stream));                       // (own_rows is a local)
+    return GENLIB_OK;
+}
+
+// the index arrays of layers [t0, t1) -> device (the whole plan: t0 = 0, t1 = layers)
+int upload_layers(genlib_engine &E, int t0, int t1) {
+    const Plan &P = E.plan->p;
+    if (t1 <= t0) return GENLIB_OK;
+    const Layer &A = P.layers[(size_t)t0], &Z = P.layers[(size_t)t1 - 1];
+    auto up = [&](auto &dev, const auto &host, size_t a, size_t b) -> cudaError_t {
+        if (b <= a) return cudaSuccess;
+        return cudaMemcpyAsync(dev.p + a, host.data() + a, (b - a) * sizeof(*dev.p), cudaMemcpyHostToDevice, E.stream);
+    };
+    CU(up(E.mem_ind, P.mem_ind, A.mem_off, Z.mem_end)); CU(up(E.mem_slot, P.mem_slot, A.mem_off, Z.mem_end));
+    CU(up(E.mem_fam, P.mem_fam, A.mem_off, Z.mem_end)); CU(up(E.mem_lrow, P.mem_lrow, A.mem_off, Z.mem_end));
+    if (sparse_schedule(P.schedule)) CU(up(E.mem_rank, P.mem_rank, A.mem_off, Z.mem_end));
+    CU(up(E.fam_pf, P.fam_pf, A.fam_off, Z.fam_end)); CU(up(E.fam_pm, P.fam_pm, A.fam_off, Z.fam_end));
+    CU(up(E.fam_q, P.fam_q, 2 * A.fam_off, 2 * Z.fam_end));
+    CU(up(E.fam_pf_lrow, P.fam_pf_lrow, A.fam_off, Z.fam_end)); CU(up(E.fam_pm_lrow, P.fam_pm_lrow, A.fam_off, Z.fam_end));
+    CU(up(E.fam_pf_owner, P.fam_pf_owner, A.fam_off, Z.fam_end)); CU(up(E.fam_pm_owner, P.fam_pm_owner, A.fam_off, Z.fam_end));
+    CU(up(E.fam_start, P.fam_start, A.fam_off + (size_t)t0, Z.fam_end + (size_t)t1));   // a layer holds couples + 1 entries
+    CU(up(E.mt_desc, P.mtile_desc, 4 * A.mtile_off, 4 * Z.mtile_end));
+    CU(up(E.flags, P.flags, A.flag_off, Z.flag_end));
+    CU(up(E.live_owner, P.live_owner, A.flag_off, Z.flag_end)); CU(up(E.live_lrow, P.live_lrow, A.flag_off, Z.flag_end));
+    CU(up(E.tile_map, P.tile_map, A.tile_off, Z.tile_end)); CU(up(E.live_tiles, P.live_tiles, A.ltile_off, Z.ltile_end));
+    return GENLIB_OK;
+}
+
+int create_engine(const genlib_plan *plan, int numerics, int device, int rank, genlib_engine **out, bool streamed = false) {
     if (!plan || !out) return fail(GENLIB_EINVAL, "genlib_engine_create: null argument");
     *out = nullptr;
     if (numerics != GENLIB_NUMERICS_REFERENCE && numerics != GENLIB_NUMERICS_FP64) return fail(GENLIB_EINVAL, "unknown numerics mode");
@@ -587,19 +753,21 @@ int create_engine(const genlib_plan *plan, int numerics, int device, int rank, g
         E->barrier_timeout = (long long)(std::max(sec, 0.001) * 2e9);
     }
     const double t0 = now_ms();
-    // launch shapes, strip buffers, sync words
+    // launch shapes, strip buffers, sync words (a streamed plan: the shapes follow layer by layer)
+    E->streamed = streamed;
     E->launch.resize(P.layers.size());
-    E->q_bytes = 256;
-    E->sync_ints = (P.layers.size() + 15) / 16 * 16;                          // the layers' error words come first
-    for (int t = 0; t < (int)P.layers.size(); t++) {
-        LayerLaunch &ll = E->launch[t];
-        ll = shape_layer(P, t, rank, E->esize, E->sm_count);
-        if (ll.grid == 0) continue;
-        E->q_bytes = std::max(E->q_bytes, strip_buffer_bytes(ll, E->esize));
-        ll.sync_off = E->sync_ints;
-        E->sync_ints += 16 * (size_t)ll.s.n_strips;
+    scratch_sizes(P, E->esize, rank, E->sm_count, streamed, E->q_bytes, E->sync_ints);
+    if (!streamed) {
+        size_t at = (P.layers.size() + 15) / 16 * 16;
+        for (int t = 0; t < (int)P.layers.size(); t++) {
+            LayerLaunch &ll = E->launch[t];
+            ll = shape_layer(P, t, rank, E->esize, E->sm_count);
+            if (ll.grid == 0) continue;
+            ll.sync_off = at;
+            at += 16 * (size_t)ll.s.n_strips;
+        }
     }
-    const size_t need = engine_bytes(P, numerics, rank, E->sm_count);
+    const size_t need = engine_bytes(P, numerics, rank, E->sm_count, streamed);
     CU(cudaStreamCreateWithFlags(&E->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&E->copy_stream, cudaStreamNonBlocking));
     {
@@ -622,20 +790,7 @@ int create_engine(const genlib_plan *plan, int numerics, int device, int rank, g
         E->sync = reinterpret_cast<int32_t *>(take(E->sync_ints * sizeof(int32_t)));
         E->fetch_stage[0] = take(kFetchStageBytes);
         E->fetch_stage[1] = take(kFetchStageBytes);
-        E->mem_ind.place(cur, P.mem_ind.size()); E->mem_slot.place(cur, P.mem_slot.size()); E->mem_fam.place(cur, P.mem_fam.size());
-        E->mem_lrow.place(cur, P.mem_lrow.size()); E->mem_rank.place(cur, P.mem_rank.size());
-        E->fam_pf.place(cur, P.fam_pf.size()); E->fam_pm.place(cur, P.fam_pm.size());
-        E->fam_q.place(cur, P.fam_q.size());
-        E->fam_pf_lrow.place(cur, P.fam_pf_lrow.size()); E->fam_pm_lrow.place(cur, P.fam_pm_lrow.size());
-        E->fam_start.place(cur, P.fam_start.size());
-        E->mt_desc.place(cur, P.mtile_desc.size());
-        E->pro_slot.place(cur, P.pro_slot.size()); E->own_pro_row.place(cur, P.pro_slot.size());
-        E->live_lrow.place(cur, P.live_lrow.size()); E->tile_map.place(cur, P.tile_map.size());
-        E->live_tiles.place(cur, P.live_tiles.size());
-        E->fam_pf_owner.place(cur, P.fam_pf_owner.size()); E->fam_pm_owner.place(cur, P.fam_pm_owner.size());
-        E->live_owner.place(cur, P.live_owner.size());
-        E->flags.place(cur, P.flags.size()); E->acc.place(cur, 4);
-        E->pro_owner.place(cur, P.pro_owner.size()); E->pro_lrow.place(cur, P.pro_lrow.size());
+        cur = place_arrays(*E, P, streamed, cur);
         if ((size_t)(cur - base) > need) return fail(GENLIB_EINVAL, "internal: arena layout overflow");
         if ((size_t)(static_cast<unsigned char *>(E->A) - base) != off_A())
             return fail(GENLIB_EINVAL, "internal: peer-visible arena offsets drifted");
@@ -659,34 +814,11 @@ int create_engine(const genlib_plan *plan, int numerics, int device, int rank, g
             if (cudaStreamSetAttribute(E->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
         }
     }
-    // this rank's probands, in output order
-    std::vector<int32_t> own_rows;
-    for (size_t u = 0; u < P.pro_ind.size(); u++)
-        if (P.pro_owner[u] == rank) { E->own_pro.push_back((int32_t)u); own_rows.push_back(P.pro_lrow[u]); }
     CU(cudaMemsetAsync(E->bar_flags, 0, kFlagBytes, E->stream));
-    CU(E->mem_ind.upload(P.mem_ind, E->stream));
-    CU(E->mem_slot.upload(P.mem_slot, E->stream));
-    CU(E->mem_fam.upload(P.mem_fam, E->stream));
-    CU(E->mem_lrow.upload(P.mem_lrow, E->stream));
-    CU(E->mem_rank.upload(P.mem_rank, E->stream));
-    CU(E->fam_pf.upload(P.fam_pf, E->stream));
-    CU(E->fam_pm.upload(P.fam_pm, E->stream));
-    CU(E->fam_q.upload(P.fam_q, E->stream));
-    CU(E->fam_pf_lrow.upload(P.fam_pf_lrow, E->stream));
-    CU(E->fam_pm_lrow.upload(P.fam_pm_lrow, E->stream));
-    CU(E->fam_pf_owner.upload(P.fam_pf_owner, E->stream));
-    CU(E->fam_pm_owner.upload(P.fam_pm_owner, E->stream));
-    CU(E->fam_start.upload(P.fam_start, E->stream));
-    CU(E->mt_desc.upload(P.mtile_desc, E->stream));
-    CU(E->pro_slot.upload(P.pro_slot, E->stream));
-    CU(E->own_pro_row.upload(own_rows, E->stream));
-    CU(E->live_owner.upload(P.live_owner, E->stream));
-    CU(E->live_lrow.upload(P.live_lrow, E->stream));
-    CU(E->tile_map.upload(P.tile_map, E->stream));
-    CU(E->live_tiles.upload(P.live_tiles, E->stream));
-    CU(E->flags.upload(P.flags, E->stream));
-    CU(E->pro_owner.upload(P.pro_owner, E->stream));
-    CU(E->pro_lrow.upload(P.pro_lrow, E->stream));
+    if (!streamed) {
+        if (int rc = upload_layers(*E, 0, (int)P.layers.size())) return rc;
+        if (int rc = upload_probands(*E)) return rc;
+    }
     CU(cudaStreamSynchronize(E->stream));
 #ifdef GENLIB_PROFILE
     CU(cudaMalloc(&E->prof, 8 * 2 * 160 * sizeof(long long)));
@@ -695,7 +827,7 @@ int create_engine(const genlib_plan *plan, int numerics, int device, int rank, g
     E->peers.A[rank] = E->A; E->bars.flags[rank] = E->bar_flags;
     E->attached = P.world == 1;
     E->info.resize(P.layers.size());
-    for (size_t t = 0; t < P.layers.size(); t++) fill_info(P.layers[t], &E->info[t]);
+    if (!streamed) for (size_t t = 0; t < P.layers.size(); t++) fill_info(P.layers[t], &E->info[t]);
     E->events.resize(P.layers.size() * 3 + 2);
     for (auto &e : E->events) CU(cudaEventCreate(&e));
     genlib_stats &s = E->stats;
@@ -971,18 +1103,7 @@ int genlib_engine_run(genlib_engine *eng, int time_layers) {
             E.info[t].ms_layer = a; E.info[t].ms_wait = w;
         }
     }
-    {
-        int32_t errw = 0;                                     // a dependency inside a layer kernel timed out
-        std::vector<int32_t> words(E.launch.size(), 0);
-        if (!words.empty()) CU(cudaMemcpy(words.data(), E.sync, words.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
-        for (int32_t w : words) if (w) { errw = w; break; }
-        if (errw) return fail(GENLIB_ECUDA, "the layer kernel reported error " + std::to_string(errw) + " (1: a strip dependency did not arrive, 2: a bulk copy did not complete)");
-    }
-    if (E.world > 1) {
-        unsigned errw = 0;
-        CU(cudaMemcpy(&errw, E.bar_flags + kMaxWorld, sizeof errw, cudaMemcpyDeviceToHost));
-        if (errw) return fail(GENLIB_ECOMM, "a rank did not reach the inter-GPU barrier within the time limit");
-    }
+    if (int rc2 = check_device_errors(E)) return rc2;
     E.ran = true;
     return GENLIB_OK;
 }
@@ -1178,23 +1299,161 @@ int genlib_phi_multi(int32_t n, const int32_t *father, const int32_t *mother, in
 int genlib_phi(int32_t n, const int32_t *father, const int32_t *mother, int32_t n_pro,
                const int32_t *proband, void *out, int out_dtype, int numerics, int device,
                genlib_stats *stats) {
-    genlib_plan *plan = nullptr;
-    int rc = genlib_plan_create(n, father, mother, n_pro, proband, 1, &plan);
+    if (out_dtype != GENLIB_F32 && out_dtype != GENLIB_F64) return fail(GENLIB_EINVAL, "unknown out_dtype");
+    // The plan is made on a worker thread and handed over layer by layer (PlanStream): the device runs the first
+    // generations while the later ones are planned.  GENLIB_STREAM=0: plan first, then run.
+    std::unique_ptr<genlib_plan> pl(new (std::nothrow) genlib_plan);
+    if (!pl) return fail(GENLIB_ENOMEM, "out of host memory");
+    const bool want_stream = env_int("GENLIB_STREAM", 1) != 0 && out != nullptr;
+    const double t0 = now_ms();
+    PlanStream ps;
+    int plan_rc = GENLIB_OK;
+    std::string plan_err;
+    auto make_plan = [&](PlanStream *stream) {
+        try {
+            adopt_retired_storage(pl->p);        // the arrays of the last destroyed plan, already paged in
+            plan_rc = build_plan(n, father, mother, nullptr, n_pro, proband, 1, GENLIB_SCHEDULE_PHI, pl->p, plan_err, stream);
+        } catch (const std::bad_alloc &) {
+            plan_rc = GENLIB_ENOMEM; plan_err = "out of host memory while planning";
+            if (stream) { stream->status.store(plan_rc); stream->stage.store(2); stream->wake(); }
+        }
+        pl->ms_plan = now_ms() - t0;
+    };
+    genlib_engine *eng = nullptr;
+    struct EngGuard { genlib_engine *&e; ~EngGuard() { genlib_engine_destroy(e); e = nullptr; } } eguard{eng};
+    int rc = GENLIB_OK;
+    bool done = false;
+    if (want_stream) {
+        std::thread worker;
+        try { worker = std::thread([&] { make_plan(&ps); }); } catch (...) { }
+        if (!worker.joinable()) make_plan(nullptr);               // no thread to be had: plan here
+        else {
+            struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{worker};
+            ps.wait([&] { return ps.stage.load() >= 1; });
+            if (ps.streamed.load() && pl->p.n_unique > 0) {
+                struct Consumer {                                 // the planner waits for us before it reallocates anything
+                    PlanStream &s;
+                    explicit Consumer(PlanStream &st) : s(st) { s.consumers.fetch_add(1); }
+                    ~Consumer() { s.consumers.fetch_sub(1); s.wake(); }
+                } consumer(ps);
+                if (!ps.overflow.load()) {
+                    rc = create_engine(pl.get(), numerics, device, 0, &eng, true);
+                    if (rc == GENLIB_OK) {
+                        DeviceGuard guard;
+                        rc = guard.enter(eng->device);
+                        if (rc == GENLIB_OK) rc = numerics == GENLIB_NUMERICS_FP64 ? run_streamed<double>(*eng, ps) : run_streamed<float>(*eng, ps);
+                        if (rc == GENLIB_OK) rc = check_device_errors(*eng);
+                        if (rc == GENLIB_OK) { eng->ran = true; done = true; }
+                    }
+                    if (rc == kRestart || rc == GENLIB_ENOMEM) rc = GENLIB_OK;   // the bounds did not hold (or did not fit): run on the finished plan
+                }
+            }
+        }                                                         // (consumer released, worker joined)
+    } else make_plan(nullptr);
+    if (plan_rc != GENLIB_OK) return fail(plan_rc, plan_err);
     if (rc != GENLIB_OK) return rc;
-    std::unique_ptr<genlib_plan> pguard(plan);
-    if (plan->p.n_unique == 0) {
-        if (stats) { std::memset(stats, 0, sizeof *stats); stats->ms_plan = plan->ms_plan; }
+    if (pl->p.n_unique == 0) {
+        if (stats) { std::memset(stats, 0, sizeof *stats); stats->ms_plan = pl->ms_plan; }
         return GENLIB_OK;                       // 0 x 0 matrix, like the reference
     }
     if (!out) return fail(GENLIB_EINVAL, "genlib_phi: out is null");
-    genlib_engine *eng = nullptr;
-    rc = genlib_engine_create(plan, numerics, device, &eng);
-    if (rc != GENLIB_OK) return rc;
-    rc = genlib_engine_run(eng, 0);
-    if (rc == GENLIB_OK) rc = genlib_engine_fetch(eng, out, out_dtype);
+    if (!done) {
+        genlib_engine_destroy(eng); eng = nullptr;
+        rc = create_engine(pl.get(), numerics, device, 0, &eng);
+        if (rc != GENLIB_OK) return rc;
+        rc = genlib_engine_run(eng, 0);
+        if (rc != GENLIB_OK) return rc;
+    }
+    eng->stats.ms_plan = pl->ms_plan;
+    rc = genlib_engine_fetch(eng, out, out_dtype);
     if (rc == GENLIB_OK && stats) *stats = eng->stats;
-    genlib_engine_destroy(eng);
+    genlib_engine_destroy(eng); eng = nullptr;                    // before the plan it refers to
+    try { retire_storage(pl->p); } catch (...) {}
     return rc;
+}
+
+int genlib_plan_stream_selftest(int32_t n, const int32_t *father, const int32_t *mother, int32_t n_pro,
+                                const int32_t *proband, int32_t world, double slack_pct,
+                                int32_t *layers_streamed, int32_t *overflowed) {
+    if (layers_streamed) *layers_streamed = 0;
+    if (overflowed) *overflowed = 0;
+    {
+        char buf[64];
+        std::snprintf(buf, sizeof buf, "%g", slack_pct);
+        setenv("GENLIB_STREAM_SLACK_PCT", buf, 1);
+    }
+    struct EnvReset { ~EnvReset() { unsetenv("GENLIB_STREAM_SLACK_PCT"); } } env_reset;
+    Plan ref, P;
+    std::string err;
+    int rc = build_plan(n, father, mother, nullptr, n_pro, proband, world, GENLIB_SCHEDULE_PHI, ref, err);
+    if (rc != GENLIB_OK) return fail(rc, err);
+    PlanStream ps;
+    int plan_rc = GENLIB_OK;
+    std::string plan_err;
+    std::thread worker([&] { plan_rc = build_plan(n, father, mother, nullptr, n_pro, proband, world, GENLIB_SCHEDULE_PHI, P, plan_err, &ps); });
+    // the consumer: copies of the published slices, taken when they are published
+    std::vector<int32_t> c_mem_slot, c_fam_pf, c_fam_start, c_live_tiles, c_mtile, c_live_lrow;
+    std::vector<uint8_t> c_flags;
+    int done = 0;
+    bool saw_overflow = false;
+    int64_t bound = 0;
+    ps.wait([&] { return ps.stage.load() >= 1; });
+    if (ps.streamed.load()) {
+        ps.consumers.fetch_add(1);
+        bound = P.capacity;
+        const int S = (int)P.layers.size();
+        while (done < S) {
+            ps.wait([&] { return ps.layers_done.load(std::memory_order_acquire) > done || ps.overflow.load() || ps.stage.load() == 2; });
+            const bool ovf = ps.overflow.load();
+            const int avail = ps.layers_done.load(std::memory_order_acquire);
+            if (avail > done) {
+                const Layer &Z = P.layers[(size_t)avail - 1];
+                auto grab = [&](auto &copy, const auto &src, size_t end) { copy.insert(copy.end(), src.data() + copy.size(), src.data() + end); };
+                grab(c_mem_slot, P.mem_slot, Z.mem_end); grab(c_fam_pf, P.fam_pf, Z.fam_end);
+                grab(c_fam_start, P.fam_start, Z.fam_end + (size_t)avail); grab(c_live_tiles, P.live_tiles, Z.ltile_end);
+                grab(c_mtile, P.mtile_desc, 4 * Z.mtile_end); grab(c_live_lrow, P.live_lrow, Z.flag_end);
+                grab(c_flags, P.flags, Z.flag_end);
+                done = avail;
+            }
+            if (ovf) { saw_overflow = true; break; }
+            if (avail < S && ps.stage.load() == 2 && ps.layers_done.load() == avail) break;
+        }
+        ps.consumers.fetch_sub(1);
+        ps.wake();
+    }
+    worker.join();
+    if (plan_rc != GENLIB_OK) return fail(plan_rc, plan_err);
+    if (layers_streamed) *layers_streamed = done;
+    if (overflowed) *overflowed = saw_overflow ? 1 : 0;
+    auto prefix_ok = [](const auto &copy, const auto &fin) { return copy.size() <= fin.size() && std::equal(copy.begin(), copy.end(), fin.begin()); };
+    if (!prefix_ok(c_mem_slot, P.mem_slot) || !prefix_ok(c_fam_pf, P.fam_pf) || !prefix_ok(c_fam_start, P.fam_start) ||
+        !prefix_ok(c_live_tiles, P.live_tiles) || !prefix_ok(c_mtile, P.mtile_desc) || !prefix_ok(c_live_lrow, P.live_lrow) ||
+        !prefix_ok(c_flags, P.flags))
+        return fail(GENLIB_EINVAL, "stream selftest: a published slice changed afterwards");
+    if (ps.streamed.load() && !saw_overflow && done != (int)P.layers.size()) return fail(GENLIB_EINVAL, "stream selftest: not every layer was published");
+    // the streamed plan against the plan made in one piece
+    bool same = P.n_unique == ref.n_unique && P.layers.size() == ref.layers.size() && P.row_updates == ref.row_updates &&
+                P.mem_ind == ref.mem_ind && P.mem_slot == ref.mem_slot && P.mem_fam == ref.mem_fam && P.mem_lrow == ref.mem_lrow &&
+                P.fam_pf == ref.fam_pf && P.fam_pm == ref.fam_pm && P.fam_q == ref.fam_q && P.fam_start == ref.fam_start &&
+                P.fam_pf_lrow == ref.fam_pf_lrow && P.fam_pm_lrow == ref.fam_pm_lrow && P.fam_pf_owner == ref.fam_pf_owner &&
+                P.fam_pm_owner == ref.fam_pm_owner && P.flags == ref.flags && P.live_owner == ref.live_owner &&
+                P.live_lrow == ref.live_lrow && P.tile_map == ref.tile_map && P.live_tiles == ref.live_tiles &&
+                P.mtile_desc == ref.mtile_desc && P.fam_base == ref.fam_base && P.mem_base == ref.mem_base &&
+                P.pro_slot == ref.pro_slot && P.pro_owner == ref.pro_owner && P.pro_lrow == ref.pro_lrow;
+    for (size_t t = 0; same && t < P.layers.size(); t++) {
+        const Layer &a = P.layers[t], &b = ref.layers[t];
+        same = a.n_new == b.n_new && a.n_fam == b.n_fam && a.rt_lo == b.rt_lo && a.rt_rows == b.rt_rows && a.mem_off == b.mem_off &&
+               a.fam_off == b.fam_off && a.flag_off == b.flag_off && a.tile_off == b.tile_off && a.ltile_off == b.ltile_off &&
+               a.mtile_off == b.mtile_off && a.n_mtiles == b.n_mtiles && a.n_live_tiles == b.n_live_tiles && a.carried == b.carried;
+    }
+    if (!same) return fail(GENLIB_EINVAL, "stream selftest: the streamed plan differs from the plan made in one piece");
+    const bool kept_bound = ps.streamed.load() && !saw_overflow;
+    if (kept_bound ? (P.capacity != bound || P.capacity < ref.capacity) : (P.capacity != ref.capacity))
+        return fail(GENLIB_EINVAL, "stream selftest: frontier width " + std::to_string(P.capacity) + " against " + std::to_string(ref.capacity));
+    for (int g = 0; g < world; g++)
+        if (kept_bound ? P.rows_cap[(size_t)g] < ref.rows_cap[(size_t)g] : P.rows_cap[(size_t)g] != ref.rows_cap[(size_t)g])
+            return fail(GENLIB_EINVAL, "stream selftest: rows of rank " + std::to_string(g));
+    return GENLIB_OK;
 }
 
 }  // extern "C"

@@ -165,18 +165,31 @@ void release_plan_cache() {
 }
 
 static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const int32_t *mother, const int64_t *ids,
-                           int32_t n_pro, const int32_t *proband, int32_t world, int schedule, Plan &P, std::string &err);
+                           int32_t n_pro, const int32_t *proband, int32_t world, int schedule, Plan &P, std::string &err,
+                           PlanStream *ps);
 
 int build_plan(int32_t n, const int32_t *father, const int32_t *mother, const int64_t *ids, int32_t n_pro,
-               const int32_t *proband, int32_t world, int schedule, Plan &P, std::string &err) {
-    std::unique_ptr<Scratch> W = take_scratch();
-    const int rc = build_plan_with(*W, n, father, mother, ids, n_pro, proband, world, schedule, P, err);
-    give_scratch(std::move(W));
+               const int32_t *proband, int32_t world, int schedule, Plan &P, std::string &err, PlanStream *ps) {
+    int rc;
+    try {
+        std::unique_ptr<Scratch> W = take_scratch();
+        rc = build_plan_with(*W, n, father, mother, ids, n_pro, proband, world, schedule, P, err, ps);
+        give_scratch(std::move(W));
+    } catch (const std::bad_alloc &) {
+        if (!ps) throw;
+        rc = GENLIB_ENOMEM; err = "out of host memory while planning";
+    }
+    if (ps) {                                  // whatever happened, the consumers must not wait for ever
+        if (rc != GENLIB_OK) { ps->err = err; ps->status.store(rc, std::memory_order_release); }
+        ps->stage.store(2, std::memory_order_release);
+        ps->wake();
+    }
     return rc;
 }
 
 static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const int32_t *mother, const int64_t *ids,
-                           int32_t n_pro, const int32_t *proband, int32_t world, int schedule, Plan &P, std::string &err) {
+                           int32_t n_pro, const int32_t *proband, int32_t world, int schedule, Plan &P, std::string &err,
+                           PlanStream *ps) {
     const bool timing = std::getenv("GENLIB_PLAN_TIMING") != nullptr;     // debugging aid: phase times on stderr
     auto t_last = std::chrono::steady_clock::now();
 #define PLAN_T(name) do { if (timing) { auto t_now = std::chrono::steady_clock::now(); std::fprintf(stderr, "[plan] %-12s %.2f ms\n", name, std::chrono::duration<double, std::milli>(t_now - t_last).count()); t_last = t_now; } } while (0)
@@ -352,6 +365,49 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         P.fam_q.reserve(2 * fcap);
         P.fam_pf_owner.reserve(fcap); P.fam_pm_owner.reserve(fcap); P.fam_start.reserve(fcap + (size_t)S);
     }
+    // ---- a streamed plan: upper bounds for what the engine sizes before the first layer exists ----
+    int64_t bound_slots = 0, bound_rows = 0;
+    bool streaming = ps != nullptr;
+    if (streaming) {
+        // most individuals in the frontier during one step: born in or before it, read in or after it
+        std::vector<int64_t> d_occ((size_t)S + 2, 0);
+        for (size_t k = 0; k < lstart[S]; k++) {
+            const int32_t x = by_layer[k], lx = S - 1 - pre[x].h;
+            d_occ[lx]++; d_occ[(size_t)std::min<int64_t>(std::max(home[x].last, lx), S - 1) + 1]--;
+        }
+        int64_t occ = 0, occ_max = 0;
+        for (int32_t k = 0; k < S; k++) { occ += d_occ[k]; occ_max = std::max(occ_max, occ); }
+        // slack: lines of kSlotLine slots shared by individuals that leave in different layers (the member order
+        // keeps those to a few per cohort and rank), and a layer always starts on a fresh line
+        const char *env = std::getenv("GENLIB_STREAM_SLACK_PCT");
+        const double pct = env ? std::atof(env) : 6.25;
+        const int64_t cohorts = std::min<int64_t>(S, 128);
+        bound_slots = round_up((int64_t)((double)occ_max * (1.0 + pct / 100.0)) + (pct >= 0 ? 2 * kSlotLine * cohorts * world + 2048 : 0), kPTile);
+        bound_slots = std::max<int64_t>(bound_slots, kPTile);
+        bound_rows = world == 1 ? bound_slots
+                                : (int64_t)((double)occ_max / world * (1.125 + pct / 100.0)) + (pct >= 0 ? (kMaxFamily + kSlotLine) * cohorts + 1024 : 1);
+        if (bound_slots >= ((int64_t)1 << 24) || bound_slots * (int64_t)S > ((int64_t)1 << 31)) streaming = false;   // not worth the arrays
+    }
+    if (streaming) {
+        P.capacity = bound_slots;
+        P.rows_cap.assign((size_t)world, bound_rows);
+        const size_t fl = (size_t)bound_slots * (size_t)S, tl = fl / kPTile, M8 = lstart[S] / 8 + 2 * (size_t)S;
+        P.flags.reserve(fl); P.live_owner.reserve(fl); P.live_lrow.reserve(fl);
+        P.tile_map.reserve(tl); P.live_tiles.reserve(tl);
+        P.mtile_desc.reserve(4 * M8);
+        P.fam_base.reserve((size_t)(world + 1) * (size_t)S); P.mem_base.reserve((size_t)(world + 1) * (size_t)S);
+        ps->streamed.store(true);
+        ps->stage.store(1);
+        ps->wake();
+    }
+    // A bound does not hold: tell the consumers, wait until none of them reads the arrays any more (they may be
+    // reallocated from here on), go on as an ordinary plan.
+    auto give_up_streaming = [&]() {
+        streaming = false;
+        ps->overflow.store(true);                   // (sequentially consistent, like the consumers' registration)
+        ps->wake();
+        ps->wait([&] { return ps->consumers.load() == 0; });
+    };
     std::vector<int32_t> &live = W.live, &next_live = W.next_live;   // individuals live before the current step
     live.clear(); next_live.clear();
     // allocators: global column slots (lines, lowest free first) and local rows per rank (stack)
@@ -360,7 +416,7 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
     for (Alloc &a : rows) a.reset();
     std::vector<std::vector<int32_t>> &freed_rows = W.freed_rows; freed_rows.resize((size_t)world);
     for (auto &v : freed_rows) v.clear();
-    P.rows_cap.assign((size_t)world, 0);
+    if (!streaming) P.rows_cap.assign((size_t)world, 0);
     std::vector<int32_t> &order = W.order;
     std::vector<int32_t> &newid = W.newid, &load = W.load, &freed = W.freed;
     load.assign((size_t)world, 0);
@@ -464,6 +520,8 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         L.flag_off = P.flags.size();
         L.mtile_off = P.mtile_desc.size() / 4;
         L.base_off = P.fam_base.size();
+        L.tile_off = P.tile_map.size();
+        L.ltile_off = P.live_tiles.size();
 
         // ---- live range and flags (state BEFORE the step) ----
         freed.clear();
@@ -490,8 +548,6 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
             for (int32_t r = 0; r < L.rt_rows; r++)        // evicted slots in ascending order -> freed lines, ascending
                 if (fl[r] == kFlagLive) slots.release(L.rt_lo + r, freed);
             // the strip buffers of the layer kernel hold the live tiles only (holes of a fragmented range cost nothing)
-            L.tile_off = P.tile_map.size();
-            L.ltile_off = P.live_tiles.size();
             P.tile_map.resize(L.tile_off + (size_t)(L.rt_rows / kPTile), -1);
             for (int32_t tl = 0; tl < L.rt_rows / kPTile; tl++) {
                 uint8_t any = 0;
@@ -593,6 +649,7 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
                 const int32_t oq = order[q], x = X[oq], f = fam_of[oq];
                 const int32_t g = fam_own[f];
                 const int32_t s = slots.take(), lr = world > 1 ? rows[g].take() : s;   // one rank: row == slot
+                if (streaming && (s >= bound_slots || lr >= bound_rows)) give_up_streaming();
                 Home &hx = home[x];
                 hx.slot = s; hx.lrow = lr; hx.owner = (int8_t)g;
                 mi[q] = by_seq ? orient[x] : x; ms[q] = s; mf[q] = newid[f]; ml[q] = lr;
@@ -640,6 +697,9 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         P.alg_elems += L.alg_elems;
         P.row_updates += nn;
 
+        L.mem_end = P.mem_ind.size(); L.fam_end = P.fam_pf.size(); L.flag_end = P.flags.size();
+        L.tile_end = P.tile_map.size(); L.ltile_end = P.live_tiles.size(); L.mtile_end = P.mtile_desc.size() / 4;
+        if (streaming) { ps->layers_done.store(t + 1, std::memory_order_release); ps->wake(); }
         LT(5);
         // ---- after the step: evicted slots / rows become reusable from the next layer on ----
         slots.end_layer(freed);
@@ -649,8 +709,11 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
     }
     if (timing) std::fprintf(stderr, "[plan]   live/flags %.2f  wait-group %.2f  owners/order %.2f  slots %.2f  couples %.2f  tiles %.2f  end %.2f\n", lt_acc[0], lt_acc[1], lt_acc[2], lt_acc[3], lt_acc[4], lt_acc[5], lt_acc[7]);
     PLAN_T("layers");
-    P.capacity = round_up(std::max<int64_t>((int64_t)slots.next_fresh * kSlotLine, 1), kPTile);
-    for (int32_t g = 0; g < world; g++) P.rows_cap[g] = world > 1 ? std::max(rows[g].next_fresh, 1) : P.capacity;
+    if (!streaming) {                  // (a streamed plan keeps the bounds its engine was sized with)
+        P.capacity = round_up(std::max<int64_t>((int64_t)slots.next_fresh * kSlotLine, 1), kPTile);
+        P.rows_cap.resize((size_t)world);
+        for (int32_t g = 0; g < world; g++) P.rows_cap[g] = world > 1 ? std::max(rows[g].next_fresh, 1) : P.capacity;
+    }
     if (std::getenv("GENLIB_PLAN_VERIFY")) {                 // debugging aid: index ranges the layer kernel relies on
         for (int32_t t = 0; t < S; t++) {
             const Layer &L = P.layers[t];

@@ -11,8 +11,11 @@
 //
 // No CUDA in this file: the plan is testable without a GPU.
 #pragma once
+#include <atomic>
+#include <condition_variable>
 #include <cstddef>
 #include <cstdint>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -57,6 +60,8 @@ struct Layer {
     size_t flag_off = 0;              // into flags
     size_t mtile_off = 0;             // into mtile_* arrays
     size_t base_off = 0;              // into fam_base / mem_base (world + 1 entries each)
+    // sizes of the concatenated arrays once the layer is complete (a streamed plan is uploaded layer by layer)
+    size_t mem_end = 0, fam_end = 0, flag_end = 0, tile_end = 0, ltile_end = 0, mtile_end = 0;
     double alg_elems = 0;             // 4 n L + 3 n^2
 };
 
@@ -107,6 +112,28 @@ struct Plan {
     }
 };
 
+// Hand-over of a plan that is still being built: the planner publishes the layers one by one, an engine on
+// another thread uploads and launches them while the later layers are planned (planning is otherwise the
+// largest host-side part of a call).  What the engine must know before the first layer -- the frontier width
+// (leading dimension of the frontier matrix), the rows per rank, the sizes of the index arrays -- exists only
+// as an UPPER BOUND then: the planner derives it from the pre-pass (most individuals in the frontier at once,
+// plus slack for the line-granular slot allocator), reserves every array at its bound (no reallocation under
+// the reader) and keeps the bound as Plan::capacity.  Should a layer need more, it raises `overflow`, waits
+// until the consumer has stopped, and finishes as an ordinary plan with exact sizes.
+struct PlanStream {
+    std::atomic<int32_t> stage{0};         // 0: pre-pass; 1: bounds set, arrays reserved, layers are coming; 2: finished
+    std::atomic<int32_t> layers_done{0};   // layers [0, layers_done) are final in the plan's arrays
+    std::atomic<int32_t> status{0};        // a GENLIB_E* code once the planner has failed
+    std::atomic<bool> streamed{false};     // set with stage 1: the plan carries bounds and is published layer by layer
+    std::atomic<bool> overflow{false};     // a bound was too small: consumers stop, the plan ends with exact sizes
+    std::atomic<int32_t> consumers{0};     // consumers still reading the arrays (the planner waits for 0 on overflow)
+    std::string err;                       // the planner's message (read after stage == 2)
+    std::mutex mu;
+    std::condition_variable cv;
+    void wake() { { std::lock_guard<std::mutex> lk(mu); } cv.notify_all(); }
+    template <class Pred> void wait(Pred &&pred) { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, pred); }
+};
+
 // Recycling of plan storage across calls (bounded: one retired plan, one set of planner scratch).
 void adopt_retired_storage(Plan &into);   // moves a retired plan's (empty, reserved) arrays into `into`
 void retire_storage(Plan &from);          // keeps `from`'s arrays for the next adopt_retired_storage
@@ -120,7 +147,9 @@ int set_error(int code, const std::string &msg);
 // Returns 0 or a GENLIB_E* status; `err` receives a message.
 // `ids` (nullable, by rank) orders the founders in sparse_phi's queue (founder() sorts by ID,
 // identify.jl:15-19); without it they are taken in rank order.
+// With `stream` the plan is published layer by layer (see PlanStream); stage 2 is always reached.
 int build_plan(int32_t n, const int32_t *father, const int32_t *mother, const int64_t *ids, int32_t n_pro,
-               const int32_t *proband, int32_t world, int schedule, Plan &plan, std::string &err);
+               const int32_t *proband, int32_t world, int schedule, Plan &plan, std::string &err,
+               PlanStream *stream = nullptr);
 
 }  // namespace genlib

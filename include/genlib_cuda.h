@@ -199,6 +199,18 @@ int genlib_phi(int32_t n, const int32_t *father, const int32_t *mother, int32_t 
                const int32_t *proband, void *out, int out_dtype, int numerics, int device,
                genlib_stats *stats);
 
+/* genlib_phi and genlib_phi_multi plan on a worker thread and hand the layers to the device one by one while the
+ * later ones are still being planned (the planner is otherwise the largest host-side part of a call; environment
+ * GENLIB_STREAM=0 plans first and runs afterwards).  This diagnostic runs that hand-over WITHOUT a device: a
+ * consumer thread copies every layer's slice of the index arrays when it is published, and at the end the copies
+ * must equal the finished plan, which in turn must equal the plan made in one piece (only the frontier width
+ * differs: a streamed plan keeps the upper bound its engine was sized with).  slack_pct < 0 makes the bound too
+ * small on purpose (the planner must then notice, wait for the consumer and finish with exact sizes).
+ * layers_streamed / overflowed (nullable) report what happened.  CPU only. */
+int genlib_plan_stream_selftest(int32_t n, const int32_t *father, const int32_t *mother, int32_t n_pro,
+                                const int32_t *proband, int32_t world, double slack_pct,
+                                int32_t *layers_streamed, int32_t *overflowed);
+
 /* The same call on SEVERAL devices of one box, from one process (`n_dev, devices`):
  * one plan, the frontier's rows sharded over the devices, one host thread per device, NVLink peer
  * access between all of them (cudaDeviceEnablePeerAccess), no MPI / IPC.  Every device assembles a

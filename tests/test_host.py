@@ -266,3 +266,42 @@ def test_loader_file_equals_columns_and_oracle(gen, ob, tmp_path):
     n = 200000
     chain = gen.genealogy({"ind": np.arange(1, n + 1), "father": np.arange(0, n), "mother": np.zeros(n, int), "sex": np.ones(n, int)})
     assert chain.ids[0] == 1 and chain.ids[-1] == n and chain.depth() == n
+
+
+def _stream_selftest(gen, ped, ranks, world, slack):
+    import ctypes as C
+    from genlib_b200 import engine as ge
+    fa, mo = np.ascontiguousarray(ped.father, np.int32), np.ascontiguousarray(ped.mother, np.int32)
+    pr = np.ascontiguousarray(ranks, np.int32)
+    n_l, ovf = C.c_int32(0), C.c_int32(0)
+    rc = gen.lib().genlib_plan_stream_selftest(len(fa), ge.ptr(fa), ge.ptr(mo), len(pr), ge.ptr(pr), world, float(slack),
+                                               C.byref(n_l), C.byref(ovf))
+    assert rc == 0, gen.lib().genlib_last_error().decode()
+    return n_l.value, bool(ovf.value)
+
+
+@pytest.mark.parametrize("world", [1, 2, 8])
+def test_streamed_plan_equals_the_plan_made_in_one_piece(gen, world):
+    """genlib_phi hands the plan to the device layer by layer while it is still being made: every published
+    slice must be final, and the finished plan must be the one planned in one piece (csrc/plan.hpp PlanStream)."""
+    ped = gen.genealogy(gen.genea140)
+    ranks = ped.rank_of(gen.pro(ped))
+    n_layers = gen.Plan(ped.father, ped.mother, ranks, world=world).n_layers
+    done, overflow = _stream_selftest(gen, ped, ranks, world, 6.25)
+    assert done == n_layers and not overflow
+    for seed in (3, 11):
+        ped = gen.genealogy(random_pedigree(np.random.default_rng(seed), 3000, 40, window=60 if seed == 3 else 400))
+        ranks = ped.rank_of(ped.ids[-200:])
+        done, overflow = _stream_selftest(gen, ped, ranks, world, 6.25)
+        assert not overflow and done == gen.Plan(ped.father, ped.mother, ranks, world=world).n_layers
+
+
+@pytest.mark.parametrize("world", [1, 4])
+def test_streamed_plan_with_a_bound_that_does_not_hold(gen, world):
+    """A frontier bound that is too small on purpose: the planner notices, waits for the consumer and finishes
+    with exact sizes; what was published until then stays valid."""
+    ped = gen.genealogy(gen.genea140)
+    ranks = ped.rank_of(gen.pro(ped))
+    n_layers = gen.Plan(ped.father, ped.mother, ranks, world=world).n_layers
+    done, overflow = _stream_selftest(gen, ped, ranks, world, -40.0)
+    assert overflow and 0 < done < n_layers
