@@ -13,7 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GENLIB_CUDA_LIB") or os.path.join(_HERE, "libgenlib_cuda.so")
 
-OK, EINVAL, EKEY, EORDER, ECUDA, ENOMEM, ECOMM = range(7)
+OK, EINVAL, EKEY, EORDER, ECUDA, ENOMEM, ECOMM, ERESTART = range(8)
 SCHEDULES = {"phi": 0, "sparse_phi": 1, "sparse_phi_symmetric": 2}
 NUMERICS = {"reference": 0, "fp64": 1, 0: 0, 1: 1}
 DTYPES = {np.dtype(np.float32): 0, np.dtype(np.float64): 1}
@@ -23,6 +23,12 @@ class GenlibError(RuntimeError):
     def __init__(self, status: int, message: str):
         super().__init__(f"libgenlib_cuda status {status}: {message}")
         self.status = status
+
+
+class PlanBoundsExceeded(GenlibError):
+    """genlib_engine_run on an engine of a plan that was still being made (Plan(..., stream=True)): a size
+    bound did not hold (GENLIB_ERESTART).  Close the engine, create it again -- the plan is finished by
+    then -- and run."""
 
 
 class LayerInfo(C.Structure):
@@ -88,6 +94,7 @@ SYMBOLS = {
                              C.POINTER(Stats)]),
     "genlib_phi_multi": (C.c_int, [C.c_int32, _P, _P, C.c_int32, _P, _P, C.c_int, C.c_int, C.c_int32, _P,
                                    C.POINTER(Stats)]),
+    "genlib_plan_create_async": (C.c_int, [C.c_int32, _P, _P, _P, C.c_int32, _P, C.c_int32, C.c_int, C.POINTER(_P)]),
     "genlib_plan_stream_selftest": (C.c_int, [C.c_int32, _P, _P, C.c_int32, _P, C.c_int32, C.c_double, _P, _P]),
     "genlib_engine_create": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P)]),
     "genlib_engine_destroy": (None, [_P]),
@@ -136,6 +143,8 @@ def check(status: int):
             raise FileNotFoundError(msg)
         if status == ENOMEM:
             raise MemoryError(msg)
+        if status == ERESTART:
+            raise PlanBoundsExceeded(status, msg)
         raise GenlibError(status, msg)
 
 

@@ -162,7 +162,23 @@ constexpr size_t kFetchStageBytes = (size_t)64 << 20;
 struct genlib_plan {
     Plan p;
     double ms_plan = 0;
+    // genlib_plan_create_async: the plan is made on `worker` and handed over through `stream` (PlanStream); whoever
+    // needs the whole plan calls settle() first.  The caller's input arrays stay alive until then.
+    std::unique_ptr<PlanStream> stream;
+    std::thread worker;
+    std::mutex settle_mu;
+    int worker_rc = GENLIB_OK;
+    std::string worker_err;
+    void settle() {
+        std::lock_guard<std::mutex> lk(settle_mu);
+        if (worker.joinable()) worker.join();
+    }
+    bool streaming() const {            // layers are still coming and the bounds hold so far
+        return stream && stream->streamed.load() && !stream->overflow.load() && stream->stage.load() != 2;
+    }
+    ~genlib_plan() { if (worker.joinable()) worker.join(); }
 };
+inline void settle(const genlib_plan *plan) { if (plan) const_cast<genlib_plan *>(plan)->settle(); }
 
 // launch shape of one layer's persistent kernel (layer_kernel.cuh)
 struct LayerLaunch {
@@ -208,6 +224,8 @@ struct genlib_engine : IndexBufs {
     unsigned epoch = 0;
     long long barrier_timeout = (long long)20e9;   // cycles an inter-GPU barrier may wait (GENLIB_BARRIER_TIMEOUT_S)
     bool streamed = false;                 // built on a plan that was still being made: sized by its bounds, uploaded layer by layer
+    PlanStream *consuming = nullptr;       // registered as a reader of that plan's arrays (until the streamed run ends)
+    void stop_consuming() { if (consuming) { consuming->consumers.fetch_sub(1); consuming->wake(); consuming = nullptr; } }
     std::vector<int32_t> own_pro;          // proband indices (output rows) this rank owns, ascending
     std::vector<genlib_layer_info> info;
     std::vector<cudaEvent_t> events;
@@ -215,6 +233,7 @@ struct genlib_engine : IndexBufs {
     bool ran = false;
     int32_t layer_limit = -1;
     ~genlib_engine() {
+        stop_consuming();
         for (auto e : events) cudaEventDestroy(e);
         if (stream) cudaStreamSynchronize(stream);
         if (copy_stream) cudaStreamSynchronize(copy_stream);
@@ -903,24 +922,63 @@ int genlib_plan_create_ex(int32_t n, const int32_t *father, const int32_t *mothe
     return GENLIB_OK;
 }
 
+int genlib_plan_create_async(int32_t n, const int32_t *father, const int32_t *mother, const int64_t *ids, int32_t n_pro,
+                             const int32_t *proband, int32_t world, int schedule, genlib_plan **out) {
+    if (!out) return fail(GENLIB_EINVAL, "genlib_plan_create: out is null");
+    *out = nullptr;
+    if (env_int("GENLIB_STREAM", 1) == 0) return genlib_plan_create_ex(n, father, mother, ids, n_pro, proband, world, schedule, out);
+    std::unique_ptr<genlib_plan> pl(new (std::nothrow) genlib_plan);
+    if (!pl) return fail(GENLIB_ENOMEM, "out of host memory");
+    pl->stream.reset(new (std::nothrow) PlanStream);
+    if (!pl->stream) return fail(GENLIB_ENOMEM, "out of host memory");
+    genlib_plan *raw = pl.get();
+    const double t0 = now_ms();
+    try {
+        raw->worker = std::thread([=] {
+            try {
+                adopt_retired_storage(raw->p);
+                raw->worker_rc = build_plan(n, father, mother, ids, n_pro, proband, world, schedule, raw->p, raw->worker_err, raw->stream.get());
+            } catch (const std::bad_alloc &) {
+                raw->worker_rc = GENLIB_ENOMEM; raw->worker_err = "out of host memory while planning";
+                raw->stream->status.store(GENLIB_ENOMEM); raw->stream->stage.store(2); raw->stream->wake();
+            }
+            raw->ms_plan = now_ms() - t0;
+        });
+    } catch (...) {                              // no thread to be had
+        pl.reset();
+        return genlib_plan_create_ex(n, father, mother, ids, n_pro, proband, world, schedule, out);
+    }
+    PlanStream &ps = *raw->stream;
+    ps.wait([&] { return ps.stage.load() >= 1; });
+    if (ps.stage.load() == 2) {                  // finished already: an error of the pre-pass, or nothing to stream
+        raw->settle();
+        if (raw->worker_rc != GENLIB_OK) return fail(raw->worker_rc, raw->worker_err);
+    }
+    *out = pl.release();
+    return GENLIB_OK;
+}
+
 void genlib_plan_destroy(genlib_plan *plan) {
     if (!plan) return;
+    plan->settle();
     try { retire_storage(plan->p); } catch (...) {}
     delete plan;
 }
 int32_t genlib_plan_n_unique(const genlib_plan *plan) { return plan ? plan->p.n_unique : -1; }
 int32_t genlib_plan_schedule(const genlib_plan *plan) { return plan ? plan->p.schedule : -1; }
-int32_t genlib_plan_n_layers(const genlib_plan *plan) { return plan ? (int32_t)plan->p.layers.size() : -1; }
-int64_t genlib_plan_capacity(const genlib_plan *plan) { return plan ? plan->p.capacity : -1; }
-int64_t genlib_plan_row_updates(const genlib_plan *plan) { return plan ? plan->p.row_updates : -1; }
+int32_t genlib_plan_n_layers(const genlib_plan *plan) { settle(plan); return plan ? (int32_t)plan->p.layers.size() : -1; }
+int64_t genlib_plan_capacity(const genlib_plan *plan) { settle(plan); return plan ? plan->p.capacity : -1; }
+int64_t genlib_plan_row_updates(const genlib_plan *plan) { settle(plan); return plan ? plan->p.row_updates : -1; }
 
 int genlib_plan_layer_info(const genlib_plan *plan, int32_t layer, genlib_layer_info *out) {
+    settle(plan);
     if (!plan || !out || layer < 0 || layer >= (int32_t)plan->p.layers.size()) return fail(GENLIB_EINVAL, "bad layer");
     fill_info(plan->p.layers[layer], out);
     return GENLIB_OK;
 }
 
 int64_t genlib_plan_device_bytes(const genlib_plan *plan, int numerics, int32_t rank) {
+    settle(plan);
     if (!plan || rank < 0 || rank >= plan->p.world || plan->p.n_unique == 0) return plan ? 0 : -1;
     return (int64_t)engine_bytes(plan->p, numerics, rank);      // strip buffers sized for 148 SMs
 }
@@ -928,6 +986,7 @@ int64_t genlib_plan_device_bytes(const genlib_plan *plan, int numerics, int32_t 
 int genlib_plan_layer_arrays(const genlib_plan *plan, int32_t layer, int32_t *member_ind,
                              int32_t *member_slot, int32_t *member_fam, int32_t *fam_father_slot,
                              int32_t *fam_mother_slot, int32_t *member_owner) {
+    settle(plan);
     if (!plan || layer < 0 || layer >= (int32_t)plan->p.layers.size()) return fail(GENLIB_EINVAL, "bad layer");
     const Plan &P = plan->p;
     const Layer &L = P.layers[layer];
@@ -949,6 +1008,7 @@ int genlib_plan_layer_arrays(const genlib_plan *plan, int32_t layer, int32_t *me
 }
 
 int genlib_plan_layer_ranks(const genlib_plan *plan, int32_t layer, int32_t *member_rank) {
+    settle(plan);
     if (!plan || !member_rank || layer < 0 || layer >= (int32_t)plan->p.layers.size()) return fail(GENLIB_EINVAL, "bad layer");
     const Plan &P = plan->p;
     const Layer &L = P.layers[layer];
@@ -960,6 +1020,7 @@ int genlib_plan_layer_ranks(const genlib_plan *plan, int32_t layer, int32_t *mem
 int genlib_plan_layer_shard(const genlib_plan *plan, int32_t layer, int32_t *fam_base, int32_t *mem_base,
                             int32_t *member_lrow, int32_t *fam_father_owner, int32_t *fam_father_lrow,
                             int32_t *fam_mother_owner, int32_t *fam_mother_lrow) {
+    settle(plan);
     if (!plan || layer < 0 || layer >= (int32_t)plan->p.layers.size()) return fail(GENLIB_EINVAL, "bad layer");
     const Plan &P = plan->p;
     const Layer &L = P.layers[layer];
@@ -979,6 +1040,7 @@ int genlib_plan_layer_shard(const genlib_plan *plan, int32_t layer, int32_t *fam
 }
 
 int genlib_plan_layer_live_rows(const genlib_plan *plan, int32_t layer, int32_t *live_owner, int32_t *live_lrow) {
+    settle(plan);
     if (!plan || !live_owner || !live_lrow || layer < 0 || layer >= (int32_t)plan->p.layers.size()) return fail(GENLIB_EINVAL, "bad layer");
     const Plan &P = plan->p;
     const Layer &L = P.layers[layer];
@@ -992,6 +1054,7 @@ int genlib_plan_layer_live_rows(const genlib_plan *plan, int32_t layer, int32_t 
 }
 
 int64_t genlib_plan_rank_rows(const genlib_plan *plan, int32_t rank) {
+    settle(plan);
     if (!plan || rank < 0 || rank >= plan->p.world) return -1;
     return plan->p.rows_cap.empty() ? 0 : (int64_t)total_rows(plan->p, rank);
 }
@@ -999,12 +1062,14 @@ int64_t genlib_plan_rank_rows(const genlib_plan *plan, int32_t rank) {
 int32_t genlib_plan_world(const genlib_plan *plan) { return plan ? plan->p.world : -1; }
 
 int genlib_plan_proband_rows(const genlib_plan *plan, int32_t *owner, int32_t *lrow) {
+    settle(plan);
     if (!plan || !owner || !lrow) return fail(GENLIB_EINVAL, "null argument");
     for (size_t u = 0; u < plan->p.pro_ind.size(); u++) { owner[u] = plan->p.pro_owner[u]; lrow[u] = plan->p.pro_lrow[u]; }
     return GENLIB_OK;
 }
 
 int genlib_plan_layer_flags(const genlib_plan *plan, int32_t layer, uint8_t *live_flags) {
+    settle(plan);
     if (!plan || !live_flags || layer < 0 || layer >= (int32_t)plan->p.layers.size()) return fail(GENLIB_EINVAL, "bad layer");
     const Plan &P = plan->p;
     const Layer &L = P.layers[layer];
@@ -1014,18 +1079,35 @@ int genlib_plan_layer_flags(const genlib_plan *plan, int32_t layer, uint8_t *liv
 }
 
 int genlib_plan_proband_slots(const genlib_plan *plan, int32_t *slots) {
+    settle(plan);
     if (!plan || !slots) return fail(GENLIB_EINVAL, "null argument");
     std::copy(plan->p.pro_slot.begin(), plan->p.pro_slot.end(), slots);
     return GENLIB_OK;
 }
 
+// An engine on a plan that is still being made registers as a reader of its arrays before it looks at them.
+static int create_engine_public(const genlib_plan *plan, int numerics, int device, int rank, genlib_engine **out) {
+    if (plan && plan->streaming()) {
+        PlanStream &ps = *plan->stream;
+        ps.consumers.fetch_add(1);
+        if (!ps.overflow.load() && ps.stage.load() != 2) {
+            int rc = create_engine(plan, numerics, device, rank, out, true);
+            if (rc == GENLIB_OK) { (*out)->consuming = &ps; return rc; }
+            ps.consumers.fetch_sub(1); ps.wake();
+            if (rc != GENLIB_ENOMEM) return rc;             // (the bounds did not fit: size by the finished plan)
+        } else { ps.consumers.fetch_sub(1); ps.wake(); }
+    }
+    settle(plan);
+    if (plan && plan->worker_rc != GENLIB_OK) return fail(plan->worker_rc, plan->worker_err);
+    return create_engine(plan, numerics, device, rank, out);
+}
+
 int genlib_engine_create(const genlib_plan *plan, int numerics, int device, genlib_engine **out) {
-    if (plan && plan->p.world != 1) return fail(GENLIB_EINVAL, "plan was built for several ranks: use genlib_engine_create_dist");
-    return create_engine(plan, numerics, device, 0, out);
+    return create_engine_public(plan, numerics, device, 0, out);
 }
 
 int genlib_engine_create_dist(const genlib_plan *plan, int numerics, int device, int32_t rank, genlib_engine **out) {
-    return create_engine(plan, numerics, device, rank, out);
+    return create_engine_public(plan, numerics, device, rank, out);
 }
 
 int genlib_engine_ipc_export(genlib_engine *eng, void *handle64) {
@@ -1081,6 +1163,19 @@ int genlib_engine_run(genlib_engine *eng, int time_layers) {
     if (int rc = guard.enter(eng->device)) return rc;
     genlib_engine &E = *eng;
     if (!E.attached) return fail(GENLIB_ECOMM, "genlib_engine_run before genlib_engine_ipc_attach");
+    if (E.streamed && !E.ran) {                                 // first run on a plan that is still being made
+        if (!E.consuming) return fail(GENLIB_ERESTART, "the streamed plan's bounds did not hold: create the engine again");
+        PlanStream &ps = *E.consuming;
+        int rc = E.numerics == GENLIB_NUMERICS_FP64 ? run_streamed<double>(E, ps) : run_streamed<float>(E, ps);
+        E.stop_consuming();
+        settle(E.plan);
+        if (rc == kRestart) return fail(GENLIB_ERESTART, "a size bound of the streamed plan did not hold: destroy this engine, create it again and run");
+        if (rc != GENLIB_OK) return rc == E.plan->worker_rc ? fail(rc, E.plan->worker_err) : rc;
+        if (int rc2 = check_device_errors(E)) return rc2;
+        E.stats.ms_plan = E.plan->ms_plan;
+        E.ran = true;
+        return GENLIB_OK;
+    }
     const size_t nev = E.events.size();
     CU(cudaEventRecord(E.events[nev - 2], E.stream));
     int rc = E.numerics == GENLIB_NUMERICS_FP64 ? launch_layers<double>(E, time_layers != 0)
@@ -1109,6 +1204,7 @@ int genlib_engine_run(genlib_engine *eng, int time_layers) {
 }
 
 int genlib_engine_layer_info(genlib_engine *eng, int32_t layer, genlib_layer_info *out) {
+    if (eng) settle(eng->plan);
     if (!eng || !out || layer < 0 || layer >= (int32_t)eng->info.size()) return fail(GENLIB_EINVAL, "bad layer");
     account_layers(*eng);
     *out = eng->info[layer];
@@ -1223,52 +1319,126 @@ int genlib_phi_multi(int32_t n, const int32_t *father, const int32_t *mother, in
         if (devices[g] < 0 || devices[g] >= ndev) return fail(GENLIB_EINVAL, "genlib_phi_multi: no such device");
         for (int h = 0; h < g; h++) if (devices[h] == devices[g]) return fail(GENLIB_EINVAL, "genlib_phi_multi: a device is listed twice");
     }
-    genlib_plan *plan = nullptr;
-    int rc = genlib_plan_create(n, father, mother, n_pro, proband, n_dev, &plan);       // ONE plan for all ranks
+    // ONE plan for all ranks, made on a worker thread and handed over layer by layer (see genlib_phi)
+    std::unique_ptr<genlib_plan> plan_owner(new (std::nothrow) genlib_plan);
+    if (!plan_owner) return fail(GENLIB_ENOMEM, "out of host memory");
+    genlib_plan *plan = plan_owner.get();
+    const bool want_stream = env_int("GENLIB_STREAM", 1) != 0 && out != nullptr;
+    const double tp0 = now_ms();
+    PlanStream ps;
+    int plan_rc = GENLIB_OK;
+    std::string plan_err;
+    auto make_plan = [&](PlanStream *stream) {
+        try {
+            adopt_retired_storage(plan->p);
+            plan_rc = build_plan(n, father, mother, nullptr, n_pro, proband, n_dev, GENLIB_SCHEDULE_PHI, plan->p, plan_err, stream);
+        } catch (const std::bad_alloc &) {
+            plan_rc = GENLIB_ENOMEM; plan_err = "out of host memory while planning";
+            if (stream) { stream->status.store(plan_rc); stream->stage.store(2); stream->wake(); }
+        }
+        plan->ms_plan = now_ms() - tp0;
+    };
+    std::thread worker;
+    if (want_stream) { try { worker = std::thread([&] { make_plan(&ps); }); } catch (...) { } }
+    const bool streaming = worker.joinable();
+    if (!streaming) make_plan(nullptr);
+    // (destruction order: consumer registration, engines, worker joined, plan storage retired)
+    struct PlanRetire { genlib_plan *p; ~PlanRetire() { try { retire_storage(p->p); } catch (...) {} } } retire{plan};
+    struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{worker};   // (joins before the plan is retired)
+    std::vector<genlib_engine *> eng((size_t)n_dev, nullptr);
+    struct EngGuard { std::vector<genlib_engine *> &e; ~EngGuard() { for (auto *&x : e) { genlib_engine_destroy(x); x = nullptr; } } } eguard{eng};
+    int prev_dev = -1;
+    cudaGetDevice(&prev_dev);
+    struct DevRestore { int d; ~DevRestore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_dev};
+    // every device sees every other device's memory (NVLink peer access) -- while the planner's pre-pass runs
+    int peer_rc = GENLIB_OK;
+    for (int g = 0; g < n_dev && peer_rc == GENLIB_OK; g++) {
+        if (cudaSetDevice(devices[g]) != cudaSuccess) { peer_rc = fail(GENLIB_ECUDA, "cudaSetDevice failed"); break; }
+        for (int h = 0; h < n_dev; h++) {
+            if (h == g) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, devices[g], devices[h]);
+            if (!can) { peer_rc = fail(GENLIB_ECOMM, "devices " + std::to_string(devices[g]) + " and " + std::to_string(devices[h]) + " have no peer access"); break; }
+            const cudaError_t ce = cudaDeviceEnablePeerAccess(devices[h], 0);
+            if (ce != cudaSuccess && ce != cudaErrorPeerAccessAlreadyEnabled) { peer_rc = fail(GENLIB_ECOMM, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(ce)); break; }
+            cudaGetLastError();
+        }
+    }
+    // one host thread per device
+    std::vector<int> status((size_t)n_dev, GENLIB_OK);
+    std::vector<std::string> message((size_t)n_dev);
+    auto run_all = [&](auto &&fn) {                              // statuses stay in `status`
+        std::vector<std::thread> th;
+        for (int g = 0; g < n_dev; g++)
+            th.emplace_back([&, g] { status[(size_t)g] = fn(g); if (status[(size_t)g] != GENLIB_OK) message[(size_t)g] = g_err; });
+        for (auto &t : th) t.join();
+    };
+    auto first_error = [&](bool restart_is_error) {              // GENLIB_OK, kRestart (nothing worse happened) or an error
+        int rc2 = GENLIB_OK;
+        for (int g = 0; g < n_dev; g++) {
+            const int st = status[(size_t)g];
+            if (st == GENLIB_OK) continue;
+            if ((st == kRestart || st == GENLIB_ENOMEM) && !restart_is_error) { if (rc2 == GENLIB_OK) rc2 = kRestart; continue; }
+            return fail(st, "device " + std::to_string(devices[g]) + ": " + message[(size_t)g]);
+        }
+        return rc2;
+    };
+    auto on_all = [&](auto &&fn) { run_all(fn); return first_error(true); };
+    auto wire_peers = [&]() {                                    // plain peer pointers instead of IPC mappings
+        for (int g = 0; g < n_dev; g++) {
+            for (int h = 0; h < n_dev; h++) { eng[(size_t)g]->peers.A[h] = eng[(size_t)h]->A; eng[(size_t)g]->bars.flags[h] = eng[(size_t)h]->bar_flags; }
+            eng[(size_t)g]->attached = true;
+        }
+    };
+    int rc = GENLIB_OK;
+    bool done = false;
+    if (streaming) {
+        ps.wait([&] { return ps.stage.load() >= 1; });
+        if (peer_rc == GENLIB_OK && ps.streamed.load() && plan->p.n_unique > 0) {
+            struct Consumer {                                     // one registration for all device threads
+                PlanStream &s;
+                explicit Consumer(PlanStream &st) : s(st) { s.consumers.fetch_add(1); }
+                ~Consumer() { s.consumers.fetch_sub(1); s.wake(); }
+            } consumer(ps);
+            if (!ps.overflow.load()) {
+                run_all([&](int g) { return create_engine(plan, numerics, devices[g], g, &eng[(size_t)g], true); });
+                rc = first_error(false);
+                if (rc == GENLIB_OK) {
+                    wire_peers();
+                    run_all([&](int g) {
+                        genlib_engine &E = *eng[(size_t)g];
+                        DeviceGuard guard;
+                        if (int r = guard.enter(E.device)) return r;
+                        int r = numerics == GENLIB_NUMERICS_FP64 ? run_streamed<double>(E, ps) : run_streamed<float>(E, ps);
+                        if (r == GENLIB_OK) r = check_device_errors(E);
+                        if (r == GENLIB_OK) E.ran = true;
+                        return r;
+                    });
+                    rc = first_error(false);
+                    done = rc == GENLIB_OK;
+                }
+                if (rc == kRestart) rc = GENLIB_OK;
+            }
+        }
+        worker.join();
+    }
+    if (plan_rc != GENLIB_OK) return fail(plan_rc, plan_err);
+    if (peer_rc != GENLIB_OK) return peer_rc;
     if (rc != GENLIB_OK) return rc;
-    struct PlanGuard { genlib_plan *p; ~PlanGuard() { genlib_plan_destroy(p); } } pguard{plan};
     if (plan->p.n_unique == 0) {
         if (stats) { std::memset(stats, 0, sizeof *stats); stats->ms_plan = plan->ms_plan; }
         return GENLIB_OK;
     }
     if (!out) return fail(GENLIB_EINVAL, "genlib_phi_multi: out is null");
-    int prev_dev = -1;
-    cudaGetDevice(&prev_dev);
-    struct DevRestore { int d; ~DevRestore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_dev};
-    // every device sees every other device's memory (NVLink peer access)
-    for (int g = 0; g < n_dev; g++) {
-        if (cudaSetDevice(devices[g]) != cudaSuccess) return fail(GENLIB_ECUDA, "cudaSetDevice failed");
-        for (int h = 0; h < n_dev; h++) {
-            if (h == g) continue;
-            int can = 0;
-            cudaDeviceCanAccessPeer(&can, devices[g], devices[h]);
-            if (!can) return fail(GENLIB_ECOMM, "devices " + std::to_string(devices[g]) + " and " + std::to_string(devices[h]) + " have no peer access");
-            const cudaError_t ce = cudaDeviceEnablePeerAccess(devices[h], 0);
-            if (ce != cudaSuccess && ce != cudaErrorPeerAccessAlreadyEnabled) return fail(GENLIB_ECOMM, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(ce));
-            cudaGetLastError();
-        }
+    if (!done) {                                                // plan first, then run (no streaming, or its bounds did not hold)
+        for (auto *&x : eng) { genlib_engine_destroy(x); x = nullptr; }
+        rc = on_all([&](int g) { return create_engine(plan, numerics, devices[g], g, &eng[(size_t)g]); });
+        if (rc != GENLIB_OK) return rc;
+        wire_peers();
+        rc = on_all([&](int g) { return genlib_engine_run(eng[(size_t)g], 0); });
+        if (rc != GENLIB_OK) return rc;
     }
-    // one host thread per device: engine (upload of the plan), then, all together, the layers and the fetch
-    std::vector<genlib_engine *> eng((size_t)n_dev, nullptr);
-    std::vector<int> status((size_t)n_dev, GENLIB_OK);
-    std::vector<std::string> message((size_t)n_dev);
-    auto on_all = [&](auto &&fn) {
-        std::vector<std::thread> th;
-        for (int g = 0; g < n_dev; g++)
-            th.emplace_back([&, g] { status[(size_t)g] = fn(g); if (status[(size_t)g] != GENLIB_OK) message[(size_t)g] = g_err; });
-        for (auto &t : th) t.join();
-        for (int g = 0; g < n_dev; g++) if (status[(size_t)g] != GENLIB_OK) return fail(status[(size_t)g], "device " + std::to_string(devices[g]) + ": " + message[(size_t)g]);
-        return (int)GENLIB_OK;
-    };
-    struct EngGuard { std::vector<genlib_engine *> &e; ~EngGuard() { for (auto *x : e) genlib_engine_destroy(x); } } eguard{eng};
-    rc = on_all([&](int g) { return create_engine(plan, numerics, devices[g], g, &eng[(size_t)g]); });
-    if (rc != GENLIB_OK) return rc;
-    for (int g = 0; g < n_dev; g++) {                           // plain peer pointers instead of IPC mappings
-        for (int h = 0; h < n_dev; h++) { eng[(size_t)g]->peers.A[h] = eng[(size_t)h]->A; eng[(size_t)g]->bars.flags[h] = eng[(size_t)h]->bar_flags; }
-        eng[(size_t)g]->attached = true;
-    }
-    rc = on_all([&](int g) { return genlib_engine_run(eng[(size_t)g], 0); });
-    if (rc != GENLIB_OK) return rc;
+    for (auto *x : eng) x->stats.ms_plan = plan->ms_plan;
     const int32_t nu = plan->p.n_unique;
     const double t0 = now_ms();
     rc = on_all([&](int g) {                                    // contiguous row blocks, one PCIe link each

@@ -13,14 +13,17 @@ from typing import Optional
 import numpy as np
 
 from . import _lib
-from ._lib import LayerInfo, Stats, check, lib, ptr
+from ._lib import LayerInfo, PlanBoundsExceeded, Stats, check, lib, ptr
 from .pedigree import Pedigree, pro
 
 
 class Plan:
     """Host schedule (levels, Kirkpatrick frontier, slots). Needs no GPU."""
 
-    def __init__(self, father, mother, proband_ranks, world: int = 1, schedule: str = "phi", ids=None):
+    def __init__(self, father, mother, proband_ranks, world: int = 1, schedule: str = "phi", ids=None,
+                 stream: bool = False):
+        """stream=True: the plan is made on a worker thread (genlib_plan_create_async); an Engine created on
+        it runs every layer as soon as it is planned.  Any query but n_unique / world waits for the whole plan."""
         self.father = np.ascontiguousarray(father, np.int32)
         self.mother = np.ascontiguousarray(mother, np.int32)
         self.probands = np.ascontiguousarray(proband_ranks, np.int32)
@@ -31,9 +34,9 @@ class Plan:
         if self.ids is not None and len(self.ids) != len(self.father):
             raise ValueError("ids must have one entry per individual")
         h = C.c_void_p()
-        check(lib().genlib_plan_create_ex(len(self.father), ptr(self.father), ptr(self.mother), ptr(self.ids),
-                                          len(self.probands), ptr(self.probands), world,
-                                          _lib.SCHEDULES[schedule], C.byref(h)))
+        create = lib().genlib_plan_create_async if stream else lib().genlib_plan_create_ex
+        check(create(len(self.father), ptr(self.father), ptr(self.mother), ptr(self.ids),
+                     len(self.probands), ptr(self.probands), world, _lib.SCHEDULES[schedule], C.byref(h)))
         self._h = h
         self.world = world
         self.schedule = schedule
@@ -242,7 +245,7 @@ def phi(pedigree: Pedigree, probandIDs=None, *, verbose: bool = False, compute: 
     the frontier over several GPUs of the box from this one process (genlib_phi_multi)."""
     IDs = pro(pedigree) if probandIDs is None else np.asarray(probandIDs, np.int64)
     ranks = pedigree.rank_of(IDs)                       # KeyError, like pedigree[ID]
-    plan = Plan(pedigree.father, pedigree.mother, ranks)
+    plan = Plan(pedigree.father, pedigree.mother, ranks, stream=compute and not verbose and devices is None)
     if verbose or not compute:
         for line in plan.verbose_lines():
             print(line)
@@ -264,12 +267,41 @@ def phi(pedigree: Pedigree, probandIDs=None, *, verbose: bool = False, compute: 
         device = int(devices[0])
     eng = Engine(plan, numerics=numerics, device=device)
     try:
-        eng.run()
+        try:
+            eng.run()
+        except PlanBoundsExceeded:                      # a bound of the streamed plan did not hold: the plan is finished now
+            eng.close()
+            eng = Engine(plan, numerics=numerics, device=device)
+            eng.run()
         res = eng.fetch(out=out, dtype=dtype)
         stats = eng.stats()
     finally:
         eng.close()
     return (res, stats) if return_stats else res
+
+
+def run_distributed(plan: Plan, numerics="reference", device: int = 0, rank: int = 0) -> Engine:
+    """This rank's engine of a `torch.distributed` job, attached to its peers and run once.  Collective.
+    With a streamed plan (Plan(..., stream=True)) the layers run while the later ones are planned; if a size
+    bound of that plan does not hold, every rank finds out (same plan, same bounds) and all start over."""
+    import torch.distributed as dist
+    for attempt in (0, 1):
+        eng = Engine(plan, numerics=numerics, device=device, rank=rank)
+        try:
+            handles = [None] * plan.world
+            dist.all_gather_object(handles, eng.ipc_handle())
+            eng.attach(handles)
+            dist.barrier()
+            eng.run()
+            return eng
+        except PlanBoundsExceeded:
+            dist.barrier()                  # nobody unmaps while a peer may still read
+            eng.close()
+            if attempt:
+                raise
+        except BaseException:
+            eng.close()
+            raise
 
 
 def phi_distributed(pedigree: Pedigree, probandIDs=None, *, numerics="reference", dtype=np.float32,
@@ -287,7 +319,7 @@ def phi_distributed(pedigree: Pedigree, probandIDs=None, *, numerics="reference"
     IDs = pro(pedigree) if probandIDs is None else np.asarray(probandIDs, np.int64)
     ranks = pedigree.rank_of(IDs)
     plan = Plan(pedigree.father, pedigree.mother, ranks, world=world, schedule=schedule,
-                ids=pedigree.ids if schedule != "phi" else None)
+                ids=pedigree.ids if schedule != "phi" else None, stream=True)
     n = plan.n_unique
     if n == 0:
         res = np.zeros((0, 0), dtype)
@@ -295,13 +327,8 @@ def phi_distributed(pedigree: Pedigree, probandIDs=None, *, numerics="reference"
     if device is None:
         import os
         device = int(os.environ.get("LOCAL_RANK", rank))
-    eng = Engine(plan, numerics=numerics, device=device, rank=rank)
+    eng = run_distributed(plan, numerics=numerics, device=device, rank=rank)
     try:
-        handles = [None] * world
-        dist.all_gather_object(handles, eng.ipc_handle())
-        eng.attach(handles)
-        dist.barrier()
-        eng.run()
         own, rows = eng.own_probands(), eng.fetch(dtype=dtype)
         stats = eng.stats()
         dist.barrier()                      # nobody unmaps while a peer may still read

@@ -38,6 +38,10 @@ extern "C" {
 #define GENLIB_ECUDA 4     /* CUDA runtime / driver error, no usable device             */
 #define GENLIB_ENOMEM 5    /* working set does not fit the device(s)                    */
 #define GENLIB_ECOMM 6     /* NCCL / peer-memory set-up failed                          */
+#define GENLIB_ERESTART 7  /* genlib_engine_run on an engine of a plan that was still    */
+                           /* being made (genlib_plan_create_async): a size bound did    */
+                           /* not hold; destroy the engine, create it again (the plan is */
+                           /* finished by then) and run                                  */
 
 /* numerics: how the frontier is stored between generation steps */
 #define GENLIB_NUMERICS_REFERENCE 0 /* Float32 storage, Float64 arithmetic, one RN32 per   */
@@ -155,6 +159,15 @@ int genlib_plan_create_scheduled(int32_t n, const int32_t *father, const int32_t
  * the rank.  Ignored by GENLIB_SCHEDULE_PHI. */
 int genlib_plan_create_ex(int32_t n, const int32_t *father, const int32_t *mother, const int64_t *ids,
                           int32_t n_pro, const int32_t *proband, int32_t world, int schedule, genlib_plan **out);
+/* The same, made on a worker thread: the call returns when the pre-pass is done (validation errors are reported
+ * here, like above) and the layers follow one by one.  An engine created on such a plan is sized by upper bounds
+ * and genlib_engine_run uploads and launches every layer as soon as it is planned -- planning overlaps the device
+ * (it is otherwise the largest host-side part of a call; genlib_phi does the same internally).  If a bound turns
+ * out too small, genlib_engine_run returns GENLIB_ERESTART (see there).  father / mother / ids / proband must
+ * stay valid until the plan is finished: until genlib_engine_run, any genlib_plan_* query other than n_unique /
+ * world / schedule, or genlib_plan_destroy returns.  In a multi-rank job every rank takes the same decisions. */
+int genlib_plan_create_async(int32_t n, const int32_t *father, const int32_t *mother, const int64_t *ids,
+                             int32_t n_pro, const int32_t *proband, int32_t world, int schedule, genlib_plan **out);
 int32_t genlib_plan_schedule(const genlib_plan *plan);
 void genlib_plan_destroy(genlib_plan *plan);
 int32_t genlib_plan_n_unique(const genlib_plan *plan);
