@@ -308,6 +308,7 @@ LayerLaunch shape_layer(const Plan &P, int t, int rank, size_t es, int sm_count)
     // producer items: 2 ft parent rows x one live tile; consumer items: the member tiles
     s.n_pitems = live ? (sw / s.ft) * L.n_live_tiles : 0;
     s.n_citems = L.n_mtiles;
+    s.discard = env_int("GENLIB_DISCARD", 2);     // 0: off, 1: without the release fence (experiments), 2: on
     // One CTA per SM: four producer warps and a consumer group of eight.  Every CTA of a gang takes part in the
     // hand-over of each of the gang's strips, whether it has an item there or not, and a switch of strips costs a
     // CTA some microseconds of dependent loads: a strip should bring every CTA several items.  Layers with short

@@ -80,6 +80,7 @@ struct StripArgs {
     int32_t cons_bytes;  // dynamic shared memory of one consumer group
     int32_t n_pitems;    // producer items per strip: (sw / ft) * live tiles
     int32_t n_citems;    // consumer items per strip: the layer's member tiles
+    int32_t discard;     // a consumer drops the strip-buffer rows it was the only one to read from L2 (no write-back of dead lines)
     int32_t ring_off;    // byte offset of the producer ring in dynamic shared memory (after the consumer's part)
     int64_t qstride;     // pairs per strip buffer (live tiles * kPTile * sw)
     void *Q;             // strip buffers
@@ -565,9 +566,14 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
     // A group's share of a strip is done: its copies of the strip's pairs have landed in shared memory (it waited
     // for them), which is all the producers that will overwrite the buffer need to know -- no fence: the rows it
     // wrote are read by the next kernel at the earliest.
+    // With discards in flight the count is a release: the producers that overwrite the buffer must find the
+    // group's discards performed (the barrier makes them the counting thread's business, the fence orders them).
     auto consumed = [&](int *counter) {
         cons_sync();
-        if (tid == 0) atomicAdd(counter, 1);
+        if (tid == 0) {
+            if (S.discard > 1) __threadfence();
+            atomicAdd(counter, 1);
+        }
     };
     const int prod_arrivals = S.n_prod / G;                        // what done_p[s] reaches when strip s is complete
     constexpr int kMetaSlots = 3, kMetaInts = 4 * kMTile;          // per slot: qrow[128] | couple[128] | rank[128] | slot[128]
@@ -614,7 +620,7 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
     auto stage_tile = [&](const P2 *Q, int nfJ, int slot) {
         if (lane < 2 * kMaxTileFam / kGroupWarps) {                 // the issue is serial per warp
             const int r = warp * (2 * kMaxTileFam / kGroupWarps) + lane;
-            const int q = r < 2 * nfJ ? meta[slot * kMetaInts + r] : -1;
+            const int q0 = r < 2 * nfJ ? meta[slot * kMetaInts + r] : -1, q = q0 >= 0 ? (q0 & ~kSoleReader) : -1;
             CHECK(q >= -1 && (long long)q * sw < S.qstride);
             const unsigned dst = stg_s + (unsigned)(r * row_bytes);
             if (q >= 0) {                                          // (write after read of the staging area: no proxy fence)
@@ -704,6 +710,16 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
         cp_async_wait<0>();                                        // the next tile's metadata (own copies) ...
         await_tile();                                              // ... and this tile's segments have landed
         cons_sync();                                               // for everybody; the previous item is written
+        // The segments are in shared memory.  Those this tile was the only one to read (kSoleReader: the parent has no
+        // other couple in the layer) are dead in the strip buffer, but dirty: dropped from L2 now (discard.global.L2),
+        // they are neither written back to DRAM nor do they take the room of pairs that have not been read yet.
+        if (S.discard && row_bytes >= 128 && tid < 2 * nfJ) {
+            const int q0 = meta[slot0 * kMetaInts + tid];
+            if (q0 >= 0 && (q0 & kSoleReader)) {
+                const unsigned char *seg = reinterpret_cast<const unsigned char *>(Q + (size_t)(q0 & ~kSoleReader) * sw);
+                for (int b = 0; b < row_bytes; b += 128) asm volatile("discard.global.L2 [%0], 128;" ::"l"(seg + b) : "memory");
+            }
+        }
         PROF_MARK(3);
         // is the next item's strip produced?  Asked now, answered after the arithmetic (an L2 round trip)
         const bool peek_next = is_tile(c1) && c1.s != s;

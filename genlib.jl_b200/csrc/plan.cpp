@@ -693,6 +693,17 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
             L.n_mtiles++;
             q0 = q1;
         }
+        {   // Parents of ONE couple of the layer whose members lie in ONE member tile: their strip-buffer rows are read
+            // by a single consumer item (kSoleReader).  A couple whose members straddle a tile cut counts twice.
+            std::vector<int32_t> &readers = W.cnt; readers.assign((size_t)std::max(L.n_live_tiles, 1) * kPTile, 0);
+            int32_t *fq = P.fam_q.data() + 2 * L.fam_off;
+            for (int32_t k = 0; k < 2 * nf; k++) if (fq[k] >= 0) readers[(size_t)fq[k]]++;
+            const int32_t *md = P.mtile_desc.data() + 4 * L.mtile_off;
+            for (int32_t j = 1; j < L.n_mtiles; j++)
+                if (md[4 * j] == md[4 * (j - 1)] + md[4 * (j - 1) + 1] - 1)           // first couple == the previous tile's last
+                    for (int32_t k = 2 * md[4 * j]; k < 2 * md[4 * j] + 2; k++) if (fq[k] >= 0) readers[(size_t)fq[k]]++;
+            for (int32_t k = 0; k < 2 * nf; k++) if (fq[k] >= 0 && readers[(size_t)fq[k]] == 1) fq[k] |= kSoleReader;
+        }
         L.alg_elems = 4.0 * nn * (double)L.live_before + 3.0 * (double)nn * nn;
         P.alg_elems += L.alg_elems;
         P.row_updates += nn;
@@ -720,7 +731,7 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
             const int64_t qrows = (int64_t)L.n_live_tiles * kPTile;
             for (int32_t f = 0; f < L.n_fam; f++)
                 for (int s2 = 0; s2 < 2; s2++) {
-                    const int32_t q = P.fam_q[2 * (L.fam_off + (size_t)f) + s2];
+                    const int32_t q0 = P.fam_q[2 * (L.fam_off + (size_t)f) + s2], q = q0 >= 0 ? (q0 & ~kSoleReader) : q0;
                     const int32_t slot = s2 ? P.fam_pm[L.fam_off + f] : P.fam_pf[L.fam_off + f];
                     if (q < -1 || q >= qrows || (q < 0) != (slot < 0)) { err = "verify: fam_q out of range in layer " + std::to_string(t) + " couple " + std::to_string(f) + " q " + std::to_string(q) + " qrows " + std::to_string(qrows) + " slot " + std::to_string(slot) + " rt_lo " + std::to_string(L.rt_lo); return GENLIB_EINVAL; }
                 }

@@ -41,6 +41,8 @@ constexpr int kSchedulePhi = 0, kScheduleSparsePhi = 1, kScheduleSparsePhiSymmet
 inline bool sparse_schedule(int s) { return s == kScheduleSparsePhi || s == kScheduleSparsePhiSymmetric; }
 
 constexpr int32_t kTileCarried = 1 << 30;   // live_tiles entry: the tile has a carried column
+constexpr int32_t kSoleReader = 1 << 30;    // fam_q entry (>= 0): no other couple of the layer has this parent -- whoever reads its row of a
+                                            // strip buffer is the only one to do so (and may drop it from L2 afterwards)
 constexpr uint8_t kFlagLive = 1;     // slot holds an individual that is live before the step
 constexpr uint8_t kFlagCarried = 2;  // ... and stays live after it
 
@@ -76,7 +78,7 @@ struct Plan {
     std::vector<int32_t> mem_ind, mem_slot, mem_fam;   // family-major order inside a layer
     std::vector<int32_t> mem_rank;                     // sparse_phi schedules: the members' pedigree ranks (mem_ind = queue position)
     std::vector<int32_t> fam_pf, fam_pm, fam_start;    // parents as slots (-1 = none)
-    std::vector<int32_t> fam_q;                        // 2 per couple: father, mother as rows of the layer kernel's strip buffers (-1 = none)
+    std::vector<int32_t> fam_q;                        // 2 per couple: father, mother as rows of the layer kernel's strip buffers (-1 = none), | kSoleReader
     std::vector<uint8_t> flags;
     std::vector<int32_t> tile_map;                     // per tile of a layer's live range: its index among the live tiles (-1: hole)
     std::vector<int32_t> live_tiles;                   // the inverse: live tiles in order, | kTileCarried if a column is carried
