@@ -236,7 +236,13 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
     for (int32_t x : P.pro_ind) { pre[x].h = 0; pre[x].rl = 0; }
     int32_t hmax = 0;
     std::vector<int32_t> &hist = W.hist; hist.clear();
+    constexpr int32_t kPf = 24;                  // software prefetch distance of the planner's random accesses
     for (int32_t x = n - 1; x >= 0; x--) {
+        if (x >= kPf) {
+            const int32_t y = x - kPf, fy = father[y], my = mother[y];
+            if (fy >= 0) __builtin_prefetch(&pre[fy], 1);
+            if (my >= 0) __builtin_prefetch(&pre[my], 1);
+        }
         const Pre px = pre[x];
         if (px.h < 0) continue;
         if (px.h >= (int32_t)hist.size()) hist.resize((size_t)px.h + 64, 0);
@@ -528,14 +534,20 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         next_live.clear();
         if (!live.empty()) {
             int32_t lo = INT_MAX, hi = -1;
-            for (int32_t x : live) { lo = std::min(lo, home[x].slot); hi = std::max(hi, home[x].slot); }
+            for (size_t li = 0; li < live.size(); li++) {
+                if (li + kPf < live.size()) __builtin_prefetch(&home[live[li + kPf]]);
+                const int32_t sl = home[live[li]].slot;
+                lo = std::min(lo, sl); hi = std::max(hi, sl);
+            }
             L.rt_lo = (lo / kPTile) * kPTile;
             L.rt_rows = round_up(hi + 1, kPTile) - L.rt_lo;
             P.flags.resize(L.flag_off + (size_t)L.rt_rows, 0);
             P.live_owner.resize(L.flag_off + (size_t)L.rt_rows, 0);
             P.live_lrow.resize(L.flag_off + (size_t)L.rt_rows, 0);
             uint8_t *fl = P.flags.data() + L.flag_off;
-            for (int32_t x : live) {
+            for (size_t li = 0; li < live.size(); li++) {
+                if (li + kPf < live.size()) __builtin_prefetch(&home[live[li + kPf]]);
+                const int32_t x = live[li];
                 const Home hx = home[x];
                 const bool stays = hx.last > t;      // read for the last time in step `last`
                 const int32_t r = hx.slot - L.rt_lo;
@@ -646,6 +658,8 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
             int32_t *mi = P.mem_ind.data() + L.mem_off, *ms = P.mem_slot.data() + L.mem_off;
             int32_t *mf = P.mem_fam.data() + L.mem_off, *ml = P.mem_lrow.data() + L.mem_off;
             for (int32_t q = 0; q < nn; q++) {
+                if (q + kPf < nn) __builtin_prefetch(&home[X[order[q + kPf]]], 1);
+                if (q + 2 * kPf < nn) { __builtin_prefetch(&X[order[q + 2 * kPf]]); __builtin_prefetch(&fam_of[order[q + 2 * kPf]]); }
                 const int32_t oq = order[q], x = X[oq], f = fam_of[oq];
                 const int32_t g = fam_own[f];
                 const int32_t s = slots.take(), lr = world > 1 ? rows[g].take() : s;   // one rank: row == slot
@@ -662,6 +676,12 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         P.fam_pf_lrow.resize(L.fam_off + (size_t)nf, -1); P.fam_pm_lrow.resize(L.fam_off + (size_t)nf, -1);
         P.fam_q.resize(2 * (L.fam_off + (size_t)nf), -1);
         for (int32_t f = 0; f < nf_real; f++) {
+            if (f + kPf < nf_real) {
+                const int32_t y = X[fam_first[f + kPf]], fy = father[y], my = mother[y];
+                if (fy >= 0) __builtin_prefetch(&home[fy]);
+                if (my >= 0) __builtin_prefetch(&home[my]);
+            }
+            if (f + 2 * kPf < nf_real) { const int32_t y = X[fam_first[f + 2 * kPf]]; __builtin_prefetch(&father[y]); __builtin_prefetch(&mother[y]); }
             const int32_t x = X[fam_first[f]], fa = father[x], mo = mother[x];
             const size_t k = L.fam_off + (size_t)newid[f];
             int32_t *ps[2] = {&P.fam_pf[k], &P.fam_pm[k]};
