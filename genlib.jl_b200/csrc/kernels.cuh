@@ -226,8 +226,8 @@ rowsum_kernel(const T *__restrict__ A, int64_t ld, const int32_t *__restrict__ o
 // barrier_kernel: all ranks of one box meet here (one process per GPU, so every rank's
 // kernel is resident on its own device).  Rank r stores `epoch` into slot r of every peer's
 // flag array (release, system scope, through the NVLink mapping) and waits until all slots of
-// its own array have reached `epoch`.  A rank that waits longer than ~10 s records an error
-// instead of hanging.
+// its own array have reached `epoch`.  A rank that waits longer than ~10 s (GENLIB_BARRIER_TIMEOUT_S)
+// records an error in every rank's flag block instead of hanging: all ranks' genlib_engine_run fail.
 // =====================================================================================
 struct BarrierTable {
     unsigned *flags[kMaxWorld];   // [world] words on each rank; word kMaxWorld = error flag
@@ -244,7 +244,11 @@ __global__ void barrier_kernel(BarrierTable B, int rank, int world, unsigned epo
         unsigned v;
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
         if ((int)(v - epoch) >= 0) break;
-        if (clock64() - t0 > timeout_cycles) { B.flags[rank][kMaxWorld] = 1u; break; }
+        if (clock64() - t0 > timeout_cycles) {               // tell EVERY rank: the peers that arrive later pass this barrier,
+            for (int g = 0; g < world; g++)                   // but their genlib_engine_run must fail as well
+                asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(B.flags[g] + kMaxWorld), "r"(1u) : "memory");
+            break;
+        }
         __nanosleep(200);
     }
     __threadfence_system();
