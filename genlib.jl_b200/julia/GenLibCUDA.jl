@@ -76,6 +76,19 @@ function phi(pedigree::GenLib.Pedigree, probandIDs::Vector{Int} = GenLib.pro(ped
              device::Integer = -1, devices::Vector{<:Integer} = Int[], pinned::Bool = false)
     father, mother = flatten(pedigree)
     probands = Int32[pedigree[ID].rank - 1 for ID in probandIDs]      # KeyError on unknown ID
+    if compute && !verbose
+        # The one-call entry points plan on a worker thread and run every generation as soon as it is planned
+        # (planning is otherwise the largest host-side part of the call): nothing here needs the plan itself.
+        n = length(unique(probands))                                   # duplicates collapse (src/compute.jl:251)
+        ϕ = pinned ? pinned_matrix(Float32, n) : Matrix{Float32}(undef, n, n)   # symmetric: layout-free
+        n == 0 && return ϕ
+        devs = isempty(devices) ? Int32[device] : Int32.(devices)      # one device: genlib_phi; several: sharded rows
+        GC.@preserve ϕ check(ccall((:genlib_phi_multi, libgenlib[]), Cint,
+            (Int32, Ptr{Int32}, Ptr{Int32}, Int32, Ptr{Int32}, Ptr{Cvoid}, Cint, Cint, Int32, Ptr{Int32}, Ptr{Cvoid}),
+            length(father), father, mother, length(probands), probands, ϕ, 0,
+            numerics === :fp64 ? 1 : 0, length(devs), devs, C_NULL))
+        return ϕ
+    end
     plan = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:genlib_plan_create, libgenlib[]), Cint,
                 (Int32, Ptr{Int32}, Ptr{Int32}, Int32, Ptr{Int32}, Int32, Ptr{Ptr{Cvoid}}),
