@@ -183,6 +183,7 @@ inline void settle(const genlib_plan *plan) { if (plan) const_cast<genlib_plan *
 // launch shape of one layer's persistent kernel (layer_kernel.cuh)
 struct LayerLaunch {
     StripArgs s{};
+    int prod_warps = 4;                    // producer warps per CTA (template parameter of the layer kernel)
     int grid = 0;
     size_t smem = 0;
     size_t sync_off = 0;                   // ints, into the engine's sync region
@@ -335,7 +336,12 @@ LayerLaunch shape_layer(const Plan &P, int t, int rank, size_t es, int sm_count)
     s.groups = groups;
     s.n_cons = G * std::min(ctas * groups, s.n_citems);
     const size_t stage = (size_t)2 * s.ft * (kPTile * es + 16);
-    const size_t cons_bytes = layer_consumer_bytes(sw, es);
+    // eight producer warps (and four consumer warps) where the producers have the carried columns to write as well
+    {
+        const int forced = env_int("GENLIB_PROD_WARPS", 0);
+        out.prod_warps = forced == 4 || forced == 8 ? forced : (L.carried > 0 && live && kConsGroups == 1 ? 8 : 4);
+    }
+    const size_t cons_bytes = layer_consumer_bytes(sw, es, out.prod_warps);
     const size_t smem_cap = (size_t)227 * 1024 - 2048;      // (static shared memory and the driver's share)
     s.stages = (int)std::max<size_t>(2, std::min<size_t>((size_t)std::min(kMaxStages, env_int("GENLIB_STAGES", kMaxStages)), (smem_cap - groups * cons_bytes) / stage));
     s.cons_bytes = (int32_t)cons_bytes;
@@ -435,15 +441,19 @@ int launch_barrier(genlib_engine &E) {
 }
 
 template <typename T>
-auto layer_function(const Plan &P) {
-    return sparse_schedule(P.schedule) ? layer_kernel<T, true> : layer_kernel<T, false>;   // sparse_phi's arithmetic (Float32 halves of stored values)
+auto layer_function(const Plan &P, int prod_warps) {
+    const bool stored = sparse_schedule(P.schedule);           // sparse_phi's arithmetic (Float32 halves of stored values)
+    if (prod_warps == 8) return stored ? layer_kernel<T, true, 8> : layer_kernel<T, false, 8>;
+    return stored ? layer_kernel<T, true, 4> : layer_kernel<T, false, 4>;
 }
 
 template <typename T>
 int prepare_launches(genlib_engine &E, size_t smem_max) {
-    auto layer_fn = layer_function<T>(E.plan->p);
-    CU(cudaFuncSetAttribute(layer_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-    CU(cudaFuncSetAttribute(layer_fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    for (int pw : {4, 8}) {
+        auto layer_fn = layer_function<T>(E.plan->p, pw);
+        CU(cudaFuncSetAttribute(layer_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+        CU(cudaFuncSetAttribute(layer_fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    }
     CU(cudaMemsetAsync(E.sync, 0, std::max<size_t>(E.sync_ints, 1) * sizeof(int32_t), E.stream));
     return GENLIB_OK;
 }
@@ -456,9 +466,9 @@ int launch_layer(genlib_engine &E, int t, bool timed, size_t &ev, int &launches)
     if (L.n_new == 0) return GENLIB_OK;
     T *A = static_cast<T *>(E.A);
     const int64_t ld = P.capacity;
-    auto layer_fn = layer_function<T>(P);
     LayerArgs a = layer_args(E, t);
     LayerLaunch &ll = E.launch[t];
+    auto layer_fn = layer_function<T>(P, ll.prod_warps);
     if (timed) CU(cudaEventRecord(E.events[ev++], E.stream));
     if (ll.grid > 0) {
         ll.s.Q = E.Q;

@@ -57,15 +57,16 @@ namespace genlib {
 #ifndef GENLIB_CONS_GROUPS
 #define GENLIB_CONS_GROUPS 1
 #endif
-constexpr int kConsGroups = GENLIB_CONS_GROUPS, kGroupWarps = 8, kProdWarps = 4;   // consumer groups per CTA, warps per group
-constexpr int kConsWarps = kConsGroups * kGroupWarps;
-constexpr int kGroupThreads = kGroupWarps * 32, kConsThreads = kConsWarps * 32, kProdThreads = kProdWarps * 32;
-constexpr int kLayerThreads = kConsThreads + kProdThreads;
+// A CTA has 12 warps.  How many of them produce is a template parameter of the kernel (PW): 4 producer warps and a
+// consumer group of 8 for layers without carried individuals (C3, C4: the two roles take the same time), 8 and 4
+// where the producers also write the members' rows against the carried columns and their mirror image (C5,
+// genea140: the producers set the pace there and the consumers mostly wait).
+constexpr int kConsGroups = GENLIB_CONS_GROUPS;    // consumer groups per CTA
+constexpr int kLayerWarps = 12, kLayerThreads = kLayerWarps * 32;
+__host__ __device__ constexpr int group_warps(int pw) { return (kLayerWarps - pw) / kConsGroups; }
 constexpr int kMaxStrip = 64;                   // couples per strip (upper bound of StripArgs::sw)
 constexpr int kVPitch = kMaxTileFam + 1;        // row pitch of the staged couple tile (65: conflict-free)
 constexpr int kMaxStages = 4;
-constexpr int kRowCache = kGroupThreads;         // strip member rows a consumer group keeps in shared memory at a time
-constexpr int kProdCols = kPTile / kProdWarps;  // columns of a tile that one producer warp transposes
 
 struct StripArgs {
     int32_t sw;          // strip width: couples per strip (8, 16, 32 or 64)
@@ -113,9 +114,10 @@ __device__ __forceinline__ void mbar_arrive(unsigned bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 // barrier of one consumer group only (the producer warps never meet anybody)
+template <int THREADS>
 __device__ __forceinline__ void group_sync(int grp) {
-    if constexpr (kConsGroups == 1) asm volatile("bar.sync 1, %0;" ::"n"(kGroupThreads) : "memory");
-    else asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kGroupThreads) : "memory");
+    if constexpr (kConsGroups == 1) asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+    else asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(THREADS) : "memory");
 }
 
 // The two groupings of the four frontier entries of a couple pair (see the header).  hs(x, y) = RN(x/2 + y/2)
@@ -135,9 +137,9 @@ __device__ __forceinline__ void couple_pair(double ax, double ay, double cx, dou
 inline size_t layer_ring_bytes(int ft, int stages, size_t es) { return (size_t)stages * 2 * ft * (kPTile * es + 16); }
 // consumer: staged parent-row segments of a couple tile (2 x kMaxTileFam rows x sw pairs), Va | Vb, a ring of
 // three tiles' metadata, the strip's member rows (row descriptors)
-inline size_t layer_consumer_bytes(int sw, size_t es) {
+inline size_t layer_consumer_bytes(int sw, size_t es, int prod_warps) {
     const size_t b = (size_t)2 * kMaxTileFam * sw * 2 * es + (size_t)2 * sw * kVPitch * es + (size_t)3 * 4 * kMTile * 4 +
-                     (size_t)kRowCache * 16;
+                     (size_t)group_warps(prod_warps) * 32 * 16;
     return (b + 127) / 128 * 128;
 }
 
@@ -153,10 +155,15 @@ inline size_t layer_consumer_bytes(int sw, size_t es) {
 #define PROF_FLUSH(role, who) do { } while (0)
 #endif
 
-template <typename T, bool STORED>
+template <typename T, bool STORED, int PW>
 __global__ void __launch_bounds__(kLayerThreads, 1)
 layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs S) {
     using P2 = typename PairOf<T>::type;
+    constexpr int kProdWarps = PW, kGroupWarps = group_warps(PW), kConsWarps = kConsGroups * kGroupWarps;
+    constexpr int kGroupThreads = kGroupWarps * 32;
+    constexpr int kRowCache = kGroupThreads;         // strip member rows a consumer group keeps in shared memory at a time
+    constexpr int kProdCols = kPTile / kProdWarps;   // columns of a tile that one producer warp transposes
+    static_assert(kConsWarps + kProdWarps == kLayerWarps && kProdCols % 4 == 0 && kProdCols <= 32 && 2 * kMaxTileFam / kGroupWarps <= 32, "role split");
     extern __shared__ __align__(128) unsigned char dyn_smem[];    // consumer: staged segments | Va | Vb | metadata; then the producer ring
     __shared__ __align__(8) unsigned long long s_full[kMaxStages];   // producer ring: "stage filled" (bulk copies landed)
     __shared__ __align__(8) unsigned long long s_empty[kMaxStages];  // producer ring: "stage read by every producer warp"
@@ -295,7 +302,7 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
         };
         // where the rows of the warp's kProdCols columns of a tile live (lane = column): read with the tile's flags
         auto tile_rows = [&](int tinfo) -> T * {
-            if (tinfo & kTileCarried) {
+            if ((tinfo & kTileCarried) && lane < kProdCols) {
                 const size_t at = (size_t)(tinfo & (kTileCarried - 1)) * kPTile + pw * kProdCols + lane;
                 return static_cast<T *>(PT.A[__ldg(L.live_owner + at)]) + (int64_t)__ldg(L.live_lrow + at) * ld;
             }
@@ -547,7 +554,7 @@ layer_kernel(T *__restrict__ A, int64_t ld, PeerTable PT, LayerArgs L, StripArgs
     const int G = S.gangs, kk = blockIdx.x * S.groups + grp, NC = S.n_cons / G, NI = S.n_citems;
     if (grp >= S.groups || kk >= S.n_cons) return;
     const int gang = kk % G, k = kk / G;                           // this group is consumer k of NC in its gang
-    auto cons_sync = [&]() { group_sync(grp); };
+    auto cons_sync = [&]() { group_sync<kGroupThreads>(grp); };
     PROF_DECL
     // Thread 0 spins, the group follows (see the producer's wait_for for the time-out).
     auto wait_for = [&](const int *counter, int target) {
