@@ -106,6 +106,27 @@ def test_named_configs_scaled(gen, ob, name, scale):
     assert stats["n_unique"] == len(s.probands)
 
 
+@pytest.mark.parametrize("knobs", [{"GENLIB_PROD_WARPS": "4"}, {"GENLIB_PROD_WARPS": "8"}, {"GENLIB_GANGS": "1"},
+                                   {"GENLIB_GANGS": "8", "GENLIB_MAX_SW": "16"}, {"GENLIB_DISCARD": "0"},
+                                   {"GENLIB_MAX_NBUF": "2", "GENLIB_CTAS_PER_ROLE": "37"}])
+def test_launch_shapes_do_not_change_the_bits(gen, ob, monkeypatch, knobs):
+    """Every launch shape of the layer kernel the engine can choose (producer / consumer warp split, gangs,
+    strip width, buffers, L2 discard) gives the oracle's bits, with and without carried individuals."""
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    for name, scale in (("C3", 0.03), ("C5", 0.03)):
+        s = gen.synth.config(name, scale)
+        ped = gen.genealogy(s.as_columns())
+        o = ob.OraclePedigree.from_arrays(s.ind, s.father, s.mother, s.sex)
+        assert_bit_equal(gen.phi(ped, s.probands), o.phi(s.probands))
+    rng = np.random.default_rng(41)
+    ped_cols = random_pedigree(rng, 1500, 20, p_single=0.1, p_none=0.02, window=200)
+    ped = gen.genealogy(ped_cols)
+    pro = rng.permutation(ped.ids)[:200]
+    assert_bit_equal(gen.phi(ped, pro), ob.OraclePedigree.from_arrays(ped_cols["ind"], ped_cols["father"], ped_cols["mother"],
+                                                                     ped_cols["sex"]).phi(pro))
+
+
 def test_deep_pedigree_rounding_schedule(gen, ob):
     """Float32 stores are lossy and Float64 sums inexact here: only the
     reference's rounding points and rank grouping reproduce the matrix."""
