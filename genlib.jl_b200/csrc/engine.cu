@@ -67,6 +67,7 @@ struct Arena {
     void *base = nullptr;
     size_t size = 0;
     int device = -1;
+    bool exported = false;      // a CUDA-IPC handle of it was handed out: peer processes may keep it mapped
 };
 
 class ArenaCache {
@@ -81,14 +82,16 @@ public:
                 if (free_[i].device == device && free_[i].size >= bytes && (best < 0 || free_[i].size < free_[best].size)) best = i;
             if (best >= 0) { out = free_[best]; free_.erase(free_.begin() + best); return cudaSuccess; }
         }
-        // Nothing cached fits.  Cached arenas may still be mapped by peer processes (CUDA IPC), and
-        // freeing exported memory under an open mapping is undefined, so they are only given back
-        // when the device is out of memory.
-        out = Arena{nullptr, bytes, device};
+        // Nothing cached fits.  The smaller cached arenas of this device are given back first (a long-lived
+        // process would otherwise pin one arena per size it ever needed) -- except those a peer process may
+        // still have mapped (CUDA IPC: freeing exported memory under an open mapping is undefined); these go
+        // only when the device is out of memory.
+        release_device(device, /*also_exported=*/false);
+        out = Arena{nullptr, bytes, device, false};
         cudaError_t ce = cudaMalloc(&out.base, bytes);
         if (ce == cudaErrorMemoryAllocation) {
             cudaGetLastError();
-            release_device(device);
+            release_device(device, true);
             ce = cudaMalloc(&out.base, bytes);
         }
         return ce;
@@ -98,10 +101,10 @@ public:
         std::lock_guard<std::mutex> g(mu_);
         free_.push_back(a);
     }
-    void release_device(int device) {
+    void release_device(int device, bool also_exported = true) {
         std::lock_guard<std::mutex> g(mu_);
         for (size_t i = 0; i < free_.size();) {
-            if (device < 0 || free_[i].device == device) {
+            if ((device < 0 || free_[i].device == device) && (also_exported || !free_[i].exported)) {
                 int prev = -1; cudaGetDevice(&prev);
                 cudaSetDevice(free_[i].device); cudaFree(free_[i].base);
                 if (prev >= 0) cudaSetDevice(prev);
@@ -1128,6 +1131,7 @@ int genlib_engine_ipc_export(genlib_engine *eng, void *handle64) {
     if (int rc = guard.enter(eng->device)) return rc;
     cudaIpcMemHandle_t h;
     CU(cudaIpcGetMemHandle(&h, eng->arena.base));
+    eng->arena.exported = true;
     std::memcpy(handle64, &h, sizeof h);
     return GENLIB_OK;
 }
