@@ -283,25 +283,40 @@ def phi(pedigree: Pedigree, probandIDs=None, *, verbose: bool = False, compute: 
 def run_distributed(plan: Plan, numerics="reference", device: int = 0, rank: int = 0) -> Engine:
     """This rank's engine of a `torch.distributed` job, attached to its peers and run once.  Collective.
     With a streamed plan (Plan(..., stream=True)) the layers run while the later ones are planned; if a size
-    bound of that plan does not hold, every rank finds out (same plan, same bounds) and all start over."""
+    bound of that plan does not hold, every rank finds out (same plan, same bounds) and all start over.
+    The ranks agree on the outcome before anybody goes on to fetch or gather: a failure of one rank (an
+    inter-GPU barrier that timed out also marks every peer) raises on all of them instead of leaving the
+    others waiting in the next collective."""
     import torch.distributed as dist
     for attempt in (0, 1):
         eng = Engine(plan, numerics=numerics, device=device, rank=rank)
+        outcome, error = "ok", None
         try:
             handles = [None] * plan.world
             dist.all_gather_object(handles, eng.ipc_handle())
             eng.attach(handles)
             dist.barrier()
-            eng.run()
-            return eng
-        except PlanBoundsExceeded:
-            dist.barrier()                  # nobody unmaps while a peer may still read
-            eng.close()
-            if attempt:
-                raise
+            try:
+                eng.run()
+            except PlanBoundsExceeded:
+                outcome = "restart"
+            except Exception as e:                                  # noqa: BLE001 -- reported to every rank below
+                outcome, error = "failed", e
+            outcomes = [None] * plan.world
+            dist.all_gather_object(outcomes, outcome)              # (also: nobody unmaps while a peer may still read)
         except BaseException:
             eng.close()
             raise
+        if all(o == "ok" for o in outcomes):
+            return eng
+        eng.close()
+        if "failed" in outcomes:
+            if error is not None:
+                raise error
+            raise RuntimeError(f"gen.phi: rank(s) {[g for g, o in enumerate(outcomes) if o == 'failed']} failed")
+        if attempt:
+            raise PlanBoundsExceeded(7, "the plan's bounds did not hold on the finished plan")
+    raise AssertionError("unreachable")
 
 
 def phi_distributed(pedigree: Pedigree, probandIDs=None, *, numerics="reference", dtype=np.float32,

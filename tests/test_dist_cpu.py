@@ -84,13 +84,15 @@ def test_shard_invariants(gen):
         assert len(owner) == plan.n_unique and (owner >= 0).all() and (owner < world).all()
 
 
-def test_world2_gloo(tmp_path):
-    """Two processes, gloo backend: each simulates its own rank and exchanges peer memory."""
+@pytest.mark.parametrize("worker", ["gloo_worker.py", "gloo_protocol_worker.py"])
+def test_world2_gloo(tmp_path, worker):
+    """Two processes, gloo backend.  gloo_worker: each simulates its own rank and exchanges peer memory;
+    gloo_protocol_worker: gen.run_distributed with a stub engine (all fine / all start over / one rank fails)."""
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     out = tmp_path / "result.txt"
-    procs = [subprocess.Popen([sys.executable, os.path.join(HERE, "gloo_worker.py"), str(r), "2", str(port), str(out)],
+    procs = [subprocess.Popen([sys.executable, os.path.join(HERE, worker), str(r), "2", str(port), str(out)],
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
     logs = []
     for p in procs:
