@@ -83,9 +83,13 @@ typedef struct genlib_stats {
     int64_t capacity;      /* W: slots (rows/columns) of the frontier matrix             */
     int64_t device_bytes;  /* device memory the engine allocated on this rank            */
     double alg_bytes;      /* sum over layers of s*(4nL+3n^2)                             */
-    double ms_plan;        /* host planning                                              */
-    double ms_upload;      /* plan H2D                                                   */
-    double ms_kernels;     /* all layers, CUDA events on the engine's stream             */
+    double ms_plan;        /* host planning (on a worker thread, beside the device, when */
+                           /* the plan is streamed: genlib_phi, genlib_plan_create_async) */
+    double ms_upload;      /* engine set-up + plan H2D (a streamed plan is uploaded      */
+                           /* layer by layer inside ms_kernels instead)                  */
+    double ms_kernels;     /* all layers, CUDA events on the engine's stream; with a     */
+                           /* streamed plan: first launch to last, waits for the planner */
+                           /* included                                                   */
     double ms_fetch;       /* proband gather + D2H                                       */
     int64_t h2d_bytes;
     int64_t d2h_bytes;
