@@ -336,6 +336,7 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
     std::vector<int32_t> &by_layer = W.by_layer; by_layer.resize(lstart[S]);
     std::vector<int64_t> &d_cut = W.d_cut, &d_both = W.d_both;
     d_cut.assign((size_t)S + 2, 0); d_both.assign((size_t)S + 2, 0);
+    std::vector<int64_t> d_occ((size_t)S + 2, 0);                 // individuals in the frontier per step (streamed plans: bounds)
     std::vector<Home> &home = W.home; home.resize((size_t)n);     // entries outside the plan are never read
     {
         std::vector<size_t> &pos = W.pos; pos.assign(lstart.begin(), lstart.end() - 1);
@@ -349,6 +350,7 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
             Home &hx = home[x];
             hx.slot = -1; hx.lrow = -1; hx.owner = 0;
             hx.last = is_pro[x] ? INT_MAX : S - 1 - px.minch;     // probands stay to the end
+            d_occ[lx]++; d_occ[(size_t)std::min<int64_t>(std::max(hx.last, lx), S - 1) + 1]--;   // born in or before, read in or after
             d_cut[lx]++; d_cut[ref_last + 1]--;                    // in cut[k] for layer <= k <= ref_last
             if (ref_last > lx) { d_both[lx]++; d_both[ref_last]--; }   // in cut[k] and cut[k+1]
         }
@@ -375,12 +377,7 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
     int64_t bound_slots = 0, bound_rows = 0;
     bool streaming = ps != nullptr;
     if (streaming) {
-        // most individuals in the frontier during one step: born in or before it, read in or after it
-        std::vector<int64_t> d_occ((size_t)S + 2, 0);
-        for (size_t k = 0; k < lstart[S]; k++) {
-            const int32_t x = by_layer[k], lx = S - 1 - pre[x].h;
-            d_occ[lx]++; d_occ[(size_t)std::min<int64_t>(std::max(home[x].last, lx), S - 1) + 1]--;
-        }
+        // most individuals in the frontier during one step (counted in the bucket pass above)
         int64_t occ = 0, occ_max = 0;
         for (int32_t k = 0; k < S; k++) { occ += d_occ[k]; occ_max = std::max(occ_max, occ); }
         // slack: lines of kSlotLine slots shared by individuals that leave in different layers (the member order
