@@ -81,8 +81,8 @@ struct Alloc {
 
 // Column slots are handed out in whole LINES of kSlotLine consecutive slots (128 bytes of a float
 // row): the members of a layer fill free lines in ascending order, so every group of four members
-// sits in four consecutive, 16-byte aligned columns (the 128-bit stores of expand_kernel) and the
-// scattered 4-byte column writes of mirror_kernel fill whole 32-byte sectors.  A line returns to the
+// sits in four consecutive, 16-byte aligned columns (the 128-bit row stores of the layer kernel's consumers) and
+// the 4-byte column writes into the carried rows (its producers' mirror pass) fill whole 32-byte sectors.  A line returns to the
 // free list only when every individual in it has been evicted (lowest free line first).
 struct LineAlloc {
     std::vector<int32_t> freelist, merged;     // free lines, ascending

@@ -305,3 +305,15 @@ def test_streamed_plan_with_a_bound_that_does_not_hold(gen, world):
     n_layers = gen.Plan(ped.father, ped.mother, ranks, world=world).n_layers
     done, overflow = _stream_selftest(gen, ped, ranks, world, -40.0)
     assert overflow and 0 < done < n_layers
+
+
+@pytest.mark.parametrize("name,worlds", [("C3", (1, 2, 8)), ("C5", (1, 2)), ("C4", (8,))])
+def test_streamed_plan_bounds_hold_at_benchmark_sizes(gen, name, worlds):
+    """The frontier / row bounds a streamed plan hands its engine must hold on the workloads that are
+    benchmarked (an overflow is handled, but costs the overlap of planning and device)."""
+    s = gen.synth.config(name)
+    ped = gen.genealogy(s.as_columns())
+    ranks = ped.rank_of(s.probands)
+    for world in worlds:
+        done, overflow = _stream_selftest(gen, ped, ranks, world, 6.25)
+        assert not overflow and done > 0
