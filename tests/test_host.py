@@ -317,3 +317,28 @@ def test_streamed_plan_bounds_hold_at_benchmark_sizes(gen, name, worlds):
     for world in worlds:
         done, overflow = _stream_selftest(gen, ped, ranks, world, 6.25)
         assert not overflow and done > 0
+
+
+@pytest.mark.parametrize("world", [1, 3])
+def test_async_plan_is_the_same_plan(gen, world):
+    """Plan(..., stream=True) = genlib_plan_create_async: made on a worker thread; queries wait for it.  Without
+    an engine reading it, it ends as the plan made in one piece (layers, arrays; the frontier width is the bound
+    its engine would have been sized with)."""
+    ped = gen.genealogy(gen.genea140)
+    ranks = ped.rank_of(gen.pro(ped))
+    a = gen.Plan(ped.father, ped.mother, ranks, world=world, stream=True)
+    assert a.n_unique == 140                                   # known before the layers are
+    b = gen.Plan(ped.father, ped.mother, ranks, world=world)
+    assert a.n_layers == b.n_layers and a.row_updates == b.row_updates and a.capacity >= b.capacity
+    for t in range(b.n_layers):
+        x, y = a.layer_arrays(t), b.layer_arrays(t)
+        assert x.keys() == y.keys()
+        for k in x:
+            if k == "live_flags":                              # (as wide as the frontier: the bound vs the exact width)
+                assert np.array_equal(x[k][: len(y[k])], y[k]) and not x[k][len(y[k]):].any()
+            else:
+                assert np.array_equal(x[k], y[k]), (t, k)
+        assert a.layer_info(t) == b.layer_info(t)
+    with pytest.raises(KeyError):                              # validation errors surface at creation, as usual
+        gen.Plan(ped.father, ped.mother, np.array([len(ped.father) + 5], np.int32), stream=True)
+    del a, b
