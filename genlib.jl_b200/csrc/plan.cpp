@@ -757,6 +757,31 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
                 if (d[0] < 0 || d[1] < 1 || d[1] > kMaxTileFam || d[0] + d[1] > L.n_fam || d[2] < 0 || d[3] < 1 || d[3] > kMTile || d[2] + d[3] > L.n_new || (d[2] & 7))
                     { err = "verify: tile descriptor in layer " + std::to_string(t) + " tile " + std::to_string(j) + ": " + std::to_string(d[0]) + " " + std::to_string(d[1]) + " " + std::to_string(d[2]) + " " + std::to_string(d[3]); return GENLIB_EINVAL; }
             }
+            // kSoleReader: the consumer item that stages such a strip-buffer row drops it from L2 afterwards, so it
+            // must be the ONLY item that stages it -- count the (member tile, couple, parent) triples per row
+            {
+                std::vector<int32_t> staged((size_t)std::max<int64_t>(qrows, 1), 0);
+                std::vector<uint8_t> marked((size_t)std::max<int64_t>(qrows, 1), 0);
+                for (int32_t j = 0; j < L.n_mtiles; j++) {
+                    const int32_t *d = &P.mtile_desc[4 * (L.mtile_off + (size_t)j)];
+                    for (int32_t f = d[0]; f < d[0] + d[1]; f++)
+                        for (int s2 = 0; s2 < 2; s2++) {
+                            const int32_t q0 = P.fam_q[2 * (L.fam_off + (size_t)f) + s2];
+                            if (q0 < 0) continue;
+                            staged[(size_t)(q0 & ~kSoleReader)]++;
+                            if (q0 & kSoleReader) marked[(size_t)(q0 & ~kSoleReader)] = 1;
+                        }
+                }
+                for (int64_t q = 0; q < qrows; q++)
+                    if (marked[(size_t)q] && staged[(size_t)q] != 1) { err = "verify: strip-buffer row " + std::to_string(q) + " of layer " + std::to_string(t) + " is marked sole-reader but staged " + std::to_string(staged[(size_t)q]) + " times"; return GENLIB_EINVAL; }
+                // every couple with members must be covered by the tiles (its rows are computed by somebody)
+                for (int32_t j = 0, next = 0; j < L.n_mtiles; j++) {
+                    const int32_t *d = &P.mtile_desc[4 * (L.mtile_off + (size_t)j)];
+                    if (d[2] != next) { err = "verify: member tiles of layer " + std::to_string(t) + " do not tile the members"; return GENLIB_EINVAL; }
+                    next = d[2] + d[3];
+                    if (j == L.n_mtiles - 1 && next != L.n_new) { err = "verify: member tiles of layer " + std::to_string(t) + " end early"; return GENLIB_EINVAL; }
+                }
+            }
         }
     }
     const size_t np = P.pro_ind.size();

@@ -342,3 +342,30 @@ def test_async_plan_is_the_same_plan(gen, world):
     with pytest.raises(KeyError):                              # validation errors surface at creation, as usual
         gen.Plan(ped.father, ped.mother, np.array([len(ped.father) + 5], np.int32), stream=True)
     del a, b
+
+
+def test_planner_self_check_on_many_pedigrees(gen, monkeypatch):
+    """GENLIB_PLAN_VERIFY: the index ranges the layer kernel relies on, and the sole-reader marks (a consumer
+    drops such a strip-buffer row from L2 after staging it: nobody else may stage it), on real, synthetic and
+    random pedigrees, one and several ranks, both schedules."""
+    monkeypatch.setenv("GENLIB_PLAN_VERIFY", "1")
+    peds = [gen.genealogy(gen.geneaJi), gen.genealogy(gen.genea140)]
+    for name, scale in (("C3", 0.05), ("C4", 0.01), ("C5", 0.05)):
+        s = gen.synth.config(name, scale)
+        peds.append(gen.genealogy(s.as_columns()))
+    rng = np.random.default_rng(9)
+    for k in range(12):
+        peds.append(gen.genealogy(random_pedigree(rng, int(rng.integers(50, 4000)), int(rng.integers(2, 60)),
+                                                  p_single=0.15, p_none=0.03, window=int(rng.choice([0, 30, 300])))))
+    # polygamy and big sibships: parents with several couples, couples split at 32 members and across tiles
+    n = 3000
+    ind = np.arange(1, n + 1)
+    father = np.where(ind > 40, 1 + (ind % 7), 0)
+    mother = np.where(ind > 40, 8 + (ind % 11), 0)
+    peds.append(gen.genealogy({"ind": ind, "father": father, "mother": mother, "sex": np.where(ind <= 7, 1, 2)}))
+    for ped in peds:
+        ranks = ped.rank_of(gen.pro(ped))
+        for world in (1, 3):
+            for schedule in ("phi", "sparse_phi"):
+                plan = gen.Plan(ped.father, ped.mother, ranks, world=world, schedule=schedule, ids=ped.ids)
+                assert plan.n_layers > 0
