@@ -90,6 +90,7 @@ SYMBOLS = {
     "genlib_plan_proband_rows": (C.c_int, [_P, _P, _P]),
     "genlib_plan_layer_flags": (C.c_int, [_P, C.c_int32, _P]),
     "genlib_plan_proband_slots": (C.c_int, [_P, _P]),
+    "genlib_plan_digest": (C.c_uint64, [_P, C.c_int]),
     "genlib_phi": (C.c_int, [C.c_int32, _P, _P, C.c_int32, _P, _P, C.c_int, C.c_int, C.c_int,
                              C.POINTER(Stats)]),
     "genlib_phi_multi": (C.c_int, [C.c_int32, _P, _P, C.c_int32, _P, _P, C.c_int, C.c_int, C.c_int32, _P,

@@ -126,11 +126,11 @@ struct Scratch {
     std::vector<Home> home;
     std::vector<size_t> lstart, pos;
     std::vector<int64_t> d_cut, d_both;
-    std::vector<int32_t> live, next_live;
+    std::vector<int32_t> live, next_live, last_of;
     std::vector<int32_t> fam_of, fam_count, fam_first, fam_key, fam_n;   // couples of every layer (grouped ahead by helper threads)
-    std::vector<int32_t> order, newid, load, freed, cnt, ipos;
+    std::vector<int32_t> order, newid, load, freed, evicted, cnt, ipos;
     std::vector<FamilyTable> tables;          // one per planning thread
-    std::vector<int8_t> fam_own;
+    std::vector<int8_t> fam_own, owner_of;
     std::vector<std::vector<int32_t>> freed_rows;
     LineAlloc slots;
     std::vector<Alloc> rows;
@@ -201,30 +201,35 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         return GENLIB_EINVAL;
     }
     P.n = n; P.world = world;
-    for (int32_t i = 0; i < n; i++) {
-        int32_t f = father[i], m = mother[i];
-        if (f < -1 || f >= n || m < -1 || m >= n) {
-            err = "KeyError: parent index out of range at rank " + std::to_string(i);
-            return GENLIB_EKEY;
+    // The pedigree's own errors (checked inside the reverse sweep below, reported here): the first offending rank.
+    auto pedigree_error = [&]() -> int {
+        for (int32_t i = 0; i < n; i++) {
+            int32_t f = father[i], m = mother[i];
+            if (f < -1 || f >= n || m < -1 || m >= n) {
+                err = "KeyError: parent index out of range at rank " + std::to_string(i);
+                return GENLIB_EKEY;
+            }
+            if (f >= i || m >= i) {
+                err = "parent does not precede child at rank " + std::to_string(i);
+                return GENLIB_EORDER;
+            }
         }
-        if (f >= i || m >= i) {
-            err = "parent does not precede child at rank " + std::to_string(i);
-            return GENLIB_EORDER;
-        }
-    }
+        return GENLIB_OK;
+    };
     // probands: first occurrence wins (intersect/union keep first-argument order, compute.jl:247,251)
     std::vector<uint8_t> &is_pro = W.is_pro; is_pro.assign((size_t)n + 1, 0);
     for (int32_t t = 0; t < n_pro; t++) {
         int32_t x = proband[t];
         if (x < 0 || x >= n) {
+            if (int rc = pedigree_error()) return rc;             // (a broken pedigree is reported first)
             err = "KeyError: proband index " + std::to_string(x) + " not in pedigree";
             return GENLIB_EKEY;
         }
         if (!is_pro[x]) { is_pro[x] = 1; P.pro_ind.push_back(x); }
     }
     P.n_unique = (int32_t)P.pro_ind.size();
-    if (P.n_unique == 0) return GENLIB_OK;
-    PLAN_T("validate");
+    if (P.n_unique == 0) return pedigree_error();
+    PLAN_T("probands");
 
     // One reverse sweep (children have larger ranks, so an individual is final when it is visited):
     //   h     height above the probands = longest downward path to one (compute.jl:236-241 builds
@@ -235,28 +240,33 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
     std::vector<Pre> &pre = W.pre; pre.assign((size_t)n, Pre());
     for (int32_t x : P.pro_ind) { pre[x].h = 0; pre[x].rl = 0; }
     int32_t hmax = 0;
+    bool bad_pedigree = false;
     std::vector<int32_t> &hist = W.hist; hist.clear();
     constexpr int32_t kPf = 24;                  // software prefetch distance of the planner's random accesses
     for (int32_t x = n - 1; x >= 0; x--) {
         if (x >= kPf) {
             const int32_t y = x - kPf, fy = father[y], my = mother[y];
-            if (fy >= 0) __builtin_prefetch(&pre[fy], 1);
-            if (my >= 0) __builtin_prefetch(&pre[my], 1);
+            if ((uint32_t)fy < (uint32_t)n) __builtin_prefetch(&pre[fy], 1);      // (not validated yet)
+            if ((uint32_t)my < (uint32_t)n) __builtin_prefetch(&pre[my], 1);
         }
+        // parents are -1 or precede the child (create.jl:234-254 orders them so): one unsigned compare each
+        const int32_t fx = father[x], mx = mother[x];
+        if ((uint32_t)fx + 1u > (uint32_t)x || (uint32_t)mx + 1u > (uint32_t)x) { bad_pedigree = true; continue; }
         const Pre px = pre[x];
         if (px.h < 0) continue;
         if (px.h >= (int32_t)hist.size()) hist.resize((size_t)px.h + 64, 0);
         hist[px.h]++;
         hmax = std::max(hmax, px.h);
-        const int32_t par[2] = {father[x], mother[x]};
+        const int32_t par[2] = {fx, mx};
         for (int32_t p : par) {
             if (p < 0) continue;
-            Pre &pp = pre[p];
-            if (pp.h <= px.h) pp.h = px.h + 1;
-            if (pp.minch > px.h) pp.minch = px.h;
-            if (pp.rl > px.rl + 1) pp.rl = px.rl + 1;
+            Pre &pp = pre[p];                                      // (unconditional stores: the compares do not predict)
+            pp.h = std::max(pp.h, px.h + 1);
+            pp.minch = std::min(pp.minch, px.h);
+            pp.rl = std::min(pp.rl, px.rl + 1);
         }
     }
+    if (bad_pedigree) return pedigree_error();
     // Schedule of sparse_phi (compute.jl:335-439): individuals are processed in the order of a queue
     // that starts with the founders and receives a child when its last parent has been processed --
     // i.e. by depth below the founders, ties in queue order -- and of a pair, the one processed LATER
@@ -337,7 +347,8 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
     std::vector<int64_t> &d_cut = W.d_cut, &d_both = W.d_both;
     d_cut.assign((size_t)S + 2, 0); d_both.assign((size_t)S + 2, 0);
     std::vector<int64_t> d_occ((size_t)S + 2, 0);                 // individuals in the frontier per step (streamed plans: bounds)
-    std::vector<Home> &home = W.home; home.resize((size_t)n);     // entries outside the plan are never read
+    std::vector<Home> &home = W.home; home.resize((size_t)n);     // filled when a slot is assigned; entries outside the plan are never read
+    std::vector<int32_t> &last_of = W.last_of; last_of.resize((size_t)n);   // last layer that reads the row (a sequential write here)
     {
         std::vector<size_t> &pos = W.pos; pos.assign(lstart.begin(), lstart.end() - 1);
         const int32_t n_visit = by_seq ? (int32_t)seq_order.size() : n;
@@ -347,13 +358,13 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
             if (px.h < 0) continue;
             const int32_t lx = S - 1 - px.h, ref_last = S - 1 - px.rl;
             by_layer[pos[lx]++] = x;
-            Home &hx = home[x];
-            hx.slot = -1; hx.lrow = -1; hx.owner = 0;
-            hx.last = is_pro[x] ? INT_MAX : S - 1 - px.minch;     // probands stay to the end
-            d_occ[lx]++; d_occ[(size_t)std::min<int64_t>(std::max(hx.last, lx), S - 1) + 1]--;   // born in or before, read in or after
-            d_cut[lx]++; d_cut[ref_last + 1]--;                    // in cut[k] for layer <= k <= ref_last
+            const int32_t last = is_pro[x] ? INT_MAX : S - 1 - px.minch;     // probands stay to the end
+            last_of[x] = last;
+            d_occ[(size_t)std::min<int64_t>(std::max(last, lx), S - 1) + 1]--;   // born in or before, read in or after
+            d_cut[ref_last + 1]--;                                 // in cut[k] for layer <= k <= ref_last
             if (ref_last > lx) { d_both[lx]++; d_both[ref_last]--; }   // in cut[k] and cut[k+1]
         }
+        for (int32_t t = 0; t < S; t++) { d_occ[t] += count[t]; d_cut[t] += count[t]; }   // everybody enters with its layer
     }
     std::vector<int32_t> &cut_size = W.cut_size, &both_size = W.both_size;
     cut_size.assign((size_t)S, 0); both_size.assign((size_t)S, 0);
@@ -424,6 +435,9 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
     std::vector<int32_t> &newid = W.newid, &load = W.load, &freed = W.freed;
     load.assign((size_t)world, 0);
     std::vector<int8_t> &fam_own = W.fam_own;
+    // the owners once more, one byte per individual: the owner rule reads two parents per couple, and a generation of
+    // these stays in cache where the 16-byte homes do not
+    std::vector<int8_t> &owner_of = W.owner_of; if (world > 1) owner_of.resize((size_t)n);
     int32_t rr = 0;
 
     // ---- couples: same (father, mother) => same cross row (compute.jl:111-126 gives full siblings
@@ -450,7 +464,7 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
             if (q + kAhead < nn) table.prefetch(couple_key(X[q + kAhead]));
             bool found;
             FamilyTable::Bucket &bk = table.find(couple_key(X[q]), &found);
-            const int32_t key = std::min(home[X[q]].last - t, kKeys - 1);   // >= 1: somebody is born later, or proband
+            const int32_t key = std::min(last_of[X[q]] - t, kKeys - 1);   // >= 1: somebody is born later, or proband
             if (found && fam_count[bk.val] < kMaxFamily) {
                 fam_of[q] = bk.val;
                 fam_key[bk.val] = std::max(fam_key[bk.val], key);
@@ -467,11 +481,13 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         W.fam_n[t] = nfr;
     };
     int n_threads = 1;
-    if (M >= 200000) {
+    {
+        // the planning thread, one helper that runs the second lane of the layer pipeline below, one that groups
+        // couples ahead (with two threads the helper does both); small plans are not worth the threads.
+        // GENLIB_PLAN_THREADS overrides (also for small plans: the tests run those with helpers too)
         const char *env = std::getenv("GENLIB_PLAN_THREADS");
         const int hw = (int)std::thread::hardware_concurrency();
-        // measured on a 16-core B200 host: C3 40 -> 32 ms with one helper, nothing more with three
-        n_threads = env ? std::atoi(env) : std::min(2, hw / world);
+        n_threads = env ? std::atoi(env) : (M >= 200000 ? std::min(3, hw / world) : 1);
         n_threads = std::max(1, std::min(n_threads, 16));
     }
     if (W.tables.size() < (size_t)n_threads) W.tables.resize((size_t)n_threads);
@@ -483,37 +499,38 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         try { group_layer(t, W.tables[(size_t)id]); } catch (...) { group_failed.store(true); }
         grouped[(size_t)t].store(1, std::memory_order_release);
     };
-    struct Helpers {
-        std::vector<std::thread> th;
-        void join_all() { for (auto &t : th) if (t.joinable()) t.join(); th.clear(); }
-        ~Helpers() { join_all(); }
-    } helpers;
-    for (int id = 1; id < n_threads; id++) {
-        try {
-            helpers.th.emplace_back([&, id] {
-                for (;;) {
-                    const int32_t t = next_job.fetch_add(1);
-                    if (t >= S) break;
-                    run_job(t, id);
-                }
-            });
-        } catch (...) { break; }                 // no thread: the planning thread does the jobs itself
-    }
+    // a grouping job, if one is left; false when there was none
+    auto group_one = [&](int id) {
+        const int32_t j = next_job.load(std::memory_order_relaxed) < S ? next_job.fetch_add(1) : S;
+        if (j >= S) return false;
+        run_job(j, id);
+        return true;
+    };
 
+    // ---- the layers, as a pipeline of two lanes.  What is sequential in planning is the slot assignment: the
+    //      members of layer t take the lines that the evictions of layer t-1 gave back.  The rest hangs off it:
+    //        lane A (the planning thread)  couple owners and order (t), column slots and rows (t), member tiles (t),
+    //                                      end of the layer (evicted lines and rows return, live list)
+    //        lane B (a helper thread)      live range, flags and live tiles BEFORE step t, parents of the couples (t)
+    //      Lane B of layer t reads the homes of individuals born before t and the live list that lane A closed at the
+    //      end of t-1; lane A of layer t writes the homes of the members of t.  They meet three times per layer
+    //      (go -> B, ordered -> B, coupled -> A); each array of the plan is written by one lane only.  Without a
+    //      helper thread lane A runs lane B's pieces itself, in the same order. ----
     double lt_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     auto lt_last = std::chrono::steady_clock::now();
 #define LT(k) do { if (timing) { auto n_ = std::chrono::steady_clock::now(); lt_acc[k] += std::chrono::duration<double, std::milli>(n_ - lt_last).count(); lt_last = n_; } } while (0)
-    for (int32_t t = 0; t < S; t++) {
+    double ltb_acc[2] = {0, 0};
+    std::vector<int32_t> &evicted = W.evicted;           // slots evicted by the current step, ascending (lane B -> end of layer)
+    int32_t cur_nf = 0, cur_nf_real = 0;                 // couples of the current layer with / without rank padding (A -> B)
+
+    auto begin_layer = [&](int32_t t) {
         Layer &L = P.layers[t];
-        LT(7);
-        const int32_t *X = by_layer.data() + lstart[t];
-        const int32_t nn = count[t];
-        L.n_new = nn;
+        L.n_new = count[t];
         L.live_before = (int32_t)live.size();
         L.ref_founders = t > 0 ? cut_size[t - 1] : 0;
         L.ref_probands = cut_size[t];
         L.ref_both = t > 0 ? both_size[t - 1] : 0;
-        // member arrays of a layer start 16-byte aligned (the expand kernel copies them in 16-byte chunks)
+        // member arrays of a layer start 16-byte aligned (the layer kernel copies them in 16-byte chunks)
         while (P.mem_ind.size() % 4) {
             P.mem_ind.push_back(0); P.mem_slot.push_back(0); P.mem_fam.push_back(0); P.mem_lrow.push_back(0);
             if (by_seq) P.mem_rank.push_back(0);
@@ -525,61 +542,60 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         L.base_off = P.fam_base.size();
         L.tile_off = P.tile_map.size();
         L.ltile_off = P.live_tiles.size();
+    };
 
-        // ---- live range and flags (state BEFORE the step) ----
-        freed.clear();
+    // lane B, first piece: live range and flags (state BEFORE the step)
+    auto live_flags = [&](int32_t t) {
+        Layer &L = P.layers[t];
+        evicted.clear();
         next_live.clear();
-        if (!live.empty()) {
-            int32_t lo = INT_MAX, hi = -1;
-            for (size_t li = 0; li < live.size(); li++) {
-                if (li + kPf < live.size()) __builtin_prefetch(&home[live[li + kPf]]);
-                const int32_t sl = home[live[li]].slot;
-                lo = std::min(lo, sl); hi = std::max(hi, sl);
-            }
-            L.rt_lo = (lo / kPTile) * kPTile;
-            L.rt_rows = round_up(hi + 1, kPTile) - L.rt_lo;
-            P.flags.resize(L.flag_off + (size_t)L.rt_rows, 0);
-            P.live_owner.resize(L.flag_off + (size_t)L.rt_rows, 0);
-            P.live_lrow.resize(L.flag_off + (size_t)L.rt_rows, 0);
-            uint8_t *fl = P.flags.data() + L.flag_off;
-            for (size_t li = 0; li < live.size(); li++) {
-                if (li + kPf < live.size()) __builtin_prefetch(&home[live[li + kPf]]);
-                const int32_t x = live[li];
-                const Home hx = home[x];
-                const bool stays = hx.last > t;      // read for the last time in step `last`
-                const int32_t r = hx.slot - L.rt_lo;
-                fl[r] = (uint8_t)(kFlagLive | (stays ? kFlagCarried : 0));
-                P.live_owner[L.flag_off + r] = hx.owner;
-                P.live_lrow[L.flag_off + r] = hx.lrow;
-                if (stays) { next_live.push_back(x); L.carried++; }
-                else if (world > 1) freed_rows[hx.owner].push_back(hx.lrow);
-            }
-            for (int32_t r = 0; r < L.rt_rows; r++)        // evicted slots in ascending order -> freed lines, ascending
-                if (fl[r] == kFlagLive) slots.release(L.rt_lo + r, freed);
-            // the strip buffers of the layer kernel hold the live tiles only (holes of a fragmented range cost nothing)
-            P.tile_map.resize(L.tile_off + (size_t)(L.rt_rows / kPTile), -1);
-            for (int32_t tl = 0; tl < L.rt_rows / kPTile; tl++) {
-                uint8_t any = 0;
-                for (int32_t r = tl * kPTile; r < (tl + 1) * kPTile; r++) any |= fl[r];
-                if (any) {
-                    P.tile_map[L.tile_off + (size_t)tl] = L.n_live_tiles++;
-                    P.live_tiles.push_back(tl | ((any & kFlagCarried) ? kTileCarried : 0));
-                }
+        if (live.empty()) return;
+        int32_t lo = INT_MAX, hi = -1;
+        for (size_t li = 0; li < live.size(); li++) {
+            if (li + kPf < live.size()) __builtin_prefetch(&home[live[li + kPf]]);
+            const int32_t sl = home[live[li]].slot;
+            lo = std::min(lo, sl); hi = std::max(hi, sl);
+        }
+        L.rt_lo = (lo / kPTile) * kPTile;
+        L.rt_rows = round_up(hi + 1, kPTile) - L.rt_lo;
+        P.flags.resize(L.flag_off + (size_t)L.rt_rows, 0);
+        P.live_owner.resize(L.flag_off + (size_t)L.rt_rows, 0);
+        P.live_lrow.resize(L.flag_off + (size_t)L.rt_rows, 0);
+        uint8_t *fl = P.flags.data() + L.flag_off;
+        for (size_t li = 0; li < live.size(); li++) {
+            if (li + kPf < live.size()) __builtin_prefetch(&home[live[li + kPf]]);
+            const int32_t x = live[li];
+            const Home hx = home[x];
+            const bool stays = hx.last > t;      // read for the last time in step `last`
+            const int32_t r = hx.slot - L.rt_lo;
+            fl[r] = (uint8_t)(kFlagLive | (stays ? kFlagCarried : 0));
+            P.live_owner[L.flag_off + r] = hx.owner;
+            P.live_lrow[L.flag_off + r] = hx.lrow;
+            if (stays) { next_live.push_back(x); L.carried++; }
+            else if (world > 1) freed_rows[hx.owner].push_back(hx.lrow);
+        }
+        for (int32_t r = 0; r < L.rt_rows; r++)        // evicted slots in ascending order -> freed lines, ascending
+            if (fl[r] == kFlagLive) evicted.push_back(L.rt_lo + r);
+        // the strip buffers of the layer kernel hold the live tiles only (holes of a fragmented range cost nothing)
+        P.tile_map.resize(L.tile_off + (size_t)(L.rt_rows / kPTile), -1);
+        for (int32_t tl = 0; tl < L.rt_rows / kPTile; tl++) {
+            uint8_t any = 0;
+            for (int32_t r = tl * kPTile; r < (tl + 1) * kPTile; r++) any |= fl[r];
+            if (any) {
+                P.tile_map[L.tile_off + (size_t)tl] = L.n_live_tiles++;
+                P.live_tiles.push_back(tl | ((any & kFlagCarried) ? kTileCarried : 0));
             }
         }
+    };
 
-        LT(0);
-        // ---- couples of the layer (grouped by group_layer, possibly on a helper thread) ----
-        while (!grouped[t].load(std::memory_order_acquire)) {
-            const int32_t j = next_job.load() < S ? next_job.fetch_add(1) : S;
-            if (j < S) run_job(j, 0); else std::this_thread::yield();
-        }
-        if (group_failed.load()) { helpers.join_all(); throw std::bad_alloc(); }
+    // lane A: row owners, couple order, member order
+    auto owners_order = [&](int32_t t) {
+        Layer &L = P.layers[t];
+        const int32_t *X = by_layer.data() + lstart[t];
+        const int32_t nn = count[t];
         const int32_t *fam_of = W.fam_of.data() + lstart[t], *fam_count = W.fam_count.data() + lstart[t];
         const int32_t *fam_first = W.fam_first.data() + lstart[t], *fam_key = W.fam_key.data() + lstart[t];
         const int32_t nf_real = W.fam_n[t];
-
-        LT(1);
         // ---- row owners: a couple's children live with one of their parents' rows (the other
         //      parent row is read through NVLink); spill to the least loaded rank past +12.5 %.
         //      Couples are renumbered rank-major; every rank's range starts at a multiple of 4
@@ -594,14 +610,19 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
             std::fill(load.begin(), load.end(), 0);
             const int32_t cap = (nn + world - 1) / world + (nn + world - 1) / world / 8 + kMaxFamily;
             for (int32_t f = 0; f < nf_real; f++) {
+                if (f + kPf < nf_real) {
+                    const int32_t y = X[fam_first[f + kPf]], fy = father[y], my = mother[y];
+                    if (fy >= 0) __builtin_prefetch(&owner_of[fy]);
+                    if (my >= 0) __builtin_prefetch(&owner_of[my]);
+                }
                 const int32_t x = X[fam_first[f]];
                 const int32_t fa = father[x], mo = mother[x];
                 int32_t g;
                 if (fa >= 0 && mo >= 0) {
-                    const int32_t of = home[fa].owner, om = home[mo].owner;
+                    const int32_t of = owner_of[fa], om = owner_of[mo];
                     g = load[om] < load[of] ? om : of;
-                } else if (fa >= 0) g = home[fa].owner;
-                else if (mo >= 0) g = home[mo].owner;
+                } else if (fa >= 0) g = owner_of[fa];
+                else if (mo >= 0) g = owner_of[mo];
                 else g = rr++ % world;
                 if (load[g] + fam_count[f] > cap) g = (int32_t)(std::min_element(load.begin(), load.end()) - load.begin());
                 fam_own[f] = (int8_t)g;
@@ -646,28 +667,41 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
             std::vector<int32_t> &pos = W.ipos; pos.assign(fstart, fstart + nf);
             for (int32_t q = 0; q < nn; q++) order[pos[newid[fam_of[q]]]++] = q;
         }
-        LT(2);
-        // ---- column slots (global, in lines) and local rows (per owner) ----
+        cur_nf = nf; cur_nf_real = nf_real;
+    };
+
+    // lane A: column slots (global, in lines) and local rows (per owner)
+    auto assign_slots = [&](int32_t t) {
+        Layer &L = P.layers[t];
+        const int32_t *X = by_layer.data() + lstart[t];
+        const int32_t nn = count[t];
+        const int32_t *fam_of = W.fam_of.data() + lstart[t];
         P.mem_ind.resize(L.mem_off + (size_t)nn); P.mem_slot.resize(L.mem_off + (size_t)nn);
         P.mem_fam.resize(L.mem_off + (size_t)nn); P.mem_lrow.resize(L.mem_off + (size_t)nn);
         if (by_seq) P.mem_rank.resize(L.mem_off + (size_t)nn);
-        {
-            int32_t *mi = P.mem_ind.data() + L.mem_off, *ms = P.mem_slot.data() + L.mem_off;
-            int32_t *mf = P.mem_fam.data() + L.mem_off, *ml = P.mem_lrow.data() + L.mem_off;
-            for (int32_t q = 0; q < nn; q++) {
-                if (q + kPf < nn) __builtin_prefetch(&home[X[order[q + kPf]]], 1);
-                if (q + 2 * kPf < nn) { __builtin_prefetch(&X[order[q + 2 * kPf]]); __builtin_prefetch(&fam_of[order[q + 2 * kPf]]); }
-                const int32_t oq = order[q], x = X[oq], f = fam_of[oq];
-                const int32_t g = fam_own[f];
-                const int32_t s = slots.take(), lr = world > 1 ? rows[g].take() : s;   // one rank: row == slot
-                if (streaming && (s >= bound_slots || lr >= bound_rows)) give_up_streaming();
-                Home &hx = home[x];
-                hx.slot = s; hx.lrow = lr; hx.owner = (int8_t)g;
-                mi[q] = by_seq ? orient[x] : x; ms[q] = s; mf[q] = newid[f]; ml[q] = lr;
-                if (by_seq) P.mem_rank[L.mem_off + (size_t)q] = x;
-            }
+        int32_t *mi = P.mem_ind.data() + L.mem_off, *ms = P.mem_slot.data() + L.mem_off;
+        int32_t *mf = P.mem_fam.data() + L.mem_off, *ml = P.mem_lrow.data() + L.mem_off;
+        for (int32_t q = 0; q < nn; q++) {
+            if (q + kPf < nn) { const int32_t y = X[order[q + kPf]]; __builtin_prefetch(&home[y], 1); __builtin_prefetch(&last_of[y]); }
+            if (q + 2 * kPf < nn) { __builtin_prefetch(&X[order[q + 2 * kPf]]); __builtin_prefetch(&fam_of[order[q + 2 * kPf]]); }
+            const int32_t oq = order[q], x = X[oq], f = fam_of[oq];
+            const int32_t g = fam_own[f];
+            const int32_t s = slots.take(), lr = world > 1 ? rows[g].take() : s;   // one rank: row == slot
+            if (streaming && (s >= bound_slots || lr >= bound_rows)) give_up_streaming();
+            Home &hx = home[x];
+            hx.slot = s; hx.lrow = lr; hx.owner = (int8_t)g; hx.last = last_of[x];
+            if (world > 1) owner_of[x] = (int8_t)g;
+            mi[q] = by_seq ? orient[x] : x; ms[q] = s; mf[q] = newid[f]; ml[q] = lr;
+            if (by_seq) P.mem_rank[L.mem_off + (size_t)q] = x;
         }
-        LT(3);
+    };
+
+    // lane B, second piece: the couples' parents -- slots, owners, local rows, rows of the strip buffers
+    auto couples = [&](int32_t t) {
+        Layer &L = P.layers[t];
+        const int32_t *X = by_layer.data() + lstart[t];
+        const int32_t *fam_first = W.fam_first.data() + lstart[t];
+        const int32_t nf = cur_nf, nf_real = cur_nf_real;
         P.fam_pf.resize(L.fam_off + (size_t)nf, -1); P.fam_pm.resize(L.fam_off + (size_t)nf, -1);
         P.fam_pf_owner.resize(L.fam_off + (size_t)nf, -1); P.fam_pm_owner.resize(L.fam_off + (size_t)nf, -1);
         P.fam_pf_lrow.resize(L.fam_off + (size_t)nf, -1); P.fam_pm_lrow.resize(L.fam_off + (size_t)nf, -1);
@@ -695,7 +729,12 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
                 *pq[s] = P.tile_map[L.tile_off + (size_t)(rel / kPTile)] * kPTile + rel % kPTile;
             }
         }
-        LT(4);
+    };
+
+    // lane A: member tiles, sole-reader marks, the layer is complete
+    auto finish_layer = [&](int32_t t) {
+        Layer &L = P.layers[t];
+        const int32_t nn = count[t], nf = cur_nf;
         // member tiles = the column blocks the layer kernel writes at a time: at most kMTile members and at
         // most kMaxTileFam couples (bounds the staged couple tile), cut at multiples of 8 members (whole
         // 32-byte sectors of a float row on both sides of the cut)
@@ -728,14 +767,99 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         L.mem_end = P.mem_ind.size(); L.fam_end = P.fam_pf.size(); L.flag_end = P.flags.size();
         L.tile_end = P.tile_map.size(); L.ltile_end = P.live_tiles.size(); L.mtile_end = P.mtile_desc.size() / 4;
         if (streaming) { ps->layers_done.store(t + 1, std::memory_order_release); ps->wake(); }
-        LT(5);
-        // ---- after the step: evicted slots / rows become reusable from the next layer on ----
+    };
+
+    // lane A: after the step, evicted slots / rows become reusable from the next layer on
+    auto end_layer = [&](int32_t t) {
+        const int32_t *X = by_layer.data() + lstart[t];
+        freed.clear();
+        for (int32_t s : evicted) slots.release(s, freed);
         slots.end_layer(freed);
         for (int32_t g = 0; g < world && world > 1; g++) rows[g].end_layer(freed_rows[g]);
-        for (int32_t q = 0; q < nn; q++) next_live.push_back(X[q]);
+        next_live.insert(next_live.end(), X, X + count[t]);
         live.swap(next_live);
+    };
+
+    // hand-over between the lanes: layer numbers + 1
+    std::atomic<int32_t> go{0}, ordered{0}, coupled{0};
+    std::atomic<bool> stop{false}, lane_failed{false};
+    struct Helpers {
+        std::vector<std::thread> th;
+        std::atomic<bool> *stop = nullptr;
+        void join_all() { if (stop) stop->store(true); for (auto &t : th) if (t.joinable()) t.join(); th.clear(); }
+        ~Helpers() { join_all(); }
+    } helpers;
+    helpers.stop = &stop;
+    bool piped = false;
+    for (int id = 1; id < n_threads; id++) {
+        try {
+            if (id == 1) {
+                helpers.th.emplace_back([&, id] {                 // lane B; groups couples ahead whenever it has to wait
+                    auto tb = std::chrono::steady_clock::now();
+                    auto lap = [&](int k) { if (timing) { auto n_ = std::chrono::steady_clock::now(); ltb_acc[k] += std::chrono::duration<double, std::milli>(n_ - tb).count(); } };
+                    try {
+                        for (int32_t t = 0; t < S; t++) {
+                            while (go.load(std::memory_order_acquire) <= t) {
+                                if (stop.load(std::memory_order_relaxed)) return;
+                                if (!group_one(id)) std::this_thread::yield();
+                            }
+                            if (timing) tb = std::chrono::steady_clock::now();
+                            live_flags(t);
+                            lap(0);
+                            while (ordered.load(std::memory_order_acquire) <= t) {
+                                if (stop.load(std::memory_order_relaxed)) return;
+                                if (!group_one(id)) std::this_thread::yield();
+                            }
+                            if (timing) tb = std::chrono::steady_clock::now();
+                            couples(t);
+                            lap(1);
+                            coupled.store(t + 1, std::memory_order_release);
+                        }
+                        while (group_one(id)) {}
+                    } catch (...) {
+                        lane_failed.store(true);
+                        coupled.store(INT32_MAX, std::memory_order_release);
+                    }
+                });
+                piped = true;
+            } else {
+                helpers.th.emplace_back([&, id] { while (!stop.load(std::memory_order_relaxed) && group_one(id)) {} });
+            }
+        } catch (...) { break; }                 // no thread: the planning thread does the jobs itself
     }
-    if (timing) std::fprintf(stderr, "[plan]   live/flags %.2f  wait-group %.2f  owners/order %.2f  slots %.2f  couples %.2f  tiles %.2f  end %.2f\n", lt_acc[0], lt_acc[1], lt_acc[2], lt_acc[3], lt_acc[4], lt_acc[5], lt_acc[7]);
+
+    for (int32_t t = 0; t < S; t++) {
+        LT(7);
+        begin_layer(t);
+        if (piped) go.store(t + 1, std::memory_order_release); else live_flags(t);
+        LT(0);
+        // ---- couples of the layer (grouped by group_layer, possibly on a helper thread) ----
+        while (!grouped[t].load(std::memory_order_acquire))
+            if (!group_one(0)) std::this_thread::yield();
+        if (group_failed.load()) { helpers.join_all(); throw std::bad_alloc(); }
+        LT(1);
+        owners_order(t);
+        if (piped) ordered.store(t + 1, std::memory_order_release);
+        LT(2);
+        assign_slots(t);
+        LT(3);
+        if (piped) {
+            while (coupled.load(std::memory_order_acquire) <= t)
+                if (!group_one(0)) std::this_thread::yield();
+            if (lane_failed.load() || group_failed.load()) { helpers.join_all(); throw std::bad_alloc(); }
+        } else couples(t);
+        LT(4);
+        finish_layer(t);
+        LT(5);
+        end_layer(t);
+    }
+    helpers.join_all();
+    if (group_failed.load() || lane_failed.load()) throw std::bad_alloc();
+    if (timing) {
+        std::fprintf(stderr, "[plan]   lane A: %s %.2f  wait-group %.2f  owners/order %.2f  slots %.2f  %s %.2f  tiles %.2f  end %.2f\n",
+                     piped ? "begin" : "live/flags", lt_acc[0], lt_acc[1], lt_acc[2], lt_acc[3], piped ? "wait-B" : "couples", lt_acc[4], lt_acc[5], lt_acc[7]);
+        if (piped) std::fprintf(stderr, "[plan]   lane B: live/flags %.2f  couples %.2f\n", ltb_acc[0], ltb_acc[1]);
+    }
     PLAN_T("layers");
     if (!streaming) {                  // (a streamed plan keeps the bounds its engine was sized with)
         P.capacity = round_up(std::max<int64_t>((int64_t)slots.next_fresh * kSlotLine, 1), kPTile);

@@ -207,6 +207,11 @@ int genlib_plan_proband_rows(const genlib_plan *plan, int32_t *owner, int32_t *l
 /* live_flags: capacity bytes; bit0 = live before the step, bit1 = still live after it. */
 int genlib_plan_layer_flags(const genlib_plan *plan, int32_t layer, uint8_t *live_flags);
 int genlib_plan_proband_slots(const genlib_plan *plan, int32_t *slots);
+/* A 64-bit digest (FNV-1a) of everything the plan holds: the layer table and every index array the engine uploads.
+ * Two plans with equal digests run the same schedule; the planner's helper threads (environment
+ * GENLIB_PLAN_THREADS) and the streamed hand-over must not change it.  with_bounds = 0 leaves out the frontier
+ * width and the rows per rank (a streamed plan keeps the upper bounds its engine was sized with).  CPU only. */
+uint64_t genlib_plan_digest(const genlib_plan *plan, int with_bounds);
 
 /* ---- one-shot: the `gen.phi(ped, probandIDs)` call -------------------------
  * out: n_unique^2 elements of out_dtype (row-major == column-major: symmetric),

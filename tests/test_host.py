@@ -296,6 +296,32 @@ def test_streamed_plan_equals_the_plan_made_in_one_piece(gen, world):
         assert not overflow and done == gen.Plan(ped.father, ped.mother, ranks, world=world).n_layers
 
 
+def test_planner_threads_do_not_change_the_plan(gen, monkeypatch):
+    """The planner runs the layers as a pipeline of two lanes (slot assignment on the planning thread; live flags and
+    the couples' parents on a helper that also groups couples ahead, csrc/plan.cpp): with 1, 2, 3 or 5 threads, made
+    in one piece or handed over layer by layer, on one rank or several, under either schedule, the plan is the same
+    to the last index (genlib_plan_digest).  GENLIB_PLAN_THREADS forces helpers on plans that small."""
+    cases = []
+    ped = gen.genealogy(gen.genea140)
+    cases.append((ped, ped.rank_of(gen.pro(ped))))
+    for seed, win in ((3, 60), (11, 400), (5, 0)):
+        ped = gen.genealogy(random_pedigree(np.random.default_rng(seed), 3000, 40, window=win))
+        cases.append((ped, ped.rank_of(ped.ids[-300:])))
+    s = gen.synth.generate(60000, 30, 800, alpha=0.05, demes=4, migration=0.05, overlap=3, seed=5)
+    ped = gen.genealogy(s.as_columns())
+    cases.append((ped, ped.rank_of(s.probands)))
+    for ped, ranks in cases:
+        for world, schedule in ((1, "phi"), (3, "phi"), (8, "phi"), (2, "sparse_phi")):
+            ids = ped.ids if schedule != "phi" else None
+            digests = set()
+            for threads in ("1", "2", "3", "5"):
+                monkeypatch.setenv("GENLIB_PLAN_THREADS", threads)
+                for stream in (False, True):
+                    plan = gen.Plan(ped.father, ped.mother, ranks, world=world, schedule=schedule, ids=ids, stream=stream)
+                    digests.add(int(gen.lib().genlib_plan_digest(plan._h, 0)))
+            assert len(digests) == 1 and 0 not in digests, (world, schedule, digests)
+
+
 @pytest.mark.parametrize("world", [1, 4])
 def test_streamed_plan_with_a_bound_that_does_not_hold(gen, world):
     """A frontier bound that is too small on purpose: the planner notices, waits for the consumer and finishes
