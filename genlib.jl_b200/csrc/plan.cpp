@@ -56,8 +56,15 @@ struct Pre {
 
 struct Home {
     int32_t slot = -1, lrow = -1;
-    int32_t last = -1;           // last layer that reads the row (INT_MAX for probands: kept to the end)
     int8_t owner = 0;
+};
+
+// The same for the individuals in the frontier, kept as a list in the order they entered it: the pass over the live
+// individuals of every layer (their flags, who leaves) then reads sequentially instead of one home per individual.
+struct LiveRec {
+    int32_t slot, lrow;
+    int32_t last;                // last layer that reads the row (INT_MAX for probands: kept to the end)
+    int32_t owner;
 };
 
 // Local rows of one rank: any free row will do (a row index only selects a row), so freed rows go on
@@ -126,12 +133,13 @@ struct Scratch {
     std::vector<Home> home;
     std::vector<size_t> lstart, pos;
     std::vector<int64_t> d_cut, d_both;
-    std::vector<int32_t> live, next_live, last_of;
+    std::vector<LiveRec> live, next_live;
+    std::vector<int32_t> last_of;
     std::vector<int32_t> fam_of, fam_count, fam_first, fam_key, fam_n;   // couples of every layer (grouped ahead by helper threads)
-    std::vector<int32_t> order, newid, load, freed, evicted, cnt, ipos;
+    std::vector<int32_t> order, newid, load, freed, evicted[2], cnt, ipos;
     std::vector<FamilyTable> tables;          // one per planning thread
     std::vector<int8_t> fam_own, owner_of;
-    std::vector<std::vector<int32_t>> freed_rows;
+    std::vector<std::vector<int32_t>> freed_rows[2];
     LineAlloc slots;
     std::vector<Alloc> rows;
 };
@@ -422,14 +430,14 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         ps->wake();
         ps->wait([&] { return ps->consumers.load() == 0; });
     };
-    std::vector<int32_t> &live = W.live, &next_live = W.next_live;   // individuals live before the current step
+    std::vector<LiveRec> &live = W.live, &next_live = W.next_live;   // individuals live before the current step (lane B's)
     live.clear(); next_live.clear();
     // allocators: global column slots (lines, lowest free first) and local rows per rank (stack)
     LineAlloc &slots = W.slots; slots.reset();
     std::vector<Alloc> &rows = W.rows; rows.resize((size_t)world);
     for (Alloc &a : rows) a.reset();
-    std::vector<std::vector<int32_t>> &freed_rows = W.freed_rows; freed_rows.resize((size_t)world);
-    for (auto &v : freed_rows) v.clear();
+    // (two sets: lane B fills those of layer t+1 while lane A still returns those of layer t)
+    for (auto &fr : W.freed_rows) { fr.resize((size_t)world); for (auto &v : fr) v.clear(); }
     if (!streaming) P.rows_cap.assign((size_t)world, 0);
     std::vector<int32_t> &order = W.order;
     std::vector<int32_t> &newid = W.newid, &load = W.load, &freed = W.freed;
@@ -510,23 +518,25 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
     // ---- the layers, as a pipeline of two lanes.  What is sequential in planning is the slot assignment: the
     //      members of layer t take the lines that the evictions of layer t-1 gave back.  The rest hangs off it:
     //        lane A (the planning thread)  couple owners and order (t), column slots and rows (t), member tiles (t),
-    //                                      end of the layer (evicted lines and rows return, live list)
-    //        lane B (a helper thread)      live range, flags and live tiles BEFORE step t, parents of the couples (t)
-    //      Lane B of layer t reads the homes of individuals born before t and the live list that lane A closed at the
-    //      end of t-1; lane A of layer t writes the homes of the members of t.  They meet three times per layer
-    //      (go -> B, ordered -> B, coupled -> A); each array of the plan is written by one lane only.  Without a
-    //      helper thread lane A runs lane B's pieces itself, in the same order. ----
+    //                                      end of the layer (evicted lines and rows return to the allocators)
+    //        lane B (a helper thread)      the live list, live range, flags and live tiles BEFORE step t, who is
+    //                                      evicted by it; the parents of the couples (t)
+    //      Lane B of layer t reads the homes of individuals born before t, so it may start as soon as lane A has
+    //      assigned the slots of layer t-1 (`slotted`), and needs the couple order of t for the parents (`ordered`);
+    //      lane A needs both pieces of lane B before it closes layer t (`coupled`).  Each array of the plan, and each
+    //      field of a Layer, is written by one lane only; what lane B hands back for the end of a layer (evicted
+    //      slots, freed rows) exists twice, because lane B is by then at work on the next layer.  Without a helper
+    //      thread lane A runs lane B's pieces itself, in the same order. ----
     double lt_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     auto lt_last = std::chrono::steady_clock::now();
 #define LT(k) do { if (timing) { auto n_ = std::chrono::steady_clock::now(); lt_acc[k] += std::chrono::duration<double, std::milli>(n_ - lt_last).count(); lt_last = n_; } } while (0)
     double ltb_acc[2] = {0, 0};
-    std::vector<int32_t> &evicted = W.evicted;           // slots evicted by the current step, ascending (lane B -> end of layer)
+    // slots evicted by a step, ascending (lane B -> end of the layer on lane A; two sets like freed_rows)
     int32_t cur_nf = 0, cur_nf_real = 0;                 // couples of the current layer with / without rank padding (A -> B)
 
     auto begin_layer = [&](int32_t t) {
         Layer &L = P.layers[t];
         L.n_new = count[t];
-        L.live_before = (int32_t)live.size();
         L.ref_founders = t > 0 ? cut_size[t - 1] : 0;
         L.ref_probands = cut_size[t];
         L.ref_both = t > 0 ? both_size[t - 1] : 0;
@@ -535,57 +545,72 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
             P.mem_ind.push_back(0); P.mem_slot.push_back(0); P.mem_fam.push_back(0); P.mem_lrow.push_back(0);
             if (by_seq) P.mem_rank.push_back(0);
         }
-        L.mem_off = P.mem_ind.size();
-        L.fam_off = P.fam_pf.size();
-        L.flag_off = P.flags.size();
+        L.mem_off = P.mem_ind.size();              // (the offsets into lane B's arrays are set there)
         L.mtile_off = P.mtile_desc.size() / 4;
         L.base_off = P.fam_base.size();
-        L.tile_off = P.tile_map.size();
-        L.ltile_off = P.live_tiles.size();
     };
 
-    // lane B, first piece: live range and flags (state BEFORE the step)
+    // lane B, first piece: the members of the previous layer join the live list (in rank order, after those carried);
+    // live range and flags (state BEFORE the step); who stays
     auto live_flags = [&](int32_t t) {
         Layer &L = P.layers[t];
+        if (t > 0) {
+            const int32_t *Xp = by_layer.data() + lstart[t - 1];
+            const int32_t np = count[t - 1];
+            for (int32_t q = 0; q < np; q++) {             // (ranks ascend: nearly sequential reads)
+                const int32_t x = Xp[q];
+                const Home hx = home[x];
+                live.push_back(LiveRec{hx.slot, hx.lrow, last_of[x], hx.owner});
+            }
+        }
+        L.live_before = (int32_t)live.size();
+        L.flag_off = P.flags.size();
+        L.tile_off = P.tile_map.size();
+        L.ltile_off = P.live_tiles.size();
+        std::vector<int32_t> &evicted = W.evicted[t & 1];
+        std::vector<std::vector<int32_t>> &freed_rows = W.freed_rows[t & 1];
         evicted.clear();
         next_live.clear();
+        L.flag_end = L.flag_off; L.tile_end = L.tile_off; L.ltile_end = L.ltile_off;
         if (live.empty()) return;
         int32_t lo = INT_MAX, hi = -1;
-        for (size_t li = 0; li < live.size(); li++) {
-            if (li + kPf < live.size()) __builtin_prefetch(&home[live[li + kPf]]);
-            const int32_t sl = home[live[li]].slot;
-            lo = std::min(lo, sl); hi = std::max(hi, sl);
-        }
+        for (const LiveRec &r : live) { lo = std::min(lo, r.slot); hi = std::max(hi, r.slot); }
         L.rt_lo = (lo / kPTile) * kPTile;
         L.rt_rows = round_up(hi + 1, kPTile) - L.rt_lo;
         P.flags.resize(L.flag_off + (size_t)L.rt_rows, 0);
         P.live_owner.resize(L.flag_off + (size_t)L.rt_rows, 0);
         P.live_lrow.resize(L.flag_off + (size_t)L.rt_rows, 0);
         uint8_t *fl = P.flags.data() + L.flag_off;
-        for (size_t li = 0; li < live.size(); li++) {
-            if (li + kPf < live.size()) __builtin_prefetch(&home[live[li + kPf]]);
-            const int32_t x = live[li];
-            const Home hx = home[x];
-            const bool stays = hx.last > t;      // read for the last time in step `last`
-            const int32_t r = hx.slot - L.rt_lo;
+        int8_t *lown = P.live_owner.data() + L.flag_off;
+        int32_t *llrow = P.live_lrow.data() + L.flag_off;
+        const int32_t rt_lo = L.rt_lo, rt_rows = L.rt_rows;
+        int32_t carried = 0;
+        for (const LiveRec &rec : live) {
+            const bool stays = rec.last > t;      // read for the last time in step `last`
+            const int32_t r = rec.slot - rt_lo;
             fl[r] = (uint8_t)(kFlagLive | (stays ? kFlagCarried : 0));
-            P.live_owner[L.flag_off + r] = hx.owner;
-            P.live_lrow[L.flag_off + r] = hx.lrow;
-            if (stays) { next_live.push_back(x); L.carried++; }
-            else if (world > 1) freed_rows[hx.owner].push_back(hx.lrow);
+            lown[r] = (int8_t)rec.owner;
+            llrow[r] = rec.lrow;
+            if (stays) { next_live.push_back(rec); carried++; }
+            else if (world > 1) freed_rows[(size_t)rec.owner].push_back(rec.lrow);
         }
-        for (int32_t r = 0; r < L.rt_rows; r++)        // evicted slots in ascending order -> freed lines, ascending
-            if (fl[r] == kFlagLive) evicted.push_back(L.rt_lo + r);
+        L.carried = carried;
+        for (int32_t r = 0; r < rt_rows; r++)          // evicted slots in ascending order -> freed lines, ascending
+            if (fl[r] == kFlagLive) evicted.push_back(rt_lo + r);
         // the strip buffers of the layer kernel hold the live tiles only (holes of a fragmented range cost nothing)
-        P.tile_map.resize(L.tile_off + (size_t)(L.rt_rows / kPTile), -1);
-        for (int32_t tl = 0; tl < L.rt_rows / kPTile; tl++) {
+        P.tile_map.resize(L.tile_off + (size_t)(rt_rows / kPTile), -1);
+        int32_t n_live_tiles = 0;
+        for (int32_t tl = 0; tl < rt_rows / kPTile; tl++) {
             uint8_t any = 0;
             for (int32_t r = tl * kPTile; r < (tl + 1) * kPTile; r++) any |= fl[r];
             if (any) {
-                P.tile_map[L.tile_off + (size_t)tl] = L.n_live_tiles++;
+                P.tile_map[L.tile_off + (size_t)tl] = n_live_tiles++;
                 P.live_tiles.push_back(tl | ((any & kFlagCarried) ? kTileCarried : 0));
             }
         }
+        L.n_live_tiles = n_live_tiles;
+        L.flag_end = P.flags.size(); L.tile_end = P.tile_map.size(); L.ltile_end = P.live_tiles.size();
+        live.swap(next_live);                              // those carried; the members of this layer follow at the next one
     };
 
     // lane A: row owners, couple order, member order
@@ -682,14 +707,14 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         int32_t *mi = P.mem_ind.data() + L.mem_off, *ms = P.mem_slot.data() + L.mem_off;
         int32_t *mf = P.mem_fam.data() + L.mem_off, *ml = P.mem_lrow.data() + L.mem_off;
         for (int32_t q = 0; q < nn; q++) {
-            if (q + kPf < nn) { const int32_t y = X[order[q + kPf]]; __builtin_prefetch(&home[y], 1); __builtin_prefetch(&last_of[y]); }
+            if (q + kPf < nn) __builtin_prefetch(&home[X[order[q + kPf]]], 1);
             if (q + 2 * kPf < nn) { __builtin_prefetch(&X[order[q + 2 * kPf]]); __builtin_prefetch(&fam_of[order[q + 2 * kPf]]); }
             const int32_t oq = order[q], x = X[oq], f = fam_of[oq];
             const int32_t g = fam_own[f];
             const int32_t s = slots.take(), lr = world > 1 ? rows[g].take() : s;   // one rank: row == slot
             if (streaming && (s >= bound_slots || lr >= bound_rows)) give_up_streaming();
             Home &hx = home[x];
-            hx.slot = s; hx.lrow = lr; hx.owner = (int8_t)g; hx.last = last_of[x];
+            hx.slot = s; hx.lrow = lr; hx.owner = (int8_t)g;
             if (world > 1) owner_of[x] = (int8_t)g;
             mi[q] = by_seq ? orient[x] : x; ms[q] = s; mf[q] = newid[f]; ml[q] = lr;
             if (by_seq) P.mem_rank[L.mem_off + (size_t)q] = x;
@@ -702,6 +727,7 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         const int32_t *X = by_layer.data() + lstart[t];
         const int32_t *fam_first = W.fam_first.data() + lstart[t];
         const int32_t nf = cur_nf, nf_real = cur_nf_real;
+        L.fam_off = P.fam_pf.size();
         P.fam_pf.resize(L.fam_off + (size_t)nf, -1); P.fam_pm.resize(L.fam_off + (size_t)nf, -1);
         P.fam_pf_owner.resize(L.fam_off + (size_t)nf, -1); P.fam_pm_owner.resize(L.fam_off + (size_t)nf, -1);
         P.fam_pf_lrow.resize(L.fam_off + (size_t)nf, -1); P.fam_pm_lrow.resize(L.fam_off + (size_t)nf, -1);
@@ -729,6 +755,7 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
                 *pq[s] = P.tile_map[L.tile_off + (size_t)(rel / kPTile)] * kPTile + rel % kPTile;
             }
         }
+        L.fam_end = P.fam_pf.size();
     };
 
     // lane A: member tiles, sole-reader marks, the layer is complete
@@ -764,24 +791,29 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         P.alg_elems += L.alg_elems;
         P.row_updates += nn;
 
-        L.mem_end = P.mem_ind.size(); L.fam_end = P.fam_pf.size(); L.flag_end = P.flags.size();
-        L.tile_end = P.tile_map.size(); L.ltile_end = P.live_tiles.size(); L.mtile_end = P.mtile_desc.size() / 4;
+        L.mem_end = P.mem_ind.size(); L.mtile_end = P.mtile_desc.size() / 4;     // (lane B has set the ends of its arrays)
         if (streaming) { ps->layers_done.store(t + 1, std::memory_order_release); ps->wake(); }
     };
 
     // lane A: after the step, evicted slots / rows become reusable from the next layer on
     auto end_layer = [&](int32_t t) {
-        const int32_t *X = by_layer.data() + lstart[t];
         freed.clear();
-        for (int32_t s : evicted) slots.release(s, freed);
+        for (int32_t s : W.evicted[t & 1]) slots.release(s, freed);
         slots.end_layer(freed);
-        for (int32_t g = 0; g < world && world > 1; g++) rows[g].end_layer(freed_rows[g]);
-        next_live.insert(next_live.end(), X, X + count[t]);
-        live.swap(next_live);
+        for (int32_t g = 0; g < world && world > 1; g++) rows[g].end_layer(W.freed_rows[t & 1][(size_t)g]);
     };
 
-    // hand-over between the lanes: layer numbers + 1
-    std::atomic<int32_t> go{0}, ordered{0}, coupled{0};
+    // hand-over between the lanes: layer numbers + 1.  A lane that has to wait groups couples ahead; with none left it
+    // spins politely (the other lane may run on the sibling hardware thread) and yields now and then
+    auto idle = [](unsigned &spins) {
+#if defined(__x86_64__) || defined(__i386__)
+        for (int i = 0; i < 16; i++) __builtin_ia32_pause();
+#elif defined(__aarch64__)
+        for (int i = 0; i < 16; i++) asm volatile("yield");
+#endif
+        if ((++spins & 255) == 0) std::this_thread::yield();
+    };
+    std::atomic<int32_t> slotted{0}, ordered{0}, coupled{0};
     std::atomic<bool> stop{false}, lane_failed{false};
     struct Helpers {
         std::vector<std::thread> th;
@@ -799,16 +831,17 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
                     auto lap = [&](int k) { if (timing) { auto n_ = std::chrono::steady_clock::now(); ltb_acc[k] += std::chrono::duration<double, std::milli>(n_ - tb).count(); } };
                     try {
                         for (int32_t t = 0; t < S; t++) {
-                            while (go.load(std::memory_order_acquire) <= t) {
+                            unsigned spins = 0;
+                            while (slotted.load(std::memory_order_acquire) < t) {      // the homes of layer t-1
                                 if (stop.load(std::memory_order_relaxed)) return;
-                                if (!group_one(id)) std::this_thread::yield();
+                                if (!group_one(id)) idle(spins);
                             }
                             if (timing) tb = std::chrono::steady_clock::now();
                             live_flags(t);
                             lap(0);
                             while (ordered.load(std::memory_order_acquire) <= t) {
                                 if (stop.load(std::memory_order_relaxed)) return;
-                                if (!group_one(id)) std::this_thread::yield();
+                                if (!group_one(id)) idle(spins);
                             }
                             if (timing) tb = std::chrono::steady_clock::now();
                             couples(t);
@@ -831,21 +864,23 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
     for (int32_t t = 0; t < S; t++) {
         LT(7);
         begin_layer(t);
-        if (piped) go.store(t + 1, std::memory_order_release); else live_flags(t);
+        if (!piped) live_flags(t);
         LT(0);
         // ---- couples of the layer (grouped by group_layer, possibly on a helper thread) ----
+        unsigned spins = 0;
         while (!grouped[t].load(std::memory_order_acquire))
-            if (!group_one(0)) std::this_thread::yield();
+            if (!group_one(0)) idle(spins);
         if (group_failed.load()) { helpers.join_all(); throw std::bad_alloc(); }
         LT(1);
         owners_order(t);
         if (piped) ordered.store(t + 1, std::memory_order_release);
         LT(2);
         assign_slots(t);
+        if (piped) slotted.store(t + 1, std::memory_order_release);
         LT(3);
         if (piped) {
             while (coupled.load(std::memory_order_acquire) <= t)
-                if (!group_one(0)) std::this_thread::yield();
+                if (!group_one(0)) idle(spins);
             if (lane_failed.load() || group_failed.load()) { helpers.join_all(); throw std::bad_alloc(); }
         } else couples(t);
         LT(4);
