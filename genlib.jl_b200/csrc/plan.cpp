@@ -249,9 +249,21 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
     for (int32_t x : P.pro_ind) { pre[x].h = 0; pre[x].rl = 0; }
     int32_t hmax = 0;
     bool bad_pedigree = false;
+    const bool by_seq = sparse_schedule(schedule);              // members of a layer in processing order
+    // Threads of the bucket pass further down: it works on equal ranges of ranks, and this sweep counts the heights
+    // per range for it (hist[h * kC + c]).  The same rule as for the layers (GENLIB_PLAN_THREADS, cores per rank).
+    int kC = 1;
+    const char *threads_env = std::getenv("GENLIB_PLAN_THREADS");   // (forces helpers on small plans too: the tests)
+    if (!by_seq) {
+        const int hw = (int)std::thread::hardware_concurrency();
+        kC = std::max(1, std::min(threads_env ? std::atoi(threads_env) : (n >= 400000 ? std::min(3, hw / world) : 1), 16));
+    }
+    const int32_t chunk = n / kC + 1;                            // range c = [c * chunk, (c + 1) * chunk)
     std::vector<int32_t> &hist = W.hist; hist.clear();
     constexpr int32_t kPf = 24;                  // software prefetch distance of the planner's random accesses
+    int32_t c_of_x = kC - 1, c_lo = (kC - 1) * chunk;
     for (int32_t x = n - 1; x >= 0; x--) {
+        while (x < c_lo) { c_of_x--; c_lo -= chunk; }
         if (x >= kPf) {
             const int32_t y = x - kPf, fy = father[y], my = mother[y];
             if ((uint32_t)fy < (uint32_t)n) __builtin_prefetch(&pre[fy], 1);      // (not validated yet)
@@ -262,8 +274,8 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         if ((uint32_t)fx + 1u > (uint32_t)x || (uint32_t)mx + 1u > (uint32_t)x) { bad_pedigree = true; continue; }
         const Pre px = pre[x];
         if (px.h < 0) continue;
-        if (px.h >= (int32_t)hist.size()) hist.resize((size_t)px.h + 64, 0);
-        hist[px.h]++;
+        if ((size_t)px.h * kC >= hist.size()) hist.resize(((size_t)px.h + 64) * kC, 0);
+        hist[(size_t)px.h * kC + c_of_x]++;
         hmax = std::max(hmax, px.h);
         const int32_t par[2] = {fx, mx};
         for (int32_t p : par) {
@@ -281,7 +293,6 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
     // is climbed.  The layer is then the depth, `seq` (the position in that queue) replaces the rank
     // wherever the kernels decide who is climbed, and eviction is sparse_phi's own rule (:400-430).
     // The sweep above marked the ancestors of the probands (branching, :323); re-label them.
-    const bool by_seq = sparse_schedule(schedule);              // members of a layer in processing order
     std::vector<int32_t> &seq_order = W.seq_order; seq_order.clear();
     std::vector<int32_t> &orient = W.orient;
     if (by_seq) {
@@ -345,8 +356,9 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
     }
     PLAN_T("heights");
     const int32_t S = hmax + 1;
+    hist.resize((size_t)S * kC, 0);                               // (by_seq: kC == 1)
     std::vector<int32_t> &count = W.count; count.assign((size_t)S + 1, 0);
-    for (int32_t k = 0; k < S; k++) count[S - 1 - k] = hist[k];
+    for (int32_t k = 0; k < S; k++) for (int c = 0; c < kC; c++) count[S - 1 - k] += hist[(size_t)k * kC + c];
     // members of each layer in rank order, where each row is read for the last time, and the
     // reference's cut sizes (verbose lines, compute.jl:254-261)
     std::vector<size_t> &lstart = W.lstart; lstart.assign((size_t)S + 1, 0);
@@ -358,19 +370,57 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
     std::vector<Home> &home = W.home; home.resize((size_t)n);     // filled when a slot is assigned; entries outside the plan are never read
     std::vector<int32_t> &last_of = W.last_of; last_of.resize((size_t)n);   // last layer that reads the row (a sequential write here)
     {
-        std::vector<size_t> &pos = W.pos; pos.assign(lstart.begin(), lstart.end() - 1);
+        // One range of visits: its members go to their layers from `pos` on, its share of the difference arrays to d[0..2].
+        auto bucket_range = [&](int32_t v0, int32_t v1, size_t *pos, int64_t *occ, int64_t *cut, int64_t *both) {
+            for (int32_t v = v0; v < v1; v++) {
+                const int32_t x = by_seq ? seq_order[(size_t)v] : v;
+                const Pre px = pre[x];
+                if (px.h < 0) continue;
+                const int32_t lx = S - 1 - px.h, ref_last = S - 1 - px.rl;
+                by_layer[pos[lx]++] = x;
+                const int32_t last = is_pro[x] ? INT_MAX : S - 1 - px.minch;     // probands stay to the end
+                last_of[x] = last;
+                occ[(size_t)std::min<int64_t>(std::max(last, lx), S - 1) + 1]--;   // born in or before, read in or after
+                cut[ref_last + 1]--;                                   // in cut[k] for layer <= k <= ref_last
+                if (ref_last > lx) { both[lx]++; both[ref_last]--; }   // in cut[k] and cut[k+1]
+            }
+        };
+        std::vector<size_t> &pos = W.pos;
         const int32_t n_visit = by_seq ? (int32_t)seq_order.size() : n;
-        for (int32_t v = 0; v < n_visit; v++) {
-            const int32_t x = by_seq ? seq_order[(size_t)v] : v;
-            const Pre px = pre[x];
-            if (px.h < 0) continue;
-            const int32_t lx = S - 1 - px.h, ref_last = S - 1 - px.rl;
-            by_layer[pos[lx]++] = x;
-            const int32_t last = is_pro[x] ? INT_MAX : S - 1 - px.minch;     // probands stay to the end
-            last_of[x] = last;
-            d_occ[(size_t)std::min<int64_t>(std::max(last, lx), S - 1) + 1]--;   // born in or before, read in or after
-            d_cut[ref_last + 1]--;                                 // in cut[k] for layer <= k <= ref_last
-            if (ref_last > lx) { d_both[lx]++; d_both[ref_last]--; }   // in cut[k] and cut[k+1]
+        bool done = false;
+        if (kC > 1 && (threads_env || lstart[S] >= 200000)) {
+            // ranges of ranks side by side: range c starts, in layer t, after the members that the ranges below it
+            // hold there (counted by the sweep); the difference arrays are summed afterwards
+            const size_t D = (size_t)S + 2;
+            pos.assign((size_t)kC * S, 0);
+            for (int32_t t = 0; t < S; t++) {
+                size_t at = lstart[t];
+                for (int c = 0; c < kC; c++) { pos[(size_t)c * S + t] = at; at += (size_t)hist[(size_t)(S - 1 - t) * kC + c]; }
+            }
+            std::vector<int64_t> dd((size_t)kC * 3 * D, 0);
+            std::vector<std::thread> th;
+            int started = 1;
+            try {
+                for (int c = 1; c < kC; c++, started++)
+                    th.emplace_back([&, c] {
+                        bucket_range(std::min(n, c * chunk), std::min(n, (c + 1) * chunk), pos.data() + (size_t)c * S,
+                                     dd.data() + ((size_t)c * 3) * D, dd.data() + ((size_t)c * 3 + 1) * D, dd.data() + ((size_t)c * 3 + 2) * D);
+                    });
+            } catch (...) {}                                           // no thread: the ranges left are done here
+            bucket_range(0, std::min(n, chunk), pos.data(), dd.data(), dd.data() + D, dd.data() + 2 * D);
+            for (int c = started; c < kC; c++)
+                bucket_range(std::min(n, c * chunk), std::min(n, (c + 1) * chunk), pos.data() + (size_t)c * S,
+                             dd.data() + ((size_t)c * 3) * D, dd.data() + ((size_t)c * 3 + 1) * D, dd.data() + ((size_t)c * 3 + 2) * D);
+            for (auto &t : th) t.join();
+            for (int c = 0; c < kC; c++)
+                for (size_t k = 0; k < D; k++) {
+                    d_occ[k] += dd[((size_t)c * 3) * D + k]; d_cut[k] += dd[((size_t)c * 3 + 1) * D + k]; d_both[k] += dd[((size_t)c * 3 + 2) * D + k];
+                }
+            done = true;
+        }
+        if (!done) {
+            pos.assign(lstart.begin(), lstart.end() - 1);
+            bucket_range(0, n_visit, pos.data(), d_occ.data(), d_cut.data(), d_both.data());
         }
         for (int32_t t = 0; t < S; t++) { d_occ[t] += count[t]; d_cut[t] += count[t]; }   // everybody enters with its layer
     }
@@ -493,9 +543,8 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         // the planning thread, one helper that runs the second lane of the layer pipeline below, one that groups
         // couples ahead (with two threads the helper does both); small plans are not worth the threads.
         // GENLIB_PLAN_THREADS overrides (also for small plans: the tests run those with helpers too)
-        const char *env = std::getenv("GENLIB_PLAN_THREADS");
         const int hw = (int)std::thread::hardware_concurrency();
-        n_threads = env ? std::atoi(env) : (M >= 200000 ? std::min(3, hw / world) : 1);
+        n_threads = threads_env ? std::atoi(threads_env) : (M >= 200000 ? std::min(3, hw / world) : 1);
         n_threads = std::max(1, std::min(n_threads, 16));
     }
     if (W.tables.size() < (size_t)n_threads) W.tables.resize((size_t)n_threads);
