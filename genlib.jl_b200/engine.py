@@ -417,25 +417,61 @@ class KinshipMatrix:
     reference's own test, test/runtests.jl:56)."""
 
     def __init__(self, ids: np.ndarray, ranks: np.ndarray, dense: np.ndarray):
+        """`dense`: the symmetric matrix in the order of `ids`.  Kept are the entries the reference's Dict of Dicts
+        holds where a look-up finds them (:391-394, zeros are never stored): per individual, in rank order, the
+        diagonal and the non-zero kinships with higher-ranked individuals -- compressed sparse rows."""
         order = np.argsort(ranks, kind="stable")
         self._ids = np.asarray(ids)[order]
         self._pos = {int(i): k for k, i in enumerate(self._ids)}
-        self._dense = np.ascontiguousarray(np.asarray(dense, np.float32)[np.ix_(order, order)])
+        dense = np.asarray(dense, np.float32)
+        n = len(order)
+        indptr = np.zeros(n + 1, np.int64)
+        cols, vals = [], []
+        for k in range(n):
+            row = dense[order[k]][order[k:]]                 # (k, j) for j >= k, in rank order
+            nz = np.flatnonzero(row != 0)
+            if len(nz) == 0 or nz[0] != 0:
+                nz = np.concatenate(([0], nz))               # the diagonal is always there (:398)
+            cols.append(nz + k)
+            vals.append(row[nz])
+            indptr[k + 1] = indptr[k] + len(nz)
+        self._indptr = indptr
+        self._indices = np.concatenate(cols).astype(np.int64) if n else np.zeros(0, np.int64)
+        self._data = np.concatenate(vals).astype(np.float32) if n else np.zeros(0, np.float32)
+
+    def _row(self, k: int):
+        a, b = self._indptr[k], self._indptr[k + 1]
+        return self._indices[a:b], self._data[a:b]
 
     def __getitem__(self, key) -> np.float32:
         a, b = key
-        return self._dense[self._pos[int(a)], self._pos[int(b)]]     # KeyError on an unknown ID, like the Dict
+        ka, kb = self._pos[int(a)], self._pos[int(b)]        # KeyError on an unknown ID, like the Dict
+        lo, hi = (ka, kb) if ka < kb else (kb, ka)           # phi[lower rank][higher rank] (:36-40)
+        cols, vals = self._row(lo)
+        p = int(np.searchsorted(cols, hi))
+        return vals[p] if p < len(cols) and cols[p] == hi else np.float32(0)
 
     @property
     def stored(self) -> int:
-        return int(np.count_nonzero(np.triu(self._dense, 1))) + len(self._ids)
+        return len(self._data)
+
+    def to_dense(self) -> np.ndarray:
+        """The symmetric Float32 matrix in rank order (zeros where nothing is stored)."""
+        n = len(self._ids)
+        d = np.zeros((n, n), np.float32)
+        rows = np.repeat(np.arange(n), np.diff(self._indptr))
+        d[rows, self._indices] = self._data
+        d[self._indices, rows] = self._data
+        return d
+
+    _dense = property(to_dense)
 
     def to_dict(self) -> dict:
         """{lower-ranked ID: {higher-ranked ID: kinship}}: the entries of `KinshipMatrix.dict` a look-up finds."""
         out = {}
         for k, i in enumerate(self._ids):
-            row = self._dense[k]
-            out[int(i)] = {int(self._ids[j]): row[j] for j in range(k, len(self._ids)) if j == k or row[j] != 0}
+            cols, vals = self._row(k)
+            out[int(i)] = {int(self._ids[j]): v for j, v in zip(cols, vals)}
         return out
 
     def __len__(self) -> int:
@@ -498,11 +534,13 @@ def phiMean(phi_matrix) -> np.float32:
     iteration order; here the entries a look-up can find are added in rank order -- the same number
     whenever the Float32 sum is exact, e.g. the reference's own test, test/runtests.jl:55."""
     if isinstance(phi_matrix, KinshipMatrix):
-        d, n = phi_matrix._dense, len(phi_matrix)
-        total = np.float32(0)
-        for k in range(n):
-            total = np.float32(total + d[k, k:].sum(dtype=np.float32))
-        total = np.float32(total - np.trace(d, dtype=np.float32))
+        k, n = phi_matrix, len(phi_matrix)
+        total, diag = np.float32(0), np.float32(0)
+        for r in range(n):                                   # sum(values(kinships)) per individual (:467), then their sum
+            vals = k._row(r)[1]
+            total = np.float32(total + vals.sum(dtype=np.float32))
+            diag = np.float32(diag + vals[0])                # the diagonal leads its row
+        total = np.float32(total - diag)
         return np.float32(total / (n * (n - 1) / 2))
     m = np.asarray(phi_matrix, np.float32)
     big = m.size > (1 << 22)                                        # the scalar emulation is slow: NumPy's pairwise sum

@@ -180,3 +180,36 @@ def test_kinship_matrix_counts(gen, ob):
     k = gen.KinshipMatrix(pro, ranks, dense)
     assert k.stored == info["findable"] and info["stored"] == info["findable"] + info["misfiled"] + info["orphans"]
     assert info["misfiled"] + info["orphans"] > 0
+
+
+@pytest.mark.parametrize("seed,window", [(5, 0), (302, 40), (303, 120)])
+def test_kinship_matrix_keeps_only_what_the_reference_stores(gen, ob, seed, window):
+    """The KinshipMatrix holds compressed sparse rows -- per individual the diagonal and the non-zero kinships with
+    higher-ranked individuals, what the reference's Dict of Dicts holds where a look-up finds it (compute.jl:391-394)
+    -- and still answers every look-up, its dense form and its mean like the dense matrix it was made from."""
+    rng = np.random.default_rng(seed)
+    ped = gen.genealogy(random_pedigree(rng, 600, 12, window=window))
+    pro = rng.permutation(ped.ids)[:80]
+    ranks = ped.rank_of(pro)
+    order = np.argsort(ranks, kind="stable")
+    for directed in (True, False):
+        dense = ob.sparse_phi_ranks(ped.father, ped.mother, ranks, ids=ped.ids, directed=directed)[0]
+        assert np.array_equal(dense, dense.T)
+        k = gen.KinshipMatrix(pro, ranks, dense)
+        want = np.ascontiguousarray(dense[np.ix_(order, order)])
+        assert np.array_equal(k.to_dense().view(np.uint32), want.view(np.uint32))
+        assert k.stored == int(np.count_nonzero(np.triu(want, 1))) + len(pro) == len(k._data)
+        assert k.stored < len(pro) * (len(pro) + 1) // 2                   # zeros are not kept
+        for a in range(0, 80, 7):
+            for b in range(0, 80, 5):
+                assert k[int(pro[a]), int(pro[b])] == dense[a, b] == k[int(pro[b]), int(pro[a])]
+        d = k.to_dict()
+        assert sum(len(v) for v in d.values()) == k.stored
+        assert all(d[int(i)][int(i)] == want[r, r] for r, i in enumerate(np.asarray(pro)[order]))
+        # the mean over the stored entries == the mean over the upper triangle (exact in binary64 here)
+        up = np.triu(want.astype(np.float64), 1)
+        assert abs(float(gen.phiMean(k)) - up.sum() / (80 * 79 / 2)) < 1e-6
+    with pytest.raises(KeyError):
+        k[int(pro[0]), -12345]
+    empty = gen.KinshipMatrix(np.zeros(0, np.int64), np.zeros(0, np.int32), np.zeros((0, 0), np.float32))
+    assert len(empty) == 0 and empty.stored == 0 and empty.to_dense().shape == (0, 0)
