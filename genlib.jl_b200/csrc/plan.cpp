@@ -136,7 +136,7 @@ struct Scratch {
     std::vector<LiveRec> live, next_live;
     std::vector<int32_t> last_of;
     std::vector<int32_t> fam_of, fam_count, fam_first, fam_key, fam_n;   // couples of every layer (grouped ahead by helper threads)
-    std::vector<int32_t> order, newid, load, freed, evicted[2], cnt, ipos;
+    std::vector<int32_t> order, newid, nf_of, load, freed, evicted[2], cnt, cnt_order, ipos;   // order / newid: by member / couple of every layer
     std::vector<FamilyTable> tables;          // one per planning thread
     std::vector<int8_t> fam_own, owner_of;
     std::vector<std::vector<int32_t>> freed_rows[2];
@@ -489,10 +489,8 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
     // (two sets: lane B fills those of layer t+1 while lane A still returns those of layer t)
     for (auto &fr : W.freed_rows) { fr.resize((size_t)world); for (auto &v : fr) v.clear(); }
     if (!streaming) P.rows_cap.assign((size_t)world, 0);
-    std::vector<int32_t> &order = W.order;
-    std::vector<int32_t> &newid = W.newid, &load = W.load, &freed = W.freed;
+    std::vector<int32_t> &load = W.load, &freed = W.freed;
     load.assign((size_t)world, 0);
-    std::vector<int8_t> &fam_own = W.fam_own;
     // the owners once more, one byte per individual: the owner rule reads two parents per couple, and a generation of
     // these stays in cache where the 16-byte homes do not
     std::vector<int8_t> &owner_of = W.owner_of; if (world > 1) owner_of.resize((size_t)n);
@@ -505,6 +503,7 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
     constexpr int32_t kKeys = 64;
     const size_t M = lstart[S];
     W.fam_of.resize(M); W.fam_count.resize(M); W.fam_first.resize(M); W.fam_key.resize(M);
+    W.order.resize(M); W.newid.resize(M); W.fam_own.resize(M); W.nf_of.assign((size_t)S, 0);   // (owners_order, per layer)
     W.fam_n.assign((size_t)S, 0);
     auto group_layer = [&](int32_t t, FamilyTable &table) {
         const int32_t *X = by_layer.data() + lstart[t];
@@ -564,24 +563,25 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         return true;
     };
 
-    // ---- the layers, as a pipeline of two lanes.  What is sequential in planning is the slot assignment: the
-    //      members of layer t take the lines that the evictions of layer t-1 gave back.  The rest hangs off it:
-    //        lane A (the planning thread)  couple owners and order (t), column slots and rows (t), member tiles (t),
-    //                                      end of the layer (evicted lines and rows return to the allocators)
+    // ---- the layers, as a pipeline.  What is sequential in planning is the slot assignment: the members of layer t
+    //      take the lines that the evictions of layer t-1 gave back.  The rest hangs off it:
+    //        lane A (the planning thread)  column slots and rows (t), member tiles (t), end of the layer (evicted
+    //                                      lines and rows return to the allocators)
     //        lane B (a helper thread)      the live list, live range, flags and live tiles BEFORE step t, who is
     //                                      evicted by it; the parents of the couples (t)
+    //        ahead of both, by whoever is free: couples grouped (group_layer, any layer) and the ordering chain
+    //                                      (owners_order: owners, couple and member order, layer after layer)
     //      Lane B of layer t reads the homes of individuals born before t, so it may start as soon as lane A has
     //      assigned the slots of layer t-1 (`slotted`), and needs the couple order of t for the parents (`ordered`);
-    //      lane A needs both pieces of lane B before it closes layer t (`coupled`).  Each array of the plan, and each
-    //      field of a Layer, is written by one lane only; what lane B hands back for the end of a layer (evicted
-    //      slots, freed rows) exists twice, because lane B is by then at work on the next layer.  Without a helper
-    //      thread lane A runs lane B's pieces itself, in the same order. ----
+    //      lane A needs the order of t for the slots and both pieces of lane B before it closes layer t (`coupled`).
+    //      Each array of the plan, and each field of a Layer, is written by one lane only; what lane B hands back
+    //      for the end of a layer (evicted slots, freed rows) exists twice, because lane B is by then at work on the
+    //      next layer.  Without a helper thread lane A runs everything itself, in the same order. ----
     double lt_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     auto lt_last = std::chrono::steady_clock::now();
 #define LT(k) do { if (timing) { auto n_ = std::chrono::steady_clock::now(); lt_acc[k] += std::chrono::duration<double, std::milli>(n_ - lt_last).count(); lt_last = n_; } } while (0)
     double ltb_acc[2] = {0, 0};
     // slots evicted by a step, ascending (lane B -> end of the layer on lane A; two sets like freed_rows)
-    int32_t cur_nf = 0, cur_nf_real = 0;                 // couples of the current layer with / without rank padding (A -> B)
 
     auto begin_layer = [&](int32_t t) {
         Layer &L = P.layers[t];
@@ -596,7 +596,6 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         }
         L.mem_off = P.mem_ind.size();              // (the offsets into lane B's arrays are set there)
         L.mtile_off = P.mtile_desc.size() / 4;
-        L.base_off = P.fam_base.size();
     };
 
     // lane B, first piece: the members of the previous layer join the live list (in rank order, after those carried);
@@ -662,7 +661,8 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         live.swap(next_live);                              // those carried; the members of this layer follow at the next one
     };
 
-    // lane A: row owners, couple order, member order
+    // row owners, couple order, member order: a chain of its own from layer to layer (the owner rule reads the owners of
+    // the parents), independent of the slots -- run ahead by whoever is free (see order_next below)
     auto owners_order = [&](int32_t t) {
         Layer &L = P.layers[t];
         const int32_t *X = by_layer.data() + lstart[t];
@@ -670,12 +670,14 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         const int32_t *fam_of = W.fam_of.data() + lstart[t], *fam_count = W.fam_count.data() + lstart[t];
         const int32_t *fam_first = W.fam_first.data() + lstart[t], *fam_key = W.fam_key.data() + lstart[t];
         const int32_t nf_real = W.fam_n[t];
+        int8_t *fam_own = W.fam_own.data() + lstart[t];
+        int32_t *newid = W.newid.data() + lstart[t], *order = W.order.data() + lstart[t];
+        L.base_off = P.fam_base.size();
         // ---- row owners: a couple's children live with one of their parents' rows (the other
         //      parent row is read through NVLink); spill to the least loaded rank past +12.5 %.
         //      Couples are renumbered rank-major; every rank's range starts at a multiple of 4
         //      (16-byte aligned couple columns), the gaps are empty dummy couples. ----
-        fam_own.assign((size_t)nf_real, 0);
-        newid.assign((size_t)nf_real, 0);
+        std::fill(fam_own, fam_own + nf_real, (int8_t)0);
         P.fam_base.resize(L.base_off + (size_t)world + 1, 0);
         P.mem_base.resize(L.base_off + (size_t)world + 1, 0);
         int32_t *fbase = P.fam_base.data() + L.base_off, *mbase = P.mem_base.data() + L.base_off;
@@ -702,6 +704,7 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
                 fam_own[f] = (int8_t)g;
                 load[g] += fam_count[f];
             }
+            for (int32_t q = 0; q < nn; q++) owner_of[X[q]] = fam_own[fam_of[q]];   // (ranks ascend: sequential writes)
         }
         // ---- couple order inside a rank's range: by the layer in which the couple's longest-lived
         //      member leaves the frontier, then by rank (stable).  A line of column slots then holds
@@ -711,7 +714,7 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         int32_t key_lo = kKeys, key_hi = -1;
         for (int32_t f = 0; f < nf_real; f++) { key_lo = std::min(key_lo, fam_key[f]); key_hi = std::max(key_hi, fam_key[f]); }
         if (world > 1 || key_lo != key_hi) {
-            std::vector<int32_t> &cnt = W.cnt; cnt.assign((size_t)world * kKeys, 0);
+            std::vector<int32_t> &cnt = W.cnt_order; cnt.assign((size_t)world * kKeys, 0);
             for (int32_t f = 0; f < nf_real; f++) cnt[(size_t)fam_own[f] * kKeys + fam_key[f]]++;
             for (int32_t g = 0; g < world; g++) {
                 int32_t at = fbase[g];
@@ -736,12 +739,11 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         for (int32_t f = 0; f < nf_real; f++) fstart[newid[f] + 1] = fam_count[f];
         for (int32_t f = 0; f < nf; f++) fstart[f + 1] += fstart[f];
         for (int32_t g = 0; g <= world; g++) mbase[g] = fstart[fbase[g]];
-        order.assign((size_t)nn, 0);
         {
             std::vector<int32_t> &pos = W.ipos; pos.assign(fstart, fstart + nf);
             for (int32_t q = 0; q < nn; q++) order[pos[newid[fam_of[q]]]++] = q;
         }
-        cur_nf = nf; cur_nf_real = nf_real;
+        W.nf_of[t] = nf;
     };
 
     // lane A: column slots (global, in lines) and local rows (per owner)
@@ -750,6 +752,8 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         const int32_t *X = by_layer.data() + lstart[t];
         const int32_t nn = count[t];
         const int32_t *fam_of = W.fam_of.data() + lstart[t];
+        const int8_t *fam_own = W.fam_own.data() + lstart[t];
+        const int32_t *newid = W.newid.data() + lstart[t], *order = W.order.data() + lstart[t];
         P.mem_ind.resize(L.mem_off + (size_t)nn); P.mem_slot.resize(L.mem_off + (size_t)nn);
         P.mem_fam.resize(L.mem_off + (size_t)nn); P.mem_lrow.resize(L.mem_off + (size_t)nn);
         if (by_seq) P.mem_rank.resize(L.mem_off + (size_t)nn);
@@ -764,7 +768,6 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
             if (streaming && (s >= bound_slots || lr >= bound_rows)) give_up_streaming();
             Home &hx = home[x];
             hx.slot = s; hx.lrow = lr; hx.owner = (int8_t)g;
-            if (world > 1) owner_of[x] = (int8_t)g;
             mi[q] = by_seq ? orient[x] : x; ms[q] = s; mf[q] = newid[f]; ml[q] = lr;
             if (by_seq) P.mem_rank[L.mem_off + (size_t)q] = x;
         }
@@ -775,7 +778,8 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         Layer &L = P.layers[t];
         const int32_t *X = by_layer.data() + lstart[t];
         const int32_t *fam_first = W.fam_first.data() + lstart[t];
-        const int32_t nf = cur_nf, nf_real = cur_nf_real;
+        const int32_t nf = W.nf_of[t], nf_real = W.fam_n[t];
+        const int32_t *newid = W.newid.data() + lstart[t];
         L.fam_off = P.fam_pf.size();
         P.fam_pf.resize(L.fam_off + (size_t)nf, -1); P.fam_pm.resize(L.fam_off + (size_t)nf, -1);
         P.fam_pf_owner.resize(L.fam_off + (size_t)nf, -1); P.fam_pm_owner.resize(L.fam_off + (size_t)nf, -1);
@@ -810,7 +814,7 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
     // lane A: member tiles, sole-reader marks, the layer is complete
     auto finish_layer = [&](int32_t t) {
         Layer &L = P.layers[t];
-        const int32_t nn = count[t], nf = cur_nf;
+        const int32_t nn = count[t], nf = W.nf_of[t];
         // member tiles = the column blocks the layer kernel writes at a time: at most kMTile members and at
         // most kMaxTileFam couples (bounds the staged couple tile), cut at multiples of 8 members (whole
         // 32-byte sectors of a float row on both sides of the cut)
@@ -864,6 +868,27 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
     };
     std::atomic<int32_t> slotted{0}, ordered{0}, coupled{0};
     std::atomic<bool> stop{false}, lane_failed{false};
+    // The ordering chain (owners_order, layer after layer) belongs to nobody: whoever is free and finds the next
+    // layer grouped takes it (one at a time), so it runs ahead of the slots on a helper when there is one and on
+    // the planning thread when there is not.  Returns false when there was nothing to take.
+    std::atomic<bool> order_busy{false};
+    int32_t order_next = 0;                              // (guarded by order_busy)
+    auto order_one = [&]() {
+        if (ordered.load(std::memory_order_relaxed) >= S) return false;
+        if (order_busy.exchange(true, std::memory_order_acquire)) return false;
+        bool did = false;
+        const int32_t t = order_next;
+        if (t < S && grouped[(size_t)t].load(std::memory_order_acquire) && !group_failed.load()) {
+            try { owners_order(t); } catch (...) { lane_failed.store(true); }
+            order_next = t + 1;
+            ordered.store(t + 1, std::memory_order_release);
+            did = true;
+        }
+        order_busy.store(false, std::memory_order_release);
+        return did;
+    };
+    // what a waiting thread does meanwhile: the ordering chain first (it is on the way of both lanes), else grouping
+    auto side_job = [&](int id) { return order_one() || group_one(id); };
     struct Helpers {
         std::vector<std::thread> th;
         std::atomic<bool> *stop = nullptr;
@@ -878,26 +903,27 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
                 helpers.th.emplace_back([&, id] {                 // lane B; groups couples ahead whenever it has to wait
                     auto tb = std::chrono::steady_clock::now();
                     auto lap = [&](int k) { if (timing) { auto n_ = std::chrono::steady_clock::now(); ltb_acc[k] += std::chrono::duration<double, std::milli>(n_ - tb).count(); } };
+                    unsigned spins0 = 0;
                     try {
                         for (int32_t t = 0; t < S; t++) {
                             unsigned spins = 0;
                             while (slotted.load(std::memory_order_acquire) < t) {      // the homes of layer t-1
                                 if (stop.load(std::memory_order_relaxed)) return;
-                                if (!group_one(id)) idle(spins);
+                                if (!side_job(id)) idle(spins);
                             }
                             if (timing) tb = std::chrono::steady_clock::now();
                             live_flags(t);
                             lap(0);
                             while (ordered.load(std::memory_order_acquire) <= t) {
                                 if (stop.load(std::memory_order_relaxed)) return;
-                                if (!group_one(id)) idle(spins);
+                                if (!side_job(id)) idle(spins);
                             }
                             if (timing) tb = std::chrono::steady_clock::now();
                             couples(t);
                             lap(1);
                             coupled.store(t + 1, std::memory_order_release);
                         }
-                        while (group_one(id)) {}
+                        while (!stop.load(std::memory_order_relaxed) && ordered.load(std::memory_order_acquire) < S) { if (!side_job(id)) idle(spins0); }
                     } catch (...) {
                         lane_failed.store(true);
                         coupled.store(INT32_MAX, std::memory_order_release);
@@ -905,7 +931,10 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
                 });
                 piped = true;
             } else {
-                helpers.th.emplace_back([&, id] { while (!stop.load(std::memory_order_relaxed) && group_one(id)) {} });
+                helpers.th.emplace_back([&, id] {             // grouping and the ordering chain, until both are through
+                    unsigned spins = 0;
+                    while (!stop.load(std::memory_order_relaxed) && ordered.load(std::memory_order_acquire) < S) { if (!side_job(id)) idle(spins); }
+                });
             }
         } catch (...) { break; }                 // no thread: the planning thread does the jobs itself
     }
@@ -915,21 +944,20 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         begin_layer(t);
         if (!piped) live_flags(t);
         LT(0);
-        // ---- couples of the layer (grouped by group_layer, possibly on a helper thread) ----
+        // ---- couples of the layer grouped (group_layer) and ordered (owners_order), here or on a helper thread ----
         unsigned spins = 0;
-        while (!grouped[t].load(std::memory_order_acquire))
-            if (!group_one(0)) idle(spins);
-        if (group_failed.load()) { helpers.join_all(); throw std::bad_alloc(); }
-        LT(1);
-        owners_order(t);
-        if (piped) ordered.store(t + 1, std::memory_order_release);
+        while (ordered.load(std::memory_order_acquire) <= t) {
+            if (group_failed.load() || lane_failed.load()) { helpers.join_all(); throw std::bad_alloc(); }
+            if (!side_job(0)) idle(spins);
+        }
+        if (group_failed.load() || lane_failed.load()) { helpers.join_all(); throw std::bad_alloc(); }
         LT(2);
         assign_slots(t);
         if (piped) slotted.store(t + 1, std::memory_order_release);
         LT(3);
         if (piped) {
             while (coupled.load(std::memory_order_acquire) <= t)
-                if (!group_one(0)) idle(spins);
+                if (!side_job(0)) idle(spins);
             if (lane_failed.load() || group_failed.load()) { helpers.join_all(); throw std::bad_alloc(); }
         } else couples(t);
         LT(4);
@@ -940,7 +968,7 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
     helpers.join_all();
     if (group_failed.load() || lane_failed.load()) throw std::bad_alloc();
     if (timing) {
-        std::fprintf(stderr, "[plan]   lane A: %s %.2f  wait-group %.2f  owners/order %.2f  slots %.2f  %s %.2f  tiles %.2f  end %.2f\n",
+        std::fprintf(stderr, "[plan]   lane A: %s %.2f  (unused %.2f)  order: own share or wait %.2f  slots %.2f  %s %.2f  tiles %.2f  end %.2f\n",
                      piped ? "begin" : "live/flags", lt_acc[0], lt_acc[1], lt_acc[2], lt_acc[3], piped ? "wait-B" : "couples", lt_acc[4], lt_acc[5], lt_acc[7]);
         if (piped) std::fprintf(stderr, "[plan]   lane B: live/flags %.2f  couples %.2f\n", ltb_acc[0], ltb_acc[1]);
     }
