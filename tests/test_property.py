@@ -33,8 +33,21 @@ def pedigrees(draw):
 
 
 @settings(max_examples=300, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
-@given(ped=pedigrees(), world=st.integers(1, 3))
-def test_any_small_pedigree_both_schedules(gen, ob, ped, world):
+@given(ped=pedigrees(), world=st.integers(1, 3), threads=st.sampled_from([None, "2", "3", "4"]))
+def test_any_small_pedigree_both_schedules(gen, ob, ped, world, threads):
+    """`threads`: the planner's helper threads forced on these small plans too (its lanes must not change the plan)."""
+    import os
+    if threads is None:
+        os.environ.pop("GENLIB_PLAN_THREADS", None)
+    else:
+        os.environ["GENLIB_PLAN_THREADS"] = threads
+    try:
+        _check(gen, ob, ped, world)
+    finally:
+        os.environ.pop("GENLIB_PLAN_THREADS", None)
+
+
+def _check(gen, ob, ped, world):
     father, mother, probands = ped
     # parents precede children by construction, but ranks must also follow the depth order of
     # gen.genealogy (create.jl:217-227) for sparse_phi's queue; re-rank through the loader
