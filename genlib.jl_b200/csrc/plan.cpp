@@ -864,7 +864,7 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
 #elif defined(__aarch64__)
         for (int i = 0; i < 16; i++) asm volatile("yield");
 #endif
-        if ((++spins & 255) == 0) std::this_thread::yield();
+        if ((++spins & 15) == 0) std::this_thread::yield();   // (every few microseconds: ranks of a job share the host's cores)
     };
     std::atomic<int32_t> slotted{0}, ordered{0}, coupled{0};
     std::atomic<bool> stop{false}, lane_failed{false};
