@@ -85,6 +85,37 @@ def test_plan_errors(gen):
     assert gen.phi(ped, [], compute=True).shape == (0, 0)   # empty list needs no device
 
 
+def test_plan_reports_the_first_broken_rank(gen):
+    """The pedigree is checked inside the planner's reverse sweep (children before parents); what is reported is still
+    the FIRST offending rank, a broken pedigree goes before a bad proband, an empty proband list does not hide it,
+    and the streamed planner says the same."""
+    n = 50
+    fa, mo = np.full(n, -1, np.int32), np.full(n, -1, np.int32)
+    fa[10:] = np.arange(0, n - 10); mo[10:] = np.arange(1, n - 9)
+    ok = gen.Plan(fa, mo, [n - 1])
+    assert ok.n_layers > 1
+    for stream in (False, True):
+        bad = fa.copy(); bad[40] = 45; bad[20] = 33                       # two parents after their children
+        with pytest.raises(gen.GenlibError, match="parent does not precede child at rank 20"):
+            gen.Plan(bad, mo, [n - 1], stream=stream)
+        bad = fa.copy(); bad[30] = 30                                      # its own parent
+        with pytest.raises(gen.GenlibError, match="at rank 30"):
+            gen.Plan(bad, mo, [n - 1], stream=stream)
+        bad = mo.copy(); bad[44] = n + 7; bad[12] = -2
+        with pytest.raises(KeyError, match="out of range at rank 12"):
+            gen.Plan(fa, bad, [n - 1], stream=stream)
+        with pytest.raises(KeyError, match="out of range at rank 12"):    # ... before the proband that is not there
+            gen.Plan(fa, bad, [n + 3], stream=stream)
+        with pytest.raises(KeyError, match="out of range at rank 12"):
+            gen.Plan(fa, bad, [], stream=stream)
+        with pytest.raises(KeyError, match="proband index"):
+            gen.Plan(fa, mo, [0, n + 3], stream=stream)
+        # a broken row nobody descends from is found as well
+        bad = fa.copy(); bad[n - 2] = n - 1
+        with pytest.raises(gen.GenlibError, match=f"at rank {n - 2}"):
+            gen.Plan(bad, mo, [n - 1], stream=stream)
+
+
 def test_plan_invariants(gen):
     s = gen.synth.generate(4000, 10, 200, alpha=0.05, demes=2, migration=0.1, overlap=3, seed=5)
     ped = gen.genealogy(s.as_columns())
