@@ -598,6 +598,7 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         L.mtile_off = P.mtile_desc.size() / 4;
     };
 
+    int32_t live_lo = INT_MAX, live_hi = -1;             // lowest / highest slot on the live list (lane B's)
     // lane B, first piece: the members of the previous layer join the live list (in rank order, after those carried);
     // live range and flags (state BEFORE the step); who stays
     auto live_flags = [&](int32_t t) {
@@ -609,6 +610,7 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
                 const int32_t x = Xp[q];
                 const Home hx = home[x];
                 live.push_back(LiveRec{hx.slot, hx.lrow, last_of[x], hx.owner});
+                live_lo = std::min(live_lo, hx.slot); live_hi = std::max(live_hi, hx.slot);
             }
         }
         L.live_before = (int32_t)live.size();
@@ -621,10 +623,9 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         next_live.clear();
         L.flag_end = L.flag_off; L.tile_end = L.tile_off; L.ltile_end = L.ltile_off;
         if (live.empty()) return;
-        int32_t lo = INT_MAX, hi = -1;
-        for (const LiveRec &r : live) { lo = std::min(lo, r.slot); hi = std::max(hi, r.slot); }
-        L.rt_lo = (lo / kPTile) * kPTile;
-        L.rt_rows = round_up(hi + 1, kPTile) - L.rt_lo;
+        // (lowest and highest live slot: kept up to date by the pass below for those who stay, above for those who join)
+        L.rt_lo = (live_lo / kPTile) * kPTile;
+        L.rt_rows = round_up(live_hi + 1, kPTile) - L.rt_lo;
         P.flags.resize(L.flag_off + (size_t)L.rt_rows, 0);
         P.live_owner.resize(L.flag_off + (size_t)L.rt_rows, 0);
         P.live_lrow.resize(L.flag_off + (size_t)L.rt_rows, 0);
@@ -632,16 +633,17 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         int8_t *lown = P.live_owner.data() + L.flag_off;
         int32_t *llrow = P.live_lrow.data() + L.flag_off;
         const int32_t rt_lo = L.rt_lo, rt_rows = L.rt_rows;
-        int32_t carried = 0;
+        int32_t carried = 0, lo = INT_MAX, hi = -1;
         for (const LiveRec &rec : live) {
             const bool stays = rec.last > t;      // read for the last time in step `last`
             const int32_t r = rec.slot - rt_lo;
             fl[r] = (uint8_t)(kFlagLive | (stays ? kFlagCarried : 0));
             lown[r] = (int8_t)rec.owner;
             llrow[r] = rec.lrow;
-            if (stays) { next_live.push_back(rec); carried++; }
+            if (stays) { next_live.push_back(rec); carried++; lo = std::min(lo, rec.slot); hi = std::max(hi, rec.slot); }
             else if (world > 1) freed_rows[(size_t)rec.owner].push_back(rec.lrow);
         }
+        live_lo = lo; live_hi = hi;
         L.carried = carried;
         for (int32_t r = 0; r < rt_rows; r++)          // evicted slots in ascending order -> freed lines, ascending
             if (fl[r] == kFlagLive) evicted.push_back(rt_lo + r);
