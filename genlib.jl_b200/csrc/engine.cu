@@ -1370,7 +1370,7 @@ int genlib_phi_multi(int32_t n, const int32_t *father, const int32_t *mother, in
     auto make_plan = [&](PlanStream *stream) {
         try {
             adopt_retired_storage(plan->p);
-            plan_rc = build_plan(n, father, mother, nullptr, n_pro, proband, n_dev, GENLIB_SCHEDULE_PHI, plan->p, plan_err, stream);
+            plan_rc = build_plan(n, father, mother, nullptr, n_pro, proband, n_dev, GENLIB_SCHEDULE_PHI, plan->p, plan_err, stream, /*planners=*/1);
         } catch (const std::bad_alloc &) {
             plan_rc = GENLIB_ENOMEM; plan_err = "out of host memory while planning";
             if (stream) { stream->status.store(plan_rc); stream->stage.store(2); stream->wake(); }

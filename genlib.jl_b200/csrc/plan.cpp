@@ -174,14 +174,14 @@ void release_plan_cache() {
 
 static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const int32_t *mother, const int64_t *ids,
                            int32_t n_pro, const int32_t *proband, int32_t world, int schedule, Plan &P, std::string &err,
-                           PlanStream *ps);
+                           PlanStream *ps, int planners);
 
 int build_plan(int32_t n, const int32_t *father, const int32_t *mother, const int64_t *ids, int32_t n_pro,
-               const int32_t *proband, int32_t world, int schedule, Plan &P, std::string &err, PlanStream *ps) {
+               const int32_t *proband, int32_t world, int schedule, Plan &P, std::string &err, PlanStream *ps, int planners) {
     int rc;
     try {
         std::unique_ptr<Scratch> W = take_scratch();
-        rc = build_plan_with(*W, n, father, mother, ids, n_pro, proband, world, schedule, P, err, ps);
+        rc = build_plan_with(*W, n, father, mother, ids, n_pro, proband, world, schedule, P, err, ps, planners);
         give_scratch(std::move(W));
     } catch (const std::bad_alloc &) {
         if (!ps) throw;
@@ -197,7 +197,7 @@ int build_plan(int32_t n, const int32_t *father, const int32_t *mother, const in
 
 static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const int32_t *mother, const int64_t *ids,
                            int32_t n_pro, const int32_t *proband, int32_t world, int schedule, Plan &P, std::string &err,
-                           PlanStream *ps) {
+                           PlanStream *ps, int planners) {
     const bool timing = std::getenv("GENLIB_PLAN_TIMING") != nullptr;     // debugging aid: phase times on stderr
     auto t_last = std::chrono::steady_clock::now();
 #define PLAN_T(name) do { if (timing) { auto t_now = std::chrono::steady_clock::now(); std::fprintf(stderr, "[plan] %-12s %.2f ms\n", name, std::chrono::duration<double, std::milli>(t_now - t_last).count()); t_last = t_now; } } while (0)
@@ -256,7 +256,7 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
     const char *threads_env = std::getenv("GENLIB_PLAN_THREADS");   // (forces helpers on small plans too: the tests)
     if (!by_seq) {
         const int hw = (int)std::thread::hardware_concurrency();
-        kC = std::max(1, std::min(threads_env ? std::atoi(threads_env) : (n >= 400000 ? std::min(3, hw / world) : 1), 16));
+        kC = std::max(1, std::min(threads_env ? std::atoi(threads_env) : (n >= 400000 ? std::min(3, hw / std::max(planners > 0 ? planners : world, 1)) : 1), 16));
     }
     const int32_t chunk = n / kC + 1;                            // range c = [c * chunk, (c + 1) * chunk)
     std::vector<int32_t> &hist = W.hist; hist.clear();
@@ -543,7 +543,7 @@ static int build_plan_with(Scratch &W, int32_t n, const int32_t *father, const i
         // couples ahead (with two threads the helper does both); small plans are not worth the threads.
         // GENLIB_PLAN_THREADS overrides (also for small plans: the tests run those with helpers too)
         const int hw = (int)std::thread::hardware_concurrency();
-        n_threads = threads_env ? std::atoi(threads_env) : (M >= 200000 ? std::min(3, hw / world) : 1);
+        n_threads = threads_env ? std::atoi(threads_env) : (M >= 200000 ? std::min(3, hw / std::max(planners > 0 ? planners : world, 1)) : 1);
         n_threads = std::max(1, std::min(n_threads, 16));
     }
     if (W.tables.size() < (size_t)n_threads) W.tables.resize((size_t)n_threads);

@@ -150,8 +150,11 @@ int set_error(int code, const std::string &msg);
 // `ids` (nullable, by rank) orders the founders in sparse_phi's queue (founder() sorts by ID,
 // identify.jl:15-19); without it they are taken in rank order.
 // With `stream` the plan is published layer by layer (see PlanStream); stage 2 is always reached.
+// `planners`: how many planners share this host's cores while this one runs -- `world` when every rank is a process
+// of its own that plans for itself (0: assume that), 1 when one process plans for all its devices; the planner
+// takes up to three threads out of cores / planners (GENLIB_PLAN_THREADS overrides).
 int build_plan(int32_t n, const int32_t *father, const int32_t *mother, const int64_t *ids, int32_t n_pro,
                const int32_t *proband, int32_t world, int schedule, Plan &plan, std::string &err,
-               PlanStream *stream = nullptr);
+               PlanStream *stream = nullptr, int planners = 0);
 
 }  // namespace genlib
